@@ -1,0 +1,167 @@
+/*
+ * mixmogam_b200 -- C ABI of the B200-native EMMAX hot path.
+ *
+ * The reference (bvilhjal/mixmogam) is pure Python and exposes no FFI; its hot
+ * path sits behind the Python functions listed below.  This header is the
+ * boundary the drop-in Python modules (mixmogam_b200/kinship.py,
+ * linear_models.py, hdf5_data.py) bind through ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.  Each entry point cites the
+ * reference lines it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, negative = error class;
+ *     the message is available through mmg_last_error().  No C++ exception
+ *     crosses the ABI.
+ *   - host pointers are borrowed for the duration of the call only; outputs are
+ *     pre-allocated by the caller.  Matrices are row-major (C order).
+ *   - device state lives in an opaque mmg_ctx (one per GPU).  Calls on one ctx
+ *     are serialised by the caller; different ctxs may be driven from different
+ *     threads.
+ *   - there is NO CPU fallback: without a CUDA device mmg_create fails.
+ */
+#ifndef MIXMOGAM_B200_H
+#define MIXMOGAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mmg_ctx mmg_ctx;
+typedef int64_t mmg_mat;          /* handle of a device-resident FP64 matrix */
+
+enum {
+    MMG_OK = 0,
+    MMG_EBADARG = -1,             /* bad argument / shape / state            */
+    MMG_ECUDA = -2,               /* CUDA runtime or driver error            */
+    MMG_ENCCL = -3,               /* reserved (collectives run through torch.distributed) */
+    MMG_ECUSOLVER = -4,
+    MMG_EOOM = -5,                /* device or pinned-host allocation failed */
+    MMG_ECUBLAS = -6,
+    MMG_EVALUE = -7               /* input values outside the supported domain (e.g. genotype not in {0,1,2}) */
+};
+
+/* genotype codings of kinship.calc_ibs_kinship (kinship.py:14-56) */
+enum { MMG_CODING_BINARY = 0, MMG_CODING_DIPLOID = 1 };
+/* kernel implementations */
+enum { MMG_IMPL_AUTO = 0, MMG_IMPL_TCGEN05 = 1, MMG_IMPL_SIMT = 2, MMG_IMPL_DMMA = 3 };
+
+/* ---- context ---------------------------------------------------------------- */
+int mmg_create(int device, mmg_ctx** out);
+int mmg_destroy(mmg_ctx* ctx);
+const char* mmg_last_error(mmg_ctx* ctx);            /* ctx may be NULL: last creation error */
+int mmg_device_info(mmg_ctx* ctx, char* name64, int* sm_count, int* cc_major, int* cc_minor,
+                    int64_t* free_bytes, int64_t* total_bytes);
+int mmg_sync(mmg_ctx* ctx);
+/* number of kernels of THIS library launched on ctx since creation (bench.py gpu_launches) */
+int64_t mmg_launch_count(mmg_ctx* ctx);
+/* named stage timers in seconds, CUDA-event based, accumulated since the last reset.
+ * names: "h2d","pack","gram","finalize","ibd","syevd","reml","scan_prep","scan","d2h" */
+int mmg_timer_get(mmg_ctx* ctx, const char* name, double* seconds, int64_t* calls);
+int mmg_timer_reset(mmg_ctx* ctx);
+/* duration (ms) of the most recent launch of the dominant kernels, measured with CUDA
+ * events on the launching stream: which = "gram" | "scan" */
+int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms);
+
+/* pinned host memory for callers that want full-rate PCIe copies */
+int mmg_host_alloc(void** ptr, int64_t bytes);
+int mmg_host_free(void* ptr);
+
+/* ---- device FP64 matrices (plumbing for the n x n objects of linear_models.py) -- */
+int mmg_mat_create(mmg_ctx* ctx, int64_t rows, int64_t cols, mmg_mat* out);   /* zero-filled */
+int mmg_mat_free(mmg_ctx* ctx, mmg_mat m);
+int mmg_mat_shape(mmg_ctx* ctx, mmg_mat m, int64_t* rows, int64_t* cols);
+int mmg_mat_upload(mmg_ctx* ctx, mmg_mat m, const double* host, int64_t ld_host);
+int mmg_mat_download(mmg_ctx* ctx, mmg_mat m, double* host, int64_t ld_host);
+int mmg_mat_device_ptr(mmg_ctx* ctx, mmg_mat m, void** dptr, int64_t* ld);
+int mmg_mat_copy(mmg_ctx* ctx, mmg_mat dst, mmg_mat src);
+/* C = alpha * op(A) * op(B) + beta * C   (cuBLAS dgemm; a plain library GEMM, outside the hot path) */
+int mmg_mat_gemm(mmg_ctx* ctx, int trans_a, int trans_b, double alpha, mmg_mat A, mmg_mat B,
+                 double beta, mmg_mat C);
+int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat A, const double* d_host);         /* A[i,:] *= d[i] */
+int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat A, double alpha);                   /* A += alpha*I   */
+/* kinship.scale_k (kinship.py:94-100): c = tr(K) - sum(K)/n ; K *= (n-1)/c ; returns the scalar */
+int mmg_mat_scale_k(mmg_ctx* ctx, mmg_mat K, double* scalar);
+/* linalg.eigh (linear_models.py:594,613) through cuSOLVER syevd, FP64.  A is overwritten by the
+ * eigenvectors stored as ROWS (the reference's `evecs.T`, :596,:615), eigenvalues ascending in w_host. */
+int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat A, double* w_host, double* seconds);
+
+/* ---- genotypes ------------------------------------------------------------------ */
+/* snps: SNP-major int8 [m x n], row stride ld (the reference's `snps` list / 2-D array,
+ * kinship.py:21-23, linear_models.py:1317).  Replaces the resident genotype block. */
+int mmg_snps_upload(mmg_ctx* ctx, const int8_t* snps, int64_t m, int64_t n, int64_t ld);
+/* list-of-rows form: rows[s] points at n contiguous int8 */
+int mmg_snps_upload_rows(mmg_ctx* ctx, const int8_t* const* rows, int64_t m, int64_t n);
+/* reserve an (m x n) resident block, then fill row ranges (streamed / chunked uploads) */
+int mmg_snps_reserve(mmg_ctx* ctx, int64_t m, int64_t n);
+int mmg_snps_write(mmg_ctx* ctx, int64_t row0, const int8_t* snps, int64_t rows, int64_t ld);
+int mmg_snps_free(mmg_ctx* ctx);
+int mmg_snps_shape(mmg_ctx* ctx, int64_t* m, int64_t* n);
+int mmg_snps_device_ptr(mmg_ctx* ctx, void** dptr, int64_t* pitch);
+/* per-SNP sums over individuals (int64) and sums of squares, e.g. for MAF filters (hdf5_data.py:91-96) */
+int mmg_snps_row_sums(mmg_ctx* ctx, int64_t* sums_host, int64_t* sumsq_host);
+
+/* ---- stage 1: kinship --------------------------------------------------------------- */
+/* Integer Gram of the resident genotype rows [snp_begin, snp_begin+snp_count):
+ *   binary  (kinship.py:43-44): G += S S', S = 2x-1 (int8), K-dim = snp_count
+ *   diploid (kinship.py:33-41): G += T T', T = [x>=1 | x>=2] thermometer planes, K-dim = 2*snp_count
+ * accumulated into the ctx's int32 n x n Gram (bit-exact, order independent).  reset!=0 zeroes it first. */
+int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset);
+/* device pointer of the int32 Gram (n x n, row stride ld elements) for an NCCL all-reduce between ranks */
+int mmg_kinship_gram_ptr(mmg_ctx* ctx, void** dptr, int64_t* n, int64_t* ld);
+int mmg_kinship_gram_download(mmg_ctx* ctx, int32_t* G_host);
+/* kinship.py:50-55: binary  K = G/(2 m) + 0.5 ; diploid K = f64(f32(m - L1/2)/f32(m)) + I with
+ * L1 = G_ii + G_jj - 2 G_ij and a zero diagonal count; then scale_k if scaled.  m_total = SNPs in G. */
+int mmg_kinship_finalize_f64(mmg_ctx* ctx, int coding, int64_t m_total, int scaled, mmg_mat K_out,
+                             double* scale_scalar);
+/* kinship.calc_ibd_kinship (kinship.py:59-75) and the hdf5 variants (hdf5_data.py:30-62,84-115):
+ * K += sum_s z_s z_s' over resident rows [snp_begin, +snp_count) with z = (x-mean)/std (ddof 0),
+ * FP64 accumulation.  snp_mask (nullable, one byte per row in range) selects rows (MAF filter).
+ * Returns the number of rows used.  Fails with MMG_EVALUE on a monomorphic row (kinship.py:67). */
+int mmg_kinship_ibd_accumulate_f64(mmg_ctx* ctx, mmg_mat K_acc, int64_t snp_begin, int64_t snp_count,
+                                   const uint8_t* snp_mask, int64_t* used);
+
+/* ---- stage 2: REML ------------------------------------------------------------------- */
+/* LinearMixedModel.get_estimates, REML branch (linear_models.py:789-891): the delta grid
+ * (lls, dlls over deltas[g]) for T phenotypes, the sign-change bracket, the secant refinement that
+ * scipy.optimize.newton performs without fprime (tol=esp, maxiter=100), the bracket validation and
+ * the grid-maximum fallback.  sq_etas is [T x p] (one phenotype per row).
+ * flags[t]: bit0 = a zero interval was found, bit1 = secant converged, bit2 = refined delta accepted. */
+int mmg_reml_f64(mmg_ctx* ctx, const double* eig_vals, const double* sq_etas, int64_t p, int64_t T,
+                 const double* deltas, int64_t g, double esp,
+                 double* lls, double* dlls, double* opt_delta, double* opt_ll, int32_t* flags);
+
+/* ---- stage 3: SNP scan ------------------------------------------------------------------ */
+/* _emmax_f_test_ hot loops (linear_models.py:1315-1349) over the resident genotype rows
+ * [snp_begin, +snp_count):
+ *     x~ = R x            (R = M' = (I - QQ')H, [n_out x n]; the rotation GEMM of :1318)
+ *     xx = x~.x~ ; xy[v] = x~.V[v]      (V: nv rotated-space vectors [nv x n_out]; V[0] = residual y~)
+ *     rss = h0_rss - xy[0]^2/xx (kept at h0_rss when xx <= 0, the `if rss:` of :1329)
+ *     f = n_p * r2/(1-r2), r2 = xy[0]^2/(xx*h0_rss) ; p = F.sf(f, 1, n_p)   (:1345-1349)
+ * impl: MMG_IMPL_DMMA  = FP64 tensor-core (mma.sync m8n8k4 f64) rotation fused with the reductions;
+ *       MMG_IMPL_TCGEN05 = x'(R'R)x on int8 tcgen05 tensor cores with exact integer slices of R'R.
+ * Outputs (host, length snp_count, any may be NULL): ps, f_stats, rss, var_perc, xx;
+ * dots: [snp_count x nv]. */
+int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double h0_rss, double n_p,
+                       int impl, int64_t snp_begin, int64_t snp_count,
+                       double* ps, double* f_stats, double* rss, double* var_perc,
+                       double* xx, double* dots);
+/* _emmax_permutations_ inner loop (linear_models.py:1157-1164): with centred SNPs x_c = x - mean(x),
+ * x~ = R x_c, for each permuted phenotype column W[:,p] (already rotated back: W = R' Ys, [n x P]):
+ *     ratio[p] = max over SNPs of (x_c.W[:,p])^2 / (x~.x~)
+ * so that min_rss[p] = |Ys_p|^2 - ratio[p].  ratio_inout is max-accumulated (initialise to 0). */
+int mmg_emmax_perm_scan_f64(mmg_ctx* ctx, mmg_mat R, mmg_mat W, int centre, int impl,
+                            int64_t snp_begin, int64_t snp_count, double* ratio_inout);
+/* scipy.stats.f.sf(f, dfn, dfd) (linear_models.py:1349,1172) on the device, FP64 */
+int mmg_f_sf_f64(mmg_ctx* ctx, const double* f, int64_t count, double dfn, double dfd, double* out);
+
+/* ---- diagnostics ---------------------------------------------------------------------------- */
+/* raw pipe rates measured with CUDA events: which = "dmma" (TFLOP/s), "dfma" (TFLOP/s),
+ * "imma_tcgen05" (TOP/s, smem-resident operands, no loads), "copy" (GB/s) */
+int mmg_microbench(mmg_ctx* ctx, const char* which, double* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXMOGAM_B200_H */

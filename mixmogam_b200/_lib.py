@@ -1,0 +1,517 @@
+"""
+ctypes binding of libmixmogam_b200.so (include/mixmogam_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or creating a
+context without a B200, raises.  Build the library with `python -c "import __graft_entry__ as g; g.build()"`
+(or `make -C mixmogam_b200/csrc`).
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmixmogam_b200.so')
+
+CODING_BINARY, CODING_DIPLOID = 0, 1
+IMPL_AUTO, IMPL_TCGEN05, IMPL_SIMT, IMPL_DMMA = 0, 1, 2, 3
+_IMPL_NAMES = {'auto': IMPL_AUTO, 'tcgen05': IMPL_TCGEN05, 'simt': IMPL_SIMT, 'dmma': IMPL_DMMA}
+
+ERROR_NAMES = {0: 'MMG_OK', -1: 'MMG_EBADARG', -2: 'MMG_ECUDA', -3: 'MMG_ENCCL', -4: 'MMG_ECUSOLVER',
+               -5: 'MMG_EOOM', -6: 'MMG_ECUBLAS', -7: 'MMG_EVALUE'}
+
+
+class MmgError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, '%s: %s' % (ERROR_NAMES.get(code, code), msg))
+        self.code = code
+
+
+# every symbol the header declares: name -> (restype, argtypes)
+_c_ctx = C.c_void_p
+_i64 = C.c_int64
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+SIGNATURES = {
+    'mmg_create': (C.c_int, [C.c_int, C.POINTER(_c_ctx)]),
+    'mmg_destroy': (C.c_int, [_c_ctx]),
+    'mmg_last_error': (C.c_char_p, [_c_ctx]),
+    'mmg_device_info': (C.c_int, [_c_ctx, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(_i64), C.POINTER(_i64)]),
+    'mmg_sync': (C.c_int, [_c_ctx]),
+    'mmg_launch_count': (_i64, [_c_ctx]),
+    'mmg_timer_get': (C.c_int, [_c_ctx, C.c_char_p, _dp, C.POINTER(_i64)]),
+    'mmg_timer_reset': (C.c_int, [_c_ctx]),
+    'mmg_last_kernel_ms': (C.c_int, [_c_ctx, C.c_char_p, _dp]),
+    'mmg_host_alloc': (C.c_int, [C.POINTER(_vp), _i64]),
+    'mmg_host_free': (C.c_int, [_vp]),
+    'mmg_mat_create': (C.c_int, [_c_ctx, _i64, _i64, C.POINTER(_i64)]),
+    'mmg_mat_free': (C.c_int, [_c_ctx, _i64]),
+    'mmg_mat_shape': (C.c_int, [_c_ctx, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    'mmg_mat_upload': (C.c_int, [_c_ctx, _i64, _vp, _i64]),
+    'mmg_mat_download': (C.c_int, [_c_ctx, _i64, _vp, _i64]),
+    'mmg_mat_device_ptr': (C.c_int, [_c_ctx, _i64, C.POINTER(_vp), C.POINTER(_i64)]),
+    'mmg_mat_copy': (C.c_int, [_c_ctx, _i64, _i64]),
+    'mmg_mat_gemm': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_double, _i64, _i64, C.c_double, _i64]),
+    'mmg_mat_scale_rows': (C.c_int, [_c_ctx, _i64, _vp]),
+    'mmg_mat_add_diag': (C.c_int, [_c_ctx, _i64, C.c_double]),
+    'mmg_mat_scale_k': (C.c_int, [_c_ctx, _i64, _dp]),
+    'mmg_mat_syevd': (C.c_int, [_c_ctx, _i64, _vp, _dp]),
+    'mmg_snps_upload': (C.c_int, [_c_ctx, _vp, _i64, _i64, _i64]),
+    'mmg_snps_upload_rows': (C.c_int, [_c_ctx, _vp, _i64, _i64]),
+    'mmg_snps_reserve': (C.c_int, [_c_ctx, _i64, _i64]),
+    'mmg_snps_write': (C.c_int, [_c_ctx, _i64, _vp, _i64, _i64]),
+    'mmg_snps_free': (C.c_int, [_c_ctx]),
+    'mmg_snps_shape': (C.c_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64)]),
+    'mmg_snps_device_ptr': (C.c_int, [_c_ctx, C.POINTER(_vp), C.POINTER(_i64)]),
+    'mmg_snps_row_sums': (C.c_int, [_c_ctx, _vp, _vp]),
+    'mmg_kinship_gram_i8': (C.c_int, [_c_ctx, C.c_int, C.c_int, _i64, _i64, C.c_int]),
+    'mmg_kinship_gram_ptr': (C.c_int, [_c_ctx, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
+    'mmg_kinship_gram_download': (C.c_int, [_c_ctx, _vp]),
+    'mmg_kinship_finalize_f64': (C.c_int, [_c_ctx, C.c_int, _i64, C.c_int, _i64, _dp]),
+    'mmg_kinship_ibd_accumulate_f64': (C.c_int, [_c_ctx, _i64, _i64, _i64, _vp, C.POINTER(_i64)]),
+    'mmg_reml_f64': (C.c_int, [_c_ctx, _vp, _vp, _i64, _i64, _vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_emmax_scan_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _i64, _i64,
+                                     _vp, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_emmax_perm_scan_f64': (C.c_int, [_c_ctx, _i64, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
+    'mmg_f_sf_f64': (C.c_int, [_c_ctx, _vp, _i64, C.c_double, C.c_double, _vp]),
+    'mmg_microbench': (C.c_int, [_c_ctx, C.c_char_p, _dp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the shared library and attach the prototypes (no GPU needed for this)."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError('mixmogam_b200: %s is missing -- build it first (__graft_entry__.build()); '
+                                  'there is no CPU fallback' % LIB_PATH)
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def impl_id(impl):
+    if isinstance(impl, str):
+        return _IMPL_NAMES[impl.lower()]
+    return int(impl)
+
+
+class DeviceMatrix(object):
+    """FP64 row-major matrix resident in HBM (mmg_mat handle)."""
+
+    def __init__(self, ctx, rows, cols):
+        self.ctx = ctx
+        self.shape = (int(rows), int(cols))
+        h = _i64(0)
+        ctx._ck(ctx.lib.mmg_mat_create(ctx.h, rows, cols, C.byref(h)))
+        self.handle = h.value
+
+    @classmethod
+    def from_host(cls, ctx, a):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        m = cls(ctx, a.shape[0], a.shape[1])
+        m.upload(a)
+        return m
+
+    def upload(self, a):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        assert a.shape == self.shape, (a.shape, self.shape)
+        self.ctx._ck(self.ctx.lib.mmg_mat_upload(self.ctx.h, self.handle, _ptr(a), a.shape[1]))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        self.ctx._ck(self.ctx.lib.mmg_mat_download(self.ctx.h, self.handle, _ptr(out), out.shape[1]))
+        return out
+
+    def copy(self):
+        m = DeviceMatrix(self.ctx, *self.shape)
+        self.ctx._ck(self.ctx.lib.mmg_mat_copy(self.ctx.h, m.handle, self.handle))
+        return m
+
+    def device_ptr(self):
+        p, ld = C.c_void_p(0), _i64(0)
+        self.ctx._ck(self.ctx.lib.mmg_mat_device_ptr(self.ctx.h, self.handle, C.byref(p), C.byref(ld)))
+        return p.value, ld.value
+
+    def free(self):
+        if self.handle and self.ctx.h:
+            self.ctx.lib.mmg_mat_free(self.ctx.h, self.handle)
+        self.handle = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class LazyHostArray(object):
+    """A device matrix that turns into a numpy array on demand (np.asarray(x), x[...], x.shape ...).
+    Returned wherever the reference returns an n x n matrix the caller rarely touches
+    (H_sqrt_inv, eigenvectors, the scaled kinship), so the 0.8 GB download only happens when asked for."""
+
+    def __init__(self, dev, rows=None):
+        self.dev = dev
+        self._rows = rows      # optional row slice (start, stop) applied on materialisation
+        self._host = None
+
+    @property
+    def shape(self):
+        if self._rows is None:
+            return self.dev.shape
+        return (self._rows[1] - self._rows[0], self.dev.shape[1])
+
+    def host(self):
+        if self._host is None:
+            a = self.dev.download()
+            if self._rows is not None:
+                a = a[self._rows[0]:self._rows[1]]
+            self._host = a
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.host()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, k):
+        return self.host()[k]
+
+    def __len__(self):
+        return self.shape[0]
+
+    @property
+    def T(self):
+        return self.host().T
+
+    def __matmul__(self, o):
+        return self.host() @ np.asarray(o)
+
+    def __rmatmul__(self, o):
+        return np.asarray(o) @ self.host()
+
+
+class Context(object):
+    """One per GPU (mmg_ctx).  Holds the resident genotype block and the device matrices."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = None
+        h = _c_ctx(0)
+        rc = self.lib.mmg_create(int(device), C.byref(h))
+        if rc != 0:
+            raise MmgError(rc, self.lib.mmg_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+        self._snps_key = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MmgError(rc, self.lib.mmg_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.mmg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- info / timers ----
+    def device_info(self):
+        name = C.create_string_buffer(64)
+        sm, maj, mnr = C.c_int(0), C.c_int(0), C.c_int(0)
+        fr, tot = _i64(0), _i64(0)
+        self._ck(self.lib.mmg_device_info(self.h, name, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(fr), C.byref(tot)))
+        return {'name': name.value.decode(), 'sm_count': sm.value, 'cc': (maj.value, mnr.value),
+                'free_bytes': fr.value, 'total_bytes': tot.value}
+
+    def launch_count(self):
+        return int(self.lib.mmg_launch_count(self.h))
+
+    def timer(self, name):
+        s, c = C.c_double(0), _i64(0)
+        self._ck(self.lib.mmg_timer_get(self.h, name.encode(), C.byref(s), C.byref(c)))
+        return s.value, c.value
+
+    def timers(self):
+        return {k: self.timer(k)[0] for k in ('h2d', 'pack', 'gram', 'finalize', 'ibd', 'syevd', 'reml', 'scan', 'd2h')}
+
+    def timer_reset(self):
+        self._ck(self.lib.mmg_timer_reset(self.h))
+
+    def last_kernel_ms(self, which):
+        v = C.c_double(0)
+        self._ck(self.lib.mmg_last_kernel_ms(self.h, which.encode(), C.byref(v)))
+        return v.value
+
+    def microbench(self, which):
+        v = C.c_double(0)
+        self._ck(self.lib.mmg_microbench(self.h, which.encode(), C.byref(v)))
+        return v.value
+
+    def sync(self):
+        self._ck(self.lib.mmg_sync(self.h))
+
+    # ---- genotypes ----
+    @staticmethod
+    def _fingerprint(a):
+        flat = a.reshape(-1)
+        step = max(1, flat.size // 4096)
+        return hash(flat[::step].tobytes())
+
+    def invalidate_snps(self):
+        self._snps_key = None
+
+    def ensure_snps(self, snps):
+        """Make `snps` (list of m int8 rows or an (m, n) array, SNP-major; kinship.py:21-23) the resident
+        genotype block.  Re-uploads unless the same buffer (address, shape, sampled fingerprint) is
+        already resident.  Returns (m, n)."""
+        if isinstance(snps, np.ndarray) and snps.ndim == 2:
+            a = snps
+            if a.dtype != np.int8:
+                a = _as_int8(a)
+            if not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a)
+            key = ('arr', a.ctypes.data, a.shape, self._fingerprint(a))
+            if key != self._snps_key:
+                self._ck(self.lib.mmg_snps_upload(self.h, _ptr(a), a.shape[0], a.shape[1], a.shape[1]))
+                self._snps_key = key
+            return a.shape
+        m = len(snps)
+        if m == 0:
+            raise ValueError('no SNPs')
+        n = len(snps[0])
+        rows_ok = all(isinstance(r, np.ndarray) and r.dtype == np.int8 and r.ndim == 1 and r.flags.c_contiguous
+                      and r.shape[0] == n for r in snps)
+        if not rows_ok:
+            return self.ensure_snps(_as_int8(np.asarray(snps)))
+        ptrs = np.fromiter((r.ctypes.data for r in snps), dtype=np.uint64, count=m)
+        step = max(1, m // 64)
+        key = ('rows', m, n, hash(ptrs.tobytes()), hash(b''.join(snps[i].tobytes() for i in range(0, m, step))))
+        if key != self._snps_key:
+            self._ck(self.lib.mmg_snps_upload_rows(self.h, _ptr(ptrs), m, n))
+            self._snps_key = key
+        return (m, n)
+
+    def snps_shape(self):
+        m, n = _i64(0), _i64(0)
+        self._ck(self.lib.mmg_snps_shape(self.h, C.byref(m), C.byref(n)))
+        return m.value, n.value
+
+    def snps_row_sums(self, with_sumsq=False):
+        m, n = self.snps_shape()
+        s = np.empty(m, dtype=np.int64)
+        q = np.empty(m, dtype=np.int64) if with_sumsq else None
+        self._ck(self.lib.mmg_snps_row_sums(self.h, _ptr(s), _ptr(q)))
+        return (s, q) if with_sumsq else s
+
+    # ---- matrices ----
+    def matrix(self, rows, cols):
+        return DeviceMatrix(self, rows, cols)
+
+    def to_device(self, a):
+        if isinstance(a, LazyHostArray):
+            if a._rows is None:
+                return a.dev
+            a = a.host()
+        if isinstance(a, DeviceMatrix):
+            return a
+        return DeviceMatrix.from_host(self, a)
+
+    def gemm(self, A, B, C_out=None, ta=False, tb=False, alpha=1.0, beta=0.0):
+        m = A.shape[1] if ta else A.shape[0]
+        n = B.shape[0] if tb else B.shape[1]
+        if C_out is None:
+            C_out = DeviceMatrix(self, m, n)
+        self._ck(self.lib.mmg_mat_gemm(self.h, int(ta), int(tb), alpha, A.handle, B.handle, beta, C_out.handle))
+        return C_out
+
+    def scale_rows(self, A, d):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        assert d.shape[0] == A.shape[0]
+        self._ck(self.lib.mmg_mat_scale_rows(self.h, A.handle, _ptr(d)))
+
+    def add_diag(self, A, alpha):
+        self._ck(self.lib.mmg_mat_add_diag(self.h, A.handle, float(alpha)))
+
+    def scale_k(self, K):
+        s = C.c_double(0)
+        self._ck(self.lib.mmg_mat_scale_k(self.h, K.handle, C.byref(s)))
+        return s.value
+
+    def syevd(self, A):
+        """In place: A <- eigenvectors as rows; returns ascending eigenvalues."""
+        w = np.empty(A.shape[0], dtype=np.float64)
+        self._ck(self.lib.mmg_mat_syevd(self.h, A.handle, _ptr(w), None))
+        return w
+
+    # ---- stage 1 ----
+    def kinship_gram(self, coding, impl=IMPL_AUTO, snp_begin=0, snp_count=None, reset=True):
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        self._ck(self.lib.mmg_kinship_gram_i8(self.h, coding, impl_id(impl), snp_begin, snp_count, int(bool(reset))))
+
+    def kinship_gram_download(self):
+        m, n = self.snps_shape()
+        g = np.empty((n, n), dtype=np.int32)
+        self._ck(self.lib.mmg_kinship_gram_download(self.h, _ptr(g)))
+        return g
+
+    def kinship_gram_ptr(self):
+        p, n, ld = C.c_void_p(0), _i64(0), _i64(0)
+        self._ck(self.lib.mmg_kinship_gram_ptr(self.h, C.byref(p), C.byref(n), C.byref(ld)))
+        return p.value, n.value, ld.value
+
+    def kinship_finalize(self, coding, m_total, scaled, K=None):
+        m, n = self.snps_shape()
+        if K is None:
+            K = DeviceMatrix(self, n, n)
+        s = C.c_double(1.0)
+        self._ck(self.lib.mmg_kinship_finalize_f64(self.h, coding, int(m_total), int(bool(scaled)), K.handle, C.byref(s)))
+        return K, s.value
+
+    def kinship_ibd_accumulate(self, K, snp_begin, snp_count, mask=None):
+        used = _i64(0)
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            assert mask.shape[0] == snp_count
+        self._ck(self.lib.mmg_kinship_ibd_accumulate_f64(self.h, K.handle, snp_begin, snp_count, _ptr(mask), C.byref(used)))
+        return used.value
+
+    # ---- stage 2 ----
+    def reml(self, eig_vals, sq_etas, deltas, esp):
+        eig_vals = np.ascontiguousarray(eig_vals, dtype=np.float64)
+        sq_etas = np.ascontiguousarray(sq_etas, dtype=np.float64)
+        if sq_etas.ndim == 1:
+            sq_etas = sq_etas.reshape(1, -1)
+        T, p = sq_etas.shape
+        assert eig_vals.shape[0] == p
+        deltas = np.ascontiguousarray(deltas, dtype=np.float64)
+        g = deltas.shape[0]
+        lls = np.empty((T, g))
+        dlls = np.empty((T, g))
+        od = np.empty(T)
+        ol = np.empty(T)
+        fl = np.empty(T, dtype=np.int32)
+        self._ck(self.lib.mmg_reml_f64(self.h, _ptr(eig_vals), _ptr(sq_etas), p, T, _ptr(deltas), g, float(esp),
+                                       _ptr(lls), _ptr(dlls), _ptr(od), _ptr(ol), _ptr(fl)))
+        return {'lls': lls, 'dlls': dlls, 'delta': od, 'll': ol, 'flags': fl}
+
+    # ---- stage 3 ----
+    def emmax_scan(self, R, V, h0_rss, n_p, impl=IMPL_AUTO, snp_begin=0, snp_count=None, want_dots=False,
+                   want_stats=True):
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        V = np.ascontiguousarray(np.asarray(V, dtype=np.float64))
+        if V.ndim == 1:
+            V = V.reshape(1, -1)
+        nv = V.shape[0]
+        assert V.shape[1] == R.shape[0], (V.shape, R.shape)
+        out = {}
+        if want_stats:
+            for k in ('ps', 'f_stats', 'rss', 'var_perc'):
+                out[k] = np.empty(snp_count, dtype=np.float64)
+        out['xx'] = np.empty(snp_count, dtype=np.float64)
+        if want_dots:
+            out['dots'] = np.empty((snp_count, nv), dtype=np.float64)
+        self._ck(self.lib.mmg_emmax_scan_f64(self.h, R.handle, _ptr(V), nv, float(h0_rss), float(n_p), impl_id(impl),
+                                             snp_begin, snp_count, _ptr(out.get('ps')), _ptr(out.get('f_stats')),
+                                             _ptr(out.get('rss')), _ptr(out.get('var_perc')), _ptr(out['xx']),
+                                             _ptr(out.get('dots'))))
+        return out
+
+    def emmax_perm_scan(self, R, Wt, ratio, centre=True, impl=IMPL_AUTO, snp_begin=0, snp_count=None):
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        assert ratio.dtype == np.float64 and ratio.shape[0] == Wt.shape[0]
+        self._ck(self.lib.mmg_emmax_perm_scan_f64(self.h, R.handle, Wt.handle, int(bool(centre)), impl_id(impl), snp_begin,
+                                                  snp_count, _ptr(ratio)))
+        return ratio
+
+    def f_sf(self, f, dfn, dfd):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        out = np.empty_like(f)
+        self._ck(self.lib.mmg_f_sf_f64(self.h, _ptr(f), f.size, float(dfn), float(dfd), _ptr(out)))
+        return out
+
+
+def _as_int8(a):
+    """Genotypes must be small integers for the tensor-core paths (the reference casts to int8 itself,
+    kinship.py:31)."""
+    a = np.asarray(a)
+    if a.dtype == np.int8:
+        return a
+    if a.dtype.kind in 'iub':
+        if a.size and (a.min() < -128 or a.max() > 127):
+            raise ValueError('genotype values outside the int8 range')
+        return a.astype(np.int8)
+    if a.dtype.kind == 'f':
+        r = np.rint(a)
+        if not np.array_equal(r, a):
+            raise TypeError('mixmogam_b200 scans integer genotype codes; got non-integral values '
+                            '(there is no CPU fallback for real-valued dosages)')
+        return _as_int8(r.astype(np.int64))
+    raise TypeError('unsupported genotype dtype %r' % a.dtype)
+
+
+_default_ctx = {}
+_default_lock = threading.Lock()
+
+
+def get_context(device=None):
+    """Process-wide context per device (LOCAL_RANK / MMG_DEVICE select the default device)."""
+    if device is None:
+        device = int(os.environ.get('MMG_DEVICE', os.environ.get('LOCAL_RANK', '0')))
+    with _default_lock:
+        ctx = _default_ctx.get(device)
+        if ctx is None or ctx.h is None:
+            ctx = Context(device)
+            _default_ctx[device] = ctx
+    return ctx
+
+
+def pinned_empty(shape, dtype=np.int8):
+    """numpy array backed by page-locked host memory (mmg_host_alloc) for full-rate PCIe copies."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p(0)
+    rc = lib.mmg_host_alloc(C.byref(p), nbytes)
+    if rc != 0:
+        raise MmgError(rc, lib.mmg_last_error(None).decode())
+    buf = (C.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _pinned_keepalive[arr.ctypes.data] = p.value
+    return arr
+
+
+_pinned_keepalive = {}
+
+
+def pinned_free(arr):
+    p = _pinned_keepalive.pop(arr.ctypes.data, None)
+    if p is not None:
+        load_library().mmg_host_free(C.c_void_p(p))

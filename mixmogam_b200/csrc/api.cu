@@ -1,0 +1,1097 @@
+// libmixmogam_b200: C ABI (include/mixmogam_b200.h) over the sm_100a kernels.
+// Host-side orchestration only; every numerical stage of the hot path runs in the kernels of
+// tc_gemm.cuh / scan_tc.cuh (tcgen05), scan_dmma.cuh (FP64 tensor cores), reml.cuh, kinship_kernels.cuh.
+// cuBLAS / cuSOLVER appear only for plain library work outside the hot path (dgemm plumbing, syevd).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "ctx.h"
+#include "fdist.cuh"
+#include "kinship_kernels.cuh"
+#include "reml.cuh"
+#include "scan_dmma.cuh"
+#include "scan_tc.cuh"
+#include "tc_gemm.cuh"
+
+namespace mmg {
+thread_local std::string g_create_error;
+
+// ---- driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda) -------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// uint8 [rows x kbytes] row-major, row stride `pitch` bytes; box = 128 bytes x box_rows; 128B swizzle
+static int make_tmap_u8(mmg_ctx* ctx, CUtensorMap* tm, const void* base, int64_t kbytes, int64_t rows, int64_t pitch,
+                        int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(ctx, MMG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, MMG_ECUDA, "cuTensorMapEncodeTiled failed: %d (kbytes=%lld rows=%lld pitch=%lld)",
+                                       (int)r, (long long)kbytes, (long long)rows, (long long)pitch);
+    return MMG_OK;
+}
+
+static int ensure_scratch(mmg_ctx* ctx, int64_t bytes) {
+    if (ctx->scratch_bytes >= bytes) return MMG_OK;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    MMG_CUDA(ctx, cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return MMG_OK;
+}
+
+static MmgMat* get_mat(mmg_ctx* ctx, mmg_mat h) {
+    auto it = ctx->mats.find(h);
+    return it == ctx->mats.end() ? nullptr : &it->second;
+}
+
+static int launch_check(mmg_ctx* ctx, const char* what) {
+    ctx->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return MMG_OK;
+}
+
+static double lbeta_host(double a, double b) {
+    return (double)(lgammal((long double)a) + lgammal((long double)b) - lgammal((long double)a + (long double)b));
+}
+
+}  // namespace mmg
+
+using namespace mmg;
+
+extern "C" {
+
+// ======================================================================================================
+// context
+// ======================================================================================================
+int mmg_create(int device, mmg_ctx** out) {
+    if (!out) return fail(nullptr, MMG_EBADARG, "mmg_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, MMG_ECUDA, "no CUDA device available (%s); mixmogam_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(nullptr, MMG_EBADARG, "device %d out of range [0,%d)", device, count);
+    MMG_CUDA(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MMG_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, MMG_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    mmg_ctx* ctx = new mmg_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreate(&ctx->kev0) != cudaSuccess || cudaEventCreate(&ctx->kev1) != cudaSuccess ||
+        cudaMalloc(&ctx->flag_d, sizeof(int)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, MMG_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS || cusolverDnCreate(&ctx->cusolver) != CUSOLVER_STATUS_SUCCESS) {
+        delete ctx;
+        return fail(nullptr, MMG_ECUBLAS, "cublas/cusolver handle creation failed");
+    }
+    cublasSetStream(ctx->cublas, ctx->stream);
+    cusolverDnSetStream(ctx->cusolver, ctx->stream);
+    cublasSetPointerMode(ctx->cublas, CUBLAS_POINTER_MODE_HOST);
+    // opt in to large dynamic shared memory once
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(scan_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
+    cudaFuncSetAttribute(scan_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
+    *out = ctx;
+    return MMG_OK;
+}
+
+int mmg_destroy(mmg_ctx* ctx) {
+    if (!ctx) return MMG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->mats) cudaFree(kv.second.d);
+    cudaFree(ctx->snps);
+    cudaFree(ctx->G);
+    cudaFree(ctx->pack);
+    cudaFree(ctx->tiles_d);
+    cudaFree(ctx->flag_d);
+    cudaFree(ctx->scratch);
+    if (ctx->cublas) cublasDestroy(ctx->cublas);
+    if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->kev0);
+    cudaEventDestroy(ctx->kev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MMG_OK;
+}
+
+const char* mmg_last_error(mmg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mmg_device_info(mmg_ctx* ctx, char* name64, int* sm_count, int* cc_major, int* cc_minor, int64_t* free_bytes,
+                    int64_t* total_bytes) {
+    MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    MMG_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    if (name64) { strncpy(name64, prop.name, 63); name64[63] = 0; }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    size_t f = 0, t = 0;
+    MMG_CUDA(ctx, cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return MMG_OK;
+}
+
+int mmg_sync(mmg_ctx* ctx) {
+    MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+int64_t mmg_launch_count(mmg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mmg_timer_get(mmg_ctx* ctx, const char* name, double* seconds, int64_t* calls) {
+    MMG_CHECK(ctx, ctx && name, "bad argument");
+    auto it = ctx->timers.find(name);
+    if (seconds) *seconds = it == ctx->timers.end() ? 0.0 : it->second.seconds;
+    if (calls) *calls = it == ctx->timers.end() ? 0 : it->second.calls;
+    return MMG_OK;
+}
+int mmg_timer_reset(mmg_ctx* ctx) {
+    MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    ctx->timers.clear();
+    return MMG_OK;
+}
+int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms) {
+    MMG_CHECK(ctx, ctx && which && ms, "bad argument");
+    if (!strcmp(which, "gram")) *ms = ctx->last_gram_ms;
+    else if (!strcmp(which, "scan")) *ms = ctx->last_scan_ms;
+    else return fail(ctx, MMG_EBADARG, "unknown kernel '%s'", which);
+    return MMG_OK;
+}
+
+int mmg_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(nullptr, MMG_EBADARG, "mmg_host_alloc: bad argument");
+    cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, MMG_EOOM, "cudaHostAlloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    return MMG_OK;
+}
+int mmg_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+    return MMG_OK;
+}
+
+// ======================================================================================================
+// device matrices
+// ======================================================================================================
+int mmg_mat_create(mmg_ctx* ctx, int64_t rows, int64_t cols, mmg_mat* out) {
+    MMG_CHECK(ctx, ctx && out && rows > 0 && cols > 0, "mmg_mat_create: bad shape %lld x %lld", (long long)rows, (long long)cols);
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MmgMat m;
+    m.rows = rows;
+    m.cols = cols;
+    MMG_CUDA(ctx, cudaMalloc(&m.d, (size_t)rows * cols * sizeof(double)));
+    MMG_CUDA(ctx, cudaMemsetAsync(m.d, 0, (size_t)rows * cols * sizeof(double), ctx->stream));
+    *out = ctx->next_mat++;
+    ctx->mats[*out] = m;
+    return MMG_OK;
+}
+int mmg_mat_free(mmg_ctx* ctx, mmg_mat h) {
+    MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    auto it = ctx->mats.find(h);
+    if (it == ctx->mats.end()) return MMG_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(it->second.d);
+    ctx->mats.erase(it);
+    return MMG_OK;
+}
+int mmg_mat_shape(mmg_ctx* ctx, mmg_mat h, int64_t* rows, int64_t* cols) {
+    MmgMat* m = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, m != nullptr, "unknown matrix handle %lld", (long long)h);
+    if (rows) *rows = m->rows;
+    if (cols) *cols = m->cols;
+    return MMG_OK;
+}
+int mmg_mat_upload(mmg_ctx* ctx, mmg_mat h, const double* host, int64_t ld_host) {
+    MmgMat* m = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, m && host && ld_host >= m->cols, "mmg_mat_upload: bad argument");
+    StageTimer tm(ctx, "h2d");
+    MMG_CUDA(ctx, cudaMemcpy2DAsync(m->d, m->cols * sizeof(double), host, ld_host * sizeof(double), m->cols * sizeof(double),
+                                    m->rows, cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+int mmg_mat_download(mmg_ctx* ctx, mmg_mat h, double* host, int64_t ld_host) {
+    MmgMat* m = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, m && host && ld_host >= m->cols, "mmg_mat_download: bad argument");
+    StageTimer tm(ctx, "d2h");
+    MMG_CUDA(ctx, cudaMemcpy2DAsync(host, ld_host * sizeof(double), m->d, m->cols * sizeof(double), m->cols * sizeof(double),
+                                    m->rows, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+int mmg_mat_device_ptr(mmg_ctx* ctx, mmg_mat h, void** dptr, int64_t* ld) {
+    MmgMat* m = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, m && dptr, "mmg_mat_device_ptr: bad argument");
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *dptr = m->d;
+    if (ld) *ld = m->cols;
+    return MMG_OK;
+}
+int mmg_mat_copy(mmg_ctx* ctx, mmg_mat dst, mmg_mat src) {
+    MmgMat *d = ctx ? get_mat(ctx, dst) : nullptr, *s = ctx ? get_mat(ctx, src) : nullptr;
+    MMG_CHECK(ctx, d && s && d->rows == s->rows && d->cols == s->cols, "mmg_mat_copy: shape mismatch");
+    MMG_CUDA(ctx, cudaMemcpyAsync(d->d, s->d, (size_t)d->rows * d->cols * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return MMG_OK;
+}
+int mmg_mat_gemm(mmg_ctx* ctx, int ta, int tb, double alpha, mmg_mat Ah, mmg_mat Bh, double beta, mmg_mat Ch) {
+    MmgMat *A = ctx ? get_mat(ctx, Ah) : nullptr, *B = ctx ? get_mat(ctx, Bh) : nullptr, *C = ctx ? get_mat(ctx, Ch) : nullptr;
+    MMG_CHECK(ctx, A && B && C, "mmg_mat_gemm: unknown handle");
+    const int64_t m = ta ? A->cols : A->rows, k = ta ? A->rows : A->cols;
+    const int64_t kb = tb ? B->cols : B->rows, n = tb ? B->rows : B->cols;
+    MMG_CHECK(ctx, k == kb && C->rows == m && C->cols == n, "mmg_mat_gemm: shape mismatch (%lldx%lld)*(%lldx%lld)->(%lldx%lld)",
+              (long long)m, (long long)k, (long long)kb, (long long)n, (long long)C->rows, (long long)C->cols);
+    MMG_CHECK(ctx, C != A && C != B, "mmg_mat_gemm: output aliases an input");
+    // row-major C = op(A) op(B)  <=>  column-major C' = op(B)' op(A)'
+    MMG_CUBLAS(ctx, cublasDgemm(ctx->cublas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)n, (int)m,
+                                (int)k, &alpha, B->d, (int)B->cols, A->d, (int)A->cols, &beta, C->d, (int)C->cols));
+    return MMG_OK;
+}
+int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat h, const double* d_host) {
+    MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, A && d_host, "mmg_mat_scale_rows: bad argument");
+    MMG_TRY(ensure_scratch(ctx, A->rows * sizeof(double)));
+    MMG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, d_host, A->rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((unsigned)((A->cols + 255) / 256), (unsigned)A->rows);
+    scale_rows_kernel<<<grid, 256, 0, ctx->stream>>>(A->d, A->cols, (int)A->rows, (int)A->cols, (const double*)ctx->scratch);
+    MMG_TRY(launch_check(ctx, "scale_rows_kernel"));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat h, double alpha) {
+    MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, A && A->rows == A->cols, "mmg_mat_add_diag: needs a square matrix");
+    add_diag_kernel<<<(unsigned)((A->rows + 255) / 256), 256, 0, ctx->stream>>>(A->d, A->cols, (int)A->rows, alpha);
+    return launch_check(ctx, "add_diag_kernel");
+}
+
+static int scale_k_device(mmg_ctx* ctx, MmgMat* K, double* scalar) {
+    const int n = (int)K->rows;
+    MMG_TRY(ensure_scratch(ctx, (n + 2) * sizeof(double)));
+    double* rs = (double*)ctx->scratch;
+    rowsum_kernel<<<n, 256, 0, ctx->stream>>>(K->d, K->cols, n, rs);
+    MMG_TRY(launch_check(ctx, "rowsum_kernel"));
+    scale_k_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(rs, K->d, K->cols, n, rs + n);
+    MMG_TRY(launch_check(ctx, "scale_k_reduce_kernel"));
+    double h[2];
+    MMG_CUDA(ctx, cudaMemcpyAsync(h, rs + n, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double c = h[1] - h[0] / (double)n;                 // tr(K) - sum(K)/n  (kinship.py:95)
+    const double s = (double)(n - 1) / c;                     // :96
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    scale_matrix_kernel<<<grid, 256, 0, ctx->stream>>>(K->d, K->cols, n, n, s);
+    MMG_TRY(launch_check(ctx, "scale_matrix_kernel"));
+    if (scalar) *scalar = s;
+    return MMG_OK;
+}
+int mmg_mat_scale_k(mmg_ctx* ctx, mmg_mat h, double* scalar) {
+    MmgMat* K = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, K && K->rows == K->cols, "mmg_mat_scale_k: needs a square matrix");
+    MMG_TRY(scale_k_device(ctx, K, scalar));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat h, double* w_host, double* seconds) {
+    MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, A && A->rows == A->cols && w_host, "mmg_mat_syevd: needs a square matrix and w_host");
+    const int64_t n = A->rows;
+    StageTimer tm(ctx, "syevd");
+    cusolverDnParams_t params = nullptr;
+    MMG_CUSOLVER(ctx, cusolverDnCreateParams(&params));
+    size_t ws_dev = 0, ws_host = 0;
+    double* w_dev = nullptr;
+    void* buf_dev = nullptr;
+    void* buf_host = nullptr;
+    int* info_dev = nullptr;
+    int rc = MMG_OK;
+    do {
+        if (cudaMalloc(&w_dev, n * sizeof(double)) != cudaSuccess || cudaMalloc(&info_dev, sizeof(int)) != cudaSuccess) {
+            rc = fail(ctx, MMG_EOOM, "syevd: allocation failed");
+            break;
+        }
+        cusolverStatus_t st = cusolverDnXsyevd_bufferSize(ctx->cusolver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                                          CUDA_R_64F, A->d, n, CUDA_R_64F, w_dev, CUDA_R_64F, &ws_dev, &ws_host);
+        if (st != CUSOLVER_STATUS_SUCCESS) { rc = fail(ctx, MMG_ECUSOLVER, "Xsyevd_bufferSize status %d", (int)st); break; }
+        if (ws_dev && cudaMalloc(&buf_dev, ws_dev) != cudaSuccess) { rc = fail(ctx, MMG_EOOM, "syevd: workspace %zu B", ws_dev); break; }
+        if (ws_host) buf_host = malloc(ws_host);
+        st = cusolverDnXsyevd(ctx->cusolver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A->d, n,
+                              CUDA_R_64F, w_dev, CUDA_R_64F, buf_dev, ws_dev, buf_host, ws_host, info_dev);
+        if (st != CUSOLVER_STATUS_SUCCESS) { rc = fail(ctx, MMG_ECUSOLVER, "Xsyevd status %d", (int)st); break; }
+        int info = 0;
+        if (cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(w_host, w_dev, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rc = fail(ctx, MMG_ECUDA, "syevd: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (info != 0) { rc = fail(ctx, MMG_ECUSOLVER, "syevd did not converge (info=%d)", info); break; }
+    } while (0);
+    cudaFree(w_dev);
+    cudaFree(info_dev);
+    cudaFree(buf_dev);
+    free(buf_host);
+    cusolverDnDestroyParams(params);
+    tm.stop();
+    if (seconds) *seconds = ctx->timers["syevd"].seconds;
+    return rc;
+}
+
+// ======================================================================================================
+// genotypes
+// ======================================================================================================
+int mmg_snps_free(mmg_ctx* ctx) {
+    MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->snps);
+    ctx->snps = nullptr;
+    ctx->m = ctx->n = ctx->pitch = 0;
+    return MMG_OK;
+}
+int mmg_snps_reserve(mmg_ctx* ctx, int64_t m, int64_t n) {
+    MMG_CHECK(ctx, ctx && m > 0 && n > 0, "mmg_snps_reserve: bad shape");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t pitch = round_up(n, 256);   // zero padded: kernels read whole 16/32-byte groups up to the next 256
+    if (!(ctx->snps && ctx->m == m && ctx->n == n)) {
+        MMG_TRY(mmg_snps_free(ctx));
+        MMG_CUDA(ctx, cudaMalloc(&ctx->snps, (size_t)m * pitch));
+        ctx->m = m;
+        ctx->n = n;
+        ctx->pitch = pitch;
+        if (pitch != n) MMG_CUDA(ctx, cudaMemsetAsync(ctx->snps, 0, (size_t)m * pitch, ctx->stream));
+    }
+    return MMG_OK;
+}
+int mmg_snps_write(mmg_ctx* ctx, int64_t row0, const int8_t* snps, int64_t rows, int64_t ld) {
+    MMG_CHECK(ctx, ctx && ctx->snps && snps && row0 >= 0 && rows >= 0 && row0 + rows <= ctx->m && ld >= ctx->n,
+              "mmg_snps_write: bad argument");
+    StageTimer tm(ctx, "h2d");
+    if (rows)
+        MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->snps + row0 * ctx->pitch, ctx->pitch, snps, ld, ctx->n, rows, cudaMemcpyHostToDevice,
+                                        ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+int mmg_snps_upload(mmg_ctx* ctx, const int8_t* snps, int64_t m, int64_t n, int64_t ld) {
+    MMG_TRY(mmg_snps_reserve(ctx, m, n));
+    return mmg_snps_write(ctx, 0, snps, m, ld);
+}
+int mmg_snps_upload_rows(mmg_ctx* ctx, const int8_t* const* rows, int64_t m, int64_t n) {
+    MMG_CHECK(ctx, ctx && rows, "mmg_snps_upload_rows: bad argument");
+    MMG_TRY(mmg_snps_reserve(ctx, m, n));
+    StageTimer tm(ctx, "h2d");
+    // gather rows into two pinned staging buffers and copy them asynchronously
+    const int64_t rows_per = std::max<int64_t>(1, (32ll << 20) / n);
+    int8_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    for (int b = 0; b < 2; ++b) {
+        if (cudaHostAlloc((void**)&stage[b], (size_t)rows_per * n, cudaHostAllocDefault) != cudaSuccess) {
+            for (int c = 0; c < b; ++c) { cudaFreeHost(stage[c]); cudaEventDestroy(done[c]); }
+            return fail(ctx, MMG_EOOM, "pinned staging allocation failed");
+        }
+        cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+    }
+    int rc = MMG_OK;
+    int b = 0;
+    for (int64_t r0 = 0; r0 < m; r0 += rows_per, b ^= 1) {
+        const int64_t cnt = std::min(rows_per, m - r0);
+        cudaEventSynchronize(done[b]);
+        for (int64_t r = 0; r < cnt; ++r) memcpy(stage[b] + r * n, rows[r0 + r], (size_t)n);
+        if (cudaMemcpy2DAsync(ctx->snps + r0 * ctx->pitch, ctx->pitch, stage[b], n, n, cnt, cudaMemcpyHostToDevice, ctx->stream) !=
+            cudaSuccess) {
+            rc = fail(ctx, MMG_ECUDA, "row upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaEventRecord(done[b], ctx->stream);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (int c = 0; c < 2; ++c) { cudaFreeHost(stage[c]); cudaEventDestroy(done[c]); }
+    return rc;
+}
+int mmg_snps_shape(mmg_ctx* ctx, int64_t* m, int64_t* n) {
+    MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    if (m) *m = ctx->m;
+    if (n) *n = ctx->n;
+    return MMG_OK;
+}
+int mmg_snps_device_ptr(mmg_ctx* ctx, void** dptr, int64_t* pitch) {
+    MMG_CHECK(ctx, ctx && dptr, "bad argument");
+    *dptr = ctx->snps;
+    if (pitch) *pitch = ctx->pitch;
+    return MMG_OK;
+}
+int mmg_snps_row_sums(mmg_ctx* ctx, int64_t* sums_host, int64_t* sumsq_host) {
+    MMG_CHECK(ctx, ctx && ctx->snps && sums_host, "mmg_snps_row_sums: no resident genotypes");
+    MMG_TRY(ensure_scratch(ctx, 2 * ctx->m * sizeof(long long)));
+    long long* s = (long long*)ctx->scratch;
+    long long* q = s + ctx->m;
+    snp_row_sums_kernel<<<(unsigned)((ctx->m + 7) / 8), 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, ctx->m, (int)ctx->n, s, q);
+    MMG_TRY(launch_check(ctx, "snp_row_sums_kernel"));
+    MMG_CUDA(ctx, cudaMemcpyAsync(sums_host, s, ctx->m * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sumsq_host) MMG_CUDA(ctx, cudaMemcpyAsync(sumsq_host, q, ctx->m * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+// ======================================================================================================
+// stage 1: kinship
+// ======================================================================================================
+static int ensure_tiles(mmg_ctx* ctx, const std::vector<TcTile>& tiles) {
+    const int64_t bytes = (int64_t)tiles.size() * sizeof(TcTile);
+    if (ctx->tiles_bytes < bytes) {
+        cudaFree(ctx->tiles_d);
+        ctx->tiles_d = nullptr;
+        ctx->tiles_bytes = 0;
+        MMG_CUDA(ctx, cudaMalloc(&ctx->tiles_d, bytes));
+        ctx->tiles_bytes = bytes;
+    }
+    MMG_CUDA(ctx, cudaMemcpyAsync(ctx->tiles_d, tiles.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MMG_OK;
+}
+
+int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset) {
+    MMG_CHECK(ctx, ctx && ctx->snps, "mmg_kinship_gram_i8: no resident genotypes");
+    MMG_CHECK(ctx, coding == MMG_CODING_BINARY || coding == MMG_CODING_DIPLOID, "unknown coding %d", coding);
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count >= 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    if (impl == MMG_IMPL_AUTO) impl = MMG_IMPL_TCGEN05;
+    MMG_CHECK(ctx, impl == MMG_IMPL_TCGEN05 || impl == MMG_IMPL_SIMT, "unsupported impl %d for the Gram", impl);
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = (int)ctx->n;
+    const int c = coding == MMG_CODING_DIPLOID ? 2 : 1;
+    const int64_t g_pad = round_up(n, 256);
+    if (!ctx->G || ctx->g_pad != g_pad) {
+        cudaFree(ctx->G);
+        ctx->G = nullptr;
+        MMG_CUDA(ctx, cudaMalloc(&ctx->G, (size_t)g_pad * g_pad * sizeof(int32_t)));
+        ctx->g_pad = g_pad;
+        reset = 1;
+    }
+    if (reset) {
+        MMG_CUDA(ctx, cudaMemsetAsync(ctx->G, 0, (size_t)g_pad * g_pad * sizeof(int32_t), ctx->stream));
+        ctx->g_zero = true;
+    }
+    // int32 accumulator headroom: |entries| <= K-dim (values are +-1 or 0/1)
+    MMG_CHECK(ctx, (double)snp_count * c < 2.0e9, "Gram K-dimension too large for int32 accumulation");
+
+    const int64_t chunk = 65536;                         // SNPs per packed chunk (multiple of 128)
+    const int64_t p_pitch = chunk * c;
+    const int64_t need = (int64_t)n * p_pitch;
+    if (ctx->pack_bytes < need) {
+        cudaFree(ctx->pack);
+        ctx->pack = nullptr;
+        ctx->pack_bytes = 0;
+        MMG_CUDA(ctx, cudaMalloc(&ctx->pack, need));
+        ctx->pack_bytes = need;
+    }
+    MMG_CUDA(ctx, cudaMemsetAsync(ctx->flag_d, 0, sizeof(int), ctx->stream));
+
+    // tile table: upper-triangular 128 x 256 tiles (row tile im needed for column tile jn iff im <= 2 jn + 1)
+    std::vector<TcTile> tiles;
+    if (impl == MMG_IMPL_TCGEN05) {
+        const int tiles_m = (n + TC_BM - 1) / TC_BM, tiles_n = (n + TC_BN - 1) / TC_BN;
+        for (int jn = 0; jn < tiles_n; ++jn)
+            for (int im = 0; im < tiles_m && im <= 2 * jn + 1; ++im) tiles.push_back(TcTile{im * TC_BM, jn * TC_BN, 0, 0, 0, 0, 0, 0});
+    }
+    double gram_ms = 0.0, pack_s = 0.0;
+    for (int64_t s0 = 0; s0 < snp_count; s0 += chunk) {
+        const int64_t cnt = std::min(chunk, snp_count - s0);
+        const int64_t kbytes = round_up(cnt, 128) * c;
+        // ---- pack ----
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        dim3 pgrid((unsigned)((cnt + 127) / 128), (unsigned)((n + 63) / 64));
+        if (coding == MMG_CODING_BINARY)
+            pack_kmajor_kernel<0><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+        else
+            pack_kmajor_kernel<1><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+        MMG_TRY(launch_check(ctx, "pack_kmajor_kernel"));
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        // ---- Gram ----
+        const int accumulate = ctx->g_zero ? 0 : 1;
+        cudaEventRecord(ctx->kev0, ctx->stream);
+        if (impl == MMG_IMPL_TCGEN05) {
+            CUtensorMap tmA, tmB;
+            MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->pack, kbytes, n, p_pitch, TC_BM));
+            MMG_TRY(make_tmap_u8(ctx, &tmB, ctx->pack, kbytes, n, p_pitch, TC_BN));
+            for (auto& t : tiles) { t.kb0 = 0; t.kb1 = (int)(kbytes / TC_BK); }
+            MMG_TRY(ensure_tiles(ctx, tiles));
+            GramEpi::Params ep{ctx->G, g_pad, accumulate};
+            const int grid = std::min<int>((int)tiles.size(), ctx->sm_count);
+            tc_gemm_i8_kernel<GramEpi><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(tmA, tmB, (const TcTile*)ctx->tiles_d,
+                                                                                       (int)tiles.size(), 1, 1, 0, ep);
+            MMG_TRY(launch_check(ctx, "tc_gemm_i8_kernel<GramEpi>"));
+        } else {
+            dim3 ggrid((unsigned)((n + 63) / 64), (unsigned)((n + 63) / 64));
+            gram_simt_kernel<<<ggrid, 256, 0, ctx->stream>>>(ctx->pack, p_pitch, n, kbytes, ctx->G, g_pad, accumulate);
+            MMG_TRY(launch_check(ctx, "gram_simt_kernel"));
+        }
+        cudaEventRecord(ctx->kev1, ctx->stream);
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        pack_s += ms * 1e-3;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        gram_ms += ms;
+        ctx->g_zero = false;
+    }
+    ctx->timers["pack"].seconds += pack_s;
+    ctx->timers["pack"].calls += 1;
+    ctx->timers["gram"].seconds += gram_ms * 1e-3;
+    ctx->timers["gram"].calls += 1;
+    ctx->last_gram_ms = gram_ms;
+    int bad = 0;
+    MMG_CUDA(ctx, cudaMemcpy(&bad, ctx->flag_d, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad)
+        return fail(ctx, MMG_EVALUE, "genotype values outside the domain of the '%s' coding (%s)",
+                    coding == MMG_CODING_BINARY ? "binary" : "diploid_int", coding == MMG_CODING_BINARY ? "{0,1}" : "{0,1,2}");
+    return MMG_OK;
+}
+
+int mmg_kinship_gram_ptr(mmg_ctx* ctx, void** dptr, int64_t* n, int64_t* ld) {
+    MMG_CHECK(ctx, ctx && ctx->G && dptr, "mmg_kinship_gram_ptr: no Gram resident");
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *dptr = ctx->G;
+    if (n) *n = ctx->n;
+    if (ld) *ld = ctx->g_pad;
+    return MMG_OK;
+}
+
+int mmg_kinship_gram_download(mmg_ctx* ctx, int32_t* G_host) {
+    MMG_CHECK(ctx, ctx && ctx->G && G_host, "mmg_kinship_gram_download: no Gram resident");
+    const int n = (int)ctx->n;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    gram_mirror_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n);
+    MMG_TRY(launch_check(ctx, "gram_mirror_kernel"));
+    MMG_CUDA(ctx, cudaMemcpy2DAsync(G_host, (size_t)n * 4, ctx->G, (size_t)ctx->g_pad * 4, (size_t)n * 4, n, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+int mmg_kinship_finalize_f64(mmg_ctx* ctx, int coding, int64_t m_total, int scaled, mmg_mat K_out, double* scale_scalar) {
+    MmgMat* K = ctx ? get_mat(ctx, K_out) : nullptr;
+    MMG_CHECK(ctx, K && ctx->G, "mmg_kinship_finalize_f64: need a Gram and an output matrix");
+    MMG_CHECK(ctx, K->rows == ctx->n && K->cols == ctx->n, "K_out must be n x n");
+    MMG_CHECK(ctx, m_total > 0, "m_total must be positive");
+    StageTimer tm(ctx, "finalize");
+    const int n = (int)ctx->n;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    if (coding == MMG_CODING_BINARY)
+        kinship_finalize_kernel<0><<<grid, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n, (double)m_total, K->d, K->cols);
+    else
+        kinship_finalize_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n, (double)m_total, K->d, K->cols);
+    MMG_TRY(launch_check(ctx, "kinship_finalize_kernel"));
+    if (scale_scalar) *scale_scalar = 1.0;
+    if (scaled) MMG_TRY(scale_k_device(ctx, K, scale_scalar));
+    return MMG_OK;
+}
+
+__global__ void mirror_lower_to_upper_kernel(double* __restrict__ K, int64_t ld, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c < n && c > r) K[(int64_t)r * ld + c] = K[(int64_t)c * ld + r];
+}
+
+int mmg_kinship_ibd_accumulate_f64(mmg_ctx* ctx, mmg_mat K_acc, int64_t snp_begin, int64_t snp_count, const uint8_t* snp_mask,
+                                   int64_t* used) {
+    MmgMat* K = ctx ? get_mat(ctx, K_acc) : nullptr;
+    MMG_CHECK(ctx, K && ctx->snps, "mmg_kinship_ibd_accumulate_f64: need resident genotypes and an accumulator");
+    MMG_CHECK(ctx, K->rows == ctx->n && K->cols == ctx->n, "K_acc must be n x n");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count >= 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    StageTimer tm(ctx, "ibd");
+    std::vector<long long> rows;
+    rows.reserve(snp_count);
+    for (int64_t s = 0; s < snp_count; ++s)
+        if (!snp_mask || snp_mask[s]) rows.push_back(snp_begin + s);
+    if (used) *used = (int64_t)rows.size();
+    if (rows.empty()) return MMG_OK;
+    const int n = (int)ctx->n;
+    const int64_t chunk = 2048;
+    const int64_t zbytes = chunk * (int64_t)n * sizeof(double);
+    const int64_t rbytes = round_up((int64_t)rows.size() * sizeof(long long), 256);
+    MMG_TRY(ensure_scratch(ctx, zbytes + rbytes));
+    double* Z = (double*)ctx->scratch;
+    long long* rows_d = (long long*)((uint8_t*)ctx->scratch + zbytes);
+    MMG_CUDA(ctx, cudaMemcpyAsync(rows_d, rows.data(), rows.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, cudaMemsetAsync(ctx->flag_d, 0, sizeof(int), ctx->stream));
+    const double one = 1.0;
+    for (int64_t r0 = 0; r0 < (int64_t)rows.size(); r0 += chunk) {
+        const int64_t cnt = std::min<int64_t>(chunk, (int64_t)rows.size() - r0);
+        standardise_rows_kernel<<<(unsigned)cnt, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, rows_d + r0, n, Z, n, ctx->flag_d);
+        MMG_TRY(launch_check(ctx, "standardise_rows_kernel"));
+        // K += Z' Z.  Z row-major [cnt x n] is the column-major n x cnt matrix Zc; column-major UPPER of
+        // Zc Zc' is the row-major lower triangle, mirrored below.
+        MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, n, (int)cnt, &one, Z, n, &one, K->d, n));
+    }
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    mirror_lower_to_upper_kernel<<<grid, 256, 0, ctx->stream>>>(K->d, K->cols, n);
+    MMG_TRY(launch_check(ctx, "mirror_lower_to_upper_kernel"));
+    int bad = 0;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad) return fail(ctx, MMG_EVALUE, "monomorphic SNP in IBD kinship (std == 0; the reference asserts at kinship.py:67)");
+    return MMG_OK;
+}
+
+// ======================================================================================================
+// stage 2: REML
+// ======================================================================================================
+int mmg_reml_f64(mmg_ctx* ctx, const double* eig_vals, const double* sq_etas, int64_t p, int64_t T, const double* deltas, int64_t g,
+                 double esp, double* lls, double* dlls, double* opt_delta, double* opt_ll, int32_t* flags) {
+    MMG_CHECK(ctx, ctx && eig_vals && sq_etas && deltas && p > 0 && T > 0 && g > 1, "mmg_reml_f64: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm(ctx, "reml");
+    const int64_t nd = p + T * p + g + 2 * T * g + 2 * T;
+    MMG_TRY(ensure_scratch(ctx, nd * sizeof(double) + T * sizeof(int) + 64));
+    double* d_eig = (double*)ctx->scratch;
+    double* d_sq = d_eig + p;
+    double* d_del = d_sq + T * p;
+    double* d_lls = d_del + g;
+    double* d_dlls = d_lls + T * g;
+    double* d_od = d_dlls + T * g;
+    double* d_ol = d_od + T;
+    int* d_fl = (int*)(d_ol + T);
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_eig, eig_vals, p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_sq, sq_etas, T * p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_del, deltas, g * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((unsigned)g, (unsigned)T);
+    reml_grid_kernel<<<grid, REML_THREADS, 0, ctx->stream>>>(d_eig, d_sq, (int)p, d_del, (int)g, d_lls, d_dlls);
+    MMG_TRY(launch_check(ctx, "reml_grid_kernel"));
+    reml_refine_kernel<<<(unsigned)T, REML_THREADS, 0, ctx->stream>>>(d_eig, d_sq, (int)p, d_del, (int)g, esp, d_lls, d_dlls, d_od, d_ol,
+                                                                     d_fl);
+    MMG_TRY(launch_check(ctx, "reml_refine_kernel"));
+    if (lls) MMG_CUDA(ctx, cudaMemcpyAsync(lls, d_lls, T * g * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dlls) MMG_CUDA(ctx, cudaMemcpyAsync(dlls, d_dlls, T * g * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (opt_delta) MMG_CUDA(ctx, cudaMemcpyAsync(opt_delta, d_od, T * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (opt_ll) MMG_CUDA(ctx, cudaMemcpyAsync(opt_ll, d_ol, T * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (flags) MMG_CUDA(ctx, cudaMemcpyAsync(flags, d_fl, T * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+// ======================================================================================================
+// stage 3: scan
+// ======================================================================================================
+}  // extern "C"
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+}  // namespace
+
+// zero-padded copy of R: rows -> multiple of 128, cols -> multiple of 128
+static int pad_matrix(mmg_ctx* ctx, const MmgMat* R, DevBuf& out, int64_t* rows_pad, int64_t* ld) {
+    *rows_pad = round_up(R->rows, 128);
+    *ld = round_up(R->cols, 128);
+    MMG_CUDA(ctx, out.alloc((size_t)(*rows_pad) * (*ld) * sizeof(double)));
+    MMG_CUDA(ctx, cudaMemsetAsync(out.p, 0, (size_t)(*rows_pad) * (*ld) * sizeof(double), ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpy2DAsync(out.p, (*ld) * sizeof(double), R->d, R->cols * sizeof(double), R->cols * sizeof(double), R->rows,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    return MMG_OK;
+}
+
+static int launch_scan_dmma(mmg_ctx* ctx, bool perm, const ScanDmmaParams& prm) {
+    const int64_t blocks = (prm.row_count + SD_BM - 1) / SD_BM;
+    const int grid = (int)std::min<int64_t>(blocks, ctx->sm_count);
+    cudaEventRecord(ctx->kev0, ctx->stream);
+    if (perm)
+        scan_dmma_kernel<true><<<grid, SD_THREADS, SD_SMEM_BYTES, ctx->stream>>>(prm);
+    else
+        scan_dmma_kernel<false><<<grid, SD_THREADS, SD_SMEM_BYTES, ctx->stream>>>(prm);
+    MMG_TRY(launch_check(ctx, "scan_dmma_kernel"));
+    cudaEventRecord(ctx->kev1, ctx->stream);
+    return MMG_OK;
+}
+
+// ---- int8 tensor-core scan: x'(R'R)x on exact integer slices (scan_tc.cuh) ------------------------------
+static int scan_tc_slices() {
+    const char* e = getenv("MMG_TC_SLICES");
+    int S = e ? atoi(e) : 7;
+    if (S < 1) S = 1;
+    if (S > QS_MAX_SLICES) S = QS_MAX_SLICES;
+    return S;
+}
+
+static int scan_tc_run(mmg_ctx* ctx, const MmgMat* R, const double* V, double h0_rss, double n_p, double lbeta, int64_t snp_begin,
+                       int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p, double* d_vp) {
+    const int64_t n = ctx->n, n_out = R->rows;
+    const int S = scan_tc_slices();
+    const int64_t n_padN = round_up(n, TC_BN), ldq = round_up(n, TC_BK);
+    DevBuf A, Bq, vec;
+    MMG_CUDA(ctx, A.alloc((size_t)n * n * sizeof(double)));
+    MMG_CUDA(ctx, Bq.alloc((size_t)S * n_padN * ldq));
+    MMG_CUDA(ctx, vec.alloc((size_t)(n_padN + n_out + 1) * sizeof(double)));
+    double* d_v = vec.as<double>();
+    double* d_y = d_v + n_padN;
+    unsigned long long* d_amax = (unsigned long long*)(d_y + n_out);
+    MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)(n_padN + n_out + 1) * sizeof(double), ctx->stream));
+    MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)S * n_padN * ldq, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const double one = 1.0, zero = 0.0;
+    // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
+    // is the row-major LOWER triangle A[j][i], i <= j -- exactly the operand the slices are cut from.
+    MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero,
+                                A.as<double>(), (int)n));
+    // v = R' y~  (x~.y~ = x.v)
+    MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1));
+    dim3 agrid(8, (unsigned)n);
+    quad_amax_kernel<<<agrid, 256, 0, ctx->stream>>>(A.as<double>(), n, (int)n, d_amax);
+    MMG_TRY(launch_check(ctx, "quad_amax_kernel"));
+    double amax = 0.0;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!(amax > 0.0) || !std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "scan: R'R is zero or not finite (max |a| = %g)", amax);
+    const int E = ilogb(amax) + 2;                       // |c a| 2^-E < 1/2
+    dim3 sgrid((unsigned)((n + 255) / 256), (unsigned)n);
+    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A.as<double>(), n, (int)n, ldexp(1.0, -E), S, Bq.as<int8_t>(), n_padN, ldq);
+    MMG_TRY(launch_check(ctx, "quad_slice_kernel"));
+
+    QuadEpi::Params ep{};
+    ep.snps = ctx->snps;
+    ep.pitch = ctx->pitch;
+    ep.row_begin = snp_begin;
+    ep.row_count = snp_count;
+    for (int k = 0; k < S; ++k) ep.w[k] = ldexp(1.0, E - 7 * (k + 1));
+    ep.v = d_v;
+    ep.h0_rss = h0_rss;
+    ep.n_p = n_p;
+    ep.lbeta = lbeta;
+    ep.xx = d_xx; ep.xy = d_xy; ep.rss = d_rss; ep.f = d_f; ep.p = d_p; ep.var_perc = d_vp;
+
+    // one shared tile table: for every 256-column tile jb, one tile per slice; K only up to the diagonal
+    const int tiles_n = (int)(n_padN / TC_BN), kb_total = (int)(ldq / TC_BK);
+    std::vector<TcTile> tiles;
+    for (int jb = 0; jb < tiles_n; ++jb)
+        for (int k = 0; k < S; ++k) {
+            TcTile t{};
+            t.m0 = 0;
+            t.n0 = (int)(k * n_padN + (int64_t)jb * TC_BN);
+            t.kb0 = 0;
+            t.kb1 = std::min(kb_total, (jb + 1) * (TC_BN / TC_BK));
+            t.aux0 = k;
+            t.aux1 = (k == 0) ? 1 : 0;
+            t.col0 = jb * TC_BN;
+            tiles.push_back(t);
+        }
+    MMG_TRY(ensure_tiles(ctx, tiles));
+    CUtensorMap tmA, tmB;
+    MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq.p, ldq, (int64_t)S * n_padN, ldq, TC_BN));
+    const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
+    const int grid = std::min(groups, ctx->sm_count);
+    cudaEventRecord(ctx->kev0, ctx->stream);
+    tc_gemm_i8_kernel<QuadEpi><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(tmA, tmB, (const TcTile*)ctx->tiles_d, groups,
+                                                                               (int)tiles.size(), 0, TC_BM, ep);
+    MMG_TRY(launch_check(ctx, "tc_gemm_i8_kernel<QuadEpi>"));
+    cudaEventRecord(ctx->kev1, ctx->stream);
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // Bq / A / vec are freed on return
+    return MMG_OK;
+}
+
+extern "C" {
+
+int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double h0_rss, double n_p, int impl, int64_t snp_begin,
+                       int64_t snp_count, double* ps, double* f_stats, double* rss, double* var_perc, double* xx, double* dots) {
+    MmgMat* R = ctx ? get_mat(ctx, Rh) : nullptr;
+    MMG_CHECK(ctx, R && ctx->snps, "mmg_emmax_scan_f64: need resident genotypes and R");
+    MMG_CHECK(ctx, R->cols == ctx->n, "R must have n = %lld columns (has %lld)", (long long)ctx->n, (long long)R->cols);
+    MMG_CHECK(ctx, V && nv >= 1 && nv <= 16, "need 1..16 rotated-space vectors (V[0] = residual phenotype)");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    if (impl == MMG_IMPL_AUTO) impl = MMG_IMPL_TCGEN05;
+    MMG_CHECK(ctx, impl == MMG_IMPL_DMMA || impl == MMG_IMPL_TCGEN05, "unsupported impl %d for the scan", impl);
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n, n_out = R->rows;
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+
+    DevBuf out;      // xx, xy, rss, f, p, var_perc  (6 x snp_count doubles) + dots
+    MMG_CUDA(ctx, out.alloc((size_t)(6 + nv) * snp_count * sizeof(double)));
+    double* d_xx = out.as<double>();
+    double* d_xy = d_xx + snp_count;
+    double* d_rss = d_xy + snp_count;
+    double* d_f = d_rss + snp_count;
+    double* d_p = d_f + snp_count;
+    double* d_vp = d_p + snp_count;
+    double* d_dots = d_vp + snp_count;
+
+    {
+        StageTimer tm(ctx, "scan");
+        if (impl == MMG_IMPL_DMMA) {
+            DevBuf Rp, Vp;
+            int64_t rows_pad = 0, ld = 0;
+            MMG_TRY(pad_matrix(ctx, R, Rp, &rows_pad, &ld));
+            MMG_CUDA(ctx, Vp.alloc((size_t)rows_pad * sizeof(double)));
+            MMG_CUDA(ctx, cudaMemsetAsync(Vp.p, 0, (size_t)rows_pad * sizeof(double), ctx->stream));
+            MMG_CUDA(ctx, cudaMemcpyAsync(Vp.p, V, n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            ScanDmmaParams prm{};
+            prm.snps = ctx->snps;
+            prm.pitch = ctx->pitch;
+            prm.row_begin = snp_begin;
+            prm.row_count = snp_count;
+            prm.R = Rp.as<double>();
+            prm.ldr = ld;
+            prm.n_out_pad = (int)rows_pad;
+            prm.k_pad = (int)round_up(n, SD_BK);
+            prm.y = Vp.as<double>();
+            prm.h0_rss = h0_rss;
+            prm.n_p = n_p;
+            prm.lbeta = lbeta;
+            prm.xx = d_xx;
+            prm.xy = d_xy;
+            prm.rss = d_rss;
+            prm.f = d_f;
+            prm.p = d_p;
+            prm.var_perc = d_vp;
+            MMG_TRY(launch_scan_dmma(ctx, false, prm));
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            MMG_TRY(scan_tc_run(ctx, R, V, h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp));
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        ctx->last_scan_ms = ms;
+
+        if (dots) {
+            // x~.V[v] = x.(R' V[v]):  W = V R  ([nv x n_out] x [n_out x n]) then an HBM-bound dot kernel
+            DevBuf Vd, Wd;
+            MMG_CUDA(ctx, Vd.alloc((size_t)nv * n_out * sizeof(double)));
+            MMG_CUDA(ctx, Wd.alloc((size_t)nv * n * sizeof(double)));
+            MMG_CUDA(ctx, cudaMemcpyAsync(Vd.p, V, (size_t)nv * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            const double one = 1.0, zero = 0.0;
+            // row-major W[nv x n] = V[nv x n_out] R[n_out x n]  ->  column-major W' = R' V'
+            MMG_CUBLAS(ctx, cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, nv, (int)n_out, &one, R->d, (int)R->cols,
+                                        Vd.as<double>(), (int)n_out, &zero, Wd.as<double>(), (int)n));
+            for (int v = 0; v < nv; ++v) {
+                // one vector per launch keeps the kernel simple; dots is strided by nv on the host side
+                snp_dots_kernel<1><<<(unsigned)((snp_count + 7) / 8), 256, 0, ctx->stream>>>(
+                    ctx->snps, ctx->pitch, snp_begin, snp_count, (int)n, Wd.as<double>() + (int64_t)v * n, n, d_dots + (int64_t)v * snp_count);
+                MMG_TRY(launch_check(ctx, "snp_dots_kernel"));
+            }
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    StageTimer tm2(ctx, "d2h");
+    const size_t bytes = snp_count * sizeof(double);
+    if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (f_stats) MMG_CUDA(ctx, cudaMemcpyAsync(f_stats, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rss) MMG_CUDA(ctx, cudaMemcpyAsync(rss, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_perc) MMG_CUDA(ctx, cudaMemcpyAsync(var_perc, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xx) MMG_CUDA(ctx, cudaMemcpyAsync(xx, d_xx, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dots) {
+        // device layout is [nv][snp_count]; the ABI promises [snp_count][nv]
+        std::vector<double> tmp((size_t)nv * snp_count);
+        MMG_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_dots, (size_t)nv * bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int v = 0; v < nv; ++v)
+            for (int64_t s = 0; s < snp_count; ++s) dots[s * nv + v] = tmp[(size_t)v * snp_count + s];
+    }
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+__global__ void means_from_sums_kernel(const long long* __restrict__ sums, int64_t count, double inv_n, double* __restrict__ mu) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) mu[i] = (double)sums[i] * inv_n;
+}
+
+int mmg_emmax_perm_scan_f64(mmg_ctx* ctx, mmg_mat Rh, mmg_mat Wh, int centre, int impl, int64_t snp_begin, int64_t snp_count,
+                            double* ratio_inout) {
+    MmgMat *R = ctx ? get_mat(ctx, Rh) : nullptr, *Wt = ctx ? get_mat(ctx, Wh) : nullptr;
+    MMG_CHECK(ctx, R && Wt && ctx->snps && ratio_inout, "mmg_emmax_perm_scan_f64: bad argument");
+    MMG_CHECK(ctx, R->cols == ctx->n && Wt->cols == ctx->n, "R and W' must have n columns");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    MMG_CHECK(ctx, impl == MMG_IMPL_AUTO || impl == MMG_IMPL_DMMA, "the permutation scan runs on the DMMA path");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm(ctx, "scan");
+    const int64_t n = ctx->n, P = Wt->rows;
+    DevBuf Rp, Wp, aux;
+    int64_t r_rows = 0, r_ld = 0, w_rows = 0, w_ld = 0;
+    MMG_TRY(pad_matrix(ctx, R, Rp, &r_rows, &r_ld));
+    MMG_TRY(pad_matrix(ctx, Wt, Wp, &w_rows, &w_ld));
+    // aux: ones[n] | r1[r_rows] | wsum[w_rows] | zeros y[r_rows] | mu[snp_count] | xx[snp_count] | ratio[w_rows] | sums[snp_count]
+    const int64_t nd = r_ld + r_rows + w_rows + r_rows + 2 * snp_count + w_rows;
+    MMG_CUDA(ctx, aux.alloc((size_t)nd * sizeof(double) + (size_t)snp_count * sizeof(long long)));
+    MMG_CUDA(ctx, cudaMemsetAsync(aux.p, 0, (size_t)nd * sizeof(double), ctx->stream));
+    double* d_ones = aux.as<double>();
+    double* d_r1 = d_ones + r_ld;
+    double* d_wsum = d_r1 + r_rows;
+    double* d_y0 = d_wsum + w_rows;
+    double* d_mu = d_y0 + r_rows;
+    double* d_xx = d_mu + snp_count;
+    unsigned long long* d_ratio = (unsigned long long*)(d_xx + snp_count);
+    long long* d_sums = (long long*)(d_ratio + w_rows);
+    {
+        std::vector<double> ones((size_t)n, 1.0);
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_ones, ones.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const double one = 1.0, zero = 0.0;
+    // r1 = R 1, wsum = W' 1 (padded matrices are column-major [ld x rows]: y = A' x)
+    MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_T, (int)r_ld, (int)r_rows, &one, Rp.as<double>(), (int)r_ld, d_ones, 1, &zero, d_r1, 1));
+    MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_T, (int)w_ld, (int)w_rows, &one, Wp.as<double>(), (int)w_ld, d_ones, 1, &zero, d_wsum, 1));
+    if (centre) {
+        snp_row_sums_kernel<<<(unsigned)((snp_count + 7) / 8), 256, 0, ctx->stream>>>(ctx->snps + snp_begin * ctx->pitch, ctx->pitch,
+                                                                                      snp_count, (int)n, d_sums, nullptr);
+        MMG_TRY(launch_check(ctx, "snp_row_sums_kernel"));
+        means_from_sums_kernel<<<(unsigned)((snp_count + 255) / 256), 256, 0, ctx->stream>>>(d_sums, snp_count, 1.0 / (double)n, d_mu);
+        MMG_TRY(launch_check(ctx, "means_from_sums_kernel"));
+    }
+    ScanDmmaParams prm{};
+    prm.snps = ctx->snps;
+    prm.pitch = ctx->pitch;
+    prm.row_begin = snp_begin;
+    prm.row_count = snp_count;
+    prm.k_pad = (int)round_up(n, SD_BK);
+    prm.mu = d_mu;                     // zeros when !centre
+    // pass 1: xx of the (centred) rotated SNPs
+    prm.R = Rp.as<double>();
+    prm.ldr = r_ld;
+    prm.n_out_pad = (int)r_rows;
+    prm.y = d_y0;
+    prm.r1 = d_r1;
+    prm.xx = d_xx;
+    prm.h0_rss = 1.0;
+    prm.n_p = 1.0;
+    MMG_TRY(launch_scan_dmma(ctx, false, prm));
+    // pass 2: max over SNPs of (x_c . W_p)^2 / xx
+    prm.R = Wp.as<double>();
+    prm.ldr = w_ld;
+    prm.n_out_pad = (int)w_rows;
+    prm.r1 = d_wsum;
+    prm.xx = nullptr;
+    prm.xx_in = d_xx;
+    prm.ratio_max = d_ratio;
+    MMG_TRY(launch_scan_dmma(ctx, true, prm));
+    std::vector<double> ratio((size_t)P);
+    MMG_CUDA(ctx, cudaMemcpyAsync(ratio.data(), d_ratio, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t p = 0; p < P; ++p) ratio_inout[p] = std::max(ratio_inout[p], ratio[p]);
+    return MMG_OK;
+}
+
+int mmg_f_sf_f64(mmg_ctx* ctx, const double* f, int64_t count, double dfn, double dfd, double* out) {
+    MMG_CHECK(ctx, ctx && f && out && count >= 0 && dfn > 0 && dfd > 0, "mmg_f_sf_f64: bad argument");
+    if (count == 0) return MMG_OK;
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf buf;
+    MMG_CUDA(ctx, buf.alloc(2 * count * sizeof(double)));
+    double* d_f = buf.as<double>();
+    double* d_o = d_f + count;
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_f, f, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    f_sf_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(d_f, count, dfn, dfd, lbeta_host(0.5 * dfd, 0.5 * dfn), d_o);
+    MMG_TRY(launch_check(ctx, "f_sf_kernel"));
+    MMG_CUDA(ctx, cudaMemcpyAsync(out, d_o, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+// ======================================================================================================
+// diagnostics
+// ======================================================================================================
+__global__ void __launch_bounds__(256) bench_dmma_kernel(double* out, int iters) {
+    double c[8][2];
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma_8x8x4(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+__global__ void __launch_bounds__(256) bench_dfma_kernel(double* out, int iters) {
+    double c[16];
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-9 + i;
+    const double a = 1.0000001, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 12345.678) out[0] = s;
+}
+__global__ void bench_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n16) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
+    MMG_CHECK(ctx, ctx && which && value, "mmg_microbench: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MMG_TRY(ensure_scratch(ctx, 1 << 20));
+    float ms = 0.f;
+    if (!strcmp(which, "dmma") || !strcmp(which, "dfma")) {
+        const bool dm = !strcmp(which, "dmma");
+        const int iters = 20000, blocks = ctx->sm_count * 4;
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(ctx->kev0, ctx->stream);
+            if (dm) bench_dmma_kernel<<<blocks, 256, 0, ctx->stream>>>((double*)ctx->scratch, iters);
+            else bench_dfma_kernel<<<blocks, 256, 0, ctx->stream>>>((double*)ctx->scratch, iters);
+            MMG_TRY(launch_check(ctx, "bench kernel"));
+            cudaEventRecord(ctx->kev1, ctx->stream);
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        }
+        const double flops = dm ? (double)blocks * 8 /*warps*/ * iters * 8.0 * 512.0 : (double)blocks * 256 * iters * 16.0 * 2.0;
+        *value = flops / (ms * 1e-3) / 1e12;
+        return MMG_OK;
+    }
+    if (!strcmp(which, "copy")) {
+        const int64_t bytes = 2ll << 30;
+        DevBuf a, b;
+        MMG_CUDA(ctx, a.alloc(bytes));
+        MMG_CUDA(ctx, b.alloc(bytes));
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(ctx->kev0, ctx->stream);
+            bench_copy_kernel<<<ctx->sm_count * 16, 512, 0, ctx->stream>>>(a.as<uint4>(), b.as<uint4>(), bytes / 16);
+            MMG_TRY(launch_check(ctx, "bench_copy_kernel"));
+            cudaEventRecord(ctx->kev1, ctx->stream);
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        }
+        *value = 2.0 * bytes / (ms * 1e-3) / 1e9;
+        return MMG_OK;
+    }
+    return fail(ctx, MMG_EBADARG, "unknown microbench '%s'", which);
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Internal context of libmixmogam_b200 (not part of the ABI).
+#pragma once
+#include <cublas_v2.h>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mixmogam_b200.h"
+
+struct MmgMat {
+    double* d = nullptr;
+    int64_t rows = 0, cols = 0;   // dense row-major, ld == cols
+};
+
+struct MmgTimer {
+    double seconds = 0.0;
+    int64_t calls = 0;
+};
+
+struct mmg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cublasHandle_t cublas = nullptr;
+    cusolverDnHandle_t cusolver = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr;
+    std::string err;
+    std::map<int64_t, MmgMat> mats;
+    int64_t next_mat = 1;
+    int64_t launches = 0;
+    std::map<std::string, MmgTimer> timers;
+    double last_gram_ms = 0.0, last_scan_ms = 0.0;
+
+    // resident genotypes
+    int8_t* snps = nullptr;
+    int64_t m = 0, n = 0, pitch = 0;
+
+    // kinship state
+    int32_t* G = nullptr;          // [g_pad x g_pad]
+    int64_t g_pad = 0;
+    bool g_zero = true;
+    int8_t* pack = nullptr;        // packed K-major operand of one chunk
+    int64_t pack_bytes = 0;
+    void* tiles_d = nullptr;       // tile table
+    int64_t tiles_bytes = 0;
+    int* flag_d = nullptr;         // device error flag
+
+    // scratch
+    void* scratch = nullptr;
+    int64_t scratch_bytes = 0;
+};
+
+namespace mmg {
+
+extern thread_local std::string g_create_error;
+
+inline int fail(mmg_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define MMG_CUDA(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return mmg::fail(ctx, e__ == cudaErrorMemoryAllocation ? MMG_EOOM : MMG_ECUDA, "%s:%d %s: %s", \
+                             __FILE__, __LINE__, #call, cudaGetErrorString(e__));                        \
+    } while (0)
+#define MMG_CUBLAS(ctx, call)                                                                            \
+    do {                                                                                                 \
+        cublasStatus_t s__ = (call);                                                                     \
+        if (s__ != CUBLAS_STATUS_SUCCESS)                                                                \
+            return mmg::fail(ctx, MMG_ECUBLAS, "%s:%d %s: cublas status %d", __FILE__, __LINE__, #call, (int)s__); \
+    } while (0)
+#define MMG_CUSOLVER(ctx, call)                                                                          \
+    do {                                                                                                 \
+        cusolverStatus_t s__ = (call);                                                                   \
+        if (s__ != CUSOLVER_STATUS_SUCCESS)                                                              \
+            return mmg::fail(ctx, MMG_ECUSOLVER, "%s:%d %s: cusolver status %d", __FILE__, __LINE__, #call, (int)s__); \
+    } while (0)
+#define MMG_CHECK(ctx, cond, ...)                                      \
+    do {                                                               \
+        if (!(cond)) return mmg::fail(ctx, MMG_EBADARG, __VA_ARGS__);  \
+    } while (0)
+#define MMG_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != MMG_OK) return rc__; \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// accumulates CUDA-event time of a stage; synchronises the stream at stop()
+struct StageTimer {
+    mmg_ctx* ctx;
+    const char* name;
+    bool running;
+    StageTimer(mmg_ctx* c, const char* nm) : ctx(c), name(nm), running(true) { cudaEventRecord(c->ev0, c->stream); }
+    void stop() {
+        if (!running) return;
+        running = false;
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        MmgTimer& t = ctx->timers[name];
+        t.seconds += ms * 1e-3;
+        t.calls += 1;
+    }
+    ~StageTimer() { stop(); }
+};
+
+}  // namespace mmg

@@ -1,0 +1,314 @@
+// Stage 1 support kernels: genotype packing for the tensor-core Gram, a SIMT (dp4a) Gram used as the
+// independent cross-check of the tcgen05 kernel, the FP64 finalisation of kinship.py:50-55, scale_k
+// (kinship.py:94-100) and the per-SNP standardisation of the IBD kinship (kinship.py:66).
+#pragma once
+#include <cstdint>
+
+namespace mmg {
+
+// ---------------------------------------------------------------------------------------------------
+// pack: SNP-major genotypes [m x pitch] int8  ->  individual-major, K-major operand P [n x p_pitch] int8
+//   binary : P[i][s]              = 2 x - 1                       (kinship.py:43)
+//   diploid: P[i][32 t + j]       = [x >= 1]  (j < 16)            thermometer planes; any fixed
+//            P[i][32 t + 16 + j]  = [x >= 2]                       permutation of K is a valid Gram operand
+//            for SNP s = 16 t + j
+// Tile = 128 SNPs x 64 individuals; 4x4 byte blocks are transposed in registers (PRMT), staged through a
+// 16-byte-chunk XOR-swizzled shared tile, and written back as coalesced 16-byte vectors.
+// SNPs beyond s_count pack to 0 bytes.  Values outside the coding's domain raise *bad_flag.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bytes_lt_mask(int first_idx, int nvalid) {
+    // 0xff in byte b iff first_idx + b < nvalid
+    uint32_t m = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if (first_idx + b < nvalid) m |= 0xffu << (8 * b);
+    return m;
+}
+
+template <int CODING>
+__global__ void __launch_bounds__(256) pack_kmajor_kernel(const int8_t* __restrict__ snps, int64_t pitch,
+                                                          int64_t s_begin, int64_t s_count, int n,
+                                                          int8_t* __restrict__ P, int64_t p_pitch,
+                                                          int* __restrict__ bad_flag) {
+    __shared__ __align__(16) uint32_t tile[64][32];    // [individual][128 SNP bytes as 32 words]
+    const int t = threadIdx.x;
+    const int64_t s0 = (int64_t)blockIdx.x * 128;
+    const int i0 = blockIdx.y * 64;
+    const int i4 = t & 15, sq = t >> 4;
+    bool bad = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int quad = sq + 16 * h;                  // 4 consecutive SNPs
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t s = s0 + 4 * quad + j;
+            r[j] = (s < s_count) ? *reinterpret_cast<const uint32_t*>(snps + (s_begin + s) * pitch + i0 + 4 * i4) : 0u;
+            const uint32_t maxv = (CODING == 0) ? 0x01010101u : 0x02020202u;
+            bad |= (__vcmpgtu4(r[j], maxv) != 0u);
+        }
+        const uint32_t t0 = __byte_perm(r[0], r[1], 0x5140), t1 = __byte_perm(r[2], r[3], 0x5140);
+        const uint32_t t2 = __byte_perm(r[0], r[1], 0x7362), t3 = __byte_perm(r[2], r[3], 0x7362);
+        uint32_t w[4];
+        w[0] = __byte_perm(t0, t1, 0x5410);
+        w[1] = __byte_perm(t0, t1, 0x7632);
+        w[2] = __byte_perm(t2, t3, 0x5410);
+        w[3] = __byte_perm(t2, t3, 0x7632);
+        const int pchunk = (quad >> 2) ^ (i4 & 7);
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) tile[4 * i4 + ii][pchunk * 4 + (quad & 3)] = w[ii];
+    }
+    if (bad) atomicOr(bad_flag, 1);
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int u = t + 256 * h;
+        const int row = u >> 3, c = u & 7;             // 16 SNPs s0 + 16c ..
+        const int i = i0 + row;
+        if (i >= n) continue;
+        const int pchunk = c ^ ((row >> 2) & 7);
+        const uint4 x = *reinterpret_cast<const uint4*>(&tile[row][pchunk * 4]);
+        int64_t rem = s_count - (s0 + 16 * c);
+        const int nvalid = rem < 0 ? 0 : (rem > 16 ? 16 : (int)rem);
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+        if (CODING == 0) {
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                o[k] = __vsub4(__vadd4(xs[k], xs[k]), 0x01010101u) & bytes_lt_mask(4 * k, nvalid);
+            *reinterpret_cast<uint4*>(P + (int64_t)i * p_pitch + s0 + 16 * c) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t m = bytes_lt_mask(4 * k, nvalid);
+                a[k] = __vcmpgeu4(xs[k], 0x01010101u) & 0x01010101u & m;
+                b[k] = __vcmpgeu4(xs[k], 0x02020202u) & 0x01010101u & m;
+            }
+            int8_t* dst = P + (int64_t)i * p_pitch + 2 * (s0 + 16 * c);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(a[0], a[1], a[2], a[3]);
+            *reinterpret_cast<uint4*>(dst + 16) = make_uint4(b[0], b[1], b[2], b[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SIMT Gram on the packed operand: G[i][j] (+)= sum_k P[i][k] P[j][k] for tiles with bj >= bi, by dp4a.
+// 64 x 64 outputs per block, 4 x 4 per thread.  Slow (CUDA-core) but independent of the tcgen05 path.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_simt_kernel(const int8_t* __restrict__ P, int64_t p_pitch, int n,
+                                                        int64_t kbytes, int32_t* __restrict__ G, int64_t ldg,
+                                                        int accumulate) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    __shared__ uint32_t As[64][17], Bs[64][17];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    int acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0;
+    for (int64_t k0 = 0; k0 < kbytes; k0 += 64) {
+        {
+            const int row = t >> 2, q = t & 3;        // 64 rows x 4 chunks of 16 B
+            uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+            if (k0 + 16 * q < kbytes) {               // p_pitch is padded to 128 and zero filled
+                if (bi * 64 + row < n) va = *reinterpret_cast<const uint4*>(P + (int64_t)(bi * 64 + row) * p_pitch + k0 + 16 * q);
+                if (bj * 64 + row < n) vb = *reinterpret_cast<const uint4*>(P + (int64_t)(bj * 64 + row) * p_pitch + k0 + 16 * q);
+            }
+            As[row][4 * q + 0] = va.x; As[row][4 * q + 1] = va.y; As[row][4 * q + 2] = va.z; As[row][4 * q + 3] = va.w;
+            Bs[row][4 * q + 0] = vb.x; Bs[row][4 * q + 1] = vb.y; Bs[row][4 * q + 2] = vb.z; Bs[row][4 * q + 3] = vb.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kw = 0; kw < 16; ++kw) {
+            int a[4], b[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = (int)As[4 * ty + r][kw];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) b[c] = (int)Bs[4 * tx + c][kw];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = __dp4a(a[r], b[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = bi * 64 + 4 * ty + r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = bj * 64 + 4 * tx + c;
+            int32_t* g = G + (int64_t)i * ldg + j;     // G is padded to a multiple of 256: in range
+            *g = accumulate ? (*g + acc[r][c]) : acc[r][c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// finalize (kinship.py:50-53): reads the upper triangle of the integer Gram
+// ---------------------------------------------------------------------------------------------------
+template <int CODING>
+__global__ void kinship_finalize_kernel(const int32_t* __restrict__ G, int64_t ldg, int n, double m_total,
+                                        double* __restrict__ K, int64_t ldk) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= n) return;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const double g = (double)G[(int64_t)lo * ldg + hi];
+    double k;
+    if (CODING == 0) {
+        k = g / (2.0 * m_total) + 0.5;                                   // :53
+    } else {
+        if (i == j) {
+            k = 1.0;                                                     // :35 never fills the diagonal; 0/m + 1
+        } else {
+            const double l1 = (double)G[(int64_t)i * ldg + i] + (double)G[(int64_t)j * ldg + j] - 2.0 * g;
+            const double cnt = m_total - 0.5 * l1;                       // count0 + 0.5 count1 (:38)
+            const float q = (float)cnt / (float)m_total;                 // float32 quotient (:51)
+            k = (double)q;
+        }
+    }
+    K[(int64_t)i * ldk + j] = k;
+}
+
+// mirror the upper triangle of the integer Gram into the lower one (for downloads)
+__global__ void gram_mirror_kernel(int32_t* __restrict__ G, int64_t ldg, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= n || j >= i) return;
+    G[(int64_t)i * ldg + j] = G[(int64_t)j * ldg + i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scale_k (kinship.py:94-100): row sums + diagonal, then a single-block final reduction (deterministic)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rowsum_kernel(const double* __restrict__ K, int64_t ldk, int n,
+                                                     double* __restrict__ rowsum) {
+    __shared__ double red[8];
+    const int i = blockIdx.x;
+    double s = 0.0;
+    for (int j = threadIdx.x; j < n; j += 256) s += K[(int64_t)i * ldk + j];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tsum = 0.0;
+        for (int w = 0; w < 8; ++w) tsum += red[w];
+        rowsum[i] = tsum;
+    }
+}
+// out[0] = sum(rowsum), out[1] = trace
+__global__ void __launch_bounds__(1024) scale_k_reduce_kernel(const double* __restrict__ rowsum,
+                                                              const double* __restrict__ K, int64_t ldk, int n,
+                                                              double* __restrict__ out) {
+    __shared__ double red[2][32];
+    double s = 0.0, tr = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        s += rowsum[i];
+        tr += K[(int64_t)i * ldk + i];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = tr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 32; ++w) { a += red[0][w]; b += red[1][w]; }
+        out[0] = a;
+        out[1] = b;
+    }
+}
+__global__ void scale_matrix_kernel(double* __restrict__ A, int64_t ld, int rows, int cols, double alpha) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j < cols && i < rows) A[(int64_t)i * ld + j] *= alpha;
+}
+__global__ void scale_rows_kernel(double* __restrict__ A, int64_t ld, int rows, int cols, const double* __restrict__ d) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j < cols && i < rows) A[(int64_t)i * ld + j] *= d[i];
+}
+__global__ void add_diag_kernel(double* __restrict__ A, int64_t ld, int n, double alpha) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(int64_t)i * ld + i] += alpha;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-SNP sums (int64) over individuals; one warp per row
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) snp_row_sums_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t m,
+                                                           int n, long long* __restrict__ sums,
+                                                           long long* __restrict__ sumsq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= m) return;
+    const int8_t* x = snps + row * pitch;
+    int s = 0, q = 0;
+    for (int i0 = lane * 16; i0 < n; i0 += 512) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + i0);     // zero padded beyond n
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s = __dp4a((int)w[k], 0x01010101, s);
+            q = __dp4a((int)w[k], (int)w[k], q);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+        sums[row] = s;
+        if (sumsq) sumsq[row] = q;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// IBD standardisation (kinship.py:66 / hdf5_data.py:50,103): z = (x - mean) / std, ddof = 0, two-pass.
+// One block per selected SNP; rows[] lists the resident row indices.  Z is [count x ldz] FP64.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) standardise_rows_kernel(const int8_t* __restrict__ snps, int64_t pitch,
+                                                               const long long* __restrict__ rows, int n,
+                                                               double* __restrict__ Z, int64_t ldz,
+                                                               int* __restrict__ bad_flag) {
+    __shared__ double red[8];
+    __shared__ double bc[2];
+    const int8_t* x = snps + rows[blockIdx.x] * pitch;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += (double)x[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tsum = 0.0;
+        for (int w = 0; w < 8; ++w) tsum += red[w];
+        bc[0] = tsum / (double)n;
+    }
+    __syncthreads();
+    const double mean = bc[0];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double d = (double)x[i] - mean;
+        v += d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tsum = 0.0;
+        for (int w = 0; w < 8; ++w) tsum += red[w];
+        bc[1] = sqrt(tsum / (double)n);
+        if (!(bc[1] > 0.0)) atomicOr(bad_flag, 1);
+    }
+    __syncthreads();
+    const double sd = bc[1];
+    double* z = Z + (int64_t)blockIdx.x * ldz;
+    for (int i = threadIdx.x; i < n; i += 256) z[i] = ((double)x[i] - mean) / sd;
+}
+
+}  // namespace mmg

@@ -1,0 +1,107 @@
+"""
+Drop-in for mixmogam's `kinship` module, hot-path subset (reference kinship.py):
+
+    calc_ibs_kinship(snps, snps_data_format='binary', snp_dtype='int8', dtype='single',
+                     chunk_size=None, scaled=True)                          kinship.py:14-56
+    calc_ibd_kinship(snps, dtype='single', scaled=True)                     kinship.py:59-75
+    scale_k(k, verbose=False)                                               kinship.py:94-100
+
+Same names, argument meaning and return types; the arithmetic runs on the B200 through
+libmixmogam_b200 (no CPU fallback):
+  * IBS: the contraction over SNPs is an int8 tensor-core Gram (tcgen05.mma kind::i8, int32
+    accumulators) of the 2x-1 coded ('binary') or thermometer coded ('diploid_int') genotypes; the
+    unscaled kinship is bit-identical to the reference's float64 / float32-quotient result.
+  * IBD: per-SNP standardisation kernel + FP64 accumulation (the reference accumulates in float32).
+`dtype`, `snp_dtype` and `chunk_size` are accepted for signature compatibility; results are float64
+(which is also what the reference returns: kinship.py:44,51 promote to float64).
+"""
+import numpy as np
+
+from . import _lib
+
+__all__ = ['calc_ibs_kinship', 'calc_ibd_kinship', 'scale_k', 'calc_ibs_kinship_device', 'partial_ibs_gram']
+
+
+def _coding(snps_data_format):
+    if snps_data_format == 'binary':
+        return _lib.CODING_BINARY
+    if snps_data_format == 'diploid_int':
+        return _lib.CODING_DIPLOID
+    raise NotImplementedError          # kinship.py:45-46
+
+
+def calc_ibs_kinship_device(snps, snps_data_format='binary', scaled=True, impl='auto', ctx=None):
+    """As calc_ibs_kinship but leaves K on the device (returns a DeviceMatrix)."""
+    ctx = ctx or _lib.get_context()
+    coding = _coding(snps_data_format)
+    m, n = ctx.ensure_snps(snps)
+    ctx.kinship_gram(coding, impl=impl, reset=True)
+    K, _ = ctx.kinship_finalize(coding, m, scaled)
+    return K
+
+
+def calc_ibs_kinship(snps, snps_data_format='binary', snp_dtype='int8', dtype='single',
+                     chunk_size=None, scaled=True, impl='auto', ctx=None):
+    """
+    Calculates IBS kinship (kinship.py:14-56).
+
+    data_format: 'binary' (0/1 genotypes) and 'diploid_int' (0/1/2) are supported.
+    Returns an np.matrix for 'binary' and an ndarray for 'diploid_int', float64, as the reference does.
+    """
+    K = calc_ibs_kinship_device(snps, snps_data_format, scaled, impl, ctx)
+    k_mat = K.download()
+    K.free()
+    if snps_data_format == 'binary':
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', PendingDeprecationWarning)
+            return np.asmatrix(k_mat)       # kinship.py:43-44: sm is a matrix, so is the result
+    return k_mat
+
+
+def partial_ibs_gram(snps, snps_data_format='binary', impl='auto', ctx=None, reset=True):
+    """Multi-GPU building block: integer Gram of this rank's SNP slice, left resident for an int32
+    all-reduce (see mixmogam_b200.parallel).  Returns (device_ptr, n, ld)."""
+    ctx = ctx or _lib.get_context()
+    ctx.ensure_snps(snps)
+    ctx.kinship_gram(_coding(snps_data_format), impl=impl, reset=reset)
+    return ctx.kinship_gram_ptr()
+
+
+def calc_ibd_kinship(snps, dtype='single', scaled=True, ctx=None):
+    """kinship.py:59-75.  A monomorphic SNP raises AssertionError like the reference's `assert` (:67)."""
+    ctx = ctx or _lib.get_context()
+    m, n = ctx.ensure_snps(snps)
+    K = ctx.matrix(n, n)
+    try:
+        ctx.kinship_ibd_accumulate(K, 0, m)
+    except _lib.MmgError as e:
+        if e.code == -7:
+            raise AssertionError('WTF?')    # kinship.py:67
+        raise
+    k_mat = K.download()
+    K.free()
+    k_mat = k_mat / float(m)                # :72
+    if scaled:
+        k_mat = scale_k(k_mat, ctx=ctx)
+    return k_mat
+
+
+def scale_k(k, verbose=False, ctx=None):
+    """kinship.py:94-100: K * (n-1) / (tr K - sum(K)/n), evaluated on the device."""
+    ctx = ctx or _lib.get_context()
+    is_matrix = isinstance(k, np.matrix)
+    if isinstance(k, _lib.LazyHostArray):
+        k = k.host()
+    K = _lib.DeviceMatrix.from_host(ctx, np.asarray(k, dtype=np.float64))
+    scalar = ctx.scale_k(K)
+    if verbose:
+        print('Kinship scaled by: %0.4f' % scalar)
+    out = K.download()
+    K.free()
+    if is_matrix:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', PendingDeprecationWarning)
+            return np.asmatrix(out)
+    return out

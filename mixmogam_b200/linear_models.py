@@ -1,0 +1,619 @@
+"""
+Drop-in for the EMMAX path of mixmogam's `linear_models` module (reference linear_models.py):
+
+    LinearMixedModel(Y, dtype='single')                                      :558
+        .add_factor / .set_factors                                           :98-130
+        .add_random_effect(cov_matrix)                                       :577
+        ._get_eigen_L_(K=None) / ._get_eigen_R_(X=None, K=None)              :589 / :600
+        ._rell_ / ._redll_                                                   :618 / :626
+        .get_REML(ngrids=100, llim=-10, ulim=10, esp=1e-6, eig_L, eig_R)     :653
+        .get_estimates(eig_L, K, xs, ngrids=50, ..., method='REML', eig_R)   :771
+        .expedited_REML_t_test(snps, ...)                                    :931
+        .emmax_f_test(snps, snp_priors, Z, with_betas, method, eig_L, eig_R, emma_num=100)   :1233
+        ._emmax_f_test_(snps, H_sqrt_inv, ...)                               :1272
+        ._emmax_permutations_(snps, K, H_sqrt_inv, num_perm=100)             :1125
+    emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_num=0)          :1790
+    emma(snps, phenotypes, K, cofactors=None)                                :1725
+    get_emma_reml_estimates(y, K, ...)                                       :1690 (single-K form)
+
+Same names, arguments, defaults, returned dict keys and error behaviour.  The n x n objects (K, the
+eigenbases, H_sqrt_inv, M) live in HBM; the three stages run in hand-written sm_100a kernels behind
+libmixmogam_b200 (no CPU fallback).  All device arithmetic is float64, i.e. the reference's algebra at
+higher precision than its hard-coded float32 (`dtype='single'`, :558,:589,:600,:773,:1283);
+the `dtype` arguments are accepted and ignored.
+
+Known, deliberate differences from the reference (each covered by a test):
+  * eig_R is computed once per model, not recomputed inside get_estimates (:787 always recomputes it;
+    the values are identical).
+  * `vg`/`ve` reproduce the reference's (p,1)/(p,) broadcast at :894-896 in closed form:
+    vg = sum(sq_etas) * sum(1/(lambda+delta)) / p.
+  * eigenvectors are defined up to sign (cuSOLVER vs LAPACK): compare H'H, not H.
+"""
+import time
+import warnings
+
+import numpy as np
+
+from . import _lib
+from . import kinship
+from ._lib import DeviceMatrix, LazyHostArray
+
+__all__ = ['LinearModel', 'LinearMixedModel', 'emmax', 'emma', 'get_emma_reml_estimates']
+
+_VERBOSE = False
+
+
+def _say(*a):
+    if _VERBOSE:
+        print(*a)
+
+
+def _is_none(x):
+    return x is None
+
+
+def _col(x, n):
+    a = np.asarray(x, dtype=np.float64)
+    return a.reshape(n, -1) if a.ndim != 2 or a.shape[0] != n else a
+
+
+class _LazyIdentity(object):
+    """random_effects[0][1] of the reference is a dense identity (linear_models.py:574); keep it lazy."""
+
+    def __init__(self, n):
+        self.n = n
+        self.shape = (n, n)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.identity(self.n, dtype=dtype or np.float64)
+
+
+class LinearModel(object):
+    """linear_models.py:81-130 (the parts LinearMixedModel inherits on the EMMAX path)."""
+
+    def __init__(self, Y=None):
+        self.n = len(Y)
+        self.Y = np.asarray(Y, dtype=np.float64).reshape(self.n, 1)
+        self.X = np.ones((self.n, 1))
+        self.p = 1
+        self.beta_est = None
+        self.cofactors = []
+
+    def add_factor(self, x, lin_depend_thres=1e-8):
+        """linear_models.py:98-113."""
+        new_x = np.array(x, dtype=np.float64)
+        new_x.shape = len(x)
+        (beta, rss, rank, sigma) = np.linalg.lstsq(self.X, new_x, rcond=None)
+        rss_v = float(rss[0]) if np.size(rss) else float(np.sum((new_x - self.X @ beta) ** 2))
+        if rss_v < lin_depend_thres:
+            warnings.warn('A factor was found to be linearly dependent on the factors already in the X matrix.  Hence skipping it!')
+            return False
+        new_x.shape = (self.n, 1)
+        self.X = np.hstack([self.X, new_x])
+        self.cofactors.append(x)
+        self.p += 1
+        self._invalidate()
+        return True
+
+    def set_factors(self, factors, include_intercept=True):
+        """linear_models.py:116-130."""
+        self.p = 0
+        if include_intercept:
+            self.X = np.ones((self.n, 1))
+            self.p = 1
+            if len(factors) > 0:
+                self.X = np.hstack([self.X, np.asarray(factors, dtype=np.float64).T])
+            self.p += len(factors)
+        else:
+            self.X = np.asarray(factors, dtype=np.float64).T
+            self.p = len(factors)
+        self._invalidate()
+
+    def _invalidate(self):
+        pass
+
+
+class EigenDict(dict):
+    """{'values', 'vectors'} as the reference returns (linear_models.py:596,615), eigenvectors as ROWS.
+    'vectors' is a LazyHostArray: it stays in HBM until someone asks for the numbers."""
+    pass
+
+
+class LinearMixedModel(LinearModel):
+    """
+    A class for linear mixed models (linear_models.py:554).
+    """
+
+    def __init__(self, Y=None, dtype='single', ctx=None, scan_impl='auto'):
+        self.ctx = ctx or _lib.get_context()
+        self.scan_impl = scan_impl
+        self.n = len(Y)
+        self.y_var = np.var(Y, ddof=1)
+        self.Y = np.array(Y, dtype=np.float64).reshape(self.n, 1)
+        self.X = np.ones((self.n, 1))
+        self.p = 1
+        self.beta_est = None
+        self.cofactors = []
+        # A list of random effect type, and the cov matrix.  The first random effect is the IID error.
+        self.random_effects = [('normal', _LazyIdentity(self.n))]
+        self._K_dev = []
+        self._eig_R_cache = None
+
+    def _invalidate(self):
+        self._eig_R_cache = None
+
+    # ------------------------------------------------------------------------------------------
+    def add_random_effect(self, cov_matrix=None, effect_type='normal'):
+        """linear_models.py:577-580: stores kinship.scale_k(cov_matrix)."""
+        if effect_type != 'normal':
+            raise Exception('Currently, only Normal random effects are allowed.')
+        if isinstance(cov_matrix, DeviceMatrix):
+            K = cov_matrix.copy()
+        else:
+            K = self.ctx.to_device(cov_matrix)
+            if isinstance(cov_matrix, LazyHostArray):
+                K = K.copy()
+        if K.shape != (self.n, self.n):
+            raise ValueError('kinship must be %d x %d' % (self.n, self.n))
+        self.ctx.scale_k(K)
+        self._K_dev.append(K)
+        self.random_effects.append((effect_type, LazyHostArray(K)))
+        self._invalidate()
+
+    def set_random_effect(self, cov_matrix_list, effect_types=None):
+        """linear_models.py:583-586."""
+        self.random_effects = [('normal', _LazyIdentity(self.n))]
+        self._K_dev = []
+        for cov_matrix in cov_matrix_list:
+            self.add_random_effect(cov_matrix=kinship.scale_k(np.asarray(cov_matrix), ctx=self.ctx))
+
+    def _K_device(self, K=None):
+        if _is_none(K):
+            return self._K_dev[0]
+        return self.ctx.to_device(K)
+
+    # ------------------------------------------------------------------------------------------
+    def _get_eigen_L_(self, K=None, dtype='single'):
+        """linear_models.py:589-596: eigh(K); 'vectors' holds the eigenvectors as rows."""
+        Kd = self._K_device(K)
+        U = Kd.copy()
+        w = self.ctx.syevd(U)
+        return EigenDict(values=w, vectors=LazyHostArray(U))
+
+    def _get_eigen_R_(self, X=None, K=None, hat_matrix=None, dtype='single'):
+        """linear_models.py:600-615: eigh(S(K+I)S), S = I - X(X'X)^+X'; drop the q smallest; values - 1."""
+        if _is_none(X):
+            X = self.X
+        X = np.asarray(X, dtype=np.float64)
+        q = X.shape[1]
+        ctx = self.ctx
+        Kd = self._K_device(K)
+        A = Kd.copy()
+        ctx.add_diag(A, 1.0)                                  # K + I   (:610)
+        # S A S = A - X(G B') - (B G)X' + X(G C G)X' with B = A X, C = X'B, G = (X'X)^+  -- rank-q updates
+        G = np.linalg.pinv(X.T @ X)                           # :605
+        Xd = DeviceMatrix.from_host(ctx, X)
+        B = ctx.gemm(A, Xd).download()                        # n x q
+        Cm = X.T @ B
+        left = DeviceMatrix.from_host(ctx, np.hstack([-X, -(B @ G), X @ (G @ Cm @ G)]))       # n x 3q
+        right = DeviceMatrix.from_host(ctx, np.hstack([B @ G.T, X, X]))                       # n x 3q
+        ctx.gemm(left, right, A, tb=True, beta=1.0)           # A += left right'
+        for t in (Xd, left, right):
+            t.free()
+        w = ctx.syevd(A)
+        eig_values = w[q:] - 1                                # :614
+        return EigenDict(values=eig_values, vectors=LazyHostArray(A, rows=(q, self.n)), _q=q)
+
+    def _rell_(self, delta, eig_vals, sq_etas):
+        """linear_models.py:618-623."""
+        num_eig_vals = len(eig_vals)
+        c_1 = 0.5 * num_eig_vals * (np.log(num_eig_vals / (2.0 * np.pi)) - 1)
+        v = eig_vals + delta
+        res = c_1 - 0.5 * (num_eig_vals * np.log(np.sum(np.asarray(sq_etas).flatten() / v)) + np.sum(np.log(v)))
+        return res
+
+    def _redll_(self, delta, eig_vals, sq_etas):
+        """linear_models.py:626-631."""
+        num_eig_vals = len(eig_vals)
+        v1 = eig_vals + delta
+        v2 = np.asarray(sq_etas).flatten() / v1
+        res = (num_eig_vals * np.sum(v2 / v1) / np.sum(v2) - np.sum(1.0 / v1))
+        return res
+
+    # ------------------------------------------------------------------------------------------
+    def get_REML(self, ngrids=100, llim=-10, ulim=10, esp=1e-6, eig_L=None, eig_R=None):
+        """
+        Get REML estimates for the effect sizes, as well as the random effect contributions.
+        This is EMMA (linear_models.py:653-668).
+        """
+        if not eig_L:
+            eig_L = self._get_eigen_L_(None)
+        res = self.get_estimates(eig_L, ngrids=ngrids, llim=llim, ulim=ulim, esp=esp, method='REML', eig_R=eig_R)
+        res['eig_L'] = eig_L
+        return res
+
+    def _etas(self, eig_R, Y):
+        """etas = eig_R['vectors'] * Y (:794) with the eigenbasis resident in HBM."""
+        ctx = self.ctx
+        vec = eig_R['vectors']
+        Yd = DeviceMatrix.from_host(ctx, Y)
+        if isinstance(vec, LazyHostArray):
+            full = ctx.gemm(vec.dev, Yd).download()
+            r = vec._rows
+            etas = full if r is None else full[r[0]:r[1]]
+        else:
+            Ud = DeviceMatrix.from_host(ctx, np.asarray(vec, dtype=np.float64))
+            etas = ctx.gemm(Ud, Yd).download()
+            Ud.free()
+        Yd.free()
+        return etas
+
+    def get_estimates(self, eig_L, K=None, xs=None, ngrids=50, llim=-10, ulim=10, esp=1e-6,
+                      return_pvalue=False, return_f_stat=False, method='REML', verbose=False,
+                      dtype='single', eig_R=None, rss_0=None):
+        """
+        Get REML estimates for the effect sizes, as well as the random effect contributions, using the
+        EMMA algorithm (Kang et al., Genetics, 2008)  -- linear_models.py:771-927, REML branch.
+        """
+        if method != 'REML':
+            raise NotImplementedError("mixmogam_b200 implements method='REML' (the EMMAX path); 'ML' is outside it")
+        if xs is not None:
+            xs = _col(xs, self.n)
+            X = np.hstack([self.X, xs])
+        else:
+            X = self.X
+        if not eig_R or xs is not None:
+            if xs is None and self._eig_R_cache is not None and _is_none(K):
+                eig_R = self._eig_R_cache
+            else:
+                eig_R = self._get_eigen_R_(X=X, K=K)
+                if xs is None and _is_none(K):
+                    self._eig_R_cache = eig_R
+        q = X.shape[1]
+        n = self.n
+        p = n - q
+        m = ngrids + 1
+
+        etas = self._etas(eig_R, self.Y)                                       # :794
+        sq_etas = etas * etas
+        log_deltas = (np.arange(m, dtype=np.float64) / ngrids) * (ulim - llim) + llim      # :796
+        deltas = np.exp(log_deltas)
+        assert len(deltas) == m, 'Number of deltas is incorrect.'
+        eig_vals = np.array(eig_R['values'], dtype=np.float64)
+        assert len(eig_vals) == p, 'Number of eigenvalues is incorrect.'
+
+        r = self.ctx.reml(eig_vals, sq_etas.T, deltas, esp)                    # :802-891 on the device
+        opt_delta = float(r['delta'][0])
+        opt_ll = float(r['ll'][0])
+
+        # :894-896 -- the reference divides a (p,1) by a (p,) array: a p x p outer quotient
+        opt_vg = float(np.sum(sq_etas) * np.sum(1.0 / (eig_vals + opt_delta)) / p)
+        opt_ve = opt_vg * opt_delta
+
+        # H_sqrt_inv = diag(1/sqrt(eig_L.values + delta)) eig_L.vectors   (:898)
+        ctx = self.ctx
+        UL = ctx.to_device(eig_L['vectors'])
+        H = UL.copy()
+        ctx.scale_rows(H, 1.0 / np.sqrt(np.asarray(eig_L['values'], dtype=np.float64) + opt_delta))
+        XY = DeviceMatrix.from_host(ctx, np.hstack([X, self.Y]))
+        t = ctx.gemm(H, XY).download()
+        XY.free()
+        X_t, Y_t = t[:, :q], t[:, q:]
+        (beta_est, mahalanobis_rss, rank, sigma) = np.linalg.lstsq(X_t, Y_t, rcond=None)
+        if np.size(mahalanobis_rss) == 0:
+            mahalanobis_rss = np.array([np.sum((Y_t - X_t @ beta_est) ** 2)])
+        x_beta = X @ beta_est
+        residuals = self.Y - x_beta
+        rss = residuals.T @ residuals
+        res_dict = {'max_ll': opt_ll, 'delta': opt_delta, 'beta': beta_est, 've': opt_ve, 'vg': opt_vg,
+                    'rss': rss, 'mahalanobis_rss': mahalanobis_rss, 'H_sqrt_inv': LazyHostArray(H),
+                    'pseudo_heritability': 1.0 / (1 + opt_delta)}
+        self._last_reml = {'lls': r['lls'][0], 'dlls': r['dlls'][0], 'deltas': deltas, 'flags': int(r['flags'][0]),
+                           'eig_R': eig_R}
+
+        if xs is not None and return_f_stat:
+            h0_X = X_t[:, :self.X.shape[1]]
+            (h0_betas, h0_rss, h0_rank, h0_s) = np.linalg.lstsq(h0_X, Y_t, rcond=None)
+            f_stat = (h0_rss / mahalanobis_rss - 1) * p / xs.shape[1]
+            res_dict['var_perc'] = 1.0 - mahalanobis_rss / h0_rss
+            res_dict['f_stat'] = float(np.asarray(f_stat).reshape(-1)[0])
+        if return_pvalue:
+            p_val = ctx.f_sf(np.array([res_dict['f_stat']]), xs.shape[1], p)
+            res_dict['p_val'] = float(p_val[0])
+        return res_dict
+
+    def expedited_REML_t_test(self, snps, ngrids=50, llim=-4, ulim=10, esp=1e-6, verbose=True, eig_L=None):
+        """
+        Single SNP analysis, i.e. EMMA (linear_models.py:931-968): one REML fit, hence one n x n
+        eigendecomposition of S(K+I)S, per SNP.
+        """
+        assert len(self.random_effects) == 2, "Expedited REMLE only works when we have exactly two random effects."
+        if _is_none(eig_L):
+            eig_L = self._get_eigen_L_(None)
+        num_snps = len(snps)
+        f_stats = np.empty(num_snps)
+        vgs = np.empty(num_snps)
+        ves = np.empty(num_snps)
+        max_lls = np.empty(num_snps)
+        var_perc = np.empty(num_snps)
+        rss_list = np.empty(num_snps)
+        betas = []
+        p_vals = np.empty(num_snps)
+        for i, snp in enumerate(snps):
+            res = self.get_estimates(eig_L=eig_L, xs=np.asarray(snp, dtype=np.float64).reshape(-1, 1), ngrids=ngrids,
+                                     llim=llim, ulim=ulim, esp=esp, return_pvalue=True, return_f_stat=True)
+            f_stats[i] = res['f_stat']
+            vgs[i] = res['vg']
+            ves[i] = res['ve']
+            max_lls[i] = res['max_ll']
+            var_perc[i] = np.asarray(res['var_perc']).reshape(-1)[0]
+            betas.append(list(map(float, list(np.asarray(res['beta']).reshape(-1)))))
+            p_vals[i] = res['p_val']
+            rss_list[i] = np.asarray(res['rss']).reshape(-1)[0]
+            res['H_sqrt_inv'].dev.free()
+        return {'ps': p_vals, 'f_stats': f_stats, 'vgs': vgs, 'ves': ves, 'var_perc': var_perc,
+                'max_lls': max_lls, 'betas': betas, 'rss': rss_list}
+
+    # ------------------------------------------------------------------------------------------
+    def emmax_f_test(self, snps, snp_priors=None, Z=None, with_betas=False, method='REML',
+                     eig_L=None, eig_R=None, emma_num=100):
+        """
+        EMMAX implementation, single SNPs (linear_models.py:1233-1267).
+        """
+        if not eig_L:
+            _say('Calculating the eigenvalues of K')
+            s0 = time.time()
+            eig_L = self._get_eigen_L_()
+            _say('Done.\nTook %0.2f seconds' % (time.time() - s0))
+        if not eig_R:
+            _say("Calculating the eigenvalues of S(K+I)S where S = I-X(X'X)^-1X'")
+            s0 = time.time()
+            eig_R = self._get_eigen_R_(X=self.X)
+            _say('Done\nTook %0.2f seconds' % (time.time() - s0))
+
+        _say('Getting variance estimates')
+        s0 = time.time()
+        res = self.get_estimates(eig_L, method=method, eig_R=eig_R)
+        _say('Done.\nTook %0.2f seconds' % (time.time() - s0))
+        _say('pseudo_heritability:', res['pseudo_heritability'])
+
+        s0 = time.time()
+        r = self._emmax_f_test_(snps, res['H_sqrt_inv'], snp_priors=snp_priors, Z=Z, with_betas=with_betas,
+                                emma_num=emma_num, eig_L=eig_L)
+        _say('Took %0.2f seconds' % (time.time() - s0))
+        r['pseudo_heritability'] = res['pseudo_heritability']
+        r['ve'] = res['ve']
+        r['vg'] = res['vg']
+        r['max_ll'] = res['max_ll']
+        return r
+
+    def _null_fit(self, H, Z=None, project=True):
+        """Set-up of _emmax_f_test_ (linear_models.py:1290-1306): null GLS fit in the rotated space and
+        the rotation R = M' = (I - QQ')H (or H with no projection), resident in HBM."""
+        ctx = self.ctx
+        n = self.n
+        q0 = self.X.shape[1]
+        XY = DeviceMatrix.from_host(ctx, np.hstack([self.X, self.Y]))
+        t = ctx.gemm(H, XY).download()
+        XY.free()
+        h0_X, Y = t[:, :q0], t[:, q0:]
+        (h0_betas, h0_rss, h0_rank, h0_s) = np.linalg.lstsq(h0_X, Y, rcond=None)
+        Yres = Y - h0_X @ h0_betas
+        if np.size(h0_rss) == 0:
+            h0_rss = np.array([np.sum(Yres ** 2)])
+        Hz = H
+        if Z is not None:
+            Zd = DeviceMatrix.from_host(ctx, np.asarray(Z, dtype=np.float64))
+            Hz = ctx.gemm(H, Zd)                              # :1297  H <- H Z
+            Zd.free()
+        if project:
+            (Q, Rq) = np.linalg.qr(h0_X)                      # :1300
+            Qd = DeviceMatrix.from_host(ctx, Q)
+            QtH = ctx.gemm(Qd, Hz, ta=True)                   # q0 x n
+            Rm = Hz.copy() if Hz is H else Hz
+            ctx.gemm(Qd, QtH, Rm, alpha=-1.0, beta=1.0)       # R = H - Q (Q'H)      (:1303, transposed)
+            Qd.free()
+            QtH.free()
+        else:
+            Rm = Hz                                           # :1306  M = H'
+        return {'h0_X': h0_X, 'h0_betas': h0_betas, 'h0_rss': h0_rss, 'Yres': Yres, 'R': Rm}
+
+    def _emmax_f_test_(self, snps, H_sqrt_inv, snp_priors=None, verbose=True, return_transformed_snps=False,
+                       Z=None, with_betas=False, emma_num=100, eig_L=None, **kwargs):
+        """
+        EMMAX implementation, single SNPs (linear_models.py:1272-1380).  The two hot loops (:1316-1339) --
+        the rotation GEMM and the per-SNP least squares -- and the F / p-value epilogue (:1345-1349) run
+        as one fused kernel over the resident genotypes.
+        """
+        ctx = self.ctx
+        q = 1  # Single SNP is being tested
+        p = len(self.X.T) + q
+        n = self.n
+        n_p = n - p
+        num_snps, n_lines = ctx.ensure_snps(snps)
+        H = ctx.to_device(H_sqrt_inv)
+        nf = self._null_fit(H, Z=Z, project=not with_betas)
+        h0_rss = nf['h0_rss']
+        h0_rss_f = float(np.asarray(h0_rss).reshape(-1)[0])
+        h0_betas = list(map(float, list(np.asarray(nf['h0_betas']).reshape(-1))))
+        Rm = nf['R']
+        if Rm.shape[1] != n_lines:
+            raise ValueError('SNP length %d does not match the model (%d)' % (n_lines, Rm.shape[1]))
+        impl = kwargs.get('impl', self.scan_impl)
+
+        if not with_betas:
+            out = ctx.emmax_scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
+            p_vals, f_stats, rss_list, var_perc = out['ps'], out['f_stats'], out['rss'], out['var_perc']
+        else:
+            # lstsq([h0_X, x~], Y) (:1323) through its normal equations: the kernel supplies
+            # xx = x~.x~, xy = x~.Yres, b = x~.h0_X; the (q0+1)x(q0+1) solve is a Schur complement per SNP.
+            h0_X, Yres = nf['h0_X'], nf['Yres']
+            V = np.vstack([Yres.T, h0_X.T])
+            out = ctx.emmax_scan(Rm, V, h0_rss_f, n_p, impl=impl, want_dots=True, want_stats=False)
+            xx, dots = out['xx'], out['dots']
+            xy, b = dots[:, 0], dots[:, 1:]
+            A = h0_X.T @ h0_X
+            c0 = (h0_X.T @ Yres).reshape(-1)
+            Ainv = np.linalg.inv(A)
+            Ab = b @ Ainv.T                                   # rows: A^-1 b_s
+            s = xx - np.einsum('ij,ij->i', b, Ab)
+            ok = s > 1e-12 * np.maximum(xx, 1e-300)
+            s_safe = np.where(ok, s, 1.0)
+            beta_x = (xy - Ab @ c0) / s_safe
+            beta_0 = (Ainv @ c0)[None, :] - Ab * beta_x[:, None]
+            yy = float(np.sum(Yres ** 2))
+            rss_full = yy - (beta_0 @ c0 + beta_x * xy)
+            good = ok & (rss_full != 0)
+            rss_list = np.where(good, rss_full, h0_rss_f)
+            betas_arr = np.hstack([beta_0, beta_x[:, None]])
+            betas_list = [list(map(float, row)) if g else h0_betas for row, g in zip(betas_arr, good)]
+            rss_ratio = h0_rss_f / rss_list
+            var_perc = 1 - 1 / rss_ratio
+            f_stats = (rss_ratio - 1) * n_p / float(q)
+            p_vals = ctx.f_sf(f_stats, q, n_p)
+
+        res_d = {'ps': p_vals, 'f_stats': f_stats, 'rss': rss_list, 'var_perc': var_perc,
+                 'h0_rss': h0_rss, 'h0_betas': h0_betas}
+        if with_betas:
+            res_d['betas'] = betas_list
+        if return_transformed_snps:
+            res_d['t_snps'] = self._transformed_snps(snps, Rm)
+        if snp_priors is not None:
+            snp_priors = np.array(snp_priors)
+            log_bfs = np.where(rss_list != h0_rss_f, np.log(h0_rss_f) - np.log(rss_list), 0.0)      # :1335
+            bfs = np.exp((log_bfs * n - np.log(n)) * 1 / 2)                                          # :1358
+            res_d['bfs'] = bfs
+            pos = bfs * snp_priors / (1 - snp_priors)
+            res_d['pos'] = pos
+            res_d['ppas'] = pos / (1 + pos)
+        if Rm is not H:
+            Rm.free()
+
+        if emma_num > 0:                                                                            # :1365-1377
+            pval_indices = sorted(zip(res_d['ps'], range(num_snps)))[:emma_num]
+            _say('Updating p-values using EMMA for the smallest %d p-values.' % len(pval_indices))
+            l = list(map(list, zip(*pval_indices)))
+            top_snps = [np.asarray(snps[pi]) for pi in l[1]]
+            top_emma_res = self.expedited_REML_t_test(top_snps, eig_L=eig_L)
+            for pi, pv, f, r, v in zip(l[1], top_emma_res['ps'], top_emma_res['f_stats'],
+                                       top_emma_res['rss'], top_emma_res['var_perc']):
+                res_d['ps'][pi] = pv
+                res_d['f_stats'][pi] = f
+                res_d['rss'][pi] = r
+                res_d['var_perc'][pi] = v
+        return res_d
+
+    def _transformed_snps(self, snps, Rm, chunk=4096):
+        """t_snps of :1320-1321: the rotated SNPs x~ = R x, materialised (small m only)."""
+        ctx = self.ctx
+        out = []
+        m = len(snps)
+        for s0 in range(0, m, chunk):
+            xc = DeviceMatrix.from_host(ctx, np.asarray(snps[s0:s0 + chunk], dtype=np.float64))
+            t = ctx.gemm(xc, Rm, tb=True).download()
+            xc.free()
+            out.extend(list(t))
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def _emmax_permutations_(self, snps, K, H_sqrt_inv, num_perm=100):
+        """
+        EMMAX permutation test, single SNPs (linear_models.py:1125-1175).  Returns the list of min p-values
+        and max F statistics.  Reference quirks kept: self.Y is mean-centred in place (:1140); the null fit
+        is subtracted twice (:1144,:1147); SNPs are centred and rotated by H' with no Q projection
+        (:1159-1160); the permuted phenotypes come from cumulative in-place np.random.shuffle calls on the
+        global legacy RNG (:1151-1154), so seeding np.random reproduces the reference's Ys.
+        """
+        ctx = self.ctx
+        q = 1
+        p = len(self.X.T) + q
+        n = self.n
+        n_p = n - p
+        if self.X.shape[1] != 1:
+            raise ValueError('the reference (:1147) only type-checks with a single fixed effect')
+        self.Y = self.Y - np.mean(self.Y)                                      # :1140
+        H = ctx.to_device(H_sqrt_inv)
+        XY = DeviceMatrix.from_host(ctx, np.hstack([self.X, self.Y]))
+        t = ctx.gemm(H, XY).download()
+        XY.free()
+        h0_X, Y = t[:, :1], t[:, 1:]
+        (h0_betas, h0_rss, h0_rank, h0_s) = np.linalg.lstsq(h0_X, Y, rcond=None)
+        Y = Y - h0_X @ h0_betas                                                # :1144
+        Y = Y - h0_X * float(h0_betas[0, 0])                                   # :1147
+        Ys = np.zeros((n, num_perm))
+        for perm_i in range(num_perm):
+            np.random.shuffle(Y)                                               # :1153
+            Ys[:, perm_i] = Y[:, 0]
+        h0_rss_f = float(np.asarray(h0_rss).reshape(-1)[0])
+
+        num_snps, n_lines = ctx.ensure_snps(snps)
+        # x~_c . Ys_p = x_c . (H' Ys_p): W' = Ys' H  ([P x n])
+        Ysd = DeviceMatrix.from_host(ctx, Ys)
+        Wt = ctx.gemm(Ysd, H, ta=True)
+        Ysd.free()
+        ratio = np.zeros(num_perm)
+        ctx.emmax_perm_scan(H, Wt, ratio, centre=True, impl=_lib.IMPL_DMMA)
+        Wt.free()
+        ynorm = np.sum(Ys * Ys, axis=0)
+        min_rss_list = np.minimum(np.repeat(h0_rss_f, num_perm), ynorm - ratio)      # :1156,:1164
+        max_f_stats = ((h0_rss_f / min_rss_list) - 1.0) * n_p / float(q)             # :1171
+        min_pvals = ctx.f_sf(max_f_stats, q, n_p)                                    # :1172
+        return {'min_ps': min_pvals, 'max_f_stats': max_f_stats}
+
+
+# ----------------------------------------------------------------------------------------------
+def get_emma_reml_estimates(y, K, K2=None, cofactors=None, include_intercept=True):
+    """linear_models.py:1690-1706 (single-kinship form)."""
+    if K2 is not None:
+        raise NotImplementedError('two-kinship models are outside the EMMAX hot path')
+    lmm = LinearMixedModel(y)
+    lmm.add_random_effect(K)
+    if cofactors is not None:
+        lmm.set_factors(cofactors, include_intercept=include_intercept)
+    res = lmm.get_REML()
+    H = np.asarray(res['H_sqrt_inv'])
+    res['Y_t'] = H @ lmm.Y
+    res['X_t'] = H @ lmm.X
+    res['lmm'] = lmm
+    return res
+
+
+def emma(snps, phenotypes, K, cofactors=None):
+    """Run EMMA (linear_models.py:1725-1745)."""
+    lmm = LinearMixedModel(phenotypes)
+    lmm.add_random_effect(K)
+    if cofactors:
+        for cofactor in cofactors:
+            lmm.add_factor(cofactor)
+    return lmm.expedited_REML_t_test(snps)
+
+
+def emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_num=0, scan_impl='auto', ctx=None):
+    """
+    Run EMMAX (linear_models.py:1790-1816).
+    """
+    lmm = LinearMixedModel(phenotypes, ctx=ctx, scan_impl=scan_impl)
+    if Z is not None:
+        Zm = np.asarray(Z, dtype=np.float64)
+        Kh = np.asarray(K, dtype=np.float64)
+        lmm.add_random_effect(Zm @ Kh @ Zm.T)
+        if cofactors:
+            for cofactor in cofactors:
+                lmm.add_factor(Zm @ np.asarray(cofactor, dtype=np.float64))
+    else:
+        lmm.add_random_effect(K)
+        if cofactors:
+            for cofactor in cofactors:
+                lmm.add_factor(cofactor)
+
+    _say("Running EMMAX")
+    s1 = time.time()
+    res = lmm.emmax_f_test(snps, Z=Z, with_betas=with_betas, emma_num=emma_num)
+    secs = time.time() - s1
+    if secs > 60:
+        mins = int(secs) // 60
+        secs = secs - mins * 60
+        _say('Took %d mins and %f seconds.' % (mins, secs))
+    else:
+        _say('Took %f seconds.' % (secs))
+    return res

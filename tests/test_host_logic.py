@@ -1,0 +1,127 @@
+"""CPU: the product's host/device headers (built with g++) against golden vectors; the C ABI loads and
+exports every symbol of include/mixmogam_b200.h; the product never imports the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+
+
+def _run(built, mode, payload):
+    exe = os.path.join(ROOT, 'tests', 'host_check')
+    out = subprocess.run([exe, mode], input=np.asarray(payload, dtype=np.float64).tobytes(), capture_output=True, check=True)
+    return np.frombuffer(out.stdout, dtype=np.float64)
+
+
+@pytest.mark.parametrize('dfn,key', [(1, 'sf'), (2, 'sf2'), (3, 'sf3')])
+def test_f_sf_matches_scipy(built, dfn, key):
+    g = golden('f_sf.npz')
+    F, D, S = g['f'].ravel(), g['dfd'].ravel(), g[key].ravel()
+    payload = np.concatenate([[F.size], np.stack([F, np.full_like(F, dfn), D], axis=1).ravel()])
+    out = _run(built, 'fsf', payload)
+    tail = (S > 0) & (S < 0.5)
+    assert np.max(np.abs(out[tail] - S[tail]) / S[tail]) < 1e-10       # relative in the tail, down to 1e-300
+    body = S >= 0.5
+    assert np.max(np.abs(out[body] - S[body])) < 1e-13
+    assert np.all(out[S == 0] < 1e-300)                                # underflows where scipy returns 0
+    # -log10 space, the parity measure
+    assert np.max(np.abs(np.log10(out[tail]) - np.log10(S[tail]))) < 1e-9
+
+
+def _reml_case(built, gname, ngrids):
+    g = golden(gname)
+    from oracle import reference_py3 as o
+    lmm = o.LinearMixedModel(g['y'], 'double')
+    lmm.add_random_effect(g['K'])
+    res = lmm.get_REML(ngrids=ngrids)
+    eig_R = res['_eig_R']
+    etas = (eig_R['vectors'] @ lmm.Y).reshape(-1)
+    deltas = np.asarray(res['_deltas'], dtype=np.float64)
+    p = len(etas)
+    payload = np.concatenate([[p, len(deltas), 1e-6], eig_R['values'], etas ** 2, deltas])
+    out = _run(built, 'reml', payload)
+    gl = len(deltas)
+    np.testing.assert_allclose(out[3:3 + gl], res['_lls'], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(out[3 + gl:3 + 2 * gl], res['_dlls'], rtol=1e-8, atol=1e-8)
+    return out[0], out[1], int(out[2]), res
+
+
+@pytest.mark.parametrize('ngrids', [100, 50, 10])
+def test_reml_logic_interior_root(built, ngrids):
+    """Sign change + secant refinement (linear_models.py:829-871) replicated step for step."""
+    delta, ll, flags, res = _reml_case(built, 'emmax_diploid_n400.npz', ngrids)
+    assert flags == 7
+    assert abs(delta - res['delta']) / res['delta'] < 1e-9
+    assert abs(ll - res['max_ll']) < 1e-8
+
+
+def test_reml_logic_boundary_optimum(built):
+    """FT10 against unrelated synthetic genotypes has no heritable signal: no sign change, the optimum is
+    the last grid point delta = e^10 (linear_models.py:888-891)."""
+    delta, ll, flags, res = _reml_case(built, 'emmax_ft10_n198.npz', 100)
+    assert flags == 0
+    assert delta == res['delta'] == np.exp(10.0)
+    assert abs(ll - res['max_ll']) < 1e-8
+
+
+def test_reml_logic_boundary_cases(built):
+    """No sign change -> grid maximum (linear_models.py:888-891)."""
+    p = 50
+    rng = np.random.default_rng(0)
+    eig = np.sort(rng.uniform(0.1, 3, p))
+    deltas = np.exp(np.linspace(-10, 10, 51))
+    sq = rng.normal(size=p) ** 2 * 1e-6 * (eig + 1e-9)      # essentially no genetic signal: ll increases with delta
+    out = _run(built, 'reml', np.concatenate([[p, 51, 1e-6], eig, sq, deltas]))
+    lls = out[3:3 + 51]
+    dlls = out[3 + 51:]
+    has_interval = np.any((dlls[1:] < 0) & (dlls[:-1] > 0))
+    if not has_interval:
+        assert int(out[2]) == 0
+        assert out[0] == deltas[np.argmax(lls)]
+
+
+def test_abi_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, 'include', 'mixmogam_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(mmg_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 40
+    from mixmogam_b200 import _lib
+    lib = _lib.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'library does not export %s' % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_no_gpu_fails_loudly(built):
+    """Without a device the product raises; it never falls back to CPU code."""
+    import ctypes
+    from mixmogam_b200 import _lib
+    lib = _lib.load_library()
+    h = ctypes.c_void_p(0)
+    rc = lib.mmg_create(0, ctypes.byref(h))
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        assert rc != 0 and not h.value
+        assert b'no CPU fallback' in lib.mmg_last_error(None) or rc == -2
+        with pytest.raises(_lib.MmgError):
+            _lib.Context(0)
+    else:
+        assert rc == 0
+        lib.mmg_destroy(h)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'mixmogam_b200')
+    for dp, dn, fn in os.walk(pkg):
+        for f in fn:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dp, f)).read()
+                assert 'oracle' not in src.replace('no oracle', ''), '%s references the oracle' % f
+                assert 'import scipy' not in src and 'from scipy' not in src, '%s routes through scipy' % f
