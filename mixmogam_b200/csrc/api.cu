@@ -72,6 +72,16 @@ static int launch_check(mmg_ctx* ctx, const char* what) {
     return MMG_OK;
 }
 
+// MMG_GRAM_IMPL / MMG_SCAN_IMPL = tcgen05 | simt | dmma select what MMG_IMPL_AUTO means (both are CUDA paths)
+static int env_impl(const char* var, int dflt) {
+    const char* e = getenv(var);
+    if (!e) return dflt;
+    if (!strcmp(e, "tcgen05")) return MMG_IMPL_TCGEN05;
+    if (!strcmp(e, "simt")) return MMG_IMPL_SIMT;
+    if (!strcmp(e, "dmma")) return MMG_IMPL_DMMA;
+    return dflt;
+}
+
 static double lbeta_host(double a, double b) {
     return (double)(lgammal((long double)a) + lgammal((long double)b) - lgammal((long double)a + (long double)b));
 }
@@ -488,7 +498,7 @@ int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, i
     MMG_CHECK(ctx, ctx && ctx->snps, "mmg_kinship_gram_i8: no resident genotypes");
     MMG_CHECK(ctx, coding == MMG_CODING_BINARY || coding == MMG_CODING_DIPLOID, "unknown coding %d", coding);
     MMG_CHECK(ctx, snp_begin >= 0 && snp_count >= 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
-    if (impl == MMG_IMPL_AUTO) impl = MMG_IMPL_TCGEN05;
+    if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_GRAM_IMPL", MMG_IMPL_TCGEN05);
     MMG_CHECK(ctx, impl == MMG_IMPL_TCGEN05 || impl == MMG_IMPL_SIMT, "unsupported impl %d for the Gram", impl);
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int n = (int)ctx->n;
@@ -835,7 +845,7 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
     MMG_CHECK(ctx, R->cols == ctx->n, "R must have n = %lld columns (has %lld)", (long long)ctx->n, (long long)R->cols);
     MMG_CHECK(ctx, V && nv >= 1 && nv <= 16, "need 1..16 rotated-space vectors (V[0] = residual phenotype)");
     MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
-    if (impl == MMG_IMPL_AUTO) impl = MMG_IMPL_TCGEN05;
+    if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_SCAN_IMPL", MMG_IMPL_TCGEN05);
     MMG_CHECK(ctx, impl == MMG_IMPL_DMMA || impl == MMG_IMPL_TCGEN05, "unsupported impl %d for the scan", impl);
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t n = ctx->n, n_out = R->rows;

@@ -119,7 +119,7 @@ def main():
     res = lmm.get_REML()
     np.random.seed(20240607)
     pr = lmm._emmax_permutations_(x3.astype(np.float64), K3, res['H_sqrt_inv'], num_perm=25)
-    save('perm_n120.npz', snps=x3, y=y3, K=K3, seed=np.int64(20240607), Ys=pr['_Ys'],
+    save('perm_n120.npz', snps=x3, y=y3, K=K3, seed=np.int64(20240607), Ys=pr['_Ys'], H_sqrt_inv=res['H_sqrt_inv'],
          min_ps=pr['min_ps'], max_f_stats=pr['max_f_stats'], h0_rss=np.asarray(pr['_h0_rss']).reshape(-1),
          delta=np.float64(res['delta']))
 

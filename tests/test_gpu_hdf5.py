@@ -1,0 +1,61 @@
+"""GPU: the hdf5_data entry points on an in-memory file with the plink2hdf5 layout."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import golden, neglog10_rel_err
+
+pytestmark = pytest.mark.gpu
+warnings.simplefilter('ignore')
+
+
+def _h5_like(chroms, y):
+    gg = {}
+    for i, x in enumerate(chroms):
+        gg['chrom_%d' % (i + 1)] = {'raw_snps': x, 'freqs': x.mean(1) / 2.0, 'positions': np.arange(len(x)) * 100 + 1}
+    n = chroms[0].shape[1]
+    return {'genot_data': gg, 'indiv_data': {'indiv_ids': np.arange(n), 'phenotypes': y},
+            'num_snps': np.array(sum(len(x) for x in chroms))}
+
+
+def test_ibd_hdf5_variant(ctx):
+    from mixmogam_b200 import hdf5_data
+    g = golden('ibd_hdf5_n198.npz')
+    snps = golden('ibs_diploid_n198.npz')['snps']
+    f = _h5_like([snps[:1700], snps[1700:]], np.zeros(198))
+    K, n_snps = hdf5_data._ibd_kinship_device(ctx, f['genot_data'], 198, min_maf=0.1)
+    assert n_snps == int(g['n_snps'])
+    np.testing.assert_allclose(K.download(), g['K'], rtol=1e-10, atol=1e-12)
+    hdf5_data.calculate_ibd_kinship(f)
+    assert f['kinship'].shape == (198, 198)
+
+
+def test_run_emmax_and_perm(ctx):
+    from mixmogam_b200 import hdf5_data
+    from oracle import reference_py3 as o
+    snps = golden('ibs_diploid_n198.npz')['snps']
+    chroms = [snps[:1700], snps[1700:]]
+    k, n_snps = o.hdf5_ibd_kinship(chroms, [c.mean(1) / 2.0 for c in chroms], 0.1, dtype='double')
+    y = o.synth_phenotype(snps, k, seed=9)
+    f = _h5_like(chroms, y)
+    out = {}
+    hdf5_data.run_emmax(f, out, min_maf=0.1)
+    lmm = o.LinearMixedModel(y, 'double')
+    lmm.add_random_effect(k)
+    eig_L = lmm._get_eigen_L_()
+    res = lmm.get_estimates(eig_L)
+    np.testing.assert_allclose(float(out['pseudo_heritability']), res['pseudo_heritability'], rtol=1e-7)
+    for ci, c in enumerate(chroms):
+        fr = c.mean(1) / 2.0
+        keep = np.minimum(fr, 1 - fr) > 0.1
+        ro = lmm._emmax_f_test_(list(c[keep]), res['H_sqrt_inv'], emma_num=0)
+        got = out['chrom_results']['chrom_%d' % (ci + 1)]
+        assert neglog10_rel_err(got['ps'], ro['ps']) < 1e-6
+        assert np.array_equal(got['positions'], (np.arange(len(c)) * 100 + 1)[keep])
+    outp = {}
+    np.random.seed(3)
+    hdf5_data.run_emmax_perm(f, outp, min_maf=0.1, num_perm=40)
+    assert outp['perm_min_ps'].shape == (40,) and np.all(np.diff(outp['perm_min_ps']) >= 0)
+    assert outp['kinship'].shape == (198, 198)
+    assert float(outp['five_perc_perm_min_ps']) == outp['perm_min_ps'][2]

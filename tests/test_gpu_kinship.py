@@ -1,0 +1,112 @@
+"""GPU: stage 1 (kinship) through the C ABI against the oracle / golden vectors.  Bit-exact for the integer
+Gram and the unscaled kinship (both codings, both Gram implementations)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _gram_ref(snps, coding):
+    x = snps.astype(np.int64)
+    if coding == 0:
+        s = 2 * x - 1
+        return s.T @ s
+    t = np.concatenate([(x >= 1), (x >= 2)], axis=0).astype(np.int64)
+    return t.T @ t
+
+
+def _rand_snps(m, n, coding, seed):
+    rng = np.random.default_rng(seed)
+    if coding == 0:
+        return (rng.random((m, n)) < rng.uniform(0.05, 0.95, size=(m, 1))).astype(np.int8)
+    return rng.binomial(2, rng.uniform(0.05, 0.95, size=(m, 1)), size=(m, n)).astype(np.int8)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05'])
+@pytest.mark.parametrize('coding', [0, 1])
+@pytest.mark.parametrize('m,n', [(700, 37), (3000, 198), (5001, 300), (1, 5), (129, 257), (2048, 1000)])
+def test_gram_bit_exact(ctx, impl, coding, m, n):
+    snps = _rand_snps(m, n, coding, seed=m * 1000 + n + coding)
+    ctx.invalidate_snps()
+    ctx.ensure_snps(snps)
+    ctx.kinship_gram(coding, impl=impl)
+    G = ctx.kinship_gram_download()
+    assert np.array_equal(G.astype(np.int64), _gram_ref(snps, coding))
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05'])
+def test_gram_chunk_boundary_and_accumulate(ctx, impl):
+    """m crosses the 65536-SNP pack chunk; a second call with reset=False accumulates (multi-call == one call)."""
+    n, m = 130, 70000
+    snps = _rand_snps(m, n, 1, seed=5)
+    ctx.invalidate_snps()
+    ctx.ensure_snps(snps)
+    ctx.kinship_gram(1, impl=impl)
+    G1 = ctx.kinship_gram_download()
+    assert np.array_equal(G1.astype(np.int64), _gram_ref(snps, 1))
+    ctx.kinship_gram(1, impl=impl, snp_begin=0, snp_count=30001, reset=True)
+    ctx.kinship_gram(1, impl=impl, snp_begin=30001, snp_count=m - 30001, reset=False)
+    assert np.array_equal(ctx.kinship_gram_download(), G1)
+
+
+def test_gram_rejects_out_of_domain_values(ctx):
+    from mixmogam_b200 import MmgError
+    snps = _rand_snps(300, 40, 1, seed=1)
+    snps[17, 3] = 3
+    ctx.invalidate_snps()
+    ctx.ensure_snps(snps)
+    with pytest.raises(MmgError):
+        ctx.kinship_gram(1)
+    snps[17, 3] = 2
+    ctx.invalidate_snps()
+    ctx.ensure_snps(snps)
+    with pytest.raises(MmgError):
+        ctx.kinship_gram(0)          # a 2 is not a binary genotype
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05'])
+@pytest.mark.parametrize('name,fmt', [('ibs_binary_n37.npz', 'binary'), ('ibs_diploid_n37.npz', 'diploid_int'),
+                                      ('ibs_diploid_n198.npz', 'diploid_int')])
+def test_calc_ibs_kinship_golden(ctx, impl, name, fmt):
+    from mixmogam_b200 import kinship
+    g = golden(name)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(list(g['snps']), fmt, scaled=False, impl=impl)
+    assert np.array_equal(np.asarray(K), g['K_unscaled'])            # bit-exact
+    assert isinstance(K, np.matrix) == (fmt == 'binary')             # kinship.py:43 returns a matrix for 'binary'
+    Ks = np.asarray(kinship.calc_ibs_kinship(g['snps'], fmt, scaled=True, impl=impl))
+    ulp = np.abs(Ks - g['K_scaled']) / np.spacing(np.abs(g['K_scaled']))
+    assert ulp.max() <= 4, ulp.max()
+    with pytest.raises(NotImplementedError):
+        kinship.calc_ibs_kinship(g['snps'], 'triploid')
+
+
+def test_calc_ibs_kinship_matches_oracle_midsize(ctx):
+    from mixmogam_b200 import kinship
+    from oracle import reference_py3 as o
+    snps = o.synth_genotypes(20000, 1000, 'diploid_int', seed=77)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int', scaled=False)
+    assert np.array_equal(K, o.calc_ibs_kinship_diploid_fast(snps, scaled=False))
+    # size-independent properties: symmetry, unit diagonal, entries are multiples of 1/(2m) before the f32 quotient
+    assert np.array_equal(K, K.T) and np.all(np.diag(K) == 1.0)
+
+
+def test_scale_k_and_ibd(ctx):
+    from mixmogam_b200 import kinship
+    g = golden('ibd_n37.npz')
+    ctx.invalidate_snps()
+    K = kinship.calc_ibd_kinship(list(g['snps']))
+    np.testing.assert_allclose(K, g['K_double'], rtol=1e-11, atol=1e-13)
+    Ku = kinship.calc_ibd_kinship(g['snps'], scaled=False)
+    np.testing.assert_allclose(Ku, g['K_double_unscaled'], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(kinship.scale_k(Ku), g['K_double'], rtol=1e-12)
+    # the float32-accumulating reference differs at the 1e-6 level only
+    np.testing.assert_allclose(K, g['K_single'], rtol=2e-4, atol=2e-6)
+    mono = g['snps'].copy()
+    mono[3] = 1
+    ctx.invalidate_snps()
+    with pytest.raises(AssertionError):
+        kinship.calc_ibd_kinship(mono)

@@ -1,0 +1,175 @@
+"""GPU: stages 2 and 3 (REML, scan, permutations) through the public API against the float64 oracle.
+Tolerance of BASELINE.json: |d(-log10 p)| <= 1e-6 * max(-log10 p, 1e-3), identical top-hit ranking."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import golden, neglog10_rel_err
+
+pytestmark = pytest.mark.gpu
+warnings.simplefilter('ignore')
+
+SCAN_IMPLS = ['dmma', 'tcgen05']
+
+
+def test_f_sf_device(ctx):
+    g = golden('f_sf.npz')
+    for dfn, key in ((1, 'sf'), (2, 'sf2'), (3, 'sf3')):
+        for j in range(g['dfd'].shape[1]):
+            F, S = g['f'][:, j], g[key][:, j]
+            out = ctx.f_sf(F, dfn, g['dfd'][0, j])
+            tail = (S > 0) & (S < 0.5)
+            assert np.max(np.abs(out[tail] - S[tail]) / S[tail]) < 1e-10
+            assert np.max(np.abs(out[S >= 0.5] - S[S >= 0.5])) < 1e-13
+
+
+def test_syevd_and_eigen(ctx):
+    from mixmogam_b200 import linear_models as lm
+    g = golden('emmax_ft10_n198.npz')
+    lmm = lm.LinearMixedModel(g['y'])
+    lmm.add_random_effect(g['K'])
+    eig_L = lmm._get_eigen_L_()
+    np.testing.assert_allclose(eig_L['values'], g['reml_eigL_values'], rtol=1e-9, atol=1e-11)
+    U = np.asarray(eig_L['vectors'])
+    np.testing.assert_allclose(U @ U.T, np.eye(len(U)), atol=1e-12)              # rows are orthonormal eigenvectors
+    Ks = np.asarray(lmm.random_effects[1][1])
+    np.testing.assert_allclose(U.T @ np.diag(eig_L['values']) @ U, Ks, atol=1e-10)
+    eig_R = lmm._get_eigen_R_()
+    assert eig_R['values'].shape == (197,) and eig_R['vectors'].shape == (197, 198)
+    np.testing.assert_allclose(eig_R['values'], g['reml_eigR_values'], rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize('name', ['emmax_ft10_n198.npz', 'emmax_diploid_n400.npz'])
+def test_get_reml(ctx, name):
+    from mixmogam_b200 import linear_models as lm
+    g = golden(name)
+    lmm = lm.LinearMixedModel(g['y'])
+    lmm.add_random_effect(g['K'])
+    res = lmm.get_REML()
+    if name.startswith('emmax_ft10'):
+        assert res['delta'] == g['reml_delta']                                  # boundary optimum: exactly e^10
+        np.testing.assert_allclose(res['max_ll'], g['reml_max_ll'], rtol=1e-10)
+        np.testing.assert_allclose(lmm._last_reml['lls'], g['reml_lls'], rtol=1e-9, atol=1e-8)
+        np.testing.assert_allclose(lmm._last_reml['dlls'], g['reml_dlls'], rtol=1e-7, atol=1e-8)
+        np.testing.assert_allclose(res['vg'], g['reml_vg'], rtol=1e-9)
+        np.testing.assert_allclose(res['ve'], g['reml_ve'], rtol=1e-9)
+        H = np.asarray(res['H_sqrt_inv'])
+        np.testing.assert_allclose(H.T @ H, g['reml_HtH'], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(np.asarray(res['beta']).reshape(-1), g['reml_beta'], rtol=1e-8)
+        np.testing.assert_allclose(np.asarray(res['mahalanobis_rss']).reshape(-1), g['reml_mahalanobis_rss'], rtol=1e-8)
+        assert set(res) >= {'max_ll', 'delta', 'beta', 've', 'vg', 'rss', 'mahalanobis_rss', 'H_sqrt_inv',
+                            'pseudo_heritability', 'eig_L'}
+    else:
+        from oracle import reference_py3 as o
+        ol = o.LinearMixedModel(g['y'], 'double')
+        ol.add_random_effect(g['K'])
+        ro = ol.get_REML()
+        assert abs(res['delta'] - ro['delta']) / ro['delta'] < 1e-9
+        assert abs(res['max_ll'] - ro['max_ll']) < 1e-7
+        assert lmm._last_reml['flags'] == 7
+
+
+@pytest.mark.parametrize('impl', SCAN_IMPLS)
+@pytest.mark.parametrize('name', ['emmax_ft10_n198.npz', 'emmax_diploid_n400.npz'])
+def test_emmax_golden(ctx, impl, name):
+    from mixmogam_b200 import linear_models as lm
+    g = golden(name)
+    ctx.invalidate_snps()
+    r = lm.emmax(list(g['snps']), g['y'], g['K'], scan_impl=impl)
+    assert set(r) >= {'ps', 'f_stats', 'rss', 'var_perc', 'h0_rss', 'h0_betas', 'pseudo_heritability', 've', 'vg', 'max_ll'}
+    assert neglog10_rel_err(r['ps'], g['double_ps']) < 1e-6
+    np.testing.assert_allclose(r['f_stats'], g['double_f_stats'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(r['rss'], g['double_rss'], rtol=1e-9)
+    np.testing.assert_allclose(r['var_perc'], g['double_var_perc'], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(np.asarray(r['h0_rss']).reshape(-1), g['double_h0_rss'], rtol=1e-9)
+    np.testing.assert_allclose(r['pseudo_heritability'], g['double_pseudo_heritability'], rtol=1e-8)
+    np.testing.assert_allclose(r['vg'], g['double_vg'], rtol=1e-8)
+    np.testing.assert_allclose(r['max_ll'], g['double_max_ll'], rtol=1e-9)
+    # identical ranking of the top hits, against both oracle modes; 1e-2 absolute against the float32-faithful mode
+    assert np.array_equal(np.argsort(r['ps'], kind='stable')[:20], np.argsort(g['double_ps'], kind='stable')[:20])
+    assert np.array_equal(np.argsort(r['ps'], kind='stable')[:20], np.argsort(g['single_ps'], kind='stable')[:20])
+    assert np.max(np.abs(np.log10(r['ps']) - np.log10(g['single_ps']))) < 1e-2
+
+
+@pytest.mark.parametrize('impl', SCAN_IMPLS)
+def test_emmax_with_betas_cofactor_emma(ctx, impl):
+    from mixmogam_b200 import linear_models as lm
+    g = golden('emmax_ft10_n198.npz')
+    ctx.invalidate_snps()
+    r = lm.emmax(g['snps'], g['y'], g['K'], with_betas=True, scan_impl=impl)
+    assert neglog10_rel_err(r['ps'], g['double_wb_ps']) < 1e-6
+    np.testing.assert_allclose(np.asarray(r['betas']), g['double_wb_betas'], rtol=1e-5, atol=1e-8)
+    g2 = golden('emmax_diploid_n400.npz')
+    ctx.invalidate_snps()
+    rc = lm.emmax(g2['snps'], g2['y'], g2['K'], cofactors=[g2['cofactor']], scan_impl=impl)
+    ok = np.arange(len(rc['ps'])) != 17          # SNP 17 is the cofactor itself: x~ = 0 up to rounding, p is noise in every implementation
+    assert neglog10_rel_err(rc['ps'][ok], g2['double_cof_ps'][ok]) < 1e-6
+    ctx.invalidate_snps()
+    re = lm.emmax(g['snps'][:400], g['y'], g['K'], emma_num=5, scan_impl=impl)
+    assert neglog10_rel_err(re['ps'], g['double_emma5_ps']) < 1e-5
+
+
+def test_snp_priors_and_transformed_snps(ctx):
+    from mixmogam_b200 import linear_models as lm
+    from oracle import reference_py3 as o
+    g = golden('emmax_diploid_n400.npz')
+    snps = g['snps'][:300]
+    pri = np.full(len(snps), 1e-3)
+    lmm = lm.LinearMixedModel(g['y'])
+    lmm.add_random_effect(g['K'])
+    ctx.invalidate_snps()
+    r = lmm.emmax_f_test(snps, snp_priors=pri, emma_num=0)
+    ol = o.LinearMixedModel(g['y'], 'double')
+    ol.add_random_effect(g['K'])
+    ro = ol.emmax_f_test(list(snps), snp_priors=pri, emma_num=0)
+    np.testing.assert_allclose(r['ppas'], ro['ppas'], rtol=1e-5)
+    np.testing.assert_allclose(r['bfs'], ro['bfs'], rtol=1e-5)
+    res = lmm.get_REML()
+    rt = lmm._emmax_f_test_(snps, res['H_sqrt_inv'], return_transformed_snps=True, emma_num=0)
+    t = np.asarray(rt['t_snps'])
+    np.testing.assert_allclose(np.sum(t * t, axis=1) * 0 + np.sum(t * t, axis=1), np.sum(t * t, axis=1))
+    assert t.shape == (300, 400)
+
+
+def test_permutations_golden(ctx):
+    """_emmax_permutations_ shuffles the ROTATED residual phenotype (linear_models.py:1151-1154), so its output
+    depends on the sign convention of the eigenvectors inside H_sqrt_inv.  Feed the oracle's H_sqrt_inv (the
+    method takes it as an argument) and the same np.random seed: then every number is comparable."""
+    from mixmogam_b200 import linear_models as lm
+    g = golden('perm_n120.npz')
+    lmm = lm.LinearMixedModel(g['y'])
+    lmm.add_random_effect(g['K'])
+    np.random.seed(int(g['seed']))
+    ctx.invalidate_snps()
+    pr = lmm._emmax_permutations_(g['snps'].astype(np.float64), g['K'], g['H_sqrt_inv'], num_perm=25)
+    np.testing.assert_allclose(pr['max_f_stats'], g['max_f_stats'], rtol=1e-6)
+    assert neglog10_rel_err(pr['min_ps'], g['min_ps']) < 1e-6
+    assert abs(float(np.mean(lmm.Y))) < 1e-12                       # :1140 mutates the model
+    # with our own (cuSOLVER) eigenbasis the permutation null is the same in distribution, not element-wise
+    lmm2 = lm.LinearMixedModel(g['y'])
+    lmm2.add_random_effect(g['K'])
+    res = lmm2.get_REML()
+    np.random.seed(int(g['seed']))
+    pr2 = lmm2._emmax_permutations_(g['snps'], g['K'], res['H_sqrt_inv'], num_perm=25)
+    assert pr2['min_ps'].shape == (25,) and np.all((pr2['min_ps'] > 0) & (pr2['min_ps'] < 1))
+    assert 0.2 < np.median(pr2['max_f_stats']) / np.median(g['max_f_stats']) < 5
+
+
+@pytest.mark.parametrize('n,m', [(1000, 6000), (2000, 3000)])
+def test_scan_implementations_agree_and_match_oracle_sample(ctx, n, m):
+    """Mid-size: the FP64 tensor-core path and the int8-slice path agree, and a sample matches the oracle."""
+    from mixmogam_b200 import kinship, linear_models as lm
+    from oracle import reference_py3 as o
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=n + m)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int')
+    y = o.synth_phenotype(snps, K, seed=5)
+    ra = lm.emmax(snps, y, K, scan_impl='dmma')
+    rb = lm.emmax(snps, y, K, scan_impl='tcgen05')
+    assert neglog10_rel_err(ra['ps'], rb['ps']) < 1e-7
+    assert np.array_equal(np.argsort(ra['ps'], kind='stable')[:100], np.argsort(rb['ps'], kind='stable')[:100])
+    sub = np.sort(np.random.default_rng(0).choice(m, 400, replace=False))
+    ro = o.emmax(list(snps[sub]), y, K, dtype='double')
+    assert neglog10_rel_err(ra['ps'][sub], ro['ps']) < 1e-6
+    assert abs(ra['pseudo_heritability'] - ro['pseudo_heritability']) < 1e-8
