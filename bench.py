@@ -43,8 +43,8 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--n', type=int, default=int(os.environ.get('MMG_BENCH_N', 10000)))
-    ap.add_argument('--m', type=int, default=int(os.environ.get('MMG_BENCH_M', 1000000)))
+    ap.add_argument('--indivs', dest='n', type=int, default=int(os.environ.get('MMG_BENCH_N', 10000)))
+    ap.add_argument('--snps', dest='m', type=int, default=int(os.environ.get('MMG_BENCH_M', 1000000)))
     ap.add_argument('--scan-impl', default=os.environ.get('MMG_BENCH_SCAN_IMPL', 'tcgen05'), choices=['tcgen05', 'dmma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')

@@ -72,6 +72,47 @@ static int launch_check(mmg_ctx* ctx, const char* what) {
     return MMG_OK;
 }
 
+static int env_int(const char* var, int dflt) {
+    const char* e = getenv(var);
+    return e ? atoi(e) : dflt;
+}
+
+// Launch the tcgen05 GEMM with a cluster of CS CTAs.  The persistent grid is the number of clusters that can be
+// co-resident (cudaOccupancyMaxActiveClusters; clusters of 4 do not tile every GPC) times CS.
+template <class Epi, int CS>
+static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcTile* tiles_d, int num_groups,
+                          int tiles_per_group, int table_stride, int group_m_step, int rank_m_step,
+                          const typename Epi::Params& ep, const char* name) {
+    auto kern = tc_gemm_i8_kernel<Epi, CS>;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = ctx->sm_count / CS;
+    if (CS > 1) {
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count / CS * CS));
+        int q = 0;
+        if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0) max_clusters = std::min(max_clusters, q);
+        else cudaGetLastError();
+    }
+    const int cgroups = (num_groups + CS - 1) / CS;
+    const int clusters = std::max(1, std::min(cgroups, max_clusters));
+    cfg.gridDim = dim3((unsigned)(clusters * CS));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tiles_d, num_groups, tiles_per_group, table_stride, group_m_step,
+                                       rank_m_step, ep);
+    ctx->launches += 1;
+    if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of %s (cluster %d, grid %d) failed: %s", name, CS, clusters * CS,
+                                      cudaGetErrorString(e));
+    return MMG_OK;
+}
+
 // MMG_GRAM_IMPL / MMG_SCAN_IMPL = tcgen05 | simt | dmma select what MMG_IMPL_AUTO means (both are CUDA paths)
 static int env_impl(const char* var, int dflt) {
     const char* e = getenv(var);
@@ -128,8 +169,11 @@ int mmg_create(int device, mmg_ctx** out) {
     cusolverDnSetStream(ctx->cusolver, ctx->stream);
     cublasSetPointerMode(ctx->cublas, CUBLAS_POINTER_MODE_HOST);
     // opt in to large dynamic shared memory once
-    cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(scan_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
     cudaFuncSetAttribute(scan_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
     *out = ctx;
@@ -530,12 +574,15 @@ int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, i
     }
     MMG_CUDA(ctx, cudaMemsetAsync(ctx->flag_d, 0, sizeof(int), ctx->stream));
 
-    // tile table: upper-triangular 128 x 256 tiles (row tile im needed for column tile jn iff im <= 2 jn + 1)
+    // tile table: upper-triangular 128 x 256 tiles (row tile im needed for column tile jn iff im <= 2 jn + 1).
+    // With a cluster of 2, one entry covers the row-tile pair (im, im+1) of a column tile (2 jn + 2 is even).
+    int gram_cs = env_int("MMG_GRAM_CLUSTER", 2);
+    if (gram_cs != 1) gram_cs = 2;
     std::vector<TcTile> tiles;
     if (impl == MMG_IMPL_TCGEN05) {
-        const int tiles_m = (n + TC_BM - 1) / TC_BM, tiles_n = (n + TC_BN - 1) / TC_BN;
+        const int tiles_n = (n + TC_BN - 1) / TC_BN;
         for (int jn = 0; jn < tiles_n; ++jn)
-            for (int im = 0; im < tiles_m && im <= 2 * jn + 1; ++im) tiles.push_back(TcTile{im * TC_BM, jn * TC_BN, 0, 0, 0, 0, 0, 0});
+            for (int im = 0; im <= 2 * jn + 1; im += gram_cs) tiles.push_back(TcTile{im * TC_BM, jn * TC_BN, 0, 0, 0, 0, 0, 0});
     }
     double gram_ms = 0.0, pack_s = 0.0;
     for (int64_t s0 = 0; s0 < snp_count; s0 += chunk) {
@@ -556,14 +603,15 @@ int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, i
         if (impl == MMG_IMPL_TCGEN05) {
             CUtensorMap tmA, tmB;
             MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->pack, kbytes, n, p_pitch, TC_BM));
-            MMG_TRY(make_tmap_u8(ctx, &tmB, ctx->pack, kbytes, n, p_pitch, TC_BN));
+            MMG_TRY(make_tmap_u8(ctx, &tmB, ctx->pack, kbytes, n, p_pitch, TC_BN / gram_cs));
             for (auto& t : tiles) { t.kb0 = 0; t.kb1 = (int)(kbytes / TC_BK); }
             MMG_TRY(ensure_tiles(ctx, tiles));
             GramEpi::Params ep{ctx->G, g_pad, accumulate};
-            const int grid = std::min<int>((int)tiles.size(), ctx->sm_count);
-            tc_gemm_i8_kernel<GramEpi><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(tmA, tmB, (const TcTile*)ctx->tiles_d,
-                                                                                       (int)tiles.size(), 1, 1, 0, ep);
-            MMG_TRY(launch_check(ctx, "tc_gemm_i8_kernel<GramEpi>"));
+            const int ngroups = (int)tiles.size() * gram_cs;
+            if (gram_cs == 2)
+                MMG_TRY((launch_tc_gemm<GramEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep, "tc_gemm_i8_kernel<GramEpi,2>")));
+            else
+                MMG_TRY((launch_tc_gemm<GramEpi, 1>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, 0, ep, "tc_gemm_i8_kernel<GramEpi,1>")));
         } else {
             dim3 ggrid((unsigned)((n + 63) / 64), (unsigned)((n + 63) / 64));
             gram_simt_kernel<<<ggrid, 256, 0, ctx->stream>>>(ctx->pack, p_pitch, n, kbytes, ctx->G, g_pad, accumulate);
@@ -822,15 +870,20 @@ static int scan_tc_run(mmg_ctx* ctx, const MmgMat* R, const double* V, double h0
             tiles.push_back(t);
         }
     MMG_TRY(ensure_tiles(ctx, tiles));
+    int cs = env_int("MMG_SCAN_CLUSTER", 2);
+    if (cs != 1 && cs != 2 && cs != 4) cs = 2;
     CUtensorMap tmA, tmB;
     MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
-    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq.p, ldq, (int64_t)S * n_padN, ldq, TC_BN));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq.p, ldq, (int64_t)S * n_padN, ldq, TC_BN / cs));
     const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
-    const int grid = std::min(groups, ctx->sm_count);
     cudaEventRecord(ctx->kev0, ctx->stream);
-    tc_gemm_i8_kernel<QuadEpi><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(tmA, tmB, (const TcTile*)ctx->tiles_d, groups,
-                                                                               (int)tiles.size(), 0, TC_BM, ep);
-    MMG_TRY(launch_check(ctx, "tc_gemm_i8_kernel<QuadEpi>"));
+    const TcTile* td = (const TcTile*)ctx->tiles_d;
+    if (cs == 4)
+        MMG_TRY((launch_tc_gemm<QuadEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,4>")));
+    else if (cs == 2)
+        MMG_TRY((launch_tc_gemm<QuadEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,2>")));
+    else
+        MMG_TRY((launch_tc_gemm<QuadEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,1>")));
     cudaEventRecord(ctx->kev1, ctx->stream);
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // Bq / A / vec are freed on return
     return MMG_OK;

@@ -37,15 +37,24 @@ struct TcTile {
     int pad_;
 };
 
-template <class Epi>
+// CS = cluster size (1, 2 or 4).  With CS > 1 the CS CTAs of a cluster walk the same tile sequence in lockstep
+// on CS different 128-row A blocks that share the B tile: each CTA fetches 1/CS of the B rows and TMA-multicasts
+// them into the shared memory of every CTA of the cluster, so the L2 -> SM operand traffic per CTA drops from
+// 16+32 KB to 16+32/CS KB per K block.  A smem stage may only be refilled once every CTA of the cluster has
+// consumed it, hence the MMA issuer's tcgen05.commit arrives on the empty barrier of all CS CTAs.
+//
+// Work assignment: cluster c, rank r processes group g = (c + i * num_clusters) * CS + r, i = 0, 1, ...;
+// tile ti of that group is tiles[(g / CS) * table_stride + ti] with m0 += g * group_m_step + r * rank_m_step.
+//   scan: one shared table (table_stride 0), group_m_step = 128 (consecutive SNP row blocks), rank_m_step = 0
+//   Gram: one entry per cluster group (table_stride 1), group_m_step = 0, rank_m_step = 128 (adjacent row tiles)
+template <class Epi, int CS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcTile* __restrict__ tiles, int num_groups, int tiles_per_group, int table_stride,
-                  int group_m_step, const typename Epi::Params ep) {
-    // group g processes tiles[g * table_stride + ti], ti < tiles_per_group, with m0 advanced by g * group_m_step
-    // (table_stride = 0: every group shares one table, e.g. the N tiles x slices of a 128-SNP row block).
+                  int group_m_step, int rank_m_step, const typename Epi::Params ep) {
     extern __shared__ uint8_t smem_raw[];
-    // 128B swizzle wants 1024-byte aligned stage bases
+    // 128B swizzle wants 1024-byte aligned stage bases (the dynamic smem base is the same in every CTA of a
+    // cluster, so CTA-relative offsets agree across the cluster)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* full_bar = bars;                               // [TC_STAGES]
@@ -56,13 +65,19 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
+    const int cluster_id = blockIdx.x / CS;
+    const int num_clusters = gridDim.x / CS;
+    const int num_cgroups = (num_groups + CS - 1) / CS;      // cluster-level groups (the last may be ragged)
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+    constexpr int kBRows = TC_BN / CS;                       // B rows fetched by one CTA
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CS);   // one tcgen05.commit arrival from every CTA of the cluster
         }
         for (int a = 0; a < TC_ACC_STAGES; ++a) {
             mbar_init(&tfull_bar[a], 1);
@@ -75,7 +90,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_relinquish();
     }
     tc_fence_before();
-    __syncthreads();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -84,16 +99,22 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int g = blockIdx.x; g < num_groups; g += gridDim.x) {
+            for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
+                const int g = cg * CS + crank;
                 for (int ti = 0; ti < tiles_per_group; ++ti) {
-                    TcTile t = tiles[(int64_t)g * table_stride + ti];
-                    t.m0 += g * group_m_step;
+                    TcTile t = tiles[(int64_t)cg * table_stride + ti];
+                    t.m0 += g * group_m_step + crank * rank_m_step;
                     for (int kb = t.kb0; kb < t.kb1; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
                         uint8_t* sa = smem + stage * TC_STAGE_BYTES;
                         tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, t.m0);
-                        tma_load_2d(sa + TC_A_BYTES, &tmB, &full_bar[stage], kb * TC_BK, t.n0);
+                        if (CS == 1) {
+                            tma_load_2d(sa + TC_A_BYTES, &tmB, &full_bar[stage], kb * TC_BK, t.n0);
+                        } else {
+                            tma_load_2d_mcast(sa + TC_A_BYTES + crank * kBRows * TC_BK, &tmB, &full_bar[stage], kb * TC_BK,
+                                              t.n0 + crank * kBRows, kMask);
+                        }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -108,9 +129,9 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int g = blockIdx.x; g < num_groups; g += gridDim.x) {
+            for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
                 for (int ti = 0; ti < tiles_per_group; ++ti) {
-                    const TcTile t = tiles[(int64_t)g * table_stride + ti];
+                    const TcTile t = tiles[(int64_t)cg * table_stride + ti];
                     mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * TC_BN;
@@ -126,7 +147,8 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             umma_i8(d_tmem, da + (uint64_t)(k * (TC_UMMA_K >> 4)), db + (uint64_t)(k * (TC_UMMA_K >> 4)),
                                     idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
                         }
-                        umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
+                        // frees the smem slot (in every CTA of the cluster) when these MMAs retire
+                        if (CS == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], kMask);
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
@@ -142,32 +164,36 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         Epi epi;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int g = blockIdx.x; g < num_groups; g += gridDim.x) {
-            epi.begin_group(ep, g, row);
+        for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
+            const int g = cg * CS + crank;
+            const bool live = g < num_groups;      // ragged last cluster group: take part in the protocol, skip the output
+            if (live) epi.begin_group(ep, g, row);
             for (int ti = 0; ti < tiles_per_group; ++ti) {
-                TcTile t = tiles[(int64_t)g * table_stride + ti];
-                t.m0 += g * group_m_step;
+                TcTile t = tiles[(int64_t)cg * table_stride + ti];
+                t.m0 += g * group_m_step + crank * rank_m_step;
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * TC_BN + (static_cast<uint32_t>(quad * 32) << 16);
+                if (live) {
 #pragma unroll 1
-                for (int c = 0; c < TC_BN / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    epi.chunk(ep, t, row, c, v);
+                    for (int c = 0; c < TC_BN / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr + c * 32, v);
+                        tmem_ld_wait();
+                        epi.chunk(ep, t, row, c, v);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
-            epi.end_group(ep, g, row);
+            if (live) epi.end_group(ep, g, row);
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while a peer may still signal its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TC_TMEM_COLS);
