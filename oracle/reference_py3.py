@@ -9,13 +9,18 @@ and `bench.py`'s cpu_baseline / `--impl reference` legs may import this module;
 
 Why a restatement: the reference is Python-2 source on top of `scipy` used as a
 numpy alias (`sp.mat`, `sp.zeros`, ...), neither of which exists in this image
-(Python 3.12, numpy 2.3, scipy 1.18), and the reference ships no tests, golden
-vectors or fixtures for this path.
+(Python 3.12, numpy 2.3, scipy 1.18), and it ships no tests, golden vectors or
+fixtures for this path.
 
-PARITY UNPINNED: there is no reference-side golden vector to pin this oracle
-against and the reference itself cannot be executed here.  The pin is this
-line-by-line restatement plus the committed fixtures in tests/golden/
-(generated by tests/golden/make_golden.py from this file with fixed seeds).
+PARITY PIN: the reference's own sources ARE executed in the build container --
+tests/golden/py2shim.py token-translates them Python 2 -> 3 in memory and
+re-points `scipy` at numpy for the removed aliases -- and their outputs are
+committed as tests/golden/ref_*.npz (tests/golden/make_reference_golden.py).
+In dtype='single', promotion='numpy2' mode this oracle reproduces every one of
+those outputs BIT FOR BIT (kinship x3, emmax, with_betas, cofactors, Z,
+emma_num, snp_priors, get_REML, permutations, the hdf5_data entry points:
+tests/test_reference_pin.py).  The dtype='double' mode the CUDA path is held
+to is the same code with the dtype switched.
 
 Two arithmetic modes:
   dtype='single'  reference-faithful: float32 wherever the reference hard-codes
@@ -194,8 +199,22 @@ def _residue_value(rss):
 class LinearMixedModel(object):
     """linear_models.py:554-1380 (EMMAX subset)."""
 
-    def __init__(self, Y=None, dtype='single'):
-        """linear_models.py:558-574."""
+    def __init__(self, Y=None, dtype='single', promotion='numpy1'):
+        """linear_models.py:558-574.
+
+        promotion: scalar type-promotion rules the float32 mode runs under.
+          'numpy1' (default) -- value-based casting of numpy < 2, what the reference was written for: a
+                     float64 *scalar* never upcasts a float32 array, but scalar-with-scalar arithmetic
+                     (np.float32 with a Python float) gives float64, so the secant refinement of
+                     delta runs in float64.
+          'numpy2' -- NEP 50, what the reference's own source does when executed in this container
+                     (tests/golden/py2shim.py): Python floats are weak (the secant refinement stays in
+                     float32) and an np.float64 scalar upcasts a float32 array (the lls grid, :806).
+                     In this mode the oracle reproduces the reference run here bit for bit
+                     (tests/test_oracle_golden.py::test_oracle_matches_reference_run_*).
+        With dtype='double' the two are identical."""
+        assert promotion in ('numpy1', 'numpy2')
+        self.promotion = promotion
         self.dtype = _dt(dtype)
         self.n = len(Y)
         self.y_var = np.var(Y, ddof=1, dtype=self.dtype)
@@ -317,7 +336,10 @@ class LinearMixedModel(object):
         lambdas = np.reshape(np.repeat(eig_vals, m), (p, m)) + np.reshape(np.repeat(deltas, p), (m, p)).T
         s1 = np.sum(sq_etas / lambdas, axis=0)
         s2 = np.sum(np.log(lambdas), axis=0)
-        lls = 0.5 * (p * (float(np.log((p) / (2.0 * np.pi))) - 1 - np.log(s1)) - s2)
+        log_c = np.log((p) / (2.0 * np.pi))                    # np.float64 scalar
+        if self.promotion == 'numpy1':
+            log_c = float(log_c)                               # value-based casting: does not upcast s1, s2
+        lls = 0.5 * (p * (log_c - 1 - np.log(s1)) - s2)
         s3 = np.sum(sq_etas / (lambdas * lambdas), axis=0)
         s4 = np.sum(1 / lambdas, axis=0)
         dlls = 0.5 * (p * s3 / s1 - s4)
@@ -336,14 +358,17 @@ class LinearMixedModel(object):
 
         if len(zero_intervals) > 0:
             opt_ll, opt_i = max(zero_intervals)
-            # numpy 1.x: float32 scalar * Python float -> float64 scalar
-            opt_delta = 0.5 * (float(deltas[opt_i - 1]) + float(deltas[opt_i]))
+            opt_delta = deltas[opt_i - 1] + deltas[opt_i]     # float32 scalar sum (:841)
+            if self.promotion == 'numpy1':
+                opt_delta = float(opt_delta)                   # float32 scalar * Python float -> float64 scalar
+            opt_delta = 0.5 * opt_delta
             try:
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")
                     new_opt_delta = optimize.newton(self._redll_, opt_delta, args=(eig_vals, sq_etas), tol=esp,
                                                     maxiter=100)
-                    new_opt_delta = float(new_opt_delta)
+                    if self.promotion == 'numpy1':
+                        new_opt_delta = float(new_opt_delta)
             except Exception:
                 new_opt_delta = opt_delta
             if opt_i > 1 and deltas[opt_i - 1] - esp < new_opt_delta < deltas[opt_i] + esp:
@@ -359,10 +384,12 @@ class LinearMixedModel(object):
             opt_ll = self._rell_(opt_delta, eig_vals, sq_etas)                 # :881-882
 
             if opt_ll < max_ll:
-                opt_delta = float(deltas[max_ll_i])
+                opt_delta = deltas[max_ll_i]
         else:
-            opt_delta = float(deltas[max_ll_i])
+            opt_delta = deltas[max_ll_i]
             opt_ll = max_ll
+        if self.promotion == 'numpy1':
+            opt_delta = float(opt_delta)                       # same value; a Python float is 'weak' under NEP 50
 
         if literal_vg is None:
             literal_vg = p <= 3000
@@ -546,7 +573,9 @@ class LinearMixedModel(object):
         h0_betas = list(map(float, list(np.asarray(h0_betas).reshape(-1))))
         if len(h0_betas) != 1:
             raise ValueError('reference :1147 only type-checks with a single fixed effect')
-        Y = Y - h0_X * h0_betas[0]                                         # :1147 second subtraction
+        # :1147 second subtraction: h0_betas is now a Python list, `matrix * list` goes through
+        # asmatrix(list) -- a float64 1x1 matrix -- so from here on Y is float64 in the reference too
+        Y = Y - h0_X @ np.asarray(h0_betas, dtype=np.float64).reshape(1, 1)
         num_snps = len(snps)
         chunk_size = len(Y)
         if Ys is None:
@@ -568,9 +597,10 @@ class LinearMixedModel(object):
         return {'min_ps': min_pvals, 'max_f_stats': max_f_stats, '_Ys': Ys, '_h0_rss': h0_rss}
 
 
-def emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_num=0, dtype='single'):
+def emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_num=0, dtype='single',
+          promotion='numpy1'):
     """linear_models.py:1790-1816."""
-    lmm = LinearMixedModel(phenotypes, dtype=dtype)
+    lmm = LinearMixedModel(phenotypes, dtype=dtype, promotion=promotion)
     if Z is not None:
         lmm.add_random_effect(Z @ K @ Z.T)
         if cofactors:
