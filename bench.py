@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument('--scan-impl', default=os.environ.get('MMG_BENCH_SCAN_IMPL', 'tcgen05'), choices=['tcgen05', 'dmma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--profile-host', default=None, help='write a cProfile of one resident step and one e2e step to this file')
     return ap.parse_args()
 
 
@@ -286,6 +287,25 @@ def main():
     for _ in range(args.warmup):
         step_resident()
 
+    if args.profile_host and rank == 0:
+        import cProfile
+        import io
+        import pstats
+        buf = io.StringIO()
+        for name, fn in (('resident', step_resident), ('e2e', step_e2e)):
+            fn()
+            ctx.timer_reset()
+            pr = cProfile.Profile()
+            t0 = time.perf_counter()
+            pr.enable()
+            fn()
+            barrier()
+            pr.disable()
+            buf.write('==== %s step: %.1f ms wall; stage timers (ms): %s\n' % (
+                name, 1e3 * (time.perf_counter() - t0), {k: round(1e3 * v, 2) for k, v in ctx.timers().items()}))
+            pstats.Stats(pr, stream=buf).sort_stats('cumulative').print_stats(45)
+        open(args.profile_host, 'w').write(buf.getvalue())
+
     gram_ms, scan_ms = [], []
     ctx.timer_reset()
     l0 = ctx.launch_count()
@@ -307,14 +327,17 @@ def main():
     timers = ctx.timers()
 
     e2e = None
+    e2e_timers = {}
     if not args.no_e2e:
         step_e2e()
         barrier()
+        ctx.timer_reset()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             res_e, ps_e = step_e2e()
         barrier()
         t_e2e = time.perf_counter() - t0
+        e2e_timers = ctx.timers()
     if world > 1:
         tt = torch.tensor([t_res, t_e2e if not args.no_e2e else 0.0], dtype=torch.float64, device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -322,10 +345,13 @@ def main():
     else:
         t_e2e_max = t_e2e if not args.no_e2e else 0.0
     if not args.no_e2e:
-        h2d = m_loc * n + (n * n * 8 if world == 1 else 0) + n * 8 * 2
+        # K is downloaded to the caller (read-only, pinned) but its device copy is kept and found again by
+        # add_random_effect: no K upload.  Uploads: genotypes + X|Y columns for the two null fits.
+        h2d = m_loc * n + n * 8 * 2 * 2
         d2h = (n * n * 8 if world == 1 else 0) + 5 * m_loc * 8
         e2e = {'value': m * args.steps / t_e2e_max, 'unit': 'SNP-tests/s', 'h2d_bytes_per_step': int(h2d),
-               'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * t_e2e_max / args.steps}
+               'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * t_e2e_max / args.steps,
+               'stage_seconds_per_step': {k: v / args.steps for k, v in e2e_timers.items()}}
 
     if rank == 0:
         value = m * args.steps / t_res

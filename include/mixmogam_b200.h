@@ -61,7 +61,7 @@ int64_t mmg_launch_count(mmg_ctx* ctx);
 int mmg_timer_get(mmg_ctx* ctx, const char* name, double* seconds, int64_t* calls);
 int mmg_timer_reset(mmg_ctx* ctx);
 /* duration (ms) of the most recent launch of the dominant kernels, measured with CUDA
- * events on the launching stream: which = "gram" | "scan" */
+ * events on the launching stream: which = "gram" | "scan" | "perm" | "ibd" */
 int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms);
 
 /* pinned host memory for callers that want full-rate PCIe copies */
@@ -147,10 +147,19 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double 
                        int impl, int64_t snp_begin, int64_t snp_count,
                        double* ps, double* f_stats, double* rss, double* var_perc,
                        double* xx, double* dots);
+/* Phenotype-batched scan: T phenotypes scanned against one genotype block in ONE launch (BASELINE.json configs[2];
+ * the reference calls linear_models.emmax once per phenotype, linear_models.py:1790).  R[t] is the rotation of
+ * phenotype t (its own delta_t enters through H_t), V[t] its residual phenotype in the rotated space ([T x n_out]),
+ * h0_rss[t] its null RSS.  int8 tcgen05 path.  Outputs are [T x snp_count], any may be NULL. */
+int mmg_emmax_scan_multi_f64(mmg_ctx* ctx, const mmg_mat* R, int T, const double* V, const double* h0_rss, double n_p,
+                             int64_t snp_begin, int64_t snp_count,
+                             double* ps, double* f_stats, double* rss, double* var_perc, double* xx);
 /* _emmax_permutations_ inner loop (linear_models.py:1157-1164): with centred SNPs x_c = x - mean(x),
  * x~ = R x_c, for each permuted phenotype column W[:,p] (already rotated back: W = R' Ys, [n x P]):
  *     ratio[p] = max over SNPs of (x_c.W[:,p])^2 / (x~.x~)
- * so that min_rss[p] = |Ys_p|^2 - ratio[p].  ratio_inout is max-accumulated (initialise to 0). */
+ * so that min_rss[p] = |Ys_p|^2 - ratio[p].  ratio_inout is max-accumulated (initialise to 0).
+ * impl: MMG_IMPL_TCGEN05 (default) = x_c'(R'R)x_c by the int8 quadratic-form scan of R(I - 11'/n), then an int8
+ *       tcgen05 GEMM of the genotype block with 8 exact digit planes of W;  MMG_IMPL_DMMA = FP64 tensor cores. */
 int mmg_emmax_perm_scan_f64(mmg_ctx* ctx, mmg_mat R, mmg_mat W, int centre, int impl,
                             int64_t snp_begin, int64_t snp_count, double* ratio_inout);
 /* scipy.stats.f.sf(f, dfn, dfd) (linear_models.py:1349,1172) on the device, FP64 */

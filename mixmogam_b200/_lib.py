@@ -8,6 +8,7 @@ context without a B200, raises.  Build the library with `python -c "import __gra
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -74,6 +75,7 @@ SIGNATURES = {
     'mmg_reml_f64': (C.c_int, [_c_ctx, _vp, _vp, _i64, _i64, _vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _i64, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_emmax_scan_multi_f64': (C.c_int, [_c_ctx, _vp, C.c_int, _vp, _vp, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_perm_scan_f64': (C.c_int, [_c_ctx, _i64, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
     'mmg_f_sf_f64': (C.c_int, [_c_ctx, _vp, _i64, C.c_double, C.c_double, _vp]),
     'mmg_microbench': (C.c_int, [_c_ctx, C.c_char_p, _dp]),
@@ -134,9 +136,9 @@ class DeviceMatrix(object):
         assert a.shape == self.shape, (a.shape, self.shape)
         self.ctx._ck(self.ctx.lib.mmg_mat_upload(self.ctx.h, self.handle, _ptr(a), a.shape[1]))
 
-    def download(self, out=None):
+    def download(self, out=None, pinned=False):
         if out is None:
-            out = np.empty(self.shape, dtype=np.float64)
+            out = pinned_empty(self.shape, np.float64) if pinned else np.empty(self.shape, dtype=np.float64)
         self.ctx._ck(self.ctx.lib.mmg_mat_download(self.ctx.h, self.handle, _ptr(out), out.shape[1]))
         return out
 
@@ -220,6 +222,7 @@ class Context(object):
         self.h = h
         self.device = int(device)
         self._snps_key = None
+        self._resident = {}
 
     def _ck(self, rc):
         if rc != 0:
@@ -336,7 +339,37 @@ class Context(object):
             a = a.host()
         if isinstance(a, DeviceMatrix):
             return a
+        hit = self.lookup_resident(a)
+        if hit is not None:
+            return hit.copy()
         return DeviceMatrix.from_host(self, a)
+
+    # ---- host arrays this context produced and still holds on the device (the kinship handed back by
+    #      calc_ibs_kinship is usually passed straight into add_random_effect: skip the 0.8 GB round trip) ----
+    def remember_resident(self, host, dev):
+        host.flags.writeable = False
+        base = np.asarray(host)
+        key = (base.ctypes.data, base.shape)
+        self._resident[key] = (dev, self._fingerprint(base), weakref.ref(base.base if base.base is not None else base))
+        while len(self._resident) > 2:
+            k0 = next(iter(self._resident))
+            self._resident.pop(k0)[0].free()
+
+    def lookup_resident(self, a):
+        # only read-only arrays qualify: the host copy cannot have diverged from the device copy
+        if (not self._resident or not isinstance(a, np.ndarray) or a.dtype != np.float64 or not a.flags.c_contiguous
+                or a.flags.writeable):
+            return None
+        base = np.asarray(a)
+        ent = self._resident.get((base.ctypes.data, base.shape))
+        if ent is None:
+            return None
+        dev, fp, ref = ent
+        if ref() is None or not dev.handle or self._fingerprint(base) != fp:
+            self._resident.pop((base.ctypes.data, base.shape), None)
+            dev.free()
+            return None
+        return dev
 
     def gemm(self, A, B, C_out=None, ta=False, tb=False, alpha=1.0, beta=0.0):
         m = A.shape[1] if ta else A.shape[0]
@@ -442,6 +475,23 @@ class Context(object):
                                              _ptr(out.get('dots'))))
         return out
 
+    def emmax_scan_multi(self, Rs, V, h0_rss, n_p, snp_begin=0, snp_count=None, want=('ps', 'f_stats', 'rss', 'var_perc')):
+        """T phenotypes in one launch: Rs = list of T rotations (DeviceMatrix), V [T x n_out], h0_rss [T].
+        Returns a dict of [T x snp_count] arrays."""
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        T = len(Rs)
+        V = np.ascontiguousarray(np.asarray(V, dtype=np.float64)).reshape(T, -1)
+        assert V.shape[1] == Rs[0].shape[0], (V.shape, Rs[0].shape)
+        h0 = np.ascontiguousarray(np.asarray(h0_rss, dtype=np.float64).reshape(T))
+        handles = np.array([r.handle for r in Rs], dtype=np.int64)
+        out = {k: np.empty((T, snp_count), dtype=np.float64) for k in want}
+        self._ck(self.lib.mmg_emmax_scan_multi_f64(self.h, _ptr(handles), T, _ptr(V), _ptr(h0), float(n_p), snp_begin, snp_count,
+                                                   _ptr(out.get('ps')), _ptr(out.get('f_stats')), _ptr(out.get('rss')),
+                                                   _ptr(out.get('var_perc')), _ptr(out.get('xx'))))
+        return out
+
     def emmax_perm_scan(self, R, Wt, ratio, centre=True, impl=IMPL_AUTO, snp_begin=0, snp_count=None):
         m, n = self.snps_shape()
         if snp_count is None:
@@ -493,25 +543,52 @@ def get_context(device=None):
     return ctx
 
 
+class _PinnedBlock(object):
+    """Owner of one page-locked host allocation; exposes it to numpy through __array_interface__ so that every
+    array (and view) built on it keeps it alive.  When the last view dies the block goes back to a small pool:
+    cudaHostAlloc of a 0.8 GB kinship costs more than copying it."""
+    _pool = {}                      # nbytes -> [ptr]
+    _pool_lock = threading.Lock()
+    _POOL_MAX_PER_SIZE = 2
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        with _PinnedBlock._pool_lock:
+            lst = _PinnedBlock._pool.get(self.nbytes)
+            self.ptr = lst.pop() if lst else None
+        if self.ptr is None:
+            lib = load_library()
+            p = C.c_void_p(0)
+            rc = lib.mmg_host_alloc(C.byref(p), self.nbytes)
+            if rc != 0:
+                raise MmgError(rc, lib.mmg_last_error(None).decode())
+            self.ptr = p.value
+        self.__array_interface__ = {'shape': (self.nbytes,), 'typestr': '|u1', 'data': (self.ptr, False), 'version': 3}
+
+    def __del__(self):
+        try:
+            ptr, self.ptr = self.ptr, None
+            if ptr is None:
+                return
+            with _PinnedBlock._pool_lock:
+                lst = _PinnedBlock._pool.setdefault(self.nbytes, [])
+                if len(lst) < _PinnedBlock._POOL_MAX_PER_SIZE:
+                    lst.append(ptr)
+                    return
+            load_library().mmg_host_free(C.c_void_p(ptr))
+        except Exception:
+            pass
+
+
 def pinned_empty(shape, dtype=np.int8):
-    """numpy array backed by page-locked host memory (mmg_host_alloc) for full-rate PCIe copies."""
-    lib = load_library()
+    """numpy array backed by page-locked host memory (mmg_host_alloc) for full-rate PCIe copies.  The memory is
+    released (to a pool) when the array and all its views are garbage collected."""
     dtype = np.dtype(dtype)
-    nbytes = int(np.prod(shape)) * dtype.itemsize
-    p = C.c_void_p(0)
-    rc = lib.mmg_host_alloc(C.byref(p), nbytes)
-    if rc != 0:
-        raise MmgError(rc, lib.mmg_last_error(None).decode())
-    buf = (C.c_char * nbytes).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    _pinned_keepalive[arr.ctypes.data] = p.value
-    return arr
-
-
-_pinned_keepalive = {}
+    nbytes = max(1, int(np.prod(shape)) * dtype.itemsize)
+    blk = _PinnedBlock(nbytes)
+    return np.asarray(blk)[:int(np.prod(shape)) * dtype.itemsize].view(dtype).reshape(shape)
 
 
 def pinned_free(arr):
-    p = _pinned_keepalive.pop(arr.ctypes.data, None)
-    if p is not None:
-        load_library().mmg_host_free(C.c_void_p(p))
+    """Kept for API compatibility: pinned arrays are reference counted now."""
+    return None

@@ -9,6 +9,7 @@
 
 #include "ctx.h"
 #include "fdist.cuh"
+#include "ibd_tc.cuh"
 #include "kinship_kernels.cuh"
 #include "reml.cuh"
 #include "scan_dmma.cuh"
@@ -17,6 +18,35 @@
 
 namespace mmg {
 thread_local std::string g_create_error;
+
+// Temporary device buffer from the stream-ordered pool (cudaMallocAsync): allocation and release are ordered on the
+// context's stream, cost no device synchronisation, and the pool keeps freed blocks for the next call
+// (release threshold = unlimited, set in mmg_create; trimmed when a plain cudaMalloc runs out of memory).
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t alloc(cudaStream_t st, size_t bytes) {
+        s = st;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, st);
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// cudaMalloc for the long-lived blocks (genotypes, Gram, packed operand); gives the async pool's cache back first if needed
+static cudaError_t persistent_malloc(int device, void** ptr, size_t bytes) {
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+        e = cudaMalloc(ptr, bytes);
+    }
+    return e;
+}
 
 // ---- driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda) -------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -55,7 +85,7 @@ static int ensure_scratch(mmg_ctx* ctx, int64_t bytes) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     ctx->scratch = nullptr;
     ctx->scratch_bytes = 0;
-    MMG_CUDA(ctx, cudaMalloc(&ctx->scratch, bytes));
+    MMG_CUDA(ctx, persistent_malloc(ctx->device, &ctx->scratch, bytes));
     ctx->scratch_bytes = bytes;
     return MMG_OK;
 }
@@ -77,12 +107,22 @@ static int env_int(const char* var, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+static uint64_t env_policy(const char* var, uint64_t dflt) {
+    const char* e = getenv(var);
+    if (!e) return dflt;
+    if (!strcmp(e, "first")) return L2_EVICT_FIRST;
+    if (!strcmp(e, "last")) return L2_EVICT_LAST;
+    if (!strcmp(e, "normal")) return L2_EVICT_NORMAL;
+    return dflt;
+}
+
 // Launch the tcgen05 GEMM with a cluster of CS CTAs.  The persistent grid is the number of clusters that can be
 // co-resident (cudaOccupancyMaxActiveClusters; clusters of 4 do not tile every GPC) times CS.
 template <class Epi, int CS>
 static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcTile* tiles_d, int num_groups,
                           int tiles_per_group, int table_stride, int group_m_step, int rank_m_step,
-                          const typename Epi::Params& ep, const char* name) {
+                          const typename Epi::Params& ep, const char* name, uint64_t hint_a = L2_EVICT_NORMAL,
+                          uint64_t hint_b = L2_EVICT_NORMAL) {
     auto kern = tc_gemm_i8_kernel<Epi, CS>;
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(TC_THREADS);
@@ -105,8 +145,10 @@ static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMa
     const int cgroups = (num_groups + CS - 1) / CS;
     const int clusters = std::max(1, std::min(cgroups, max_clusters));
     cfg.gridDim = dim3((unsigned)(clusters * CS));
+    // L2 eviction priority of the two operand streams: MMG_TC_HINT_A / MMG_TC_HINT_B = normal | first | last
+    const uint64_t pa = env_policy("MMG_TC_HINT_A", hint_a), pb = env_policy("MMG_TC_HINT_B", hint_b);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tiles_d, num_groups, tiles_per_group, table_stride, group_m_step,
-                                       rank_m_step, ep);
+                                       rank_m_step, pa, pb, ep);
     ctx->launches += 1;
     if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of %s (cluster %d, grid %d) failed: %s", name, CS, clusters * CS,
                                       cudaGetErrorString(e));
@@ -165,6 +207,13 @@ int mmg_create(int device, mmg_ctx** out) {
         delete ctx;
         return fail(nullptr, MMG_ECUBLAS, "cublas/cusolver handle creation failed");
     }
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cublasSetStream(ctx->cublas, ctx->stream);
     cusolverDnSetStream(ctx->cusolver, ctx->stream);
     cublasSetPointerMode(ctx->cublas, CUBLAS_POINTER_MODE_HOST);
@@ -174,6 +223,10 @@ int mmg_create(int device, mmg_ctx** out) {
     cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<IbdEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<IbdEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<PermEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<PermEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(scan_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
     cudaFuncSetAttribute(scan_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
     *out = ctx;
@@ -184,7 +237,8 @@ int mmg_destroy(mmg_ctx* ctx) {
     if (!ctx) return MMG_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->mats) cudaFree(kv.second.d);
+    for (auto& kv : ctx->mats) cudaFreeAsync(kv.second.d, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->snps);
     cudaFree(ctx->G);
     cudaFree(ctx->pack);
@@ -245,6 +299,8 @@ int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms) {
     MMG_CHECK(ctx, ctx && which && ms, "bad argument");
     if (!strcmp(which, "gram")) *ms = ctx->last_gram_ms;
     else if (!strcmp(which, "scan")) *ms = ctx->last_scan_ms;
+    else if (!strcmp(which, "perm")) *ms = ctx->last_perm_ms;
+    else if (!strcmp(which, "ibd")) *ms = ctx->last_ibd_ms;
     else return fail(ctx, MMG_EBADARG, "unknown kernel '%s'", which);
     return MMG_OK;
 }
@@ -269,7 +325,7 @@ int mmg_mat_create(mmg_ctx* ctx, int64_t rows, int64_t cols, mmg_mat* out) {
     MmgMat m;
     m.rows = rows;
     m.cols = cols;
-    MMG_CUDA(ctx, cudaMalloc(&m.d, (size_t)rows * cols * sizeof(double)));
+    MMG_CUDA(ctx, cudaMallocAsync((void**)&m.d, (size_t)rows * cols * sizeof(double), ctx->stream));
     MMG_CUDA(ctx, cudaMemsetAsync(m.d, 0, (size_t)rows * cols * sizeof(double), ctx->stream));
     *out = ctx->next_mat++;
     ctx->mats[*out] = m;
@@ -279,8 +335,7 @@ int mmg_mat_free(mmg_ctx* ctx, mmg_mat h) {
     MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
     auto it = ctx->mats.find(h);
     if (it == ctx->mats.end()) return MMG_OK;
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(it->second.d);
+    cudaFreeAsync(it->second.d, ctx->stream);        // stream ordered: work already queued on the matrix completes first
     ctx->mats.erase(it);
     return MMG_OK;
 }
@@ -395,14 +450,14 @@ int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat h, double* w_host, double* seconds) {
     int* info_dev = nullptr;
     int rc = MMG_OK;
     do {
-        if (cudaMalloc(&w_dev, n * sizeof(double)) != cudaSuccess || cudaMalloc(&info_dev, sizeof(int)) != cudaSuccess) {
+        if (persistent_malloc(ctx->device, (void**)&w_dev, n * sizeof(double)) != cudaSuccess || persistent_malloc(ctx->device, (void**)&info_dev, sizeof(int)) != cudaSuccess) {
             rc = fail(ctx, MMG_EOOM, "syevd: allocation failed");
             break;
         }
         cusolverStatus_t st = cusolverDnXsyevd_bufferSize(ctx->cusolver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
                                                           CUDA_R_64F, A->d, n, CUDA_R_64F, w_dev, CUDA_R_64F, &ws_dev, &ws_host);
         if (st != CUSOLVER_STATUS_SUCCESS) { rc = fail(ctx, MMG_ECUSOLVER, "Xsyevd_bufferSize status %d", (int)st); break; }
-        if (ws_dev && cudaMalloc(&buf_dev, ws_dev) != cudaSuccess) { rc = fail(ctx, MMG_EOOM, "syevd: workspace %zu B", ws_dev); break; }
+        if (ws_dev && persistent_malloc(ctx->device, &buf_dev, ws_dev) != cudaSuccess) { rc = fail(ctx, MMG_EOOM, "syevd: workspace %zu B", ws_dev); break; }
         if (ws_host) buf_host = malloc(ws_host);
         st = cusolverDnXsyevd(ctx->cusolver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A->d, n,
                               CUDA_R_64F, w_dev, CUDA_R_64F, buf_dev, ws_dev, buf_host, ws_host, info_dev);
@@ -443,7 +498,7 @@ int mmg_snps_reserve(mmg_ctx* ctx, int64_t m, int64_t n) {
     const int64_t pitch = round_up(n, 256);   // zero padded: kernels read whole 16/32-byte groups up to the next 256
     if (!(ctx->snps && ctx->m == m && ctx->n == n)) {
         MMG_TRY(mmg_snps_free(ctx));
-        MMG_CUDA(ctx, cudaMalloc(&ctx->snps, (size_t)m * pitch));
+        MMG_CUDA(ctx, persistent_malloc(ctx->device, (void**)&ctx->snps, (size_t)m * pitch));
         ctx->m = m;
         ctx->n = n;
         ctx->pitch = pitch;
@@ -455,6 +510,7 @@ int mmg_snps_write(mmg_ctx* ctx, int64_t row0, const int8_t* snps, int64_t rows,
     MMG_CHECK(ctx, ctx && ctx->snps && snps && row0 >= 0 && rows >= 0 && row0 + rows <= ctx->m && ld >= ctx->n,
               "mmg_snps_write: bad argument");
     StageTimer tm(ctx, "h2d");
+    // one strided DMA; measured at the PCIe rate (52 GB/s from page-locked memory), a staged 1-D copy + re-pitch kernel was no faster
     if (rows)
         MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->snps + row0 * ctx->pitch, ctx->pitch, snps, ld, ctx->n, rows, cudaMemcpyHostToDevice,
                                         ctx->stream));
@@ -551,7 +607,7 @@ int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, i
     if (!ctx->G || ctx->g_pad != g_pad) {
         cudaFree(ctx->G);
         ctx->G = nullptr;
-        MMG_CUDA(ctx, cudaMalloc(&ctx->G, (size_t)g_pad * g_pad * sizeof(int32_t)));
+        MMG_CUDA(ctx, persistent_malloc(ctx->device, (void**)&ctx->G, (size_t)g_pad * g_pad * sizeof(int32_t)));
         ctx->g_pad = g_pad;
         reset = 1;
     }
@@ -569,7 +625,7 @@ int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, i
         cudaFree(ctx->pack);
         ctx->pack = nullptr;
         ctx->pack_bytes = 0;
-        MMG_CUDA(ctx, cudaMalloc(&ctx->pack, need));
+        MMG_CUDA(ctx, persistent_malloc(ctx->device, (void**)&ctx->pack, need));
         ctx->pack_bytes = need;
     }
     MMG_CUDA(ctx, cudaMemsetAsync(ctx->flag_d, 0, sizeof(int), ctx->stream));
@@ -684,19 +740,10 @@ __global__ void mirror_lower_to_upper_kernel(double* __restrict__ K, int64_t ld,
     if (c < n && c > r) K[(int64_t)r * ld + c] = K[(int64_t)c * ld + r];
 }
 
-int mmg_kinship_ibd_accumulate_f64(mmg_ctx* ctx, mmg_mat K_acc, int64_t snp_begin, int64_t snp_count, const uint8_t* snp_mask,
-                                   int64_t* used) {
-    MmgMat* K = ctx ? get_mat(ctx, K_acc) : nullptr;
-    MMG_CHECK(ctx, K && ctx->snps, "mmg_kinship_ibd_accumulate_f64: need resident genotypes and an accumulator");
-    MMG_CHECK(ctx, K->rows == ctx->n && K->cols == ctx->n, "K_acc must be n x n");
-    MMG_CHECK(ctx, snp_begin >= 0 && snp_count >= 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
-    StageTimer tm(ctx, "ibd");
-    std::vector<long long> rows;
-    rows.reserve(snp_count);
-    for (int64_t s = 0; s < snp_count; ++s)
-        if (!snp_mask || snp_mask[s]) rows.push_back(snp_begin + s);
-    if (used) *used = (int64_t)rows.size();
-    if (rows.empty()) return MMG_OK;
+}  // extern "C"
+
+// FP64 library path: standardise rows, cuBLAS dsyrk.  Handles any int8 genotype coding.
+static int ibd_dsyrk_run(mmg_ctx* ctx, MmgMat* K, const std::vector<long long>& rows) {
     const int n = (int)ctx->n;
     const int64_t chunk = 2048;
     const int64_t zbytes = chunk * (int64_t)n * sizeof(double);
@@ -723,6 +770,149 @@ int mmg_kinship_ibd_accumulate_f64(mmg_ctx* ctx, mmg_mat K_acc, int64_t snp_begi
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (bad) return fail(ctx, MMG_EVALUE, "monomorphic SNP in IBD kinship (std == 0; the reference asserts at kinship.py:67)");
     return MMG_OK;
+}
+
+// int8 tensor-core path (ibd_tc.cuh).  *domain_bad is set (and nothing is added to K) when a genotype is outside {0,1,2}.
+static int ibd_tc_run(mmg_ctx* ctx, MmgMat* K, const std::vector<long long>& rows, int* domain_bad) {
+    *domain_bad = 0;
+    const int n = (int)ctx->n;
+    const int64_t count = (int64_t)rows.size();
+    int S = env_int("MMG_IBD_SLICES", 6);
+    S = std::max(1, std::min(S, IBD_MAX_SLICES));
+    const int64_t g_pad = round_up(n, 256), n_padM = g_pad;
+    const int64_t dig_pitch = round_up(count, 128) + 128;
+    DevBuf st, dig, Gw, P;
+    // st: sums[m] | sumsq[m] | rows[count] (int64)  then  w | mean | coef [count] | u[g_pad] | cacc | amax (8-byte words)
+    const int64_t n64 = 2 * ctx->m + count;
+    const int64_t nd = 3 * count + g_pad + 2;
+    MMG_CUDA(ctx, st.alloc(ctx->stream, (size_t)(n64 + nd) * 8));
+    long long* d_sums = st.as<long long>();
+    long long* d_sumsq = d_sums + ctx->m;
+    long long* d_rows = d_sumsq + ctx->m;
+    double* d_w = (double*)(d_rows + count);
+    double* d_mean = d_w + count;
+    double* d_coef = d_mean + count;
+    double* d_u = d_coef + count;
+    double* d_c = d_u + g_pad;
+    unsigned long long* d_amax = (unsigned long long*)(d_c + 1);
+    MMG_CUDA(ctx, cudaMemsetAsync(d_u, 0, (size_t)(g_pad + 2) * 8, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_rows, rows.data(), (size_t)count * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, cudaMemsetAsync(ctx->flag_d, 0, sizeof(int), ctx->stream));
+    snp_row_sums_kernel<<<(unsigned)((ctx->m + 7) / 8), 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, ctx->m, n, d_sums, d_sumsq);
+    MMG_TRY(launch_check(ctx, "snp_row_sums_kernel"));
+    ibd_weights_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(d_sums, d_sumsq, d_rows, count, n, d_w, d_mean, d_amax,
+                                                                                 ctx->flag_d);
+    MMG_TRY(launch_check(ctx, "ibd_weights_kernel"));
+    double amax = 0.0;
+    int bad = 0;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad & 1) return fail(ctx, MMG_EVALUE, "monomorphic SNP in IBD kinship (std == 0; the reference asserts at kinship.py:67)");
+    if (!(amax > 0.0) || !std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "IBD kinship: bad weights (max %g)", amax);
+    const int E = ilogb(amax) + 2;
+    MMG_CUDA(ctx, dig.alloc(ctx->stream, (size_t)S * dig_pitch));
+    MMG_CUDA(ctx, cudaMemsetAsync(dig.p, 0, (size_t)S * dig_pitch, ctx->stream));
+    ibd_digits_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(d_w, d_mean, count, ldexp(1.0, -E), ldexp(1.0, E), S,
+                                                                                dig.as<int8_t>(), dig_pitch, d_coef, d_c);
+    MMG_TRY(launch_check(ctx, "ibd_digits_kernel"));
+    const int slab = 2048;
+    snp_weighted_colsum_kernel<<<dim3((unsigned)((n + 1023) / 1024), (unsigned)((count + slab - 1) / slab)), 256, 0, ctx->stream>>>(
+        ctx->snps, ctx->pitch, d_rows, d_coef, count, slab, n, d_u);
+    MMG_TRY(launch_check(ctx, "snp_weighted_colsum_kernel"));
+
+    MMG_CUDA(ctx, Gw.alloc(ctx->stream, (size_t)g_pad * g_pad * sizeof(double)));
+    MMG_CUDA(ctx, cudaMemsetAsync(Gw.p, 0, (size_t)g_pad * g_pad * sizeof(double), ctx->stream));
+    int64_t chunk = (int64_t)(3.0e9 / ((double)(S + 1) * (double)n_padM)) / 128 * 128;
+    chunk = std::max<int64_t>(4096, std::min<int64_t>(65536, chunk));
+    chunk = std::min(chunk, round_up(count, 128));
+    const int64_t p_pitch = chunk;
+    MMG_CUDA(ctx, P.alloc(ctx->stream, (size_t)(S + 1) * n_padM * p_pitch));
+    MMG_CUDA(ctx, cudaMemsetAsync(P.p, 0, (size_t)(S + 1) * n_padM * p_pitch, ctx->stream));
+
+    int cs = env_int("MMG_GRAM_CLUSTER", 2);
+    if (cs != 1) cs = 2;
+    const int tiles_n = (n + TC_BN - 1) / TC_BN;
+    std::vector<TcTile> tiles;
+    int entries = 0;
+    for (int jn = 0; jn < tiles_n; ++jn)
+        for (int im = 0; im <= 2 * jn + 1; im += cs) {
+            for (int k = 0; k < S; ++k) {
+                TcTile tl{};
+                tl.m0 = (int)((int64_t)(k + 1) * n_padM + (int64_t)im * TC_BM);
+                tl.n0 = jn * TC_BN;
+                tl.aux0 = k;
+                tiles.push_back(tl);
+            }
+            ++entries;
+        }
+    IbdEpi::Params ep{};
+    ep.Gw = Gw.as<double>();
+    ep.ld = g_pad;
+    ep.n_padM = n_padM;
+    for (int k = 0; k < S; ++k) ep.w[k] = ldexp(1.0, E - 6 * (k + 1));
+    double ibd_ms = 0.0;
+    for (int64_t r0 = 0; r0 < count; r0 += chunk) {
+        const int64_t cnt = std::min(chunk, count - r0);
+        const int64_t kbytes = round_up(cnt, 128);
+        pack_ibd_kernel<<<dim3((unsigned)((cnt + 127) / 128), (unsigned)((n + 63) / 64)), 256, 0, ctx->stream>>>(
+            ctx->snps, ctx->pitch, d_rows + r0, cnt, n, dig.as<int8_t>() + r0, dig_pitch, S, P.as<int8_t>(), p_pitch, n_padM, ctx->flag_d);
+        MMG_TRY(launch_check(ctx, "pack_ibd_kernel"));
+        CUtensorMap tmA, tmB;
+        MMG_TRY(make_tmap_u8(ctx, &tmA, P.p, kbytes, (int64_t)(S + 1) * n_padM, p_pitch, TC_BM));
+        MMG_TRY(make_tmap_u8(ctx, &tmB, P.p, kbytes, n, p_pitch, TC_BN / cs));
+        for (auto& t : tiles) { t.kb0 = 0; t.kb1 = (int)(kbytes / TC_BK); }
+        MMG_TRY(ensure_tiles(ctx, tiles));
+        cudaEventRecord(ctx->kev0, ctx->stream);
+        if (cs == 2)
+            MMG_TRY((launch_tc_gemm<IbdEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, entries * 2, S, S, 0, TC_BM, ep, "tc_gemm_i8_kernel<IbdEpi,2>")));
+        else
+            MMG_TRY((launch_tc_gemm<IbdEpi, 1>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, entries, S, S, 0, 0, ep, "tc_gemm_i8_kernel<IbdEpi,1>")));
+        cudaEventRecord(ctx->kev1, ctx->stream);
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the tile table and P are rewritten by the next chunk
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        ibd_ms += ms;
+    }
+    ctx->last_ibd_ms = ibd_ms;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad & 2) {
+        *domain_bad = 1;
+        return MMG_OK;
+    }
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    ibd_finalize_add_kernel<<<grid, 256, 0, ctx->stream>>>(Gw.as<double>(), g_pad, n, d_u, d_c, K->d, K->cols);
+    MMG_TRY(launch_check(ctx, "ibd_finalize_add_kernel"));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+extern "C" {
+
+int mmg_kinship_ibd_accumulate_f64(mmg_ctx* ctx, mmg_mat K_acc, int64_t snp_begin, int64_t snp_count, const uint8_t* snp_mask,
+                                   int64_t* used) {
+    MmgMat* K = ctx ? get_mat(ctx, K_acc) : nullptr;
+    MMG_CHECK(ctx, K && ctx->snps, "mmg_kinship_ibd_accumulate_f64: need resident genotypes and an accumulator");
+    MMG_CHECK(ctx, K->rows == ctx->n && K->cols == ctx->n, "K_acc must be n x n");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count >= 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm(ctx, "ibd");
+    std::vector<long long> rows;
+    rows.reserve(snp_count);
+    for (int64_t s = 0; s < snp_count; ++s)
+        if (!snp_mask || snp_mask[s]) rows.push_back(snp_begin + s);
+    if (used) *used = (int64_t)rows.size();
+    if (rows.empty()) return MMG_OK;
+    // MMG_IBD_IMPL = tcgen05 (default; genotypes in {0,1,2}) | dsyrk (FP64 library GEMM, any int8 coding)
+    const char* e = getenv("MMG_IBD_IMPL");
+    bool use_tc = !(e && !strcmp(e, "dsyrk"));
+    if (use_tc) {
+        int domain_bad = 0;
+        MMG_TRY(ibd_tc_run(ctx, K, rows, &domain_bad));
+        if (!domain_bad) return MMG_OK;
+    }
+    return ibd_dsyrk_run(ctx, K, rows);
 }
 
 // ======================================================================================================
@@ -766,20 +956,16 @@ int mmg_reml_f64(mmg_ctx* ctx, const double* eig_vals, const double* sq_etas, in
 // ======================================================================================================
 }  // extern "C"
 
-namespace {
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    template <class T> T* as() { return reinterpret_cast<T*>(p); }
-};
-}  // namespace
+__global__ void means_from_sums_kernel(const long long* __restrict__ sums, int64_t count, double inv_n, double* __restrict__ mu) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) mu[i] = (double)sums[i] * inv_n;
+}
 
 // zero-padded copy of R: rows -> multiple of 128, cols -> multiple of 128
 static int pad_matrix(mmg_ctx* ctx, const MmgMat* R, DevBuf& out, int64_t* rows_pad, int64_t* ld) {
     *rows_pad = round_up(R->rows, 128);
     *ld = round_up(R->cols, 128);
-    MMG_CUDA(ctx, out.alloc((size_t)(*rows_pad) * (*ld) * sizeof(double)));
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)(*rows_pad) * (*ld) * sizeof(double)));
     MMG_CUDA(ctx, cudaMemsetAsync(out.p, 0, (size_t)(*rows_pad) * (*ld) * sizeof(double), ctx->stream));
     MMG_CUDA(ctx, cudaMemcpy2DAsync(out.p, (*ld) * sizeof(double), R->d, R->cols * sizeof(double), R->cols * sizeof(double), R->rows,
                                     cudaMemcpyDeviceToDevice, ctx->stream));
@@ -808,30 +994,20 @@ static int scan_tc_slices() {
     return S;
 }
 
-static int scan_tc_run(mmg_ctx* ctx, const MmgMat* R, const double* V, double h0_rss, double n_p, double lbeta, int64_t snp_begin,
-                       int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p, double* d_vp) {
-    const int64_t n = ctx->n, n_out = R->rows;
-    const int S = scan_tc_slices();
-    const int64_t n_padN = round_up(n, TC_BN), ldq = round_up(n, TC_BK);
-    DevBuf A, Bq, vec;
-    MMG_CUDA(ctx, A.alloc((size_t)n * n * sizeof(double)));
-    MMG_CUDA(ctx, Bq.alloc((size_t)S * n_padN * ldq));
-    MMG_CUDA(ctx, vec.alloc((size_t)(n_padN + n_out + 1) * sizeof(double)));
-    double* d_v = vec.as<double>();
-    double* d_y = d_v + n_padN;
-    unsigned long long* d_amax = (unsigned long long*)(d_y + n_out);
-    MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)(n_padN + n_out + 1) * sizeof(double), ctx->stream));
-    MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)S * n_padN * ldq, ctx->stream));
-    MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+// Digit planes of A = R'R (lower triangle, off-diagonal doubled) into Bq (S planes of [n_padN x ldq]) and v = R'y into
+// d_v; returns the binary exponent E used for the scaling.  `A` is an n x n FP64 work matrix.
+static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, double* A, unsigned long long* d_amax, int S,
+                        int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, int* E_out) {
+    const int64_t n = R->cols, n_out = R->rows;
     const double one = 1.0, zero = 0.0;
     // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
     // is the row-major LOWER triangle A[j][i], i <= j -- exactly the operand the slices are cut from.
-    MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero,
-                                A.as<double>(), (int)n));
+    MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero, A, (int)n));
     // v = R' y~  (x~.y~ = x.v)
-    MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1));
+    if (d_y) MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1));
+    MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
     dim3 agrid(8, (unsigned)n);
-    quad_amax_kernel<<<agrid, 256, 0, ctx->stream>>>(A.as<double>(), n, (int)n, d_amax);
+    quad_amax_kernel<<<agrid, 256, 0, ctx->stream>>>(A, n, (int)n, d_amax);
     MMG_TRY(launch_check(ctx, "quad_amax_kernel"));
     double amax = 0.0;
     MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -839,53 +1015,203 @@ static int scan_tc_run(mmg_ctx* ctx, const MmgMat* R, const double* V, double h0
     if (!(amax > 0.0) || !std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "scan: R'R is zero or not finite (max |a| = %g)", amax);
     const int E = ilogb(amax) + 2;                       // |c a| 2^-E < 1/2
     dim3 sgrid((unsigned)((n + 255) / 256), (unsigned)n);
-    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A.as<double>(), n, (int)n, ldexp(1.0, -E), S, Bq.as<int8_t>(), n_padN, ldq);
+    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A, n, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq);
     MMG_TRY(launch_check(ctx, "quad_slice_kernel"));
+    *E_out = E;
+    return MMG_OK;
+}
+
+// T phenotypes (each with its own rotation R_t, residual y~_t and h0_rss_t) in one launch.  Device outputs are
+// [T][snp_count]; any may be NULL.
+static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const double* V, const double* h0_rss, double n_p, double lbeta,
+                       int64_t snp_begin, int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p,
+                       double* d_vp) {
+    const int64_t n = ctx->n, n_out = Rs[0]->rows;
+    const int S = scan_tc_slices();
+    const int64_t n_padN = round_up(n, TC_BN), ldq = round_up(n, TC_BK);
+    const int64_t plane = n_padN * ldq;
+    DevBuf A, Bq, vec;
+    MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)n * n * sizeof(double)));
+    MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S * plane));
+    // vec: v[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | amax
+    const int64_t nd = (int64_t)T * n_padN + (int64_t)T * n_out + 2 * T + 1;
+    MMG_CUDA(ctx, vec.alloc(ctx->stream, (size_t)nd * sizeof(double)));
+    double* d_v = vec.as<double>();
+    double* d_y = d_v + (int64_t)T * n_padN;
+    double* d_h0 = d_y + (int64_t)T * n_out;
+    double* d_es = d_h0 + T;
+    unsigned long long* d_amax = (unsigned long long*)(d_es + T);
+    MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)nd * sizeof(double), ctx->stream));
+    MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)T * S * plane, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> escale((size_t)T);
+    for (int t = 0; t < T; ++t) {
+        int E = 0;
+        MMG_TRY(quad_prepare(ctx, Rs[t], d_y + (int64_t)t * n_out, A.as<double>(), d_amax, S, Bq.as<int8_t>() + (int64_t)t * S * plane,
+                             n_padN, ldq, d_v + (int64_t)t * n_padN, &E));
+        escale[t] = ldexp(1.0, E);
+    }
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_es, escale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 
     QuadEpi::Params ep{};
     ep.snps = ctx->snps;
     ep.pitch = ctx->pitch;
     ep.row_begin = snp_begin;
     ep.row_count = snp_count;
-    for (int k = 0; k < S; ++k) ep.w[k] = ldexp(1.0, E - 7 * (k + 1));
+    for (int k = 0; k < S; ++k) ep.w[k] = ldexp(1.0, -7 * (k + 1));
+    ep.escale = d_es;
     ep.v = d_v;
-    ep.h0_rss = h0_rss;
+    ep.v_stride = n_padN;
+    ep.h0_rss = d_h0;
     ep.n_p = n_p;
     ep.lbeta = lbeta;
+    ep.out_stride = snp_count;
     ep.xx = d_xx; ep.xy = d_xy; ep.rss = d_rss; ep.f = d_f; ep.p = d_p; ep.var_perc = d_vp;
 
-    // one shared tile table: for every 256-column tile jb, one tile per slice; K only up to the diagonal
+    // one shared tile table: for every phenotype, for every 256-column tile jb, one tile per slice; K only up to the diagonal
     const int tiles_n = (int)(n_padN / TC_BN), kb_total = (int)(ldq / TC_BK);
     std::vector<TcTile> tiles;
-    for (int jb = 0; jb < tiles_n; ++jb)
-        for (int k = 0; k < S; ++k) {
-            TcTile t{};
-            t.m0 = 0;
-            t.n0 = (int)(k * n_padN + (int64_t)jb * TC_BN);
-            t.kb0 = 0;
-            t.kb1 = std::min(kb_total, (jb + 1) * (TC_BN / TC_BK));
-            t.aux0 = k;
-            t.aux1 = (k == 0) ? 1 : 0;
-            t.col0 = jb * TC_BN;
-            tiles.push_back(t);
-        }
+    tiles.reserve((size_t)T * tiles_n * S);
+    for (int t = 0; t < T; ++t)
+        for (int jb = 0; jb < tiles_n; ++jb)
+            for (int k = 0; k < S; ++k) {
+                TcTile tl{};
+                tl.m0 = 0;
+                tl.n0 = (int)(((int64_t)t * S + k) * n_padN + (int64_t)jb * TC_BN);
+                tl.kb0 = 0;
+                tl.kb1 = std::min(kb_total, (jb + 1) * (TC_BN / TC_BK));
+                tl.aux0 = k;
+                tl.aux1 = (t << QS_PHEN_SHIFT) | (k == 0 ? QS_FLAG_XY : 0) | ((jb == 0 && k == 0) ? QS_FLAG_FIRST : 0) |
+                          ((jb == tiles_n - 1 && k == S - 1) ? QS_FLAG_LAST : 0);
+                tl.col0 = jb * TC_BN;
+                tiles.push_back(tl);
+            }
+    MMG_CHECK(ctx, (int64_t)T * S * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
     MMG_TRY(ensure_tiles(ctx, tiles));
     int cs = env_int("MMG_SCAN_CLUSTER", 2);
     if (cs != 1 && cs != 2 && cs != 4) cs = 2;
     CUtensorMap tmA, tmB;
     MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
-    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq.p, ldq, (int64_t)S * n_padN, ldq, TC_BN / cs));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq.p, ldq, (int64_t)T * S * n_padN, ldq, TC_BN / cs));
     const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
     cudaEventRecord(ctx->kev0, ctx->stream);
     const TcTile* td = (const TcTile*)ctx->tiles_d;
     if (cs == 4)
-        MMG_TRY((launch_tc_gemm<QuadEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,4>")));
+        MMG_TRY((launch_tc_gemm<QuadEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,4>", L2_EVICT_FIRST, L2_EVICT_LAST)));
     else if (cs == 2)
-        MMG_TRY((launch_tc_gemm<QuadEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,2>")));
+        MMG_TRY((launch_tc_gemm<QuadEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,2>", L2_EVICT_FIRST, L2_EVICT_LAST)));
     else
-        MMG_TRY((launch_tc_gemm<QuadEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,1>")));
+        MMG_TRY((launch_tc_gemm<QuadEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,1>", L2_EVICT_FIRST, L2_EVICT_LAST)));
     cudaEventRecord(ctx->kev1, ctx->stream);
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // Bq / A / vec are freed on return
+    return MMG_OK;
+}
+
+// ---- int8 tensor-core permutation scan (linear_models.py:1157-1164) --------------------------------------------
+//   pass 1: xx_s = x_c'(R'R)x_c through the quadratic-form scan of the centred rotation R C (C = I - 11'/n)
+//   pass 2: PermEpi GEMM of the genotype block with the 8 digit planes of W' = Ys'R ([P x n]),
+//           ratio_p = max_s (x_c.W_p)^2 / xx_s
+static int perm_scan_tc(mmg_ctx* ctx, const MmgMat* R, const MmgMat* Wt, int centre, int64_t snp_begin, int64_t snp_count,
+                        double* ratio_inout) {
+    StageTimer tm(ctx, "scan");
+    const int64_t n = ctx->n, n_out = R->rows, P = Wt->rows;
+    const int64_t P_pad = round_up(P, 32), ldq = round_up(n, TC_BK);
+    const double one = 1.0, zero = 0.0;
+    DevBuf Rc, aux, Wq;
+    // aux: ones[n] | r1[n_out] | wsum[P_pad] | mu[snp_count] | xx[snp_count] | ratio[P_pad] | amax | sums[snp_count]
+    const int64_t nd = n + n_out + P_pad + 2 * snp_count + P_pad + 1;
+    MMG_CUDA(ctx, aux.alloc(ctx->stream, (size_t)nd * sizeof(double) + (size_t)snp_count * sizeof(long long)));
+    MMG_CUDA(ctx, cudaMemsetAsync(aux.p, 0, (size_t)nd * sizeof(double), ctx->stream));
+    double* d_ones = aux.as<double>();
+    double* d_r1 = d_ones + n;
+    double* d_wsum = d_r1 + n_out;
+    double* d_mu = d_wsum + P_pad;
+    double* d_xx = d_mu + snp_count;
+    unsigned long long* d_ratio = (unsigned long long*)(d_xx + snp_count);
+    unsigned long long* d_amax = d_ratio + P_pad;
+    long long* d_sums = (long long*)(d_amax + 1);
+    {
+        std::vector<double> ones((size_t)n, 1.0);
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_ones, ones.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // row-major [rows x n] matrices are column-major n x rows: y = A' x gives the row sums
+    MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_T, (int)n, (int)P, &one, Wt->d, (int)n, d_ones, 1, &zero, d_wsum, 1));
+    MmgMat Rcm = *R;
+    if (centre) {
+        MMG_CUDA(ctx, Rc.alloc(ctx->stream, (size_t)n_out * n * sizeof(double)));
+        MMG_CUDA(ctx, cudaMemcpyAsync(Rc.p, R->d, (size_t)n_out * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_T, (int)n, (int)n_out, &one, R->d, (int)n, d_ones, 1, &zero, d_r1, 1));
+        dim3 cgrid((unsigned)((n + 255) / 256), (unsigned)n_out);
+        centre_cols_kernel<<<cgrid, 256, 0, ctx->stream>>>(Rc.as<double>(), n, (int)n_out, (int)n, d_r1, 1.0 / (double)n);
+        MMG_TRY(launch_check(ctx, "centre_cols_kernel"));
+        Rcm.d = Rc.as<double>();
+        snp_row_sums_kernel<<<(unsigned)((snp_count + 7) / 8), 256, 0, ctx->stream>>>(ctx->snps + snp_begin * ctx->pitch, ctx->pitch,
+                                                                                      snp_count, (int)n, d_sums, nullptr);
+        MMG_TRY(launch_check(ctx, "snp_row_sums_kernel"));
+        means_from_sums_kernel<<<(unsigned)((snp_count + 255) / 256), 256, 0, ctx->stream>>>(d_sums, snp_count, 1.0 / (double)n, d_mu);
+        MMG_TRY(launch_check(ctx, "means_from_sums_kernel"));
+    }
+    // pass 1
+    {
+        std::vector<double> y0((size_t)n_out, 0.0);
+        const double h0 = 1.0;
+        const MmgMat* Rs[1] = {&Rcm};
+        MMG_TRY(scan_tc_run(ctx, 1, Rs, y0.data(), &h0, 1.0, 0.0, snp_begin, snp_count, d_xx, nullptr, nullptr, nullptr, nullptr, nullptr));
+    }
+    // digit planes of W'
+    mat_amax_kernel<<<dim3(8, (unsigned)P), 256, 0, ctx->stream>>>(Wt->d, n, (int)P, (int)n, d_amax);
+    MMG_TRY(launch_check(ctx, "mat_amax_kernel"));
+    double amax = 0.0;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "permutation scan: W is not finite");
+    const int E = amax > 0.0 ? ilogb(amax) + 2 : 0;
+    const int64_t wq_rows = P_pad * PS_SLICES;
+    MMG_CUDA(ctx, Wq.alloc(ctx->stream, (size_t)wq_rows * ldq));
+    MMG_CUDA(ctx, cudaMemsetAsync(Wq.p, 0, (size_t)wq_rows * ldq, ctx->stream));
+    perm_slice_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)P), 256, 0, ctx->stream>>>(Wt->d, n, (int)P, (int)n, ldexp(1.0, -E),
+                                                                                                Wq.as<int8_t>(), ldq);
+    MMG_TRY(launch_check(ctx, "perm_slice_kernel"));
+    // pass 2
+    PermEpi::Params ep{};
+    ep.row_count = snp_count;
+    for (int k = 0; k < PS_SLICES; ++k) ep.w[k] = ldexp(1.0, E - 7 * (k + 1));
+    ep.xx = d_xx;
+    ep.mu = centre ? d_mu : nullptr;
+    ep.wsum = d_wsum;
+    ep.ratio = d_ratio;
+    std::vector<TcTile> tiles;
+    for (int b = 0; b < (int)(P_pad / 32); ++b) {
+        TcTile tl{};
+        tl.n0 = b * TC_BN;
+        tl.kb0 = 0;
+        tl.kb1 = (int)(ldq / TC_BK);
+        tl.col0 = b * 32;
+        tiles.push_back(tl);
+    }
+    MMG_TRY(ensure_tiles(ctx, tiles));
+    int cs = env_int("MMG_SCAN_CLUSTER", 2);
+    if (cs != 1 && cs != 2) cs = 2;
+    CUtensorMap tmA, tmB;
+    MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Wq.p, ldq, wq_rows, ldq, TC_BN / cs));
+    const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
+    const TcTile* td = (const TcTile*)ctx->tiles_d;
+    cudaEventRecord(ctx->kev0, ctx->stream);
+    if (cs == 2)
+        MMG_TRY((launch_tc_gemm<PermEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<PermEpi,2>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+    else
+        MMG_TRY((launch_tc_gemm<PermEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<PermEpi,1>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+    cudaEventRecord(ctx->kev1, ctx->stream);
+    std::vector<double> ratio((size_t)P);
+    MMG_CUDA(ctx, cudaMemcpyAsync(ratio.data(), d_ratio, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+    ctx->last_perm_ms = ms;
+    for (int64_t p = 0; p < P; ++p) ratio_inout[p] = std::max(ratio_inout[p], ratio[p]);
     return MMG_OK;
 }
 
@@ -905,7 +1231,7 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
     const double lbeta = lbeta_host(0.5 * n_p, 0.5);
 
     DevBuf out;      // xx, xy, rss, f, p, var_perc  (6 x snp_count doubles) + dots
-    MMG_CUDA(ctx, out.alloc((size_t)(6 + nv) * snp_count * sizeof(double)));
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)(6 + nv) * snp_count * sizeof(double)));
     double* d_xx = out.as<double>();
     double* d_xy = d_xx + snp_count;
     double* d_rss = d_xy + snp_count;
@@ -920,7 +1246,7 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
             DevBuf Rp, Vp;
             int64_t rows_pad = 0, ld = 0;
             MMG_TRY(pad_matrix(ctx, R, Rp, &rows_pad, &ld));
-            MMG_CUDA(ctx, Vp.alloc((size_t)rows_pad * sizeof(double)));
+            MMG_CUDA(ctx, Vp.alloc(ctx->stream, (size_t)rows_pad * sizeof(double)));
             MMG_CUDA(ctx, cudaMemsetAsync(Vp.p, 0, (size_t)rows_pad * sizeof(double), ctx->stream));
             MMG_CUDA(ctx, cudaMemcpyAsync(Vp.p, V, n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             ScanDmmaParams prm{};
@@ -945,7 +1271,8 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
             MMG_TRY(launch_scan_dmma(ctx, false, prm));
             MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         } else {
-            MMG_TRY(scan_tc_run(ctx, R, V, h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp));
+            const MmgMat* Rs[1] = {R};
+            MMG_TRY(scan_tc_run(ctx, 1, Rs, V, &h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp));
             MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
         float ms = 0.f;
@@ -955,8 +1282,8 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
         if (dots) {
             // x~.V[v] = x.(R' V[v]):  W = V R  ([nv x n_out] x [n_out x n]) then an HBM-bound dot kernel
             DevBuf Vd, Wd;
-            MMG_CUDA(ctx, Vd.alloc((size_t)nv * n_out * sizeof(double)));
-            MMG_CUDA(ctx, Wd.alloc((size_t)nv * n * sizeof(double)));
+            MMG_CUDA(ctx, Vd.alloc(ctx->stream, (size_t)nv * n_out * sizeof(double)));
+            MMG_CUDA(ctx, Wd.alloc(ctx->stream, (size_t)nv * n * sizeof(double)));
             MMG_CUDA(ctx, cudaMemcpyAsync(Vd.p, V, (size_t)nv * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             const double one = 1.0, zero = 0.0;
             // row-major W[nv x n] = V[nv x n_out] R[n_out x n]  ->  column-major W' = R' V'
@@ -990,10 +1317,46 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
     return MMG_OK;
 }
 
-__global__ void means_from_sums_kernel(const long long* __restrict__ sums, int64_t count, double inv_n, double* __restrict__ mu) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) mu[i] = (double)sums[i] * inv_n;
+// Phenotype-batched scan (BASELINE.json configs[2]; the reference runs one emmax() per phenotype): T rotations R_t
+// (same shape), V[t] = residual phenotype of t in its rotated space, h0_rss[t]; outputs are [T x snp_count].
+int mmg_emmax_scan_multi_f64(mmg_ctx* ctx, const mmg_mat* Rh, int T, const double* V, const double* h0_rss, double n_p,
+                             int64_t snp_begin, int64_t snp_count, double* ps, double* f_stats, double* rss, double* var_perc,
+                             double* xx) {
+    MMG_CHECK(ctx, ctx && ctx->snps && Rh && V && h0_rss && T >= 1 && T <= (1 << 20), "mmg_emmax_scan_multi_f64: bad argument");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    std::vector<const MmgMat*> Rs((size_t)T);
+    for (int t = 0; t < T; ++t) {
+        Rs[t] = get_mat(ctx, Rh[t]);
+        MMG_CHECK(ctx, Rs[t] && Rs[t]->cols == ctx->n && Rs[t]->rows == Rs[0]->rows, "R[%d]: unknown handle or shape mismatch", t);
+    }
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+    DevBuf out;      // xx, rss, f, p, var_perc: 5 x T x snp_count doubles
+    const int64_t cnt = (int64_t)T * snp_count;
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)5 * cnt * sizeof(double)));
+    double* d_xx = out.as<double>();
+    double* d_rss = d_xx + cnt;
+    double* d_f = d_rss + cnt;
+    double* d_p = d_f + cnt;
+    double* d_vp = d_p + cnt;
+    {
+        StageTimer tm(ctx, "scan");
+        MMG_TRY(scan_tc_run(ctx, T, Rs.data(), V, h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, nullptr, d_rss, d_f, d_p, d_vp));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        ctx->last_scan_ms = ms;
+    }
+    StageTimer tm2(ctx, "d2h");
+    const size_t bytes = (size_t)cnt * sizeof(double);
+    if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (f_stats) MMG_CUDA(ctx, cudaMemcpyAsync(f_stats, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rss) MMG_CUDA(ctx, cudaMemcpyAsync(rss, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_perc) MMG_CUDA(ctx, cudaMemcpyAsync(var_perc, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xx) MMG_CUDA(ctx, cudaMemcpyAsync(xx, d_xx, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
 }
+
 
 int mmg_emmax_perm_scan_f64(mmg_ctx* ctx, mmg_mat Rh, mmg_mat Wh, int centre, int impl, int64_t snp_begin, int64_t snp_count,
                             double* ratio_inout) {
@@ -1001,8 +1364,10 @@ int mmg_emmax_perm_scan_f64(mmg_ctx* ctx, mmg_mat Rh, mmg_mat Wh, int centre, in
     MMG_CHECK(ctx, R && Wt && ctx->snps && ratio_inout, "mmg_emmax_perm_scan_f64: bad argument");
     MMG_CHECK(ctx, R->cols == ctx->n && Wt->cols == ctx->n, "R and W' must have n columns");
     MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
-    MMG_CHECK(ctx, impl == MMG_IMPL_AUTO || impl == MMG_IMPL_DMMA, "the permutation scan runs on the DMMA path");
+    if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_PERM_IMPL", MMG_IMPL_TCGEN05);
+    MMG_CHECK(ctx, impl == MMG_IMPL_TCGEN05 || impl == MMG_IMPL_DMMA, "unsupported impl %d for the permutation scan", impl);
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (impl == MMG_IMPL_TCGEN05) return perm_scan_tc(ctx, R, Wt, centre, snp_begin, snp_count, ratio_inout);
     StageTimer tm(ctx, "scan");
     const int64_t n = ctx->n, P = Wt->rows;
     DevBuf Rp, Wp, aux;
@@ -1011,7 +1376,7 @@ int mmg_emmax_perm_scan_f64(mmg_ctx* ctx, mmg_mat Rh, mmg_mat Wh, int centre, in
     MMG_TRY(pad_matrix(ctx, Wt, Wp, &w_rows, &w_ld));
     // aux: ones[n] | r1[r_rows] | wsum[w_rows] | zeros y[r_rows] | mu[snp_count] | xx[snp_count] | ratio[w_rows] | sums[snp_count]
     const int64_t nd = r_ld + r_rows + w_rows + r_rows + 2 * snp_count + w_rows;
-    MMG_CUDA(ctx, aux.alloc((size_t)nd * sizeof(double) + (size_t)snp_count * sizeof(long long)));
+    MMG_CUDA(ctx, aux.alloc(ctx->stream, (size_t)nd * sizeof(double) + (size_t)snp_count * sizeof(long long)));
     MMG_CUDA(ctx, cudaMemsetAsync(aux.p, 0, (size_t)nd * sizeof(double), ctx->stream));
     double* d_ones = aux.as<double>();
     double* d_r1 = d_ones + r_ld;
@@ -1075,7 +1440,7 @@ int mmg_f_sf_f64(mmg_ctx* ctx, const double* f, int64_t count, double dfn, doubl
     if (count == 0) return MMG_OK;
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     DevBuf buf;
-    MMG_CUDA(ctx, buf.alloc(2 * count * sizeof(double)));
+    MMG_CUDA(ctx, buf.alloc(ctx->stream, 2 * count * sizeof(double)));
     double* d_f = buf.as<double>();
     double* d_o = d_f + count;
     MMG_CUDA(ctx, cudaMemcpyAsync(d_f, f, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1141,8 +1506,8 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
     if (!strcmp(which, "copy")) {
         const int64_t bytes = 2ll << 30;
         DevBuf a, b;
-        MMG_CUDA(ctx, a.alloc(bytes));
-        MMG_CUDA(ctx, b.alloc(bytes));
+        MMG_CUDA(ctx, a.alloc(ctx->stream, bytes));
+        MMG_CUDA(ctx, b.alloc(ctx->stream, bytes));
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(ctx->kev0, ctx->stream);
             bench_copy_kernel<<<ctx->sm_count * 16, 512, 0, ctx->stream>>>(a.as<uint4>(), b.as<uint4>(), bytes / 16);

@@ -36,7 +36,7 @@ struct mmg_ctx {
     int64_t next_mat = 1;
     int64_t launches = 0;
     std::map<std::string, MmgTimer> timers;
-    double last_gram_ms = 0.0, last_scan_ms = 0.0;
+    double last_gram_ms = 0.0, last_scan_ms = 0.0, last_perm_ms = 0.0, last_ibd_ms = 0.0;
 
     // resident genotypes
     int8_t* snps = nullptr;

@@ -9,7 +9,15 @@
 //     q_s += w_k * sum_j acc[s][j] * x[s][j],   w_k = 2^E 128^-(k+1)
 // in FP64.  Because B is lower triangular, N tile jb only needs K in [0, 256(jb+1)): half the MACs of
 // the full rotation.  The same epilogue accumulates x~.y~ = x.(R'y~) and, once a 128-SNP row block has
-// seen every tile, evaluates RSS / F / p (linear_models.py:1345-1349).
+// seen every tile of a phenotype, evaluates RSS / F / p (linear_models.py:1345-1349).
+//
+// Phenotype batching: T phenotypes with their own delta_t (hence their own A_t = R_t'R_t) are scanned in ONE
+// launch -- the tile table lists the slices of A_0, A_1, ... one after the other, the 128-SNP genotype block
+// (operand A of the MMA) is reused from shared memory/L2 by all T*S*ceil(n/256) tiles of its group.
+//
+// Permutation scan (linear_models.py:1157-1164): PermEpi contracts the genotype block with the digit planes
+// of W = R'Ys ([P x n], all permuted phenotypes rotated back), 32 permutations x 8 slices per 256-column
+// tile, and keeps the per-permutation maximum of (x_c.W_p)^2 / (x~_c.x~_c) over SNPs.
 #pragma once
 #include "fdist.cuh"
 #include "tc_gemm.cuh"
@@ -17,25 +25,42 @@
 namespace mmg {
 
 constexpr int QS_MAX_SLICES = 10;
+constexpr int QS_FLAG_XY = 1;        // TcTile.aux1: accumulate x.v on this tile (first slice of a column tile)
+constexpr int QS_FLAG_FIRST = 2;     //              first tile of a phenotype: reset the running sums
+constexpr int QS_FLAG_LAST = 4;      //              last tile of a phenotype: evaluate and store
+constexpr int QS_PHEN_SHIFT = 8;     //              phenotype index = aux1 >> 8
 
 struct QuadEpi {
     struct Params {
         const int8_t* snps;
         int64_t pitch;
         int64_t row_begin, row_count;
-        double w[QS_MAX_SLICES];     // slice weights
-        const double* v;             // [n_padN] R'y~ (zero padded)
-        double h0_rss, n_p, lbeta;
+        double w[QS_MAX_SLICES];     // slice weights 2^(-7(k+1)); the per-phenotype 2^E_t is in escale
+        const double* escale;        // [T] 2^E_t
+        const double* v;             // [T][v_stride] R_t'y~_t (zero padded)
+        int64_t v_stride;
+        const double* h0_rss;        // [T]
+        double n_p, lbeta;
+        int64_t out_stride;          // outputs are [T][out_stride]
         double *xx, *xy, *rss, *f, *p, *var_perc;
     };
     double q, xy;
     const int8_t* xrow;
+    int64_t orow;
 
     __device__ __forceinline__ void begin_group(const Params& p, int g, int row) {
         q = 0.0;
         xy = 0.0;
-        const int64_t r = (int64_t)g * TC_BM + row;
-        xrow = (r < p.row_count) ? p.snps + (p.row_begin + r) * p.pitch : nullptr;
+        orow = (int64_t)g * TC_BM + row;
+        xrow = (orow < p.row_count) ? p.snps + (p.row_begin + orow) * p.pitch : nullptr;
+    }
+    __device__ __forceinline__ void end_group(const Params&, int, int) {}
+    __device__ __forceinline__ int tile_begin(const Params&, const TcTile& t, int) {
+        if (t.aux1 & QS_FLAG_FIRST) {
+            q = 0.0;
+            xy = 0.0;
+        }
+        return TC_BN / 32;           // uniform across the warp: tcgen05.ld is warp-collective
     }
     __device__ __forceinline__ void chunk(const Params& p, const TcTile& t, int row, int c, const uint32_t (&v)[32]) {
         if (xrow == nullptr) return;
@@ -50,8 +75,8 @@ struct QuadEpi {
             s += (int)v[j] * xv;
         }
         q = fma(p.w[t.aux0], (double)s, q);
-        if (t.aux1 & 1) {
-            const double* vv = p.v + col0;
+        if (t.aux1 & QS_FLAG_XY) {
+            const double* vv = p.v + (int64_t)(t.aux1 >> QS_PHEN_SHIFT) * p.v_stride + col0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int xv = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xffu);
@@ -59,16 +84,18 @@ struct QuadEpi {
             }
         }
     }
-    __device__ __forceinline__ void end_group(const Params& p, int g, int row) {
-        if (xrow == nullptr) return;
-        const int64_t o = (int64_t)g * TC_BM + row;
-        const double sxx = q, sxy = xy;
+    __device__ __forceinline__ void tile_end(const Params& p, const TcTile& t, int row, int lane) {
+        if (!(t.aux1 & QS_FLAG_LAST) || xrow == nullptr) return;
+        const int ph = t.aux1 >> QS_PHEN_SHIFT;
+        const int64_t o = (int64_t)ph * p.out_stride + orow;
+        const double h0 = p.h0_rss[ph];
+        const double sxx = q * p.escale[ph], sxy = xy;
         if (p.xx) p.xx[o] = sxx;
         if (p.xy) p.xy[o] = sxy;
-        double rss = p.h0_rss, f = 0.0, vp = 0.0, pv = 1.0;
+        double rss = h0, f = 0.0, vp = 0.0, pv = 1.0;
         if (sxx > 0.0) {
-            const double r2 = (sxy * sxy) / (sxx * p.h0_rss);
-            const double rs = p.h0_rss - (sxy * sxy) / sxx;
+            const double r2 = (sxy * sxy) / (sxx * h0);
+            const double rs = h0 - (sxy * sxy) / sxx;
             if (rs != 0.0) {
                 rss = rs;
                 vp = r2;
@@ -80,6 +107,67 @@ struct QuadEpi {
         if (p.f) p.f[o] = f;
         if (p.var_perc) p.var_perc[o] = vp;
         if (p.p) p.p[o] = pv;
+    }
+};
+
+// ---- permutation scan epilogue --------------------------------------------------------------------------
+// B operand rows of perm block b: row (b*8 + k)*32 + j = digit plane k of permutation 32 b + j.
+constexpr int PS_SLICES = 8;
+
+struct PermEpi {
+    struct Params {
+        int64_t row_count;
+        double w[PS_SLICES];          // 2^E 128^-(k+1)
+        const double* xx;             // [row_count] x~_c.x~_c (from the quadratic-form scan of the centred rotation)
+        const double* mu;             // [row_count] SNP means (nullptr when SNPs are not centred)
+        const double* wsum;           // [P_pad] sum_i W[p][i]
+        unsigned long long* ratio;    // [P_pad] running max, bits of non-negative doubles
+    };
+    double d[32];
+    double inv_xx, mu;
+
+    __device__ __forceinline__ void begin_group(const Params& p, int g, int row) {
+        const int64_t r = (int64_t)g * TC_BM + row;
+        inv_xx = 0.0;
+        mu = 0.0;
+        if (r < p.row_count) {
+            const double sxx = p.xx[r];
+            inv_xx = sxx > 0.0 ? 1.0 / sxx : 0.0;     // x~ = 0: lstsq returns an empty residue, the minimum is kept (:1164)
+            mu = p.mu ? p.mu[r] : 0.0;
+        }
+    }
+    __device__ __forceinline__ void end_group(const Params&, int, int) {}
+    __device__ __forceinline__ int tile_begin(const Params&, const TcTile&, int) { return PS_SLICES; }
+    __device__ __forceinline__ void chunk(const Params& p, const TcTile&, int, int c, const uint32_t (&v)[32]) {
+        const double wk = p.w[c];
+        if (c == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d[j] = wk * (double)(int)v[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d[j] = fma(wk, (double)(int)v[j], d[j]);
+        }
+    }
+    __device__ __forceinline__ void tile_end(const Params& p, const TcTile& t, int, int lane) {
+        const double* ws = p.wsum + t.col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const double dot = d[j] - mu * ws[j];                 // x_c.W_p = x.W_p - mean(x) sum(W_p)
+            d[j] = dot * dot * inv_xx;
+        }
+        // transposing max-reduction over the 32 lanes (rows): lane l ends with max over rows of permutation l
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+                const double send = up ? d[i] : d[i + o];
+                const double keep = up ? d[i + o] : d[i];
+                const double recv = __shfl_xor_sync(0xffffffffu, send, o);
+                d[i] = fmax(keep, recv);
+            }
+        }
+        atomicMax(p.ratio + t.col0 + lane, (unsigned long long)__double_as_longlong(d[0]));
     }
 };
 
@@ -108,6 +196,39 @@ __global__ void quad_slice_kernel(const double* __restrict__ A, int64_t ld, int 
         r -= d;                                                          // exact: |r| <= 0.5
         Bq[((int64_t)k * n_padN + j) * ldq + i] = (int8_t)(int)d;
     }
+}
+
+// max |W| over a row-major [rows x cols] matrix -> bits of a non-negative double
+__global__ void mat_amax_kernel(const double* __restrict__ W, int64_t ld, int rows, int cols, unsigned long long* __restrict__ amax_bits) {
+    const int r = blockIdx.y;
+    double m = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += gridDim.x * blockDim.x) m = fmax(m, fabs(W[(int64_t)r * ld + i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(amax_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// digits of W[p][i] 2^-E into the permutation operand: Wq[((p/32)*8 + k)*32 + p%32][i], k < 8
+__global__ void perm_slice_kernel(const double* __restrict__ W, int64_t ld, int P, int n, double scale, int8_t* __restrict__ Wq,
+                                  int64_t ldq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
+    if (i >= n || p >= P) return;
+    double r = W[(int64_t)p * ld + i] * scale;                           // |r| < 0.5
+    const int64_t base = ((int64_t)(p >> 5) * PS_SLICES * 32 + (p & 31)) * ldq + i;
+#pragma unroll
+    for (int k = 0; k < PS_SLICES; ++k) {
+        r *= 128.0;
+        const double d = rint(r);
+        r -= d;
+        Wq[base + (int64_t)k * 32 * ldq] = (int8_t)(int)d;
+    }
+}
+
+// R[r][:] -= r1[r] / n   (right-multiplication by the centring matrix C = I - 11'/n: R C = R - (R 1) 1'/n)
+__global__ void centre_cols_kernel(double* __restrict__ R, int64_t ld, int rows, int cols, const double* __restrict__ r1, double inv_n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j < cols && i < rows) R[(int64_t)i * ld + j] -= r1[i] * inv_n;
 }
 
 }  // namespace mmg

@@ -51,7 +51,7 @@ template <class Epi, int CS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcTile* __restrict__ tiles, int num_groups, int tiles_per_group, int table_stride,
-                  int group_m_step, int rank_m_step, const typename Epi::Params ep) {
+                  int group_m_step, int rank_m_step, uint64_t policy_a, uint64_t policy_b, const typename Epi::Params ep) {
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle wants 1024-byte aligned stage bases (the dynamic smem base is the same in every CTA of a
     // cluster, so CTA-relative offsets agree across the cluster)
@@ -108,12 +108,12 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
                         uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, t.m0);
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, t.m0, policy_a);
                         if (CS == 1) {
-                            tma_load_2d(sa + TC_A_BYTES, &tmB, &full_bar[stage], kb * TC_BK, t.n0);
+                            tma_load_2d(sa + TC_A_BYTES, &tmB, &full_bar[stage], kb * TC_BK, t.n0, policy_b);
                         } else {
                             tma_load_2d_mcast(sa + TC_A_BYTES + crank * kBRows * TC_BK, &tmB, &full_bar[stage], kb * TC_BK,
-                                              t.n0 + crank * kBRows, kMask);
+                                              t.n0 + crank * kBRows, kMask, policy_b);
                         }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -175,13 +175,15 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * TC_BN + (static_cast<uint32_t>(quad * 32) << 16);
                 if (live) {
+                    const int nchunks = epi.tile_begin(ep, t, row);     // 32-column chunks of this tile that carry data
 #pragma unroll 1
-                    for (int c = 0; c < TC_BN / 32; ++c) {
+                    for (int c = 0; c < nchunks; ++c) {
                         uint32_t v[32];
                         tmem_ld_32x32(taddr + c * 32, v);
                         tmem_ld_wait();
                         epi.chunk(ep, t, row, c, v);
                     }
+                    epi.tile_end(ep, t, row, lane);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -209,6 +211,8 @@ struct GramEpi {
     };
     __device__ __forceinline__ void begin_group(const Params&, int, int) {}
     __device__ __forceinline__ void end_group(const Params&, int, int) {}
+    __device__ __forceinline__ int tile_begin(const Params&, const TcTile&, int) { return TC_BN / 32; }
+    __device__ __forceinline__ void tile_end(const Params&, const TcTile&, int, int) {}
     __device__ __forceinline__ void chunk(const Params& p, const TcTile& t, int row, int c, const uint32_t (&v)[32]) {
         int4* dst = reinterpret_cast<int4*>(p.G + (int64_t)(t.m0 + row) * p.ld + t.n0 + c * 32);
         if (p.accumulate) {

@@ -47,10 +47,13 @@ def calc_ibs_kinship(snps, snps_data_format='binary', snp_dtype='int8', dtype='s
 
     data_format: 'binary' (0/1 genotypes) and 'diploid_int' (0/1/2) are supported.
     Returns an np.matrix for 'binary' and an ndarray for 'diploid_int', float64, as the reference does.
+    The array lives in page-locked host memory and is READ-ONLY (copy it to modify it): the library keeps the
+    device copy it was downloaded from, so handing it to LinearMixedModel.add_random_effect / emmax costs no upload.
     """
+    ctx = ctx or _lib.get_context()
     K = calc_ibs_kinship_device(snps, snps_data_format, scaled, impl, ctx)
-    k_mat = K.download()
-    K.free()
+    k_mat = K.download(pinned=True)         # page-locked: D2H at the PCIe rate
+    ctx.remember_resident(k_mat, K)         # emmax(snps, y, K) right after this call finds K still in HBM
     if snps_data_format == 'binary':
         import warnings
         with warnings.catch_warnings():

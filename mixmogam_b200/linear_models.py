@@ -14,6 +14,7 @@ Drop-in for the EMMAX path of mixmogam's `linear_models` module (reference linea
         ._emmax_permutations_(snps, K, H_sqrt_inv, num_perm=100)             :1125
     emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_num=0)          :1790
     emma(snps, phenotypes, K, cofactors=None)                                :1725
+    emmax_multi(snps, phenotypes[T], K, cofactors=None)                      T x emmax() on one eigenbasis, one scan launch
     get_emma_reml_estimates(y, K, ...)                                       :1690 (single-K form)
 
 Same names, arguments, defaults, returned dict keys and error behaviour.  The n x n objects (K, the
@@ -38,7 +39,7 @@ from . import _lib
 from . import kinship
 from ._lib import DeviceMatrix, LazyHostArray
 
-__all__ = ['LinearModel', 'LinearMixedModel', 'emmax', 'emma', 'get_emma_reml_estimates']
+__all__ = ['LinearModel', 'LinearMixedModel', 'emmax', 'emmax_multi', 'emma', 'get_emma_reml_estimates']
 
 _VERBOSE = False
 
@@ -552,7 +553,7 @@ class LinearMixedModel(LinearModel):
         Wt = ctx.gemm(Ysd, H, ta=True)
         Ysd.free()
         ratio = np.zeros(num_perm)
-        ctx.emmax_perm_scan(H, Wt, ratio, centre=True, impl=_lib.IMPL_DMMA)
+        ctx.emmax_perm_scan(H, Wt, ratio, centre=True, impl=getattr(self, 'perm_impl', 'auto'))
         Wt.free()
         ynorm = np.sum(Ys * Ys, axis=0)
         min_rss_list = np.minimum(np.repeat(h0_rss_f, num_perm), ynorm - ratio)      # :1156,:1164
@@ -617,3 +618,76 @@ def emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_nu
     else:
         _say('Took %f seconds.' % (secs))
     return res
+
+
+def emmax_multi(snps, phenotypes, K, cofactors=None, ngrids=50, llim=-10, ulim=10, esp=1e-6, batch=None, ctx=None):
+    """
+    EMMAX for T phenotypes measured on the same individuals (BASELINE.json configs[2]: "all phenotypes scanned
+    against one kinship eigenbasis").  Equivalent to [emmax(snps, y, K, cofactors) for y in phenotypes]
+    (linear_models.py:1790-1816, emma_num=0) with the work shared:
+      * K is scaled and eigendecomposed once (eig_L and eig_R do not depend on the phenotype);
+      * the REML grid + secant refinement of all T phenotypes is one launch pair (mmg_reml_f64, T rows);
+      * the T scans -- each phenotype has its own delta, hence its own rotation -- are ONE int8 tensor-core launch
+        in which every 128-SNP genotype block is reused by the digit planes of all T rotations.
+    `phenotypes` is a sequence of T length-n vectors.  Returns a list of T result dicts with emmax()'s keys.
+    `batch` bounds the number of phenotypes per launch (default: sized from free HBM).
+    """
+    Y = np.asarray(phenotypes, dtype=np.float64)
+    if Y.ndim != 2:
+        raise ValueError('phenotypes must be a sequence of T equally long vectors')
+    T, n = Y.shape
+    base = LinearMixedModel(Y[0], ctx=ctx)
+    ctx = base.ctx
+    base.add_random_effect(K)
+    if cofactors:
+        for cofactor in cofactors:
+            base.add_factor(cofactor)
+    X = base.X
+    q0 = X.shape[1]
+    p = n - q0
+    n_p = n - (q0 + 1)
+    eig_L = base._get_eigen_L_()
+    eig_R = base._get_eigen_R_(X=X)
+    eig_vals = np.array(eig_R['values'], dtype=np.float64)
+    eigL_vals = np.asarray(eig_L['values'], dtype=np.float64)
+    etas = base._etas(eig_R, Y.T)                                             # p x T   (:794 for every phenotype)
+    sq_etas = etas * etas
+    m_g = ngrids + 1
+    deltas = np.exp((np.arange(m_g, dtype=np.float64) / ngrids) * (ulim - llim) + llim)
+    r = ctx.reml(eig_vals, sq_etas.T, deltas, esp)                            # :802-891, T phenotypes at once
+    num_snps, n_lines = ctx.ensure_snps(snps)
+    if n_lines != n:
+        raise ValueError('SNP length %d does not match the phenotypes (%d)' % (n_lines, n))
+    UL = ctx.to_device(eig_L['vectors'])
+    if batch is None:
+        free = ctx.device_info()['free_bytes']
+        n_pad = (n + 255) // 256 * 256
+        per = n * n * 8 + 7 * n_pad * n_pad + 5 * 8 * num_snps
+        batch = max(1, min(T, int(0.5 * free / per)))
+    results = []
+    for t0 in range(0, T, batch):
+        ts = range(t0, min(T, t0 + batch))
+        Rs, V, h0, meta = [], [], [], []
+        for t in ts:
+            delta = float(r['delta'][t])
+            H = UL.copy()
+            ctx.scale_rows(H, 1.0 / np.sqrt(eigL_vals + delta))               # :898
+            mt = LinearMixedModel(Y[t], ctx=ctx)
+            mt.X = X
+            nf = mt._null_fit(H, project=True)                                # :1290-1303
+            H.free()
+            Rs.append(nf['R'])
+            V.append(nf['Yres'].reshape(-1))
+            h0.append(float(np.asarray(nf['h0_rss']).reshape(-1)[0]))
+            vg = float(np.sum(sq_etas[:, t]) * np.sum(1.0 / (eig_vals + delta)) / p)      # :894-896
+            meta.append({'h0_rss': nf['h0_rss'], 'h0_betas': list(map(float, np.asarray(nf['h0_betas']).reshape(-1))),
+                         'pseudo_heritability': 1.0 / (1 + delta), 'vg': vg, 've': vg * delta, 'max_ll': float(r['ll'][t]),
+                         'delta': delta})
+        out = ctx.emmax_scan_multi(Rs, np.asarray(V), h0, n_p)
+        for Rm in Rs:
+            Rm.free()
+        for i, md in enumerate(meta):
+            d = {'ps': out['ps'][i], 'f_stats': out['f_stats'][i], 'rss': out['rss'][i], 'var_perc': out['var_perc'][i]}
+            d.update(md)
+            results.append(d)
+    return results

@@ -94,15 +94,17 @@ def test_calc_ibs_kinship_matches_oracle_midsize(ctx):
     assert np.array_equal(K, K.T) and np.all(np.diag(K) == 1.0)
 
 
-def test_scale_k_and_ibd(ctx):
+@pytest.mark.parametrize('ibd_impl,rtol,atol', [('tcgen05', 1e-8, 1e-10), ('dsyrk', 1e-11, 1e-13)])
+def test_scale_k_and_ibd(ctx, monkeypatch, ibd_impl, rtol, atol):
     from mixmogam_b200 import kinship
+    monkeypatch.setenv('MMG_IBD_IMPL', ibd_impl)
     g = golden('ibd_n37.npz')
     ctx.invalidate_snps()
     K = kinship.calc_ibd_kinship(list(g['snps']))
-    np.testing.assert_allclose(K, g['K_double'], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(K, g['K_double'], rtol=rtol, atol=atol)
     Ku = kinship.calc_ibd_kinship(g['snps'], scaled=False)
-    np.testing.assert_allclose(Ku, g['K_double_unscaled'], rtol=1e-11, atol=1e-13)
-    np.testing.assert_allclose(kinship.scale_k(Ku), g['K_double'], rtol=1e-12)
+    np.testing.assert_allclose(Ku, g['K_double_unscaled'], rtol=rtol, atol=atol)
+    np.testing.assert_allclose(kinship.scale_k(Ku), g['K_double'], rtol=rtol, atol=atol)
     # the float32-accumulating reference differs at the 1e-6 level only
     np.testing.assert_allclose(K, g['K_single'], rtol=2e-4, atol=2e-6)
     mono = g['snps'].copy()
@@ -110,3 +112,69 @@ def test_scale_k_and_ibd(ctx):
     ctx.invalidate_snps()
     with pytest.raises(AssertionError):
         kinship.calc_ibd_kinship(mono)
+
+
+@pytest.mark.parametrize('n,m', [(700, 9000), (300, 70000)])
+def test_ibd_tensor_core_matches_fp64(ctx, monkeypatch, n, m):
+    """int8 digit-plane IBD Gram (ibd_tc.cuh) against the FP64 library path and the float64 oracle: several row tiles,
+    a ragged last K block, two packed chunks (m > 65536), rare alleles (wide range of 1/var weights), a MAF mask."""
+    from mixmogam_b200 import kinship
+    from oracle import reference_py3 as o
+    rng = np.random.default_rng(n)
+    f = np.concatenate([rng.uniform(0.004, 0.05, m // 4), rng.uniform(0.05, 0.5, m - m // 4)])[:, None]
+    snps = ((rng.random((m, n)) < f).astype(np.int8) + (rng.random((m, n)) < f).astype(np.int8))
+    snps = snps[snps.min(1) != snps.max(1)]
+    ctx.invalidate_snps()
+    monkeypatch.setenv('MMG_IBD_IMPL', 'tcgen05')
+    Kt = kinship.calc_ibd_kinship(snps, scaled=False)
+    assert ctx.last_kernel_ms('ibd') > 0                            # the tensor-core kernel ran
+    monkeypatch.setenv('MMG_IBD_IMPL', 'dsyrk')
+    Kd = kinship.calc_ibd_kinship(snps, scaled=False)
+    scale = np.abs(Kd).max()
+    assert np.max(np.abs(Kt - Kd)) <= 1e-9 * scale
+    assert np.array_equal(Kt, Kt.T)
+    if n * len(snps) <= 8e6:
+        Ko = o.calc_ibd_kinship(list(snps), dtype='double', scaled=False)
+        assert np.max(np.abs(Kt - Ko)) <= 1e-9 * scale
+    # masked accumulation (hdf5_data.py:91-96)
+    monkeypatch.setenv('MMG_IBD_IMPL', 'tcgen05')
+    mask = (np.arange(len(snps)) % 3 != 0)
+    Ka = ctx.matrix(n, n)
+    used = ctx.kinship_ibd_accumulate(Ka, 0, len(snps), mask)
+    assert used == int(mask.sum())
+    monkeypatch.setenv('MMG_IBD_IMPL', 'dsyrk')
+    Kb = ctx.matrix(n, n)
+    ctx.kinship_ibd_accumulate(Kb, 0, len(snps), mask)
+    a, b = Ka.download(), Kb.download()
+    assert np.max(np.abs(a - b)) <= 1e-9 * np.abs(b).max()
+    # genotypes outside {0,1,2} take the FP64 path transparently
+    monkeypatch.setenv('MMG_IBD_IMPL', 'tcgen05')
+    odd = snps[:500].copy()
+    odd[odd == 2] = 3
+    ctx.invalidate_snps()
+    Ko3 = kinship.calc_ibd_kinship(odd, scaled=False)
+    z = odd.astype(np.float64)
+    z = (z - z.mean(1, keepdims=True)) / z.std(1, keepdims=True)
+    np.testing.assert_allclose(Ko3, z.T @ z / len(odd), rtol=1e-10, atol=1e-12)
+
+
+def test_returned_kinship_stays_resident(ctx):
+    """calc_ibs_kinship hands back a read-only page-locked array and keeps the device copy: emmax(snps, y, K) must
+    give the same result whether it finds that copy or uploads a fresh (writable) one."""
+    from mixmogam_b200 import kinship, linear_models as lm
+    from oracle import reference_py3 as o
+    snps = o.synth_genotypes(3000, 300, 'diploid_int', seed=12)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int')
+    assert not K.flags.writeable and ctx.lookup_resident(K) is not None
+    with pytest.raises(ValueError):
+        K[0, 0] = 2.0
+    y = o.synth_phenotype(snps, np.asarray(K), seed=4)
+    r1 = lm.emmax(snps, y, K)
+    K2 = np.array(K)                                     # a writable copy takes the upload path
+    assert ctx.lookup_resident(K2) is None
+    r2 = lm.emmax(snps, y, K2)
+    assert np.array_equal(r1['ps'], r2['ps'])
+    Kb = kinship.calc_ibs_kinship((snps > 0).astype(np.int8), 'binary')
+    assert isinstance(Kb, np.matrix) and ctx.lookup_resident(Kb) is not None
+    del K, Kb

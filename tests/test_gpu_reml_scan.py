@@ -132,13 +132,15 @@ def test_snp_priors_and_transformed_snps(ctx):
     assert t.shape == (300, 400)
 
 
-def test_permutations_golden(ctx):
+@pytest.mark.parametrize('perm_impl', ['tcgen05', 'dmma'])
+def test_permutations_golden(ctx, perm_impl):
     """_emmax_permutations_ shuffles the ROTATED residual phenotype (linear_models.py:1151-1154), so its output
     depends on the sign convention of the eigenvectors inside H_sqrt_inv.  Feed the oracle's H_sqrt_inv (the
     method takes it as an argument) and the same np.random seed: then every number is comparable."""
     from mixmogam_b200 import linear_models as lm
     g = golden('perm_n120.npz')
     lmm = lm.LinearMixedModel(g['y'])
+    lmm.perm_impl = perm_impl
     lmm.add_random_effect(g['K'])
     np.random.seed(int(g['seed']))
     ctx.invalidate_snps()
@@ -173,3 +175,63 @@ def test_scan_implementations_agree_and_match_oracle_sample(ctx, n, m):
     ro = o.emmax(list(snps[sub]), y, K, dtype='double')
     assert neglog10_rel_err(ra['ps'][sub], ro['ps']) < 1e-6
     assert abs(ra['pseudo_heritability'] - ro['pseudo_heritability']) < 1e-8
+
+
+@pytest.mark.parametrize('n,m,P', [(500, 3000, 70), (1300, 2000, 33)])
+def test_permutation_scan_tcgen05_matches_dmma(ctx, n, m, P):
+    """The int8 tensor-core permutation scan (centred quadratic form + digit-plane GEMM) against the FP64 tensor-core
+    one on sizes that span several K blocks, N tiles and a ragged permutation block."""
+    from mixmogam_b200 import _lib
+    from mixmogam_b200._lib import DeviceMatrix
+    from oracle import reference_py3 as o
+    rng = np.random.default_rng(n + P)
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=n)
+    ctx.invalidate_snps()
+    ctx.ensure_snps(snps)
+    H = rng.standard_normal((n, n)) / np.sqrt(n) + np.eye(n)
+    Ys = rng.standard_normal((n, P))
+    Hd = DeviceMatrix.from_host(ctx, H)
+    Wt = DeviceMatrix.from_host(ctx, Ys.T @ H)
+    ra = ctx.emmax_perm_scan(Hd, Wt, np.zeros(P), centre=True, impl=_lib.IMPL_DMMA)
+    rb = ctx.emmax_perm_scan(Hd, Wt, np.zeros(P), centre=True, impl=_lib.IMPL_TCGEN05)
+    np.testing.assert_allclose(rb, ra, rtol=1e-8)
+    xc = snps.astype(np.float64) - snps.mean(1, keepdims=True)
+    xt = xc @ H.T
+    ref = np.max((xt @ Ys) ** 2 / np.sum(xt * xt, axis=1)[:, None], axis=0)
+    np.testing.assert_allclose(rb, ref, rtol=1e-8)
+    rc = ctx.emmax_perm_scan(Hd, Wt, np.zeros(P), centre=False, impl=_lib.IMPL_TCGEN05)
+    xt = snps.astype(np.float64) @ H.T
+    np.testing.assert_allclose(rc, np.max((xt @ Ys) ** 2 / np.sum(xt * xt, axis=1)[:, None], axis=0), rtol=1e-8)
+
+
+def test_emmax_multi_matches_single_and_oracle(ctx):
+    """Phenotype-batched scan (configs[2]): T phenotypes, one eigenbasis, one launch == T independent emmax() calls."""
+    from mixmogam_b200 import linear_models as lm
+    from oracle import reference_py3 as o
+    g = golden('emmax_diploid_n400.npz')
+    snps, K = g['snps'], g['K']
+    rng = np.random.default_rng(5)
+    Y = [g['y']] + [o.synth_phenotype(snps, K, seed=100 + t, h2_poly=h) for t, h in enumerate((0.0, 0.3, 0.8, 0.5))]
+    Y.append(rng.standard_normal(400))
+    ctx.invalidate_snps()
+    res = lm.emmax_multi(snps, Y, K)
+    assert len(res) == len(Y)
+    for t, y in enumerate(Y):
+        single = lm.emmax(snps, y, K, scan_impl='tcgen05')
+        # same kernels; the only difference is cuBLAS gemm vs gemv rounding in etas = U_R Y (delta moves by ~1e-13)
+        np.testing.assert_allclose(res[t]['ps'], single['ps'], rtol=1e-9, atol=0)
+        np.testing.assert_allclose(res[t]['rss'], single['rss'], rtol=1e-10)
+        for k in ('pseudo_heritability', 'vg', 've', 'max_ll'):
+            np.testing.assert_allclose(res[t][k], single[k], rtol=1e-9)
+        np.testing.assert_allclose(res[t]['h0_betas'], single['h0_betas'], rtol=1e-8, atol=1e-12)
+        if t in (0, 2, 5):
+            ro = o.emmax(list(snps), y, K, dtype='double')
+            assert neglog10_rel_err(res[t]['ps'], ro['ps']) < 1e-6
+            assert abs(res[t]['pseudo_heritability'] - ro['pseudo_heritability']) < 1e-8
+    # with a cofactor and a batch size that does not divide T
+    cof = g['cofactor']
+    res2 = lm.emmax_multi(snps, Y[:3], K, cofactors=[cof], batch=2)
+    ok = np.arange(len(snps)) != 17
+    for t in range(3):
+        single = lm.emmax(snps, Y[t], K, cofactors=[cof], scan_impl='tcgen05')
+        np.testing.assert_allclose(res2[t]['ps'][ok], single['ps'][ok], rtol=1e-9)
