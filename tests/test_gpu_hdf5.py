@@ -26,7 +26,9 @@ def test_ibd_hdf5_variant(ctx):
     f = _h5_like([snps[:1700], snps[1700:]], np.zeros(198))
     K, n_snps = hdf5_data._ibd_kinship_device(ctx, f['genot_data'], 198, min_maf=0.1)
     assert n_snps == int(g['n_snps'])
-    np.testing.assert_allclose(K.download(), g['K'], rtol=1e-10, atol=1e-12)
+    # int8 digit-plane IBD Gram (default): 8 exact base-128 digits of z -> |dK| <= 1e-10 absolute on K ~ 1
+    # (SURVEY 8c asks 1e-6 relative; the reference itself accumulates in float32)
+    np.testing.assert_allclose(K.download(), g['K'], rtol=1e-8, atol=1e-10)
     hdf5_data.calculate_ibd_kinship(f)
     assert f['kinship'].shape == (198, 198)
 
