@@ -371,7 +371,7 @@ def main():
             exec_ops = 2.0 * m_loc * 256 * 128 * kblocks * S           # int8 MAC*2 actually issued (lower-triangular K ranges)
             bf16 = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops') or 1590.0
             int8_peak = 2.0 * bf16                                       # int8 tcgen05 rate = 2 x bf16 (same pipe, K=32 vs 16)
-            roof = {'bound': 'tensor', 'kernel': 'tc_gemm_i8_kernel<QuadEpi>', 'achieved': exec_ops / scan_s / 1e12,
+            roof = {'bound': 'tensor', 'kernel': 'tc_gemm_i8_kernel<QuadEpi>' if os.environ.get('MMG_SCAN_SCHED') == 'table' else 'scan_quad_kernel', 'achieved': exec_ops / scan_s / 1e12,
                     'peak': int8_peak, 'unit': 'TFLOP/s', 'frac': exec_ops / scan_s / 1e12 / int8_peak, 'traffic': None,
                     'pipe': 'int8 tcgen05 (TOP/s); peak = 2 x measured sustained bf16 %s' % ('of measured' if peaks else 'of fallback'),
                     'algorithmic_fp64_tflops': alg_flops / scan_s / 1e12, 'fp64_tensor_peak_measured': fp64_peak,

@@ -14,6 +14,7 @@
 #include "reml.cuh"
 #include "scan_dmma.cuh"
 #include "scan_tc.cuh"
+#include "scan_quad.cuh"
 #include "tc_gemm.cuh"
 
 namespace mmg {
@@ -153,6 +154,60 @@ static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMa
     if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of %s (cluster %d, grid %d) failed: %s", name, CS, clusters * CS,
                                       cudaGetErrorString(e));
     return MMG_OK;
+}
+
+// Launch the genotype-stationary scan kernel (scan_quad.cuh): cluster CS, panel of PKB K-blocks, STAGES digit stages.
+template <int CS, int PKB, int STAGES, bool PAIR>
+static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, QuadShape sh, const QuadEpi::Params& ep) {
+    auto kern = scan_quad_kernel<CS, PKB, STAGES, PAIR>;
+    constexpr int smem = QuadSmem<PKB, STAGES, PAIR>::kBytes;
+    {   // per device, cheap: set on every launch
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "scan_quad_kernel: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(QP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = ctx->sm_count / CS;
+    if (CS > 1) {
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count / CS * CS));
+        int q = 0;
+        if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0) max_clusters = std::min(max_clusters, q);
+        else cudaGetLastError();
+    }
+    const int cgroups = (sh.num_groups + CS - 1) / CS;
+    const int clusters = std::max(1, std::min(cgroups, max_clusters));
+    cfg.gridDim = dim3((unsigned)(clusters * CS));
+    const uint64_t pa = env_policy("MMG_TC_HINT_A", L2_EVICT_FIRST), pb = env_policy("MMG_TC_HINT_B", L2_EVICT_LAST);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, sh, pa, pb, ep);
+    ctx->launches += 1;
+    if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of scan_quad_kernel<%d,%d,%d,%d> (grid %d) failed: %s", CS, PKB, STAGES,
+                                      (int)PAIR, clusters * CS, cudaGetErrorString(e));
+    return MMG_OK;
+}
+
+template <int CS>
+static int launch_scan_quad_cs(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
+                               const QuadEpi::Params& ep) {
+    if (panel == 8) return launch_scan_quad<CS, 8, 3, false>(ctx, tmA, tmB, sh, ep);
+    if (panel == 4) return launch_scan_quad<CS, 4, 5, false>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<CS, 6, 4, false>(ctx, tmA, tmB, sh, ep);
+}
+
+// CTA-pair form (tcgen05.mma.cta_group::2): half digit tiles of 16 KB per stage
+static int launch_scan_quad_pair(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
+                                 const QuadEpi::Params& ep) {
+    if (panel == 8) return launch_scan_quad<2, 8, 6, true>(ctx, tmA, tmB, sh, ep);
+    if (panel == 4) return launch_scan_quad<2, 4, 10, true>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<2, 6, 8, true>(ctx, tmA, tmB, sh, ep);
 }
 
 // MMG_GRAM_IMPL / MMG_SCAN_IMPL = tcgen05 | simt | dmma select what MMG_IMPL_AUTO means (both are CUDA paths)
@@ -1069,40 +1124,86 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     ep.out_stride = snp_count;
     ep.xx = d_xx; ep.xy = d_xy; ep.rss = d_rss; ep.f = d_f; ep.p = d_p; ep.var_perc = d_vp;
 
-    // one shared tile table: for every phenotype, for every 256-column tile jb, one tile per slice; K only up to the diagonal
     const int tiles_n = (int)(n_padN / TC_BN), kb_total = (int)(ldq / TC_BK);
-    std::vector<TcTile> tiles;
-    tiles.reserve((size_t)T * tiles_n * S);
-    for (int t = 0; t < T; ++t)
-        for (int jb = 0; jb < tiles_n; ++jb)
-            for (int k = 0; k < S; ++k) {
-                TcTile tl{};
-                tl.m0 = 0;
-                tl.n0 = (int)(((int64_t)t * S + k) * n_padN + (int64_t)jb * TC_BN);
-                tl.kb0 = 0;
-                tl.kb1 = std::min(kb_total, (jb + 1) * (TC_BN / TC_BK));
-                tl.aux0 = k;
-                tl.aux1 = (t << QS_PHEN_SHIFT) | (k == 0 ? QS_FLAG_XY : 0) | ((jb == 0 && k == 0) ? QS_FLAG_FIRST : 0) |
-                          ((jb == tiles_n - 1 && k == S - 1) ? QS_FLAG_LAST : 0);
-                tl.col0 = jb * TC_BN;
-                tiles.push_back(tl);
-            }
     MMG_CHECK(ctx, (int64_t)T * S * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
-    MMG_TRY(ensure_tiles(ctx, tiles));
     int cs = env_int("MMG_SCAN_CLUSTER", 2);
     if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+    // MMG_SCAN_SCHED = panel (genotype-stationary schedule, scan_quad.cuh) | pair (same, MMA as a CTA pair) |
+    //                  table (tile-table kernel, tc_gemm.cuh)
+    const char* sched = getenv("MMG_SCAN_SCHED");
+    if (!sched) sched = "panel";
+    const bool pair = strcmp(sched, "pair") == 0;
+    if (pair) cs = 2;
     CUtensorMap tmA, tmB;
     MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
     MMG_TRY(make_tmap_u8(ctx, &tmB, Bq.p, ldq, (int64_t)T * S * n_padN, ldq, TC_BN / cs));
     const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
-    cudaEventRecord(ctx->kev0, ctx->stream);
-    const TcTile* td = (const TcTile*)ctx->tiles_d;
-    if (cs == 4)
-        MMG_TRY((launch_tc_gemm<QuadEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,4>", L2_EVICT_FIRST, L2_EVICT_LAST)));
-    else if (cs == 2)
-        MMG_TRY((launch_tc_gemm<QuadEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,2>", L2_EVICT_FIRST, L2_EVICT_LAST)));
-    else
-        MMG_TRY((launch_tc_gemm<QuadEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,1>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+    if (strcmp(sched, "table") != 0) {
+        QuadShape sh{};
+        sh.num_groups = groups;
+        sh.T = T;
+        sh.S = S;
+        sh.tiles_n = tiles_n;
+        sh.kb_total = kb_total;
+        sh.n_padN = (int)n_padN;
+        sh.prefetch = std::max(0, env_int("MMG_SCAN_PREFETCH", 8));
+        // MMG_SCAN_DBG_CLOCKS=<file>: per-CTA cycle counters of the three warp roles (time spent in each barrier wait)
+        const char* dbg_path = getenv("MMG_SCAN_DBG_CLOCKS");
+        DevBuf dbg;
+        const int dbg_ctas = ctx->sm_count;
+        if (dbg_path) {
+            MMG_CUDA(ctx, dbg.alloc(ctx->stream, (size_t)dbg_ctas * 16 * sizeof(long long)));
+            MMG_CUDA(ctx, cudaMemsetAsync(dbg.p, 0, (size_t)dbg_ctas * 16 * sizeof(long long), ctx->stream));
+            sh.dbg = dbg.as<long long>();
+        }
+        const int panel = env_int("MMG_SCAN_PANEL", 8);
+        cudaEventRecord(ctx->kev0, ctx->stream);
+        if (pair) MMG_TRY(launch_scan_quad_pair(ctx, panel, tmA, tmB, sh, ep));
+        else if (cs == 4) MMG_TRY(launch_scan_quad_cs<4>(ctx, panel, tmA, tmB, sh, ep));
+        else if (cs == 2) MMG_TRY(launch_scan_quad_cs<2>(ctx, panel, tmA, tmB, sh, ep));
+        else MMG_TRY(launch_scan_quad_cs<1>(ctx, panel, tmA, tmB, sh, ep));
+        if (dbg_path) {
+            std::vector<long long> h((size_t)dbg_ctas * 16);
+            MMG_CUDA(ctx, cudaMemcpyAsync(h.data(), dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (FILE* f = fopen(dbg_path, "w")) {
+                fprintf(f, "# cta prod_total prod_wait_empty prod_wait_aempty - mma_total mma_wait_full mma_wait_tempty mma_wait_afull epi_total epi_wait_tfull\n");
+                for (int c = 0; c < dbg_ctas; ++c) {
+                    fprintf(f, "%d", c);
+                    for (int k = 0; k < 11; ++k) fprintf(f, " %lld", h[(size_t)c * 16 + k]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
+    } else {
+        // one shared tile table: for every phenotype, for every 256-column tile jb, one tile per slice; K only up to the diagonal
+        std::vector<TcTile> tiles;
+        tiles.reserve((size_t)T * tiles_n * S);
+        for (int t = 0; t < T; ++t)
+            for (int jb = 0; jb < tiles_n; ++jb)
+                for (int k = 0; k < S; ++k) {
+                    TcTile tl{};
+                    tl.m0 = 0;
+                    tl.n0 = (int)(((int64_t)t * S + k) * n_padN + (int64_t)jb * TC_BN);
+                    tl.kb0 = 0;
+                    tl.kb1 = std::min(kb_total, (jb + 1) * (TC_BN / TC_BK));
+                    tl.aux0 = k;
+                    tl.aux1 = (t << QS_PHEN_SHIFT) | (k == 0 ? QS_FLAG_XY : 0) | ((jb == 0 && k == 0) ? QS_FLAG_FIRST : 0) |
+                              ((jb == tiles_n - 1 && k == S - 1) ? QS_FLAG_LAST : 0);
+                    tl.col0 = jb * TC_BN;
+                    tiles.push_back(tl);
+                }
+        MMG_TRY(ensure_tiles(ctx, tiles));
+        cudaEventRecord(ctx->kev0, ctx->stream);
+        const TcTile* td = (const TcTile*)ctx->tiles_d;
+        if (cs == 4)
+            MMG_TRY((launch_tc_gemm<QuadEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,4>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+        else if (cs == 2)
+            MMG_TRY((launch_tc_gemm<QuadEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,2>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+        else
+            MMG_TRY((launch_tc_gemm<QuadEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,1>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+    }
     cudaEventRecord(ctx->kev1, ctx->stream);
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // Bq / A / vec are freed on return
     return MMG_OK;
@@ -1482,6 +1583,78 @@ __global__ void bench_copy_kernel(const uint4* __restrict__ src, uint4* __restri
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+}  // extern "C"
+
+// tcgen05 int8 MMA issue rate with shared-memory-resident operands (no loads): one thread per CTA issues `iters` K blocks
+// (4 x UMMA K=32, M=128 per CTA, N=256) into two alternating accumulators.  ldtm != 0: the four epilogue warps read
+// the accumulators back with tcgen05.ld at the rate of one full 128x256 tile per `ldtm` K blocks, free running
+// (measures whether TMEM reads take cycles from the tensor pipe).  PAIR: cta_group::2 (M = 256 over two CTAs).
+template <bool PAIR>
+__global__ void __launch_bounds__(TC_THREADS, 1) bench_imma_kernel(int iters, int ldtm, unsigned* sink) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (TC_A_BYTES + TC_B_BYTES) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = (0x9E3779B9u * (i + 1)) & 0x03030303u;      // genotype-like bytes 0..3
+    if (threadIdx.x == 0) {
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) {
+        if (PAIR) { tmem_alloc_pair(&tmem_slot, TC_TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(&tmem_slot, TC_TMEM_COLS); tmem_relinquish(); }
+    }
+    tc_fence_before();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const bool leader = !PAIR || cluster_ctarank() == 0;
+    if (warp == 1 && lane == 0 && leader) {
+        constexpr uint32_t idesc = umma_idesc_i8(PAIR ? 2 * TC_BM : TC_BM, TC_BN);
+        const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem)), db = umma_desc_kmajor_sw128(smem_u32(smem) + TC_A_BYTES);
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t d = tmem_base + ((it >> 3) & 1) * TC_BN;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (PAIR) umma_i8_pair(d, da + 2 * kk, db + 2 * kk, idesc, ((it & 7) | kk) ? 1u : 0u);
+                else umma_i8(d, da + 2 * kk, db + 2 * kk, idesc, ((it & 7) | kk) ? 1u : 0u);
+            }
+        }
+        if (PAIR) umma_commit_pair(&done_bar, 0b11); else umma_commit(&done_bar);
+    }
+    if (warp >= 2 && ldtm > 0) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        unsigned acc = 0;
+        const int tiles = iters / ldtm;
+        for (int t = 0; t < tiles; ++t) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                uint32_t v[16];
+                tmem_ld_32x16(taddr + (t & 1) * TC_BN + c * 16, v);
+                tmem_ld_wait_dep(v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc += v[j];
+            }
+        }
+        if (acc == 0x12345678u) sink[0] = acc;
+    }
+    if (warp == 1 || warp == 0) {
+        if (lane == 0) mbar_wait(&done_bar, 0);
+        __syncwarp();
+    }
+    tc_fence_before();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        if (PAIR) tmem_dealloc_pair(tmem_base, TC_TMEM_COLS); else tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+extern "C" {
+
 int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
     MMG_CHECK(ctx, ctx && which && value, "mmg_microbench: bad argument");
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1517,6 +1690,40 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
             cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
         }
         *value = 2.0 * bytes / (ms * 1e-3) / 1e9;
+        return MMG_OK;
+    }
+    if (!strncmp(which, "imma", 4)) {
+        // "imma_tcgen05" | "imma_pair" | "imma_tcgen05_ldtm<k>" | "imma_pair_ldtm<k>": TOP/s
+        const bool pair = strstr(which, "pair") != nullptr;
+        const char* l = strstr(which, "ldtm");
+        const int ldtm = l ? std::max(1, atoi(l + 4)) : 0;
+        const int iters = 40000, smem = TC_A_BYTES + TC_B_BYTES + 1024;
+        const int grid = pair ? ctx->sm_count / 2 * 2 : ctx->sm_count;
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pair ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaFuncSetAttribute(bench_imma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(bench_imma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(ctx->kev0, ctx->stream);
+            cudaError_t e = pair ? cudaLaunchKernelEx(&cfg, bench_imma_kernel<true>, iters, ldtm, (unsigned*)ctx->scratch)
+                                 : cudaLaunchKernelEx(&cfg, bench_imma_kernel<false>, iters, ldtm, (unsigned*)ctx->scratch);
+            ctx->launches += 1;
+            if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "bench_imma_kernel launch failed: %s", cudaGetErrorString(e));
+            cudaEventRecord(ctx->kev1, ctx->stream);
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        }
+        *value = 2.0 * (double)grid * iters * TC_BM * TC_BN * TC_BK / (ms * 1e-3) / 1e12;
         return MMG_OK;
     }
     return fail(ctx, MMG_EBADARG, "unknown microbench '%s'", which);

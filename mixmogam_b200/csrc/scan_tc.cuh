@@ -86,7 +86,10 @@ struct QuadEpi {
     }
     __device__ __forceinline__ void tile_end(const Params& p, const TcTile& t, int row, int lane) {
         if (!(t.aux1 & QS_FLAG_LAST) || xrow == nullptr) return;
-        const int ph = t.aux1 >> QS_PHEN_SHIFT;
+        store(p, t.aux1 >> QS_PHEN_SHIFT, orow, q, xy);
+    }
+    // RSS / F / p of one SNP for phenotype ph from q = x'Ax 2^-E and xy = x.(R'y~)  (linear_models.py:1329,1345-1349)
+    static __device__ __forceinline__ void store(const Params& p, int ph, int64_t orow, double q, double xy) {
         const int64_t o = (int64_t)ph * p.out_stride + orow;
         const double h0 = p.h0_rss[ph];
         const double sxx = q * p.escale[ph], sxy = xy;

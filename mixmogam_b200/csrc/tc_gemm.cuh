@@ -63,7 +63,9 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tempty_bar = bars + 2 * TC_STAGES + TC_ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_ACC_STAGES);
 
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle: the role branches are then provably warp-uniform, so loop counters, addresses and
+    // descriptors live in uniform registers and UTCIMMA / UTMALDG issue without per-lane ELECT loops
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
     const int cluster_id = blockIdx.x / CS;
@@ -95,8 +97,8 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (all lanes run the loops, one elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
@@ -106,14 +108,16 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     t.m0 += g * group_m_step + crank * rank_m_step;
                     for (int kb = t.kb0; kb < t.kb1; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-                        uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, t.m0, policy_a);
-                        if (CS == 1) {
-                            tma_load_2d(sa + TC_A_BYTES, &tmB, &full_bar[stage], kb * TC_BK, t.n0, policy_b);
-                        } else {
-                            tma_load_2d_mcast(sa + TC_A_BYTES + crank * kBRows * TC_BK, &tmB, &full_bar[stage], kb * TC_BK,
-                                              t.n0 + crank * kBRows, kMask, policy_b);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+                            uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+                            tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, t.m0, policy_a);
+                            if (CS == 1) {
+                                tma_load_2d(sa + TC_A_BYTES, &tmB, &full_bar[stage], kb * TC_BK, t.n0, policy_b);
+                            } else {
+                                tma_load_2d_mcast(sa + TC_A_BYTES + crank * kBRows * TC_BK, &tmB, &full_bar[stage], kb * TC_BK,
+                                                  t.n0 + crank * kBRows, kMask, policy_b);
+                            }
                         }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -122,9 +126,10 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (all lanes run the loops, one elected lane issues) =====================
+        {
             constexpr uint32_t idesc = umma_idesc_i8(TC_BM, TC_BN);
+            const uint64_t da0 = umma_desc_kmajor_sw128(smem_u32(smem)), db0 = umma_desc_kmajor_sw128(smem_u32(smem) + TC_A_BYTES);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -138,20 +143,22 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int kb = t.kb0; kb < t.kb1; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
-                        const uint64_t da = umma_desc_kmajor_sw128(sa);
-                        const uint64_t db = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
+                        if (elect_one()) {
+                            // the descriptor's start-address field is (addr >> 4); stages are whole multiples of 1024 B
+                            const uint64_t da = da0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
+                            const uint64_t db = db0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
 #pragma unroll
-                        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                            // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
-                            umma_i8(d_tmem, da + (uint64_t)(k * (TC_UMMA_K >> 4)), db + (uint64_t)(k * (TC_UMMA_K >> 4)),
-                                    idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                                // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
+                                umma_i8(d_tmem, da + (uint64_t)(k * (TC_UMMA_K >> 4)), db + (uint64_t)(k * (TC_UMMA_K >> 4)),
+                                        idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+                            }
+                            // frees the smem slot (in every CTA of the cluster) when these MMAs retire
+                            if (CS == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], kMask);
                         }
-                        // frees the smem slot (in every CTA of the cluster) when these MMAs retire
-                        if (CS == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], kMask);
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
+                    if (elect_one()) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
                     if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
                 }
             }
