@@ -364,7 +364,7 @@ def main():
         except Exception:
             pass
         if args.scan_impl == 'tcgen05':
-            S = int(os.environ.get('MMG_TC_SLICES', 7))
+            S, rho = ctx.last_scan_info()                               # planes chosen by the certified-bound rule, its bound
             npad = (n + 255) // 256 * 256
             nt = npad // 256
             kblocks = sum(min((n + 127) // 128, 2 * (jb + 1)) for jb in range(nt))
@@ -375,7 +375,7 @@ def main():
                     'peak': int8_peak, 'unit': 'TFLOP/s', 'frac': exec_ops / scan_s / 1e12 / int8_peak, 'traffic': None,
                     'pipe': 'int8 tcgen05 (TOP/s); peak = 2 x measured sustained bf16 %s' % ('of measured' if peaks else 'of fallback'),
                     'algorithmic_fp64_tflops': alg_flops / scan_s / 1e12, 'fp64_tensor_peak_measured': fp64_peak,
-                    'slices': S, 'launch_ms': scan_s * 1e3}
+                    'slices': S, 'certified_rel_bound_xx': rho, 'launch_ms': scan_s * 1e3}
         else:
             roof = {'bound': 'tensor', 'kernel': 'scan_dmma_kernel', 'achieved': alg_flops / scan_s / 1e12, 'peak': fp64_peak,
                     'unit': 'TFLOP/s', 'frac': alg_flops / scan_s / 1e12 / fp64_peak, 'traffic': None,

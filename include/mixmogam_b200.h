@@ -64,6 +64,10 @@ int mmg_timer_reset(mmg_ctx* ctx);
  * events on the launching stream: which = "gram" | "scan" | "perm" | "ibd" */
 int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms);
 
+/* the most recent int8 tensor-core scan: number of base-128 digit planes it used (chosen per call unless MMG_TC_SLICES
+ * fixes it) and the certified bound max_s |d(x~.x~)| / x~.x~ of the truncation, measured over every SNP of that launch */
+int mmg_last_scan_info(mmg_ctx* ctx, int* slices, double* rho);
+
 /* pinned host memory for callers that want full-rate PCIe copies */
 int mmg_host_alloc(void** ptr, int64_t bytes);
 int mmg_host_free(void* ptr);
@@ -140,7 +144,9 @@ int mmg_reml_f64(mmg_ctx* ctx, const double* eig_vals, const double* sq_etas, in
  *     rss = h0_rss - xy[0]^2/xx (kept at h0_rss when xx <= 0, the `if rss:` of :1329)
  *     f = n_p * r2/(1-r2), r2 = xy[0]^2/(xx*h0_rss) ; p = F.sf(f, 1, n_p)   (:1345-1349)
  * impl: MMG_IMPL_DMMA  = FP64 tensor-core (mma.sync m8n8k4 f64) rotation fused with the reductions;
- *       MMG_IMPL_TCGEN05 = x'(R'R)x on int8 tcgen05 tensor cores with exact integer slices of R'R.
+ *       MMG_IMPL_TCGEN05 = x'(R'R)x on int8 tcgen05 tensor cores: diagonal in FP64, off-diagonal as exact base-128
+ *                          digit planes of R'R; the number of planes is chosen so that the certified truncation bound
+ *                          on x~.x~ is <= MMG_TC_TOL (1e-7) for every SNP (mmg_last_scan_info).
  * Outputs (host, length snp_count, any may be NULL): ps, f_stats, rss, var_perc, xx;
  * dots: [snp_count x nv]. */
 int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double h0_rss, double n_p,

@@ -45,6 +45,7 @@ SIGNATURES = {
     'mmg_timer_get': (C.c_int, [_c_ctx, C.c_char_p, _dp, C.POINTER(_i64)]),
     'mmg_timer_reset': (C.c_int, [_c_ctx]),
     'mmg_last_kernel_ms': (C.c_int, [_c_ctx, C.c_char_p, _dp]),
+    'mmg_last_scan_info': (C.c_int, [_c_ctx, C.POINTER(C.c_int), _dp]),
     'mmg_host_alloc': (C.c_int, [C.POINTER(_vp), _i64]),
     'mmg_host_free': (C.c_int, [_vp]),
     'mmg_mat_create': (C.c_int, [_c_ctx, _i64, _i64, C.POINTER(_i64)]),
@@ -266,6 +267,12 @@ class Context(object):
         v = C.c_double(0)
         self._ck(self.lib.mmg_last_kernel_ms(self.h, which.encode(), C.byref(v)))
         return v.value
+
+    def last_scan_info(self):
+        """(digit planes used, certified max relative truncation bound on x~.x~) of the most recent int8 scan."""
+        k, rho = C.c_int(0), C.c_double(0)
+        self._ck(self.lib.mmg_last_scan_info(self.h, C.byref(k), C.byref(rho)))
+        return k.value, rho.value
 
     def microbench(self, which):
         v = C.c_double(0)

@@ -360,6 +360,13 @@ int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms) {
     return MMG_OK;
 }
 
+int mmg_last_scan_info(mmg_ctx* ctx, int* slices, double* rho) {
+    MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    if (slices) *slices = ctx->last_scan_slices;
+    if (rho) *rho = ctx->last_scan_rho;
+    return MMG_OK;
+}
+
 int mmg_host_alloc(void** ptr, int64_t bytes) {
     if (!ptr || bytes < 0) return fail(nullptr, MMG_EBADARG, "mmg_host_alloc: bad argument");
     cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault);
@@ -1041,18 +1048,29 @@ static int launch_scan_dmma(mmg_ctx* ctx, bool perm, const ScanDmmaParams& prm) 
 }
 
 // ---- int8 tensor-core scan: x'(R'R)x on exact integer slices (scan_tc.cuh) ------------------------------
-static int scan_tc_slices() {
+// Number of digit planes.  MMG_TC_SLICES = k fixes it; otherwise it is chosen per call from the certified truncation
+// bound  |d(x~.x~)| / x~.x~ <= 0.25 128^-S 2^E ||x||_1^2 / x~.x~ <= MMG_TC_TOL (default 1e-7, i.e. < 2e-7 relative in
+// -log10 p for r^2 <= 0.5): a pilot launch over the first SNPs measures max_s 2^E ||x||_1^2 / x~.x~, the full launch
+// re-measures the bound over every SNP and is repeated with one more plane if a SNP violates it.
+constexpr int QS_AUTO_PLANES = 8;          // planes cut in auto mode (bound <= 0.25 128^-8 ... ~ 3e-18 2^E ||x||_1^2)
+constexpr int QS_PILOT_PLANES = 3;
+constexpr int64_t QS_PILOT_ROWS = 64 * TC_BM;
+
+static int scan_tc_fixed_slices() {
     const char* e = getenv("MMG_TC_SLICES");
-    int S = e ? atoi(e) : 7;
-    if (S < 1) S = 1;
-    if (S > QS_MAX_SLICES) S = QS_MAX_SLICES;
-    return S;
+    if (!e) return 0;
+    return std::max(1, std::min(QS_MAX_SLICES, atoi(e)));
+}
+static double scan_tc_tol() {
+    const char* e = getenv("MMG_TC_TOL");
+    const double t = e ? atof(e) : 1e-7;
+    return t > 0.0 ? t : 1e-7;
 }
 
-// Digit planes of A = R'R (lower triangle, off-diagonal doubled) into Bq (S planes of [n_padN x ldq]) and v = R'y into
-// d_v; returns the binary exponent E used for the scaling.  `A` is an n x n FP64 work matrix.
+// Digit planes of the strict lower triangle of A = R'R (doubled) into Bq (S planes of [n_padN x ldq]), diag(A) into
+// d_dg and v = R'y into d_v; returns the binary exponent E used for the scaling.  `A` is an n x n FP64 work matrix.
 static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, double* A, unsigned long long* d_amax, int S,
-                        int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, int* E_out) {
+                        int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, double* d_dg, int* E_out) {
     const int64_t n = R->cols, n_out = R->rows;
     const double one = 1.0, zero = 0.0;
     // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
@@ -1067,65 +1085,19 @@ static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, double
     double amax = 0.0;
     MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!(amax > 0.0) || !std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "scan: R'R is zero or not finite (max |a| = %g)", amax);
-    const int E = ilogb(amax) + 2;                       // |c a| 2^-E < 1/2
+    if (!std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "scan: R'R is not finite (max |a| = %g)", amax);
+    const int E = amax > 0.0 ? ilogb(amax) + 2 : 0;       // |2 a| 2^-E < 1/2 (a diagonal R'R has no off-diagonal digits at all)
     dim3 sgrid((unsigned)((n + 255) / 256), (unsigned)n);
-    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A, n, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq);
+    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A, n, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq, d_dg);
     MMG_TRY(launch_check(ctx, "quad_slice_kernel"));
     *E_out = E;
     return MMG_OK;
 }
 
-// T phenotypes (each with its own rotation R_t, residual y~_t and h0_rss_t) in one launch.  Device outputs are
-// [T][snp_count]; any may be NULL.
-static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const double* V, const double* h0_rss, double n_p, double lbeta,
-                       int64_t snp_begin, int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p,
-                       double* d_vp) {
-    const int64_t n = ctx->n, n_out = Rs[0]->rows;
-    const int S = scan_tc_slices();
-    const int64_t n_padN = round_up(n, TC_BN), ldq = round_up(n, TC_BK);
-    const int64_t plane = n_padN * ldq;
-    DevBuf A, Bq, vec;
-    MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)n * n * sizeof(double)));
-    MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S * plane));
-    // vec: v[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | amax
-    const int64_t nd = (int64_t)T * n_padN + (int64_t)T * n_out + 2 * T + 1;
-    MMG_CUDA(ctx, vec.alloc(ctx->stream, (size_t)nd * sizeof(double)));
-    double* d_v = vec.as<double>();
-    double* d_y = d_v + (int64_t)T * n_padN;
-    double* d_h0 = d_y + (int64_t)T * n_out;
-    double* d_es = d_h0 + T;
-    unsigned long long* d_amax = (unsigned long long*)(d_es + T);
-    MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)nd * sizeof(double), ctx->stream));
-    MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)T * S * plane, ctx->stream));
-    MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<double> escale((size_t)T);
-    for (int t = 0; t < T; ++t) {
-        int E = 0;
-        MMG_TRY(quad_prepare(ctx, Rs[t], d_y + (int64_t)t * n_out, A.as<double>(), d_amax, S, Bq.as<int8_t>() + (int64_t)t * S * plane,
-                             n_padN, ldq, d_v + (int64_t)t * n_padN, &E));
-        escale[t] = ldexp(1.0, E);
-    }
-    MMG_CUDA(ctx, cudaMemcpyAsync(d_es, escale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-
-    QuadEpi::Params ep{};
-    ep.snps = ctx->snps;
-    ep.pitch = ctx->pitch;
-    ep.row_begin = snp_begin;
-    ep.row_count = snp_count;
-    for (int k = 0; k < S; ++k) ep.w[k] = ldexp(1.0, -7 * (k + 1));
-    ep.escale = d_es;
-    ep.v = d_v;
-    ep.v_stride = n_padN;
-    ep.h0_rss = d_h0;
-    ep.n_p = n_p;
-    ep.lbeta = lbeta;
-    ep.out_stride = snp_count;
-    ep.xx = d_xx; ep.xy = d_xy; ep.rss = d_rss; ep.f = d_f; ep.p = d_p; ep.var_perc = d_vp;
-
+// one launch of the quadratic-form scan over resident rows [snp_begin, +snp_count) with S of the S_alloc cut planes
+static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* Bq, int64_t n_padN, int64_t ldq, int64_t snp_begin,
+                          int64_t snp_count, QuadEpi::Params ep) {
     const int tiles_n = (int)(n_padN / TC_BN), kb_total = (int)(ldq / TC_BK);
-    MMG_CHECK(ctx, (int64_t)T * S * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
     int cs = env_int("MMG_SCAN_CLUSTER", 2);
     if (cs != 1 && cs != 2 && cs != 4) cs = 2;
     // MMG_SCAN_SCHED = panel (genotype-stationary schedule, scan_quad.cuh) | pair (same, MMA as a CTA pair) |
@@ -1134,15 +1106,19 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     if (!sched) sched = "panel";
     const bool pair = strcmp(sched, "pair") == 0;
     if (pair) cs = 2;
+    ep.row_begin = snp_begin;
+    ep.row_count = snp_count;
+    ep.out_stride = snp_count;
     CUtensorMap tmA, tmB;
     MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
-    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq.p, ldq, (int64_t)T * S * n_padN, ldq, TC_BN / cs));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq, ldq, (int64_t)T * S_alloc * n_padN, ldq, TC_BN / cs));
     const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
     if (strcmp(sched, "table") != 0) {
         QuadShape sh{};
         sh.num_groups = groups;
         sh.T = T;
         sh.S = S;
+        sh.S_stride = S_alloc;
         sh.tiles_n = tiles_n;
         sh.kb_total = kb_total;
         sh.n_padN = (int)n_padN;
@@ -1157,7 +1133,6 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
             sh.dbg = dbg.as<long long>();
         }
         const int panel = env_int("MMG_SCAN_PANEL", 8);
-        cudaEventRecord(ctx->kev0, ctx->stream);
         if (pair) MMG_TRY(launch_scan_quad_pair(ctx, panel, tmA, tmB, sh, ep));
         else if (cs == 4) MMG_TRY(launch_scan_quad_cs<4>(ctx, panel, tmA, tmB, sh, ep));
         else if (cs == 2) MMG_TRY(launch_scan_quad_cs<2>(ctx, panel, tmA, tmB, sh, ep));
@@ -1185,7 +1160,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
                 for (int k = 0; k < S; ++k) {
                     TcTile tl{};
                     tl.m0 = 0;
-                    tl.n0 = (int)(((int64_t)t * S + k) * n_padN + (int64_t)jb * TC_BN);
+                    tl.n0 = (int)(((int64_t)t * S_alloc + k) * n_padN + (int64_t)jb * TC_BN);
                     tl.kb0 = 0;
                     tl.kb1 = std::min(kb_total, (jb + 1) * (TC_BN / TC_BK));
                     tl.aux0 = k;
@@ -1195,7 +1170,6 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
                     tiles.push_back(tl);
                 }
         MMG_TRY(ensure_tiles(ctx, tiles));
-        cudaEventRecord(ctx->kev0, ctx->stream);
         const TcTile* td = (const TcTile*)ctx->tiles_d;
         if (cs == 4)
             MMG_TRY((launch_tc_gemm<QuadEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,4>", L2_EVICT_FIRST, L2_EVICT_LAST)));
@@ -1204,8 +1178,104 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         else
             MMG_TRY((launch_tc_gemm<QuadEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,1>", L2_EVICT_FIRST, L2_EVICT_LAST)));
     }
-    cudaEventRecord(ctx->kev1, ctx->stream);
-    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // Bq / A / vec are freed on return
+    return MMG_OK;
+}
+
+// T phenotypes (each with its own rotation R_t, residual y~_t and h0_rss_t) in one launch.  Device outputs are
+// [T][snp_count]; any may be NULL.
+static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const double* V, const double* h0_rss, double n_p, double lbeta,
+                       int64_t snp_begin, int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p,
+                       double* d_vp) {
+    const int64_t n = ctx->n, n_out = Rs[0]->rows;
+    const int S_fixed = scan_tc_fixed_slices();
+    const int S_alloc = S_fixed ? S_fixed : QS_AUTO_PLANES;
+    const double tol = scan_tc_tol();
+    const int64_t n_padN = round_up(n, TC_BN), ldq = round_up(n, TC_BK);
+    const int64_t plane = n_padN * ldq;
+    MMG_CHECK(ctx, (int64_t)T * S_alloc * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
+    DevBuf A, Bq, vec;
+    MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)n * n * sizeof(double)));
+    MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S_alloc * plane));
+    // vec: v[T][n_padN] | dg[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | bscale[T] | amax | rho
+    const int64_t nd = 2 * (int64_t)T * n_padN + (int64_t)T * n_out + 3 * T + 2;
+    MMG_CUDA(ctx, vec.alloc(ctx->stream, (size_t)nd * sizeof(double)));
+    double* d_v = vec.as<double>();
+    double* d_dg = d_v + (int64_t)T * n_padN;
+    double* d_y = d_dg + (int64_t)T * n_padN;
+    double* d_h0 = d_y + (int64_t)T * n_out;
+    double* d_es = d_h0 + T;
+    double* d_bs = d_es + T;
+    unsigned long long* d_amax = (unsigned long long*)(d_bs + T);
+    unsigned long long* d_rho = d_amax + 1;
+    MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)nd * sizeof(double), ctx->stream));
+    MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)T * S_alloc * plane, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> escale((size_t)T), bscale((size_t)T);
+    for (int t = 0; t < T; ++t) {
+        int E = 0;
+        MMG_TRY(quad_prepare(ctx, Rs[t], d_y + (int64_t)t * n_out, A.as<double>(), d_amax, S_alloc,
+                             Bq.as<int8_t>() + (int64_t)t * S_alloc * plane, n_padN, ldq, d_v + (int64_t)t * n_padN,
+                             d_dg + (int64_t)t * n_padN, &E));
+        escale[t] = ldexp(1.0, E);
+    }
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_es, escale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+
+    QuadEpi::Params ep{};
+    ep.snps = ctx->snps;
+    ep.pitch = ctx->pitch;
+    for (int k = 0; k < QS_MAX_SLICES; ++k) ep.w[k] = ldexp(1.0, -7 * (k + 1));
+    ep.escale = d_es;
+    ep.v = d_v;
+    ep.dg = d_dg;
+    ep.bscale = d_bs;
+    ep.rho_max = d_rho;
+    ep.v_stride = n_padN;
+    ep.h0_rss = d_h0;
+    ep.n_p = n_p;
+    ep.lbeta = lbeta;
+
+    // bound scale for S planes: 0.25 128^-S 2^E_t
+    auto set_bscale = [&](int S) -> int {
+        for (int t = 0; t < T; ++t) bscale[t] = 0.25 * ldexp(1.0, -7 * S) * escale[t];
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_bs, bscale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaMemsetAsync(d_rho, 0, sizeof(unsigned long long), ctx->stream));
+        return MMG_OK;
+    };
+    auto read_rho = [&](double* rho) -> int {
+        MMG_CUDA(ctx, cudaMemcpyAsync(rho, d_rho, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return MMG_OK;
+    };
+
+    int S = S_fixed ? S_fixed : 7;
+    if (!S_fixed && snp_count >= 4 * QS_PILOT_ROWS) {
+        // pilot: bound of the first rows with few planes; the bound scales exactly by 128 per plane
+        QuadEpi::Params pp = ep;
+        pp.xx = pp.xy = pp.rss = pp.f = pp.p = pp.var_perc = nullptr;
+        MMG_TRY(set_bscale(QS_PILOT_PLANES));
+        MMG_TRY(scan_tc_launch(ctx, T, QS_PILOT_PLANES, S_alloc, Bq.p, n_padN, ldq, snp_begin, QS_PILOT_ROWS, pp));
+        double rho = 0.0;
+        MMG_TRY(read_rho(&rho));
+        S = QS_PILOT_PLANES;
+        while (S < S_alloc && rho * 4.0 /* head-room for the rows the pilot did not see */ > tol) {
+            rho /= 128.0;
+            ++S;
+        }
+    }
+    double rho = 0.0;
+    for (;;) {
+        ep.xx = d_xx; ep.xy = d_xy; ep.rss = d_rss; ep.f = d_f; ep.p = d_p; ep.var_perc = d_vp;
+        MMG_TRY(set_bscale(S));
+        cudaEventRecord(ctx->kev0, ctx->stream);
+        MMG_TRY(scan_tc_launch(ctx, T, S, S_alloc, Bq.p, n_padN, ldq, snp_begin, snp_count, ep));
+        cudaEventRecord(ctx->kev1, ctx->stream);
+        MMG_TRY(read_rho(&rho));                                // also: Bq / A / vec are freed on return
+        if (S_fixed || rho <= tol || S >= S_alloc) break;
+        ++S;                                                    // a SNP outside the certified bound: one more plane, again
+    }
+    ctx->last_scan_slices = S;
+    ctx->last_scan_rho = rho;
     return MMG_OK;
 }
 

@@ -37,6 +37,8 @@ struct mmg_ctx {
     int64_t launches = 0;
     std::map<std::string, MmgTimer> timers;
     double last_gram_ms = 0.0, last_scan_ms = 0.0, last_perm_ms = 0.0, last_ibd_ms = 0.0;
+    int last_scan_slices = 0;          // digit planes used by the most recent int8 scan
+    double last_scan_rho = 0.0;        // its certified relative truncation bound on x~.x~ (max over SNPs)
 
     // resident genotypes
     int8_t* snps = nullptr;

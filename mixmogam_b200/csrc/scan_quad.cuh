@@ -33,7 +33,8 @@ namespace mmg {
 struct QuadShape {
     int num_groups;     // 128-SNP row blocks
     int T;              // phenotypes
-    int S;              // digit planes per phenotype
+    int S;              // digit planes used per phenotype
+    int S_stride;       // digit planes allocated per phenotype (plane k of phenotype t starts at row (t S_stride + k) n_padN)
     int tiles_n;        // 256-column tiles of B (n_padN / 256)
     int kb_total;       // 128-byte K blocks (ldq / 128)
     int n_padN;         // rows per digit plane
@@ -93,7 +94,7 @@ struct QuadIter {
         if (++t >= sh.T) t = 0;         // the next group sweeps the same stream again
         set_panel(sh);
     }
-    __device__ __forceinline__ int row(const QuadShape& sh) const { return (t * sh.S + k) * sh.n_padN + jb * TC_BN; }
+    __device__ __forceinline__ int row(const QuadShape& sh) const { return (t * sh.S_stride + k) * sh.n_padN + jb * TC_BN; }
     __device__ __forceinline__ int kb() const { return kbase + i; }
 };
 
@@ -199,7 +200,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int jb = kbase >> 1; jb < sh.tiles_n; ++jb) {
                             const int nkb = min(nka, 2 * (jb + 1) - kbase);
                             for (int k = 0; k < sh.S; ++k) {
-                                const int rowB = (t * sh.S + k) * sh.n_padN + jb * TC_BN + crank * kBRows;
+                                const int rowB = (t * sh.S_stride + k) * sh.n_padN + jb * TC_BN + crank * kBRows;
                                 for (int i = 0; i < nkb; ++i) {
                                     if (sh.prefetch) {
                                         if (elect_one()) tma_prefetch_2d(&tmB, pf.kb() * TC_BK, pf.row(sh) + crank * kBRows);
@@ -319,6 +320,19 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int half = (warp - 2) >> 2;                       // 0: columns 0..127 of a tile, 1: columns 128..255
         const int row = quad * 32 + lane;
         constexpr int kCols = TC_BN / 2;
+        auto load_x = [](const int8_t* xrow, int col, uint32_t (&dst)[kCols / 4]) {
+            if (xrow != nullptr) {
+                const uint4* xp = reinterpret_cast<const uint4*>(xrow + col);
+#pragma unroll
+                for (int u = 0; u < kCols / 16; ++u) {
+                    const uint4 w = __ldg(xp + u);
+                    dst[4 * u + 0] = w.x; dst[4 * u + 1] = w.y; dst[4 * u + 2] = w.z; dst[4 * u + 3] = w.w;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < kCols / 4; ++u) dst[u] = 0u;
+            }
+        };
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
@@ -326,14 +340,19 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int64_t orow = (int64_t)g * TC_BM + row;
             const int8_t* xrow = (g < sh.num_groups && orow < ep.row_count) ? ep.snps + (ep.row_begin + orow) * ep.pitch : nullptr;
             for (int t = 0; t < sh.T; ++t) {
-                double q = 0.0, xy = 0.0;
+                double q = 0.0, xy = 0.0, qd = 0.0;
+                int a1 = 0;
+                uint32_t xn[kCols / 4];
+                bool have_next = false;
                 const double* vt = ep.v + (int64_t)t * ep.v_stride;
+                const double* dt = ep.dg + (int64_t)t * ep.v_stride;
                 for (int kbase = 0; kbase < sh.kb_total; kbase += PKB) {
                     for (int jb = kbase >> 1; jb < sh.tiles_n; ++jb) {
                         const int col0 = jb * TC_BN + half * kCols;
                         if (kbase == 0 && xrow != nullptr) {    // x.(R'y~): every column tile meets panel 0 exactly once
                             const uint4* xp = reinterpret_cast<const uint4*>(xrow + col0);
                             const double* vv = vt + col0;
+                            const double* dd = dt + col0;
 #pragma unroll 1
                             for (int u = 0; u < kCols / 16; ++u) {
                                 const uint4 w = __ldg(xp + u);
@@ -342,21 +361,25 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 for (int j = 0; j < 16; ++j) {
                                     const int xv = (int)(int8_t)((ww[j >> 2] >> (8 * (j & 3))) & 0xffu);
                                     xy = fma((double)xv, vv[16 * u + j], xy);
+                                    qd = fma((double)(xv * xv), dd[16 * u + j], qd);      // diagonal of x'Ax, FP64
+                                    a1 += abs(xv);
                                 }
                             }
                         }
-                        // this SNP's genotypes at the warp's 128 columns, reused by the S digit planes
+                        // this SNP's genotypes at the warp's 128 columns, reused by the S digit planes; the loads for the
+                        // next column tile are issued now and land while this tile's S accumulators are drained
                         uint32_t xr[kCols / 4];
-                        if (xrow != nullptr) {
-                            const uint4* xp = reinterpret_cast<const uint4*>(xrow + col0);
+                        if (have_next) {
 #pragma unroll
-                            for (int u = 0; u < kCols / 16; ++u) {
-                                const uint4 w = __ldg(xp + u);
-                                xr[4 * u + 0] = w.x; xr[4 * u + 1] = w.y; xr[4 * u + 2] = w.z; xr[4 * u + 3] = w.w;
-                            }
+                            for (int u = 0; u < kCols / 4; ++u) xr[u] = xn[u];
                         } else {
-#pragma unroll
-                            for (int u = 0; u < kCols / 4; ++u) xr[u] = 0u;
+                            load_x(xrow, col0, xr);
+                        }
+                        {
+                            int nk = kbase, nj = jb + 1;
+                            if (nj >= sh.tiles_n) { nk = kbase + PKB; nj = nk >> 1; }
+                            have_next = nk < sh.kb_total;
+                            if (have_next) load_x(xrow, nj * TC_BN + half * kCols, xn);
                         }
                         for (int k = 0; k < sh.S; ++k) {
                             // keep the packed bytes opaque per digit plane: otherwise the sign-extended genotypes are
@@ -405,14 +428,15 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
                 // fold the two column halves of each SNP, then RSS / F / p by the lower half's thread
-                if (half == 1) xchg[row] = q;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0) q += xchg[row];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 1) xchg[row] = xy;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0 && xrow != nullptr) QuadEpi::store(ep, t, orow, q, xy + xchg[row]);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                double part[4] = {q, xy, qd, (double)a1};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (half == 1) xchg[row] = part[u];
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (half == 0) part[u] += xchg[row];
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+                if (half == 0 && xrow != nullptr) QuadEpi::store(ep, t, orow, part[0], part[1], part[2], part[3]);
             }
         }
         if (timed && warp == 2 && lane == 0) {

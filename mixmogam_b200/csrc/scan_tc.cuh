@@ -2,8 +2,9 @@
 //
 // The left operand of the EMMAX rotation (linear_models.py:1317-1318) is an exact small-integer genotype
 // vector, so only the FP64 matrix has to be split.  With A = R'R (symmetric, FP64):
-//     x'Ax = sum_j x_j * sum_{i<=j} c_ij A_ji x_i ,   c_ij = 2 (i<j), 1 (i==j)
-// B[j][i] = c_ij A_ji * 2^-E (|B| < 1/2) is cut into S signed base-128 digits b_k in [-64,64]:
+//     x'Ax = sum_j A_jj x_j^2  +  sum_j x_j * sum_{i<j} 2 A_ji x_i
+// The diagonal term stays in FP64 (epilogue).  B[j][i] = 2 A_ji * 2^-E (i < j, |B| < 1/2) is cut into S signed
+// base-128 digits b_k in [-64,64]:
 //     B = sum_k 128^-(k+1) b_k  (+ error <= 0.5 * 128^-S),
 // every partial product x.b_k is an exact int32 (tcgen05.mma kind::i8), and the epilogue folds
 //     q_s += w_k * sum_j acc[s][j] * x[s][j],   w_k = 2^E 128^-(k+1)
@@ -38,19 +39,24 @@ struct QuadEpi {
         double w[QS_MAX_SLICES];     // slice weights 2^(-7(k+1)); the per-phenotype 2^E_t is in escale
         const double* escale;        // [T] 2^E_t
         const double* v;             // [T][v_stride] R_t'y~_t (zero padded)
+        const double* dg;            // [T][v_stride] diag(R_t'R_t): the diagonal of the quadratic form is kept in FP64
+        const double* bscale;        // [T] 0.25 * 128^-S * 2^E_t: truncation bound of the off-diagonal digits per unit ||x||_1^2
+        unsigned long long* rho_max; // max over SNPs of bound / (x~.x~), bits of a non-negative double (certification)
         int64_t v_stride;
         const double* h0_rss;        // [T]
         double n_p, lbeta;
         int64_t out_stride;          // outputs are [T][out_stride]
         double *xx, *xy, *rss, *f, *p, *var_perc;
     };
-    double q, xy;
+    double q, xy, qd, xl1;
     const int8_t* xrow;
     int64_t orow;
 
     __device__ __forceinline__ void begin_group(const Params& p, int g, int row) {
         q = 0.0;
         xy = 0.0;
+        qd = 0.0;
+        xl1 = 0.0;
         orow = (int64_t)g * TC_BM + row;
         xrow = (orow < p.row_count) ? p.snps + (p.row_begin + orow) * p.pitch : nullptr;
     }
@@ -59,6 +65,8 @@ struct QuadEpi {
         if (t.aux1 & QS_FLAG_FIRST) {
             q = 0.0;
             xy = 0.0;
+            qd = 0.0;
+            xl1 = 0.0;
         }
         return TC_BN / 32;           // uniform across the warp: tcgen05.ld is warp-collective
     }
@@ -77,22 +85,33 @@ struct QuadEpi {
         q = fma(p.w[t.aux0], (double)s, q);
         if (t.aux1 & QS_FLAG_XY) {
             const double* vv = p.v + (int64_t)(t.aux1 >> QS_PHEN_SHIFT) * p.v_stride + col0;
+            const double* dd = p.dg + (int64_t)(t.aux1 >> QS_PHEN_SHIFT) * p.v_stride + col0;
+            int a1 = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int xv = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xffu);
                 xy = fma((double)xv, vv[j], xy);
+                qd = fma((double)(xv * xv), dd[j], qd);
+                a1 += abs(xv);
             }
+            xl1 += (double)a1;
         }
     }
     __device__ __forceinline__ void tile_end(const Params& p, const TcTile& t, int row, int lane) {
         if (!(t.aux1 & QS_FLAG_LAST) || xrow == nullptr) return;
-        store(p, t.aux1 >> QS_PHEN_SHIFT, orow, q, xy);
+        store(p, t.aux1 >> QS_PHEN_SHIFT, orow, q, xy, qd, xl1);
     }
-    // RSS / F / p of one SNP for phenotype ph from q = x'Ax 2^-E and xy = x.(R'y~)  (linear_models.py:1329,1345-1349)
-    static __device__ __forceinline__ void store(const Params& p, int ph, int64_t orow, double q, double xy) {
+    // RSS / F / p of one SNP for phenotype ph (linear_models.py:1329,1345-1349) from
+    //   q  = off-diagonal part of x'Ax in units of 2^E (digit planes), qd = sum_j A_jj x_j^2 (FP64), xy = x.(R'y~),
+    //   x1 = ||x||_1 (for the certified truncation bound |dq| <= 0.25 128^-S 2^E ||x||_1^2)
+    static __device__ __forceinline__ void store(const Params& p, int ph, int64_t orow, double q, double xy, double qd, double x1) {
         const int64_t o = (int64_t)ph * p.out_stride + orow;
         const double h0 = p.h0_rss[ph];
-        const double sxx = q * p.escale[ph], sxy = xy;
+        const double sxx = fma(q, p.escale[ph], qd), sxy = xy;
+        if (p.rho_max != nullptr && sxx > 0.0) {
+            const double rho = p.bscale[ph] * x1 * x1 / sxx;
+            atomicMax(p.rho_max, (unsigned long long)__double_as_longlong(rho));
+        }
         if (p.xx) p.xx[o] = sxx;
         if (p.xy) p.xy[o] = sxy;
         double rss = h0, f = 0.0, vp = 0.0, pv = 1.0;
@@ -174,25 +193,30 @@ struct PermEpi {
     }
 };
 
-// max |c_ij A[j][i]| over the row-major lower triangle (i <= j) -> bits of a non-negative double
+// max |2 A[j][i]| over the strict lower triangle (i < j) of the row-major matrix -> bits of a non-negative double
 __global__ void quad_amax_kernel(const double* __restrict__ A, int64_t ld, int n, unsigned long long* __restrict__ amax_bits) {
     const int j = blockIdx.y;
     double m = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= j; i += gridDim.x * blockDim.x) {
-        const double a = fabs(A[(int64_t)j * ld + i]) * (i < j ? 2.0 : 1.0);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j; i += gridDim.x * blockDim.x) {
+        const double a = fabs(A[(int64_t)j * ld + i]) * 2.0;
         m = fmax(m, a);
     }
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(amax_bits, (unsigned long long)__double_as_longlong(m));
 }
 
-// digits of B[j][i] = c_ij A[j][i] 2^-E into S stacked int8 planes Bq[(k * n_padN + j) * ldq + i]
+// digits of B[j][i] = 2 A[j][i] 2^-E (i < j) into S stacked int8 planes Bq[(k * n_padN + j) * ldq + i]; the diagonal
+// goes to dg[j] = A[j][j] and stays in FP64 (it is usually the largest entry: keeping it out of the digit planes lowers E)
 __global__ void quad_slice_kernel(const double* __restrict__ A, int64_t ld, int n, double scale /* 2^-E */, int S,
-                                  int8_t* __restrict__ Bq, int64_t n_padN, int64_t ldq) {
+                                  int8_t* __restrict__ Bq, int64_t n_padN, int64_t ldq, double* __restrict__ dg) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i > j || i >= n) return;
-    double r = A[(int64_t)j * ld + i] * (i < j ? 2.0 : 1.0) * scale;     // |r| < 0.5, exact scaling
+    if (i == j) {
+        dg[j] = A[(int64_t)j * ld + j];
+        return;
+    }
+    double r = A[(int64_t)j * ld + i] * 2.0 * scale;                     // |r| < 0.5, exact scaling
     for (int k = 0; k < S; ++k) {
         r *= 128.0;
         const double d = rint(r);                                        // in [-64, 64]
