@@ -251,6 +251,7 @@ def main():
 
     # ---- set-up outside the hot path: K once, its two eigendecompositions (timed separately) ----
     fp64_peak = ctx.microbench('dmma') if rank == 0 else 0.0      # FP64 tensor (DMMA) issue rate, GPU still cool
+    imma_peak = ctx.microbench('imma_tcgen05') if rank == 0 else 0.0   # tcgen05 int8 issue rate, smem-resident operands
     ctx.ensure_snps(snps)
     Kd = parallel.calc_ibs_kinship_sharded(snps, m, 'diploid_int', ctx=ctx)
     lmm = lm.LinearMixedModel(y, ctx=ctx, scan_impl=args.scan_impl)
@@ -371,8 +372,13 @@ def main():
             exec_ops = 2.0 * m_loc * 256 * 128 * kblocks * S           # int8 MAC*2 actually issued (lower-triangular K ranges)
             bf16 = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops') or 1590.0
             int8_peak = 2.0 * bf16                                       # int8 tcgen05 rate = 2 x bf16 (same pipe, K=32 vs 16)
+            # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu capture of this very configuration
+            # (profiles/r01_ncu_full_scan_quad_1m.txt); null for any other shape
+            traffic = 76745941248 + 59100672 if (n, m, world) == (10000, 1000000, 1) and not os.environ.get('MMG_SCAN_SCHED') else None
             roof = {'bound': 'tensor', 'kernel': 'tc_gemm_i8_kernel<QuadEpi>' if os.environ.get('MMG_SCAN_SCHED') == 'table' else 'scan_quad_kernel', 'achieved': exec_ops / scan_s / 1e12,
-                    'peak': int8_peak, 'unit': 'TFLOP/s', 'frac': exec_ops / scan_s / 1e12 / int8_peak, 'traffic': None,
+                    'peak': int8_peak, 'unit': 'TFLOP/s', 'frac': exec_ops / scan_s / 1e12 / int8_peak, 'traffic': traffic,
+                    'algorithmic_bytes': float(m_loc) * n + 8.0 * m_loc, 'int8_issue_rate_measured': imma_peak,
+                    'frac_of_issue_rate': exec_ops / scan_s / 1e12 / imma_peak if imma_peak else None,
                     'pipe': 'int8 tcgen05 (TOP/s); peak = 2 x measured sustained bf16 %s' % ('of measured' if peaks else 'of fallback'),
                     'algorithmic_fp64_tflops': alg_flops / scan_s / 1e12, 'fp64_tensor_peak_measured': fp64_peak,
                     'slices': S, 'certified_rel_bound_xx': rho, 'launch_ms': scan_s * 1e3}

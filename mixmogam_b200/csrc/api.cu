@@ -157,10 +157,10 @@ static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMa
 }
 
 // Launch the genotype-stationary scan kernel (scan_quad.cuh): cluster CS, panel of PKB K-blocks, STAGES digit stages.
-template <int CS, int PKB, int STAGES, bool PAIR>
+template <int CS, int PKB, int STAGES, bool PAIR, int BN>
 static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, QuadShape sh, const QuadEpi::Params& ep) {
-    auto kern = scan_quad_kernel<CS, PKB, STAGES, PAIR>;
-    constexpr int smem = QuadSmem<PKB, STAGES, PAIR>::kBytes;
+    auto kern = scan_quad_kernel<CS, PKB, STAGES, PAIR, BN>;
+    constexpr int smem = QuadSmem<PKB, STAGES, PAIR, BN>::kBytes;
     {   // per device, cheap: set on every launch
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "scan_quad_kernel: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
@@ -197,17 +197,33 @@ static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensor
 template <int CS>
 static int launch_scan_quad_cs(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
                                const QuadEpi::Params& ep) {
-    if (panel == 8) return launch_scan_quad<CS, 8, 3, false>(ctx, tmA, tmB, sh, ep);
-    if (panel == 4) return launch_scan_quad<CS, 4, 5, false>(ctx, tmA, tmB, sh, ep);
-    return launch_scan_quad<CS, 6, 4, false>(ctx, tmA, tmB, sh, ep);
+    if (panel == 8) return launch_scan_quad<CS, 8, 3, false, 256>(ctx, tmA, tmB, sh, ep);
+    if (panel == 4) return launch_scan_quad<CS, 4, 5, false, 256>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<CS, 6, 4, false, 256>(ctx, tmA, tmB, sh, ep);
 }
 
 // CTA-pair form (tcgen05.mma.cta_group::2): half digit tiles of 16 KB per stage
 static int launch_scan_quad_pair(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
                                  const QuadEpi::Params& ep) {
-    if (panel == 8) return launch_scan_quad<2, 8, 6, true>(ctx, tmA, tmB, sh, ep);
-    if (panel == 4) return launch_scan_quad<2, 4, 10, true>(ctx, tmA, tmB, sh, ep);
-    return launch_scan_quad<2, 6, 8, true>(ctx, tmA, tmB, sh, ep);
+    if (panel == 8) return launch_scan_quad<2, 8, 6, true, 256>(ctx, tmA, tmB, sh, ep);
+    if (panel == 4) return launch_scan_quad<2, 4, 10, true, 256>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<2, 6, 8, true, 256>(ctx, tmA, tmB, sh, ep);
+}
+
+// CTA-pair form with 128-column tiles: four accumulator stages in TMEM, so the MMA may run three tiles ahead of the
+// epilogue and the cross-CTA barrier latency of the pair leaves the critical path; 8 KB half tiles per stage
+static int launch_scan_quad_pair128(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
+                                    const QuadEpi::Params& ep) {
+    if (panel == 12) return launch_scan_quad<2, 12, 4, true, 128>(ctx, tmA, tmB, sh, ep);
+    if (panel == 10) return launch_scan_quad<2, 10, 8, true, 128>(ctx, tmA, tmB, sh, ep);
+    if (panel == 6) return launch_scan_quad<2, 6, 16, true, 128>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<2, 8, 12, true, 128>(ctx, tmA, tmB, sh, ep);
+}
+// single-CTA MMA with 128-column tiles (four accumulator stages), digit tiles multicast over the cluster of 2
+static int launch_scan_quad_n128(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
+                                 const QuadEpi::Params& ep) {
+    if (panel == 10) return launch_scan_quad<2, 10, 4, false, 128>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<2, 8, 6, false, 128>(ctx, tmA, tmB, sh, ep);
 }
 
 // MMG_GRAM_IMPL / MMG_SCAN_IMPL = tcgen05 | simt | dmma select what MMG_IMPL_AUTO means (both are CUDA paths)
@@ -552,6 +568,7 @@ int mmg_snps_free(mmg_ctx* ctx) {
     cudaFree(ctx->snps);
     ctx->snps = nullptr;
     ctx->m = ctx->n = ctx->pitch = 0;
+    ctx->snps_absmax = -1;
     return MMG_OK;
 }
 int mmg_snps_reserve(mmg_ctx* ctx, int64_t m, int64_t n) {
@@ -571,6 +588,7 @@ int mmg_snps_reserve(mmg_ctx* ctx, int64_t m, int64_t n) {
 int mmg_snps_write(mmg_ctx* ctx, int64_t row0, const int8_t* snps, int64_t rows, int64_t ld) {
     MMG_CHECK(ctx, ctx && ctx->snps && snps && row0 >= 0 && rows >= 0 && row0 + rows <= ctx->m && ld >= ctx->n,
               "mmg_snps_write: bad argument");
+    ctx->snps_absmax = -1;
     StageTimer tm(ctx, "h2d");
     // one strided DMA; measured at the PCIe rate (52 GB/s from page-locked memory), a staged 1-D copy + re-pitch kernel was no faster
     if (rows)
@@ -586,6 +604,7 @@ int mmg_snps_upload(mmg_ctx* ctx, const int8_t* snps, int64_t m, int64_t n, int6
 int mmg_snps_upload_rows(mmg_ctx* ctx, const int8_t* const* rows, int64_t m, int64_t n) {
     MMG_CHECK(ctx, ctx && rows, "mmg_snps_upload_rows: bad argument");
     MMG_TRY(mmg_snps_reserve(ctx, m, n));
+    ctx->snps_absmax = -1;
     StageTimer tm(ctx, "h2d");
     // gather rows into two pinned staging buffers and copy them asynchronously
     const int64_t rows_per = std::max<int64_t>(1, (32ll << 20) / n);
@@ -623,6 +642,7 @@ int mmg_snps_shape(mmg_ctx* ctx, int64_t* m, int64_t* n) {
 }
 int mmg_snps_device_ptr(mmg_ctx* ctx, void** dptr, int64_t* pitch) {
     MMG_CHECK(ctx, ctx && dptr, "bad argument");
+    ctx->snps_absmax = -1;             // the caller may write through the pointer
     *dptr = ctx->snps;
     if (pitch) *pitch = ctx->pitch;
     return MMG_OK;
@@ -1047,6 +1067,41 @@ static int launch_scan_dmma(mmg_ctx* ctx, bool perm, const ScanDmmaParams& prm) 
     return MMG_OK;
 }
 
+// max |x| over the resident genotype block (zero padding included), 16 bytes per thread per step
+__global__ void snps_absmax_kernel(const uint4* __restrict__ p, int64_t n16, int* __restrict__ out) {
+    int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 w = p[i];
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int v = (int)(int8_t)((ww[j >> 2] >> (8 * (j & 3))) & 0xffu);
+            m = max(m, v < 0 ? -v : v);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// The int8 scan keeps per-tile sums in int32: |acc| <= 128 PKB |x| 64 and 16 columns x |x| per chain, safe for
+// |x| <= QS_MAX_ABS_GENOTYPE (genotypes are 0/1/2, kinship.py:14-56).  Measured once per resident block.
+constexpr int QS_MAX_ABS_GENOTYPE = 8;
+static int scan_tc_check_domain(mmg_ctx* ctx) {
+    if (ctx->snps_absmax < 0) {
+        MMG_CUDA(ctx, cudaMemsetAsync(ctx->flag_d, 0, sizeof(int), ctx->stream));
+        snps_absmax_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint4*)ctx->snps, ctx->m * ctx->pitch / 16, ctx->flag_d);
+        MMG_TRY(launch_check(ctx, "snps_absmax_kernel"));
+        int v = 0;
+        MMG_CUDA(ctx, cudaMemcpyAsync(&v, ctx->flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->snps_absmax = v;
+    }
+    if (ctx->snps_absmax > QS_MAX_ABS_GENOTYPE)
+        return fail(ctx, MMG_EVALUE, "int8 tensor-core scan: |genotype| up to %d exceeds its exact-integer domain (<= %d); "
+                    "use the FP64 tensor-core path (scan_impl='dmma')", ctx->snps_absmax, QS_MAX_ABS_GENOTYPE);
+    return MMG_OK;
+}
+
 // ---- int8 tensor-core scan: x'(R'R)x on exact integer slices (scan_tc.cuh) ------------------------------
 // Number of digit planes.  MMG_TC_SLICES = k fixes it; otherwise it is chosen per call from the certified truncation
 // bound  |d(x~.x~)| / x~.x~ <= 0.25 128^-S 2^E ||x||_1^2 / x~.x~ <= MMG_TC_TOL (default 1e-7, i.e. < 2e-7 relative in
@@ -1096,22 +1151,24 @@ static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, double
 
 // one launch of the quadratic-form scan over resident rows [snp_begin, +snp_count) with S of the S_alloc cut planes
 static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* Bq, int64_t n_padN, int64_t ldq, int64_t snp_begin,
-                          int64_t snp_count, QuadEpi::Params ep) {
-    const int tiles_n = (int)(n_padN / TC_BN), kb_total = (int)(ldq / TC_BK);
+                          int64_t snp_count, QuadEpi::Params ep, unsigned* d_wave_sync) {
     int cs = env_int("MMG_SCAN_CLUSTER", 2);
     if (cs != 1 && cs != 2 && cs != 4) cs = 2;
     // MMG_SCAN_SCHED = panel (genotype-stationary schedule, scan_quad.cuh) | pair (same, MMA as a CTA pair) |
-    //                  table (tile-table kernel, tc_gemm.cuh)
+    //                  pair128 / n128 (128-column tiles, four accumulator stages) | table (tile-table kernel, tc_gemm.cuh)
     const char* sched = getenv("MMG_SCAN_SCHED");
     if (!sched) sched = "panel";
-    const bool pair = strcmp(sched, "pair") == 0;
-    if (pair) cs = 2;
+    const bool pair128 = strcmp(sched, "pair128") == 0, n128 = strcmp(sched, "n128") == 0;
+    const bool pair = strcmp(sched, "pair") == 0 || pair128;
+    if (pair || n128) cs = 2;
+    const int bn = (pair128 || n128) ? 128 : TC_BN;
+    const int tiles_n = (int)(n_padN / bn), kb_total = (int)(ldq / TC_BK);
     ep.row_begin = snp_begin;
     ep.row_count = snp_count;
     ep.out_stride = snp_count;
     CUtensorMap tmA, tmB;
     MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
-    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq, ldq, (int64_t)T * S_alloc * n_padN, ldq, TC_BN / cs));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq, ldq, (int64_t)T * S_alloc * n_padN, ldq, bn / cs));
     const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
     if (strcmp(sched, "table") != 0) {
         QuadShape sh{};
@@ -1123,6 +1180,10 @@ static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* B
         sh.kb_total = kb_total;
         sh.n_padN = (int)n_padN;
         sh.prefetch = std::max(0, env_int("MMG_SCAN_PREFETCH", 8));
+        if (env_int("MMG_SCAN_WAVE_SYNC", 1) && d_wave_sync) {
+            MMG_CUDA(ctx, cudaMemsetAsync(d_wave_sync, 0, sizeof(unsigned), ctx->stream));
+            sh.wave_sync = d_wave_sync;
+        }
         // MMG_SCAN_DBG_CLOCKS=<file>: per-CTA cycle counters of the three warp roles (time spent in each barrier wait)
         const char* dbg_path = getenv("MMG_SCAN_DBG_CLOCKS");
         DevBuf dbg;
@@ -1133,7 +1194,9 @@ static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* B
             sh.dbg = dbg.as<long long>();
         }
         const int panel = env_int("MMG_SCAN_PANEL", 8);
-        if (pair) MMG_TRY(launch_scan_quad_pair(ctx, panel, tmA, tmB, sh, ep));
+        if (pair128) MMG_TRY(launch_scan_quad_pair128(ctx, panel, tmA, tmB, sh, ep));
+        else if (n128) MMG_TRY(launch_scan_quad_n128(ctx, panel, tmA, tmB, sh, ep));
+        else if (pair) MMG_TRY(launch_scan_quad_pair(ctx, panel, tmA, tmB, sh, ep));
         else if (cs == 4) MMG_TRY(launch_scan_quad_cs<4>(ctx, panel, tmA, tmB, sh, ep));
         else if (cs == 2) MMG_TRY(launch_scan_quad_cs<2>(ctx, panel, tmA, tmB, sh, ep));
         else MMG_TRY(launch_scan_quad_cs<1>(ctx, panel, tmA, tmB, sh, ep));
@@ -1187,6 +1250,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
                        int64_t snp_begin, int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p,
                        double* d_vp) {
     const int64_t n = ctx->n, n_out = Rs[0]->rows;
+    MMG_TRY(scan_tc_check_domain(ctx));
     const int S_fixed = scan_tc_fixed_slices();
     const int S_alloc = S_fixed ? S_fixed : QS_AUTO_PLANES;
     const double tol = scan_tc_tol();
@@ -1196,8 +1260,8 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     DevBuf A, Bq, vec;
     MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)n * n * sizeof(double)));
     MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S_alloc * plane));
-    // vec: v[T][n_padN] | dg[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | bscale[T] | amax | rho
-    const int64_t nd = 2 * (int64_t)T * n_padN + (int64_t)T * n_out + 3 * T + 2;
+    // vec: v[T][n_padN] | dg[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | bscale[T] | amax | rho | wave counter
+    const int64_t nd = 2 * (int64_t)T * n_padN + (int64_t)T * n_out + 3 * T + 3;
     MMG_CUDA(ctx, vec.alloc(ctx->stream, (size_t)nd * sizeof(double)));
     double* d_v = vec.as<double>();
     double* d_dg = d_v + (int64_t)T * n_padN;
@@ -1207,6 +1271,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     double* d_bs = d_es + T;
     unsigned long long* d_amax = (unsigned long long*)(d_bs + T);
     unsigned long long* d_rho = d_amax + 1;
+    unsigned* d_wave = (unsigned*)(d_rho + 1);
     MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)nd * sizeof(double), ctx->stream));
     MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)T * S_alloc * plane, ctx->stream));
     MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1254,7 +1319,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         QuadEpi::Params pp = ep;
         pp.xx = pp.xy = pp.rss = pp.f = pp.p = pp.var_perc = nullptr;
         MMG_TRY(set_bscale(QS_PILOT_PLANES));
-        MMG_TRY(scan_tc_launch(ctx, T, QS_PILOT_PLANES, S_alloc, Bq.p, n_padN, ldq, snp_begin, QS_PILOT_ROWS, pp));
+        MMG_TRY(scan_tc_launch(ctx, T, QS_PILOT_PLANES, S_alloc, Bq.p, n_padN, ldq, snp_begin, QS_PILOT_ROWS, pp, d_wave));
         double rho = 0.0;
         MMG_TRY(read_rho(&rho));
         S = QS_PILOT_PLANES;
@@ -1268,7 +1333,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         ep.xx = d_xx; ep.xy = d_xy; ep.rss = d_rss; ep.f = d_f; ep.p = d_p; ep.var_perc = d_vp;
         MMG_TRY(set_bscale(S));
         cudaEventRecord(ctx->kev0, ctx->stream);
-        MMG_TRY(scan_tc_launch(ctx, T, S, S_alloc, Bq.p, n_padN, ldq, snp_begin, snp_count, ep));
+        MMG_TRY(scan_tc_launch(ctx, T, S, S_alloc, Bq.p, n_padN, ldq, snp_begin, snp_count, ep, d_wave));
         cudaEventRecord(ctx->kev1, ctx->stream);
         MMG_TRY(read_rho(&rho));                                // also: Bq / A / vec are freed on return
         if (S_fixed || rho <= tol || S >= S_alloc) break;

@@ -43,6 +43,7 @@ struct mmg_ctx {
     // resident genotypes
     int8_t* snps = nullptr;
     int64_t m = 0, n = 0, pitch = 0;
+    int snps_absmax = -1;          // max |genotype| of the resident block, -1 = not measured since the last write
 
     // kinship state
     int32_t* G = nullptr;          // [g_pad x g_pad]

@@ -93,8 +93,11 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
+// arrive on a barrier of another CTA of the cluster.  Default (.release.cta) semantics as in CUTLASS' ClusterBarrier:
+// the consumers only READ tensor memory before this arrive and order it with tcgen05.fence::before_thread_sync; a
+// .release.cluster here costs a cluster-scope fence per tile per warp.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair into ITS OWN shared memory; complete_tx lands on the barrier at
 // cluster address `bar_cluster` (the leader CTA's barrier)

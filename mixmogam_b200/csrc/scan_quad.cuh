@@ -35,11 +35,12 @@ struct QuadShape {
     int T;              // phenotypes
     int S;              // digit planes used per phenotype
     int S_stride;       // digit planes allocated per phenotype (plane k of phenotype t starts at row (t S_stride + k) n_padN)
-    int tiles_n;        // 256-column tiles of B (n_padN / 256)
+    int tiles_n;        // BN-column tiles of B (n_padN / BN)
     int kb_total;       // 128-byte K blocks (ldq / 128)
     int n_padN;         // rows per digit plane
     int prefetch;       // L2 prefetch distance in K blocks (0 = off)
     long long* dbg;     // nullptr, or [grid x 16] cycle counters of the three roles (MMG_SCAN_DBG_CLOCKS)
+    unsigned* wave_sync;  // nullptr, or a zeroed counter: CTAs start each wave of SNP groups together (see below)
 };
 
 // mbarrier wait that adds the cycles spent waiting to *acc when counters are requested
@@ -53,30 +54,33 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
     }
 }
 
-template <int PKB, int STAGES, bool PAIR = false>
+template <int PKB, int STAGES, bool PAIR = false, int BN = TC_BN>
 struct QuadSmem {
-    static constexpr int kBStage = PAIR ? TC_B_BYTES / 2 : TC_B_BYTES;
+    static constexpr int kBTile = BN * TC_BK;                              // one digit K-block of a BN-column tile
+    static constexpr int kAccStages = TC_TMEM_COLS / BN;                   // 2 (BN = 256) or 4 (BN = 128)
+    static constexpr int kBStage = PAIR ? kBTile / 2 : kBTile;
     static constexpr int kABytes = PKB * TC_A_BYTES;
     static constexpr int kBBytes = STAGES * kBStage;
-    static constexpr int kBars = 2 * STAGES + 2 * PKB + 2 * TC_ACC_STAGES;
-    static_assert(kBars + 1 <= 40, "barrier block");
-    static constexpr int kBytes = kABytes + kBBytes + 1024 /*align slack*/ + 320 /*barriers + tmem slot*/ + 1024 /*q, xy exchange*/;
+    static constexpr int kBars = 2 * STAGES + 2 * PKB + 2 * kAccStages;
+    static_assert(kBars + 1 <= 64, "barrier block");
+    static constexpr int kBytes = kABytes + kBBytes + 1024 /*align slack*/ + 512 /*barriers + tmem slot*/ + 1024 /*q, xy exchange*/;
     static_assert(kBytes <= 232448, "shared memory budget (227 KB)");
 };
 
 // position in the digit-plane stream of one group: (t, kp, jb, k, i) -> B row / K block; used by the L2 prefetcher
-template <int PKB>
+template <int PKB, int BN>
 struct QuadIter {
+    static constexpr int kKbPerTile = BN / TC_BK;      // K blocks (of 128 individuals) per column tile
     int t, kp, jb, k, i, kbase, nka, nkb;
     __device__ __forceinline__ void set_jb(const QuadShape& sh) {
-        nkb = min(nka, 2 * (jb + 1) - kbase);
+        nkb = min(nka, kKbPerTile * (jb + 1) - kbase);
         k = 0;
         i = 0;
     }
     __device__ __forceinline__ void set_panel(const QuadShape& sh) {
         kbase = kp * PKB;
         nka = min(PKB, sh.kb_total - kbase);
-        jb = kbase >> 1;
+        jb = kbase / kKbPerTile;
         set_jb(sh);
     }
     __device__ __forceinline__ void reset(const QuadShape& sh) {
@@ -94,21 +98,26 @@ struct QuadIter {
         if (++t >= sh.T) t = 0;         // the next group sweeps the same stream again
         set_panel(sh);
     }
-    __device__ __forceinline__ int row(const QuadShape& sh) const { return (t * sh.S_stride + k) * sh.n_padN + jb * TC_BN; }
+    __device__ __forceinline__ int row(const QuadShape& sh) const { return (t * sh.S_stride + k) * sh.n_padN + jb * BN; }
     __device__ __forceinline__ int kb() const { return kbase + i; }
 };
 
 constexpr int QP_EPI_WARPS = 8;
 constexpr int QP_THREADS = 64 + 32 * QP_EPI_WARPS;       // producer warp, MMA warp, 8 epilogue warps
 
-template <int CS, int PKB, int STAGES, bool PAIR>
+template <int CS, int PKB, int STAGES, bool PAIR, int BN>
 __global__ void __launch_bounds__(QP_THREADS, 1)
 scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const QuadShape sh,
                  uint64_t policy_a, uint64_t policy_b, const QuadEpi::Params ep) {
-    static_assert(PKB % 2 == 0 && PKB <= 8, "panel = whole 256-column tiles, per-tile sums must fit int32");
+    static_assert(PKB <= 12, "per-tile integer sums: |acc| <= 128 PKB |x| 64 must leave room for 16 columns x |x| in int32");
     static_assert(!PAIR || CS == 2, "a CTA pair is a cluster of 2");
-    using SM = QuadSmem<PKB, STAGES, PAIR>;
+    static_assert(BN == 256 || BN == 128, "column tile");
+    static_assert(PKB % (BN / TC_BK) == 0, "panel = whole column tiles");
+    using SM = QuadSmem<PKB, STAGES, PAIR, BN>;
     constexpr int kBStage = SM::kBStage;
+    constexpr int kBTile = SM::kBTile;
+    constexpr int kAcc = SM::kAccStages;               // accumulator stages in the 512 TMEM columns
+    constexpr int kKbPerTile = BN / TC_BK;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;                              // PKB genotype K-blocks  [128 x 128 B], 128B swizzle
@@ -119,9 +128,9 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* afull_bar = empty_bar + STAGES;         // [PKB]     genotype K-block landed
     uint64_t* aempty_bar = afull_bar + PKB;           // [PKB]     last MMA of the panel on this K-block retired
     uint64_t* tfull_bar = aempty_bar + PKB;           // [2]       accumulator complete
-    uint64_t* tempty_bar = tfull_bar + TC_ACC_STAGES; // [2]       accumulator drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + TC_ACC_STAGES);
-    double* xchg = reinterpret_cast<double*>(bars + 40);    // [128] q, then xy, of the upper column half (1 KB)
+    uint64_t* tempty_bar = tfull_bar + kAcc;          // [kAcc]    accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAcc);
+    double* xchg = reinterpret_cast<double*>(bars + 64);    // [128] q, then xy, of the upper column half (1 KB)
 
     // warp index through a shuffle: the compiler then knows the role branches are warp-uniform, keeps loop counters,
     // addresses and descriptors in uniform registers and issues UTCIMMA / UTMALDG without per-lane ELECT loops
@@ -132,7 +141,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_clusters = gridDim.x / CS;
     const int num_cgroups = (sh.num_groups + CS - 1) / CS;
     constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
-    constexpr int kBRows = TC_BN / CS;                // digit-tile rows this CTA fetches
+    constexpr int kBRows = BN / CS;                   // digit-tile rows this CTA fetches
     const bool leader = !PAIR || crank == 0;
 
     if (warp == 0 && lane == 0) {
@@ -146,7 +155,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&afull_bar[i], 1);
             mbar_init(&aempty_bar[i], 1);
         }
-        for (int a = 0; a < TC_ACC_STAGES; ++a) {
+        for (int a = 0; a < kAcc; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], PAIR ? 2 * QP_EPI_WARPS : QP_EPI_WARPS);  // pair: both CTAs' epilogue warps release the leader's MMA
         }
@@ -176,31 +185,66 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool timed = sh.dbg != nullptr;
             long long w_aempty = 0, w_empty = 0;
             const long long t_start = timed ? clock64() : 0;
-            QuadIter<PKB> pf;
+            QuadIter<PKB, BN> pf;
             pf.reset(sh);
             for (int d = 0; d < sh.prefetch; ++d) pf.advance(sh);
-            for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
+            unsigned wave_target = 0;
+            int wave = 0;
+            uint32_t pre = 0;                           // genotype K-blocks of the coming panel that are already requested
+            auto issue_a = [&](int i, int kb0, int row0) {
+                mbar_wait_timed(&aempty_bar[i], ((abits >> i) & 1u) ^ 1u, timed, w_aempty);
+                abits ^= 1u << i;
+                if (elect_one()) {
+                    if (PAIR) {
+                        if (leader) mbar_expect_tx(&afull_bar[i], 2 * TC_A_BYTES);
+                        tma_load_2d_pair(smA + i * TC_A_BYTES, &tmA, mapa_u32(&afull_bar[i], 0), (kb0 + i) * TC_BK, row0, policy_a);
+                    } else {
+                        mbar_expect_tx(&afull_bar[i], TC_A_BYTES);
+                        tma_load_2d(smA + i * TC_A_BYTES, &tmA, &afull_bar[i], (kb0 + i) * TC_BK, row0, policy_a);
+                    }
+                }
+            };
+            for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters, ++wave) {
                 const int m0 = (cg * CS + crank) * TC_BM;
+                if (sh.wave_sync != nullptr) {
+                    // Every CTA sweeps the same digit-plane stream once per SNP group.  Left alone the CTAs drift apart over
+                    // the ~50 waves of a 1M-SNP scan until the stream (0.26 GB) is re-read from HBM by each of them
+                    // (ncu: 474 GB of DRAM reads); starting each wave together keeps the stream L2-resident: one HBM
+                    // pass per wave.  All CTAs are co-resident (persistent grid <= SM count), so the spin cannot deadlock.
+                    const int clusters_in_wave = min(num_clusters, num_cgroups - wave * num_clusters);
+                    wave_target += (unsigned)(clusters_in_wave * CS);
+                    if (elect_one()) {
+                        atomicAdd(sh.wave_sync, 1u);
+                        unsigned seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sh.wave_sync) : "memory");
+                            if (seen < wave_target) __nanosleep(200);
+                        } while (seen < wave_target);
+                    }
+                    __syncwarp();
+                }
                 for (int t = 0; t < sh.T; ++t) {
                     for (int kbase = 0; kbase < sh.kb_total; kbase += PKB) {
                         const int nka = min(PKB, sh.kb_total - kbase);
-                        for (int i = 0; i < nka; ++i) {
-                            mbar_wait_timed(&aempty_bar[i], ((abits >> i) & 1u) ^ 1u, timed, w_aempty);
-                            abits ^= 1u << i;
-                            if (elect_one()) {
-                                if (PAIR) {
-                                    if (leader) mbar_expect_tx(&afull_bar[i], 2 * TC_A_BYTES);
-                                    tma_load_2d_pair(smA + i * TC_A_BYTES, &tmA, mapa_u32(&afull_bar[i], 0), (kbase + i) * TC_BK, m0, policy_a);
-                                } else {
-                                    mbar_expect_tx(&afull_bar[i], TC_A_BYTES);
-                                    tma_load_2d(smA + i * TC_A_BYTES, &tmA, &afull_bar[i], (kbase + i) * TC_BK, m0, policy_a);
-                                }
-                            }
+                        for (int i = 0; i < nka; ++i)
+                            if (!((pre >> i) & 1u)) issue_a(i, kbase, m0);             // not loaded ahead (first panel of the launch)
+                        pre = 0;
+                        // the panel after this one (next panel / phenotype / SNP group of this CTA): its genotype K-blocks are
+                        // requested while the LAST tile of this panel is still being multiplied, K-block by K-block as the
+                        // MMA retires them, so a panel switch does not drain the pipeline
+                        int nk = kbase + PKB, ncg = cg;
+                        if (nk >= sh.kb_total) {
+                            nk = 0;
+                            if (t + 1 >= sh.T) ncg = cg + num_clusters;
                         }
-                        for (int jb = kbase >> 1; jb < sh.tiles_n; ++jb) {
-                            const int nkb = min(nka, 2 * (jb + 1) - kbase);
+                        const bool has_next = ncg < num_cgroups;
+                        const int nka_next = has_next ? min(PKB, sh.kb_total - nk) : 0;
+                        const int m0_next = (ncg * CS + crank) * TC_BM;
+                        for (int jb = kbase / kKbPerTile; jb < sh.tiles_n; ++jb) {
+                            const int nkb = min(nka, kKbPerTile * (jb + 1) - kbase);
                             for (int k = 0; k < sh.S; ++k) {
-                                const int rowB = (t * sh.S_stride + k) * sh.n_padN + jb * TC_BN + crank * kBRows;
+                                const int rowB = (t * sh.S_stride + k) * sh.n_padN + jb * BN + crank * kBRows;
+                                const bool last_tile = (jb == sh.tiles_n - 1) && (k == sh.S - 1);
                                 for (int i = 0; i < nkb; ++i) {
                                     if (sh.prefetch) {
                                         if (elect_one()) tma_prefetch_2d(&tmB, pf.kb() * TC_BK, pf.row(sh) + crank * kBRows);
@@ -209,12 +253,12 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     mbar_wait_timed(&empty_bar[stage], phase ^ 1, timed, w_empty);
                                     if (elect_one()) {
                                         if (PAIR) {
-                                            if (leader) mbar_expect_tx(&full_bar[stage], TC_B_BYTES);  // both halves
+                                            if (leader) mbar_expect_tx(&full_bar[stage], kBTile);      // both halves
                                             tma_load_2d_pair(smB + stage * kBStage, &tmB, mapa_u32(&full_bar[stage], 0), (kbase + i) * TC_BK,
                                                              rowB, policy_b);
                                         } else {
-                                            mbar_expect_tx(&full_bar[stage], TC_B_BYTES);
-                                            uint8_t* sb = smB + stage * TC_B_BYTES + crank * kBRows * TC_BK;
+                                            mbar_expect_tx(&full_bar[stage], kBTile);
+                                            uint8_t* sb = smB + stage * kBTile + crank * kBRows * TC_BK;
                                             if (CS == 1)
                                                 tma_load_2d(sb, &tmB, &full_bar[stage], (kbase + i) * TC_BK, rowB, policy_b);
                                             else
@@ -222,9 +266,20 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                         }
                                     }
                                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                    // the slot just refilled was freed by the MMA of K-block i - STAGES of this tile, which also
+                                    // released genotype K-block i - STAGES of the panel: reload it for the next panel now
+                                    if (last_tile && i >= STAGES && i - STAGES < nka_next) {
+                                        issue_a(i - STAGES, nk, m0_next);
+                                        pre |= 1u << (i - STAGES);
+                                    }
                                 }
                             }
                         }
+                        for (int i = max(0, nka - STAGES); i < nka_next; ++i)
+                            if (!((pre >> i) & 1u)) {
+                                issue_a(i, nk, m0_next);
+                                pre |= 1u << i;
+                            }
                     }
                 }
             }
@@ -241,7 +296,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== MMA issuer (all lanes run the loops, one elected lane issues) =====================
         if (leader) {
             const bool one = lane == 0;
-            constexpr uint32_t idesc = umma_idesc_i8(PAIR ? 2 * TC_BM : TC_BM, TC_BN);
+            constexpr uint32_t idesc = umma_idesc_i8(PAIR ? 2 * TC_BM : TC_BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -256,13 +311,13 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int kbase = 0; kbase < sh.kb_total; kbase += PKB) {
                         const int nka = min(PKB, sh.kb_total - kbase);
                         uint32_t seen = 0;
-                        for (int jb = kbase >> 1; jb < sh.tiles_n; ++jb) {
-                            const int nkb = min(nka, 2 * (jb + 1) - kbase);
+                        for (int jb = kbase / kKbPerTile; jb < sh.tiles_n; ++jb) {
+                            const int nkb = min(nka, kKbPerTile * (jb + 1) - kbase);
                             for (int k = 0; k < sh.S; ++k) {
                                 const bool last_tile = (jb == sh.tiles_n - 1) && (k == sh.S - 1);
                                 mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1, timed, w_tempty);
                                 tc_fence_after();
-                                const uint32_t d_tmem = tmem_base + acc * TC_BN;
+                                const uint32_t d_tmem = tmem_base + acc * BN;
                                 for (int i = 0; i < nkb; ++i) {
                                     if (!((seen >> i) & 1u)) {             // first use of this genotype K-block in the panel
                                         mbar_wait_timed(&afull_bar[i], (abits >> i) & 1u, timed, w_afull);
@@ -294,7 +349,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 if (elect_one()) {
                                     if (PAIR) umma_commit_pair(&tfull_bar[acc], 0b11); else umma_commit(&tfull_bar[acc]);
                                 }
-                                if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                                if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
                             }
                         }
                     }
@@ -319,7 +374,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;                       // 0: columns 0..127 of a tile, 1: columns 128..255
         const int row = quad * 32 + lane;
-        constexpr int kCols = TC_BN / 2;
+        constexpr int kCols = BN / 2;
         auto load_x = [](const int8_t* xrow, int col, uint32_t (&dst)[kCols / 4]) {
             if (xrow != nullptr) {
                 const uint4* xp = reinterpret_cast<const uint4*>(xrow + col);
@@ -347,8 +402,8 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const double* vt = ep.v + (int64_t)t * ep.v_stride;
                 const double* dt = ep.dg + (int64_t)t * ep.v_stride;
                 for (int kbase = 0; kbase < sh.kb_total; kbase += PKB) {
-                    for (int jb = kbase >> 1; jb < sh.tiles_n; ++jb) {
-                        const int col0 = jb * TC_BN + half * kCols;
+                    for (int jb = kbase / kKbPerTile; jb < sh.tiles_n; ++jb) {
+                        const int col0 = jb * BN + half * kCols;
                         if (kbase == 0 && xrow != nullptr) {    // x.(R'y~): every column tile meets panel 0 exactly once
                             const uint4* xp = reinterpret_cast<const uint4*>(xrow + col0);
                             const double* vv = vt + col0;
@@ -377,9 +432,9 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         {
                             int nk = kbase, nj = jb + 1;
-                            if (nj >= sh.tiles_n) { nk = kbase + PKB; nj = nk >> 1; }
+                            if (nj >= sh.tiles_n) { nk = kbase + PKB; nj = nk / kKbPerTile; }
                             have_next = nk < sh.kb_total;
-                            if (have_next) load_x(xrow, nj * TC_BN + half * kCols, xn);
+                            if (have_next) load_x(xrow, nj * BN + half * kCols, xn);
                         }
                         for (int k = 0; k < sh.S; ++k) {
                             // keep the packed bytes opaque per digit plane: otherwise the sign-extended genotypes are
@@ -388,7 +443,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int u = 0; u < kCols / 4; ++u) asm volatile("" : "+r"(xr[u]));
                             mbar_wait_timed(&tfull_bar[acc], acc_phase, timed, w_tfull);
                             tc_fence_after();
-                            const uint32_t taddr = tmem_base + acc * TC_BN + half * kCols + (static_cast<uint32_t>(quad * 32) << 16);
+                            const uint32_t taddr = tmem_base + acc * BN + half * kCols + (static_cast<uint32_t>(quad * 32) << 16);
                             uint32_t va[16], vb[16];
                             int s0 = 0, s1 = 0, s2 = 0, s3 = 0;                // four chains
                             tmem_ld_32x16(taddr, va);
@@ -420,9 +475,9 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) {
-                                if (PAIR) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0)); else mbar_arrive(&tempty_bar[acc]);
+                                if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0)); else mbar_arrive(&tempty_bar[acc]);
                             }
-                            if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                            if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
                             q = fma(ep.w[k], qt, q);
                         }
                     }

@@ -235,3 +235,72 @@ def test_emmax_multi_matches_single_and_oracle(ctx):
     for t in range(3):
         single = lm.emmax(snps, Y[t], K, cofactors=[cof], scan_impl='tcgen05')
         np.testing.assert_allclose(res2[t]['ps'][ok], single['ps'][ok], rtol=1e-9)
+
+
+@pytest.mark.parametrize('sched,panel', [('panel', '8'), ('panel', '6'), ('pair', '8'), ('pair128', '10'), ('n128', '8'), ('table', '8')])
+def test_scan_schedules_agree(ctx, monkeypatch, sched, panel):
+    """Every schedule of the int8 scan (genotype-stationary panels, CTA-pair MMA, 128-column tiles, tile table) gives the
+    same statistics as the FP64 tensor-core path: several panels, ragged last SNP group, three waves of SNP groups."""
+    from mixmogam_b200 import kinship, linear_models as lm
+    from oracle import reference_py3 as o
+    n, m = 1100, 40000 + 77
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=77)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int')
+    y = o.synth_phenotype(snps, K, seed=6)
+    ra = lm.emmax(snps, y, K, scan_impl='dmma')
+    monkeypatch.setenv('MMG_SCAN_SCHED', sched)
+    monkeypatch.setenv('MMG_SCAN_PANEL', panel)
+    rb = lm.emmax(snps, y, K, scan_impl='tcgen05')
+    assert neglog10_rel_err(ra['ps'], rb['ps']) < 1e-6
+    assert np.array_equal(np.argsort(ra['ps'], kind='stable')[:100], np.argsort(rb['ps'], kind='stable')[:100])
+    np.testing.assert_allclose(rb['rss'], ra['rss'], rtol=1e-7)
+
+
+def test_scan_plane_count_is_certified(ctx, monkeypatch):
+    """The number of base-128 digit planes is chosen from the certified truncation bound (pilot launch + check over every
+    SNP); MMG_TC_SLICES fixes it, MMG_TC_TOL moves it."""
+    from mixmogam_b200 import kinship, linear_models as lm
+    from oracle import reference_py3 as o
+    n, m = 600, 36000
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=5)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int')
+    y = o.synth_phenotype(snps, K, seed=2)
+    ref = lm.emmax(snps, y, K, scan_impl='dmma')
+    r = lm.emmax(snps, y, K, scan_impl='tcgen05')
+    S, rho = ctx.last_scan_info()
+    assert 3 <= S <= 8 and 0.0 < rho <= 1e-7
+    assert neglog10_rel_err(ref['ps'], r['ps']) < 1e-6
+    monkeypatch.setenv('MMG_TC_TOL', '1e-12')
+    r2 = lm.emmax(snps, y, K, scan_impl='tcgen05')
+    S2, rho2 = ctx.last_scan_info()
+    assert S2 > S and rho2 <= 1e-12
+    assert neglog10_rel_err(ref['ps'], r2['ps']) < 1e-7
+    monkeypatch.delenv('MMG_TC_TOL')
+    monkeypatch.setenv('MMG_TC_SLICES', '3')
+    r3 = lm.emmax(snps, y, K, scan_impl='tcgen05')
+    S3, rho3 = ctx.last_scan_info()
+    assert S3 == 3 and rho3 > rho
+    # the certified bound really bounds the error of x~.x~ (rss = h0_rss - xy^2/xx moves by at most ~rho3 relative in xx)
+    xx_ref = ref['h0_rss'] - ref['rss']
+    xx_3 = r3['h0_rss'] - r3['rss']
+    ok = xx_ref > 1e-9 * ref['h0_rss']
+    assert np.max(np.abs(xx_3[ok] / xx_ref[ok] - 1.0)) <= 2.0 * rho3 + 1e-9
+
+
+def test_scan_int8_domain_guard(ctx):
+    """Genotype magnitudes beyond the exact-integer domain of the int8 scan are refused loudly; the FP64 path takes them."""
+    from mixmogam_b200 import _lib, linear_models as lm
+    from oracle import reference_py3 as o
+    g = golden('emmax_diploid_n400.npz')
+    snps = g['snps'].copy()
+    snps[3, 5] = 9
+    ctx.invalidate_snps()
+    with pytest.raises(_lib.MmgError):
+        lm.emmax(snps, g['y'], g['K'], scan_impl='tcgen05')
+    ctx.invalidate_snps()
+    r = lm.emmax(snps, g['y'], g['K'], scan_impl='dmma')
+    ro = o.emmax(list(snps), g['y'], g['K'], dtype='double')
+    assert neglog10_rel_err(r['ps'], ro['ps']) < 1e-6
+    ctx.invalidate_snps()
