@@ -228,6 +228,8 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
+        # rank 0 prints exactly ONE line on stdout (the JSON): NCCL's own banner / debug lines go to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda:%d' % local))
     device = torch.device('cuda:%d' % local)
 

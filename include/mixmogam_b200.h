@@ -83,6 +83,9 @@ int mmg_mat_copy(mmg_ctx* ctx, mmg_mat dst, mmg_mat src);
 /* C = alpha * op(A) * op(B) + beta * C   (cuBLAS dgemm; a plain library GEMM, outside the hot path) */
 int mmg_mat_gemm(mmg_ctx* ctx, int trans_a, int trans_b, double alpha, mmg_mat A, mmg_mat B,
                  double beta, mmg_mat C);
+/* A = R[row_begin:+row_count, :]' R[row_begin:+row_count, :]  -- row-major LOWER triangle of the n x n matrix A
+ * (n = cols of R); the multi-GPU scan sums these per-rank blocks into R'R (linear_models.py:1299-1303 gives M = R') */
+int mmg_mat_syrk_rows(mmg_ctx* ctx, mmg_mat R, int64_t row_begin, int64_t row_count, mmg_mat A);
 int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat A, const double* d_host);         /* A[i,:] *= d[i] */
 int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat A, double alpha);                   /* A += alpha*I   */
 /* kinship.scale_k (kinship.py:94-100): c = tr(K) - sum(K)/n ; K *= (n-1)/c ; returns the scalar */
@@ -153,6 +156,11 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double 
                        int impl, int64_t snp_begin, int64_t snp_count,
                        double* ps, double* f_stats, double* rss, double* var_perc,
                        double* xx, double* dots);
+/* The int8 tensor-core form of mmg_emmax_scan_f64 for a caller that already holds A = R'R (n x n, row-major lower
+ * triangle valid) and v = R'y~ [n] -- e.g. A summed over ranks from mmg_mat_syrk_rows blocks.  Same outputs. */
+int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat A, const double* v, double h0_rss, double n_p,
+                            int64_t snp_begin, int64_t snp_count,
+                            double* ps, double* f_stats, double* rss, double* var_perc, double* xx);
 /* Phenotype-batched scan: T phenotypes scanned against one genotype block in ONE launch (BASELINE.json configs[2];
  * the reference calls linear_models.emmax once per phenotype, linear_models.py:1790).  R[t] is the rotation of
  * phenotype t (its own delta_t enters through H_t), V[t] its residual phenotype in the rotated space ([T x n_out]),

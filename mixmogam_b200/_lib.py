@@ -56,6 +56,7 @@ SIGNATURES = {
     'mmg_mat_device_ptr': (C.c_int, [_c_ctx, _i64, C.POINTER(_vp), C.POINTER(_i64)]),
     'mmg_mat_copy': (C.c_int, [_c_ctx, _i64, _i64]),
     'mmg_mat_gemm': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_double, _i64, _i64, C.c_double, _i64]),
+    'mmg_mat_syrk_rows': (C.c_int, [_c_ctx, _i64, _i64, _i64, _i64]),
     'mmg_mat_scale_rows': (C.c_int, [_c_ctx, _i64, _vp]),
     'mmg_mat_add_diag': (C.c_int, [_c_ctx, _i64, C.c_double]),
     'mmg_mat_scale_k': (C.c_int, [_c_ctx, _i64, _dp]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     'mmg_reml_f64': (C.c_int, [_c_ctx, _vp, _vp, _i64, _i64, _vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _i64, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_emmax_scan_quad_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_double, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_multi_f64': (C.c_int, [_c_ctx, _vp, C.c_int, _vp, _vp, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_perm_scan_f64': (C.c_int, [_c_ctx, _i64, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
     'mmg_f_sf_f64': (C.c_int, [_c_ctx, _vp, _i64, C.c_double, C.c_double, _vp]),
@@ -258,7 +260,7 @@ class Context(object):
         return s.value, c.value
 
     def timers(self):
-        return {k: self.timer(k)[0] for k in ('h2d', 'pack', 'gram', 'finalize', 'ibd', 'syevd', 'reml', 'scan', 'd2h')}
+        return {k: self.timer(k)[0] for k in ('h2d', 'pack', 'gram', 'finalize', 'ibd', 'syevd', 'reml', 'scan_prep', 'scan', 'd2h')}
 
     def timer_reset(self):
         self._ck(self.lib.mmg_timer_reset(self.h))
@@ -386,6 +388,13 @@ class Context(object):
         self._ck(self.lib.mmg_mat_gemm(self.h, int(ta), int(tb), alpha, A.handle, B.handle, beta, C_out.handle))
         return C_out
 
+    def syrk_rows(self, R, row_begin, row_count, A_out=None):
+        """A = R[row_begin:+row_count, :]' R[...] (row-major lower triangle of the n x n result)."""
+        if A_out is None:
+            A_out = DeviceMatrix(self, R.shape[1], R.shape[1])
+        self._ck(self.lib.mmg_mat_syrk_rows(self.h, R.handle, int(row_begin), int(row_count), A_out.handle))
+        return A_out
+
     def scale_rows(self, A, d):
         d = np.ascontiguousarray(d, dtype=np.float64)
         assert d.shape[0] == A.shape[0]
@@ -480,6 +489,19 @@ class Context(object):
                                              snp_begin, snp_count, _ptr(out.get('ps')), _ptr(out.get('f_stats')),
                                              _ptr(out.get('rss')), _ptr(out.get('var_perc')), _ptr(out['xx']),
                                              _ptr(out.get('dots'))))
+        return out
+
+    def emmax_scan_quad(self, A, v, h0_rss, n_p, snp_begin=0, snp_count=None):
+        """The int8 scan given the quadratic form A = R'R (DeviceMatrix, lower triangle) and v = R'y~ (length n)."""
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+        assert v.shape[0] == n and A.shape == (n, n), (v.shape, A.shape, n)
+        out = {k: np.empty(snp_count, dtype=np.float64) for k in ('ps', 'f_stats', 'rss', 'var_perc', 'xx')}
+        self._ck(self.lib.mmg_emmax_scan_quad_f64(self.h, A.handle, _ptr(v), float(h0_rss), float(n_p), snp_begin, snp_count,
+                                                  _ptr(out['ps']), _ptr(out['f_stats']), _ptr(out['rss']), _ptr(out['var_perc']),
+                                                  _ptr(out['xx'])))
         return out
 
     def emmax_scan_multi(self, Rs, V, h0_rss, n_p, snp_begin=0, snp_count=None, want=('ps', 'f_stats', 'rss', 'var_perc')):

@@ -469,6 +469,28 @@ int mmg_mat_gemm(mmg_ctx* ctx, int ta, int tb, double alpha, mmg_mat Ah, mmg_mat
                                 (int)k, &alpha, B->d, (int)B->cols, A->d, (int)A->cols, &beta, C->d, (int)C->cols));
     return MMG_OK;
 }
+// A = R[row_begin : row_begin + row_count, :]' R[...]   (row-major LOWER triangle of the n x n matrix A; the strict upper
+// triangle is left as it was).  Row blocks of R are contiguous, so ranks that each take a block of the n_out rows of the
+// rotation and sum their A's (all-reduce) get R'R with 1/ranks of the flops each.
+int mmg_mat_syrk_rows(mmg_ctx* ctx, mmg_mat Rh, int64_t row_begin, int64_t row_count, mmg_mat Ah) {
+    MmgMat* R = ctx ? get_mat(ctx, Rh) : nullptr;
+    MmgMat* A = ctx ? get_mat(ctx, Ah) : nullptr;
+    MMG_CHECK(ctx, R && A, "mmg_mat_syrk_rows: unknown matrix handle");
+    MMG_CHECK(ctx, A->rows == R->cols && A->cols == R->cols, "A must be %lld x %lld", (long long)R->cols, (long long)R->cols);
+    MMG_CHECK(ctx, row_begin >= 0 && row_count >= 0 && row_begin + row_count <= R->rows, "row block out of range");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm(ctx, "scan_prep");
+    const int64_t n = R->cols;
+    const double one = 1.0, zero = 0.0;
+    if (row_count == 0) {
+        MMG_CUDA(ctx, cudaMemsetAsync(A->d, 0, (size_t)n * n * sizeof(double), ctx->stream));
+        return MMG_OK;
+    }
+    // the row block is the column-major n x row_count matrix Rc; column-major UPPER of Rc Rc' = row-major LOWER of A
+    MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)row_count, &one, R->d + row_begin * n, (int)n,
+                                &zero, A->d, (int)n));
+    return MMG_OK;
+}
 int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat h, const double* d_host) {
     MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, A && d_host, "mmg_mat_scale_rows: bad argument");
@@ -1124,15 +1146,20 @@ static double scan_tc_tol() {
 
 // Digit planes of the strict lower triangle of A = R'R (doubled) into Bq (S planes of [n_padN x ldq]), diag(A) into
 // d_dg and v = R'y into d_v; returns the binary exponent E used for the scaling.  `A` is an n x n FP64 work matrix.
-static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, double* A, unsigned long long* d_amax, int S,
-                        int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, double* d_dg, int* E_out) {
-    const int64_t n = R->cols, n_out = R->rows;
+static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const double* A_given, double* A_work, unsigned long long* d_amax,
+                        int S, int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, double* d_dg, int* E_out) {
+    const int64_t n = ctx->n;
     const double one = 1.0, zero = 0.0;
-    // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
-    // is the row-major LOWER triangle A[j][i], i <= j -- exactly the operand the slices are cut from.
-    MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero, A, (int)n));
-    // v = R' y~  (x~.y~ = x.v)
-    if (d_y) MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1));
+    const double* A = A_given;
+    if (!A_given) {
+        const int64_t n_out = R->rows;
+        // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
+        // is the row-major LOWER triangle A[j][i], i <= j -- exactly the operand the slices are cut from.
+        MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero, A_work, (int)n));
+        // v = R' y~  (x~.y~ = x.v)
+        if (d_y) MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1));
+        A = A_work;
+    }
     MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
     dim3 agrid(8, (unsigned)n);
     quad_amax_kernel<<<agrid, 256, 0, ctx->stream>>>(A, n, (int)n, d_amax);
@@ -1246,10 +1273,14 @@ static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* B
 
 // T phenotypes (each with its own rotation R_t, residual y~_t and h0_rss_t) in one launch.  Device outputs are
 // [T][snp_count]; any may be NULL.
+//
+// A_given / v_given (T = 1 only): the quadratic form A = R'R (row-major lower triangle valid) and v = R'y~ were formed by
+// the caller -- the multi-GPU path builds A from per-rank row blocks of R and an all-reduce (parallel.py) instead of
+// repeating the n^3 product on every rank; Rs and V are then unused.
 static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const double* V, const double* h0_rss, double n_p, double lbeta,
                        int64_t snp_begin, int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p,
-                       double* d_vp) {
-    const int64_t n = ctx->n, n_out = Rs[0]->rows;
+                       double* d_vp, const MmgMat* A_given = nullptr, const double* v_given = nullptr) {
+    const int64_t n = ctx->n, n_out = A_given ? 1 : Rs[0]->rows;
     MMG_TRY(scan_tc_check_domain(ctx));
     const int S_fixed = scan_tc_fixed_slices();
     const int S_alloc = S_fixed ? S_fixed : QS_AUTO_PLANES;
@@ -1258,7 +1289,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     const int64_t plane = n_padN * ldq;
     MMG_CHECK(ctx, (int64_t)T * S_alloc * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
     DevBuf A, Bq, vec;
-    MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)n * n * sizeof(double)));
+    if (!A_given) MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)n * n * sizeof(double)));
     MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S_alloc * plane));
     // vec: v[T][n_padN] | dg[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | bscale[T] | amax | rho | wave counter
     const int64_t nd = 2 * (int64_t)T * n_padN + (int64_t)T * n_out + 3 * T + 3;
@@ -1274,12 +1305,13 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     unsigned* d_wave = (unsigned*)(d_rho + 1);
     MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)nd * sizeof(double), ctx->stream));
     MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)T * S_alloc * plane, ctx->stream));
-    MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (A_given) MMG_CUDA(ctx, cudaMemcpyAsync(d_v, v_given, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<double> escale((size_t)T), bscale((size_t)T);
     for (int t = 0; t < T; ++t) {
         int E = 0;
-        MMG_TRY(quad_prepare(ctx, Rs[t], d_y + (int64_t)t * n_out, A.as<double>(), d_amax, S_alloc,
+        MMG_TRY(quad_prepare(ctx, A_given ? nullptr : Rs[t], d_y + (int64_t)t * n_out, A_given ? A_given->d : nullptr, A.as<double>(), d_amax, S_alloc,
                              Bq.as<int8_t>() + (int64_t)t * S_alloc * plane, n_padN, ldq, d_v + (int64_t)t * n_padN,
                              d_dg + (int64_t)t * n_padN, &E));
         escale[t] = ldexp(1.0, E);
@@ -1549,6 +1581,45 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
         for (int v = 0; v < nv; ++v)
             for (int64_t s = 0; s < snp_count; ++s) dots[s * nv + v] = tmp[(size_t)v * snp_count + s];
     }
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+// The int8 scan when the caller already holds the quadratic form A = R'R (n x n, row-major lower triangle valid) and
+// v = R'y~: the multi-GPU path forms A from per-rank row blocks of R (mmg_mat_syrk_rows) and one all-reduce instead of
+// repeating the 2 n^3 / 2 flops of the product on every rank (28 ms at n = 10k, more than an 8-way shard of the scan itself).
+int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat Ah, const double* v, double h0_rss, double n_p, int64_t snp_begin,
+                            int64_t snp_count, double* ps, double* f_stats, double* rss, double* var_perc, double* xx) {
+    MmgMat* A = ctx ? get_mat(ctx, Ah) : nullptr;
+    MMG_CHECK(ctx, A && ctx->snps && v, "mmg_emmax_scan_quad_f64: need resident genotypes, A and v");
+    MMG_CHECK(ctx, A->rows == ctx->n && A->cols == ctx->n, "A must be n x n with n = %lld (is %lld x %lld)", (long long)ctx->n,
+              (long long)A->rows, (long long)A->cols);
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+    DevBuf out;      // xx, xy, rss, f, p, var_perc
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)6 * snp_count * sizeof(double)));
+    double* d_xx = out.as<double>();
+    double* d_xy = d_xx + snp_count;
+    double* d_rss = d_xy + snp_count;
+    double* d_f = d_rss + snp_count;
+    double* d_p = d_f + snp_count;
+    double* d_vp = d_p + snp_count;
+    {
+        StageTimer tm(ctx, "scan");
+        MMG_TRY(scan_tc_run(ctx, 1, nullptr, nullptr, &h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp, A, v));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        ctx->last_scan_ms = ms;
+    }
+    StageTimer tm2(ctx, "d2h");
+    const size_t bytes = snp_count * sizeof(double);
+    if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (f_stats) MMG_CUDA(ctx, cudaMemcpyAsync(f_stats, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rss) MMG_CUDA(ctx, cudaMemcpyAsync(rss, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_perc) MMG_CUDA(ctx, cudaMemcpyAsync(var_perc, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xx) MMG_CUDA(ctx, cudaMemcpyAsync(xx, d_xx, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMG_OK;
 }

@@ -33,6 +33,8 @@ Known, deliberate differences from the reference (each covered by a test):
 import time
 import warnings
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -443,7 +445,18 @@ class LinearMixedModel(LinearModel):
         impl = kwargs.get('impl', self.scan_impl)
 
         if not with_betas:
-            out = ctx.emmax_scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
+            from . import parallel
+            int8_scan = impl == 'tcgen05' or (impl in ('auto', None) and os.environ.get('MMG_SCAN_IMPL', 'tcgen05') == 'tcgen05')
+            if int8_scan and parallel.world_size() > 1 and parallel.nccl_backend():
+                # one process per GPU: R'R is formed once across the ranks instead of once per rank (parallel.py)
+                A = parallel.quad_form_sharded(ctx, Rm)
+                yd = DeviceMatrix.from_host(ctx, nf['Yres'].reshape(-1, 1))
+                vd = ctx.gemm(Rm, yd, ta=True)                 # v = R' y~   (x~.y~ = x.v)
+                out = ctx.emmax_scan_quad(A, vd.download().reshape(-1), h0_rss_f, n_p)
+                for d in (A, yd, vd):
+                    d.free()
+            else:
+                out = ctx.emmax_scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
             p_vals, f_stats, rss_list, var_perc = out['ps'], out['f_stats'], out['rss'], out['var_perc']
         else:
             # lstsq([h0_X, x~], Y) (:1323) through its normal equations: the kernel supplies

@@ -6,8 +6,11 @@ step of each stage:
     kinship : every rank forms the integer Gram of its SNP slice -> all_reduce(SUM, int32) of the n x n
               Gram.  Integer addition is exact and order independent, so K is bit-identical for any
               number of ranks.
-    scan    : every rank scans its own slice against the replicated rotation; the per-SNP outputs are
-              all_gathered.  Permutations: all_reduce(MAX) of the per-permutation ratios.
+    scan    : the quadratic form A = R'R of the int8 scan (2 n^3 / 2 FP64 flops, 28 ms at n = 10k -- as long as an
+              8-way shard of the scan itself) is formed cooperatively: every rank multiplies its block of the
+              rows of R (mmg_mat_syrk_rows) and the n x n partial sums are all_reduced (SUM, float64).  Then every
+              rank scans its own SNP slice; the per-SNP outputs are all_gathered.  Permutations: all_reduce(MAX)
+              of the per-permutation ratios.
 
 PyTorch is plumbing here (process group + collectives on device pointers owned by libmixmogam_b200).
 """
@@ -49,6 +52,46 @@ def allreduce_gram(ctx, group=None):
     t = gram_as_tensor(ctx)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     torch.cuda.synchronize(ctx.device)
+
+
+def world_size(group=None):
+    """Number of ranks of the initialised process group (1 without torch.distributed)."""
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return 1
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
+def nccl_backend(group=None):
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_backend(group) == 'nccl'
+
+
+def split_rows(rows, rank, world):
+    """Contiguous block [begin, end) of `rows` rows for `rank`: sizes differ by at most one, blocks cover [0, rows)."""
+    base, extra = divmod(rows, world)
+    b = rank * base + min(rank, extra)
+    return b, b + base + (1 if rank < extra else 0)
+
+
+def quad_form_sharded(ctx, R, group=None):
+    """A = R'R (DeviceMatrix, row-major lower triangle valid) with the n^3 product split over the ranks:
+    rank r forms R[rows_r, :]' R[rows_r, :] and the partial sums are all-reduced over NCCL (SUM, float64)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    b, e = split_rows(R.shape[0], rank, world)
+    A = ctx.syrk_rows(R, b, e - b)
+    ptr, ld = A.device_ptr()
+    n = A.shape[0]
+    t = torch.as_tensor(_DevPtr(ptr, (n, ld), '<f8'), device='cuda:%d' % ctx.device)
+    ctx.sync()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.synchronize(ctx.device)
+    return A
 
 
 def allgather_rows(local, m_total, group=None, device=None):

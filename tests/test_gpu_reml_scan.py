@@ -304,3 +304,36 @@ def test_scan_int8_domain_guard(ctx):
     ro = o.emmax(list(snps), g['y'], g['K'], dtype='double')
     assert neglog10_rel_err(r['ps'], ro['ps']) < 1e-6
     ctx.invalidate_snps()
+
+
+def test_quad_form_row_blocks_and_scan_quad(ctx):
+    """The multi-GPU preparation path on one GPU: R'R summed from row blocks of R (mmg_mat_syrk_rows) equals the one-shot
+    product, and the scan fed with that A and v = R'y (mmg_emmax_scan_quad_f64) equals mmg_emmax_scan_f64."""
+    from mixmogam_b200 import parallel
+    from mixmogam_b200._lib import DeviceMatrix
+    from oracle import reference_py3 as o
+    rng = np.random.default_rng(11)
+    n, m = 700, 5000
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=3)
+    ctx.invalidate_snps()
+    ctx.ensure_snps(snps)
+    R = rng.standard_normal((n - 1, n)) / np.sqrt(n)
+    y = rng.standard_normal(n - 1)
+    Rd = DeviceMatrix.from_host(ctx, R)
+    parts = [parallel.split_rows(n - 1, r, 3) for r in range(3)]
+    assert parts[0][0] == 0 and parts[-1][1] == n - 1 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    A = np.zeros((n, n))
+    for b, e in parts:
+        Ab = ctx.syrk_rows(Rd, b, e - b)
+        A += np.tril(Ab.download())
+        Ab.free()
+    np.testing.assert_allclose(A, np.tril(R.T @ R), rtol=1e-12, atol=1e-14)
+    Ad = DeviceMatrix.from_host(ctx, A)
+    h0 = float(y @ y)
+    ra = ctx.emmax_scan(Rd, y.reshape(1, -1), h0, n - 2, impl='tcgen05')
+    rb = ctx.emmax_scan_quad(Ad, R.T @ y, h0, n - 2)
+    for k in ('ps', 'f_stats', 'rss', 'var_perc', 'xx'):
+        np.testing.assert_allclose(rb[k], ra[k], rtol=1e-9, atol=1e-300)
+    xt = snps.astype(np.float64) @ R.T
+    np.testing.assert_allclose(rb['xx'], np.sum(xt * xt, axis=1), rtol=1e-7)
+    ctx.invalidate_snps()

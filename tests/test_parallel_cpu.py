@@ -74,3 +74,15 @@ def test_sharded_gram_and_gather_gloo(world):
         assert np.array_equal(g.astype(np.int64), ref)                # integer all-reduce: bit-identical for any world size
         assert np.array_equal(full, np.arange(m) * 0.5)
         assert np.array_equal(mx, np.array([world - 1, 10.0, 3.0]))
+
+
+def test_split_rows_covers_and_balances():
+    from mixmogam_b200 import parallel
+    for rows in (1, 7, 9999, 10000):
+        for world in (1, 2, 3, 8):
+            parts = [parallel.split_rows(rows, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == rows
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [e - b for b, e in parts]
+            assert max(sizes) - min(sizes) <= 1
+    assert parallel.world_size() == 1
