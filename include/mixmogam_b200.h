@@ -115,6 +115,12 @@ int mmg_snps_row_sums(mmg_ctx* ctx, int64_t* sums_host, int64_t* sumsq_host);
  *   diploid (kinship.py:33-41): G += T T', T = [x>=1 | x>=2] thermometer planes, K-dim = 2*snp_count
  * accumulated into the ctx's int32 n x n Gram (bit-exact, order independent).  reset!=0 zeroes it first. */
 int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset);
+/* The same Gram straight from HOST genotypes (kinship.py:29-32 walks the caller's `snps` chunk by chunk): the rows
+ * stream into the resident block on a copy stream, one 65 536-SNP chunk at a time, and the pack + Gram of chunk c start
+ * as soon as chunk c has landed, so the contraction hides behind the PCIe transfer.  Equivalent to mmg_snps_upload +
+ * mmg_kinship_gram_i8(0, m); the genotypes stay resident for the scan.  snps is borrowed until the call returns. */
+int mmg_kinship_gram_i8_host(mmg_ctx* ctx, int coding, int impl, const int8_t* snps, int64_t m, int64_t n, int64_t ld,
+                             int reset);
 /* device pointer of the int32 Gram (n x n, row stride ld elements) for an NCCL all-reduce between ranks */
 int mmg_kinship_gram_ptr(mmg_ctx* ctx, void** dptr, int64_t* n, int64_t* ld);
 int mmg_kinship_gram_download(mmg_ctx* ctx, int32_t* G_host);

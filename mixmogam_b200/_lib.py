@@ -70,6 +70,7 @@ SIGNATURES = {
     'mmg_snps_device_ptr': (C.c_int, [_c_ctx, C.POINTER(_vp), C.POINTER(_i64)]),
     'mmg_snps_row_sums': (C.c_int, [_c_ctx, _vp, _vp]),
     'mmg_kinship_gram_i8': (C.c_int, [_c_ctx, C.c_int, C.c_int, _i64, _i64, C.c_int]),
+    'mmg_kinship_gram_i8_host': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, _i64, _i64, _i64, C.c_int]),
     'mmg_kinship_gram_ptr': (C.c_int, [_c_ctx, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     'mmg_kinship_gram_download': (C.c_int, [_c_ctx, _vp]),
     'mmg_kinship_finalize_f64': (C.c_int, [_c_ctx, C.c_int, _i64, C.c_int, _i64, _dp]),
@@ -294,17 +295,20 @@ class Context(object):
     def invalidate_snps(self):
         self._snps_key = None
 
+    def _array_key(self, snps):
+        a = snps
+        if a.dtype != np.int8:
+            a = _as_int8(a)
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        return a, ('arr', a.ctypes.data, a.shape, self._fingerprint(a))
+
     def ensure_snps(self, snps):
         """Make `snps` (list of m int8 rows or an (m, n) array, SNP-major; kinship.py:21-23) the resident
         genotype block.  Re-uploads unless the same buffer (address, shape, sampled fingerprint) is
         already resident.  Returns (m, n)."""
         if isinstance(snps, np.ndarray) and snps.ndim == 2:
-            a = snps
-            if a.dtype != np.int8:
-                a = _as_int8(a)
-            if not a.flags.c_contiguous:
-                a = np.ascontiguousarray(a)
-            key = ('arr', a.ctypes.data, a.shape, self._fingerprint(a))
+            a, key = self._array_key(snps)
             if key != self._snps_key:
                 self._ck(self.lib.mmg_snps_upload(self.h, _ptr(a), a.shape[0], a.shape[1], a.shape[1]))
                 self._snps_key = key
@@ -420,6 +424,22 @@ class Context(object):
         if snp_count is None:
             snp_count = m - snp_begin
         self._ck(self.lib.mmg_kinship_gram_i8(self.h, coding, impl_id(impl), snp_begin, snp_count, int(bool(reset))))
+
+    def kinship_gram_from(self, snps, coding, impl=IMPL_AUTO):
+        """Integer Gram of all of `snps`, which become the resident genotype block.  A 2-D array that is not resident yet
+        is streamed: its 65 536-SNP chunks are copied on a second stream while the Gram of the chunks that have landed
+        runs (mmg_kinship_gram_i8_host); anything else is uploaded first (ensure_snps).  Returns (m, n)."""
+        if isinstance(snps, np.ndarray) and snps.ndim == 2 and snps.shape[0] > 0:
+            a, key = self._array_key(snps)
+            if key != self._snps_key:
+                self._snps_key = None
+                self._ck(self.lib.mmg_kinship_gram_i8_host(self.h, coding, impl_id(impl), _ptr(a), a.shape[0], a.shape[1],
+                                                           a.shape[1], 1))
+                self._snps_key = key
+                return a.shape
+        shape = self.ensure_snps(snps)
+        self.kinship_gram(coding, impl=impl, reset=True)
+        return shape
 
     def kinship_gram_download(self):
         m, n = self.snps_shape()

@@ -698,7 +698,50 @@ static int ensure_tiles(mmg_ctx* ctx, const std::vector<TcTile>& tiles) {
     return MMG_OK;
 }
 
+// Host genotypes streaming into the resident block while the Gram runs (mmg_kinship_gram_i8_host): the copies go out on
+// their own stream in the Gram's 65 536-SNP chunks, one event per chunk; the pack kernel of chunk c waits for event c only.
+struct GramHostSource {
+    const int8_t* snps = nullptr;      // SNP-major host rows, row stride ld
+    int64_t ld = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> done;     // one per chunk
+    cudaEvent_t t0 = nullptr;
+    int64_t issued = 0;
+    ~GramHostSource() {
+        for (cudaEvent_t e : done) cudaEventDestroy(e);
+        if (t0) cudaEventDestroy(t0);
+        if (stream) {
+            cudaStreamSynchronize(stream);      // the host rows are borrowed for the duration of the call only
+            cudaStreamDestroy(stream);
+        }
+    }
+};
+
+static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset, GramHostSource* src);
+
 int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset) {
+    return gram_run(ctx, coding, impl, snp_begin, snp_count, reset, nullptr);
+}
+
+int mmg_kinship_gram_i8_host(mmg_ctx* ctx, int coding, int impl, const int8_t* snps, int64_t m, int64_t n, int64_t ld, int reset) {
+    MMG_CHECK(ctx, ctx && snps && m > 0 && n > 0 && ld >= n, "mmg_kinship_gram_i8_host: bad argument");
+    MMG_TRY(mmg_snps_reserve(ctx, m, n));
+    ctx->snps_absmax = -1;
+    GramHostSource src;
+    src.snps = snps;
+    src.ld = ld;
+    MMG_CUDA(ctx, cudaStreamCreateWithFlags(&src.stream, cudaStreamNonBlocking));
+    MMG_CUDA(ctx, cudaEventCreate(&src.t0));
+    // the zero fill of the row padding (mmg_snps_reserve, compute stream) must not race with the copies
+    MMG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamWaitEvent(src.stream, ctx->ev0, 0));
+    MMG_CUDA(ctx, cudaEventRecord(src.t0, src.stream));
+    const int rc = gram_run(ctx, coding, impl, 0, m, reset, &src);
+    if (rc == MMG_OK) ctx->snps_absmax = coding == MMG_CODING_DIPLOID ? 2 : 1;   // the pack kernels checked every byte against the coding
+    return rc;
+}
+
+static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset, GramHostSource* src) {
     MMG_CHECK(ctx, ctx && ctx->snps, "mmg_kinship_gram_i8: no resident genotypes");
     MMG_CHECK(ctx, coding == MMG_CODING_BINARY || coding == MMG_CODING_DIPLOID, "unknown coding %d", coding);
     MMG_CHECK(ctx, snp_begin >= 0 && snp_count >= 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
@@ -745,9 +788,27 @@ int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, i
             for (int im = 0; im <= 2 * jn + 1; im += gram_cs) tiles.push_back(TcTile{im * TC_BM, jn * TC_BN, 0, 0, 0, 0, 0, 0});
     }
     double gram_ms = 0.0, pack_s = 0.0;
+    // host source: keep one chunk copy queued ahead of the one the Gram is waiting for (page-locked rows: fully asynchronous
+    // strided DMA at the PCIe rate; pageable rows: the driver stages them and the call blocks, the pipeline still overlaps)
+    auto issue_copy = [&](int64_t s0) -> int {
+        const int64_t cnt = std::min(chunk, snp_count - s0);
+        cudaEvent_t ev;
+        MMG_CUDA(ctx, cudaEventCreate(&ev));
+        src->done.push_back(ev);
+        MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->snps + (snp_begin + s0) * ctx->pitch, ctx->pitch, src->snps + (snp_begin + s0) * src->ld, src->ld,
+                                        ctx->n, cnt, cudaMemcpyHostToDevice, src->stream));
+        MMG_CUDA(ctx, cudaEventRecord(ev, src->stream));
+        src->issued = s0 + cnt;
+        return MMG_OK;
+    };
+    if (src && snp_count > 0) MMG_TRY(issue_copy(0));
     for (int64_t s0 = 0; s0 < snp_count; s0 += chunk) {
         const int64_t cnt = std::min(chunk, snp_count - s0);
         const int64_t kbytes = round_up(cnt, 128) * c;
+        if (src) {
+            if (src->issued < snp_count) MMG_TRY(issue_copy(src->issued));
+            MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, src->done[(size_t)(s0 / chunk)], 0));
+        }
         // ---- pack ----
         cudaEventRecord(ctx->ev0, ctx->stream);
         dim3 pgrid((unsigned)((cnt + 127) / 128), (unsigned)((n + 63) / 64));
@@ -791,6 +852,13 @@ int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, i
     ctx->timers["gram"].seconds += gram_ms * 1e-3;
     ctx->timers["gram"].calls += 1;
     ctx->last_gram_ms = gram_ms;
+    if (src && !src->done.empty()) {
+        float ms = 0.f;
+        cudaEventSynchronize(src->done.back());
+        cudaEventElapsedTime(&ms, src->t0, src->done.back());
+        ctx->timers["h2d"].seconds += ms * 1e-3;           // span of the copy stream: overlaps the pack / gram timers
+        ctx->timers["h2d"].calls += 1;
+    }
     int bad = 0;
     MMG_CUDA(ctx, cudaMemcpy(&bad, ctx->flag_d, sizeof(int), cudaMemcpyDeviceToHost));
     if (bad)
@@ -1105,7 +1173,7 @@ __global__ void snps_absmax_kernel(const uint4* __restrict__ p, int64_t n16, int
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 
-// The int8 scan keeps per-tile sums in int32: |acc| <= 128 PKB |x| 64 and 16 columns x |x| per chain, safe for
+// The int8 scan keeps per-tile sums in int32: |acc| <= 128 PKB |x| 128 and 32 columns x |x| per chain (2^28 at PKB = 8), safe for
 // |x| <= QS_MAX_ABS_GENOTYPE (genotypes are 0/1/2, kinship.py:14-56).  Measured once per resident block.
 constexpr int QS_MAX_ABS_GENOTYPE = 8;
 static int scan_tc_check_domain(mmg_ctx* ctx) {
@@ -1126,11 +1194,12 @@ static int scan_tc_check_domain(mmg_ctx* ctx) {
 
 // ---- int8 tensor-core scan: x'(R'R)x on exact integer slices (scan_tc.cuh) ------------------------------
 // Number of digit planes.  MMG_TC_SLICES = k fixes it; otherwise it is chosen per call from the certified truncation
-// bound  |d(x~.x~)| / x~.x~ <= 0.25 128^-S 2^E ||x||_1^2 / x~.x~ <= MMG_TC_TOL (default 1e-7, i.e. < 2e-7 relative in
+// bound  |d(x~.x~)| / x~.x~ <= (64/255) 256^-S 2^E ||x||_1^2 / x~.x~ <= MMG_TC_TOL (default 1e-7, i.e. < 2e-7 relative in
 // -log10 p for r^2 <= 0.5): a pilot launch over the first SNPs measures max_s 2^E ||x||_1^2 / x~.x~, the full launch
 // re-measures the bound over every SNP and is repeated with one more plane if a SNP violates it.
-constexpr int QS_AUTO_PLANES = 8;          // planes cut in auto mode (bound <= 0.25 128^-8 ... ~ 3e-18 2^E ||x||_1^2)
-constexpr int QS_PILOT_PLANES = 3;
+constexpr int QS_AUTO_PLANES = 6;          // planes cut in auto mode: 48 bits of B (bound <= (64/255) 256^-6 ~ 9e-16 2^E ||x||_1^2)
+constexpr int QS_PILOT_PLANES = 2;
+constexpr double QS_PILOT_HEADROOM = 3.0;  // for the rows the pilot did not see; the full launch re-checks every SNP anyway
 constexpr int64_t QS_PILOT_ROWS = 64 * TC_BM;
 
 static int scan_tc_fixed_slices() {
@@ -1168,7 +1237,7 @@ static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const 
     MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (!std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "scan: R'R is not finite (max |a| = %g)", amax);
-    const int E = amax > 0.0 ? ilogb(amax) + 2 : 0;       // |2 a| 2^-E < 1/2 (a diagonal R'R has no off-diagonal digits at all)
+    const int E = digit256_exponent(amax);                // |2 a| 2^-E <= 0.498 (a diagonal R'R has no off-diagonal digits at all)
     dim3 sgrid((unsigned)((n + 255) / 256), (unsigned)n);
     quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A, n, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq, d_dg);
     MMG_TRY(launch_check(ctx, "quad_slice_kernel"));
@@ -1321,7 +1390,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     QuadEpi::Params ep{};
     ep.snps = ctx->snps;
     ep.pitch = ctx->pitch;
-    for (int k = 0; k < QS_MAX_SLICES; ++k) ep.w[k] = ldexp(1.0, -7 * (k + 1));
+    for (int k = 0; k < QS_MAX_SLICES; ++k) ep.w[k] = ldexp(1.0, -8 * (k + 1));
     ep.escale = d_es;
     ep.v = d_v;
     ep.dg = d_dg;
@@ -1332,9 +1401,9 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     ep.n_p = n_p;
     ep.lbeta = lbeta;
 
-    // bound scale for S planes: 0.25 128^-S 2^E_t
+    // bound scale for S planes: |remainder| <= 128/255 per entry of B, sum_{i<j} |x_i||x_j| <= ||x||_1^2 / 2
     auto set_bscale = [&](int S) -> int {
-        for (int t = 0; t < T; ++t) bscale[t] = 0.25 * ldexp(1.0, -7 * S) * escale[t];
+        for (int t = 0; t < T; ++t) bscale[t] = 0.5 * DIGIT256_REM * ldexp(1.0, -8 * S) * escale[t];
         MMG_CUDA(ctx, cudaMemcpyAsync(d_bs, bscale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         MMG_CUDA(ctx, cudaMemsetAsync(d_rho, 0, sizeof(unsigned long long), ctx->stream));
         return MMG_OK;
@@ -1345,9 +1414,9 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         return MMG_OK;
     };
 
-    int S = S_fixed ? S_fixed : 7;
+    int S = S_fixed ? S_fixed : S_alloc;                        // short scans: no pilot, every plane that was cut
     if (!S_fixed && snp_count >= 4 * QS_PILOT_ROWS) {
-        // pilot: bound of the first rows with few planes; the bound scales exactly by 128 per plane
+        // pilot: bound of the first rows with few planes; the bound scales exactly by 256 per plane
         QuadEpi::Params pp = ep;
         pp.xx = pp.xy = pp.rss = pp.f = pp.p = pp.var_perc = nullptr;
         MMG_TRY(set_bscale(QS_PILOT_PLANES));
@@ -1355,8 +1424,8 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         double rho = 0.0;
         MMG_TRY(read_rho(&rho));
         S = QS_PILOT_PLANES;
-        while (S < S_alloc && rho * 4.0 /* head-room for the rows the pilot did not see */ > tol) {
-            rho /= 128.0;
+        while (S < S_alloc && rho * QS_PILOT_HEADROOM > tol) {
+            rho /= 256.0;
             ++S;
         }
     }

@@ -1,6 +1,6 @@
 // Stage 3, int8 tensor-core scan, genotype-stationary schedule.
 //
-// Same arithmetic as QuadEpi in scan_tc.cuh (x~.x~ = x'(R'R)x on exact base-128 digit planes of the lower-triangular
+// Same arithmetic as QuadEpi in scan_tc.cuh (x~.x~ = x'(R'R)x on exact base-256 digit planes of the lower-triangular
 // B = c o R'R 2^-E, x~.y~ = x.(R'y~), then RSS / F / p, linear_models.py:1315-1349), different data movement.
 //
 // The table-driven kernel re-reads the 128-SNP genotype block (128 x n bytes = 1.3 MB at n = 10k) from L2 once per
@@ -109,7 +109,7 @@ template <int CS, int PKB, int STAGES, bool PAIR, int BN>
 __global__ void __launch_bounds__(QP_THREADS, 1)
 scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const QuadShape sh,
                  uint64_t policy_a, uint64_t policy_b, const QuadEpi::Params ep) {
-    static_assert(PKB <= 12, "per-tile integer sums: |acc| <= 128 PKB |x| 64 must leave room for 16 columns x |x| in int32");
+    static_assert(PKB <= 12, "per-tile integer sums: |acc| <= 128 PKB |x| 128 (|x| <= 8) must leave room for 32 columns x |x| in int32");
     static_assert(!PAIR || CS == 2, "a CTA pair is a cluster of 2");
     static_assert(BN == 256 || BN == 128, "column tile");
     static_assert(PKB % (BN / TC_BK) == 0, "panel = whole column tiles");
@@ -470,7 +470,8 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     s3 += (int)vb[j + 3] * (int)(int8_t)(w >> 24);
                                 }
                             }
-                            // |s_k| <= 32 columns x 2^17 (|acc| <= 1024 K x 2 x 64) x |x| <= 2^23 |x|: exact in int32 for |x| <= 127
+                            // |s_k| <= 32 columns x |acc| x |x|, |acc| <= 128 PKB K x |x| x 128 (base-256 digits): 2^5 2^20 2^3 = 2^28 at PKB = 8, |x| <= 8
+                            // (QS_MAX_ABS_GENOTYPE, enforced on the host): exact in int32
                             const double qt = (double)s0 + (double)s1 + ((double)s2 + (double)s3);
                             tc_fence_before();
                             __syncwarp();

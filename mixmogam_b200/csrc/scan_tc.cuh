@@ -3,11 +3,11 @@
 // The left operand of the EMMAX rotation (linear_models.py:1317-1318) is an exact small-integer genotype
 // vector, so only the FP64 matrix has to be split.  With A = R'R (symmetric, FP64):
 //     x'Ax = sum_j A_jj x_j^2  +  sum_j x_j * sum_{i<j} 2 A_ji x_i
-// The diagonal term stays in FP64 (epilogue).  B[j][i] = 2 A_ji * 2^-E (i < j, |B| < 1/2) is cut into S signed
-// base-128 digits b_k in [-64,64]:
-//     B = sum_k 128^-(k+1) b_k  (+ error <= 0.5 * 128^-S),
+// The diagonal term stays in FP64 (epilogue).  B[j][i] = 2 A_ji * 2^-E (i < j, |B| <= 0.498) is cut into S signed
+// base-256 digits b_k in [-128,127] (digits.cuh: every value of an int8, 8 bits per plane):
+//     B = sum_k 256^-(k+1) b_k  (+ error <= (128/255) * 256^-S),
 // every partial product x.b_k is an exact int32 (tcgen05.mma kind::i8), and the epilogue folds
-//     q_s += w_k * sum_j acc[s][j] * x[s][j],   w_k = 2^E 128^-(k+1)
+//     q_s += w_k * sum_j acc[s][j] * x[s][j],   w_k = 2^E 256^-(k+1)
 // in FP64.  Because B is lower triangular, N tile jb only needs K in [0, 256(jb+1)): half the MACs of
 // the full rotation.  The same epilogue accumulates x~.y~ = x.(R'y~) and, once a 128-SNP row block has
 // seen every tile of a phenotype, evaluates RSS / F / p (linear_models.py:1345-1349).
@@ -20,12 +20,13 @@
 // of W = R'Ys ([P x n], all permuted phenotypes rotated back), 32 permutations x 8 slices per 256-column
 // tile, and keeps the per-permutation maximum of (x_c.W_p)^2 / (x~_c.x~_c) over SNPs.
 #pragma once
+#include "digits.cuh"
 #include "fdist.cuh"
 #include "tc_gemm.cuh"
 
 namespace mmg {
 
-constexpr int QS_MAX_SLICES = 10;
+constexpr int QS_MAX_SLICES = DIGIT256_MAX_PLANES;
 constexpr int QS_FLAG_XY = 1;        // TcTile.aux1: accumulate x.v on this tile (first slice of a column tile)
 constexpr int QS_FLAG_FIRST = 2;     //              first tile of a phenotype: reset the running sums
 constexpr int QS_FLAG_LAST = 4;      //              last tile of a phenotype: evaluate and store
@@ -36,11 +37,11 @@ struct QuadEpi {
         const int8_t* snps;
         int64_t pitch;
         int64_t row_begin, row_count;
-        double w[QS_MAX_SLICES];     // slice weights 2^(-7(k+1)); the per-phenotype 2^E_t is in escale
+        double w[QS_MAX_SLICES];     // slice weights 2^(-8(k+1)); the per-phenotype 2^E_t is in escale
         const double* escale;        // [T] 2^E_t
         const double* v;             // [T][v_stride] R_t'y~_t (zero padded)
         const double* dg;            // [T][v_stride] diag(R_t'R_t): the diagonal of the quadratic form is kept in FP64
-        const double* bscale;        // [T] 0.25 * 128^-S * 2^E_t: truncation bound of the off-diagonal digits per unit ||x||_1^2
+        const double* bscale;        // [T] (64/255) * 256^-S * 2^E_t: truncation bound of the off-diagonal digits per unit ||x||_1^2
         unsigned long long* rho_max; // max over SNPs of bound / (x~.x~), bits of a non-negative double (certification)
         int64_t v_stride;
         const double* h0_rss;        // [T]
@@ -76,11 +77,13 @@ struct QuadEpi {
         const uint4* xp = reinterpret_cast<const uint4*>(xrow + col0);
         const uint4 x0 = xp[0], x1 = xp[1];
         const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        int s = 0;
+        // the accumulator spans the whole contraction here (|acc| <= n |x| 128): 32 columns x |x| can pass 2^31 at
+        // n = 10k, |x| = 8, so this (non-default) kernel sums in 64 bits; the panel kernel's per-panel sums fit int32
+        long long s = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const int xv = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xffu);
-            s += (int)v[j] * xv;
+            s += (long long)((int)v[j]) * xv;
         }
         q = fma(p.w[t.aux0], (double)s, q);
         if (t.aux1 & QS_FLAG_XY) {
@@ -103,7 +106,7 @@ struct QuadEpi {
     }
     // RSS / F / p of one SNP for phenotype ph (linear_models.py:1329,1345-1349) from
     //   q  = off-diagonal part of x'Ax in units of 2^E (digit planes), qd = sum_j A_jj x_j^2 (FP64), xy = x.(R'y~),
-    //   x1 = ||x||_1 (for the certified truncation bound |dq| <= 0.25 128^-S 2^E ||x||_1^2)
+    //   x1 = ||x||_1 (for the certified truncation bound |dq| <= (64/255) 256^-S 2^E ||x||_1^2)
     static __device__ __forceinline__ void store(const Params& p, int ph, int64_t orow, double q, double xy, double qd, double x1) {
         const int64_t o = (int64_t)ph * p.out_stride + orow;
         const double h0 = p.h0_rss[ph];
@@ -216,13 +219,10 @@ __global__ void quad_slice_kernel(const double* __restrict__ A, int64_t ld, int 
         dg[j] = A[(int64_t)j * ld + j];
         return;
     }
-    double r = A[(int64_t)j * ld + i] * 2.0 * scale;                     // |r| < 0.5, exact scaling
-    for (int k = 0; k < S; ++k) {
-        r *= 128.0;
-        const double d = rint(r);                                        // in [-64, 64]
-        r -= d;                                                          // exact: |r| <= 0.5
-        Bq[((int64_t)k * n_padN + j) * ldq + i] = (int8_t)(int)d;
-    }
+    const double r = A[(int64_t)j * ld + i] * 2.0 * scale;               // |r| <= 0.498, exact scaling
+    int d[DIGIT256_MAX_PLANES];
+    digit256_split(r, S, d);                                             // base 256, exact (digits.cuh)
+    for (int k = 0; k < S; ++k) Bq[((int64_t)k * n_padN + j) * ldq + i] = (int8_t)d[k];
 }
 
 // max |W| over a row-major [rows x cols] matrix -> bits of a non-negative double

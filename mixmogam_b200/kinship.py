@@ -34,8 +34,7 @@ def calc_ibs_kinship_device(snps, snps_data_format='binary', scaled=True, impl='
     """As calc_ibs_kinship but leaves K on the device (returns a DeviceMatrix)."""
     ctx = ctx or _lib.get_context()
     coding = _coding(snps_data_format)
-    m, n = ctx.ensure_snps(snps)
-    ctx.kinship_gram(coding, impl=impl, reset=True)
+    m, n = ctx.kinship_gram_from(snps, coding, impl=impl)      # host genotypes stream in underneath the Gram
     K, _ = ctx.kinship_finalize(coding, m, scaled)
     return K
 
@@ -66,8 +65,11 @@ def partial_ibs_gram(snps, snps_data_format='binary', impl='auto', ctx=None, res
     """Multi-GPU building block: integer Gram of this rank's SNP slice, left resident for an int32
     all-reduce (see mixmogam_b200.parallel).  Returns (device_ptr, n, ld)."""
     ctx = ctx or _lib.get_context()
-    ctx.ensure_snps(snps)
-    ctx.kinship_gram(_coding(snps_data_format), impl=impl, reset=reset)
+    if reset:
+        ctx.kinship_gram_from(snps, _coding(snps_data_format), impl=impl)
+    else:
+        ctx.ensure_snps(snps)
+        ctx.kinship_gram(_coding(snps_data_format), impl=impl, reset=False)
     return ctx.kinship_gram_ptr()
 
 

@@ -2,11 +2,13 @@
 // check them against the golden vectors without a GPU.  Reads binary doubles from stdin:
 //   mode "fsf":  count, then count x (f, dfn, dfd)                    -> count x sf
 //   mode "reml": p, g, esp, eig_vals[p], sq_etas[p], deltas[g]         -> delta, ll, flags, lls[g], dlls[g]
+//   mode "digits": count, S, then count x amax-scaled value a          -> per value: E, S digits, carry out  (digits.cuh)
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <vector>
 
+#include "digits.cuh"
 #include "fdist.cuh"
 #include "reml_logic.cuh"
 
@@ -51,6 +53,22 @@ int main(int argc, char** argv) {
             const double f = rd(), dfn = rd(), dfd = rd();
             const double lb = (double)(lgammal(0.5L * dfd) + lgammal(0.5L * dfn) - lgammal(0.5L * (dfd + dfn)));
             wr(mmg::f_sf(f, dfn, dfd, lb));
+        }
+        return 0;
+    }
+    if (!strcmp(argv[1], "digits")) {
+        // every value is treated as its own amax: E from digit256_exponent, r = a 2^-E, then S digits
+        const long n = (long)rd();
+        const int S = (int)rd();
+        for (long i = 0; i < n; ++i) {
+            const double a = rd();
+            const int E = mmg::digit256_exponent(fabs(a));
+            const double r = ldexp(a, -E);
+            int d[mmg::DIGIT256_MAX_PLANES];
+            const long long carry = mmg::digit256_split(r, S, d);
+            wr((double)E);
+            for (int k = 0; k < S; ++k) wr((double)d[k]);
+            wr((double)carry);
         }
         return 0;
     }

@@ -51,6 +51,47 @@ def test_gram_chunk_boundary_and_accumulate(ctx, impl):
     assert np.array_equal(ctx.kinship_gram_download(), G1)
 
 
+@pytest.mark.parametrize('pinned', [False, True])
+@pytest.mark.parametrize('coding,m,n', [(1, 140001, 130), (0, 65536, 77), (1, 300, 200), (0, 196608 + 5, 40)])
+def test_gram_streamed_from_host_bit_exact(ctx, coding, m, n, pinned):
+    """mmg_kinship_gram_i8_host: the genotypes stream into the resident block chunk by chunk while the Gram of the chunks
+    that have landed runs; same integer Gram as upload-then-Gram, from pageable and from page-locked rows, across the
+    65 536-SNP chunk boundaries (one chunk exactly, three chunks + 5, ragged), and the block is left resident."""
+    from mixmogam_b200 import _lib
+    snps = _rand_snps(m, n, coding, seed=9 * m + n)
+    if pinned:
+        host = _lib.pinned_empty((m, n), np.int8)
+        host[...] = snps
+        snps = host
+    ctx.invalidate_snps()
+    assert ctx.kinship_gram_from(snps, coding) == (m, n)
+    G = ctx.kinship_gram_download()
+    ctx.kinship_gram(coding, reset=True)                                  # the resident copy, Gram again
+    assert np.array_equal(ctx.kinship_gram_download(), G)
+    if m <= 70000:
+        assert np.array_equal(G.astype(np.int64), _gram_ref(np.asarray(snps), coding))
+    else:
+        x = np.asarray(snps)                                              # int64 reference in slabs (memory)
+        ref = sum(_gram_ref(x[i:i + 50000], coding) for i in range(0, m, 50000))
+        assert np.array_equal(G.astype(np.int64), ref)
+    sums = ctx.snps_row_sums()
+    assert np.array_equal(sums, np.asarray(snps).astype(np.int64).sum(axis=1))   # every row landed
+    assert ctx.kinship_gram_from(snps, coding) == (m, n)                 # already resident: plain Gram, same result
+    assert np.array_equal(ctx.kinship_gram_download(), G)
+
+
+def test_gram_streamed_rejects_out_of_domain_values(ctx):
+    from mixmogam_b200 import MmgError
+    snps = _rand_snps(70000, 40, 1, seed=2)
+    snps[69999, 39] = 3
+    ctx.invalidate_snps()
+    with pytest.raises(MmgError):
+        ctx.kinship_gram_from(snps, 1)
+    snps[69999, 39] = 1
+    ctx.kinship_gram_from(snps, 1)                                       # a failed call leaves nothing marked resident
+    assert np.array_equal(ctx.kinship_gram_download().astype(np.int64), _gram_ref(snps, 1))
+
+
 def test_gram_rejects_out_of_domain_values(ctx):
     from mixmogam_b200 import MmgError
     snps = _rand_snps(300, 40, 1, seed=1)

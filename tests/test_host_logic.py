@@ -125,3 +125,30 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert 'oracle' not in src.replace('no oracle', ''), '%s references the oracle' % f
                 assert 'import scipy' not in src and 'from scipy' not in src, '%s routes through scipy' % f
+
+
+def test_base256_digit_expansion(built):
+    """digits.cuh (the digit planes of the int8 scan): every digit fits an int8, no carry leaves the top digit, the
+    expansion equals rint(r 256^S) EXACTLY (integer arithmetic), and every prefix of S' planes is within
+    (128/255) 256^-S' of r -- the truncation bound the scan certifies -- including the edges of the accepted
+    interval and the sliver (0.498, 1/2) that needs one more exponent bit."""
+    from fractions import Fraction
+    rng = np.random.default_rng(0)
+    edge = [127.0 / 255.0, -127.0 / 255.0, np.nextafter(0.5, 0), -np.nextafter(0.5, 0), 0.25, -0.25, 0.499, 0.4981, 0.498,
+            np.nextafter(0.498, 1), -0.498, 1.0, 3.0, -7.5, 1e-300, -1e300, 0.0, 2.0 ** -40, 127.5 / 256, -128.5 / 256, 255.0 / 512]
+    vals = np.concatenate([edge, rng.standard_normal(3000) * 10.0 ** rng.uniform(-6, 6, 3000),
+                           0.498 * 2.0 ** rng.integers(-5, 5, 500) * (1 - rng.uniform(0, 1e-6, 500))])
+    bound = Fraction(128, 255)
+    for S in (1, 4, 6, 7):
+        out = _run(built, 'digits', np.concatenate([[vals.size, S], vals])).reshape(vals.size, S + 2)
+        for a, row in zip(vals, out):
+            E, digs, carry = int(row[0]), [int(d) for d in row[1:1 + S]], row[1 + S]
+            assert carry == 0 and min(digs) >= -128 and max(digs) <= 127
+            r = Fraction(float(a)) / Fraction(2) ** E
+            if a != 0.0:
+                assert Fraction(249, 1000) <= abs(r) <= Fraction(498, 1000)            # in range, no wasted head-room
+            N = sum(d * 256 ** (S - 1 - k) for k, d in enumerate(digs))
+            assert abs(r * 256 ** S - N) <= Fraction(1, 2)                              # N = rint(r 256^S)
+            for Sp in range(0, S + 1):
+                part = sum(Fraction(d, 256 ** (k + 1)) for k, d in enumerate(digs[:Sp]))
+                assert abs(r - part) <= bound / 256 ** Sp
