@@ -117,6 +117,30 @@ static uint64_t env_policy(const char* var, uint64_t dflt) {
     return dflt;
 }
 
+// clusters of CS CTAs of tc_gemm_i8_kernel<Epi, CS> that can be co-resident: the persistent grid of launch_tc_gemm
+template <class Epi, int CS>
+static int tc_gemm_max_clusters(mmg_ctx* ctx) {
+    int max_clusters = ctx->sm_count / CS;
+    if (CS > 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count / CS * CS));
+        int q = 0;
+        if (cudaOccupancyMaxActiveClusters(&q, tc_gemm_i8_kernel<Epi, CS>, &cfg) == cudaSuccess && q > 0) max_clusters = std::min(max_clusters, q);
+        else cudaGetLastError();
+    }
+    return std::max(1, max_clusters);
+}
+
 // Launch the tcgen05 GEMM with a cluster of CS CTAs.  The persistent grid is the number of clusters that can be
 // co-resident (cudaOccupancyMaxActiveClusters; clusters of 4 do not tile every GPC) times CS.
 template <class Epi, int CS>
@@ -136,13 +160,7 @@ static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    int max_clusters = ctx->sm_count / CS;
-    if (CS > 1) {
-        cfg.gridDim = dim3((unsigned)(ctx->sm_count / CS * CS));
-        int q = 0;
-        if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0) max_clusters = std::min(max_clusters, q);
-        else cudaGetLastError();
-    }
+    const int max_clusters = tc_gemm_max_clusters<Epi, CS>(ctx);
     const int cgroups = (num_groups + CS - 1) / CS;
     const int clusters = std::max(1, std::min(cgroups, max_clusters));
     cfg.gridDim = dim3((unsigned)(clusters * CS));
@@ -781,12 +799,40 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     // With a cluster of 2, one entry covers the row-tile pair (im, im+1) of a column tile (2 jn + 2 is even).
     int gram_cs = env_int("MMG_GRAM_CLUSTER", 2);
     if (gram_cs != 1) gram_cs = 2;
-    std::vector<TcTile> tiles;
+    std::vector<TcTile> tiles, table;
+    int gram_clusters = 1;
     if (impl == MMG_IMPL_TCGEN05) {
         const int tiles_n = (n + TC_BN - 1) / TC_BN;
         for (int jn = 0; jn < tiles_n; ++jn)
             for (int im = 0; im <= 2 * jn + 1; im += gram_cs) tiles.push_back(TcTile{im * TC_BM, jn * TC_BN, 0, 0, 0, 0, 0, 0});
+        gram_clusters = gram_cs == 2 ? tc_gemm_max_clusters<GramEpi, 2>(ctx) : tc_gemm_max_clusters<GramEpi, 1>(ctx);
     }
+    // Tile table of one chunk.  Entry e runs on cluster e % W (W co-resident clusters), every tile costs the same, so
+    // nt = q W + r tiles take q + 1 waves with only r clusters busy in the last one (n = 10k: 820 = 11 x 74 + 6, an 8 %
+    // tail).  The r tail tiles are cut along K into floor(W / r) slices each, one slice per cluster, accumulated with
+    // integer atomics (exact): the tail shrinks to 1 / floor(W / r) of a wave.  MMG_GRAM_SPLITK=0 turns it off.
+    const bool split_tail = env_int("MMG_GRAM_SPLITK", 1) != 0;
+    auto build_table = [&](int KB) {
+        table.clear();
+        const int nt = (int)tiles.size(), W = gram_clusters;
+        const int r = nt % W, full = nt - r;
+        const int splits = (split_tail && nt > W && r > 0) ? std::min(W / r, KB / 8) : 1;
+        for (int e = 0; e < (splits > 1 ? full : nt); ++e) {
+            TcTile t = tiles[(size_t)e];
+            t.kb0 = 0;
+            t.kb1 = KB;
+            table.push_back(t);
+        }
+        if (splits > 1)
+            for (int sl = 0; sl < splits; ++sl)
+                for (int e = full; e < nt; ++e) {
+                    TcTile t = tiles[(size_t)e];
+                    t.kb0 = (int)((int64_t)KB * sl / splits);
+                    t.kb1 = (int)((int64_t)KB * (sl + 1) / splits);
+                    t.aux0 = 1;                                   // GramEpi: atomic accumulate
+                    table.push_back(t);
+                }
+    };
     double gram_ms = 0.0, pack_s = 0.0;
     // host source: keep one chunk copy queued ahead of the one the Gram is waiting for (page-locked rows: fully asynchronous
     // strided DMA at the PCIe rate; pageable rows: the driver stages them and the call blocks, the pipeline still overlaps)
@@ -825,10 +871,10 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
             CUtensorMap tmA, tmB;
             MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->pack, kbytes, n, p_pitch, TC_BM));
             MMG_TRY(make_tmap_u8(ctx, &tmB, ctx->pack, kbytes, n, p_pitch, TC_BN / gram_cs));
-            for (auto& t : tiles) { t.kb0 = 0; t.kb1 = (int)(kbytes / TC_BK); }
-            MMG_TRY(ensure_tiles(ctx, tiles));
+            build_table((int)(kbytes / TC_BK));
+            MMG_TRY(ensure_tiles(ctx, table));
             GramEpi::Params ep{ctx->G, g_pad, accumulate};
-            const int ngroups = (int)tiles.size() * gram_cs;
+            const int ngroups = (int)table.size() * gram_cs;
             if (gram_cs == 2)
                 MMG_TRY((launch_tc_gemm<GramEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep, "tc_gemm_i8_kernel<GramEpi,2>")));
             else

@@ -222,7 +222,13 @@ struct GramEpi {
     __device__ __forceinline__ void tile_end(const Params&, const TcTile&, int, int) {}
     __device__ __forceinline__ void chunk(const Params& p, const TcTile& t, int row, int c, const uint32_t (&v)[32]) {
         int4* dst = reinterpret_cast<int4*>(p.G + (int64_t)(t.m0 + row) * p.ld + t.n0 + c * 32);
-        if (p.accumulate) {
+        if (t.aux0) {
+            // split-K slice of a tail tile (several clusters share one output tile): integer atomics are exact and order
+            // independent; G was zeroed at reset, so the first chunk needs no special case
+            int* d = reinterpret_cast<int*>(dst);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(d + j, (int)v[j]);
+        } else if (p.accumulate) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 int4 o = dst[j];

@@ -92,6 +92,34 @@ def test_gram_streamed_rejects_out_of_domain_values(ctx):
     assert np.array_equal(ctx.kinship_gram_download().astype(np.int64), _gram_ref(snps, 1))
 
 
+@pytest.mark.parametrize('coding', [0, 1])
+def test_gram_split_k_tail_bit_exact(ctx, monkeypatch, coding):
+    """n large enough that the tile count passes the number of co-resident clusters (n = 3112: 13 column tiles, 91 cluster
+    tiles > 74): the tiles of the last partial wave are cut along K and accumulated with integer atomics.  Same bits as
+    the unsplit schedule, the SIMT Gram and an exact FP64 BLAS reference (all sums < 2^53); two chunks, accumulate."""
+    n, m = 3112, 66000
+    snps = _rand_snps(m, n, coding, seed=31 + coding)
+    ctx.invalidate_snps()
+    ctx.ensure_snps(snps)
+    ctx.kinship_gram(coding, impl='tcgen05')
+    G = ctx.kinship_gram_download()
+    monkeypatch.setenv('MMG_GRAM_SPLITK', '0')
+    ctx.kinship_gram(coding, impl='tcgen05')
+    assert np.array_equal(ctx.kinship_gram_download(), G)
+    monkeypatch.delenv('MMG_GRAM_SPLITK')
+    x = snps.astype(np.float64)
+    if coding == 0:
+        s = 2.0 * x - 1.0
+        ref = s.T @ s
+    else:
+        t1, t2 = (x >= 1).astype(np.float64), (x >= 2).astype(np.float64)
+        ref = t1.T @ t1 + t2.T @ t2
+    assert np.array_equal(G.astype(np.float64), ref)
+    ctx.kinship_gram(coding, impl='tcgen05', snp_begin=0, snp_count=1000, reset=True)     # short K: too few K-blocks to split
+    ctx.kinship_gram(coding, impl='tcgen05', snp_begin=1000, snp_count=m - 1000, reset=False)
+    assert np.array_equal(ctx.kinship_gram_download(), G)
+
+
 def test_gram_rejects_out_of_domain_values(ctx):
     from mixmogam_b200 import MmgError
     snps = _rand_snps(300, 40, 1, seed=1)
