@@ -175,9 +175,9 @@ static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMa
 }
 
 // Launch the genotype-stationary scan kernel (scan_quad.cuh): cluster CS, panel of PKB K-blocks, STAGES digit stages.
-template <int CS, int PKB, int STAGES, bool PAIR, int BN>
+template <int CS, int PKB, int STAGES, bool PAIR, int BN, int LDW = 16>
 static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, QuadShape sh, const QuadEpi::Params& ep) {
-    auto kern = scan_quad_kernel<CS, PKB, STAGES, PAIR, BN>;
+    auto kern = scan_quad_kernel<CS, PKB, STAGES, PAIR, BN, LDW>;
     constexpr int smem = QuadSmem<PKB, STAGES, PAIR, BN>::kBytes;
     {   // per device, cheap: set on every launch
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -215,7 +215,13 @@ static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensor
 template <int CS>
 static int launch_scan_quad_cs(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
                                const QuadEpi::Params& ep) {
-    if (panel == 8) return launch_scan_quad<CS, 8, 3, false, 256>(ctx, tmA, tmB, sh, ep);
+    if (panel == 8) {
+        // MMG_SCAN_LD = 16 | 32: columns per tcgen05.ld of the epilogue (clusters of 2 only)
+        if constexpr (CS == 2) {
+            if (env_int("MMG_SCAN_LD", 16) == 32) return launch_scan_quad<CS, 8, 3, false, 256, 32>(ctx, tmA, tmB, sh, ep);
+        }
+        return launch_scan_quad<CS, 8, 3, false, 256>(ctx, tmA, tmB, sh, ep);
+    }
     if (panel == 4) return launch_scan_quad<CS, 4, 5, false, 256>(ctx, tmA, tmB, sh, ep);
     return launch_scan_quad<CS, 6, 4, false, 256>(ctx, tmA, tmB, sh, ep);
 }
@@ -223,7 +229,10 @@ static int launch_scan_quad_cs(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, 
 // CTA-pair form (tcgen05.mma.cta_group::2): half digit tiles of 16 KB per stage
 static int launch_scan_quad_pair(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
                                  const QuadEpi::Params& ep) {
-    if (panel == 8) return launch_scan_quad<2, 8, 6, true, 256>(ctx, tmA, tmB, sh, ep);
+    if (panel == 8) {
+        if (env_int("MMG_SCAN_LD", 16) == 32) return launch_scan_quad<2, 8, 6, true, 256, 32>(ctx, tmA, tmB, sh, ep);
+        return launch_scan_quad<2, 8, 6, true, 256>(ctx, tmA, tmB, sh, ep);
+    }
     if (panel == 4) return launch_scan_quad<2, 4, 10, true, 256>(ctx, tmA, tmB, sh, ep);
     return launch_scan_quad<2, 6, 8, true, 256>(ctx, tmA, tmB, sh, ep);
 }
@@ -1295,14 +1304,15 @@ static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const 
 static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* Bq, int64_t n_padN, int64_t ldq, int64_t snp_begin,
                           int64_t snp_count, QuadEpi::Params ep, unsigned* d_wave_sync) {
     int cs = env_int("MMG_SCAN_CLUSTER", 2);
-    if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+    if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 2;
     // MMG_SCAN_SCHED = panel (genotype-stationary schedule, scan_quad.cuh) | pair (same, MMA as a CTA pair) |
     //                  pair128 / n128 (128-column tiles, four accumulator stages) | table (tile-table kernel, tc_gemm.cuh)
     const char* sched = getenv("MMG_SCAN_SCHED");
-    if (!sched) sched = "panel";
+    if (!sched) sched = "pair";         // the CTA-pair MMA halves the L2 -> SM digit traffic per SM: 138 vs 145 ms per 1M SNPs at n = 10k
     const bool pair128 = strcmp(sched, "pair128") == 0, n128 = strcmp(sched, "n128") == 0;
     const bool pair = strcmp(sched, "pair") == 0 || pair128;
     if (pair || n128) cs = 2;
+    if (cs == 8 && strcmp(sched, "table") == 0) cs = 4;      // the tile-table kernel is instantiated for clusters of 1, 2, 4
     const int bn = (pair128 || n128) ? 128 : TC_BN;
     const int tiles_n = (int)(n_padN / bn), kb_total = (int)(ldq / TC_BK);
     ep.row_begin = snp_begin;
@@ -1322,6 +1332,7 @@ static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* B
         sh.kb_total = kb_total;
         sh.n_padN = (int)n_padN;
         sh.prefetch = std::max(0, env_int("MMG_SCAN_PREFETCH", 8));
+        sh.pf_share = std::max(1, env_int("MMG_SCAN_PF_SHARE", 1));
         if (env_int("MMG_SCAN_WAVE_SYNC", 1) && d_wave_sync) {
             MMG_CUDA(ctx, cudaMemsetAsync(d_wave_sync, 0, sizeof(unsigned), ctx->stream));
             sh.wave_sync = d_wave_sync;
@@ -1339,6 +1350,7 @@ static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* B
         if (pair128) MMG_TRY(launch_scan_quad_pair128(ctx, panel, tmA, tmB, sh, ep));
         else if (n128) MMG_TRY(launch_scan_quad_n128(ctx, panel, tmA, tmB, sh, ep));
         else if (pair) MMG_TRY(launch_scan_quad_pair(ctx, panel, tmA, tmB, sh, ep));
+        else if (cs == 8) MMG_TRY(launch_scan_quad_cs<8>(ctx, panel, tmA, tmB, sh, ep));
         else if (cs == 4) MMG_TRY(launch_scan_quad_cs<4>(ctx, panel, tmA, tmB, sh, ep));
         else if (cs == 2) MMG_TRY(launch_scan_quad_cs<2>(ctx, panel, tmA, tmB, sh, ep));
         else MMG_TRY(launch_scan_quad_cs<1>(ctx, panel, tmA, tmB, sh, ep));
@@ -1347,10 +1359,10 @@ static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* B
             MMG_CUDA(ctx, cudaMemcpyAsync(h.data(), dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
             MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (FILE* f = fopen(dbg_path, "w")) {
-                fprintf(f, "# cta prod_total prod_wait_empty prod_wait_aempty - mma_total mma_wait_full mma_wait_tempty mma_wait_afull epi_total epi_wait_tfull\n");
+                fprintf(f, "# cta prod_total prod_wait_empty prod_wait_aempty - mma_total mma_wait_full mma_wait_tempty mma_wait_afull epi_total epi_wait_tfull epi_xload epi_fp64 epi_drain\n");
                 for (int c = 0; c < dbg_ctas; ++c) {
                     fprintf(f, "%d", c);
-                    for (int k = 0; k < 11; ++k) fprintf(f, " %lld", h[(size_t)c * 16 + k]);
+                    for (int k = 0; k < 13; ++k) fprintf(f, " %lld", h[(size_t)c * 16 + k]);
                     fprintf(f, "\n");
                 }
                 fclose(f);
@@ -1444,6 +1456,22 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     ep.rho_max = d_rho;
     ep.v_stride = n_padN;
     ep.h0_rss = d_h0;
+    // linear pre-pass: x.v_t, sum_j A_jj x_j^2 and ||x||_1 of every SNP in range, one HBM-rate stream over the genotypes
+    DevBuf pre;
+    MMG_CUDA(ctx, pre.alloc(ctx->stream, (size_t)(2 * T + 1) * snp_count * sizeof(double)));
+    {
+        double* p_xy = pre.as<double>();
+        double* p_qd = p_xy + (int64_t)T * snp_count;
+        double* p_a1 = p_qd + (int64_t)T * snp_count;
+        const int rows_per_block = 8 * PRE_ROWS;
+        snp_prepass_kernel<<<(unsigned)((snp_count + rows_per_block - 1) / rows_per_block), 256, 0, ctx->stream>>>(
+            ctx->snps, ctx->pitch, snp_begin, snp_count, T, d_v, d_dg, n_padN, p_xy, p_qd, p_a1, snp_count);
+        MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
+        ep.pre_xy = p_xy;
+        ep.pre_qd = p_qd;
+        ep.pre_a1 = p_a1;
+        ep.pre_stride = snp_count;
+    }
     ep.n_p = n_p;
     ep.lbeta = lbeta;
 
@@ -1974,6 +2002,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bench_imma_kernel(int iters, in
     }
 }
 
+// TMEM read-back rate of the scan's epilogue pattern: WARPS epilogue warps (WARPS / 4 per lane quadrant, each 256 * 4 / WARPS
+// columns of a 128 x 256 int32 accumulator tile), tcgen05.ld.32x32b.x<LDW> double buffered with a multiply-accumulate per
+// element between the waits, while (with_mma) the tensor pipe runs flat out into the other accumulator.  Reports SM cycles per tile.
+template <int WARPS, int LDW>
+__global__ void __launch_bounds__(64 + 32 * WARPS, 1) bench_ldtm_kernel(int tiles, int with_mma, long long* out, unsigned* sink) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int stop_flag;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (TC_A_BYTES + TC_B_BYTES) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = (0x9E3779B9u * (i + 1)) & 0x03030303u;
+    if (threadIdx.x == 0) {
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+        stop_flag = 0;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) { tmem_alloc(&tmem_slot, TC_TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (warp == 1 && lane == 0) {
+        if (with_mma) {
+            constexpr uint32_t idesc = umma_idesc_i8(TC_BM, TC_BN);
+            const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem)), db = umma_desc_kmajor_sw128(smem_u32(smem) + TC_A_BYTES);
+            // keep the pipe busy until the readers are done: batches of 64 K-blocks, then look at the flag
+            for (int it = 0; it < (1 << 22); ++it) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_i8(tmem_base + TC_BN, da + 2 * kk, db + 2 * kk, idesc, (it | kk) ? 1u : 0u);
+                if ((it & 63) == 63 && *(volatile int*)&stop_flag >= WARPS) break;
+            }
+        }
+        umma_commit(&done_bar);
+    }
+    if (warp >= 2) {
+        constexpr int kCols = 256 * 4 / WARPS;
+        const int quad = warp & 3, part = (warp - 2) >> 2;
+        const uint32_t taddr = tmem_base + part * kCols + (static_cast<uint32_t>(quad * 32) << 16);
+        int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        const uint32_t xw = 0x01020100u + lane;
+        const long long t0 = clock64();
+        for (int t = 0; t < tiles; ++t) {
+            uint32_t va[LDW], vb[LDW];
+            if constexpr (LDW == 32) tmem_ld_32x32(taddr, va); else tmem_ld_32x16(taddr, va);
+#pragma unroll
+            for (int c = 0; c < kCols / LDW; c += 2) {
+                tmem_ld_wait_dep(va, s0, s1, s2, s3);
+                if constexpr (LDW == 32) tmem_ld_32x32(taddr + (c + 1) * LDW, vb); else tmem_ld_32x16(taddr + (c + 1) * LDW, vb);
+#pragma unroll
+                for (int j = 0; j < LDW; j += 4) {
+                    const uint32_t w = xw + j;
+                    s0 += (int)va[j + 0] * (int)(int8_t)(w & 0xffu);
+                    s1 += (int)va[j + 1] * (int)(int8_t)((w >> 8) & 0xffu);
+                    s2 += (int)va[j + 2] * (int)(int8_t)((w >> 16) & 0xffu);
+                    s3 += (int)va[j + 3] * (int)(int8_t)(w >> 24);
+                }
+                tmem_ld_wait_dep(vb, s0, s1, s2, s3);
+                if (c + 2 < kCols / LDW) {
+                    if constexpr (LDW == 32) tmem_ld_32x32(taddr + (c + 2) * LDW, va); else tmem_ld_32x16(taddr + (c + 2) * LDW, va);
+                }
+#pragma unroll
+                for (int j = 0; j < LDW; j += 4) {
+                    const uint32_t w = xw + j + 1;
+                    s0 += (int)vb[j + 0] * (int)(int8_t)(w & 0xffu);
+                    s1 += (int)vb[j + 1] * (int)(int8_t)((w >> 8) & 0xffu);
+                    s2 += (int)vb[j + 2] * (int)(int8_t)((w >> 16) & 0xffu);
+                    s3 += (int)vb[j + 3] * (int)(int8_t)(w >> 24);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        if (lane == 0) {
+            atomicAdd(&stop_flag, 1);
+            if (warp == 2) out[blockIdx.x] = t1 - t0;
+        }
+        if (s0 + s1 + s2 + s3 == 0x12345678) sink[0] = 1;
+    }
+    if (warp == 1 || warp == 0) {
+        if (lane == 0) mbar_wait(&done_bar, 0);
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+template <int WARPS, int LDW>
+static int run_bench_ldtm(mmg_ctx* ctx, int with_mma, double* value) {
+    const int tiles = 2000, smem = TC_A_BYTES + TC_B_BYTES + 1024, grid = ctx->sm_count;
+    auto kern = bench_ldtm_kernel<WARPS, LDW>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    MMG_CUDA(ctx, cudaMemsetAsync(ctx->scratch, 0, (size_t)(grid + 2) * sizeof(long long), ctx->stream));
+    long long* out = (long long*)ctx->scratch;
+    kern<<<grid, 64 + 32 * WARPS, smem, ctx->stream>>>(tiles, with_mma, out, (unsigned*)(out + grid));
+    ctx->launches += 1;
+    MMG_TRY(launch_check(ctx, "bench_ldtm_kernel"));
+    std::vector<long long> h((size_t)grid);
+    MMG_CUDA(ctx, cudaMemcpyAsync(h.data(), out, (size_t)grid * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    for (long long v : h) sum += (double)v;
+    *value = sum / grid / tiles;
+    return MMG_OK;
+}
+
 extern "C" {
 
 int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
@@ -2012,6 +2151,18 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
         }
         *value = 2.0 * bytes / (ms * 1e-3) / 1e9;
         return MMG_OK;
+    }
+    if (!strncmp(which, "ldtm", 4)) {
+        // "ldtm_w<4|8|16>_x<16|32>[_mma]": SM cycles per 128 x 256 int32 tile read back by the epilogue pattern
+        const int w = strstr(which, "_w16") ? 16 : strstr(which, "_w8") ? 8 : 4;
+        const int x = strstr(which, "_x32") ? 32 : 16;
+        const int mma = strstr(which, "_mma") ? 1 : 0;
+        if (w == 4 && x == 16) return run_bench_ldtm<4, 16>(ctx, mma, value);
+        if (w == 4 && x == 32) return run_bench_ldtm<4, 32>(ctx, mma, value);
+        if (w == 8 && x == 16) return run_bench_ldtm<8, 16>(ctx, mma, value);
+        if (w == 8 && x == 32) return run_bench_ldtm<8, 32>(ctx, mma, value);
+        if (w == 16 && x == 16) return run_bench_ldtm<16, 16>(ctx, mma, value);
+        return run_bench_ldtm<16, 32>(ctx, mma, value);
     }
     if (!strncmp(which, "imma", 4)) {
         // "imma_tcgen05" | "imma_pair" | "imma_tcgen05_ldtm<k>" | "imma_pair_ldtm<k>": TOP/s

@@ -229,6 +229,17 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[16], int& s0, int
                  :
                  : "memory");
 }
+// 32-column form of the pinned wait (x32 loads: half as many waits per tile, twice the arithmetic between them)
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32], int& s0, int& s1, int& s2, int& s3) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]),
+                   "+r"(s0), "+r"(s1), "+r"(s2), "+r"(s3)
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // same, with a data dependency on the loaded registers so that no use of v can be scheduled above the wait
 __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {

@@ -39,6 +39,8 @@ struct QuadShape {
     int kb_total;       // 128-byte K blocks (ldq / 128)
     int n_padN;         // rows per digit plane
     int prefetch;       // L2 prefetch distance in K blocks (0 = off)
+    int pf_share;       // every pf_share-th K block is prefetched by this cluster (all clusters sweep the same digit stream in
+                        // lockstep, so they can split the prefetch stream between them); 1 = every cluster prefetches everything
     long long* dbg;     // nullptr, or [grid x 16] cycle counters of the three roles (MMG_SCAN_DBG_CLOCKS)
     unsigned* wave_sync;  // nullptr, or a zeroed counter: CTAs start each wave of SNP groups together (see below)
 };
@@ -105,7 +107,8 @@ struct QuadIter {
 constexpr int QP_EPI_WARPS = 8;
 constexpr int QP_THREADS = 64 + 32 * QP_EPI_WARPS;       // producer warp, MMA warp, 8 epilogue warps
 
-template <int CS, int PKB, int STAGES, bool PAIR, int BN>
+// LDW = columns per tcgen05.ld of the epilogue (16 or 32), double buffered either way
+template <int CS, int PKB, int STAGES, bool PAIR, int BN, int LDW = 16>
 __global__ void __launch_bounds__(QP_THREADS, 1)
 scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const QuadShape sh,
                  uint64_t policy_a, uint64_t policy_b, const QuadEpi::Params ep) {
@@ -188,6 +191,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             QuadIter<PKB, BN> pf;
             pf.reset(sh);
             for (int d = 0; d < sh.prefetch; ++d) pf.advance(sh);
+            int pf_count = cluster_id % sh.pf_share;    // position in the shared prefetch rota
             unsigned wave_target = 0;
             int wave = 0;
             uint32_t pre = 0;                           // genotype K-blocks of the coming panel that are already requested
@@ -247,7 +251,10 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 const bool last_tile = (jb == sh.tiles_n - 1) && (k == sh.S - 1);
                                 for (int i = 0; i < nkb; ++i) {
                                     if (sh.prefetch) {
-                                        if (elect_one()) tma_prefetch_2d(&tmB, pf.kb() * TC_BK, pf.row(sh) + crank * kBRows);
+                                        if (pf_count == 0) {
+                                            if (elect_one()) tma_prefetch_2d(&tmB, pf.kb() * TC_BK, pf.row(sh) + crank * kBRows);
+                                        }
+                                        if (++pf_count == sh.pf_share) pf_count = 0;
                                         pf.advance(sh);
                                     }
                                     mbar_wait_timed(&empty_bar[stage], phase ^ 1, timed, w_empty);
@@ -369,7 +376,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // two warps per TMEM lane quadrant (a warp may only read lanes 32 (warp % 4) .. +31): each takes 128 of the tile's
         // 256 columns, so every SM sub-partition runs two epilogue warps that hide each other's tcgen05.ld / IMAD latency
         const bool timed = sh.dbg != nullptr;
-        long long w_tfull = 0, w_x = 0;
+        long long w_tfull = 0, w_x = 0, w_fp = 0, w_drain = 0;      // cycles: waiting for accumulators | x register loads | FP64 x.v pass | drain
         const long long t_start = timed ? clock64() : 0;
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;                       // 0: columns 0..127 of a tile, 1: columns 128..255
@@ -395,32 +402,14 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int64_t orow = (int64_t)g * TC_BM + row;
             const int8_t* xrow = (g < sh.num_groups && orow < ep.row_count) ? ep.snps + (ep.row_begin + orow) * ep.pitch : nullptr;
             for (int t = 0; t < sh.T; ++t) {
-                double q = 0.0, xy = 0.0, qd = 0.0;
-                int a1 = 0;
+                double q = 0.0;
                 uint32_t xn[kCols / 4];
                 bool have_next = false;
-                const double* vt = ep.v + (int64_t)t * ep.v_stride;
-                const double* dt = ep.dg + (int64_t)t * ep.v_stride;
                 for (int kbase = 0; kbase < sh.kb_total; kbase += PKB) {
                     for (int jb = kbase / kKbPerTile; jb < sh.tiles_n; ++jb) {
                         const int col0 = jb * BN + half * kCols;
-                        if (kbase == 0 && xrow != nullptr) {    // x.(R'y~): every column tile meets panel 0 exactly once
-                            const uint4* xp = reinterpret_cast<const uint4*>(xrow + col0);
-                            const double* vv = vt + col0;
-                            const double* dd = dt + col0;
-#pragma unroll 1
-                            for (int u = 0; u < kCols / 16; ++u) {
-                                const uint4 w = __ldg(xp + u);
-                                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int xv = (int)(int8_t)((ww[j >> 2] >> (8 * (j & 3))) & 0xffu);
-                                    xy = fma((double)xv, vv[16 * u + j], xy);
-                                    qd = fma((double)(xv * xv), dd[16 * u + j], qd);      // diagonal of x'Ax, FP64
-                                    a1 += abs(xv);
-                                }
-                            }
-                        }
+                        const long long tc0 = timed ? clock64() : 0;
+                        const long long tc1 = timed ? clock64() : 0;
                         // this SNP's genotypes at the warp's 128 columns, reused by the S digit planes; the loads for the
                         // next column tile are issued now and land while this tile's S accumulators are drained
                         uint32_t xr[kCols / 4];
@@ -436,6 +425,11 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             have_next = nk < sh.kb_total;
                             if (have_next) load_x(xrow, nj * BN + half * kCols, xn);
                         }
+                        if (timed) {
+                            const long long tc2 = clock64();
+                            w_fp += tc1 - tc0;
+                            w_x += tc2 - tc1;
+                        }
                         for (int k = 0; k < sh.S; ++k) {
                             // keep the packed bytes opaque per digit plane: otherwise the sign-extended genotypes are
                             // hoisted out of this loop and spill
@@ -443,9 +437,37 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int u = 0; u < kCols / 4; ++u) asm volatile("" : "+r"(xr[u]));
                             mbar_wait_timed(&tfull_bar[acc], acc_phase, timed, w_tfull);
                             tc_fence_after();
+                            const long long td0 = timed ? clock64() : 0;
                             const uint32_t taddr = tmem_base + acc * BN + half * kCols + (static_cast<uint32_t>(quad * 32) << 16);
-                            uint32_t va[16], vb[16];
                             int s0 = 0, s1 = 0, s2 = 0, s3 = 0;                // four chains
+                            if constexpr (LDW == 32) {
+                                uint32_t va[32], vb[32];
+                                tmem_ld_32x32(taddr, va);
+#pragma unroll
+                                for (int c = 0; c < kCols / 32; c += 2) {      // 32-column chunks, loads double buffered
+                                    tmem_ld_wait_dep(va, s0, s1, s2, s3);      // after the arithmetic on the previous chunk
+                                    tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 4) {
+                                        const uint32_t w = xr[8 * c + (j >> 2)];
+                                        s0 += (int)va[j + 0] * (int)(int8_t)(w & 0xffu);
+                                        s1 += (int)va[j + 1] * (int)(int8_t)((w >> 8) & 0xffu);
+                                        s2 += (int)va[j + 2] * (int)(int8_t)((w >> 16) & 0xffu);
+                                        s3 += (int)va[j + 3] * (int)(int8_t)(w >> 24);
+                                    }
+                                    tmem_ld_wait_dep(vb, s0, s1, s2, s3);
+                                    if (c + 2 < kCols / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 4) {
+                                        const uint32_t w = xr[8 * (c + 1) + (j >> 2)];
+                                        s0 += (int)vb[j + 0] * (int)(int8_t)(w & 0xffu);
+                                        s1 += (int)vb[j + 1] * (int)(int8_t)((w >> 8) & 0xffu);
+                                        s2 += (int)vb[j + 2] * (int)(int8_t)((w >> 16) & 0xffu);
+                                        s3 += (int)vb[j + 3] * (int)(int8_t)(w >> 24);
+                                    }
+                                }
+                            } else {
+                            uint32_t va[16], vb[16];
                             tmem_ld_32x16(taddr, va);
 #pragma unroll
                             for (int c = 0; c < kCols / 16; c += 2) {          // 16-column chunks, loads double buffered
@@ -470,6 +492,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     s3 += (int)vb[j + 3] * (int)(int8_t)(w >> 24);
                                 }
                             }
+                            }
                             // |s_k| <= 32 columns x |acc| x |x|, |acc| <= 128 PKB K x |x| x 128 (base-256 digits): 2^5 2^20 2^3 = 2^28 at PKB = 8, |x| <= 8
                             // (QS_MAX_ABS_GENOTYPE, enforced on the host): exact in int32
                             const double qt = (double)s0 + (double)s1 + ((double)s2 + (double)s3);
@@ -480,19 +503,20 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                             if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
                             q = fma(ep.w[k], qt, q);
+                            if (timed) w_drain += clock64() - td0;
                         }
                     }
                 }
-                // fold the two column halves of each SNP, then RSS / F / p by the lower half's thread
-                double part[4] = {q, xy, qd, (double)a1};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (half == 1) xchg[row] = part[u];
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (half == 0) part[u] += xchg[row];
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                // fold the two column halves of each SNP, then RSS / F / p by the lower half's thread; x.v, the FP64
+                // diagonal of the quadratic form and ||x||_1 come from the linear pre-pass (snp_prepass_kernel)
+                if (half == 1) xchg[row] = q;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0) q += xchg[row];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0 && xrow != nullptr) {
+                    const int64_t po = (int64_t)t * ep.pre_stride + orow;
+                    QuadEpi::store(ep, t, orow, q, ep.pre_xy[po], ep.pre_qd[po], ep.pre_a1[orow]);
                 }
-                if (half == 0 && xrow != nullptr) QuadEpi::store(ep, t, orow, part[0], part[1], part[2], part[3]);
             }
         }
         if (timed && warp == 2 && lane == 0) {
@@ -500,6 +524,8 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             d[8] = clock64() - t_start;
             d[9] = w_tfull;
             d[10] = w_x;
+            d[11] = w_fp;
+            d[12] = w_drain;
         }
     }
 

@@ -43,6 +43,10 @@ struct QuadEpi {
         const double* dg;            // [T][v_stride] diag(R_t'R_t): the diagonal of the quadratic form is kept in FP64
         const double* bscale;        // [T] (64/255) * 256^-S * 2^E_t: truncation bound of the off-diagonal digits per unit ||x||_1^2
         unsigned long long* rho_max; // max over SNPs of bound / (x~.x~), bits of a non-negative double (certification)
+        const double* pre_xy;        // [T][pre_stride] x.v_t, [T][pre_stride] sum_j A_jj x_j^2 and [pre_stride] ||x||_1 from
+        const double* pre_qd;        //   snp_prepass_kernel (scan_quad_kernel reads them; the tile-table kernel computes its own)
+        const double* pre_a1;
+        int64_t pre_stride;
         int64_t v_stride;
         const double* h0_rss;        // [T]
         double n_p, lbeta;
@@ -195,6 +199,75 @@ struct PermEpi {
         atomicMax(p.ratio + t.col0 + lane, (unsigned long long)__double_as_longlong(d[0]));
     }
 };
+
+// ---- linear pre-pass of the scan ------------------------------------------------------------------------------
+// Per SNP s and phenotype t:  xy[t][s] = x_s.v_t  (= x~.y~, linear_models.py:1328),  qd[t][s] = sum_j A_t[j][j] x_sj^2  (the
+// FP64 diagonal of the quadratic form),  a1[s] = ||x_s||_1 (for the certified truncation bound).  One warp per SNP, the
+// genotype row read once, coalesced (16 bytes per lane), v_t and diag(A_t) from L1.  int8 -> double without the
+// quarter-rate I2F: the byte is biased to 0..255, placed in the mantissa of 2^52 and the bias removed by one exact DADD.
+// The scan epilogue used to do this inside its accumulator-drain loop (I2F + dependent DFMA chains, 16 k cycles per
+// column tile during which the MMA ran out of accumulators); here it is an HBM-rate stream of its own.
+constexpr int PRE_ROWS = 4;      // SNP rows per warp: v_t / diag(A_t) are fetched from L1 once per 4 rows
+__global__ void __launch_bounds__(256) snp_prepass_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t row_begin, int64_t row_count,
+                                                          int T, const double* __restrict__ v, const double* __restrict__ dg, int64_t v_stride,
+                                                          double* __restrict__ xy, double* __restrict__ qd, double* __restrict__ a1,
+                                                          int64_t out_stride) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PRE_ROWS;
+    if (r0 >= row_count) return;
+    const int nr = (int)min((int64_t)PRE_ROWS, row_count - r0);
+    const int8_t* xrow = snps + (row_begin + r0) * pitch;
+    const double kBias = 4503599627370496.0 + 128.0;               // 2^52 + 128
+    int l1[PRE_ROWS];
+#pragma unroll
+    for (int i = 0; i < PRE_ROWS; ++i) l1[i] = 0;
+    for (int t = 0; t < T; ++t) {
+        const double* vt = v + (int64_t)t * v_stride;
+        const double* dt = dg + (int64_t)t * v_stride;
+        double sxy[PRE_ROWS], sqd[PRE_ROWS];
+#pragma unroll
+        for (int i = 0; i < PRE_ROWS; ++i) sxy[i] = sqd[i] = 0.0;
+        // every load is fully coalesced: lane l takes columns c + 2l, c + 2l + 1 (one double2 of v_t and of diag(A_t), one
+        // 16-bit genotype pair per row); 64 columns per warp step.  pitch is a multiple of 256, v / dg are zero padded past n.
+#pragma unroll 4
+        for (int64_t c = 2 * lane; c < pitch; c += 64) {
+            const double2 vv = __ldg(reinterpret_cast<const double2*>(vt + c));
+            const double2 dd = __ldg(reinterpret_cast<const double2*>(dt + c));
+#pragma unroll
+            for (int i = 0; i < PRE_ROWS; ++i) {
+                const uint32_t g = i < nr ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(xrow + i * pitch + c)) : 0u;
+                if (t == 0) l1[i] = __dp4a((int)__vabsss4(g), 0x01010101, l1[i]);
+                const uint32_t b = g ^ 0x8080u;                      // bytes + 128
+                const double x0 = __hiloint2double(0x43300000, (int)(b & 0xffu)) - kBias;
+                const double x1 = __hiloint2double(0x43300000, (int)(b >> 8)) - kBias;
+                sxy[i] = fma(x0, vv.x, sxy[i]);
+                sqd[i] = fma(x0 * x0, dd.x, sqd[i]);
+                sxy[i] = fma(x1, vv.y, sxy[i]);
+                sqd[i] = fma(x1 * x1, dd.y, sqd[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PRE_ROWS; ++i) {
+            double a = sxy[i], b = sqd[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0 && i < nr) {
+                xy[(int64_t)t * out_stride + r0 + i] = a;
+                qd[(int64_t)t * out_stride + r0 + i] = b;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PRE_ROWS; ++i) {
+        int a = l1[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && i < nr) a1[r0 + i] = (double)a;
+    }
+}
 
 // max |2 A[j][i]| over the strict lower triangle (i < j) of the row-major matrix -> bits of a non-negative double
 __global__ void quad_amax_kernel(const double* __restrict__ A, int64_t ld, int n, unsigned long long* __restrict__ amax_bits) {

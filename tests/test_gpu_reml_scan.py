@@ -257,6 +257,25 @@ def test_scan_schedules_agree(ctx, monkeypatch, sched, panel):
     np.testing.assert_allclose(rb['rss'], ra['rss'], rtol=1e-7)
 
 
+@pytest.mark.parametrize('cs', ['1', '2', '4', '8'])
+def test_scan_cluster_sizes_agree(ctx, monkeypatch, cs):
+    """The single-CTA-MMA form of the genotype-stationary scan with the digit tiles TMA-multicast to clusters of 1 / 2 / 4 / 8 CTAs: same
+    statistics as the FP64 tensor-core path; 313 SNP groups do not divide by 8 (ragged last cluster group)."""
+    from mixmogam_b200 import kinship, linear_models as lm
+    from oracle import reference_py3 as o
+    n, m = 900, 40000 + 13
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=78)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int')
+    y = o.synth_phenotype(snps, K, seed=7)
+    ra = lm.emmax(snps, y, K, scan_impl='dmma')
+    monkeypatch.setenv('MMG_SCAN_SCHED', 'panel')
+    monkeypatch.setenv('MMG_SCAN_CLUSTER', cs)
+    rb = lm.emmax(snps, y, K, scan_impl='tcgen05')
+    assert neglog10_rel_err(ra['ps'], rb['ps']) < 1e-6
+    np.testing.assert_allclose(rb['rss'], ra['rss'], rtol=1e-7)
+
+
 def test_scan_plane_count_is_certified(ctx, monkeypatch):
     """The number of base-256 digit planes is chosen from the certified truncation bound (pilot launch + check over every
     SNP); MMG_TC_SLICES fixes it, MMG_TC_TOL moves it."""
