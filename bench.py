@@ -355,7 +355,8 @@ def main():
         d2h = (n * n * 8 if world == 1 else 0) + 5 * m_loc * 8
         e2e = {'value': m * args.steps / t_e2e_max, 'unit': 'SNP-tests/s', 'h2d_bytes_per_step': int(h2d),
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * t_e2e_max / args.steps,
-               'stage_seconds_per_step': {k: v / args.steps for k, v in e2e_timers.items()}}
+               'stage_seconds_per_step': {k: v / args.steps for k, v in e2e_timers.items()},
+               'h2d_lanes': dict(zip(('chunks_packed_2bit', 'chunks_raw', 'host_pack_gbs'), ctx.last_h2d_info()))}
 
     if rank == 0:
         value = m * args.steps / t_res
@@ -376,8 +377,8 @@ def main():
             bf16 = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops') or 1590.0
             int8_peak = 2.0 * bf16                                       # int8 tcgen05 rate = 2 x bf16 (same pipe, K=32 vs 16)
             # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu capture of this very configuration
-            # (profiles/r01_ncu_full_scan_quad_1m.txt); null for any other shape
-            traffic = 71667460000 + 59310080 if (n, m, world, S) == (10000, 1000000, 1, 4) and not os.environ.get('MMG_SCAN_SCHED') else None
+            # (profiles/r01_ncu_full_scan_quad_1m.txt: CTA-pair schedule, 4 planes); null for any other shape
+            traffic = 67002602000 + 60958720 if (n, m, world, S) == (10000, 1000000, 1, 4) and not os.environ.get('MMG_SCAN_SCHED') else None
             roof = {'bound': 'tensor', 'kernel': 'tc_gemm_i8_kernel<QuadEpi>' if os.environ.get('MMG_SCAN_SCHED') == 'table' else 'scan_quad_kernel', 'achieved': exec_ops / scan_s / 1e12,
                     'peak': int8_peak, 'unit': 'TFLOP/s', 'frac': exec_ops / scan_s / 1e12 / int8_peak, 'traffic': traffic,
                     'algorithmic_bytes': float(m_loc) * n + 8.0 * m_loc, 'int8_issue_rate_measured': imma_peak,

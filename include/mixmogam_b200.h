@@ -121,6 +121,15 @@ int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, i
  * mmg_kinship_gram_i8(0, m); the genotypes stay resident for the scan.  snps is borrowed until the call returns. */
 int mmg_kinship_gram_i8_host(mmg_ctx* ctx, int coding, int impl, const int8_t* snps, int64_t m, int64_t n, int64_t ld,
                              int reset);
+/* Host-side helper of the streamed upload (no GPU involved): packs rows [0, rows) of SNP-major int8 genotype codes 0..3
+ * (row stride ld) to 2 bits each with `threads` host threads -- code j of a row in bits 2 (j % 4) of byte j / 4, row stride
+ * dst_ld >= ceil(n / 4), tail bytes zeroed.  Returns 0, or 1 when a code outside 0..3 was met (dst is then not usable).
+ * mmg_kinship_gram_i8_host sends part of the chunks this way (a quarter of the PCIe bytes) while the DMA engine moves the
+ * others unpacked; MMG_H2D_PACK=0 switches the packed lane off, MMG_HOST_THREADS sets the thread count. */
+int mmg_host_pack2(const int8_t* src, int64_t rows, int64_t n, int64_t ld, uint8_t* dst, int64_t dst_ld, int threads);
+int mmg_host_threads_default(void);
+/* lanes of the most recent mmg_kinship_gram_i8_host: 65 536-SNP chunks sent packed / unpacked, measured host packing rate (GB/s) */
+int mmg_last_h2d_info(mmg_ctx* ctx, int64_t* packed_chunks, int64_t* raw_chunks, double* pack_gbs);
 /* device pointer of the int32 Gram (n x n, row stride ld elements) for an NCCL all-reduce between ranks */
 int mmg_kinship_gram_ptr(mmg_ctx* ctx, void** dptr, int64_t* n, int64_t* ld);
 int mmg_kinship_gram_download(mmg_ctx* ctx, int32_t* G_host);

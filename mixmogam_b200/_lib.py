@@ -71,6 +71,9 @@ SIGNATURES = {
     'mmg_snps_row_sums': (C.c_int, [_c_ctx, _vp, _vp]),
     'mmg_kinship_gram_i8': (C.c_int, [_c_ctx, C.c_int, C.c_int, _i64, _i64, C.c_int]),
     'mmg_kinship_gram_i8_host': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, _i64, _i64, _i64, C.c_int]),
+    'mmg_host_pack2': (C.c_int, [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64, C.c_int]),
+    'mmg_host_threads_default': (C.c_int, []),
+    'mmg_last_h2d_info': (C.c_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64), _dp]),
     'mmg_kinship_gram_ptr': (C.c_int, [_c_ctx, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     'mmg_kinship_gram_download': (C.c_int, [_c_ctx, _vp]),
     'mmg_kinship_finalize_f64': (C.c_int, [_c_ctx, C.c_int, _i64, C.c_int, _i64, _dp]),
@@ -276,6 +279,12 @@ class Context(object):
         k, rho = C.c_int(0), C.c_double(0)
         self._ck(self.lib.mmg_last_scan_info(self.h, C.byref(k), C.byref(rho)))
         return k.value, rho.value
+
+    def last_h2d_info(self):
+        """(chunks sent packed, chunks sent unpacked, host packing rate in GB/s) of the most recent streamed Gram."""
+        p, r, g = _i64(0), _i64(0), C.c_double(0)
+        self._ck(self.lib.mmg_last_h2d_info(self.h, C.byref(p), C.byref(r), C.byref(g)))
+        return p.value, r.value, g.value
 
     def microbench(self, which):
         v = C.c_double(0)

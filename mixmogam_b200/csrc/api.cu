@@ -343,6 +343,10 @@ int mmg_destroy(mmg_ctx* ctx) {
     cudaFree(ctx->tiles_d);
     cudaFree(ctx->flag_d);
     cudaFree(ctx->scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage_host[i]) cudaFreeHost(ctx->stage_host[i]);
+        cudaFree(ctx->stage_dev[i]);
+    }
     if (ctx->cublas) cublasDestroy(ctx->cublas);
     if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
     cudaEventDestroy(ctx->ev0);
@@ -403,6 +407,13 @@ int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms) {
     return MMG_OK;
 }
 
+int mmg_last_h2d_info(mmg_ctx* ctx, int64_t* packed_chunks, int64_t* raw_chunks, double* pack_gbs) {
+    MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    if (packed_chunks) *packed_chunks = ctx->last_h2d_packed;
+    if (raw_chunks) *raw_chunks = ctx->last_h2d_raw;
+    if (pack_gbs) *pack_gbs = ctx->pack_s_per_byte > 0.0 ? 1e-9 / ctx->pack_s_per_byte : 0.0;
+    return MMG_OK;
+}
 int mmg_last_scan_info(mmg_ctx* ctx, int* slices, double* rho) {
     MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
     if (slices) *slices = ctx->last_scan_slices;
@@ -727,22 +738,65 @@ static int ensure_tiles(mmg_ctx* ctx, const std::vector<TcTile>& tiles) {
 
 // Host genotypes streaming into the resident block while the Gram runs (mmg_kinship_gram_i8_host): the copies go out on
 // their own stream in the Gram's 65 536-SNP chunks, one event per chunk; the pack kernel of chunk c waits for event c only.
+//
+// Two lanes feed the chunks.  RAW: one strided DMA of the int8 rows (page-locked source: asynchronous, ~52 GB/s).  PACKED:
+// all host threads squeeze the chunk to 2 bits per genotype (host_pack.cpp; codes 0..3 only), a quarter-size copy follows
+// and unpack2_kernel expands it into the resident block.  Each chunk goes to the lane that is expected to deliver it
+// first (the DMA backlog against the measured pack time), so the PCIe link and the host cores work side by side:
+// 10 GB arrive in ~10 / (52 + pack rate) seconds instead of 10 / 52.  MMG_H2D_PACK=0 keeps everything on the raw lane.
 struct GramHostSource {
     const int8_t* snps = nullptr;      // SNP-major host rows, row stride ld
     int64_t ld = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // raw lane
+    cudaStream_t stream2 = nullptr;    // packed lane (its small copies must not queue behind the raw ones)
     std::vector<cudaEvent_t> done;     // one per chunk
     cudaEvent_t t0 = nullptr;
-    int64_t issued = 0;
+    cudaEvent_t slot_free[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    bool pinned = false;               // source rows are page-locked (raw copies are asynchronous)
+    bool pack_ok = true;               // packed lane available (switched off by MMG_H2D_PACK=0 or a code outside 0..3)
+    int threads = 1;
+    int next_slot = 0;
+    double dma_free_at = 0.0;          // host clock (s) at which the raw lane is expected to have drained
+    int64_t packed_chunks = 0, raw_chunks = 0;
     ~GramHostSource() {
+        for (cudaStream_t st : {stream, stream2})
+            if (st) cudaStreamSynchronize(st);  // the host rows are borrowed for the duration of the call only
         for (cudaEvent_t e : done) cudaEventDestroy(e);
         if (t0) cudaEventDestroy(t0);
-        if (stream) {
-            cudaStreamSynchronize(stream);      // the host rows are borrowed for the duration of the call only
-            cudaStreamDestroy(stream);
-        }
+        for (cudaEvent_t e : slot_free)
+            if (e) cudaEventDestroy(e);
+        for (cudaStream_t st : {stream, stream2})
+            if (st) cudaStreamDestroy(st);
     }
 };
+
+extern "C" int mmg_host_pack2(const int8_t* src, int64_t rows, int64_t n, int64_t ld, uint8_t* dst, int64_t dst_ld, int threads);
+extern "C" int mmg_host_threads_default();
+
+// packed [rows x p_ld] (2 bits per genotype, code j of a row in bits 2 (j % 4) of byte j / 4) -> int8 [rows x pitch];
+// one thread per 32-bit word = 16 genotypes = one 16-byte store
+__global__ void unpack2_kernel(const uint8_t* __restrict__ packed, int64_t p_ld, int8_t* __restrict__ out, int64_t pitch, int64_t rows) {
+    const int64_t wpr = p_ld >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * wpr) return;
+    const int64_t r = idx / wpr, w = idx - r * wpr;
+    if (16 * w >= pitch) return;
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(packed + r * p_ld + 4 * w);
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t b = (v >> (8 * k)) & 0xffu;
+        o[k] = (b & 3u) | (((b >> 2) & 3u) << 8) | (((b >> 4) & 3u) << 16) | ((b >> 6) << 24);
+    }
+    *reinterpret_cast<uint4*>(out + r * pitch + 16 * w) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+static double host_now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset, GramHostSource* src);
 
@@ -758,10 +812,20 @@ int mmg_kinship_gram_i8_host(mmg_ctx* ctx, int coding, int impl, const int8_t* s
     src.snps = snps;
     src.ld = ld;
     MMG_CUDA(ctx, cudaStreamCreateWithFlags(&src.stream, cudaStreamNonBlocking));
+    MMG_CUDA(ctx, cudaStreamCreateWithFlags(&src.stream2, cudaStreamNonBlocking));
     MMG_CUDA(ctx, cudaEventCreate(&src.t0));
+    for (int i = 0; i < 2; ++i) MMG_CUDA(ctx, cudaEventCreateWithFlags(&src.slot_free[i], cudaEventDisableTiming));
+    {
+        cudaPointerAttributes pa{};
+        src.pinned = cudaPointerGetAttributes(&pa, snps) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
+    src.pack_ok = env_int("MMG_H2D_PACK", 1) != 0;
+    src.threads = std::max(1, env_int("MMG_HOST_THREADS", mmg_host_threads_default()));
     // the zero fill of the row padding (mmg_snps_reserve, compute stream) must not race with the copies
     MMG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     MMG_CUDA(ctx, cudaStreamWaitEvent(src.stream, ctx->ev0, 0));
+    MMG_CUDA(ctx, cudaStreamWaitEvent(src.stream2, ctx->ev0, 0));
     MMG_CUDA(ctx, cudaEventRecord(src.t0, src.stream));
     const int rc = gram_run(ctx, coding, impl, 0, m, reset, &src);
     if (rc == MMG_OK) ctx->snps_absmax = coding == MMG_CODING_DIPLOID ? 2 : 1;   // the pack kernels checked every byte against the coding
@@ -845,37 +909,119 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     double gram_ms = 0.0, pack_s = 0.0;
     // host source: keep one chunk copy queued ahead of the one the Gram is waiting for (page-locked rows: fully asynchronous
     // strided DMA at the PCIe rate; pageable rows: the driver stages them and the call blocks, the pipeline still overlaps)
-    auto issue_copy = [&](int64_t s0) -> int {
-        const int64_t cnt = std::min(chunk, snp_count - s0);
-        cudaEvent_t ev;
-        MMG_CUDA(ctx, cudaEventCreate(&ev));
-        src->done.push_back(ev);
+    const int64_t p2_ld = round_up((ctx->n + 3) / 4, 16);            // packed row: 2 bits per genotype
+    const double pcie_rate = 1e9 * std::max(1, env_int("MMG_PCIE_GBS", 50));
+    const int64_t n_chunks = (snp_count + chunk - 1) / chunk;
+    std::vector<char> staged((size_t)n_chunks, 0);
+    if (src) {
+        src->done.resize((size_t)n_chunks, nullptr);
+        for (auto& e : src->done) MMG_CUDA(ctx, cudaEventCreate(&e));
+    }
+    auto chunk_rows = [&](int64_t ci) { return std::min(chunk, snp_count - ci * chunk); };
+    auto raw_seconds = [&](int64_t ci) { return (double)chunk_rows(ci) * (double)ctx->n / pcie_rate; };
+    auto queue_raw = [&](int64_t ci) -> int {
+        const int64_t s0 = ci * chunk, cnt = chunk_rows(ci);
         MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->snps + (snp_begin + s0) * ctx->pitch, ctx->pitch, src->snps + (snp_begin + s0) * src->ld, src->ld,
                                         ctx->n, cnt, cudaMemcpyHostToDevice, src->stream));
-        MMG_CUDA(ctx, cudaEventRecord(ev, src->stream));
-        src->issued = s0 + cnt;
+        MMG_CUDA(ctx, cudaEventRecord(src->done[(size_t)ci], src->stream));
+        src->dma_free_at = std::max(src->dma_free_at, host_now()) + (src->pinned ? raw_seconds(ci) : 0.0);
+        src->raw_chunks += 1;
+        staged[(size_t)ci] = 1;
         return MMG_OK;
     };
-    if (src && snp_count > 0) MMG_TRY(issue_copy(0));
+    // returns MMG_OK with staged[ci] still 0 when the chunk holds a code outside 0..3 (the caller then takes the raw lane)
+    auto queue_packed = [&](int64_t ci) -> int {
+        const int64_t s0 = ci * chunk, cnt = chunk_rows(ci);
+        if (ctx->stage_bytes < chunk * p2_ld) {
+            for (int i = 0; i < 2; ++i) {
+                if (ctx->stage_host[i]) cudaFreeHost(ctx->stage_host[i]);
+                cudaFree(ctx->stage_dev[i]);
+                ctx->stage_host[i] = ctx->stage_dev[i] = nullptr;
+            }
+            ctx->stage_bytes = 0;
+            for (int i = 0; i < 2; ++i) {
+                MMG_CUDA(ctx, cudaHostAlloc((void**)&ctx->stage_host[i], (size_t)(chunk * p2_ld), cudaHostAllocDefault));
+                MMG_CUDA(ctx, cudaMalloc((void**)&ctx->stage_dev[i], (size_t)(chunk * p2_ld)));
+            }
+            ctx->stage_bytes = chunk * p2_ld;
+        }
+        const int sl = src->next_slot;
+        if (src->slot_used[sl]) MMG_CUDA(ctx, cudaEventSynchronize(src->slot_free[sl]));
+        const double t0 = host_now();
+        if (mmg_host_pack2(src->snps + (snp_begin + s0) * src->ld, cnt, ctx->n, src->ld, ctx->stage_host[sl], p2_ld, src->threads) != 0) {
+            src->pack_ok = false;                       // this and all later chunks take the raw lane
+            return MMG_OK;
+        }
+        const double per_byte = (host_now() - t0) / ((double)cnt * (double)ctx->n);
+        ctx->pack_s_per_byte = ctx->pack_s_per_byte > 0.0 ? 0.5 * (ctx->pack_s_per_byte + per_byte) : per_byte;
+        MMG_CUDA(ctx, cudaMemcpyAsync(ctx->stage_dev[sl], ctx->stage_host[sl], (size_t)(cnt * p2_ld), cudaMemcpyHostToDevice, src->stream2));
+        const int64_t words = cnt * (p2_ld >> 2);
+        unpack2_kernel<<<(unsigned)((words + 255) / 256), 256, 0, src->stream2>>>(ctx->stage_dev[sl], p2_ld, ctx->snps + (snp_begin + s0) * ctx->pitch,
+                                                                                ctx->pitch, cnt);
+        ctx->launches += 1;
+        MMG_TRY(launch_check(ctx, "unpack2_kernel"));
+        MMG_CUDA(ctx, cudaEventRecord(src->slot_free[sl], src->stream2));
+        MMG_CUDA(ctx, cudaEventRecord(src->done[(size_t)ci], src->stream2));
+        src->slot_used[sl] = true;
+        src->next_slot = sl ^ 1;
+        src->dma_free_at = std::max(src->dma_free_at, host_now()) + 0.25 * raw_seconds(ci);       // its quarter-size copy shares the link
+        src->packed_chunks += 1;
+        staged[(size_t)ci] = 1;
+        return MMG_OK;
+    };
+    // Stage chunk ci (if a look-ahead has not done so already).  Packed lane when the raw lane would deliver it later:
+    // pageable rows always (a raw copy blocks the host at the pageable rate), page-locked rows when the DMA backlog exceeds the
+    // time the host needs to pack the chunk.  Before the host disappears into a pack, the raw lane is topped up with the
+    // following chunks so that the link stays busy meanwhile.
+    auto issue_copy = [&](int64_t ci) -> int {
+        if (staged[(size_t)ci]) return MMG_OK;
+        const double raw_s = raw_seconds(ci);
+        const double pack_s = ctx->pack_s_per_byte > 0.0 ? ctx->pack_s_per_byte * (double)chunk_rows(ci) * (double)ctx->n : raw_s;
+        const double backlog = std::max(0.0, src->dma_free_at - host_now());
+        if (src->pack_ok && (!src->pinned || backlog + raw_s > pack_s + 0.25 * raw_s)) {
+            if (src->pinned) {
+                double ahead = backlog;
+                for (int64_t cj = ci + 1; cj < n_chunks && ahead < pack_s; ++cj) {
+                    if (staged[(size_t)cj]) continue;
+                    MMG_TRY(queue_raw(cj));
+                    ahead += raw_seconds(cj);
+                }
+            }
+            MMG_TRY(queue_packed(ci));
+        }
+        if (!staged[(size_t)ci]) MMG_TRY(queue_raw(ci));
+        return MMG_OK;
+    };
+    // host source: no host synchronisation inside the chunk loop (the host packs while the GPU works): per-chunk events
+    std::vector<cudaEvent_t> tev;
+    struct TevGuard {
+        std::vector<cudaEvent_t>& v;
+        ~TevGuard() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+    } tev_guard{tev};
     for (int64_t s0 = 0; s0 < snp_count; s0 += chunk) {
         const int64_t cnt = std::min(chunk, snp_count - s0);
         const int64_t kbytes = round_up(cnt, 128) * c;
+        cudaEvent_t e_p0 = ctx->ev0, e_p1 = ctx->ev1, e_g0 = ctx->kev0, e_g1 = ctx->kev1;
         if (src) {
-            if (src->issued < snp_count) MMG_TRY(issue_copy(src->issued));
+            MMG_TRY(issue_copy(s0 / chunk));
             MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, src->done[(size_t)(s0 / chunk)], 0));
+            for (cudaEvent_t* e : {&e_p0, &e_p1, &e_g0, &e_g1}) {
+                MMG_CUDA(ctx, cudaEventCreate(e));
+                tev.push_back(*e);
+            }
         }
         // ---- pack ----
-        cudaEventRecord(ctx->ev0, ctx->stream);
+        cudaEventRecord(e_p0, ctx->stream);
         dim3 pgrid((unsigned)((cnt + 127) / 128), (unsigned)((n + 63) / 64));
         if (coding == MMG_CODING_BINARY)
             pack_kmajor_kernel<0><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
         else
             pack_kmajor_kernel<1><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
         MMG_TRY(launch_check(ctx, "pack_kmajor_kernel"));
-        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventRecord(e_p1, ctx->stream);
         // ---- Gram ----
         const int accumulate = ctx->g_zero ? 0 : 1;
-        cudaEventRecord(ctx->kev0, ctx->stream);
+        cudaEventRecord(e_g0, ctx->stream);
         if (impl == MMG_IMPL_TCGEN05) {
             CUtensorMap tmA, tmB;
             MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->pack, kbytes, n, p_pitch, TC_BM));
@@ -893,14 +1039,25 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
             gram_simt_kernel<<<ggrid, 256, 0, ctx->stream>>>(ctx->pack, p_pitch, n, kbytes, ctx->G, g_pad, accumulate);
             MMG_TRY(launch_check(ctx, "gram_simt_kernel"));
         }
-        cudaEventRecord(ctx->kev1, ctx->stream);
+        cudaEventRecord(e_g1, ctx->stream);
+        ctx->g_zero = false;
+        if (src) continue;                                      // timed after the loop
         MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         pack_s += ms * 1e-3;
         cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
         gram_ms += ms;
-        ctx->g_zero = false;
+    }
+    if (src) {
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i + 3 < tev.size(); i += 4) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+            pack_s += ms * 1e-3;
+            cudaEventElapsedTime(&ms, tev[i + 2], tev[i + 3]);
+            gram_ms += ms;
+        }
     }
     ctx->timers["pack"].seconds += pack_s;
     ctx->timers["pack"].calls += 1;
@@ -908,11 +1065,16 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     ctx->timers["gram"].calls += 1;
     ctx->last_gram_ms = gram_ms;
     if (src && !src->done.empty()) {
-        float ms = 0.f;
-        cudaEventSynchronize(src->done.back());
-        cudaEventElapsedTime(&ms, src->t0, src->done.back());
-        ctx->timers["h2d"].seconds += ms * 1e-3;           // span of the copy stream: overlaps the pack / gram timers
+        // span from the first copy to the arrival of the last chunk (either lane): overlaps the pack / gram timers
+        float ms = 0.f, span = 0.f;
+        for (cudaEvent_t e : src->done) {
+            cudaEventSynchronize(e);
+            if (cudaEventElapsedTime(&ms, src->t0, e) == cudaSuccess) span = std::max(span, ms);
+        }
+        ctx->timers["h2d"].seconds += span * 1e-3;
         ctx->timers["h2d"].calls += 1;
+        ctx->last_h2d_packed = src->packed_chunks;
+        ctx->last_h2d_raw = src->raw_chunks;
     }
     int bad = 0;
     MMG_CUDA(ctx, cudaMemcpy(&bad, ctx->flag_d, sizeof(int), cudaMemcpyDeviceToHost));

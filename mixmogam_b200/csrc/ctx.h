@@ -55,6 +55,14 @@ struct mmg_ctx {
     int64_t tiles_bytes = 0;
     int* flag_d = nullptr;         // device error flag
 
+    // packed (2-bit) host -> device staging of the streamed Gram (mmg_kinship_gram_i8_host): two page-locked host slots and
+    // two device slots, kept across calls (page-locking 330 MB costs more than a whole kinship)
+    uint8_t* stage_host[2] = {nullptr, nullptr};
+    uint8_t* stage_dev[2] = {nullptr, nullptr};
+    int64_t stage_bytes = 0;
+    int64_t last_h2d_packed = 0, last_h2d_raw = 0;   // chunks the last streamed Gram sent over each lane
+    double pack_s_per_byte = 0.0;                    // measured host packing cost (seconds per genotype byte), 0 = not measured yet
+
     // scratch
     void* scratch = nullptr;
     int64_t scratch_bytes = 0;

@@ -105,7 +105,8 @@ struct QuadIter {
 };
 
 constexpr int QP_EPI_WARPS = 8;
-constexpr int QP_THREADS = 64 + 32 * QP_EPI_WARPS;       // producer warp, MMA warp, 8 epilogue warps
+constexpr int QP_FIRST_EPI_WARP = 3;
+constexpr int QP_THREADS = 32 * (QP_FIRST_EPI_WARP + QP_EPI_WARPS);   // producer warp, MMA warp, L2-prefetch warp, 8 epilogue warps
 
 // LDW = columns per tcgen05.ld of the epilogue (16 or 32), double buffered either way
 template <int CS, int PKB, int STAGES, bool PAIR, int BN, int LDW = 16>
@@ -133,6 +134,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull_bar = aempty_bar + PKB;           // [2]       accumulator complete
     uint64_t* tempty_bar = tfull_bar + kAcc;          // [kAcc]    accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAcc);
+    volatile uint32_t* progress = tmem_slot + 1;       // digit K-blocks the producer has requested so far (read by the prefetch warp)
     double* xchg = reinterpret_cast<double*>(bars + 64);    // [128] q, then xy, of the upper column half (1 KB)
 
     // warp index through a shuffle: the compiler then knows the role branches are warp-uniform, keeps loop counters,
@@ -148,6 +150,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool leader = !PAIR || crank == 0;
 
     if (warp == 0 && lane == 0) {
+        *progress = 0u;
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) {
@@ -188,10 +191,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool timed = sh.dbg != nullptr;
             long long w_aempty = 0, w_empty = 0;
             const long long t_start = timed ? clock64() : 0;
-            QuadIter<PKB, BN> pf;
-            pf.reset(sh);
-            for (int d = 0; d < sh.prefetch; ++d) pf.advance(sh);
-            int pf_count = cluster_id % sh.pf_share;    // position in the shared prefetch rota
+            uint32_t requested = 0;                     // digit K-blocks requested so far, published for the prefetch warp
             unsigned wave_target = 0;
             int wave = 0;
             uint32_t pre = 0;                           // genotype K-blocks of the coming panel that are already requested
@@ -250,13 +250,6 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 const int rowB = (t * sh.S_stride + k) * sh.n_padN + jb * BN + crank * kBRows;
                                 const bool last_tile = (jb == sh.tiles_n - 1) && (k == sh.S - 1);
                                 for (int i = 0; i < nkb; ++i) {
-                                    if (sh.prefetch) {
-                                        if (pf_count == 0) {
-                                            if (elect_one()) tma_prefetch_2d(&tmB, pf.kb() * TC_BK, pf.row(sh) + crank * kBRows);
-                                        }
-                                        if (++pf_count == sh.pf_share) pf_count = 0;
-                                        pf.advance(sh);
-                                    }
                                     mbar_wait_timed(&empty_bar[stage], phase ^ 1, timed, w_empty);
                                     if (elect_one()) {
                                         if (PAIR) {
@@ -273,6 +266,8 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                         }
                                     }
                                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                    ++requested;
+                                    if (sh.prefetch && one) *progress = requested;
                                     // the slot just refilled was freed by the MMA of K-block i - STAGES of this tile, which also
                                     // released genotype K-block i - STAGES of the panel: reload it for the next panel now
                                     if (last_tile && i >= STAGES && i - STAGES < nka_next) {
@@ -371,15 +366,49 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
         __syncwarp();
+    } else if (warp == 2) {
+        // ===================== L2 prefetch warp =====================
+        // Walks the same digit-plane stream as the producer, `sh.prefetch` K-blocks ahead of it (cp.async.bulk.prefetch.tensor
+        // into L2).  In its own warp: inside the producer loop the extra ~45 instructions per K-block made the single-thread
+        // issue chain (~700 cycles per K-block) slower than the tensor pipe (512) -- the MMA spent half its time waiting for
+        // tiles that had not been requested yet.
+        if (sh.prefetch) {
+            uint32_t done = 0;
+            const int rota = cluster_id % sh.pf_share;
+            int pf_count = rota;
+            for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
+                for (int t = 0; t < sh.T; ++t) {
+                    for (int kbase = 0; kbase < sh.kb_total; kbase += PKB) {
+                        const int nka = min(PKB, sh.kb_total - kbase);
+                        for (int jb = kbase / kKbPerTile; jb < sh.tiles_n; ++jb) {
+                            const int nkb = min(nka, kKbPerTile * (jb + 1) - kbase);
+                            for (int k = 0; k < sh.S; ++k) {
+                                const int rowB = (t * sh.S_stride + k) * sh.n_padN + jb * BN + crank * kBRows;
+                                for (int i = 0; i < nkb; ++i) {
+                                    // stay at most sh.prefetch K-blocks ahead of what the producer has requested
+                                    while ((int)(done - *progress) >= sh.prefetch) __nanosleep(64);
+                                    if (pf_count == 0) {
+                                        if (elect_one()) tma_prefetch_2d(&tmB, (kbase + i) * TC_BK, rowB);
+                                    }
+                                    if (++pf_count == sh.pf_share) pf_count = 0;
+                                    ++done;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
     } else {
-        // ===================== epilogue warps 2..9 =====================
+        // ===================== epilogue warps 3..10 =====================
         // two warps per TMEM lane quadrant (a warp may only read lanes 32 (warp % 4) .. +31): each takes 128 of the tile's
         // 256 columns, so every SM sub-partition runs two epilogue warps that hide each other's tcgen05.ld / IMAD latency
         const bool timed = sh.dbg != nullptr;
         long long w_tfull = 0, w_x = 0, w_fp = 0, w_drain = 0;      // cycles: waiting for accumulators | x register loads | FP64 x.v pass | drain
         const long long t_start = timed ? clock64() : 0;
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;                       // 0: columns 0..127 of a tile, 1: columns 128..255
+        const int half = (warp - QP_FIRST_EPI_WARP) >> 2;       // 0: columns 0..127 of a tile, 1: columns 128..255
         const int row = quad * 32 + lane;
         constexpr int kCols = BN / 2;
         auto load_x = [](const int8_t* xrow, int col, uint32_t (&dst)[kCols / 4]) {
@@ -519,7 +548,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
-        if (timed && warp == 2 && lane == 0) {
+        if (timed && warp == QP_FIRST_EPI_WARP && lane == 0) {
             long long* d = sh.dbg + (int64_t)blockIdx.x * 16;
             d[8] = clock64() - t_start;
             d[9] = w_tfull;

@@ -218,9 +218,9 @@ __global__ void __launch_bounds__(256) snp_prepass_kernel(const int8_t* __restri
     const int nr = (int)min((int64_t)PRE_ROWS, row_count - r0);
     const int8_t* xrow = snps + (row_begin + r0) * pitch;
     const double kBias = 4503599627370496.0 + 128.0;               // 2^52 + 128
-    int l1[PRE_ROWS];
-#pragma unroll
-    for (int i = 0; i < PRE_ROWS; ++i) l1[i] = 0;
+    double l1[PRE_ROWS];             // ||x||_1 in FP64 too (|.| is a free operand modifier; the byte-SIMD / dot-product
+#pragma unroll                       // instructions run on the quarter-rate XU pipe and bounded the first version of this kernel)
+    for (int i = 0; i < PRE_ROWS; ++i) l1[i] = 0.0;
     for (int t = 0; t < T; ++t) {
         const double* vt = v + (int64_t)t * v_stride;
         const double* dt = dg + (int64_t)t * v_stride;
@@ -236,7 +236,6 @@ __global__ void __launch_bounds__(256) snp_prepass_kernel(const int8_t* __restri
 #pragma unroll
             for (int i = 0; i < PRE_ROWS; ++i) {
                 const uint32_t g = i < nr ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(xrow + i * pitch + c)) : 0u;
-                if (t == 0) l1[i] = __dp4a((int)__vabsss4(g), 0x01010101, l1[i]);
                 const uint32_t b = g ^ 0x8080u;                      // bytes + 128
                 const double x0 = __hiloint2double(0x43300000, (int)(b & 0xffu)) - kBias;
                 const double x1 = __hiloint2double(0x43300000, (int)(b >> 8)) - kBias;
@@ -244,6 +243,7 @@ __global__ void __launch_bounds__(256) snp_prepass_kernel(const int8_t* __restri
                 sqd[i] = fma(x0 * x0, dd.x, sqd[i]);
                 sxy[i] = fma(x1, vv.y, sxy[i]);
                 sqd[i] = fma(x1 * x1, dd.y, sqd[i]);
+                if (t == 0) l1[i] += fabs(x0) + fabs(x1);
             }
         }
 #pragma unroll
@@ -262,10 +262,10 @@ __global__ void __launch_bounds__(256) snp_prepass_kernel(const int8_t* __restri
     }
 #pragma unroll
     for (int i = 0; i < PRE_ROWS; ++i) {
-        int a = l1[i];
+        double a = l1[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0 && i < nr) a1[r0 + i] = (double)a;
+        if (lane == 0 && i < nr) a1[r0 + i] = a;
     }
 }
 

@@ -65,6 +65,8 @@ def test_gram_streamed_from_host_bit_exact(ctx, coding, m, n, pinned):
         snps = host
     ctx.invalidate_snps()
     assert ctx.kinship_gram_from(snps, coding) == (m, n)
+    packed, raw, _ = ctx.last_h2d_info()
+    assert packed + raw == (m + 65535) // 65536 and (pinned or raw == 0)  # pageable rows all go through the 2-bit lane
     G = ctx.kinship_gram_download()
     ctx.kinship_gram(coding, reset=True)                                  # the resident copy, Gram again
     assert np.array_equal(ctx.kinship_gram_download(), G)
@@ -78,6 +80,35 @@ def test_gram_streamed_from_host_bit_exact(ctx, coding, m, n, pinned):
     assert np.array_equal(sums, np.asarray(snps).astype(np.int64).sum(axis=1))   # every row landed
     assert ctx.kinship_gram_from(snps, coding) == (m, n)                 # already resident: plain Gram, same result
     assert np.array_equal(ctx.kinship_gram_download(), G)
+
+
+def test_gram_streamed_lanes(ctx, monkeypatch):
+    """Both lanes of the streamed upload give the same resident block and Gram: packed lane off (MMG_H2D_PACK=0), and a
+    chunk with a code the 2-bit packing cannot hold (5, invalid for the coding too) falling back to the raw lane and then
+    being refused by the coding check."""
+    from mixmogam_b200 import MmgError
+    m, n = 150000, 70
+    snps = _rand_snps(m, n, 1, seed=77)
+    ctx.invalidate_snps()
+    ctx.kinship_gram_from(snps, 1)
+    assert ctx.last_h2d_info()[0] == 3
+    G = ctx.kinship_gram_download()
+    monkeypatch.setenv('MMG_H2D_PACK', '0')
+    ctx.invalidate_snps()
+    ctx.kinship_gram_from(snps, 1)
+    assert ctx.last_h2d_info()[:2] == (0, 3)
+    assert np.array_equal(ctx.kinship_gram_download(), G)
+    monkeypatch.delenv('MMG_H2D_PACK')
+    snps[70000, 3] = 5                                                    # second chunk
+    ctx.invalidate_snps()
+    with pytest.raises(MmgError):
+        ctx.kinship_gram_from(snps, 1)
+    assert ctx.last_h2d_info()[:2] == (1, 2)
+    snps[70000, 3] = 0
+    ctx.invalidate_snps()
+    ctx.kinship_gram_from(snps, 1)
+    snps2 = snps.copy()
+    assert np.array_equal(ctx.snps_row_sums(), snps2.astype(np.int64).sum(axis=1))
 
 
 def test_gram_streamed_rejects_out_of_domain_values(ctx):

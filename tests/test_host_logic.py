@@ -152,3 +152,32 @@ def test_base256_digit_expansion(built):
             for Sp in range(0, S + 1):
                 part = sum(Fraction(d, 256 ** (k + 1)) for k, d in enumerate(digs[:Sp]))
                 assert abs(r - part) <= bound / 256 ** Sp
+
+
+@pytest.mark.parametrize('rows,n,ld,threads', [(1, 1, 1, 1), (7, 37, 37, 3), (64, 10000, 10000, 4), (33, 198, 256, 2), (5, 31, 40, 8), (300, 131, 131, 5)])
+def test_host_pack2_matches_numpy(built, rows, n, ld, threads):
+    """The host side of the packed genotype upload (csrc/host_pack.cpp, AVX2 or scalar): 2 bits per code, code j of a row in
+    bits 2 (j % 4) of byte j / 4, zeroed tail; any code outside 0..3 is reported."""
+    from mixmogam_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(rows * 1000 + n)
+    buf = rng.integers(0, 4, size=(rows, ld), dtype=np.int8)
+    n4 = (n + 3) // 4
+    dst_ld = (n4 + 15) // 16 * 16
+    out = np.full((rows, dst_ld), 0xAB, dtype=np.uint8)
+    rc = lib.mmg_host_pack2(buf.ctypes.data, rows, n, ld, out.ctypes.data, dst_ld, threads)
+    assert rc == 0
+    x = np.zeros((rows, n4 * 4), dtype=np.uint8)
+    x[:, :n] = buf[:, :n]
+    ref = x[:, 0::4] | (x[:, 1::4] << 2) | (x[:, 2::4] << 4) | (x[:, 3::4] << 6)
+    assert np.array_equal(out[:, :n4], ref) and not out[:, n4:].any()
+    for bad in (4, -1, 127, -128):
+        b2 = buf.copy()
+        b2[rows - 1, n - 1] = bad
+        assert lib.mmg_host_pack2(b2.ctypes.data, rows, n, ld, out.ctypes.data, dst_ld, threads) == 1
+    if ld > n:                                         # bytes between n and ld are not part of the row
+        b3 = buf.copy()
+        b3[:, n:] = 9
+        assert lib.mmg_host_pack2(b3.ctypes.data, rows, n, ld, out.ctypes.data, dst_ld, threads) == 0
+        assert np.array_equal(out[:, :n4], ref)
+    assert lib.mmg_host_threads_default() >= 1
