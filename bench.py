@@ -227,8 +227,12 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    # rank 0 prints exactly ONE line on stdout (the JSON).  NCCL writes its version banner straight to file descriptor 1
+    # from C, so the descriptor itself is pointed at stderr for the whole run and the JSON goes out through a saved copy.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # rank 0 prints exactly ONE line on stdout (the JSON): NCCL's own banner / debug lines go to stderr
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda:%d' % local))
     device = torch.device('cuda:%d' % local)
@@ -410,7 +414,8 @@ def main():
             out['cpu_baseline'] = cpu_baseline(n, m)
         else:
             out['cpu_baseline'] = None
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
