@@ -1626,7 +1626,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         double* p_qd = p_xy + (int64_t)T * snp_count;
         double* p_a1 = p_qd + (int64_t)T * snp_count;
         const int rows_per_block = 8 * PRE_ROWS;
-        snp_prepass_kernel<<<(unsigned)((snp_count + rows_per_block - 1) / rows_per_block), 256, 0, ctx->stream>>>(
+        snp_prepass_kernel<PRE_ROWS, 4, 4><<<(unsigned)((snp_count + rows_per_block - 1) / rows_per_block), 256, 0, ctx->stream>>>(
             ctx->snps, ctx->pitch, snp_begin, snp_count, T, d_v, d_dg, n_padN, p_xy, p_qd, p_a1, snp_count);
         MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
         ep.pre_xy = p_xy;
@@ -2312,6 +2312,42 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
             cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
         }
         *value = 2.0 * bytes / (ms * 1e-3) / 1e9;
+        return MMG_OK;
+    }
+    if (!strncmp(which, "prepass", 7)) {
+        // "prepass_r<rows>_u<unroll>_b<min blocks>": ms of the scan's linear pre-pass over the resident genotypes (tuning aid)
+        MMG_CHECK(ctx, ctx->snps != nullptr, "prepass microbench: no resident genotypes");
+        const int64_t npad = round_up(ctx->n, 256), cnt = ctx->m;
+        DevBuf buf;
+        MMG_CUDA(ctx, buf.alloc(ctx->stream, (size_t)(2 * npad + 3 * cnt) * sizeof(double)));
+        MMG_CUDA(ctx, cudaMemsetAsync(buf.p, 0, (size_t)(2 * npad) * sizeof(double), ctx->stream));
+        double* v = buf.as<double>();
+        double* o = v + 2 * npad;
+        auto run = [&](auto kern, int rows) {
+            for (int rep = 0; rep < 3; ++rep) {
+                cudaEventRecord(ctx->kev0, ctx->stream);
+                kern<<<(unsigned)((cnt + 8 * rows - 1) / (8 * rows)), 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, 0, cnt, 1, v, v + npad, npad, o, o + cnt,
+                                                                                        o + 2 * cnt, cnt);
+                cudaEventRecord(ctx->kev1, ctx->stream);
+                cudaStreamSynchronize(ctx->stream);
+                cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+            }
+        };
+        if (!strcmp(which, "prepass_r4_u4_b3")) run(snp_prepass_kernel<4, 4, 3>, 4);
+        else if (!strcmp(which, "prepass_r4_u4_b1")) run(snp_prepass_kernel<4, 4, 1>, 4);
+        else if (!strcmp(which, "prepass_r4_u2_b3")) run(snp_prepass_kernel<4, 2, 3>, 4);
+        else if (!strcmp(which, "prepass_r2_u4_b4")) run(snp_prepass_kernel<2, 4, 4>, 2);
+        else if (!strcmp(which, "prepass_r4_u8_b1")) run(snp_prepass_kernel<4, 8, 1>, 4);
+        else if (!strcmp(which, "prepass_r4_u4_b4")) run(snp_prepass_kernel<4, 4, 4>, 4);
+        else if (!strcmp(which, "prepass_r4_u8_b4")) run(snp_prepass_kernel<4, 8, 4>, 4);
+        else if (!strcmp(which, "prepass_r8_u4_b2")) run(snp_prepass_kernel<8, 4, 2>, 8);
+        else if (!strcmp(which, "prepass_r8_u2_b3")) run(snp_prepass_kernel<8, 2, 3>, 8);
+        else if (!strcmp(which, "prepass_r2_u8_b4")) run(snp_prepass_kernel<2, 8, 4>, 2);
+        else if (!strcmp(which, "prepass_r2_u16_b4")) run(snp_prepass_kernel<2, 16, 4>, 2);
+        else if (!strcmp(which, "prepass_r1_u16_b4")) run(snp_prepass_kernel<1, 16, 4>, 1);
+        else return fail(ctx, MMG_EBADARG, "unknown microbench '%s'", which);
+        MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
+        *value = ms;
         return MMG_OK;
     }
     if (!strncmp(which, "ldtm", 4)) {

@@ -207,8 +207,10 @@ struct PermEpi {
 // quarter-rate I2F: the byte is biased to 0..255, placed in the mantissa of 2^52 and the bias removed by one exact DADD.
 // The scan epilogue used to do this inside its accumulator-drain loop (I2F + dependent DFMA chains, 16 k cycles per
 // column tile during which the MMA ran out of accumulators); here it is an HBM-rate stream of its own.
-constexpr int PRE_ROWS = 4;      // SNP rows per warp: v_t / diag(A_t) are fetched from L1 once per 4 rows
-__global__ void __launch_bounds__(256) snp_prepass_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t row_begin, int64_t row_count,
+constexpr int PRE_ROWS = 2;      // SNP rows per warp (v_t / diag(A_t) are fetched from L1 once per PRE_ROWS rows); measured on 262 144 SNPs x 10 k
+                                 // (profiles/r01_microbench_prepass.txt): <2 rows, unroll 4, 4 blocks/SM> 1.82 ms, <4, 4, 3> 2.61 ms, <8, 4, 2> 2.80 ms
+template <int PRE_ROWS = 4, int PRE_UNROLL = 4, int PRE_MINB = 1>
+__global__ void __launch_bounds__(256, PRE_MINB) snp_prepass_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t row_begin, int64_t row_count,
                                                           int T, const double* __restrict__ v, const double* __restrict__ dg, int64_t v_stride,
                                                           double* __restrict__ xy, double* __restrict__ qd, double* __restrict__ a1,
                                                           int64_t out_stride) {
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(256) snp_prepass_kernel(const int8_t* __restri
         for (int i = 0; i < PRE_ROWS; ++i) sxy[i] = sqd[i] = 0.0;
         // every load is fully coalesced: lane l takes columns c + 2l, c + 2l + 1 (one double2 of v_t and of diag(A_t), one
         // 16-bit genotype pair per row); 64 columns per warp step.  pitch is a multiple of 256, v / dg are zero padded past n.
-#pragma unroll 4
+#pragma unroll PRE_UNROLL
         for (int64_t c = 2 * lane; c < pitch; c += 64) {
             const double2 vv = __ldg(reinterpret_cast<const double2*>(vt + c));
             const double2 dd = __ldg(reinterpret_cast<const double2*>(dt + c));
