@@ -750,6 +750,7 @@ struct GramHostSource {
     cudaStream_t stream = nullptr;     // raw lane
     cudaStream_t stream2 = nullptr;    // packed lane (its small copies must not queue behind the raw ones)
     std::vector<cudaEvent_t> done;     // one per chunk
+    std::vector<cudaEvent_t> pre;      // raw lane: recorded right before the chunk's copy (copy duration = pre -> done)
     cudaEvent_t t0 = nullptr;
     cudaEvent_t slot_free[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
@@ -757,12 +758,16 @@ struct GramHostSource {
     bool pack_ok = true;               // packed lane available (switched off by MMG_H2D_PACK=0 or a code outside 0..3)
     int threads = 1;
     int next_slot = 0;
-    double dma_free_at = 0.0;          // host clock (s) at which the raw lane is expected to have drained
+    std::vector<int64_t> raw_queue;    // chunk ids on the raw lane in queue order
+    size_t raw_done = 0;               // how many of them have been seen complete
+    double raw_rate = 0.0;             // measured raw-lane rate (bytes/s) once a copy has completed
     int64_t packed_chunks = 0, raw_chunks = 0;
     ~GramHostSource() {
         for (cudaStream_t st : {stream, stream2})
             if (st) cudaStreamSynchronize(st);  // the host rows are borrowed for the duration of the call only
         for (cudaEvent_t e : done) cudaEventDestroy(e);
+        for (cudaEvent_t e : pre)
+            if (e) cudaEventDestroy(e);
         if (t0) cudaEventDestroy(t0);
         for (cudaEvent_t e : slot_free)
             if (e) cudaEventDestroy(e);
@@ -915,16 +920,19 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     std::vector<char> staged((size_t)n_chunks, 0);
     if (src) {
         src->done.resize((size_t)n_chunks, nullptr);
+        src->pre.resize((size_t)n_chunks, nullptr);
         for (auto& e : src->done) MMG_CUDA(ctx, cudaEventCreate(&e));
     }
     auto chunk_rows = [&](int64_t ci) { return std::min(chunk, snp_count - ci * chunk); };
     auto raw_seconds = [&](int64_t ci) { return (double)chunk_rows(ci) * (double)ctx->n / pcie_rate; };
     auto queue_raw = [&](int64_t ci) -> int {
         const int64_t s0 = ci * chunk, cnt = chunk_rows(ci);
+        MMG_CUDA(ctx, cudaEventCreate(&src->pre[(size_t)ci]));
+        MMG_CUDA(ctx, cudaEventRecord(src->pre[(size_t)ci], src->stream));
         MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->snps + (snp_begin + s0) * ctx->pitch, ctx->pitch, src->snps + (snp_begin + s0) * src->ld, src->ld,
                                         ctx->n, cnt, cudaMemcpyHostToDevice, src->stream));
         MMG_CUDA(ctx, cudaEventRecord(src->done[(size_t)ci], src->stream));
-        src->dma_free_at = std::max(src->dma_free_at, host_now()) + (src->pinned ? raw_seconds(ci) : 0.0);
+        src->raw_queue.push_back(ci);
         src->raw_chunks += 1;
         staged[(size_t)ci] = 1;
         return MMG_OK;
@@ -964,7 +972,6 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
         MMG_CUDA(ctx, cudaEventRecord(src->done[(size_t)ci], src->stream2));
         src->slot_used[sl] = true;
         src->next_slot = sl ^ 1;
-        src->dma_free_at = std::max(src->dma_free_at, host_now()) + 0.25 * raw_seconds(ci);       // its quarter-size copy shares the link
         src->packed_chunks += 1;
         staged[(size_t)ci] = 1;
         return MMG_OK;
@@ -975,16 +982,31 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     // following chunks so that the link stays busy meanwhile.
     auto issue_copy = [&](int64_t ci) -> int {
         if (staged[(size_t)ci]) return MMG_OK;
-        const double raw_s = raw_seconds(ci);
+        double raw_s = raw_seconds(ci);
         const double pack_s = ctx->pack_s_per_byte > 0.0 ? ctx->pack_s_per_byte * (double)chunk_rows(ci) * (double)ctx->n : raw_s;
-        const double backlog = std::max(0.0, src->dma_free_at - host_now());
+        // backlog of the raw lane: bytes queued and not yet seen complete, at the rate measured on the copies that are
+        // (the link is shared with the packed lane's copies and the host cores' own reads, so the nominal rate is not it)
+        while (src->raw_done < src->raw_queue.size() && cudaEventQuery(src->done[(size_t)src->raw_queue[src->raw_done]]) == cudaSuccess) {
+            const int64_t cd = src->raw_queue[src->raw_done++];
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, src->pre[(size_t)cd], src->done[(size_t)cd]) == cudaSuccess && ms > 0.f) {
+                const double r = (double)chunk_rows(cd) * (double)ctx->n / (1e-3 * ms);
+                src->raw_rate = src->raw_rate > 0.0 ? 0.5 * (src->raw_rate + r) : r;
+            }
+        }
+        cudaGetLastError();                                  // cudaErrorNotReady from the query is not an error
+        double pending = 0.0;
+        for (size_t qi = src->raw_done; qi < src->raw_queue.size(); ++qi) pending += (double)chunk_rows(src->raw_queue[qi]) * (double)ctx->n;
+        const double rate = src->raw_rate > 0.0 ? std::min(src->raw_rate, pcie_rate * 1.2) : pcie_rate;
+        const double backlog = src->pinned ? pending / rate : 0.0;
+        raw_s = (double)chunk_rows(ci) * (double)ctx->n / rate;
         if (src->pack_ok && (!src->pinned || backlog + raw_s > pack_s + 0.25 * raw_s)) {
             if (src->pinned) {
                 double ahead = backlog;
                 for (int64_t cj = ci + 1; cj < n_chunks && ahead < pack_s; ++cj) {
                     if (staged[(size_t)cj]) continue;
                     MMG_TRY(queue_raw(cj));
-                    ahead += raw_seconds(cj);
+                    ahead += (double)chunk_rows(cj) * (double)ctx->n / rate;
                 }
             }
             MMG_TRY(queue_packed(ci));
