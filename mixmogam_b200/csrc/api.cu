@@ -323,6 +323,7 @@ int mmg_create(int device, mmg_ctx** out) {
     cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<IbdEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<IbdEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<OzakiEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<PermEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<PermEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(scan_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
@@ -1454,23 +1455,97 @@ static double scan_tc_tol() {
 
 // Digit planes of the strict lower triangle of A = R'R (doubled) into Bq (S planes of [n_padN x ldq]), diag(A) into
 // d_dg and v = R'y into d_v; returns the binary exponent E used for the scaling.  `A` is an n x n FP64 work matrix.
-static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const double* A_given, double* A_work, unsigned long long* d_amax,
-                        int S, int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, double* d_dg, int* E_out) {
+// A = R'R as exact int8 digit-plane products on the tensor cores (scan_tc.cuh, "A = R'R on the int8 tensor cores"); A_work is a
+// zero-filled [n_padM x n_padM] FP64 buffer whose lower-triangular tiles are written.  *err_out: absolute error bound of its entries.
+static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_work, int64_t n_padM, unsigned long long* d_amax, double* err_out) {
+    const int64_t n = ctx->n, n_out = R->rows;
+    MMG_CHECK(ctx, n_out < 131072, "R'R on the int8 pipe: contraction too long for exact int32 accumulation");
+    MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
+    mat_amax_kernel<<<dim3(8, (unsigned)n_out), 256, 0, ctx->stream>>>(R->d, n, (int)n_out, (int)n, d_amax);
+    MMG_TRY(launch_check(ctx, "mat_amax_kernel"));
+    double rmax = 0.0;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&rmax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!std::isfinite(rmax)) return fail(ctx, MMG_EVALUE, "scan: the rotation is not finite (max |r| = %g)", rmax);
+    const int F = digit256_exponent(rmax);
+    const int64_t op_pitch = round_up(n_out, TC_BK);
+    DevBuf Op;
+    MMG_CUDA(ctx, Op.alloc(ctx->stream, (size_t)OZ_PLANES * n_padM * op_pitch));
+    MMG_CUDA(ctx, cudaMemsetAsync(Op.p, 0, (size_t)OZ_PLANES * n_padM * op_pitch, ctx->stream));
+    ozaki_planes_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n_out + 31) / 32)), 256, 0, ctx->stream>>>(
+        R->d, n, (int)n_out, (int)n, ldexp(1.0, -F), Op.as<int8_t>(), n_padM, op_pitch);
+    MMG_TRY(launch_check(ctx, "ozaki_planes_kernel"));
+    MMG_CUDA(ctx, cudaMemsetAsync(A_work, 0, (size_t)n_padM * n_padM * sizeof(double), ctx->stream));
+    // tile table: row-tile pairs (im, im + 1) x column tile jn that meet the lower triangle (rows >= columns), 28 (p, q) planes each
+    const int tiles_n = (int)(n_padM / TC_BN), tiles_m = (int)(n_padM / TC_BM), KB = (int)(op_pitch / TC_BK);
+    std::vector<TcTile> tiles;
+    int entries = 0, per_entry = 0;
+    for (int jn = 0; jn < tiles_n; ++jn)
+        for (int im = 2 * jn; im < tiles_m; im += 2) {
+            per_entry = 0;
+            for (int p = 0; p < OZ_PLANES; ++p)
+                for (int q = 0; p + q < OZ_LEVELS && q < OZ_PLANES; ++q) {
+                    TcTile tl{};
+                    tl.m0 = (int)((int64_t)p * n_padM + (int64_t)im * TC_BM);
+                    tl.n0 = (int)((int64_t)q * n_padM + (int64_t)jn * TC_BN);
+                    tl.kb0 = 0;
+                    tl.kb1 = KB;
+                    tl.aux0 = p;
+                    tl.aux1 = q;
+                    tiles.push_back(tl);
+                    ++per_entry;
+                }
+            ++entries;
+        }
+    MMG_TRY(ensure_tiles(ctx, tiles));
+    CUtensorMap tmA, tmB;
+    MMG_TRY(make_tmap_u8(ctx, &tmA, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BM));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BN / 2));
+    OzakiEpi::Params ep{};
+    ep.A = A_work;
+    ep.ld = n_padM;
+    ep.n_padM = n_padM;
+    for (int sl = 0; sl < 2 * OZ_PLANES; ++sl) ep.w[sl] = ldexp(1.0, 2 * F - 8 * (sl + 2));
+    MMG_TRY((launch_tc_gemm<OzakiEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, entries * 2, per_entry, per_entry, 0, TC_BM, ep,
+                                         "tc_gemm_i8_kernel<OzakiEpi,2>")));
+    *err_out = ozaki_error_bound(n_out) * ldexp(1.0, 2 * F);   // (Op is released in stream order when this returns)
+    return MMG_OK;
+}
+
+// MMG_QUAD_A = int8 (default: exact digit-plane products on the int8 tensor pipe) | dsyrk (cuBLAS, FP64 tensor pipe)
+static thread_local bool g_quad_force_dsyrk = false;     // set while a scan is repeated with the FP64 product (see scan_tc_run)
+static bool quad_a_int8() {
+    if (g_quad_force_dsyrk) return false;
+    const char* e = getenv("MMG_QUAD_A");
+    return !(e && strcmp(e, "dsyrk") == 0);
+}
+
+static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const double* A_given, double* A_work, int64_t lda_work,
+                        unsigned long long* d_amax, int S, int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, double* d_dg, int* E_out,
+                        double* errA_out) {
     const int64_t n = ctx->n;
     const double one = 1.0, zero = 0.0;
     const double* A = A_given;
+    int64_t lda = n;
+    *errA_out = 0.0;
     if (!A_given) {
         const int64_t n_out = R->rows;
-        // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
-        // is the row-major LOWER triangle A[j][i], i <= j -- exactly the operand the slices are cut from.
-        MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero, A_work, (int)n));
+        if (quad_a_int8() && scan_tc_tol() >= 1e-9) {
+            MMG_TRY(quad_form_int8(ctx, R, A_work, lda_work, d_amax, errA_out));
+        } else {
+            // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
+            // is the row-major LOWER triangle A[j][i], i <= j -- exactly the operand the slices are cut from.
+            MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero, A_work,
+                                        (int)lda_work));
+        }
         // v = R' y~  (x~.y~ = x.v)
         if (d_y) MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1));
         A = A_work;
+        lda = lda_work;
     }
     MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
     dim3 agrid(8, (unsigned)n);
-    quad_amax_kernel<<<agrid, 256, 0, ctx->stream>>>(A, n, (int)n, d_amax);
+    quad_amax_kernel<<<agrid, 256, 0, ctx->stream>>>(A, lda, (int)n, d_amax);
     MMG_TRY(launch_check(ctx, "quad_amax_kernel"));
     double amax = 0.0;
     MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1478,7 +1553,7 @@ static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const 
     if (!std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "scan: R'R is not finite (max |a| = %g)", amax);
     const int E = digit256_exponent(amax);                // |2 a| 2^-E <= 0.498 (a diagonal R'R has no off-diagonal digits at all)
     dim3 sgrid((unsigned)((n + 255) / 256), (unsigned)n);
-    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A, n, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq, d_dg);
+    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A, lda, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq, d_dg);
     MMG_TRY(launch_check(ctx, "quad_slice_kernel"));
     *E_out = E;
     return MMG_OK;
@@ -1600,7 +1675,8 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     const int64_t plane = n_padN * ldq;
     MMG_CHECK(ctx, (int64_t)T * S_alloc * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
     DevBuf A, Bq, vec;
-    if (!A_given) MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)n * n * sizeof(double)));
+    const int64_t lda_work = round_up(n, TC_BN);               // padded so that the int8 R'R epilogue needs no bounds checks
+    if (!A_given) MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)lda_work * lda_work * sizeof(double)));
     MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S_alloc * plane));
     // vec: v[T][n_padN] | dg[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | bscale[T] | amax | rho | wave counter
     const int64_t nd = 2 * (int64_t)T * n_padN + (int64_t)T * n_out + 3 * T + 3;
@@ -1619,12 +1695,12 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     if (A_given) MMG_CUDA(ctx, cudaMemcpyAsync(d_v, v_given, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     else MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<double> escale((size_t)T), bscale((size_t)T);
+    std::vector<double> escale((size_t)T), bscale((size_t)T), errA((size_t)T, 0.0);
     for (int t = 0; t < T; ++t) {
         int E = 0;
-        MMG_TRY(quad_prepare(ctx, A_given ? nullptr : Rs[t], d_y + (int64_t)t * n_out, A_given ? A_given->d : nullptr, A.as<double>(), d_amax, S_alloc,
-                             Bq.as<int8_t>() + (int64_t)t * S_alloc * plane, n_padN, ldq, d_v + (int64_t)t * n_padN,
-                             d_dg + (int64_t)t * n_padN, &E));
+        MMG_TRY(quad_prepare(ctx, A_given ? nullptr : Rs[t], d_y + (int64_t)t * n_out, A_given ? A_given->d : nullptr, A.as<double>(), lda_work,
+                             d_amax, S_alloc, Bq.as<int8_t>() + (int64_t)t * S_alloc * plane, n_padN, ldq, d_v + (int64_t)t * n_padN,
+                             d_dg + (int64_t)t * n_padN, &E, &errA[(size_t)t]));
         escale[t] = ldexp(1.0, E);
     }
     MMG_CUDA(ctx, cudaMemcpyAsync(d_es, escale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1661,7 +1737,8 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
 
     // bound scale for S planes: |remainder| <= 128/255 per entry of B, sum_{i<j} |x_i||x_j| <= ||x||_1^2 / 2
     auto set_bscale = [&](int S) -> int {
-        for (int t = 0; t < T; ++t) bscale[t] = 0.5 * DIGIT256_REM * ldexp(1.0, -8 * S) * escale[t];
+        // + the entry-wise error bound of A itself when it came from the int8 digit-plane product: |x'(dA)x| <= errA ||x||_1^2
+        for (int t = 0; t < T; ++t) bscale[t] = 0.5 * DIGIT256_REM * ldexp(1.0, -8 * S) * escale[t] + errA[(size_t)t];
         MMG_CUDA(ctx, cudaMemcpyAsync(d_bs, bscale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         MMG_CUDA(ctx, cudaMemsetAsync(d_rho, 0, sizeof(unsigned long long), ctx->stream));
         return MMG_OK;
@@ -1681,11 +1758,17 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         MMG_TRY(scan_tc_launch(ctx, T, QS_PILOT_PLANES, S_alloc, Bq.p, n_padN, ldq, snp_begin, QS_PILOT_ROWS, pp, d_wave));
         double rho = 0.0;
         MMG_TRY(read_rho(&rho));
+        // bound(S) / bound(pilot planes), worst phenotype: 256 per plane down to the floor set by the error of A itself
+        auto bound_ratio = [&](int planes) {
+            double r = 0.0;
+            for (int t = 0; t < T; ++t) {
+                const double c = 0.5 * DIGIT256_REM * escale[t];
+                r = std::max(r, (c * ldexp(1.0, -8 * planes) + errA[(size_t)t]) / (c * ldexp(1.0, -8 * QS_PILOT_PLANES) + errA[(size_t)t]));
+            }
+            return r;
+        };
         S = QS_PILOT_PLANES;
-        while (S < S_alloc && rho * QS_PILOT_HEADROOM > tol) {
-            rho /= 256.0;
-            ++S;
-        }
+        while (S < S_alloc && rho * bound_ratio(S) * QS_PILOT_HEADROOM > tol) ++S;
     }
     double rho = 0.0;
     for (;;) {
@@ -1700,6 +1783,16 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     }
     ctx->last_scan_slices = S;
     ctx->last_scan_rho = rho;
+    // a tolerance below what the int8 product of A can certify (its own error bound is a floor of ~1e-10 relative at n = 10k):
+    // once more with A from the FP64 dsyrk
+    bool int8_floor = false;
+    for (double e : errA) int8_floor |= e > 0.0;
+    if (!S_fixed && rho > tol && int8_floor && !g_quad_force_dsyrk) {
+        g_quad_force_dsyrk = true;
+        const int rc = scan_tc_run(ctx, T, Rs, V, h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp, A_given, v_given);
+        g_quad_force_dsyrk = false;
+        return rc;
+    }
     return MMG_OK;
 }
 

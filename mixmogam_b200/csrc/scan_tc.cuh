@@ -20,6 +20,8 @@
 // of W = R'Ys ([P x n], all permuted phenotypes rotated back), 32 permutations x 8 slices per 256-column
 // tile, and keeps the per-permutation maximum of (x_c.W_p)^2 / (x~_c.x~_c) over SNPs.
 #pragma once
+#include <algorithm>
+
 #include "digits.cuh"
 #include "fdist.cuh"
 #include "tc_gemm.cuh"
@@ -299,6 +301,79 @@ __global__ void quad_slice_kernel(const double* __restrict__ A, int64_t ld, int 
     digit256_split(r, S, d);                                             // base 256, exact (digits.cuh)
     for (int k = 0; k < S; ++k) Bq[((int64_t)k * n_padN + j) * ldq + i] = (int8_t)d[k];
 }
+
+// ---- A = R'R on the int8 tensor cores (exact digit-plane products) -------------------------------------------------
+// The one-off FP64 product of the scan (cuBLAS dsyrk, 2 n^3 / 2 flops at the DMMA rate: 28 ms at n = 10k) as integer GEMMs:
+// R 2^-F (|.| <= 0.498) is cut into P = 7 base-256 digit planes r_p (digits.cuh, exact), every plane product
+//     G_pq[j][i] = sum_k r_p[k][j] r_q[k][i]           (int32, exact: n_out 128^2 < 2^31)
+// comes from tcgen05.mma kind::i8, and the epilogue folds  A[j][i] += 2^2F 256^-(p+q+2) G_pq[j][i]  in FP64 for the
+// 28 pairs with p + q < L = 7 (lower-triangular tiles only).  What is left out is bounded rigorously (ozaki_error_bound):
+// dropped pairs  sum_{p+q>=L} 128^2 256^-(p+q+2)  and the digit remainders rho = (128/255) 256^-P per factor, times n_out --
+// ~2^-41.7 2^2F at n = 10k, added to the certified truncation bound of the scan.
+constexpr int OZ_PLANES = 7;
+constexpr int OZ_LEVELS = 7;          // pairs (p, q) with p + q < OZ_LEVELS
+
+// absolute error bound of the A entries in units of 2^2F
+inline double ozaki_error_bound(int64_t n_out) {
+    const double rho = DIGIT256_REM * ldexp(1.0, -8 * OZ_PLANES);
+    double dropped = 0.0;
+    for (int s = OZ_LEVELS; s <= 2 * OZ_PLANES - 2; ++s) {
+        const int cnt = std::min(s + 1, 2 * OZ_PLANES - 1 - s);
+        dropped += (double)cnt * 16384.0 * ldexp(1.0, -8 * (s + 2));
+    }
+    return (double)n_out * (dropped + rho + rho * rho) * 1.0000001;
+}
+
+// digit planes of R' (K-major operand): Op[(p n_padM + i) op_pitch + k] = digit_p(R[k][i] 2^-F); 32 x 32 transpose through smem
+__global__ void __launch_bounds__(256) ozaki_planes_kernel(const double* __restrict__ R, int64_t ldr, int n_out, int n, double scale,
+                                                           int8_t* __restrict__ Op, int64_t n_padM, int64_t op_pitch) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int k = k0 + ty + 8 * r, i = i0 + tx;
+        tile[ty + 8 * r][tx] = (k < n_out && i < n) ? R[(int64_t)k * ldr + i] * scale : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 8 * r, k = k0 + tx;
+        if (i >= n || k >= n_out) continue;
+        int d[DIGIT256_MAX_PLANES];
+        digit256_split(tile[tx][ty + 8 * r], OZ_PLANES, d);
+#pragma unroll
+        for (int p = 0; p < OZ_PLANES; ++p) Op[((int64_t)p * n_padM + i) * op_pitch + k] = (int8_t)d[p];
+    }
+}
+
+// epilogue: A[out_row][out_col + 32c ..] += w[p + q] acc.  The 28 (p, q) tiles of one output tile are consecutive tiles of ONE
+// group (same CTA, same epilogue thread per row), so the read-modify-write needs no atomics and stays in L2.
+struct OzakiEpi {
+    struct Params {
+        double* A;             // [n_padM x ld] FP64, zeroed; lower-triangular tiles are written
+        int64_t ld;
+        int64_t n_padM;
+        double w[2 * OZ_PLANES];
+    };
+    __device__ __forceinline__ void begin_group(const Params&, int, int) {}
+    __device__ __forceinline__ void end_group(const Params&, int, int) {}
+    __device__ __forceinline__ int tile_begin(const Params&, const TcTile&, int) { return TC_BN / 32; }
+    __device__ __forceinline__ void tile_end(const Params&, const TcTile&, int, int) {}
+    __device__ __forceinline__ void chunk(const Params& p, const TcTile& t, int row, int c, const uint32_t (&v)[32]) {
+        const int64_t orow = (int64_t)t.m0 - (int64_t)t.aux0 * p.n_padM + row;       // aux0 = p, aux1 = q
+        const int64_t ocol = (int64_t)t.n0 - (int64_t)t.aux1 * p.n_padM + c * 32;
+        double2* dst = reinterpret_cast<double2*>(p.A + orow * p.ld + ocol);
+        const double wk = p.w[t.aux0 + t.aux1];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            double2 o = dst[j];
+            o.x = fma(wk, (double)(int)v[2 * j + 0], o.x);
+            o.y = fma(wk, (double)(int)v[2 * j + 1], o.y);
+            dst[j] = o;
+        }
+    }
+};
 
 // max |W| over a row-major [rows x cols] matrix -> bits of a non-negative double
 __global__ void mat_amax_kernel(const double* __restrict__ W, int64_t ld, int rows, int cols, unsigned long long* __restrict__ amax_bits) {

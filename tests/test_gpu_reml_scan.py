@@ -356,3 +356,34 @@ def test_quad_form_row_blocks_and_scan_quad(ctx):
     xt = snps.astype(np.float64) @ R.T
     np.testing.assert_allclose(rb['xx'], np.sum(xt * xt, axis=1), rtol=1e-7)
     ctx.invalidate_snps()
+
+
+@pytest.mark.parametrize('n,n_out', [(700, 699), (1300, 1297), (257, 100)])
+def test_quad_form_on_int8_pipe(ctx, monkeypatch, n, n_out):
+    """A = R'R from exact int8 digit-plane products (tcgen05, 28 plane pairs) against the cuBLAS dsyrk path and against
+    numpy, through x~.x~ = x'Ax of the scan with every digit plane of B in use; rows of R spanning three decades so the
+    global scaling of the digit planes is exercised; the certified bound covers the observed error."""
+    from mixmogam_b200._lib import DeviceMatrix
+    from oracle import reference_py3 as o
+    rng = np.random.default_rng(n)
+    m = 5000
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=n)
+    ctx.invalidate_snps()
+    ctx.ensure_snps(snps)
+    R = rng.standard_normal((n_out, n)) / np.sqrt(n) * 10.0 ** rng.uniform(-3, 0, size=(n_out, 1))
+    y = rng.standard_normal(n_out)
+    Rd = DeviceMatrix.from_host(ctx, R)
+    h0 = float(y @ y)
+    monkeypatch.setenv('MMG_TC_SLICES', '6')
+    monkeypatch.setenv('MMG_QUAD_A', 'dsyrk')
+    ra = ctx.emmax_scan(Rd, y.reshape(1, -1), h0, n_out - 1, impl='tcgen05')
+    monkeypatch.setenv('MMG_QUAD_A', 'int8')
+    rb = ctx.emmax_scan(Rd, y.reshape(1, -1), h0, n_out - 1, impl='tcgen05')
+    S, rho = ctx.last_scan_info()
+    xt = snps.astype(np.float64) @ R.T
+    xx = np.sum(xt * xt, axis=1)
+    err_b = np.max(np.abs(rb['xx'] / xx - 1.0))
+    assert err_b <= 1e-11 and err_b <= rho + 1e-13                       # exact to FP64 noise, inside the certified bound
+    np.testing.assert_allclose(rb['xx'], ra['xx'], rtol=2e-11)
+    np.testing.assert_allclose(rb['ps'], ra['ps'], rtol=1e-8, atol=1e-300)
+    ctx.invalidate_snps()
