@@ -354,6 +354,9 @@ int mmg_destroy(mmg_ctx* ctx) {
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->kev0);
     cudaEventDestroy(ctx->kev1);
+    if (ctx->ov0) cudaEventDestroy(ctx->ov0);
+    if (ctx->ov1) cudaEventDestroy(ctx->ov1);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MMG_OK;
@@ -967,7 +970,6 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
         const int64_t words = cnt * (p2_ld >> 2);
         unpack2_kernel<<<(unsigned)((words + 255) / 256), 256, 0, src->stream2>>>(ctx->stage_dev[sl], p2_ld, ctx->snps + (snp_begin + s0) * ctx->pitch,
                                                                                 ctx->pitch, cnt);
-        ctx->launches += 1;
         MMG_TRY(launch_check(ctx, "unpack2_kernel"));
         MMG_CUDA(ctx, cudaEventRecord(src->slot_free[sl], src->stream2));
         MMG_CUDA(ctx, cudaEventRecord(src->done[(size_t)ci], src->stream2));
@@ -1696,9 +1698,49 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     else MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<double> escale((size_t)T), bscale((size_t)T), errA((size_t)T, 0.0);
+    // linear pre-pass: x.v_t, sum_j A_jj x_j^2 and ||x||_1 of every SNP in range, one stream over the genotypes.  When the rotation
+    // is at hand, v_t = R_t'y~_t and diag(A_t) = column sums of squares of R_t are formed first and the pre-pass runs on a side
+    // stream underneath the n^3 product A = R'R (FP64 / HBM work beside int8 tensor work); MMG_SCAN_OVERLAP=0 serialises them.
+    DevBuf pre;
+    MMG_CUDA(ctx, pre.alloc(ctx->stream, (size_t)((2 * T + 1) * snp_count + (int64_t)T * n_padN) * sizeof(double)));
+    double* d_dg_pre = pre.as<double>();                        // first: read as double2 by the pre-pass (16-byte aligned)
+    double* p_xy = d_dg_pre + (int64_t)T * n_padN;
+    double* p_qd = p_xy + (int64_t)T * snp_count;
+    double* p_a1 = p_qd + (int64_t)T * snp_count;
+    const int pre_rows_per_block = 8 * PRE_ROWS;
+    const unsigned pre_grid = (unsigned)((snp_count + pre_rows_per_block - 1) / pre_rows_per_block);
+    bool pre_launched = false;
+    struct SideJoin {                      // an early error return must not release `pre` under a running side-stream kernel
+        cudaStream_t s = nullptr;
+        ~SideJoin() { if (s) cudaStreamSynchronize(s); }
+    } side_join;
+    if (!A_given && env_int("MMG_SCAN_OVERLAP", 1)) {
+        if (!ctx->stream2) {
+            MMG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+            MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov0, cudaEventDisableTiming));
+            MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov1, cudaEventDisableTiming));
+        }
+        MMG_CUDA(ctx, cudaMemsetAsync(d_dg_pre, 0, (size_t)T * n_padN * sizeof(double), ctx->stream));
+        const double one = 1.0, zero = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const MmgMat* R = Rs[t];
+            MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)R->rows, &one, R->d, (int)n, d_y + (int64_t)t * n_out, 1, &zero,
+                                        d_v + (int64_t)t * n_padN, 1));
+            col_sumsq_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(R->d, n, (int)R->rows, (int)n, d_dg_pre + (int64_t)t * n_padN);
+            MMG_TRY(launch_check(ctx, "col_sumsq_kernel"));
+        }
+        MMG_CUDA(ctx, cudaEventRecord(ctx->ov0, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ov0, 0));
+        snp_prepass_kernel<PRE_ROWS, 4, 4><<<pre_grid, 256, 0, ctx->stream2>>>(ctx->snps, ctx->pitch, snp_begin, snp_count, T, d_v, d_dg_pre, n_padN, p_xy,
+                                                                            p_qd, p_a1, snp_count);
+        MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
+        side_join.s = ctx->stream2;
+        MMG_CUDA(ctx, cudaEventRecord(ctx->ov1, ctx->stream2));
+        pre_launched = true;
+    }
     for (int t = 0; t < T; ++t) {
         int E = 0;
-        MMG_TRY(quad_prepare(ctx, A_given ? nullptr : Rs[t], d_y + (int64_t)t * n_out, A_given ? A_given->d : nullptr, A.as<double>(), lda_work,
+        MMG_TRY(quad_prepare(ctx, A_given ? nullptr : Rs[t], pre_launched ? nullptr : d_y + (int64_t)t * n_out, A_given ? A_given->d : nullptr, A.as<double>(), lda_work,
                              d_amax, S_alloc, Bq.as<int8_t>() + (int64_t)t * S_alloc * plane, n_padN, ldq, d_v + (int64_t)t * n_padN,
                              d_dg + (int64_t)t * n_padN, &E, &errA[(size_t)t]));
         escale[t] = ldexp(1.0, E);
@@ -1716,22 +1758,18 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     ep.rho_max = d_rho;
     ep.v_stride = n_padN;
     ep.h0_rss = d_h0;
-    // linear pre-pass: x.v_t, sum_j A_jj x_j^2 and ||x||_1 of every SNP in range, one HBM-rate stream over the genotypes
-    DevBuf pre;
-    MMG_CUDA(ctx, pre.alloc(ctx->stream, (size_t)(2 * T + 1) * snp_count * sizeof(double)));
-    {
-        double* p_xy = pre.as<double>();
-        double* p_qd = p_xy + (int64_t)T * snp_count;
-        double* p_a1 = p_qd + (int64_t)T * snp_count;
-        const int rows_per_block = 8 * PRE_ROWS;
-        snp_prepass_kernel<PRE_ROWS, 4, 4><<<(unsigned)((snp_count + rows_per_block - 1) / rows_per_block), 256, 0, ctx->stream>>>(
-            ctx->snps, ctx->pitch, snp_begin, snp_count, T, d_v, d_dg, n_padN, p_xy, p_qd, p_a1, snp_count);
+    if (pre_launched) {
+        MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ov1, 0));        // join the side stream
+        side_join.s = nullptr;
+    } else {
+        snp_prepass_kernel<PRE_ROWS, 4, 4><<<pre_grid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin, snp_count, T, d_v, d_dg, n_padN, p_xy, p_qd,
+                                                                           p_a1, snp_count);
         MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
-        ep.pre_xy = p_xy;
-        ep.pre_qd = p_qd;
-        ep.pre_a1 = p_a1;
-        ep.pre_stride = snp_count;
     }
+    ep.pre_xy = p_xy;
+    ep.pre_qd = p_qd;
+    ep.pre_a1 = p_a1;
+    ep.pre_stride = snp_count;
     ep.n_p = n_p;
     ep.lbeta = lbeta;
 

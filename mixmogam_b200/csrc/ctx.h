@@ -31,6 +31,8 @@ struct mmg_ctx {
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, kev0 = nullptr, kev1 = nullptr;
+    cudaStream_t stream2 = nullptr;    // side stream (created on first use): the scan's linear pre-pass underneath the R'R product
+    cudaEvent_t ov0 = nullptr, ov1 = nullptr;
     std::string err;
     std::map<int64_t, MmgMat> mats;
     int64_t next_mat = 1;

@@ -375,6 +375,27 @@ struct OzakiEpi {
     }
 };
 
+// out[i] = sum_k R[k][i]^2 = diag(R'R) of the row-major [rows x cols] matrix (deterministic: fixed split of k over the 8 warps)
+__global__ void __launch_bounds__(256) col_sumsq_kernel(const double* __restrict__ R, int64_t ld, int rows, int cols, double* __restrict__ out) {
+    __shared__ double part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    double s = 0.0;
+    if (i < cols)
+        for (int k = ty; k < rows; k += 8) {
+            const double r = R[(int64_t)k * ld + i];
+            s = fma(r, r, s);
+        }
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < cols) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][tx];
+        out[i] = t;
+    }
+}
+
 // max |W| over a row-major [rows x cols] matrix -> bits of a non-negative double
 __global__ void mat_amax_kernel(const double* __restrict__ W, int64_t ld, int rows, int cols, unsigned long long* __restrict__ amax_bits) {
     const int r = blockIdx.y;
