@@ -382,7 +382,7 @@ def main():
             int8_peak = 2.0 * bf16                                       # int8 tcgen05 rate = 2 x bf16 (same pipe, K=32 vs 16)
             # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu capture of this very configuration
             # (profiles/r01_ncu_full_scan_quad_1m.txt: CTA-pair schedule, 4 planes); null for any other shape
-            traffic = 67002602000 + 60958720 if (n, m, world, S) == (10000, 1000000, 1, 4) and not os.environ.get('MMG_SCAN_SCHED') else None
+            traffic = 66381656000 + 170236160 if (n, m, world, S) == (10000, 1000000, 1, 4) and not os.environ.get('MMG_SCAN_SCHED') else None
             roof = {'bound': 'tensor', 'kernel': 'tc_gemm_i8_kernel<QuadEpi>' if os.environ.get('MMG_SCAN_SCHED') == 'table' else 'scan_quad_kernel', 'achieved': exec_ops / scan_s / 1e12,
                     'peak': int8_peak, 'unit': 'TFLOP/s', 'frac': exec_ops / scan_s / 1e12 / int8_peak, 'traffic': traffic,
                     'algorithmic_bytes': float(m_loc) * n + 8.0 * m_loc, 'int8_issue_rate_measured': imma_peak,
