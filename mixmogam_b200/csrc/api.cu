@@ -1480,13 +1480,34 @@ static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_work, int64_t
     MMG_CUDA(ctx, cudaMemsetAsync(A_work, 0, (size_t)n_padM * n_padM * sizeof(double), ctx->stream));
     // tile table: row-tile pairs (im, im + 1) x column tile jn that meet the lower triangle (rows >= columns), 28 (p, q) planes each
     const int tiles_n = (int)(n_padM / TC_BN), tiles_m = (int)(n_padM / TC_BM), KB = (int)(op_pitch / TC_BK);
+    // Entry order = order in which the co-resident clusters pick the output tiles up.  The operands are streamed from L2 / HBM
+    // by every tile (79 K-blocks only), so the clusters of one wave should share them: the lower-triangular (row-pair, column
+    // tile) grid is walked in blocks of 9 x 8 (72 ~ the 74 co-resident clusters), whose operand rows for one plane pair are
+    // 9 x 2.6 + 8 x 2.6 = 44 MB -- L2 resident -- instead of row by row (a whole 103 MB plane per tile step).
     std::vector<TcTile> tiles;
+    std::vector<std::pair<int, int>> order;                     // (jn, im)
+    {
+        const int BI = std::max(1, env_int("MMG_OZAKI_BLOCK_I", 9)), BJ = std::max(1, env_int("MMG_OZAKI_BLOCK_J", 8));
+        const int pairs_m = tiles_m / 2;
+        for (int bi = 0; bi < pairs_m; bi += BI)
+            for (int bj = 0; bj < tiles_n; bj += BJ)
+                for (int ip = bi; ip < std::min(pairs_m, bi + BI); ++ip)
+                    for (int jn = bj; jn < std::min(tiles_n, bj + BJ); ++jn)
+                        if (ip >= jn) order.emplace_back(jn, 2 * ip);
+    }
     int entries = 0, per_entry = 0;
-    for (int jn = 0; jn < tiles_n; ++jn)
-        for (int im = 2 * jn; im < tiles_m; im += 2) {
+    const bool chain = env_int("MMG_OZAKI_CHAIN", 1) != 0 && (double)OZ_LEVELS * (double)n_out * 16384.0 < 2147483647.0;
+    for (const auto& ji : order) {
+        const int jn = ji.first, im = ji.second;
+        {
+            // level by level (p + q = lv share the weight 2^2F 256^-(lv+2)): the lv + 1 plane pairs of a level are CHAINED into one
+            // int32 accumulator (7 n_out 128^2 < 2^31), so an output tile is read-modify-written 7 times, not 28 -- the FP64
+            // read-modify-write of the epilogue (a row per thread, 32 sectors per access) was what bounded this kernel
             per_entry = 0;
-            for (int p = 0; p < OZ_PLANES; ++p)
-                for (int q = 0; p + q < OZ_LEVELS && q < OZ_PLANES; ++q) {
+            for (int lv = 0; lv < OZ_LEVELS; ++lv)
+                for (int p = 0; p <= lv; ++p) {
+                    const int q = lv - p;
+                    if (p >= OZ_PLANES || q >= OZ_PLANES) continue;
                     TcTile tl{};
                     tl.m0 = (int)((int64_t)p * n_padM + (int64_t)im * TC_BM);
                     tl.n0 = (int)((int64_t)q * n_padM + (int64_t)jn * TC_BN);
@@ -1494,11 +1515,13 @@ static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_work, int64_t
                     tl.kb1 = KB;
                     tl.aux0 = p;
                     tl.aux1 = q;
+                    tl.flags = (p < lv && chain) ? TC_TILE_CHAIN : 0;       // the pair (lv, 0) ends the chain of its level
                     tiles.push_back(tl);
                     ++per_entry;
                 }
             ++entries;
         }
+    }
     MMG_TRY(ensure_tiles(ctx, tiles));
     CUtensorMap tmA, tmB;
     MMG_TRY(make_tmap_u8(ctx, &tmA, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BM));

@@ -34,8 +34,9 @@ struct TcTile {
     int aux0;  // epilogue-defined
     int aux1;
     int col0;  // epilogue-defined column offset
-    int pad_;
+    int flags; // TC_TILE_CHAIN: keep accumulating into the same TMEM accumulator with the NEXT tile (no hand-over, no epilogue)
 };
+constexpr int TC_TILE_CHAIN = 1;
 
 // CS = cluster size (1, 2 or 4).  With CS > 1 the CS CTAs of a cluster walk the same tile sequence in lockstep
 // on CS different 128-row A blocks that share the B tile: each CTA fetches 1/CS of the B rows and TMA-multicasts
@@ -134,11 +135,14 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            bool chained = false;                  // the previous tile left its sums in this accumulator (TC_TILE_CHAIN)
             for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
                 for (int ti = 0; ti < tiles_per_group; ++ti) {
                     const TcTile t = tiles[(int64_t)cg * table_stride + ti];
-                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                    tc_fence_after();
+                    if (!chained) {
+                        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                        tc_fence_after();
+                    }
                     const uint32_t d_tmem = tmem_base + acc * TC_BN;
                     for (int kb = t.kb0; kb < t.kb1; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
@@ -151,13 +155,15 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                                 // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
                                 umma_i8(d_tmem, da + (uint64_t)(k * (TC_UMMA_K >> 4)), db + (uint64_t)(k * (TC_UMMA_K >> 4)),
-                                        idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+                                        idesc, (chained || kb > t.kb0 || k > 0) ? 1u : 0u);
                             }
                             // frees the smem slot (in every CTA of the cluster) when these MMAs retire
                             if (CS == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], kMask);
                         }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
+                    chained = (t.flags & TC_TILE_CHAIN) != 0;
+                    if (chained) continue;                           // the next tile adds to the same accumulator
                     if (elect_one()) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
                     if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
                 }
@@ -177,6 +183,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (live) epi.begin_group(ep, g, row);
             for (int ti = 0; ti < tiles_per_group; ++ti) {
                 TcTile t = tiles[(int64_t)cg * table_stride + ti];
+                if (t.flags & TC_TILE_CHAIN) continue;               // folded into the tile that ends the chain
                 t.m0 += g * group_m_step + crank * rank_m_step;
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
