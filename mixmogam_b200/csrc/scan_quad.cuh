@@ -21,10 +21,15 @@
 // TMA-multicast to the CS CTAs of a cluster, which hold CS different SNP blocks), and all CTAs sweep the same digit
 // stream in near lockstep so HBM sees it about once per wave.
 //
-// PAIR = true runs the MMA as a CTA pair (tcgen05.mma.cta_group::2, M = 256 SNPs over the two SMs of a TPC): each CTA
-// stages its own 128-SNP genotype panel and HALF of every digit tile (128 of the 256 columns), the leader CTA issues
-// one MMA for both.  Shared-memory traffic per SM and K block drops from 32 KB written + 48 KB read to 16 + 32 KB,
-// which is what the single-CTA form is bound by (128 B/clk/SM), and L2 -> SM traffic halves without multicast.
+// PAIR = true (the default schedule) runs the MMA as a CTA pair (tcgen05.mma.cta_group::2, M = 256 SNPs over the two SMs
+// of a TPC): each CTA stages its own 128-SNP genotype panel and HALF of every digit tile (128 of the 256 columns), the
+// leader CTA issues one MMA for both.  Shared-memory traffic per SM and K block drops from 32 KB written + 48 KB read to
+// 16 + 32 KB and the L2 -> SM traffic halves without multicast (the single-CTA form sits on the L2 output cap).
+//
+// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warp 2 L2 prefetcher (walks the digit
+// stream `prefetch` K-blocks ahead of the producer's published progress), warps 3..10 epilogue (two per TMEM lane quadrant).
+// The linear terms of the statistic (x.v, the FP64 diagonal of the quadratic form, ||x||_1) come from snp_prepass_kernel
+// (scan_tc.cuh): the epilogue only drains accumulators.
 #pragma once
 #include "scan_tc.cuh"
 
@@ -67,41 +72,6 @@ struct QuadSmem {
     static_assert(kBars + 1 <= 64, "barrier block");
     static constexpr int kBytes = kABytes + kBBytes + 1024 /*align slack*/ + 512 /*barriers + tmem slot*/ + 1024 /*q, xy exchange*/;
     static_assert(kBytes <= 232448, "shared memory budget (227 KB)");
-};
-
-// position in the digit-plane stream of one group: (t, kp, jb, k, i) -> B row / K block; used by the L2 prefetcher
-template <int PKB, int BN>
-struct QuadIter {
-    static constexpr int kKbPerTile = BN / TC_BK;      // K blocks (of 128 individuals) per column tile
-    int t, kp, jb, k, i, kbase, nka, nkb;
-    __device__ __forceinline__ void set_jb(const QuadShape& sh) {
-        nkb = min(nka, kKbPerTile * (jb + 1) - kbase);
-        k = 0;
-        i = 0;
-    }
-    __device__ __forceinline__ void set_panel(const QuadShape& sh) {
-        kbase = kp * PKB;
-        nka = min(PKB, sh.kb_total - kbase);
-        jb = kbase / kKbPerTile;
-        set_jb(sh);
-    }
-    __device__ __forceinline__ void reset(const QuadShape& sh) {
-        t = 0;
-        kp = 0;
-        set_panel(sh);
-    }
-    __device__ __forceinline__ void advance(const QuadShape& sh) {
-        if (++i < nkb) return;
-        i = 0;
-        if (++k < sh.S) return;
-        if (++jb < sh.tiles_n) { set_jb(sh); return; }
-        if ((kp + 1) * PKB < sh.kb_total) { ++kp; set_panel(sh); return; }
-        kp = 0;
-        if (++t >= sh.T) t = 0;         // the next group sweeps the same stream again
-        set_panel(sh);
-    }
-    __device__ __forceinline__ int row(const QuadShape& sh) const { return (t * sh.S_stride + k) * sh.n_padN + jb * BN; }
-    __device__ __forceinline__ int kb() const { return kbase + i; }
 };
 
 constexpr int QP_EPI_WARPS = 8;
