@@ -5,6 +5,7 @@
 //
 // Compiled by g++ (not nvcc): AVX2 through a target attribute with a runtime CPU check, scalar otherwise.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -112,7 +113,13 @@ extern "C" int mmg_host_pack2(const int8_t* src, int64_t rows, int64_t n, int64_
     return (all & ~3u) ? 1 : 0;
 }
 
+// host threads one process should use: the cores of the box shared between the ranks torchrun started on it (LOCAL_WORLD_SIZE)
 extern "C" int mmg_host_threads_default() {
-    const unsigned hc = std::thread::hardware_concurrency();
-    return (int)(hc == 0 ? 4 : (hc > 32 ? 32 : hc));
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc == 0) hc = 4;
+    const char* lws = std::getenv("LOCAL_WORLD_SIZE");
+    const int ranks = lws ? std::atoi(lws) : 1;
+    if (ranks > 1) hc = hc / (unsigned)ranks;
+    if (hc < 1) hc = 1;
+    return (int)(hc > 32 ? 32 : hc);
 }
