@@ -944,7 +944,8 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     // returns MMG_OK with staged[ci] still 0 when the chunk holds a code outside 0..3 (the caller then takes the raw lane)
     auto queue_packed = [&](int64_t ci) -> int {
         const int64_t s0 = ci * chunk, cnt = chunk_rows(ci);
-        if (ctx->stage_bytes < chunk * p2_ld) {
+        const int64_t stage_need = std::min(chunk, snp_count) * p2_ld;       // one (largest) chunk of this call
+        if (ctx->stage_bytes < stage_need) {
             for (int i = 0; i < 2; ++i) {
                 if (ctx->stage_host[i]) cudaFreeHost(ctx->stage_host[i]);
                 cudaFree(ctx->stage_dev[i]);
@@ -952,10 +953,10 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
             }
             ctx->stage_bytes = 0;
             for (int i = 0; i < 2; ++i) {
-                MMG_CUDA(ctx, cudaHostAlloc((void**)&ctx->stage_host[i], (size_t)(chunk * p2_ld), cudaHostAllocDefault));
-                MMG_CUDA(ctx, cudaMalloc((void**)&ctx->stage_dev[i], (size_t)(chunk * p2_ld)));
+                MMG_CUDA(ctx, cudaHostAlloc((void**)&ctx->stage_host[i], (size_t)stage_need, cudaHostAllocDefault));
+                MMG_CUDA(ctx, cudaMalloc((void**)&ctx->stage_dev[i], (size_t)stage_need));
             }
-            ctx->stage_bytes = chunk * p2_ld;
+            ctx->stage_bytes = stage_need;
         }
         const int sl = src->next_slot;
         if (src->slot_used[sl]) MMG_CUDA(ctx, cudaEventSynchronize(src->slot_free[sl]));
