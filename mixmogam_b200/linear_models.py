@@ -115,6 +115,24 @@ class LinearModel(object):
     def _invalidate(self):
         pass
 
+    def fast_f_test(self, snps, verbose=True, Z=None, with_betas=False, ctx=None, scan_impl='auto'):
+        """
+        LM implementation, single SNPs (linear_models.py:196-257): the EMMAX scan without a kinship -- the rotation is
+        M = I - QQ' alone (:215-218), the per-SNP least squares, F and p are the same fused kernel
+        (_emmax_f_test_ with H = I).  Z is accepted and ignored, as in the reference.  Returns the reference's dict:
+        ps, f_stats, rss, var_perc, h0_rss, h0_betas (+ betas with with_betas=True).
+        """
+        ctx = ctx or getattr(self, 'ctx', None) or _lib.get_context()
+        mdl = LinearMixedModel(self.Y.reshape(-1), ctx=ctx, scan_impl=getattr(self, 'scan_impl', scan_impl))
+        mdl.X = self.X
+        mdl.p = self.p
+        eye = ctx.matrix(self.n, self.n)            # zero-filled on the device
+        ctx.add_diag(eye, 1.0)
+        try:
+            return mdl._emmax_f_test_(snps, eye, verbose=verbose, with_betas=with_betas, emma_num=0)
+        finally:
+            eye.free()
+
 
 class EigenDict(dict):
     """{'values', 'vectors'} as the reference returns (linear_models.py:596,615), eigenvectors as ROWS.

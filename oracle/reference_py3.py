@@ -196,6 +196,87 @@ def _residue_value(rss):
     return v
 
 
+class LinearModel(object):
+    """linear_models.py:81-130 and 196-257: the plain linear model and its SNP scan `fast_f_test` -- the EMMAX scan's
+    sibling with M = I - QQ' and no kinship.  Y and X are float64 here (:90-91, unlike the mixed
+    model's float32 :563-565); `dtype` is the reference's hard-coded 'single' of :202."""
+
+    def __init__(self, Y=None, dtype='single'):
+        self.dtype = _dt(dtype)
+        self.n = len(Y)
+        self.Y = np.array(Y, dtype=np.float64).reshape(self.n, 1)              # :90  sp.matrix(Y).T
+        self.X = np.ones((self.n, 1))                                          # :91
+        self.p = 1
+        self.beta_est = None
+        self.cofactors = []
+
+    def add_factor(self, x, lin_depend_thres=1e-8):
+        """linear_models.py:98-113."""
+        new_x = np.array(x)
+        new_x.shape = len(x)
+        (beta, rss, rank, sigma) = linalg.lstsq(self.X, new_x)
+        if float(np.asarray(rss).reshape(-1)[0] if np.asarray(rss).size else 0.0) < lin_depend_thres:
+            warnings.warn('A factor was found to be linearly dependent on the factors already in the X matrix.  Hence skipping it!')
+            return False
+        new_x.shape = (self.n, 1)
+        self.X = np.hstack([self.X, new_x])
+        self.cofactors.append(x)
+        self.p += 1
+        return True
+
+    def fast_f_test(self, snps, verbose=False, Z=None, with_betas=False):
+        """linear_models.py:196-257 (Z is accepted and ignored there too)."""
+        dtype = self.dtype                                                     # :202
+        q = 1
+        p = len(self.X.T) + q
+        n = self.n
+        n_p = n - p
+        num_snps = len(snps)
+
+        h0_X = np.array(self.X, dtype=dtype)                                   # :209
+        (h0_betas, h0_rss, h0_rank, h0_s) = linalg.lstsq(h0_X, self.Y)         # :210
+        Y = np.array(self.Y - h0_X @ h0_betas, dtype=dtype)                    # :211
+        h0_betas = list(map(float, list(np.asarray(h0_betas).reshape(-1))))
+
+        if not with_betas:
+            (Q, R) = linalg.qr(h0_X, mode='economic')                          # :215 (qr_decomp, :68-75)
+            Q = np.array(Q, dtype=dtype)
+            Q2 = Q @ Q.T
+            M = np.array(np.eye(n) - Q2, dtype=dtype)                          # :218
+        else:
+            betas_list = [h0_betas] * num_snps
+
+        rss_list = np.repeat(h0_rss, num_snps)                                 # float64 (h0_rss is)
+        chunk_size = len(Y)
+        for i in range(0, len(snps), chunk_size):
+            snps_chunk = np.array(snps[i:i + chunk_size])                      # :225  integer genotypes
+            if with_betas:
+                Xs = snps_chunk
+            else:
+                Xs = np.array(snps_chunk, dtype=dtype) @ M                     # :229
+            for j in range(len(Xs)):
+                X_j = Xs[j:j + 1]
+                if with_betas:
+                    (betas, rss, rk, sigma) = linalg.lstsq(np.hstack([h0_X, X_j.T]), Y)     # :232
+                    if _residue_value(rss) is None:                            # :234 `if not rss: continue`
+                        continue
+                    betas_list[i + j] = list(map(float, list(np.asarray(betas).reshape(-1))))
+                else:
+                    (betas, rss, rk, sigma) = linalg.lstsq(X_j.T, Y)           # :240
+                rss_list[i + j] = np.asarray(rss).reshape(-1)[0]               # :241
+
+        rss_ratio = h0_rss / rss_list
+        var_perc = 1 - 1 / rss_ratio
+        f_stats = (rss_ratio - 1) * n_p / float(q)
+        p_vals = stats.f.sf(f_stats, q, n_p)
+
+        res_d = {'ps': p_vals, 'f_stats': f_stats, 'rss': rss_list, 'var_perc': var_perc,
+                 'h0_rss': h0_rss, 'h0_betas': h0_betas}
+        if with_betas:
+            res_d['betas'] = betas_list
+        return res_d
+
+
 class LinearMixedModel(object):
     """linear_models.py:554-1380 (EMMAX subset)."""
 

@@ -78,9 +78,26 @@ def h5_file(chroms, y):
     return f
 
 
+def fast_f_test_golden(lm):
+    """LinearModel.fast_f_test (linear_models.py:196-257): the OLS sibling of the EMMAX scan."""
+    e = g('emmax_diploid_n400.npz')
+    snps, y, cof = e['snps'], e['y'], e['cofactor']
+    out = {}
+    out.update(scan_outputs('', quiet(lm.LinearModel(list(y)).fast_f_test, list(snps))))
+    m = lm.LinearModel(list(y))
+    m.add_factor(cof)
+    out.update(scan_outputs('cof_', quiet(m.fast_f_test, list(snps[:800]))))
+    m = lm.LinearModel(list(y))
+    m.add_factor(cof)
+    out.update(scan_outputs('wb_', quiet(m.fast_f_test, list(snps[:300]), with_betas=True)))
+    save('ref_fast_f_test_n400.npz', **out)
+
+
 def main():
     kin = py2shim.load('kinship')
     lm = py2shim.load('linear_models')
+    if sys.argv[1:] == ['fast_f_test']:
+        return fast_f_test_golden(lm)
 
     # ---- kinship.py:14-100, all three estimators, literal loops -------------------------------------
     xb = g('ibs_binary_n37.npz')['snps']
@@ -183,6 +200,7 @@ def main():
     quiet(hd2.calculate_ibd_kinship, 'in')
     out['ibd_kinship_nofilter'] = np.asarray(files2['in']['kinship'].data, dtype=np.float64)
     save('ref_hdf5_n198.npz', **out)
+    fast_f_test_golden(lm)
 
 
 if __name__ == '__main__':

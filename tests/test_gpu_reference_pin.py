@@ -12,7 +12,7 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import golden
+from conftest import golden, neglog10_rel_err
 
 pytestmark = pytest.mark.gpu
 warnings.simplefilter('ignore')
@@ -210,3 +210,40 @@ def test_hdf5_entry_points_vs_reference_run(ctx):
     f2 = {'genot_data': gg, 'indiv_data': {'indiv_ids': np.arange(198), 'phenotypes': ref['y']}}
     hdf5_data.calculate_ibd_kinship(f2)
     np.testing.assert_allclose(f2['kinship'], ref['ibd_kinship_nofilter'], rtol=2e-4, atol=2e-6)
+
+
+def test_fast_f_test_vs_oracle_and_reference_run(ctx):
+    """LinearModel.fast_f_test (linear_models.py:196-257): the scan with M = I - QQ' and no kinship, against the
+    float64 oracle at the north-star tolerance and against the reference's own float32 run; plain, with a cofactor
+    (SNP 17 is collinear with it: excluded, the reference's value there is noise) and with_betas."""
+    from mixmogam_b200 import linear_models as lm
+    from oracle import reference_py3 as o
+    ref = golden('ref_fast_f_test_n400.npz')
+    e = golden('emmax_diploid_n400.npz')
+    snps, y, cof = e['snps'], e['y'], e['cofactor']
+    ctx.invalidate_snps()
+    r = lm.LinearModel(y).fast_f_test(snps)
+    ro = o.LinearModel(list(y), dtype='double').fast_f_test(list(snps))
+    assert neglog10_rel_err(r['ps'], ro['ps']) < 1e-6
+    np.testing.assert_allclose(r['rss'], ro['rss'], rtol=1e-9)
+    np.testing.assert_allclose(np.asarray(r['h0_rss']).reshape(-1), np.asarray(ro['h0_rss']).reshape(-1), rtol=1e-12)
+    assert np.max(np.abs(np.log10(r['ps']) - np.log10(ref['ps']))) < 1e-2
+    assert np.array_equal(np.argsort(r['ps'], kind='stable')[:20], np.argsort(ref['ps'], kind='stable')[:20])
+    ok = np.arange(800) != 17
+    m = lm.LinearModel(y)
+    m.add_factor(cof)
+    r2 = m.fast_f_test(snps[:800])
+    mo = o.LinearModel(list(y), dtype='double')
+    mo.add_factor(cof)
+    ro2 = mo.fast_f_test(list(snps[:800]))
+    assert neglog10_rel_err(r2['ps'][ok], ro2['ps'][ok]) < 1e-6
+    assert np.max(np.abs(np.log10(r2['ps'][ok]) - np.log10(ref['cof_ps'][ok]))) < 1e-2
+    np.testing.assert_allclose(r2['h0_betas'], ro2['h0_betas'], rtol=1e-9, atol=1e-12)
+    ok3 = np.arange(300) != 17
+    r3 = m.fast_f_test(snps[:300], with_betas=True)
+    ro3 = mo.fast_f_test(list(snps[:300]), with_betas=True)
+    assert neglog10_rel_err(r3['ps'][ok3], ro3['ps'][ok3]) < 1e-6
+    b_gpu = np.array([b for b, k in zip(r3['betas'], ok3) if k])          # the collinear SNP keeps the 2 null betas (ragged list)
+    b_ora = np.array([b for b, k in zip(ro3['betas'], ok3) if k])
+    np.testing.assert_allclose(b_gpu, b_ora, rtol=1e-6, atol=1e-9)
+    ctx.invalidate_snps()

@@ -94,6 +94,32 @@ def test_emmax_diploid_cofactor_and_Z_bit_exact_vs_reference_run():
     assert_scan_bit_exact(rz, ref, 'z_')
 
 
+def test_fast_f_test_bit_exact_vs_reference_run():
+    """LinearModel.fast_f_test (linear_models.py:196-257), the OLS sibling of the EMMAX scan: plain, with a cofactor, and
+    with_betas (where SNP 17 is collinear with the cofactor-augmented design and the reference stores a NaN residue)."""
+    ref = golden('ref_fast_f_test_n400.npz')
+    e = golden('emmax_diploid_n400.npz')
+    snps, y, cof = e['snps'], e['y'], e['cofactor']
+    keys = ('ps', 'f_stats', 'rss', 'var_perc', 'h0_rss', 'h0_betas')
+
+    def same(r, prefix, extra=()):
+        for k in keys + tuple(extra):
+            a = np.asarray(r[k], dtype=np.float64).reshape(-1)
+            b = np.asarray(ref[prefix + k], dtype=np.float64).reshape(-1)
+            assert np.array_equal(a, b, equal_nan=True), prefix + k
+
+    same(o.LinearModel(list(y)).fast_f_test(list(snps)), '')
+    m = o.LinearModel(list(y))
+    m.add_factor(cof)
+    same(m.fast_f_test(list(snps[:800])), 'cof_')
+    m = o.LinearModel(list(y))
+    m.add_factor(cof)
+    same(m.fast_f_test(list(snps[:300]), with_betas=True), 'wb_', extra=('betas',))
+    # the float64 mode the GPU path is held to stays within the reference's float32 noise
+    rd = o.LinearModel(list(y), dtype='double').fast_f_test(list(snps))
+    assert np.max(np.abs(np.log10(rd['ps']) - np.log10(ref['ps']))) < 1e-2
+
+
 def test_permutations_bit_exact_vs_reference_run():
     ref = golden('ref_perm_n120.npz')
     e = golden('perm_n120.npz')
