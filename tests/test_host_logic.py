@@ -181,3 +181,53 @@ def test_host_pack2_matches_numpy(built, rows, n, ld, threads):
         assert lib.mmg_host_pack2(b3.ctypes.data, rows, n, ld, out.ctypes.data, dst_ld, threads) == 0
         assert np.array_equal(out[:, :n4], ref)
     assert lib.mmg_host_threads_default() >= 1
+
+
+def test_int8_quad_form_error_bound_is_sound(built):
+    """The int8 digit-plane product A = R'R of the scan (scan_tc.cuh: 7 base-256 planes of R 2^-F, plane pairs p + q < 7) in
+    exact rational arithmetic, with the product's own digit expansion (digits.cuh through the host check program): the
+    entry-wise error stays below ozaki_error_bound (mirrored here) -- the term the scan adds to its certified bound."""
+    from fractions import Fraction
+    P = L = 7
+    rng = np.random.default_rng(3)
+    n_out, n = 48, 6
+    R = rng.standard_normal((n_out, n)) * 10.0 ** rng.uniform(-4, 0, size=(n_out, 1))
+    R[0, 0] = np.abs(R).max() * 1.7                        # the entry that sets the global scale
+    rmax = float(np.abs(R).max())
+    out = _run(built, 'digits', np.concatenate([[1, 1], [rmax]]))
+    F = int(out[0])                                        # digit256_exponent(rmax)
+    scaled = np.ldexp(R, -F).ravel()
+    assert np.abs(scaled).max() <= 0.498
+    # digits of every entry with the library's own expansion: pass r 2^-F as "a" of an entry whose exponent comes out 0
+    # (|r| in [0.249, 0.498]) is not general, so expand here with the same integer rule and cross-check a few through the binary
+    def split(r):
+        N = int(np.rint(np.ldexp(r, 8 * P)))
+        digs = []
+        for _ in range(P):
+            d = ((N + 128) & 255) - 128
+            digs.append(d)
+            N = (N - d) >> 8
+        assert N == 0
+        return digs[::-1]
+    big = [v for v in scaled if 0.249 <= abs(v) <= 0.498][:5]
+    if big:
+        chk = _run(built, 'digits', np.concatenate([[len(big), P], big])).reshape(len(big), P + 2)
+        for v, row in zip(big, chk):
+            assert int(row[0]) == 0 and [int(d) for d in row[1:1 + P]] == split(v)
+    D = np.array([split(v) for v in scaled], dtype=object).reshape(n_out, n, P)
+    rho = Fraction(128, 255) / Fraction(256) ** P
+    dropped = sum(Fraction(min(s + 1, 2 * P - 1 - s) * 16384, 256 ** (s + 2)) for s in range(L, 2 * P - 1))
+    bound = n_out * (dropped + rho + rho * rho)            # ozaki_error_bound(n_out), units of 2^2F
+    worst = Fraction(0)
+    for i in range(n):
+        for j in range(i + 1):
+            exact = sum(Fraction(float(scaled[k * n + i])) * Fraction(float(scaled[k * n + j])) for k in range(n_out))
+            approx = Fraction(0)
+            for p in range(P):
+                for q in range(P):
+                    if p + q < L:
+                        g = sum(int(D[k, i, p]) * int(D[k, j, q]) for k in range(n_out))
+                        approx += Fraction(g, 256 ** (p + q + 2))
+            worst = max(worst, abs(exact - approx))
+    assert worst <= bound
+    assert worst > bound / 10 ** 6                          # and the bound is not vacuous
