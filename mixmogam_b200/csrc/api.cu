@@ -916,8 +916,7 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
                 }
     };
     double gram_ms = 0.0, pack_s = 0.0;
-    // host source: keep one chunk copy queued ahead of the one the Gram is waiting for (page-locked rows: fully asynchronous
-    // strided DMA at the PCIe rate; pageable rows: the driver stages them and the call blocks, the pipeline still overlaps)
+    // host source: the chunks are staged by the two lanes described at GramHostSource (raw DMA / 2-bit packed)
     const int64_t p2_ld = round_up((ctx->n + 3) / 4, 16);            // packed row: 2 bits per genotype
     const double pcie_rate = 1e9 * std::max(1, env_int("MMG_PCIE_GBS", 50));
     const int64_t n_chunks = (snp_count + chunk - 1) / chunk;
