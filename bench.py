@@ -361,6 +361,11 @@ def main():
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * t_e2e_max / args.steps,
                'stage_seconds_per_step': {k: v / args.steps for k, v in e2e_timers.items()},
                'h2d_lanes': dict(zip(('chunks_packed_2bit', 'chunks_raw', 'host_pack_gbs'), ctx.last_h2d_info()))}
+        # h2d_bytes_per_step is what the API is handed (the int8 genotype buffer); the packed lane puts a quarter of its
+        # chunks' bytes on the PCIe link, so the bytes that actually cross it are fewer
+        pk, rw, _ = ctx.last_h2d_info()
+        if pk + rw > 0:
+            e2e['h2d_pcie_bytes_per_step'] = int(m_loc * n * (rw + 0.25 * pk) / (pk + rw) + n * 8 * 2 * 2)
 
     if rank == 0:
         value = m * args.steps / t_res
