@@ -397,7 +397,9 @@ def main():
                     'frac_of_issue_rate': exec_ops / scan_s / 1e12 / imma_peak if imma_peak else None,
                     'pipe': 'int8 tcgen05 (TOP/s); peak = 2 x bf16 burst of %s' % ('MEASURED_PEAKS.json' if peaks else 'the fallback'),
                     'algorithmic_fp64_tflops': alg_flops / scan_s / 1e12, 'fp64_tensor_peak_measured': fp64_peak,
-                    'slices': S, 'certified_rel_bound_xx': rho, 'launch_ms': scan_s * 1e3}
+                    'slices': S, 'certified_rel_bound_xx': rho, 'launch_ms': scan_s * 1e3,
+                    'achieved_is': 'int8 ops the kernel executes (S planes x lower-triangular K ranges); the SURVEY 8d figure, '
+                                   '2 n^2 FP64 flops per SNP of the rotation it replaces, is algorithmic_fp64_tflops'}
         else:
             roof = {'bound': 'tensor', 'kernel': 'scan_dmma_kernel', 'achieved': alg_flops / scan_s / 1e12, 'peak': fp64_peak,
                     'unit': 'TFLOP/s', 'frac': alg_flops / scan_s / 1e12 / fp64_peak, 'traffic': None,
