@@ -231,3 +231,42 @@ def test_int8_quad_form_error_bound_is_sound(built):
             worst = max(worst, abs(exact - approx))
     assert worst <= bound
     assert worst > bound / 10 ** 6                          # and the bound is not vacuous
+
+
+def test_scan_truncation_bound_is_sound(built):
+    """The quadratic form of the int8 scan in exact rational arithmetic: x'Ax = sum_j A_jj x_j^2 + sum_j x_j sum_{i<j} 2 A_ji x_i
+    with B = 2A 2^-E (strictly lower triangle) cut into 6 base-256 digit planes (digits.cuh rule) and only the first S used:
+    the error never exceeds the bound the kernel certifies, (64/255) 256^-S 2^E ||x||_1^2 (scan_tc.cuh, api.cu set_bscale)."""
+    from fractions import Fraction
+    rng = np.random.default_rng(11)
+    n, planes = 24, 6
+    Rm = rng.standard_normal((n, n)) / np.sqrt(n)
+    A = Rm.T @ Rm
+    amax = max(abs(2 * A[j, i]) for j in range(n) for i in range(j))
+    E = int(_run(built, 'digits', np.array([1, 1, amax]))[0])          # digit256_exponent(amax)
+
+    def split(r):
+        N = int(np.rint(np.ldexp(r, 8 * planes)))
+        digs = []
+        for _ in range(planes):
+            d = ((N + 128) & 255) - 128
+            digs.append(d)
+            N = (N - d) >> 8
+        assert N == 0
+        return digs[::-1]
+
+    dig = {(j, i): split(float(np.ldexp(2 * A[j, i], -E))) for j in range(n) for i in range(j)}
+    two_E = Fraction(2) ** E
+    for trial in range(6):
+        x = rng.integers(0, 3, size=n) if trial else np.full(n, 2)
+        l1 = int(np.abs(x).sum())
+        exact = sum(Fraction(float(A[j, j])) * int(x[j]) ** 2 for j in range(n)) + \
+            sum(Fraction(float(2 * A[j, i])) * int(x[j]) * int(x[i]) for j in range(n) for i in range(j))
+        for S in range(1, planes + 1):
+            q = Fraction(0)
+            for k in range(S):
+                acc = sum(int(x[j]) * sum(dig[(j, i)][k] * int(x[i]) for i in range(j)) for j in range(n))   # what the MMA + epilogue sum
+                q += Fraction(acc, 256 ** (k + 1))
+            approx = sum(Fraction(float(A[j, j])) * int(x[j]) ** 2 for j in range(n)) + q * two_E
+            bound = Fraction(64, 255) / Fraction(256) ** S * two_E * l1 * l1
+            assert abs(approx - exact) <= bound, (trial, S)
