@@ -162,8 +162,9 @@ int mmg_reml_f64(mmg_ctx* ctx, const double* eig_vals, const double* sq_etas, in
  *     rss = h0_rss - xy[0]^2/xx (kept at h0_rss when xx <= 0, the `if rss:` of :1329)
  *     f = n_p * r2/(1-r2), r2 = xy[0]^2/(xx*h0_rss) ; p = F.sf(f, 1, n_p)   (:1345-1349)
  * impl: MMG_IMPL_DMMA  = FP64 tensor-core (mma.sync m8n8k4 f64) rotation fused with the reductions;
- *       MMG_IMPL_TCGEN05 = x'(R'R)x on int8 tcgen05 tensor cores: diagonal in FP64, off-diagonal as exact base-128
- *                          digit planes of R'R; the number of planes is chosen so that the certified truncation bound
+ *       MMG_IMPL_TCGEN05 = x'(R'R)x on int8 tcgen05 tensor cores: diagonal in FP64, off-diagonal as exact base-256
+ *                          digit planes of R'R (itself formed as exact int8 digit-plane products, or by FP64 dsyrk:
+ *                          MMG_QUAD_A); the number of planes is chosen so that the certified truncation bound
  *                          on x~.x~ is <= MMG_TC_TOL (1e-7) for every SNP (mmg_last_scan_info).
  * Outputs (host, length snp_count, any may be NULL): ps, f_stats, rss, var_perc, xx;
  * dots: [snp_count x nv]. */
