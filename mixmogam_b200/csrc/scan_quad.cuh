@@ -493,8 +493,11 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                             }
                             // |s_k| <= 32 columns x |acc| x |x|, |acc| <= 128 PKB K x |x| x 128 (base-256 digits): 2^5 2^20 2^3 = 2^28 at PKB = 8, |x| <= 8
-                            // (QS_MAX_ABS_GENOTYPE, enforced on the host): exact in int32
-                            const double qt = (double)s0 + (double)s1 + ((double)s2 + (double)s3);
+                            // (QS_MAX_ABS_GENOTYPE, enforced on the host): exact in int32, and so is the sum of the four chains
+                            // (< 2^30; 1.5 2^30 at PKB = 12).  ONE int -> double conversion per tile: the ncu source view of the
+                            // 1M-SNP scan showed a third of all warp stalls (stall_math) on the four conversions + three DADDs
+                            // that used to stand here
+                            const double qt = (double)((s0 + s1) + (s2 + s3));
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) {
