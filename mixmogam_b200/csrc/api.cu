@@ -175,9 +175,10 @@ static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMa
 }
 
 // Launch the genotype-stationary scan kernel (scan_quad.cuh): cluster CS, panel of PKB K-blocks, STAGES digit stages.
-template <int CS, int PKB, int STAGES, bool PAIR, int BN, int LDW = 16>
+template <int CS, int PKB, int STAGES, bool PAIR, int BN, int LDW = 16, bool TIMED = false>
 static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, QuadShape sh, const QuadEpi::Params& ep) {
-    auto kern = scan_quad_kernel<CS, PKB, STAGES, PAIR, BN, LDW>;
+    auto kern = scan_quad_kernel<CS, PKB, STAGES, PAIR, BN, LDW, TIMED>;
+    if (!TIMED) sh.dbg = nullptr;             // only the instrumented instances write the role counters
     constexpr int smem = QuadSmem<PKB, STAGES, PAIR, BN>::kBytes;
     {   // per device, cheap: set on every launch
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -219,6 +220,7 @@ static int launch_scan_quad_cs(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, 
         // MMG_SCAN_LD = 16 | 32: columns per tcgen05.ld of the epilogue (clusters of 2 only)
         if constexpr (CS == 2) {
             if (env_int("MMG_SCAN_LD", 16) == 32) return launch_scan_quad<CS, 8, 3, false, 256, 32>(ctx, tmA, tmB, sh, ep);
+            if (sh.dbg) return launch_scan_quad<CS, 8, 3, false, 256, 16, true>(ctx, tmA, tmB, sh, ep);
         }
         return launch_scan_quad<CS, 8, 3, false, 256>(ctx, tmA, tmB, sh, ep);
     }
@@ -231,6 +233,7 @@ static int launch_scan_quad_pair(mmg_ctx* ctx, int panel, const CUtensorMap& tmA
                                  const QuadEpi::Params& ep) {
     if (panel == 8) {
         if (env_int("MMG_SCAN_LD", 16) == 32) return launch_scan_quad<2, 8, 6, true, 256, 32>(ctx, tmA, tmB, sh, ep);
+        if (sh.dbg) return launch_scan_quad<2, 8, 6, true, 256, 16, true>(ctx, tmA, tmB, sh, ep);
         return launch_scan_quad<2, 8, 6, true, 256>(ctx, tmA, tmB, sh, ep);
     }
     if (panel == 4) return launch_scan_quad<2, 4, 10, true, 256>(ctx, tmA, tmB, sh, ep);

@@ -78,8 +78,10 @@ constexpr int QP_EPI_WARPS = 8;
 constexpr int QP_FIRST_EPI_WARP = 3;
 constexpr int QP_THREADS = 32 * (QP_FIRST_EPI_WARP + QP_EPI_WARPS);   // producer warp, MMA warp, L2-prefetch warp, 8 epilogue warps
 
-// LDW = columns per tcgen05.ld of the epilogue (16 or 32), double buffered either way
-template <int CS, int PKB, int STAGES, bool PAIR, int BN, int LDW = 16>
+// LDW = columns per tcgen05.ld of the epilogue (16 or 32), double buffered either way.  TIMED = per-role cycle counters
+// (MMG_SCAN_DBG_CLOCKS) compiled in; the production instance carries none of the clock reads (predicated-off CS2R lines showed up
+// as stall sites in the ncu source view of the run-time-flag version).
+template <int CS, int PKB, int STAGES, bool PAIR, int BN, int LDW = 16, bool TIMED = false>
 __global__ void __launch_bounds__(QP_THREADS, 1)
 scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const QuadShape sh,
                  uint64_t policy_a, uint64_t policy_b, const QuadEpi::Params ep) {
@@ -158,7 +160,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             uint32_t abits = 0;                        // per K-block parity of the aempty barriers
-            const bool timed = sh.dbg != nullptr;
+            constexpr bool timed = TIMED;
             long long w_aempty = 0, w_empty = 0;
             const long long t_start = timed ? clock64() : 0;
             uint32_t requested = 0;                     // digit K-blocks requested so far, published for the prefetch warp
@@ -274,7 +276,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int acc = 0;
             uint32_t acc_phase = 0;
             uint32_t abits = 0;                        // per K-block parity of the afull barriers
-            const bool timed = sh.dbg != nullptr;
+            constexpr bool timed = TIMED;
             long long w_tempty = 0, w_afull = 0, w_full = 0;
             const long long t_start = timed ? clock64() : 0;
             const uint64_t da0 = umma_desc_kmajor_sw128(smem_u32(smA)), db0 = umma_desc_kmajor_sw128(smem_u32(smB));
@@ -374,7 +376,7 @@ scan_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== epilogue warps 3..10 =====================
         // two warps per TMEM lane quadrant (a warp may only read lanes 32 (warp % 4) .. +31): each takes 128 of the tile's
         // 256 columns, so every SM sub-partition runs two epilogue warps that hide each other's tcgen05.ld / IMAD latency
-        const bool timed = sh.dbg != nullptr;
+        constexpr bool timed = TIMED;
         long long w_tfull = 0, w_x = 0, w_fp = 0, w_drain = 0;      // cycles: waiting for accumulators | x register loads | FP64 x.v pass | drain
         const long long t_start = timed ? clock64() : 0;
         const int quad = warp & 3;
