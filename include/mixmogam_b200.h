@@ -195,11 +195,6 @@ int mmg_emmax_perm_scan_f64(mmg_ctx* ctx, mmg_mat R, mmg_mat W, int centre, int 
 /* scipy.stats.f.sf(f, dfn, dfd) (linear_models.py:1349,1172) on the device, FP64 */
 int mmg_f_sf_f64(mmg_ctx* ctx, const double* f, int64_t count, double dfn, double dfd, double* out);
 
-/* ---- diagnostics ---------------------------------------------------------------------------- */
-/* raw pipe rates measured with CUDA events: which = "dmma" (TFLOP/s), "dfma" (TFLOP/s),
- * "imma_tcgen05" (TOP/s, smem-resident operands, no loads), "copy" (GB/s) */
-int mmg_microbench(mmg_ctx* ctx, const char* which, double* value);
-
 #ifdef __cplusplus
 }
 #endif

@@ -85,11 +85,33 @@ SIGNATURES = {
     'mmg_emmax_scan_multi_f64': (C.c_int, [_c_ctx, _vp, C.c_int, _vp, _vp, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_perm_scan_f64': (C.c_int, [_c_ctx, _i64, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
     'mmg_f_sf_f64': (C.c_int, [_c_ctx, _vp, _i64, C.c_double, C.c_double, _vp]),
+}
+# libmixmogam_b200_bench.so (include/mixmogam_b200_bench.h): diagnostics, loaded on first use only
+BENCH_LIB_PATH = os.path.join(_HERE, 'libmixmogam_b200_bench.so')
+BENCH_SIGNATURES = {
     'mmg_microbench': (C.c_int, [_c_ctx, C.c_char_p, _dp]),
 }
 
 _lib = None
+_bench_lib = None
 _lib_lock = threading.Lock()
+
+
+def load_bench_library():
+    """dlopen the microbenchmark library (bench.py's roofline denominators); the product never needs it."""
+    global _bench_lib
+    load_library()
+    with _lib_lock:
+        if _bench_lib is None:
+            if not os.path.exists(BENCH_LIB_PATH):
+                raise ImportError('mixmogam_b200: %s is missing -- build it first (__graft_entry__.build())' % BENCH_LIB_PATH)
+            lib = C.CDLL(BENCH_LIB_PATH)
+            for name, (res, args) in BENCH_SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _bench_lib = lib
+    return _bench_lib
 
 
 def load_library():
@@ -287,8 +309,9 @@ class Context(object):
         return p.value, r.value, g.value
 
     def microbench(self, which):
+        """Pipe-rate microbenchmarks of libmixmogam_b200_bench.so (see include/mixmogam_b200_bench.h)."""
         v = C.c_double(0)
-        self._ck(self.lib.mmg_microbench(self.h, which.encode(), C.byref(v)))
+        self._ck(load_bench_library().mmg_microbench(self.h, which.encode(), C.byref(v)))
         return v.value
 
     def sync(self):

@@ -1,0 +1,961 @@
+// libmixmogam_b200: stage 3 of the C ABI -- the SNP scan (int8 tcgen05 quadratic form, FP64 DMMA rotation), the
+// phenotype-batched scan and the permutation scan.
+#include "common.cuh"
+#include "fdist.cuh"
+#include "scan_dmma.cuh"
+#include "scan_tc.cuh"
+#include "scan_quad.cuh"
+
+namespace mmg {
+
+// Launch the genotype-stationary scan kernel (scan_quad.cuh): cluster CS, panel of PKB K-blocks, STAGES digit stages.
+template <int CS, int PKB, int STAGES, bool PAIR, int BN, int LDW = 16, bool TIMED = false>
+static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, QuadShape sh, const QuadEpi::Params& ep) {
+    auto kern = scan_quad_kernel<CS, PKB, STAGES, PAIR, BN, LDW, TIMED>;
+    if (!TIMED) sh.dbg = nullptr;             // only the instrumented instances write the role counters
+    constexpr int smem = QuadSmem<PKB, STAGES, PAIR, BN>::kBytes;
+    {   // per device, cheap: set on every launch
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "scan_quad_kernel: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(QP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = ctx->sm_count / CS;
+    if (CS > 1) {
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count / CS * CS));
+        int q = 0;
+        if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0) max_clusters = std::min(max_clusters, q);
+        else cudaGetLastError();
+    }
+    const int cgroups = (sh.num_groups + CS - 1) / CS;
+    const int clusters = std::max(1, std::min(cgroups, max_clusters));
+    cfg.gridDim = dim3((unsigned)(clusters * CS));
+    const uint64_t pa = env_policy("MMG_TC_HINT_A", L2_EVICT_FIRST), pb = env_policy("MMG_TC_HINT_B", L2_EVICT_LAST);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, sh, pa, pb, ep);
+    ctx->launches += 1;
+    if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of scan_quad_kernel<%d,%d,%d,%d> (grid %d) failed: %s", CS, PKB, STAGES,
+                                      (int)PAIR, clusters * CS, cudaGetErrorString(e));
+    return MMG_OK;
+}
+
+template <int CS>
+static int launch_scan_quad_cs(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
+                               const QuadEpi::Params& ep) {
+    if (panel == 8) {
+        // MMG_SCAN_LD = 16 | 32: columns per tcgen05.ld of the epilogue (clusters of 2 only)
+        if constexpr (CS == 2) {
+            if (env_int("MMG_SCAN_LD", 16) == 32) return launch_scan_quad<CS, 8, 3, false, 256, 32>(ctx, tmA, tmB, sh, ep);
+            if (sh.dbg) return launch_scan_quad<CS, 8, 3, false, 256, 16, true>(ctx, tmA, tmB, sh, ep);
+        }
+        return launch_scan_quad<CS, 8, 3, false, 256>(ctx, tmA, tmB, sh, ep);
+    }
+    if (panel == 4) return launch_scan_quad<CS, 4, 5, false, 256>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<CS, 6, 4, false, 256>(ctx, tmA, tmB, sh, ep);
+}
+
+// CTA-pair form (tcgen05.mma.cta_group::2): half digit tiles of 16 KB per stage
+static int launch_scan_quad_pair(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
+                                 const QuadEpi::Params& ep) {
+    if (panel == 8) {
+        if (env_int("MMG_SCAN_LD", 16) == 32) return launch_scan_quad<2, 8, 6, true, 256, 32>(ctx, tmA, tmB, sh, ep);
+        if (sh.dbg) return launch_scan_quad<2, 8, 6, true, 256, 16, true>(ctx, tmA, tmB, sh, ep);
+        return launch_scan_quad<2, 8, 6, true, 256>(ctx, tmA, tmB, sh, ep);
+    }
+    if (panel == 4) return launch_scan_quad<2, 4, 10, true, 256>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<2, 6, 8, true, 256>(ctx, tmA, tmB, sh, ep);
+}
+
+// CTA-pair form with 128-column tiles: four accumulator stages in TMEM, so the MMA may run three tiles ahead of the
+// epilogue and the cross-CTA barrier latency of the pair leaves the critical path; 8 KB half tiles per stage
+static int launch_scan_quad_pair128(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
+                                    const QuadEpi::Params& ep) {
+    if (panel == 12) return launch_scan_quad<2, 12, 4, true, 128>(ctx, tmA, tmB, sh, ep);
+    if (panel == 10) return launch_scan_quad<2, 10, 8, true, 128>(ctx, tmA, tmB, sh, ep);
+    if (panel == 6) return launch_scan_quad<2, 6, 16, true, 128>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<2, 8, 12, true, 128>(ctx, tmA, tmB, sh, ep);
+}
+// single-CTA MMA with 128-column tiles (four accumulator stages), digit tiles multicast over the cluster of 2
+static int launch_scan_quad_n128(mmg_ctx* ctx, int panel, const CUtensorMap& tmA, const CUtensorMap& tmB, const QuadShape& sh,
+                                 const QuadEpi::Params& ep) {
+    if (panel == 10) return launch_scan_quad<2, 10, 4, false, 128>(ctx, tmA, tmB, sh, ep);
+    return launch_scan_quad<2, 8, 6, false, 128>(ctx, tmA, tmB, sh, ep);
+}
+
+void scan_init_attrs() {
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<QuadEpi, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<OzakiEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<PermEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<PermEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(scan_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
+    cudaFuncSetAttribute(scan_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
+}
+
+}  // namespace mmg
+
+using namespace mmg;
+
+static __global__ void means_from_sums_kernel(const long long* __restrict__ sums, int64_t count, double inv_n, double* __restrict__ mu) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) mu[i] = (double)sums[i] * inv_n;
+}
+
+// zero-padded copy of R: rows -> multiple of 128, cols -> multiple of 128
+static int pad_matrix(mmg_ctx* ctx, const MmgMat* R, DevBuf& out, int64_t* rows_pad, int64_t* ld) {
+    *rows_pad = round_up(R->rows, 128);
+    *ld = round_up(R->cols, 128);
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)(*rows_pad) * (*ld) * sizeof(double)));
+    MMG_CUDA(ctx, cudaMemsetAsync(out.p, 0, (size_t)(*rows_pad) * (*ld) * sizeof(double), ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpy2DAsync(out.p, (*ld) * sizeof(double), R->d, R->cols * sizeof(double), R->cols * sizeof(double), R->rows,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    return MMG_OK;
+}
+
+static int launch_scan_dmma(mmg_ctx* ctx, bool perm, const ScanDmmaParams& prm) {
+    const int64_t blocks = (prm.row_count + SD_BM - 1) / SD_BM;
+    const int grid = (int)std::min<int64_t>(blocks, ctx->sm_count);
+    cudaEventRecord(ctx->kev0, ctx->stream);
+    if (perm)
+        scan_dmma_kernel<true><<<grid, SD_THREADS, SD_SMEM_BYTES, ctx->stream>>>(prm);
+    else
+        scan_dmma_kernel<false><<<grid, SD_THREADS, SD_SMEM_BYTES, ctx->stream>>>(prm);
+    MMG_TRY(launch_check(ctx, "scan_dmma_kernel"));
+    cudaEventRecord(ctx->kev1, ctx->stream);
+    return MMG_OK;
+}
+
+// max |x| over the resident genotype block (zero padding included), 16 bytes per thread per step
+static __global__ void snps_absmax_kernel(const uint4* __restrict__ p, int64_t n16, int* __restrict__ out) {
+    int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 w = p[i];
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int v = (int)(int8_t)((ww[j >> 2] >> (8 * (j & 3))) & 0xffu);
+            m = max(m, v < 0 ? -v : v);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// The int8 scan keeps per-tile sums in int32: |acc| <= 128 PKB |x| 128 and 32 columns x |x| per chain (2^28 at PKB = 8), safe for
+// |x| <= QS_MAX_ABS_GENOTYPE (genotypes are 0/1/2, kinship.py:14-56).  Measured once per resident block.
+constexpr int QS_MAX_ABS_GENOTYPE = 8;
+static int scan_tc_check_domain(mmg_ctx* ctx) {
+    if (ctx->snps_absmax < 0) {
+        MMG_CUDA(ctx, cudaMemsetAsync(ctx->flag_d, 0, sizeof(int), ctx->stream));
+        snps_absmax_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint4*)ctx->snps, ctx->m * ctx->pitch / 16, ctx->flag_d);
+        MMG_TRY(launch_check(ctx, "snps_absmax_kernel"));
+        int v = 0;
+        MMG_CUDA(ctx, cudaMemcpyAsync(&v, ctx->flag_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->snps_absmax = v;
+    }
+    if (ctx->snps_absmax > QS_MAX_ABS_GENOTYPE)
+        return fail(ctx, MMG_EVALUE, "int8 tensor-core scan: |genotype| up to %d exceeds its exact-integer domain (<= %d); "
+                    "use the FP64 tensor-core path (scan_impl='dmma')", ctx->snps_absmax, QS_MAX_ABS_GENOTYPE);
+    return MMG_OK;
+}
+
+// ---- int8 tensor-core scan: x'(R'R)x on exact integer slices (scan_tc.cuh) ------------------------------
+// Number of digit planes.  MMG_TC_SLICES = k fixes it; otherwise it is chosen per call from the certified truncation
+// bound  |d(x~.x~)| / x~.x~ <= (64/255) 256^-S 2^E ||x||_1^2 / x~.x~ <= MMG_TC_TOL (default 1e-7, i.e. < 2e-7 relative in
+// -log10 p for r^2 <= 0.5): a pilot launch over the first SNPs measures max_s 2^E ||x||_1^2 / x~.x~, the full launch
+// re-measures the bound over every SNP and is repeated with one more plane if a SNP violates it.
+constexpr int QS_AUTO_PLANES = 6;          // planes cut in auto mode: 48 bits of B (bound <= (64/255) 256^-6 ~ 9e-16 2^E ||x||_1^2)
+constexpr int QS_PILOT_PLANES = 2;
+constexpr double QS_PILOT_HEADROOM = 3.0;  // for the rows the pilot did not see; the full launch re-checks every SNP anyway
+constexpr int64_t QS_PILOT_ROWS = 64 * TC_BM;
+
+static int scan_tc_fixed_slices() {
+    const char* e = getenv("MMG_TC_SLICES");
+    if (!e) return 0;
+    return std::max(1, std::min(QS_MAX_SLICES, atoi(e)));
+}
+static double scan_tc_tol() {
+    const char* e = getenv("MMG_TC_TOL");
+    const double t = e ? atof(e) : 1e-7;
+    return t > 0.0 ? t : 1e-7;
+}
+
+// Digit planes of the strict lower triangle of A = R'R (doubled) into Bq (S planes of [n_padN x ldq]), diag(A) into
+// d_dg and v = R'y into d_v; returns the binary exponent E used for the scaling.  `A` is an n x n FP64 work matrix.
+// A = R'R as exact int8 digit-plane products on the tensor cores (scan_tc.cuh, "A = R'R on the int8 tensor cores"); A_work is a
+// zero-filled [n_padM x n_padM] FP64 buffer whose lower-triangular tiles are written.  *err_out: absolute error bound of its entries.
+static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_work, int64_t n_padM, unsigned long long* d_amax, double* err_out) {
+    const int64_t n = ctx->n, n_out = R->rows;
+    MMG_CHECK(ctx, n_out < 131072, "R'R on the int8 pipe: contraction too long for exact int32 accumulation");
+    MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
+    mat_amax_kernel<<<dim3(8, (unsigned)n_out), 256, 0, ctx->stream>>>(R->d, n, (int)n_out, (int)n, d_amax);
+    MMG_TRY(launch_check(ctx, "mat_amax_kernel"));
+    double rmax = 0.0;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&rmax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!std::isfinite(rmax)) return fail(ctx, MMG_EVALUE, "scan: the rotation is not finite (max |r| = %g)", rmax);
+    const int F = digit256_exponent(rmax);
+    const int64_t op_pitch = round_up(n_out, TC_BK);
+    DevBuf Op;
+    MMG_CUDA(ctx, Op.alloc(ctx->stream, (size_t)OZ_PLANES * n_padM * op_pitch));
+    MMG_CUDA(ctx, cudaMemsetAsync(Op.p, 0, (size_t)OZ_PLANES * n_padM * op_pitch, ctx->stream));
+    ozaki_planes_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n_out + 31) / 32)), 256, 0, ctx->stream>>>(
+        R->d, n, (int)n_out, (int)n, ldexp(1.0, -F), Op.as<int8_t>(), n_padM, op_pitch);
+    MMG_TRY(launch_check(ctx, "ozaki_planes_kernel"));
+    MMG_CUDA(ctx, cudaMemsetAsync(A_work, 0, (size_t)n_padM * n_padM * sizeof(double), ctx->stream));
+    // tile table: row-tile pairs (im, im + 1) x column tile jn that meet the lower triangle (rows >= columns), 28 (p, q) planes each
+    const int tiles_n = (int)(n_padM / TC_BN), tiles_m = (int)(n_padM / TC_BM), KB = (int)(op_pitch / TC_BK);
+    // Entry order = order in which the co-resident clusters pick the output tiles up.  The operands are streamed from L2 / HBM
+    // by every tile (79 K-blocks only), so the clusters of one wave should share them: the lower-triangular (row-pair, column
+    // tile) grid is walked in blocks of 9 x 8 (72 ~ the 74 co-resident clusters), whose operand rows for one plane pair are
+    // 9 x 2.6 + 8 x 2.6 = 44 MB -- L2 resident -- instead of row by row (a whole 103 MB plane per tile step).
+    std::vector<TcTile> tiles;
+    std::vector<std::pair<int, int>> order;                     // (jn, im)
+    {
+        const int BI = std::max(1, env_int("MMG_OZAKI_BLOCK_I", 9)), BJ = std::max(1, env_int("MMG_OZAKI_BLOCK_J", 8));
+        const int pairs_m = tiles_m / 2;
+        for (int bi = 0; bi < pairs_m; bi += BI)
+            for (int bj = 0; bj < tiles_n; bj += BJ)
+                for (int ip = bi; ip < std::min(pairs_m, bi + BI); ++ip)
+                    for (int jn = bj; jn < std::min(tiles_n, bj + BJ); ++jn)
+                        if (ip >= jn) order.emplace_back(jn, 2 * ip);
+    }
+    int entries = 0, per_entry = 0;
+    const bool chain = env_int("MMG_OZAKI_CHAIN", 1) != 0 && (double)OZ_LEVELS * (double)n_out * 16384.0 < 2147483647.0;
+    for (const auto& ji : order) {
+        const int jn = ji.first, im = ji.second;
+        {
+            // level by level (p + q = lv share the weight 2^2F 256^-(lv+2)): the lv + 1 plane pairs of a level are CHAINED into one
+            // int32 accumulator (7 n_out 128^2 < 2^31), so an output tile is read-modify-written 7 times, not 28 -- the FP64
+            // read-modify-write of the epilogue (a row per thread, 32 sectors per access) was what bounded this kernel
+            per_entry = 0;
+            for (int lv = 0; lv < OZ_LEVELS; ++lv)
+                for (int p = 0; p <= lv; ++p) {
+                    const int q = lv - p;
+                    if (p >= OZ_PLANES || q >= OZ_PLANES) continue;
+                    TcTile tl{};
+                    tl.m0 = (int)((int64_t)p * n_padM + (int64_t)im * TC_BM);
+                    tl.n0 = (int)((int64_t)q * n_padM + (int64_t)jn * TC_BN);
+                    tl.kb0 = 0;
+                    tl.kb1 = KB;
+                    tl.aux0 = p;
+                    tl.aux1 = q;
+                    tl.flags = (p < lv && chain) ? TC_TILE_CHAIN : 0;       // the pair (lv, 0) ends the chain of its level
+                    tiles.push_back(tl);
+                    ++per_entry;
+                }
+            ++entries;
+        }
+    }
+    MMG_TRY(ensure_tiles(ctx, tiles));
+    CUtensorMap tmA, tmB;
+    MMG_TRY(make_tmap_u8(ctx, &tmA, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BM));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BN / 2));
+    OzakiEpi::Params ep{};
+    ep.A = A_work;
+    ep.ld = n_padM;
+    ep.n_padM = n_padM;
+    for (int sl = 0; sl < 2 * OZ_PLANES; ++sl) ep.w[sl] = ldexp(1.0, 2 * F - 8 * (sl + 2));
+    MMG_TRY((launch_tc_gemm<OzakiEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, entries * 2, per_entry, per_entry, 0, TC_BM, ep,
+                                         "tc_gemm_i8_kernel<OzakiEpi,2>")));
+    *err_out = ozaki_error_bound(n_out) * ldexp(1.0, 2 * F);   // (Op is released in stream order when this returns)
+    return MMG_OK;
+}
+
+// MMG_QUAD_A = int8 (default: exact digit-plane products on the int8 tensor pipe) | dsyrk (cuBLAS, FP64 tensor pipe)
+static thread_local bool g_quad_force_dsyrk = false;     // set while a scan is repeated with the FP64 product (see scan_tc_run)
+static bool quad_a_int8() {
+    if (g_quad_force_dsyrk) return false;
+    const char* e = getenv("MMG_QUAD_A");
+    return !(e && strcmp(e, "dsyrk") == 0);
+}
+
+static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const double* A_given, double* A_work, int64_t lda_work,
+                        unsigned long long* d_amax, int S, int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, double* d_dg, int* E_out,
+                        double* errA_out) {
+    const int64_t n = ctx->n;
+    const double one = 1.0, zero = 0.0;
+    const double* A = A_given;
+    int64_t lda = n;
+    *errA_out = 0.0;
+    if (!A_given) {
+        const int64_t n_out = R->rows;
+        if (quad_a_int8() && scan_tc_tol() >= 1e-9) {
+            MMG_TRY(quad_form_int8(ctx, R, A_work, lda_work, d_amax, errA_out));
+        } else {
+            // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
+            // is the row-major LOWER triangle A[j][i], i <= j -- exactly the operand the slices are cut from.
+            MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero, A_work,
+                                        (int)lda_work));
+        }
+        // v = R' y~  (x~.y~ = x.v)
+        if (d_y) MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1));
+        A = A_work;
+        lda = lda_work;
+    }
+    MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
+    dim3 agrid(8, (unsigned)n);
+    quad_amax_kernel<<<agrid, 256, 0, ctx->stream>>>(A, lda, (int)n, d_amax);
+    MMG_TRY(launch_check(ctx, "quad_amax_kernel"));
+    double amax = 0.0;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "scan: R'R is not finite (max |a| = %g)", amax);
+    const int E = digit256_exponent(amax);                // |2 a| 2^-E <= 0.498 (a diagonal R'R has no off-diagonal digits at all)
+    dim3 sgrid((unsigned)((n + 255) / 256), (unsigned)n);
+    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A, lda, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq, d_dg);
+    MMG_TRY(launch_check(ctx, "quad_slice_kernel"));
+    *E_out = E;
+    return MMG_OK;
+}
+
+// one launch of the quadratic-form scan over resident rows [snp_begin, +snp_count) with S of the S_alloc cut planes
+static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* Bq, int64_t n_padN, int64_t ldq, int64_t snp_begin,
+                          int64_t snp_count, QuadEpi::Params ep, unsigned* d_wave_sync) {
+    int cs = env_int("MMG_SCAN_CLUSTER", 2);
+    if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 2;
+    // MMG_SCAN_SCHED = panel (genotype-stationary schedule, scan_quad.cuh) | pair (same, MMA as a CTA pair) |
+    //                  pair128 / n128 (128-column tiles, four accumulator stages) | table (tile-table kernel, tc_gemm.cuh)
+    const char* sched = getenv("MMG_SCAN_SCHED");
+    if (!sched) sched = "pair";         // the CTA-pair MMA halves the L2 -> SM digit traffic per SM: 138 vs 145 ms per 1M SNPs at n = 10k
+    const bool pair128 = strcmp(sched, "pair128") == 0, n128 = strcmp(sched, "n128") == 0;
+    const bool pair = strcmp(sched, "pair") == 0 || pair128;
+    if (pair || n128) cs = 2;
+    if (cs == 8 && strcmp(sched, "table") == 0) cs = 4;      // the tile-table kernel is instantiated for clusters of 1, 2, 4
+    const int bn = (pair128 || n128) ? 128 : TC_BN;
+    const int tiles_n = (int)(n_padN / bn), kb_total = (int)(ldq / TC_BK);
+    ep.row_begin = snp_begin;
+    ep.row_count = snp_count;
+    ep.out_stride = snp_count;
+    CUtensorMap tmA, tmB;
+    MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Bq, ldq, (int64_t)T * S_alloc * n_padN, ldq, bn / cs));
+    const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
+    if (strcmp(sched, "table") != 0) {
+        QuadShape sh{};
+        sh.num_groups = groups;
+        sh.T = T;
+        sh.S = S;
+        sh.S_stride = S_alloc;
+        sh.tiles_n = tiles_n;
+        sh.kb_total = kb_total;
+        sh.n_padN = (int)n_padN;
+        sh.prefetch = std::max(0, env_int("MMG_SCAN_PREFETCH", 8));
+        sh.pf_share = std::max(1, env_int("MMG_SCAN_PF_SHARE", 1));
+        if (env_int("MMG_SCAN_WAVE_SYNC", 1) && d_wave_sync) {
+            MMG_CUDA(ctx, cudaMemsetAsync(d_wave_sync, 0, sizeof(unsigned), ctx->stream));
+            sh.wave_sync = d_wave_sync;
+        }
+        // MMG_SCAN_DBG_CLOCKS=<file>: per-CTA cycle counters of the three warp roles (time spent in each barrier wait)
+        const char* dbg_path = getenv("MMG_SCAN_DBG_CLOCKS");
+        DevBuf dbg;
+        const int dbg_ctas = ctx->sm_count;
+        if (dbg_path) {
+            MMG_CUDA(ctx, dbg.alloc(ctx->stream, (size_t)dbg_ctas * 16 * sizeof(long long)));
+            MMG_CUDA(ctx, cudaMemsetAsync(dbg.p, 0, (size_t)dbg_ctas * 16 * sizeof(long long), ctx->stream));
+            sh.dbg = dbg.as<long long>();
+        }
+        const int panel = env_int("MMG_SCAN_PANEL", 8);
+        if (pair128) MMG_TRY(launch_scan_quad_pair128(ctx, panel, tmA, tmB, sh, ep));
+        else if (n128) MMG_TRY(launch_scan_quad_n128(ctx, panel, tmA, tmB, sh, ep));
+        else if (pair) MMG_TRY(launch_scan_quad_pair(ctx, panel, tmA, tmB, sh, ep));
+        else if (cs == 8) MMG_TRY(launch_scan_quad_cs<8>(ctx, panel, tmA, tmB, sh, ep));
+        else if (cs == 4) MMG_TRY(launch_scan_quad_cs<4>(ctx, panel, tmA, tmB, sh, ep));
+        else if (cs == 2) MMG_TRY(launch_scan_quad_cs<2>(ctx, panel, tmA, tmB, sh, ep));
+        else MMG_TRY(launch_scan_quad_cs<1>(ctx, panel, tmA, tmB, sh, ep));
+        if (dbg_path) {
+            std::vector<long long> h((size_t)dbg_ctas * 16);
+            MMG_CUDA(ctx, cudaMemcpyAsync(h.data(), dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (FILE* f = fopen(dbg_path, "w")) {
+                fprintf(f, "# cta prod_total prod_wait_empty prod_wait_aempty - mma_total mma_wait_full mma_wait_tempty mma_wait_afull epi_total epi_wait_tfull epi_xload epi_fp64 epi_drain\n");
+                for (int c = 0; c < dbg_ctas; ++c) {
+                    fprintf(f, "%d", c);
+                    for (int k = 0; k < 13; ++k) fprintf(f, " %lld", h[(size_t)c * 16 + k]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
+    } else {
+        // one shared tile table: for every phenotype, for every 256-column tile jb, one tile per slice; K only up to the diagonal
+        std::vector<TcTile> tiles;
+        tiles.reserve((size_t)T * tiles_n * S);
+        for (int t = 0; t < T; ++t)
+            for (int jb = 0; jb < tiles_n; ++jb)
+                for (int k = 0; k < S; ++k) {
+                    TcTile tl{};
+                    tl.m0 = 0;
+                    tl.n0 = (int)(((int64_t)t * S_alloc + k) * n_padN + (int64_t)jb * TC_BN);
+                    tl.kb0 = 0;
+                    tl.kb1 = std::min(kb_total, (jb + 1) * (TC_BN / TC_BK));
+                    tl.aux0 = k;
+                    tl.aux1 = (t << QS_PHEN_SHIFT) | (k == 0 ? QS_FLAG_XY : 0) | ((jb == 0 && k == 0) ? QS_FLAG_FIRST : 0) |
+                              ((jb == tiles_n - 1 && k == S - 1) ? QS_FLAG_LAST : 0);
+                    tl.col0 = jb * TC_BN;
+                    tiles.push_back(tl);
+                }
+        MMG_TRY(ensure_tiles(ctx, tiles));
+        const TcTile* td = (const TcTile*)ctx->tiles_d;
+        if (cs == 4)
+            MMG_TRY((launch_tc_gemm<QuadEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,4>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+        else if (cs == 2)
+            MMG_TRY((launch_tc_gemm<QuadEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,2>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+        else
+            MMG_TRY((launch_tc_gemm<QuadEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<QuadEpi,1>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+    }
+    return MMG_OK;
+}
+
+// T phenotypes (each with its own rotation R_t, residual y~_t and h0_rss_t) in one launch.  Device outputs are
+// [T][snp_count]; any may be NULL.
+//
+// A_given / v_given (T = 1 only): the quadratic form A = R'R (row-major lower triangle valid) and v = R'y~ were formed by
+// the caller -- the multi-GPU path builds A from per-rank row blocks of R and an all-reduce (parallel.py) instead of
+// repeating the n^3 product on every rank; Rs and V are then unused.
+static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const double* V, const double* h0_rss, double n_p, double lbeta,
+                       int64_t snp_begin, int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p,
+                       double* d_vp, const MmgMat* A_given = nullptr, const double* v_given = nullptr) {
+    const int64_t n = ctx->n, n_out = A_given ? 1 : Rs[0]->rows;
+    MMG_TRY(scan_tc_check_domain(ctx));
+    const int S_fixed = scan_tc_fixed_slices();
+    const int S_alloc = S_fixed ? S_fixed : QS_AUTO_PLANES;
+    const double tol = scan_tc_tol();
+    const int64_t n_padN = round_up(n, TC_BN), ldq = round_up(n, TC_BK);
+    const int64_t plane = n_padN * ldq;
+    MMG_CHECK(ctx, (int64_t)T * S_alloc * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
+    DevBuf A, Bq, vec;
+    const int64_t lda_work = round_up(n, TC_BN);               // padded so that the int8 R'R epilogue needs no bounds checks
+    if (!A_given) MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)lda_work * lda_work * sizeof(double)));
+    MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S_alloc * plane));
+    // vec: v[T][n_padN] | dg[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | bscale[T] | amax | rho | wave counter
+    const int64_t nd = 2 * (int64_t)T * n_padN + (int64_t)T * n_out + 3 * T + 3;
+    MMG_CUDA(ctx, vec.alloc(ctx->stream, (size_t)nd * sizeof(double)));
+    double* d_v = vec.as<double>();
+    double* d_dg = d_v + (int64_t)T * n_padN;
+    double* d_y = d_dg + (int64_t)T * n_padN;
+    double* d_h0 = d_y + (int64_t)T * n_out;
+    double* d_es = d_h0 + T;
+    double* d_bs = d_es + T;
+    unsigned long long* d_amax = (unsigned long long*)(d_bs + T);
+    unsigned long long* d_rho = d_amax + 1;
+    unsigned* d_wave = (unsigned*)(d_rho + 1);
+    MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)nd * sizeof(double), ctx->stream));
+    MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)T * S_alloc * plane, ctx->stream));
+    if (A_given) MMG_CUDA(ctx, cudaMemcpyAsync(d_v, v_given, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> escale((size_t)T), bscale((size_t)T), errA((size_t)T, 0.0);
+    // linear pre-pass: x.v_t, sum_j A_jj x_j^2 and ||x||_1 of every SNP in range, one stream over the genotypes.  When the rotation
+    // is at hand, v_t = R_t'y~_t and diag(A_t) = column sums of squares of R_t are formed first and the pre-pass runs on a side
+    // stream underneath the n^3 product A = R'R (FP64 / HBM work beside int8 tensor work); MMG_SCAN_OVERLAP=0 serialises them.
+    DevBuf pre;
+    MMG_CUDA(ctx, pre.alloc(ctx->stream, (size_t)((2 * T + 1) * snp_count + (int64_t)T * n_padN) * sizeof(double)));
+    double* d_dg_pre = pre.as<double>();                        // first: read as double2 by the pre-pass (16-byte aligned)
+    double* p_xy = d_dg_pre + (int64_t)T * n_padN;
+    double* p_qd = p_xy + (int64_t)T * snp_count;
+    double* p_a1 = p_qd + (int64_t)T * snp_count;
+    const int pre_rows_per_block = 8 * PRE_ROWS;
+    const unsigned pre_grid = (unsigned)((snp_count + pre_rows_per_block - 1) / pre_rows_per_block);
+    bool pre_launched = false;
+    struct SideJoin {                      // an early error return must not release `pre` under a running side-stream kernel
+        cudaStream_t s = nullptr;
+        ~SideJoin() { if (s) cudaStreamSynchronize(s); }
+    } side_join;
+    if (!A_given && env_int("MMG_SCAN_OVERLAP", 1)) {
+        if (!ctx->stream2) {
+            MMG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+            MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov0, cudaEventDisableTiming));
+            MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov1, cudaEventDisableTiming));
+        }
+        MMG_CUDA(ctx, cudaMemsetAsync(d_dg_pre, 0, (size_t)T * n_padN * sizeof(double), ctx->stream));
+        const double one = 1.0, zero = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const MmgMat* R = Rs[t];
+            MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)R->rows, &one, R->d, (int)n, d_y + (int64_t)t * n_out, 1, &zero,
+                                        d_v + (int64_t)t * n_padN, 1));
+            col_sumsq_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(R->d, n, (int)R->rows, (int)n, d_dg_pre + (int64_t)t * n_padN);
+            MMG_TRY(launch_check(ctx, "col_sumsq_kernel"));
+        }
+        MMG_CUDA(ctx, cudaEventRecord(ctx->ov0, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ov0, 0));
+        snp_prepass_kernel<PRE_ROWS, 4, 4><<<pre_grid, 256, 0, ctx->stream2>>>(ctx->snps, ctx->pitch, snp_begin, snp_count, T, d_v, d_dg_pre, n_padN, p_xy,
+                                                                            p_qd, p_a1, snp_count);
+        MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
+        side_join.s = ctx->stream2;
+        MMG_CUDA(ctx, cudaEventRecord(ctx->ov1, ctx->stream2));
+        pre_launched = true;
+    }
+    for (int t = 0; t < T; ++t) {
+        int E = 0;
+        MMG_TRY(quad_prepare(ctx, A_given ? nullptr : Rs[t], pre_launched ? nullptr : d_y + (int64_t)t * n_out, A_given ? A_given->d : nullptr, A.as<double>(), lda_work,
+                             d_amax, S_alloc, Bq.as<int8_t>() + (int64_t)t * S_alloc * plane, n_padN, ldq, d_v + (int64_t)t * n_padN,
+                             d_dg + (int64_t)t * n_padN, &E, &errA[(size_t)t]));
+        escale[t] = ldexp(1.0, E);
+    }
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_es, escale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+
+    QuadEpi::Params ep{};
+    ep.snps = ctx->snps;
+    ep.pitch = ctx->pitch;
+    for (int k = 0; k < QS_MAX_SLICES; ++k) ep.w[k] = ldexp(1.0, -8 * (k + 1));
+    ep.escale = d_es;
+    ep.v = d_v;
+    ep.dg = d_dg;
+    ep.bscale = d_bs;
+    ep.rho_max = d_rho;
+    ep.v_stride = n_padN;
+    ep.h0_rss = d_h0;
+    if (pre_launched) {
+        MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ov1, 0));        // join the side stream
+        side_join.s = nullptr;
+    } else {
+        snp_prepass_kernel<PRE_ROWS, 4, 4><<<pre_grid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin, snp_count, T, d_v, d_dg, n_padN, p_xy, p_qd,
+                                                                           p_a1, snp_count);
+        MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
+    }
+    ep.pre_xy = p_xy;
+    ep.pre_qd = p_qd;
+    ep.pre_a1 = p_a1;
+    ep.pre_stride = snp_count;
+    ep.n_p = n_p;
+    ep.lbeta = lbeta;
+
+    // bound scale for S planes: |remainder| <= 128/255 per entry of B, sum_{i<j} |x_i||x_j| <= ||x||_1^2 / 2
+    auto set_bscale = [&](int S) -> int {
+        // + the entry-wise error bound of A itself when it came from the int8 digit-plane product: |x'(dA)x| <= errA ||x||_1^2
+        for (int t = 0; t < T; ++t) bscale[t] = 0.5 * DIGIT256_REM * ldexp(1.0, -8 * S) * escale[t] + errA[(size_t)t];
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_bs, bscale.data(), (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaMemsetAsync(d_rho, 0, sizeof(unsigned long long), ctx->stream));
+        return MMG_OK;
+    };
+    auto read_rho = [&](double* rho) -> int {
+        MMG_CUDA(ctx, cudaMemcpyAsync(rho, d_rho, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return MMG_OK;
+    };
+
+    int S = S_fixed ? S_fixed : S_alloc;                        // short scans: no pilot, every plane that was cut
+    if (!S_fixed && snp_count >= 4 * QS_PILOT_ROWS) {
+        // pilot: bound of the first rows with few planes; the bound scales exactly by 256 per plane
+        QuadEpi::Params pp = ep;
+        pp.xx = pp.xy = pp.rss = pp.f = pp.p = pp.var_perc = nullptr;
+        MMG_TRY(set_bscale(QS_PILOT_PLANES));
+        MMG_TRY(scan_tc_launch(ctx, T, QS_PILOT_PLANES, S_alloc, Bq.p, n_padN, ldq, snp_begin, QS_PILOT_ROWS, pp, d_wave));
+        double rho = 0.0;
+        MMG_TRY(read_rho(&rho));
+        // bound(S) / bound(pilot planes), worst phenotype: 256 per plane down to the floor set by the error of A itself
+        auto bound_ratio = [&](int planes) {
+            double r = 0.0;
+            for (int t = 0; t < T; ++t) {
+                const double c = 0.5 * DIGIT256_REM * escale[t];
+                r = std::max(r, (c * ldexp(1.0, -8 * planes) + errA[(size_t)t]) / (c * ldexp(1.0, -8 * QS_PILOT_PLANES) + errA[(size_t)t]));
+            }
+            return r;
+        };
+        S = QS_PILOT_PLANES;
+        while (S < S_alloc && rho * bound_ratio(S) * QS_PILOT_HEADROOM > tol) ++S;
+    }
+    double rho = 0.0;
+    for (;;) {
+        ep.xx = d_xx; ep.xy = d_xy; ep.rss = d_rss; ep.f = d_f; ep.p = d_p; ep.var_perc = d_vp;
+        MMG_TRY(set_bscale(S));
+        cudaEventRecord(ctx->kev0, ctx->stream);
+        MMG_TRY(scan_tc_launch(ctx, T, S, S_alloc, Bq.p, n_padN, ldq, snp_begin, snp_count, ep, d_wave));
+        cudaEventRecord(ctx->kev1, ctx->stream);
+        MMG_TRY(read_rho(&rho));                                // also: Bq / A / vec are freed on return
+        if (S_fixed || rho <= tol || S >= S_alloc) break;
+        ++S;                                                    // a SNP outside the certified bound: one more plane, again
+    }
+    ctx->last_scan_slices = S;
+    ctx->last_scan_rho = rho;
+    // a tolerance below what the int8 product of A can certify (its own error bound is a floor of ~1e-10 relative at n = 10k):
+    // once more with A from the FP64 dsyrk
+    bool int8_floor = false;
+    for (double e : errA) int8_floor |= e > 0.0;
+    if (!S_fixed && rho > tol && int8_floor && !g_quad_force_dsyrk) {
+        g_quad_force_dsyrk = true;
+        const int rc = scan_tc_run(ctx, T, Rs, V, h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp, A_given, v_given);
+        g_quad_force_dsyrk = false;
+        return rc;
+    }
+    return MMG_OK;
+}
+
+// ---- int8 tensor-core permutation scan (linear_models.py:1157-1164) --------------------------------------------
+//   pass 1: xx_s = x_c'(R'R)x_c through the quadratic-form scan of the centred rotation R C (C = I - 11'/n)
+//   pass 2: PermEpi GEMM of the genotype block with the 8 digit planes of W' = Ys'R ([P x n]),
+//           ratio_p = max_s (x_c.W_p)^2 / xx_s
+static int perm_scan_tc(mmg_ctx* ctx, const MmgMat* R, const MmgMat* Wt, int centre, int64_t snp_begin, int64_t snp_count,
+                        double* ratio_inout) {
+    StageTimer tm(ctx, "scan");
+    const int64_t n = ctx->n, n_out = R->rows, P = Wt->rows;
+    const int64_t P_pad = round_up(P, 32), ldq = round_up(n, TC_BK);
+    const double one = 1.0, zero = 0.0;
+    DevBuf Rc, aux, Wq;
+    // aux: ones[n] | r1[n_out] | wsum[P_pad] | mu[snp_count] | xx[snp_count] | ratio[P_pad] | amax | sums[snp_count]
+    const int64_t nd = n + n_out + P_pad + 2 * snp_count + P_pad + 1;
+    MMG_CUDA(ctx, aux.alloc(ctx->stream, (size_t)nd * sizeof(double) + (size_t)snp_count * sizeof(long long)));
+    MMG_CUDA(ctx, cudaMemsetAsync(aux.p, 0, (size_t)nd * sizeof(double), ctx->stream));
+    double* d_ones = aux.as<double>();
+    double* d_r1 = d_ones + n;
+    double* d_wsum = d_r1 + n_out;
+    double* d_mu = d_wsum + P_pad;
+    double* d_xx = d_mu + snp_count;
+    unsigned long long* d_ratio = (unsigned long long*)(d_xx + snp_count);
+    unsigned long long* d_amax = d_ratio + P_pad;
+    long long* d_sums = (long long*)(d_amax + 1);
+    {
+        std::vector<double> ones((size_t)n, 1.0);
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_ones, ones.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // row-major [rows x n] matrices are column-major n x rows: y = A' x gives the row sums
+    MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_T, (int)n, (int)P, &one, Wt->d, (int)n, d_ones, 1, &zero, d_wsum, 1));
+    MmgMat Rcm = *R;
+    if (centre) {
+        MMG_CUDA(ctx, Rc.alloc(ctx->stream, (size_t)n_out * n * sizeof(double)));
+        MMG_CUDA(ctx, cudaMemcpyAsync(Rc.p, R->d, (size_t)n_out * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_T, (int)n, (int)n_out, &one, R->d, (int)n, d_ones, 1, &zero, d_r1, 1));
+        dim3 cgrid((unsigned)((n + 255) / 256), (unsigned)n_out);
+        centre_cols_kernel<<<cgrid, 256, 0, ctx->stream>>>(Rc.as<double>(), n, (int)n_out, (int)n, d_r1, 1.0 / (double)n);
+        MMG_TRY(launch_check(ctx, "centre_cols_kernel"));
+        Rcm.d = Rc.as<double>();
+        snp_row_sums_kernel<<<(unsigned)((snp_count + 7) / 8), 256, 0, ctx->stream>>>(ctx->snps + snp_begin * ctx->pitch, ctx->pitch,
+                                                                                      snp_count, (int)n, d_sums, nullptr);
+        MMG_TRY(launch_check(ctx, "snp_row_sums_kernel"));
+        means_from_sums_kernel<<<(unsigned)((snp_count + 255) / 256), 256, 0, ctx->stream>>>(d_sums, snp_count, 1.0 / (double)n, d_mu);
+        MMG_TRY(launch_check(ctx, "means_from_sums_kernel"));
+    }
+    // pass 1
+    {
+        std::vector<double> y0((size_t)n_out, 0.0);
+        const double h0 = 1.0;
+        const MmgMat* Rs[1] = {&Rcm};
+        MMG_TRY(scan_tc_run(ctx, 1, Rs, y0.data(), &h0, 1.0, 0.0, snp_begin, snp_count, d_xx, nullptr, nullptr, nullptr, nullptr, nullptr));
+    }
+    // digit planes of W'
+    mat_amax_kernel<<<dim3(8, (unsigned)P), 256, 0, ctx->stream>>>(Wt->d, n, (int)P, (int)n, d_amax);
+    MMG_TRY(launch_check(ctx, "mat_amax_kernel"));
+    double amax = 0.0;
+    MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "permutation scan: W is not finite");
+    const int E = amax > 0.0 ? ilogb(amax) + 2 : 0;
+    const int64_t wq_rows = P_pad * PS_SLICES;
+    MMG_CUDA(ctx, Wq.alloc(ctx->stream, (size_t)wq_rows * ldq));
+    MMG_CUDA(ctx, cudaMemsetAsync(Wq.p, 0, (size_t)wq_rows * ldq, ctx->stream));
+    perm_slice_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)P), 256, 0, ctx->stream>>>(Wt->d, n, (int)P, (int)n, ldexp(1.0, -E),
+                                                                                                Wq.as<int8_t>(), ldq);
+    MMG_TRY(launch_check(ctx, "perm_slice_kernel"));
+    // pass 2
+    PermEpi::Params ep{};
+    ep.row_count = snp_count;
+    for (int k = 0; k < PS_SLICES; ++k) ep.w[k] = ldexp(1.0, E - 7 * (k + 1));
+    ep.xx = d_xx;
+    ep.mu = centre ? d_mu : nullptr;
+    ep.wsum = d_wsum;
+    ep.ratio = d_ratio;
+    std::vector<TcTile> tiles;
+    for (int b = 0; b < (int)(P_pad / 32); ++b) {
+        TcTile tl{};
+        tl.n0 = b * TC_BN;
+        tl.kb0 = 0;
+        tl.kb1 = (int)(ldq / TC_BK);
+        tl.col0 = b * 32;
+        tiles.push_back(tl);
+    }
+    MMG_TRY(ensure_tiles(ctx, tiles));
+    int cs = env_int("MMG_SCAN_CLUSTER", 2);
+    if (cs != 1 && cs != 2) cs = 2;
+    CUtensorMap tmA, tmB;
+    MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + snp_begin * ctx->pitch, ctx->pitch, snp_count, ctx->pitch, TC_BM));
+    MMG_TRY(make_tmap_u8(ctx, &tmB, Wq.p, ldq, wq_rows, ldq, TC_BN / cs));
+    const int groups = (int)((snp_count + TC_BM - 1) / TC_BM);
+    const TcTile* td = (const TcTile*)ctx->tiles_d;
+    cudaEventRecord(ctx->kev0, ctx->stream);
+    if (cs == 2)
+        MMG_TRY((launch_tc_gemm<PermEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<PermEpi,2>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+    else
+        MMG_TRY((launch_tc_gemm<PermEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<PermEpi,1>", L2_EVICT_FIRST, L2_EVICT_LAST)));
+    cudaEventRecord(ctx->kev1, ctx->stream);
+    std::vector<double> ratio((size_t)P);
+    MMG_CUDA(ctx, cudaMemcpyAsync(ratio.data(), d_ratio, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+    ctx->last_perm_ms = ms;
+    for (int64_t p = 0; p < P; ++p) ratio_inout[p] = std::max(ratio_inout[p], ratio[p]);
+    return MMG_OK;
+}
+
+extern "C" {
+
+int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double h0_rss, double n_p, int impl, int64_t snp_begin,
+                       int64_t snp_count, double* ps, double* f_stats, double* rss, double* var_perc, double* xx, double* dots) {
+    MmgMat* R = ctx ? get_mat(ctx, Rh) : nullptr;
+    MMG_CHECK(ctx, R && ctx->snps, "mmg_emmax_scan_f64: need resident genotypes and R");
+    MMG_CHECK(ctx, R->cols == ctx->n, "R must have n = %lld columns (has %lld)", (long long)ctx->n, (long long)R->cols);
+    MMG_CHECK(ctx, V && nv >= 1 && nv <= 16, "need 1..16 rotated-space vectors (V[0] = residual phenotype)");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_SCAN_IMPL", MMG_IMPL_TCGEN05);
+    MMG_CHECK(ctx, impl == MMG_IMPL_DMMA || impl == MMG_IMPL_TCGEN05, "unsupported impl %d for the scan", impl);
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n, n_out = R->rows;
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+
+    DevBuf out;      // xx, xy, rss, f, p, var_perc  (6 x snp_count doubles) + dots
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)(6 + nv) * snp_count * sizeof(double)));
+    double* d_xx = out.as<double>();
+    double* d_xy = d_xx + snp_count;
+    double* d_rss = d_xy + snp_count;
+    double* d_f = d_rss + snp_count;
+    double* d_p = d_f + snp_count;
+    double* d_vp = d_p + snp_count;
+    double* d_dots = d_vp + snp_count;
+
+    {
+        StageTimer tm(ctx, "scan");
+        if (impl == MMG_IMPL_DMMA) {
+            DevBuf Rp, Vp;
+            int64_t rows_pad = 0, ld = 0;
+            MMG_TRY(pad_matrix(ctx, R, Rp, &rows_pad, &ld));
+            MMG_CUDA(ctx, Vp.alloc(ctx->stream, (size_t)rows_pad * sizeof(double)));
+            MMG_CUDA(ctx, cudaMemsetAsync(Vp.p, 0, (size_t)rows_pad * sizeof(double), ctx->stream));
+            MMG_CUDA(ctx, cudaMemcpyAsync(Vp.p, V, n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            ScanDmmaParams prm{};
+            prm.snps = ctx->snps;
+            prm.pitch = ctx->pitch;
+            prm.row_begin = snp_begin;
+            prm.row_count = snp_count;
+            prm.R = Rp.as<double>();
+            prm.ldr = ld;
+            prm.n_out_pad = (int)rows_pad;
+            prm.k_pad = (int)round_up(n, SD_BK);
+            prm.y = Vp.as<double>();
+            prm.h0_rss = h0_rss;
+            prm.n_p = n_p;
+            prm.lbeta = lbeta;
+            prm.xx = d_xx;
+            prm.xy = d_xy;
+            prm.rss = d_rss;
+            prm.f = d_f;
+            prm.p = d_p;
+            prm.var_perc = d_vp;
+            MMG_TRY(launch_scan_dmma(ctx, false, prm));
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            const MmgMat* Rs[1] = {R};
+            MMG_TRY(scan_tc_run(ctx, 1, Rs, V, &h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp));
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        ctx->last_scan_ms = ms;
+
+        if (dots) {
+            // x~.V[v] = x.(R' V[v]):  W = V R  ([nv x n_out] x [n_out x n]) then an HBM-bound dot kernel
+            DevBuf Vd, Wd;
+            MMG_CUDA(ctx, Vd.alloc(ctx->stream, (size_t)nv * n_out * sizeof(double)));
+            MMG_CUDA(ctx, Wd.alloc(ctx->stream, (size_t)nv * n * sizeof(double)));
+            MMG_CUDA(ctx, cudaMemcpyAsync(Vd.p, V, (size_t)nv * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            const double one = 1.0, zero = 0.0;
+            // row-major W[nv x n] = V[nv x n_out] R[n_out x n]  ->  column-major W' = R' V'
+            MMG_CUBLAS(ctx, cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, nv, (int)n_out, &one, R->d, (int)R->cols,
+                                        Vd.as<double>(), (int)n_out, &zero, Wd.as<double>(), (int)n));
+            for (int v = 0; v < nv; ++v) {
+                // one vector per launch keeps the kernel simple; dots is strided by nv on the host side
+                snp_dots_kernel<1><<<(unsigned)((snp_count + 7) / 8), 256, 0, ctx->stream>>>(
+                    ctx->snps, ctx->pitch, snp_begin, snp_count, (int)n, Wd.as<double>() + (int64_t)v * n, n, d_dots + (int64_t)v * snp_count);
+                MMG_TRY(launch_check(ctx, "snp_dots_kernel"));
+            }
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    StageTimer tm2(ctx, "d2h");
+    const size_t bytes = snp_count * sizeof(double);
+    if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (f_stats) MMG_CUDA(ctx, cudaMemcpyAsync(f_stats, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rss) MMG_CUDA(ctx, cudaMemcpyAsync(rss, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_perc) MMG_CUDA(ctx, cudaMemcpyAsync(var_perc, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xx) MMG_CUDA(ctx, cudaMemcpyAsync(xx, d_xx, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dots) {
+        // device layout is [nv][snp_count]; the ABI promises [snp_count][nv]
+        std::vector<double> tmp((size_t)nv * snp_count);
+        MMG_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_dots, (size_t)nv * bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int v = 0; v < nv; ++v)
+            for (int64_t s = 0; s < snp_count; ++s) dots[s * nv + v] = tmp[(size_t)v * snp_count + s];
+    }
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+// The int8 scan when the caller already holds the quadratic form A = R'R (n x n, row-major lower triangle valid) and
+// v = R'y~: the multi-GPU path forms A from per-rank row blocks of R (mmg_mat_syrk_rows) and one all-reduce instead of
+// repeating the 2 n^3 / 2 flops of the product on every rank (28 ms at n = 10k, more than an 8-way shard of the scan itself).
+int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat Ah, const double* v, double h0_rss, double n_p, int64_t snp_begin,
+                            int64_t snp_count, double* ps, double* f_stats, double* rss, double* var_perc, double* xx) {
+    MmgMat* A = ctx ? get_mat(ctx, Ah) : nullptr;
+    MMG_CHECK(ctx, A && ctx->snps && v, "mmg_emmax_scan_quad_f64: need resident genotypes, A and v");
+    MMG_CHECK(ctx, A->rows == ctx->n && A->cols == ctx->n, "A must be n x n with n = %lld (is %lld x %lld)", (long long)ctx->n,
+              (long long)A->rows, (long long)A->cols);
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+    DevBuf out;      // xx, xy, rss, f, p, var_perc
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)6 * snp_count * sizeof(double)));
+    double* d_xx = out.as<double>();
+    double* d_xy = d_xx + snp_count;
+    double* d_rss = d_xy + snp_count;
+    double* d_f = d_rss + snp_count;
+    double* d_p = d_f + snp_count;
+    double* d_vp = d_p + snp_count;
+    {
+        StageTimer tm(ctx, "scan");
+        MMG_TRY(scan_tc_run(ctx, 1, nullptr, nullptr, &h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp, A, v));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        ctx->last_scan_ms = ms;
+    }
+    StageTimer tm2(ctx, "d2h");
+    const size_t bytes = snp_count * sizeof(double);
+    if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (f_stats) MMG_CUDA(ctx, cudaMemcpyAsync(f_stats, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rss) MMG_CUDA(ctx, cudaMemcpyAsync(rss, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_perc) MMG_CUDA(ctx, cudaMemcpyAsync(var_perc, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xx) MMG_CUDA(ctx, cudaMemcpyAsync(xx, d_xx, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+// Phenotype-batched scan (BASELINE.json configs[2]; the reference runs one emmax() per phenotype): T rotations R_t
+// (same shape), V[t] = residual phenotype of t in its rotated space, h0_rss[t]; outputs are [T x snp_count].
+int mmg_emmax_scan_multi_f64(mmg_ctx* ctx, const mmg_mat* Rh, int T, const double* V, const double* h0_rss, double n_p,
+                             int64_t snp_begin, int64_t snp_count, double* ps, double* f_stats, double* rss, double* var_perc,
+                             double* xx) {
+    MMG_CHECK(ctx, ctx && ctx->snps && Rh && V && h0_rss && T >= 1 && T <= (1 << 20), "mmg_emmax_scan_multi_f64: bad argument");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    std::vector<const MmgMat*> Rs((size_t)T);
+    for (int t = 0; t < T; ++t) {
+        Rs[t] = get_mat(ctx, Rh[t]);
+        MMG_CHECK(ctx, Rs[t] && Rs[t]->cols == ctx->n && Rs[t]->rows == Rs[0]->rows, "R[%d]: unknown handle or shape mismatch", t);
+    }
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+    DevBuf out;      // xx, rss, f, p, var_perc: 5 x T x snp_count doubles
+    const int64_t cnt = (int64_t)T * snp_count;
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)5 * cnt * sizeof(double)));
+    double* d_xx = out.as<double>();
+    double* d_rss = d_xx + cnt;
+    double* d_f = d_rss + cnt;
+    double* d_p = d_f + cnt;
+    double* d_vp = d_p + cnt;
+    {
+        StageTimer tm(ctx, "scan");
+        MMG_TRY(scan_tc_run(ctx, T, Rs.data(), V, h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, nullptr, d_rss, d_f, d_p, d_vp));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        ctx->last_scan_ms = ms;
+    }
+    StageTimer tm2(ctx, "d2h");
+    const size_t bytes = (size_t)cnt * sizeof(double);
+    if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (f_stats) MMG_CUDA(ctx, cudaMemcpyAsync(f_stats, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rss) MMG_CUDA(ctx, cudaMemcpyAsync(rss, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_perc) MMG_CUDA(ctx, cudaMemcpyAsync(var_perc, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xx) MMG_CUDA(ctx, cudaMemcpyAsync(xx, d_xx, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+
+int mmg_emmax_perm_scan_f64(mmg_ctx* ctx, mmg_mat Rh, mmg_mat Wh, int centre, int impl, int64_t snp_begin, int64_t snp_count,
+                            double* ratio_inout) {
+    MmgMat *R = ctx ? get_mat(ctx, Rh) : nullptr, *Wt = ctx ? get_mat(ctx, Wh) : nullptr;
+    MMG_CHECK(ctx, R && Wt && ctx->snps && ratio_inout, "mmg_emmax_perm_scan_f64: bad argument");
+    MMG_CHECK(ctx, R->cols == ctx->n && Wt->cols == ctx->n, "R and W' must have n columns");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_PERM_IMPL", MMG_IMPL_TCGEN05);
+    MMG_CHECK(ctx, impl == MMG_IMPL_TCGEN05 || impl == MMG_IMPL_DMMA, "unsupported impl %d for the permutation scan", impl);
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (impl == MMG_IMPL_TCGEN05) return perm_scan_tc(ctx, R, Wt, centre, snp_begin, snp_count, ratio_inout);
+    StageTimer tm(ctx, "scan");
+    const int64_t n = ctx->n, P = Wt->rows;
+    DevBuf Rp, Wp, aux;
+    int64_t r_rows = 0, r_ld = 0, w_rows = 0, w_ld = 0;
+    MMG_TRY(pad_matrix(ctx, R, Rp, &r_rows, &r_ld));
+    MMG_TRY(pad_matrix(ctx, Wt, Wp, &w_rows, &w_ld));
+    // aux: ones[n] | r1[r_rows] | wsum[w_rows] | zeros y[r_rows] | mu[snp_count] | xx[snp_count] | ratio[w_rows] | sums[snp_count]
+    const int64_t nd = r_ld + r_rows + w_rows + r_rows + 2 * snp_count + w_rows;
+    MMG_CUDA(ctx, aux.alloc(ctx->stream, (size_t)nd * sizeof(double) + (size_t)snp_count * sizeof(long long)));
+    MMG_CUDA(ctx, cudaMemsetAsync(aux.p, 0, (size_t)nd * sizeof(double), ctx->stream));
+    double* d_ones = aux.as<double>();
+    double* d_r1 = d_ones + r_ld;
+    double* d_wsum = d_r1 + r_rows;
+    double* d_y0 = d_wsum + w_rows;
+    double* d_mu = d_y0 + r_rows;
+    double* d_xx = d_mu + snp_count;
+    unsigned long long* d_ratio = (unsigned long long*)(d_xx + snp_count);
+    long long* d_sums = (long long*)(d_ratio + w_rows);
+    {
+        std::vector<double> ones((size_t)n, 1.0);
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_ones, ones.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const double one = 1.0, zero = 0.0;
+    // r1 = R 1, wsum = W' 1 (padded matrices are column-major [ld x rows]: y = A' x)
+    MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_T, (int)r_ld, (int)r_rows, &one, Rp.as<double>(), (int)r_ld, d_ones, 1, &zero, d_r1, 1));
+    MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_T, (int)w_ld, (int)w_rows, &one, Wp.as<double>(), (int)w_ld, d_ones, 1, &zero, d_wsum, 1));
+    if (centre) {
+        snp_row_sums_kernel<<<(unsigned)((snp_count + 7) / 8), 256, 0, ctx->stream>>>(ctx->snps + snp_begin * ctx->pitch, ctx->pitch,
+                                                                                      snp_count, (int)n, d_sums, nullptr);
+        MMG_TRY(launch_check(ctx, "snp_row_sums_kernel"));
+        means_from_sums_kernel<<<(unsigned)((snp_count + 255) / 256), 256, 0, ctx->stream>>>(d_sums, snp_count, 1.0 / (double)n, d_mu);
+        MMG_TRY(launch_check(ctx, "means_from_sums_kernel"));
+    }
+    ScanDmmaParams prm{};
+    prm.snps = ctx->snps;
+    prm.pitch = ctx->pitch;
+    prm.row_begin = snp_begin;
+    prm.row_count = snp_count;
+    prm.k_pad = (int)round_up(n, SD_BK);
+    prm.mu = d_mu;                     // zeros when !centre
+    // pass 1: xx of the (centred) rotated SNPs
+    prm.R = Rp.as<double>();
+    prm.ldr = r_ld;
+    prm.n_out_pad = (int)r_rows;
+    prm.y = d_y0;
+    prm.r1 = d_r1;
+    prm.xx = d_xx;
+    prm.h0_rss = 1.0;
+    prm.n_p = 1.0;
+    MMG_TRY(launch_scan_dmma(ctx, false, prm));
+    // pass 2: max over SNPs of (x_c . W_p)^2 / xx
+    prm.R = Wp.as<double>();
+    prm.ldr = w_ld;
+    prm.n_out_pad = (int)w_rows;
+    prm.r1 = d_wsum;
+    prm.xx = nullptr;
+    prm.xx_in = d_xx;
+    prm.ratio_max = d_ratio;
+    MMG_TRY(launch_scan_dmma(ctx, true, prm));
+    std::vector<double> ratio((size_t)P);
+    MMG_CUDA(ctx, cudaMemcpyAsync(ratio.data(), d_ratio, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t p = 0; p < P; ++p) ratio_inout[p] = std::max(ratio_inout[p], ratio[p]);
+    return MMG_OK;
+}
+
+}  // extern "C"

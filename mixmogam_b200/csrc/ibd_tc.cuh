@@ -19,7 +19,7 @@ namespace mmg {
 constexpr int IBD_MAX_SLICES = 8;
 
 // per selected SNP: w = n^2 / (n q - s^2), mean = s/n; flags a monomorphic SNP (kinship.py:67); max w -> amax_bits
-__global__ void ibd_weights_kernel(const long long* __restrict__ sums, const long long* __restrict__ sumsq,
+static __global__ void ibd_weights_kernel(const long long* __restrict__ sums, const long long* __restrict__ sumsq,
                                    const long long* __restrict__ rows, int64_t count, int n, double* __restrict__ w,
                                    double* __restrict__ mean, unsigned long long* __restrict__ amax_bits, int* __restrict__ bad_flag) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,7 +41,7 @@ __global__ void ibd_weights_kernel(const long long* __restrict__ sums, const lon
 }
 
 // digits[k][i] of w_i 2^-E (base 64), coef[i] = w^_i mean_i, acc[0] += sum w^_i mean_i^2
-__global__ void __launch_bounds__(256) ibd_digits_kernel(const double* __restrict__ w, const double* __restrict__ mean, int64_t count,
+static __global__ void __launch_bounds__(256) ibd_digits_kernel(const double* __restrict__ w, const double* __restrict__ mean, int64_t count,
                                                          double scale /* 2^-E */, double inv_scale, int S, int8_t* __restrict__ digits,
                                                          int64_t dig_pitch, double* __restrict__ coef, double* __restrict__ acc) {
     __shared__ double red[8];
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) ibd_digits_kernel(const double* __restric
 //   plane 0     : x_is                     (operand B)
 //   plane 1 + k : d_sk x_is, k < S         (operand A of digit plane k)
 // Same 128 SNP x 64 individual transpose as pack_kmajor_kernel.  Genotypes outside {0,1,2} raise *bad_flag.
-__global__ void __launch_bounds__(256) pack_ibd_kernel(const int8_t* __restrict__ snps, int64_t pitch,
+static __global__ void __launch_bounds__(256) pack_ibd_kernel(const int8_t* __restrict__ snps, int64_t pitch,
                                                        const long long* __restrict__ rows, int64_t s_count, int n,
                                                        const int8_t* __restrict__ digits, int64_t dig_pitch, int S,
                                                        int8_t* __restrict__ P, int64_t p_pitch, int64_t n_padM,
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) pack_ibd_kernel(const int8_t* __restrict_
 }
 
 // u[i] += sum over selected SNPs of coef_s x_is.  Block = 256 threads x 4 individuals, slab of `slab` SNPs.
-__global__ void __launch_bounds__(256) snp_weighted_colsum_kernel(const int8_t* __restrict__ snps, int64_t pitch,
+static __global__ void __launch_bounds__(256) snp_weighted_colsum_kernel(const int8_t* __restrict__ snps, int64_t pitch,
                                                                   const long long* __restrict__ rows, const double* __restrict__ coef,
                                                                   int64_t count, int slab, int n, double* __restrict__ u) {
     const int i0 = (blockIdx.x * 256 + threadIdx.x) * 4;
@@ -190,7 +190,7 @@ struct IbdEpi {
 };
 
 // K[i][j] += Gw[min][max] - u_i - u_j + c
-__global__ void ibd_finalize_add_kernel(const double* __restrict__ Gw, int64_t ldg, int n, const double* __restrict__ u,
+static __global__ void ibd_finalize_add_kernel(const double* __restrict__ Gw, int64_t ldg, int n, const double* __restrict__ u,
                                         const double* __restrict__ c, double* __restrict__ K, int64_t ldk) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t bytes_lt_mask(int first_idx, int nvalid) {
 }
 
 template <int CODING>
-__global__ void __launch_bounds__(256) pack_kmajor_kernel(const int8_t* __restrict__ snps, int64_t pitch,
+static __global__ void __launch_bounds__(256) pack_kmajor_kernel(const int8_t* __restrict__ snps, int64_t pitch,
                                                           int64_t s_begin, int64_t s_count, int n,
                                                           int8_t* __restrict__ P, int64_t p_pitch,
                                                           int* __restrict__ bad_flag) {
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) pack_kmajor_kernel(const int8_t* __restri
 // SIMT Gram on the packed operand: G[i][j] (+)= sum_k P[i][k] P[j][k] for tiles with bj >= bi, by dp4a.
 // 64 x 64 outputs per block, 4 x 4 per thread.  Slow (CUDA-core) but independent of the tcgen05 path.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_simt_kernel(const int8_t* __restrict__ P, int64_t p_pitch, int n,
+static __global__ void __launch_bounds__(256) gram_simt_kernel(const int8_t* __restrict__ P, int64_t p_pitch, int n,
                                                         int64_t kbytes, int32_t* __restrict__ G, int64_t ldg,
                                                         int accumulate) {
     const int bi = blockIdx.y, bj = blockIdx.x;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(const int8_t* __restrict
 // finalize (kinship.py:50-53): reads the upper triangle of the integer Gram
 // ---------------------------------------------------------------------------------------------------
 template <int CODING>
-__global__ void kinship_finalize_kernel(const int32_t* __restrict__ G, int64_t ldg, int n, double m_total,
+static __global__ void kinship_finalize_kernel(const int32_t* __restrict__ G, int64_t ldg, int n, double m_total,
                                         double* __restrict__ K, int64_t ldk) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
@@ -174,7 +174,7 @@ __global__ void kinship_finalize_kernel(const int32_t* __restrict__ G, int64_t l
 }
 
 // mirror the upper triangle of the integer Gram into the lower one (for downloads)
-__global__ void gram_mirror_kernel(int32_t* __restrict__ G, int64_t ldg, int n) {
+static __global__ void gram_mirror_kernel(int32_t* __restrict__ G, int64_t ldg, int n) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= n || j >= i) return;
@@ -184,7 +184,7 @@ __global__ void gram_mirror_kernel(int32_t* __restrict__ G, int64_t ldg, int n) 
 // ---------------------------------------------------------------------------------------------------
 // scale_k (kinship.py:94-100): row sums + diagonal, then a single-block final reduction (deterministic)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rowsum_kernel(const double* __restrict__ K, int64_t ldk, int n,
+static __global__ void __launch_bounds__(256) rowsum_kernel(const double* __restrict__ K, int64_t ldk, int n,
                                                      double* __restrict__ rowsum) {
     __shared__ double red[8];
     const int i = blockIdx.x;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const double* __restrict__ 
     }
 }
 // out[0] = sum(rowsum), out[1] = trace
-__global__ void __launch_bounds__(1024) scale_k_reduce_kernel(const double* __restrict__ rowsum,
+static __global__ void __launch_bounds__(1024) scale_k_reduce_kernel(const double* __restrict__ rowsum,
                                                               const double* __restrict__ K, int64_t ldk, int n,
                                                               double* __restrict__ out) {
     __shared__ double red[2][32];
@@ -222,17 +222,17 @@ __global__ void __launch_bounds__(1024) scale_k_reduce_kernel(const double* __re
         out[1] = b;
     }
 }
-__global__ void scale_matrix_kernel(double* __restrict__ A, int64_t ld, int rows, int cols, double alpha) {
+static __global__ void scale_matrix_kernel(double* __restrict__ A, int64_t ld, int rows, int cols, double alpha) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j < cols && i < rows) A[(int64_t)i * ld + j] *= alpha;
 }
-__global__ void scale_rows_kernel(double* __restrict__ A, int64_t ld, int rows, int cols, const double* __restrict__ d) {
+static __global__ void scale_rows_kernel(double* __restrict__ A, int64_t ld, int rows, int cols, const double* __restrict__ d) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j < cols && i < rows) A[(int64_t)i * ld + j] *= d[i];
 }
-__global__ void add_diag_kernel(double* __restrict__ A, int64_t ld, int n, double alpha) {
+static __global__ void add_diag_kernel(double* __restrict__ A, int64_t ld, int n, double alpha) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) A[(int64_t)i * ld + i] += alpha;
 }
@@ -240,7 +240,7 @@ __global__ void add_diag_kernel(double* __restrict__ A, int64_t ld, int n, doubl
 // ---------------------------------------------------------------------------------------------------
 // per-SNP sums (int64) over individuals; one warp per row
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) snp_row_sums_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t m,
+static __global__ void __launch_bounds__(256) snp_row_sums_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t m,
                                                            int n, long long* __restrict__ sums,
                                                            long long* __restrict__ sumsq) {
     const int lane = threadIdx.x & 31;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) snp_row_sums_kernel(const int8_t* __restr
 // IBD standardisation (kinship.py:66 / hdf5_data.py:50,103): z = (x - mean) / std, ddof = 0, two-pass.
 // One block per selected SNP; rows[] lists the resident row indices.  Z is [count x ldz] FP64.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) standardise_rows_kernel(const int8_t* __restrict__ snps, int64_t pitch,
+static __global__ void __launch_bounds__(256) standardise_rows_kernel(const int8_t* __restrict__ snps, int64_t pitch,
                                                                const long long* __restrict__ rows, int n,
                                                                double* __restrict__ Z, int64_t ldz,
                                                                int* __restrict__ bad_flag) {

@@ -32,7 +32,7 @@ __device__ __forceinline__ void block_reduce_sum(double (&v)[NV], double* red /*
     }
 }
 
-__global__ void __launch_bounds__(REML_THREADS)
+static __global__ void __launch_bounds__(REML_THREADS)
 reml_grid_kernel(const double* __restrict__ eig, const double* __restrict__ sq_etas, int p,
                  const double* __restrict__ deltas, int g, double* __restrict__ lls, double* __restrict__ dlls) {
     __shared__ double red[4 * 8];
@@ -87,7 +87,7 @@ struct RemlDevEval {
     }
 };
 
-__global__ void __launch_bounds__(REML_THREADS)
+static __global__ void __launch_bounds__(REML_THREADS)
 reml_refine_kernel(const double* __restrict__ eig, const double* __restrict__ sq_etas, int p,
                    const double* __restrict__ deltas, int g, double esp, const double* __restrict__ lls,
                    const double* __restrict__ dlls, double* __restrict__ opt_delta, double* __restrict__ opt_ll,

@@ -53,7 +53,7 @@ __device__ __forceinline__ double i8_to_f64(int v) {
 }
 
 template <bool PERM>
-__global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const ScanDmmaParams prm) {
+static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const ScanDmmaParams prm) {
     extern __shared__ __align__(16) uint8_t sd_smem[];
     double* red = reinterpret_cast<double*>(sd_smem + SD_STAGES * SD_STAGE_BYTES);   // [2][4][128]
 
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const ScanDmma
 // x . W[:, v] for a few FP64 vectors (with_betas columns, means): one warp per SNP row, HBM-bound on X.
 // W is [nv x ldw] (vector v contiguous).  dots is [row_count x nv].
 template <int NV>
-__global__ void __launch_bounds__(256) snp_dots_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t row_begin,
+static __global__ void __launch_bounds__(256) snp_dots_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t row_begin,
                                                        int64_t row_count, int n, const double* __restrict__ W,
                                                        int64_t ldw, double* __restrict__ dots) {
     const int lane = threadIdx.x & 31;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) snp_dots_kernel(const int8_t* __restrict_
 }
 
 // per-SNP F statistics from (xx, xy): the epilogue alone, for paths that computed the moments elsewhere
-__global__ void scan_stats_kernel(const double* __restrict__ xx, const double* __restrict__ xy, int64_t count,
+static __global__ void scan_stats_kernel(const double* __restrict__ xx, const double* __restrict__ xy, int64_t count,
                                   double h0_rss, double n_p, double lbeta, double* rss_o, double* f_o, double* p_o,
                                   double* vp_o) {
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,7 +300,7 @@ __global__ void scan_stats_kernel(const double* __restrict__ xx, const double* _
     if (p_o) p_o[o] = pv;
 }
 
-__global__ void f_sf_kernel(const double* __restrict__ f, int64_t count, double dfn, double dfd, double lbeta,
+static __global__ void f_sf_kernel(const double* __restrict__ f, int64_t count, double dfn, double dfd, double lbeta,
                             double* __restrict__ out) {
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o < count) out[o] = f_sf(f[o], dfn, dfd, lbeta);

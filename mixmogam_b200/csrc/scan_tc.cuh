@@ -212,7 +212,7 @@ struct PermEpi {
 constexpr int PRE_ROWS = 2;      // SNP rows per warp (v_t / diag(A_t) are fetched from L1 once per PRE_ROWS rows); measured on 262 144 SNPs x 10 k
                                  // (profiles/r01_microbench_prepass.txt): <2 rows, unroll 4, 4 blocks/SM> 1.82 ms, <4, 4, 3> 2.61 ms, <8, 4, 2> 2.80 ms
 template <int PRE_ROWS = 4, int PRE_UNROLL = 4, int PRE_MINB = 1>
-__global__ void __launch_bounds__(256, PRE_MINB) snp_prepass_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t row_begin, int64_t row_count,
+static __global__ void __launch_bounds__(256, PRE_MINB) snp_prepass_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t row_begin, int64_t row_count,
                                                           int T, const double* __restrict__ v, const double* __restrict__ dg, int64_t v_stride,
                                                           double* __restrict__ xy, double* __restrict__ qd, double* __restrict__ a1,
                                                           int64_t out_stride) {
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256, PRE_MINB) snp_prepass_kernel(const int8_t
 }
 
 // max |2 A[j][i]| over the strict lower triangle (i < j) of the row-major matrix -> bits of a non-negative double
-__global__ void quad_amax_kernel(const double* __restrict__ A, int64_t ld, int n, unsigned long long* __restrict__ amax_bits) {
+static __global__ void quad_amax_kernel(const double* __restrict__ A, int64_t ld, int n, unsigned long long* __restrict__ amax_bits) {
     const int j = blockIdx.y;
     double m = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j; i += gridDim.x * blockDim.x) {
@@ -287,7 +287,7 @@ __global__ void quad_amax_kernel(const double* __restrict__ A, int64_t ld, int n
 
 // digits of B[j][i] = 2 A[j][i] 2^-E (i < j) into S stacked int8 planes Bq[(k * n_padN + j) * ldq + i]; the diagonal
 // goes to dg[j] = A[j][j] and stays in FP64 (it is usually the largest entry: keeping it out of the digit planes lowers E)
-__global__ void quad_slice_kernel(const double* __restrict__ A, int64_t ld, int n, double scale /* 2^-E */, int S,
+static __global__ void quad_slice_kernel(const double* __restrict__ A, int64_t ld, int n, double scale /* 2^-E */, int S,
                                   int8_t* __restrict__ Bq, int64_t n_padN, int64_t ldq, double* __restrict__ dg) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -325,7 +325,7 @@ inline double ozaki_error_bound(int64_t n_out) {
 }
 
 // digit planes of R' (K-major operand): Op[(p n_padM + i) op_pitch + k] = digit_p(R[k][i] 2^-F); 32 x 32 transpose through smem
-__global__ void __launch_bounds__(256) ozaki_planes_kernel(const double* __restrict__ R, int64_t ldr, int n_out, int n, double scale,
+static __global__ void __launch_bounds__(256) ozaki_planes_kernel(const double* __restrict__ R, int64_t ldr, int n_out, int n, double scale,
                                                            int8_t* __restrict__ Op, int64_t n_padM, int64_t op_pitch) {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
@@ -376,7 +376,7 @@ struct OzakiEpi {
 };
 
 // out[i] = sum_k R[k][i]^2 = diag(R'R) of the row-major [rows x cols] matrix (deterministic: fixed split of k over the 8 warps)
-__global__ void __launch_bounds__(256) col_sumsq_kernel(const double* __restrict__ R, int64_t ld, int rows, int cols, double* __restrict__ out) {
+static __global__ void __launch_bounds__(256) col_sumsq_kernel(const double* __restrict__ R, int64_t ld, int rows, int cols, double* __restrict__ out) {
     __shared__ double part[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + tx;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256) col_sumsq_kernel(const double* __restrict
 }
 
 // max |W| over a row-major [rows x cols] matrix -> bits of a non-negative double
-__global__ void mat_amax_kernel(const double* __restrict__ W, int64_t ld, int rows, int cols, unsigned long long* __restrict__ amax_bits) {
+static __global__ void mat_amax_kernel(const double* __restrict__ W, int64_t ld, int rows, int cols, unsigned long long* __restrict__ amax_bits) {
     const int r = blockIdx.y;
     double m = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += gridDim.x * blockDim.x) m = fmax(m, fabs(W[(int64_t)r * ld + i]));
@@ -406,7 +406,7 @@ __global__ void mat_amax_kernel(const double* __restrict__ W, int64_t ld, int ro
 }
 
 // digits of W[p][i] 2^-E into the permutation operand: Wq[((p/32)*8 + k)*32 + p%32][i], k < 8
-__global__ void perm_slice_kernel(const double* __restrict__ W, int64_t ld, int P, int n, double scale, int8_t* __restrict__ Wq,
+static __global__ void perm_slice_kernel(const double* __restrict__ W, int64_t ld, int P, int n, double scale, int8_t* __restrict__ Wq,
                                   int64_t ldq) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int p = blockIdx.y;
@@ -423,7 +423,7 @@ __global__ void perm_slice_kernel(const double* __restrict__ W, int64_t ld, int 
 }
 
 // R[r][:] -= r1[r] / n   (right-multiplication by the centring matrix C = I - 11'/n: R C = R - (R 1) 1'/n)
-__global__ void centre_cols_kernel(double* __restrict__ R, int64_t ld, int rows, int cols, const double* __restrict__ r1, double inv_n) {
+static __global__ void centre_cols_kernel(double* __restrict__ R, int64_t ld, int rows, int cols, const double* __restrict__ r1, double inv_n) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j < cols && i < rows) R[(int64_t)i * ld + j] -= r1[i] * inv_n;

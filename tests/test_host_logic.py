@@ -83,16 +83,31 @@ def test_reml_logic_boundary_cases(built):
         assert out[0] == deltas[np.argmax(lls)]
 
 
-def test_abi_exports_every_declared_symbol(built):
-    hdr = open(os.path.join(ROOT, 'include', 'mixmogam_b200.h')).read()
+def _declared(header):
+    hdr = open(os.path.join(ROOT, 'include', header)).read()
     hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
-    declared = set(re.findall(r'\b(mmg_[a-z0-9_]+)\s*\(', hdr))
+    return set(re.findall(r'\b(mmg_[a-z0-9_]+)\s*\(', hdr))
+
+
+def test_abi_exports_every_declared_symbol(built):
+    declared = _declared('mixmogam_b200.h')
     assert len(declared) >= 40
     from mixmogam_b200 import _lib
     lib = _lib.load_library()
     for name in sorted(declared):
         assert hasattr(lib, name), 'library does not export %s' % name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_bench_library_is_separate(built):
+    """The microbenchmark kernels live in their own shared library; the product library exports none of them."""
+    declared = _declared('mixmogam_b200_bench.h')
+    from mixmogam_b200 import _lib
+    assert declared == set(_lib.BENCH_SIGNATURES) and declared
+    lib, blib = _lib.load_library(), _lib.load_bench_library()
+    for name in sorted(declared):
+        assert hasattr(blib, name), 'bench library does not export %s' % name
+        assert not hasattr(lib, name), 'product library still exports %s' % name
 
 
 def test_no_gpu_fails_loudly(built):
