@@ -54,6 +54,10 @@ const char* mmg_last_error(mmg_ctx* ctx);            /* ctx may be NULL: last cr
 int mmg_device_info(mmg_ctx* ctx, char* name64, int* sm_count, int* cc_major, int* cc_minor,
                     int64_t* free_bytes, int64_t* total_bytes);
 int mmg_sync(mmg_ctx* ctx);
+/* the CUDA stream (cudaStream_t) every call on ctx is ordered on.  A multi-GPU caller enqueues its NCCL collectives on it
+ * (torch.cuda.ExternalStream in mixmogam_b200/parallel.py), so a collective on a library-owned buffer is ordered between the
+ * library's kernels without a host synchronisation. */
+int mmg_stream_handle(mmg_ctx* ctx, void** stream);
 /* number of kernels of THIS library launched on ctx since creation (bench.py gpu_launches) */
 int64_t mmg_launch_count(mmg_ctx* ctx);
 /* named stage timers in seconds, CUDA-event based, accumulated since the last reset.
@@ -74,18 +78,19 @@ int mmg_host_free(void* ptr);
 
 /* ---- device FP64 matrices (plumbing for the n x n objects of linear_models.py) -- */
 int mmg_mat_create(mmg_ctx* ctx, int64_t rows, int64_t cols, mmg_mat* out);   /* zero-filled */
+int mmg_mat_alloc(mmg_ctx* ctx, int64_t rows, int64_t cols, int zero, mmg_mat* out);   /* zero == 0: contents undefined */
 int mmg_mat_free(mmg_ctx* ctx, mmg_mat m);
 int mmg_mat_shape(mmg_ctx* ctx, mmg_mat m, int64_t* rows, int64_t* cols);
 int mmg_mat_upload(mmg_ctx* ctx, mmg_mat m, const double* host, int64_t ld_host);
 int mmg_mat_download(mmg_ctx* ctx, mmg_mat m, double* host, int64_t ld_host);
+/* rows row0, row0 + row_step, ... (nrows of them) into host [nrows x ld_host]: one strided copy */
+int mmg_mat_download_rows(mmg_ctx* ctx, mmg_mat m, int64_t row0, int64_t row_step, int64_t nrows, double* host, int64_t ld_host);
+/* raw device pointer; work on it must be ordered on the context's stream (mmg_stream_handle) or follow an mmg_sync */
 int mmg_mat_device_ptr(mmg_ctx* ctx, mmg_mat m, void** dptr, int64_t* ld);
 int mmg_mat_copy(mmg_ctx* ctx, mmg_mat dst, mmg_mat src);
 /* C = alpha * op(A) * op(B) + beta * C   (cuBLAS dgemm; a plain library GEMM, outside the hot path) */
 int mmg_mat_gemm(mmg_ctx* ctx, int trans_a, int trans_b, double alpha, mmg_mat A, mmg_mat B,
                  double beta, mmg_mat C);
-/* A = R[row_begin:+row_count, :]' R[row_begin:+row_count, :]  -- row-major LOWER triangle of the n x n matrix A
- * (n = cols of R); the multi-GPU scan sums these per-rank blocks into R'R (linear_models.py:1299-1303 gives M = R') */
-int mmg_mat_syrk_rows(mmg_ctx* ctx, mmg_mat R, int64_t row_begin, int64_t row_count, mmg_mat A);
 int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat A, const double* d_host);         /* A[i,:] *= d[i] */
 int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat A, double alpha);                   /* A += alpha*I   */
 /* kinship.scale_k (kinship.py:94-100): c = tr(K) - sum(K)/n ; K *= (n-1)/c ; returns the scalar */
@@ -133,6 +138,11 @@ int mmg_last_h2d_info(mmg_ctx* ctx, int64_t* packed_chunks, int64_t* raw_chunks,
 /* device pointer of the int32 Gram (n x n, row stride ld elements) for an NCCL all-reduce between ranks */
 int mmg_kinship_gram_ptr(mmg_ctx* ctx, void** dptr, int64_t* n, int64_t* ld);
 int mmg_kinship_gram_download(mmg_ctx* ctx, int32_t* G_host);
+/* The tensor-core Gram fills the 256 x 256 blocks on and above the block diagonal of the padded square.  direction 0 packs
+ * those blocks back to back into one contiguous int32 buffer (*dptr, *count elements: half the bytes of the square) for the
+ * all-reduce between ranks (partial Grams summed exactly in int32); direction 1 unpacks the reduced buffer into the
+ * Gram again.  Stream ordered. */
+int mmg_kinship_gram_tri(mmg_ctx* ctx, int direction, void** dptr, int64_t* count);
 /* kinship.py:50-55: binary  K = G/(2 m) + 0.5 ; diploid K = f64(f32(m - L1/2)/f32(m)) + I with
  * L1 = G_ii + G_jj - 2 G_ij and a zero diagonal count; then scale_k if scaled.  m_total = SNPs in G. */
 int mmg_kinship_finalize_f64(mmg_ctx* ctx, int coding, int64_t m_total, int scaled, mmg_mat K_out,
@@ -165,7 +175,10 @@ int mmg_reml_f64(mmg_ctx* ctx, const double* eig_vals, const double* sq_etas, in
  *       MMG_IMPL_TCGEN05 = x'(R'R)x on int8 tcgen05 tensor cores: diagonal in FP64, off-diagonal as exact base-256
  *                          digit planes of R'R (itself formed as exact int8 digit-plane products, or by FP64 dsyrk:
  *                          MMG_QUAD_A); the number of planes is chosen so that the certified truncation bound
- *                          on x~.x~ is <= MMG_TC_TOL (1e-7) for every SNP (mmg_last_scan_info).
+ *                          on x~.x~ is <= MMG_TC_TOL (1e-7) for every SNP (mmg_last_scan_info); a scan that cannot certify
+ *                          it fails with MMG_EVALUE.  A SNP whose x~.x~ is below 1e-8 of sum_j A_jj x_j^2 is collinear with
+ *                          the fixed effects (e.g. monomorphic): it keeps the null fit (rss = h0_rss, f = 0, p = 1), like the
+ *                          reference's empty-residue case (:1329), and does not enter the certification.
  * Outputs (host, length snp_count, any may be NULL): ps, f_stats, rss, var_perc, xx;
  * dots: [snp_count x nv]. */
 int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double h0_rss, double n_p,
@@ -173,10 +186,23 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double 
                        double* ps, double* f_stats, double* rss, double* var_perc,
                        double* xx, double* dots);
 /* The int8 tensor-core form of mmg_emmax_scan_f64 for a caller that already holds A = R'R (n x n, row-major lower
- * triangle valid) and v = R'y~ [n] -- e.g. A summed over ranks from mmg_mat_syrk_rows blocks.  Same outputs. */
+ * triangle valid) and v = R'y~ [n].  Same outputs. */
 int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat A, const double* v, double h0_rss, double n_p,
                             int64_t snp_begin, int64_t snp_count,
                             double* ps, double* f_stats, double* rss, double* var_perc, double* xx);
+/* Multi-GPU form of the same.  The quadratic form is kept as packed 256 x 256 FP64 blocks of its lower triangle: block (J, I),
+ * I <= J, in slot J (J + 1) / 2 + I, row-major inside a block; mmg_quad_form_slots(n) blocks in all.  mmg_quad_form_tiles forms
+ * blocks [slot_begin, +slot_count) of A = R'R as exact int8 digit-plane products on the tensor cores into the packed matrix
+ * A ([>= slots x 65536] mmg_mat) -- every block costs the same, so ranks taking equal slot ranges are balanced and one in-place
+ * all-gather of A completes it on every rank.  *err_abs: rigorous absolute error bound of the entries (same on every rank).
+ * mmg_emmax_scan_quad_dev then scans with device-resident inputs and outputs: A (packed != 0: the block layout, else dense
+ * n x n lower triangle), a_err = the error bound of A's entries (enters the certified bound; 0 for an FP64 A), v = R'y~ as an
+ * mmg_mat of n values, and out = [5 x >= snp_count] rows ps, f_stats, rss, var_perc, xx (left on the device for the all-gather
+ * of the per-rank slices). */
+int64_t mmg_quad_form_slots(int64_t n);
+int mmg_quad_form_tiles(mmg_ctx* ctx, mmg_mat R, int64_t slot_begin, int64_t slot_count, mmg_mat A, double* err_abs);
+int mmg_emmax_scan_quad_dev(mmg_ctx* ctx, mmg_mat A, int packed, double a_err, mmg_mat v, double h0_rss, double n_p,
+                            int64_t snp_begin, int64_t snp_count, mmg_mat out);
 /* Phenotype-batched scan: T phenotypes scanned against one genotype block in ONE launch (BASELINE.json configs[2];
  * the reference calls linear_models.emmax once per phenotype, linear_models.py:1790).  R[t] is the rotation of
  * phenotype t (its own delta_t enters through H_t), V[t] its residual phenotype in the rotated space ([T x n_out]),

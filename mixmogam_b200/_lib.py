@@ -41,6 +41,7 @@ SIGNATURES = {
     'mmg_device_info': (C.c_int, [_c_ctx, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(_i64), C.POINTER(_i64)]),
     'mmg_sync': (C.c_int, [_c_ctx]),
+    'mmg_stream_handle': (C.c_int, [_c_ctx, C.POINTER(_vp)]),
     'mmg_launch_count': (_i64, [_c_ctx]),
     'mmg_timer_get': (C.c_int, [_c_ctx, C.c_char_p, _dp, C.POINTER(_i64)]),
     'mmg_timer_reset': (C.c_int, [_c_ctx]),
@@ -49,14 +50,15 @@ SIGNATURES = {
     'mmg_host_alloc': (C.c_int, [C.POINTER(_vp), _i64]),
     'mmg_host_free': (C.c_int, [_vp]),
     'mmg_mat_create': (C.c_int, [_c_ctx, _i64, _i64, C.POINTER(_i64)]),
+    'mmg_mat_alloc': (C.c_int, [_c_ctx, _i64, _i64, C.c_int, C.POINTER(_i64)]),
     'mmg_mat_free': (C.c_int, [_c_ctx, _i64]),
     'mmg_mat_shape': (C.c_int, [_c_ctx, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     'mmg_mat_upload': (C.c_int, [_c_ctx, _i64, _vp, _i64]),
     'mmg_mat_download': (C.c_int, [_c_ctx, _i64, _vp, _i64]),
+    'mmg_mat_download_rows': (C.c_int, [_c_ctx, _i64, _i64, _i64, _i64, _vp, _i64]),
     'mmg_mat_device_ptr': (C.c_int, [_c_ctx, _i64, C.POINTER(_vp), C.POINTER(_i64)]),
     'mmg_mat_copy': (C.c_int, [_c_ctx, _i64, _i64]),
     'mmg_mat_gemm': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_double, _i64, _i64, C.c_double, _i64]),
-    'mmg_mat_syrk_rows': (C.c_int, [_c_ctx, _i64, _i64, _i64, _i64]),
     'mmg_mat_scale_rows': (C.c_int, [_c_ctx, _i64, _vp]),
     'mmg_mat_add_diag': (C.c_int, [_c_ctx, _i64, C.c_double]),
     'mmg_mat_scale_k': (C.c_int, [_c_ctx, _i64, _dp]),
@@ -76,12 +78,16 @@ SIGNATURES = {
     'mmg_last_h2d_info': (C.c_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64), _dp]),
     'mmg_kinship_gram_ptr': (C.c_int, [_c_ctx, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     'mmg_kinship_gram_download': (C.c_int, [_c_ctx, _vp]),
+    'mmg_kinship_gram_tri': (C.c_int, [_c_ctx, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
     'mmg_kinship_finalize_f64': (C.c_int, [_c_ctx, C.c_int, _i64, C.c_int, _i64, _dp]),
     'mmg_kinship_ibd_accumulate_f64': (C.c_int, [_c_ctx, _i64, _i64, _i64, _vp, C.POINTER(_i64)]),
     'mmg_reml_f64': (C.c_int, [_c_ctx, _vp, _vp, _i64, _i64, _vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _i64, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_quad_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_double, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_quad_form_slots': (_i64, [_i64]),
+    'mmg_quad_form_tiles': (C.c_int, [_c_ctx, _i64, _i64, _i64, _i64, _dp]),
+    'mmg_emmax_scan_quad_dev': (C.c_int, [_c_ctx, _i64, C.c_int, C.c_double, _i64, C.c_double, C.c_double, _i64, _i64, _i64]),
     'mmg_emmax_scan_multi_f64': (C.c_int, [_c_ctx, _vp, C.c_int, _vp, _vp, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_perm_scan_f64': (C.c_int, [_c_ctx, _i64, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
     'mmg_f_sf_f64': (C.c_int, [_c_ctx, _vp, _i64, C.c_double, C.c_double, _vp]),
@@ -144,11 +150,11 @@ def impl_id(impl):
 class DeviceMatrix(object):
     """FP64 row-major matrix resident in HBM (mmg_mat handle)."""
 
-    def __init__(self, ctx, rows, cols):
+    def __init__(self, ctx, rows, cols, zero=True):
         self.ctx = ctx
         self.shape = (int(rows), int(cols))
         h = _i64(0)
-        ctx._ck(ctx.lib.mmg_mat_create(ctx.h, rows, cols, C.byref(h)))
+        ctx._ck(ctx.lib.mmg_mat_alloc(ctx.h, rows, cols, int(bool(zero)), C.byref(h)))
         self.handle = h.value
 
     @classmethod
@@ -176,9 +182,21 @@ class DeviceMatrix(object):
         self.ctx._ck(self.ctx.lib.mmg_mat_copy(self.ctx.h, m.handle, self.handle))
         return m
 
-    def device_ptr(self):
+    def download_rows(self, row0, row_step, nrows, out=None):
+        """Rows row0, row0 + row_step, ... (nrows of them) as an [nrows x cols] host array (one strided copy)."""
+        if out is None:
+            out = result_empty((int(nrows), self.shape[1]))
+        self.ctx._ck(self.ctx.lib.mmg_mat_download_rows(self.ctx.h, self.handle, int(row0), int(row_step), int(nrows), _ptr(out),
+                                                        out.shape[1]))
+        return out
+
+    def device_ptr(self, sync=True):
+        """(device pointer, leading dimension).  sync=False: the caller orders its work on the context's stream
+        (parallel.on_lib_stream) instead of waiting for the stream to drain."""
         p, ld = C.c_void_p(0), _i64(0)
         self.ctx._ck(self.ctx.lib.mmg_mat_device_ptr(self.ctx.h, self.handle, C.byref(p), C.byref(ld)))
+        if sync:
+            self.ctx.sync()
         return p.value, ld.value
 
     def free(self):
@@ -251,6 +269,7 @@ class Context(object):
         self.h = h
         self.device = int(device)
         self._snps_key = None
+        self._snps_owner = None
         self._resident = {}
 
     def _ck(self, rc):
@@ -317,13 +336,17 @@ class Context(object):
     def sync(self):
         self._ck(self.lib.mmg_sync(self.h))
 
-    # ---- genotypes ----
-    @staticmethod
-    def _fingerprint(a):
-        flat = a.reshape(-1)
-        step = max(1, flat.size // 4096)
-        return hash(flat[::step].tobytes())
+    def stream_ptr(self):
+        """cudaStream_t of this context as an integer (mmg_stream_handle)."""
+        p = C.c_void_p(0)
+        self._ck(self.lib.mmg_stream_handle(self.h, C.byref(p)))
+        return int(p.value or 0)
 
+    # ---- genotypes ----
+    # Residency contract: the device copy of a genotype array is reused by later calls ONLY when the array is read-only
+    # (arr.flags.writeable == False; mixmogam_b200.resident(arr) marks it) -- a read-only buffer cannot have been edited in
+    # place between two calls, so (address, shape) identifies its contents.  A writable array is uploaded again by every
+    # call that needs it: an in-place edit (imputation, allele flip, a reused buffer) is always seen.
     def invalidate_snps(self):
         self._snps_key = None
 
@@ -333,17 +356,20 @@ class Context(object):
             a = _as_int8(a)
         if not a.flags.c_contiguous:
             a = np.ascontiguousarray(a)
-        return a, ('arr', a.ctypes.data, a.shape, self._fingerprint(a))
+        key = ('arr', a.ctypes.data, a.shape) if (a is snps and not snps.flags.writeable) else None
+        return a, key
 
     def ensure_snps(self, snps):
         """Make `snps` (list of m int8 rows or an (m, n) array, SNP-major; kinship.py:21-23) the resident
-        genotype block.  Re-uploads unless the same buffer (address, shape, sampled fingerprint) is
-        already resident.  Returns (m, n)."""
+        genotype block.  Uploads it unless this very read-only buffer is already resident (see the residency
+        contract above).  Returns (m, n)."""
         if isinstance(snps, np.ndarray) and snps.ndim == 2:
             a, key = self._array_key(snps)
-            if key != self._snps_key:
+            if key is None or key != self._snps_key:
+                self._snps_key = None
                 self._ck(self.lib.mmg_snps_upload(self.h, _ptr(a), a.shape[0], a.shape[1], a.shape[1]))
                 self._snps_key = key
+                self._snps_owner = snps if key is not None else None      # keeps the buffer (hence its address) alive
             return a.shape
         m = len(snps)
         if m == 0:
@@ -354,11 +380,13 @@ class Context(object):
         if not rows_ok:
             return self.ensure_snps(_as_int8(np.asarray(snps)))
         ptrs = np.fromiter((r.ctypes.data for r in snps), dtype=np.uint64, count=m)
-        step = max(1, m // 64)
-        key = ('rows', m, n, hash(ptrs.tobytes()), hash(b''.join(snps[i].tobytes() for i in range(0, m, step))))
-        if key != self._snps_key:
+        frozen = not any(r.flags.writeable for r in snps)
+        key = ('rows', m, n, hash(ptrs.tobytes())) if frozen else None
+        if key is None or key != self._snps_key:
+            self._snps_key = None
             self._ck(self.lib.mmg_snps_upload_rows(self.h, _ptr(ptrs), m, n))
             self._snps_key = key
+            self._snps_owner = list(snps) if key is not None else None
         return (m, n)
 
     def snps_shape(self):
@@ -395,7 +423,7 @@ class Context(object):
         host.flags.writeable = False
         base = np.asarray(host)
         key = (base.ctypes.data, base.shape)
-        self._resident[key] = (dev, self._fingerprint(base), weakref.ref(base.base if base.base is not None else base))
+        self._resident[key] = (dev, weakref.ref(base.base if base.base is not None else base))
         while len(self._resident) > 2:
             k0 = next(iter(self._resident))
             self._resident.pop(k0)[0].free()
@@ -409,8 +437,8 @@ class Context(object):
         ent = self._resident.get((base.ctypes.data, base.shape))
         if ent is None:
             return None
-        dev, fp, ref = ent
-        if ref() is None or not dev.handle or self._fingerprint(base) != fp:
+        dev, ref = ent
+        if ref() is None or not dev.handle:
             self._resident.pop((base.ctypes.data, base.shape), None)
             dev.free()
             return None
@@ -424,12 +452,16 @@ class Context(object):
         self._ck(self.lib.mmg_mat_gemm(self.h, int(ta), int(tb), alpha, A.handle, B.handle, beta, C_out.handle))
         return C_out
 
-    def syrk_rows(self, R, row_begin, row_count, A_out=None):
-        """A = R[row_begin:+row_count, :]' R[...] (row-major lower triangle of the n x n result)."""
-        if A_out is None:
-            A_out = DeviceMatrix(self, R.shape[1], R.shape[1])
-        self._ck(self.lib.mmg_mat_syrk_rows(self.h, R.handle, int(row_begin), int(row_count), A_out.handle))
-        return A_out
+    def quad_form_slots(self, n):
+        """Number of 256 x 256 blocks in the packed lower triangle of an n x n quadratic form (mmg_quad_form_slots)."""
+        return int(self.lib.mmg_quad_form_slots(int(n)))
+
+    def quad_form_tiles(self, R, slot_begin, slot_count, A_packed):
+        """Blocks [slot_begin, +slot_count) of A = R'R (int8 digit-plane products) into the packed matrix A_packed
+        ([>= slots x 65536]); returns the rigorous absolute error bound of the entries."""
+        err = C.c_double(0)
+        self._ck(self.lib.mmg_quad_form_tiles(self.h, R.handle, int(slot_begin), int(slot_count), A_packed.handle, C.byref(err)))
+        return err.value
 
     def scale_rows(self, A, d):
         d = np.ascontiguousarray(d, dtype=np.float64)
@@ -463,11 +495,12 @@ class Context(object):
         runs (mmg_kinship_gram_i8_host); anything else is uploaded first (ensure_snps).  Returns (m, n)."""
         if isinstance(snps, np.ndarray) and snps.ndim == 2 and snps.shape[0] > 0:
             a, key = self._array_key(snps)
-            if key != self._snps_key:
+            if key is None or key != self._snps_key:
                 self._snps_key = None
                 self._ck(self.lib.mmg_kinship_gram_i8_host(self.h, coding, impl_id(impl), _ptr(a), a.shape[0], a.shape[1],
                                                            a.shape[1], 1))
                 self._snps_key = key
+                self._snps_owner = snps if key is not None else None
                 return a.shape
         shape = self.ensure_snps(snps)
         self.kinship_gram(coding, impl=impl, reset=True)
@@ -483,6 +516,13 @@ class Context(object):
         p, n, ld = C.c_void_p(0), _i64(0), _i64(0)
         self._ck(self.lib.mmg_kinship_gram_ptr(self.h, C.byref(p), C.byref(n), C.byref(ld)))
         return p.value, n.value, ld.value
+
+    def kinship_gram_tri(self, direction):
+        """direction 0: pack the valid blocks of the Gram into one contiguous int32 buffer -> (device pointer, element count);
+        direction 1: unpack that buffer into the Gram again (mmg_kinship_gram_tri)."""
+        p, cnt = C.c_void_p(0), _i64(0)
+        self._ck(self.lib.mmg_kinship_gram_tri(self.h, int(direction), C.byref(p), C.byref(cnt)))
+        return p.value, cnt.value
 
     def kinship_finalize(self, coding, m_total, scaled, K=None):
         m, n = self.snps_shape()
@@ -557,6 +597,18 @@ class Context(object):
                                                   _ptr(out['xx'])))
         return out
 
+    def emmax_scan_quad_dev(self, A, v, h0_rss, n_p, packed=True, a_err=0.0, snp_begin=0, snp_count=None, out=None):
+        """The int8 scan with everything on the device: A (packed blocks or dense), v = R'y~ (DeviceMatrix of n values); the
+        results stay in `out`, a [5 x >= snp_count] DeviceMatrix with rows ps, f_stats, rss, var_perc, xx."""
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        if out is None:
+            out = DeviceMatrix(self, 5, snp_count)
+        self._ck(self.lib.mmg_emmax_scan_quad_dev(self.h, A.handle, int(bool(packed)), float(a_err), v.handle, float(h0_rss), float(n_p),
+                                                  int(snp_begin), int(snp_count), out.handle))
+        return out
+
     def emmax_scan_multi(self, Rs, V, h0_rss, n_p, snp_begin=0, snp_count=None, want=('ps', 'f_stats', 'rss', 'var_perc')):
         """T phenotypes in one launch: Rs = list of T rotations (DeviceMatrix), V [T x n_out], h0_rss [T].
         Returns a dict of [T x snp_count] arrays."""
@@ -607,6 +659,17 @@ def _as_int8(a):
                             '(there is no CPU fallback for real-valued dosages)')
         return _as_int8(r.astype(np.int64))
     raise TypeError('unsupported genotype dtype %r' % a.dtype)
+
+
+def resident(snps):
+    """Marks a genotype array (or every row of a list of rows) read-only and returns it: the opt-in that lets the library
+    keep its device copy across calls (Context.ensure_snps).  Make a copy, or set flags.writeable back, to edit it."""
+    if isinstance(snps, np.ndarray):
+        snps.flags.writeable = False
+    else:
+        for r in snps:
+            r.flags.writeable = False
+    return snps
 
 
 _default_ctx = {}

@@ -87,6 +87,8 @@ int mmg_destroy(mmg_ctx* ctx) {
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->kev0);
     cudaEventDestroy(ctx->kev1);
+    resolve_timers(ctx);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->ov0) cudaEventDestroy(ctx->ov0);
     if (ctx->ov1) cudaEventDestroy(ctx->ov1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -116,7 +118,15 @@ int mmg_device_info(mmg_ctx* ctx, char* name64, int* sm_count, int* cc_major, in
 
 int mmg_sync(mmg_ctx* ctx) {
     MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    resolve_timers(ctx);
+    return MMG_OK;
+}
+
+int mmg_stream_handle(mmg_ctx* ctx, void** stream) {
+    MMG_CHECK(ctx, ctx && stream, "mmg_stream_handle: bad argument");
+    *stream = (void*)ctx->stream;
     return MMG_OK;
 }
 
@@ -124,6 +134,7 @@ int64_t mmg_launch_count(mmg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int mmg_timer_get(mmg_ctx* ctx, const char* name, double* seconds, int64_t* calls) {
     MMG_CHECK(ctx, ctx && name, "bad argument");
+    resolve_timers(ctx);
     auto it = ctx->timers.find(name);
     if (seconds) *seconds = it == ctx->timers.end() ? 0.0 : it->second.seconds;
     if (calls) *calls = it == ctx->timers.end() ? 0 : it->second.calls;
@@ -131,6 +142,7 @@ int mmg_timer_get(mmg_ctx* ctx, const char* name, double* seconds, int64_t* call
 }
 int mmg_timer_reset(mmg_ctx* ctx) {
     MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    resolve_timers(ctx);
     ctx->timers.clear();
     return MMG_OK;
 }
@@ -172,20 +184,22 @@ int mmg_host_free(void* ptr) {
 // ======================================================================================================
 // device matrices
 // ======================================================================================================
-int mmg_mat_create(mmg_ctx* ctx, int64_t rows, int64_t cols, mmg_mat* out) {
-    MMG_CHECK(ctx, ctx && out && rows > 0 && cols > 0, "mmg_mat_create: bad shape %lld x %lld", (long long)rows, (long long)cols);
+int mmg_mat_alloc(mmg_ctx* ctx, int64_t rows, int64_t cols, int zero, mmg_mat* out) {
+    MMG_CHECK(ctx, ctx && out && rows > 0 && cols > 0, "mmg_mat_alloc: bad shape %lld x %lld", (long long)rows, (long long)cols);
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     MmgMat m;
     m.rows = rows;
     m.cols = cols;
     MMG_CUDA(ctx, cudaMallocAsync((void**)&m.d, (size_t)rows * cols * sizeof(double), ctx->stream));
-    MMG_CUDA(ctx, cudaMemsetAsync(m.d, 0, (size_t)rows * cols * sizeof(double), ctx->stream));
+    if (zero) MMG_CUDA(ctx, cudaMemsetAsync(m.d, 0, (size_t)rows * cols * sizeof(double), ctx->stream));
     *out = ctx->next_mat++;
     ctx->mats[*out] = m;
     return MMG_OK;
 }
+int mmg_mat_create(mmg_ctx* ctx, int64_t rows, int64_t cols, mmg_mat* out) { return mmg_mat_alloc(ctx, rows, cols, 1, out); }
 int mmg_mat_free(mmg_ctx* ctx, mmg_mat h) {
     MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     auto it = ctx->mats.find(h);
     if (it == ctx->mats.end()) return MMG_OK;
     cudaFreeAsync(it->second.d, ctx->stream);        // stream ordered: work already queued on the matrix completes first
@@ -202,6 +216,7 @@ int mmg_mat_shape(mmg_ctx* ctx, mmg_mat h, int64_t* rows, int64_t* cols) {
 int mmg_mat_upload(mmg_ctx* ctx, mmg_mat h, const double* host, int64_t ld_host) {
     MmgMat* m = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, m && host && ld_host >= m->cols, "mmg_mat_upload: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     StageTimer tm(ctx, "h2d");
     MMG_CUDA(ctx, cudaMemcpy2DAsync(m->d, m->cols * sizeof(double), host, ld_host * sizeof(double), m->cols * sizeof(double),
                                     m->rows, cudaMemcpyHostToDevice, ctx->stream));
@@ -211,16 +226,27 @@ int mmg_mat_upload(mmg_ctx* ctx, mmg_mat h, const double* host, int64_t ld_host)
 int mmg_mat_download(mmg_ctx* ctx, mmg_mat h, double* host, int64_t ld_host) {
     MmgMat* m = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, m && host && ld_host >= m->cols, "mmg_mat_download: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     StageTimer tm(ctx, "d2h");
     MMG_CUDA(ctx, cudaMemcpy2DAsync(host, ld_host * sizeof(double), m->d, m->cols * sizeof(double), m->cols * sizeof(double),
                                     m->rows, cudaMemcpyDeviceToHost, ctx->stream));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMG_OK;
 }
+int mmg_mat_download_rows(mmg_ctx* ctx, mmg_mat h, int64_t row0, int64_t row_step, int64_t nrows, double* host, int64_t ld_host) {
+    MmgMat* m = ctx ? get_mat(ctx, h) : nullptr;
+    MMG_CHECK(ctx, m && host && ld_host >= m->cols && row0 >= 0 && row_step >= 1 && nrows >= 1 && row0 + (nrows - 1) * row_step < m->rows,
+              "mmg_mat_download_rows: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm(ctx, "d2h");
+    MMG_CUDA(ctx, cudaMemcpy2DAsync(host, ld_host * sizeof(double), m->d + row0 * m->cols, row_step * m->cols * sizeof(double),
+                                    m->cols * sizeof(double), nrows, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
 int mmg_mat_device_ptr(mmg_ctx* ctx, mmg_mat h, void** dptr, int64_t* ld) {
     MmgMat* m = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, m && dptr, "mmg_mat_device_ptr: bad argument");
-    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *dptr = m->d;
     if (ld) *ld = m->cols;
     return MMG_OK;
@@ -228,12 +254,14 @@ int mmg_mat_device_ptr(mmg_ctx* ctx, mmg_mat h, void** dptr, int64_t* ld) {
 int mmg_mat_copy(mmg_ctx* ctx, mmg_mat dst, mmg_mat src) {
     MmgMat *d = ctx ? get_mat(ctx, dst) : nullptr, *s = ctx ? get_mat(ctx, src) : nullptr;
     MMG_CHECK(ctx, d && s && d->rows == s->rows && d->cols == s->cols, "mmg_mat_copy: shape mismatch");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     MMG_CUDA(ctx, cudaMemcpyAsync(d->d, s->d, (size_t)d->rows * d->cols * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return MMG_OK;
 }
 int mmg_mat_gemm(mmg_ctx* ctx, int ta, int tb, double alpha, mmg_mat Ah, mmg_mat Bh, double beta, mmg_mat Ch) {
     MmgMat *A = ctx ? get_mat(ctx, Ah) : nullptr, *B = ctx ? get_mat(ctx, Bh) : nullptr, *C = ctx ? get_mat(ctx, Ch) : nullptr;
     MMG_CHECK(ctx, A && B && C, "mmg_mat_gemm: unknown handle");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t m = ta ? A->cols : A->rows, k = ta ? A->rows : A->cols;
     const int64_t kb = tb ? B->cols : B->rows, n = tb ? B->rows : B->cols;
     MMG_CHECK(ctx, k == kb && C->rows == m && C->cols == n, "mmg_mat_gemm: shape mismatch (%lldx%lld)*(%lldx%lld)->(%lldx%lld)",
@@ -244,31 +272,10 @@ int mmg_mat_gemm(mmg_ctx* ctx, int ta, int tb, double alpha, mmg_mat Ah, mmg_mat
                                 (int)k, &alpha, B->d, (int)B->cols, A->d, (int)A->cols, &beta, C->d, (int)C->cols));
     return MMG_OK;
 }
-// A = R[row_begin : row_begin + row_count, :]' R[...]   (row-major LOWER triangle of the n x n matrix A; the strict upper
-// triangle is left as it was).  Row blocks of R are contiguous, so ranks that each take a block of the n_out rows of the
-// rotation and sum their A's (all-reduce) get R'R with 1/ranks of the flops each.
-int mmg_mat_syrk_rows(mmg_ctx* ctx, mmg_mat Rh, int64_t row_begin, int64_t row_count, mmg_mat Ah) {
-    MmgMat* R = ctx ? get_mat(ctx, Rh) : nullptr;
-    MmgMat* A = ctx ? get_mat(ctx, Ah) : nullptr;
-    MMG_CHECK(ctx, R && A, "mmg_mat_syrk_rows: unknown matrix handle");
-    MMG_CHECK(ctx, A->rows == R->cols && A->cols == R->cols, "A must be %lld x %lld", (long long)R->cols, (long long)R->cols);
-    MMG_CHECK(ctx, row_begin >= 0 && row_count >= 0 && row_begin + row_count <= R->rows, "row block out of range");
-    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
-    StageTimer tm(ctx, "scan_prep");
-    const int64_t n = R->cols;
-    const double one = 1.0, zero = 0.0;
-    if (row_count == 0) {
-        MMG_CUDA(ctx, cudaMemsetAsync(A->d, 0, (size_t)n * n * sizeof(double), ctx->stream));
-        return MMG_OK;
-    }
-    // the row block is the column-major n x row_count matrix Rc; column-major UPPER of Rc Rc' = row-major LOWER of A
-    MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)row_count, &one, R->d + row_begin * n, (int)n,
-                                &zero, A->d, (int)n));
-    return MMG_OK;
-}
 int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat h, const double* d_host) {
     MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, A && d_host, "mmg_mat_scale_rows: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     MMG_TRY(ensure_scratch(ctx, A->rows * sizeof(double)));
     MMG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, d_host, A->rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((unsigned)((A->cols + 255) / 256), (unsigned)A->rows);
@@ -280,6 +287,7 @@ int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat h, const double* d_host) {
 int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat h, double alpha) {
     MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, A && A->rows == A->cols, "mmg_mat_add_diag: needs a square matrix");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     add_diag_kernel<<<(unsigned)((A->rows + 255) / 256), 256, 0, ctx->stream>>>(A->d, A->cols, (int)A->rows, alpha);
     return launch_check(ctx, "add_diag_kernel");
 }
@@ -287,6 +295,7 @@ int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat h, double alpha) {
 int mmg_mat_scale_k(mmg_ctx* ctx, mmg_mat h, double* scalar) {
     MmgMat* K = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, K && K->rows == K->cols, "mmg_mat_scale_k: needs a square matrix");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     MMG_TRY(scale_k_device(ctx, K, scalar));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMG_OK;
@@ -295,6 +304,7 @@ int mmg_mat_scale_k(mmg_ctx* ctx, mmg_mat h, double* scalar) {
 int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat h, double* w_host, double* seconds) {
     MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, A && A->rows == A->cols && w_host, "mmg_mat_syevd: needs a square matrix and w_host");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t n = A->rows;
     StageTimer tm(ctx, "syevd");
     cusolverDnParams_t params = nullptr;
@@ -333,6 +343,7 @@ int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat h, double* w_host, double* seconds) {
     free(buf_host);
     cusolverDnDestroyParams(params);
     tm.stop();
+    resolve_timers(ctx);
     if (seconds) *seconds = ctx->timers["syevd"].seconds;
     return rc;
 }
@@ -342,6 +353,7 @@ int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat h, double* w_host, double* seconds) {
 // ======================================================================================================
 int mmg_snps_free(mmg_ctx* ctx) {
     MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->snps);
     ctx->snps = nullptr;
@@ -366,6 +378,7 @@ int mmg_snps_reserve(mmg_ctx* ctx, int64_t m, int64_t n) {
 int mmg_snps_write(mmg_ctx* ctx, int64_t row0, const int8_t* snps, int64_t rows, int64_t ld) {
     MMG_CHECK(ctx, ctx && ctx->snps && snps && row0 >= 0 && rows >= 0 && row0 + rows <= ctx->m && ld >= ctx->n,
               "mmg_snps_write: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->snps_absmax = -1;
     StageTimer tm(ctx, "h2d");
     // one strided DMA; measured at the PCIe rate (52 GB/s from page-locked memory), a staged 1-D copy + re-pitch kernel was no faster
@@ -381,6 +394,7 @@ int mmg_snps_upload(mmg_ctx* ctx, const int8_t* snps, int64_t m, int64_t n, int6
 }
 int mmg_snps_upload_rows(mmg_ctx* ctx, const int8_t* const* rows, int64_t m, int64_t n) {
     MMG_CHECK(ctx, ctx && rows, "mmg_snps_upload_rows: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     MMG_TRY(mmg_snps_reserve(ctx, m, n));
     ctx->snps_absmax = -1;
     StageTimer tm(ctx, "h2d");
@@ -427,6 +441,7 @@ int mmg_snps_device_ptr(mmg_ctx* ctx, void** dptr, int64_t* pitch) {
 }
 int mmg_snps_row_sums(mmg_ctx* ctx, int64_t* sums_host, int64_t* sumsq_host) {
     MMG_CHECK(ctx, ctx && ctx->snps && sums_host, "mmg_snps_row_sums: no resident genotypes");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     MMG_TRY(ensure_scratch(ctx, 2 * ctx->m * sizeof(long long)));
     long long* s = (long long*)ctx->scratch;
     long long* q = s + ctx->m;

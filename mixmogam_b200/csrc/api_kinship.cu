@@ -394,6 +394,25 @@ int mmg_kinship_gram_ptr(mmg_ctx* ctx, void** dptr, int64_t* n, int64_t* ld) {
     return MMG_OK;
 }
 
+// direction 0: pack the valid 256 x 256 blocks of the Gram (block row <= block column) into one contiguous int32 buffer and
+// return its device pointer and element count -- the buffer a multi-GPU caller all-reduces (half the bytes of the padded
+// square); direction 1: unpack the (reduced) buffer back into the Gram.  Stream ordered, no host synchronisation.
+int mmg_kinship_gram_tri(mmg_ctx* ctx, int direction, void** dptr, int64_t* count) {
+    MMG_CHECK(ctx, ctx && ctx->G, "mmg_kinship_gram_tri: no Gram resident");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t T = ctx->g_pad / 256, slots = T * (T + 1) / 2;
+    MMG_TRY(ensure_scratch(ctx, slots * 65536 * (int64_t)sizeof(int32_t)));
+    StageTimer tm(ctx, "finalize");
+    if (direction == 0)
+        gram_tri_pack_kernel<false><<<(unsigned)slots, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, (int32_t*)ctx->scratch);
+    else
+        gram_tri_pack_kernel<true><<<(unsigned)slots, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, (int32_t*)ctx->scratch);
+    MMG_TRY(launch_check(ctx, "gram_tri_pack_kernel"));
+    if (dptr) *dptr = ctx->scratch;
+    if (count) *count = slots * 65536;
+    return MMG_OK;
+}
+
 int mmg_kinship_gram_download(mmg_ctx* ctx, int32_t* G_host) {
     MMG_CHECK(ctx, ctx && ctx->G && G_host, "mmg_kinship_gram_download: no Gram resident");
     const int n = (int)ctx->n;

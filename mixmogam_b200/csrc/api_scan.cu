@@ -190,21 +190,48 @@ static double scan_tc_tol() {
     return t > 0.0 ? t : 1e-7;
 }
 
-// Digit planes of the strict lower triangle of A = R'R (doubled) into Bq (S planes of [n_padN x ldq]), diag(A) into
-// d_dg and v = R'y into d_v; returns the binary exponent E used for the scaling.  `A` is an n x n FP64 work matrix.
-// A = R'R as exact int8 digit-plane products on the tensor cores (scan_tc.cuh, "A = R'R on the int8 tensor cores"); A_work is a
-// zero-filled [n_padM x n_padM] FP64 buffer whose lower-triangular tiles are written.  *err_out: absolute error bound of its entries.
-static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_work, int64_t n_padM, unsigned long long* d_amax, double* err_out) {
+// max |r| of a contiguous FP64 array -> bits of a non-negative double (grid-stride, 16-byte loads)
+static __global__ void __launch_bounds__(256) array_amax_kernel(const double2* __restrict__ p, int64_t n2, const double* __restrict__ last,
+                                                                unsigned long long* __restrict__ amax_bits) {
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = p[i];
+        m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+    }
+    if (last && blockIdx.x == 0 && threadIdx.x == 0) m = fmax(m, fabs(*last));     // odd element count
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(amax_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// number of 256 x 256 blocks in the lower triangle of the padded n x n quadratic form
+static int64_t qa_slots(int64_t n) {
+    const int64_t T = round_up(n, QA_TILE) / QA_TILE;
+    return T * (T + 1) / 2;
+}
+
+// A = R'R as exact int8 digit-plane products on the tensor cores (scan_tc.cuh, "A = R'R on the int8 tensor cores"), written in
+// the PACKED block layout (qa_index): blocks [slot_begin, slot_begin + slot_count) of the lower triangle go to A_slots, which
+// points at block slot_begin.  Every block costs the same (the contraction runs over all n_out rows of R), so ranks that take
+// equal slot ranges are balanced.  *err_out: absolute error bound of the entries.
+static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_slots, int64_t slot_begin, int64_t slot_count, unsigned long long* d_amax,
+                          double* err_out) {
     const int64_t n = ctx->n, n_out = R->rows;
+    const int64_t n_padM = round_up(n, QA_TILE);
     MMG_CHECK(ctx, n_out < 131072, "R'R on the int8 pipe: contraction too long for exact int32 accumulation");
     MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
-    mat_amax_kernel<<<dim3(8, (unsigned)n_out), 256, 0, ctx->stream>>>(R->d, n, (int)n_out, (int)n, d_amax);
-    MMG_TRY(launch_check(ctx, "mat_amax_kernel"));
+    {
+        const int64_t cnt = n_out * n;
+        array_amax_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const double2*)R->d, cnt / 2, (cnt & 1) ? R->d + cnt - 1 : nullptr, d_amax);
+        MMG_TRY(launch_check(ctx, "array_amax_kernel"));
+    }
     double rmax = 0.0;
     MMG_CUDA(ctx, cudaMemcpyAsync(&rmax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (!std::isfinite(rmax)) return fail(ctx, MMG_EVALUE, "scan: the rotation is not finite (max |r| = %g)", rmax);
     const int F = digit256_exponent(rmax);
+    *err_out = ozaki_error_bound(n_out) * ldexp(1.0, 2 * F);
+    slot_count = std::max<int64_t>(0, std::min(slot_count, qa_slots(n) - slot_begin));
+    if (slot_count == 0) return MMG_OK;
     const int64_t op_pitch = round_up(n_out, TC_BK);
     DevBuf Op;
     MMG_CUDA(ctx, Op.alloc(ctx->stream, (size_t)OZ_PLANES * n_padM * op_pitch));
@@ -212,64 +239,54 @@ static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_work, int64_t
     ozaki_planes_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n_out + 31) / 32)), 256, 0, ctx->stream>>>(
         R->d, n, (int)n_out, (int)n, ldexp(1.0, -F), Op.as<int8_t>(), n_padM, op_pitch);
     MMG_TRY(launch_check(ctx, "ozaki_planes_kernel"));
-    MMG_CUDA(ctx, cudaMemsetAsync(A_work, 0, (size_t)n_padM * n_padM * sizeof(double), ctx->stream));
-    // tile table: row-tile pairs (im, im + 1) x column tile jn that meet the lower triangle (rows >= columns), 28 (p, q) planes each
-    const int tiles_n = (int)(n_padM / TC_BN), tiles_m = (int)(n_padM / TC_BM), KB = (int)(op_pitch / TC_BK);
-    // Entry order = order in which the co-resident clusters pick the output tiles up.  The operands are streamed from L2 / HBM
-    // by every tile (79 K-blocks only), so the clusters of one wave should share them: the lower-triangular (row-pair, column
-    // tile) grid is walked in blocks of 9 x 8 (72 ~ the 74 co-resident clusters), whose operand rows for one plane pair are
-    // 9 x 2.6 + 8 x 2.6 = 44 MB -- L2 resident -- instead of row by row (a whole 103 MB plane per tile step).
+    MMG_CUDA(ctx, cudaMemsetAsync(A_slots, 0, (size_t)slot_count * QA_TILE_ELEMS * sizeof(double), ctx->stream));
+    // tile table: one entry per block (J, I), I <= J, in slot order: the row-tile pair (2 J, 2 J + 1) x column tile I, its 28
+    // (p, q) plane pairs level by level (p + q = lv share the weight 2^2F 256^-(lv+2)).  The lv + 1 pairs of a level are CHAINED
+    // into one int32 accumulator (7 n_out 128^2 < 2^31), so a block is read-modify-written 7 times, not 28 -- the FP64
+    // read-modify-write of the epilogue (a row per thread, 32 sectors per access) was what bounded this kernel.  (Walking the
+    // blocks in L2-sized groups instead of slot order was measured and changed nothing: operand traffic is not the bound.)
+    const int KB = (int)(op_pitch / TC_BK);
     std::vector<TcTile> tiles;
-    std::vector<std::pair<int, int>> order;                     // (jn, im)
-    {
-        const int BI = std::max(1, env_int("MMG_OZAKI_BLOCK_I", 9)), BJ = std::max(1, env_int("MMG_OZAKI_BLOCK_J", 8));
-        const int pairs_m = tiles_m / 2;
-        for (int bi = 0; bi < pairs_m; bi += BI)
-            for (int bj = 0; bj < tiles_n; bj += BJ)
-                for (int ip = bi; ip < std::min(pairs_m, bi + BI); ++ip)
-                    for (int jn = bj; jn < std::min(tiles_n, bj + BJ); ++jn)
-                        if (ip >= jn) order.emplace_back(jn, 2 * ip);
-    }
     int entries = 0, per_entry = 0;
     const bool chain = env_int("MMG_OZAKI_CHAIN", 1) != 0 && (double)OZ_LEVELS * (double)n_out * 16384.0 < 2147483647.0;
-    for (const auto& ji : order) {
-        const int jn = ji.first, im = ji.second;
-        {
-            // level by level (p + q = lv share the weight 2^2F 256^-(lv+2)): the lv + 1 plane pairs of a level are CHAINED into one
-            // int32 accumulator (7 n_out 128^2 < 2^31), so an output tile is read-modify-written 7 times, not 28 -- the FP64
-            // read-modify-write of the epilogue (a row per thread, 32 sectors per access) was what bounded this kernel
-            per_entry = 0;
-            for (int lv = 0; lv < OZ_LEVELS; ++lv)
-                for (int p = 0; p <= lv; ++p) {
-                    const int q = lv - p;
-                    if (p >= OZ_PLANES || q >= OZ_PLANES) continue;
-                    TcTile tl{};
-                    tl.m0 = (int)((int64_t)p * n_padM + (int64_t)im * TC_BM);
-                    tl.n0 = (int)((int64_t)q * n_padM + (int64_t)jn * TC_BN);
-                    tl.kb0 = 0;
-                    tl.kb1 = KB;
-                    tl.aux0 = p;
-                    tl.aux1 = q;
-                    tl.flags = (p < lv && chain) ? TC_TILE_CHAIN : 0;       // the pair (lv, 0) ends the chain of its level
-                    tiles.push_back(tl);
-                    ++per_entry;
-                }
-            ++entries;
-        }
+    int J = (int)((std::sqrt(8.0 * (double)slot_begin + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(J + 1) * (J + 2) / 2 <= slot_begin) ++J;
+    while ((int64_t)J * (J + 1) / 2 > slot_begin) --J;
+    int I = (int)(slot_begin - (int64_t)J * (J + 1) / 2);
+    for (int64_t sl = 0; sl < slot_count; ++sl) {
+        per_entry = 0;
+        for (int lv = 0; lv < OZ_LEVELS; ++lv)
+            for (int p = 0; p <= lv; ++p) {
+                const int q = lv - p;
+                if (p >= OZ_PLANES || q >= OZ_PLANES) continue;
+                TcTile tl{};
+                tl.m0 = (int)((int64_t)p * n_padM + (int64_t)(2 * J) * TC_BM);
+                tl.n0 = (int)((int64_t)q * n_padM + (int64_t)I * TC_BN);
+                tl.kb0 = 0;
+                tl.kb1 = KB;
+                tl.aux0 = p;
+                tl.aux1 = q;
+                tl.flags = (p < lv && chain) ? TC_TILE_CHAIN : 0;       // the pair (lv, 0) ends the chain of its level
+                tiles.push_back(tl);
+                ++per_entry;
+            }
+        ++entries;
+        if (++I > J) { I = 0; ++J; }
     }
     MMG_TRY(ensure_tiles(ctx, tiles));
     CUtensorMap tmA, tmB;
     MMG_TRY(make_tmap_u8(ctx, &tmA, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BM));
     MMG_TRY(make_tmap_u8(ctx, &tmB, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BN / 2));
     OzakiEpi::Params ep{};
-    ep.A = A_work;
-    ep.ld = n_padM;
+    ep.A = A_slots;
+    ep.ld = 0;
     ep.n_padM = n_padM;
+    ep.packed = 1;
+    ep.slot0 = slot_begin;
     for (int sl = 0; sl < 2 * OZ_PLANES; ++sl) ep.w[sl] = ldexp(1.0, 2 * F - 8 * (sl + 2));
     MMG_TRY((launch_tc_gemm<OzakiEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, entries * 2, per_entry, per_entry, 0, TC_BM, ep,
                                          "tc_gemm_i8_kernel<OzakiEpi,2>")));
-    *err_out = ozaki_error_bound(n_out) * ldexp(1.0, 2 * F);   // (Op is released in stream order when this returns)
-    return MMG_OK;
+    return MMG_OK;                                             // (Op is released in stream order when this returns)
 }
 
 // MMG_QUAD_A = int8 (default: exact digit-plane products on the int8 tensor pipe) | dsyrk (cuBLAS, FP64 tensor pipe)
@@ -279,33 +296,49 @@ static bool quad_a_int8() {
     const char* e = getenv("MMG_QUAD_A");
     return !(e && strcmp(e, "dsyrk") == 0);
 }
+static bool quad_use_int8() { return quad_a_int8() && scan_tc_tol() >= 1e-9; }
 
-static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const double* A_given, double* A_work, int64_t lda_work,
+// A quadratic form handed to the scan: dense row-major (lower triangle valid) or packed 256 x 256 blocks (qa_index)
+struct QuadA {
+    const double* d = nullptr;
+    int64_t ld = 0;
+    bool packed = false;
+    double err = 0.0;         // absolute error bound of its entries (0: formed in FP64)
+};
+
+// Digit planes of the strict lower triangle of A = R'R (doubled) into Bq (S planes of [n_padN x ldq]), diag(A) into
+// d_dg and (when the rotation is given and d_y set) v = R'y into d_v; returns the binary exponent E used for the scaling.
+// `given` (optional): the caller already holds A.  Otherwise A is formed from R into A_work: packed blocks by the int8
+// digit-plane product, or dense [lda_work x lda_work] by cuBLAS dsyrk (A_work must hold max of the two layouts).
+static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const QuadA* given, double* A_work, int64_t lda_work,
                         unsigned long long* d_amax, int S, int8_t* Bq, int64_t n_padN, int64_t ldq, double* d_v, double* d_dg, int* E_out,
                         double* errA_out) {
     const int64_t n = ctx->n;
     const double one = 1.0, zero = 0.0;
-    const double* A = A_given;
-    int64_t lda = n;
-    *errA_out = 0.0;
-    if (!A_given) {
+    QuadA A;
+    if (given) {
+        A = *given;
+    } else {
         const int64_t n_out = R->rows;
-        if (quad_a_int8() && scan_tc_tol() >= 1e-9) {
-            MMG_TRY(quad_form_int8(ctx, R, A_work, lda_work, d_amax, errA_out));
+        if (quad_use_int8()) {
+            MMG_TRY(quad_form_int8(ctx, R, A_work, 0, qa_slots(n), d_amax, &A.err));
+            A.packed = true;
         } else {
             // A = R'R: R row-major [n_out x n] is the column-major n x n_out matrix Rc; column-major UPPER of Rc Rc'
             // is the row-major LOWER triangle A[j][i], i <= j -- exactly the operand the slices are cut from.
             MMG_CUBLAS(ctx, cublasDsyrk(ctx->cublas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, &zero, A_work,
                                         (int)lda_work));
+            A.ld = lda_work;
         }
         // v = R' y~  (x~.y~ = x.v)
         if (d_y) MMG_CUBLAS(ctx, cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1));
-        A = A_work;
-        lda = lda_work;
+        A.d = A_work;
     }
+    *errA_out = A.err;
     MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
     dim3 agrid(8, (unsigned)n);
-    quad_amax_kernel<<<agrid, 256, 0, ctx->stream>>>(A, lda, (int)n, d_amax);
+    if (A.packed) quad_amax_kernel<true><<<agrid, 256, 0, ctx->stream>>>(A.d, A.ld, (int)n, d_amax);
+    else quad_amax_kernel<false><<<agrid, 256, 0, ctx->stream>>>(A.d, A.ld, (int)n, d_amax);
     MMG_TRY(launch_check(ctx, "quad_amax_kernel"));
     double amax = 0.0;
     MMG_CUDA(ctx, cudaMemcpyAsync(&amax, d_amax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -313,13 +346,13 @@ static int quad_prepare(mmg_ctx* ctx, const MmgMat* R, const double* d_y, const 
     if (!std::isfinite(amax)) return fail(ctx, MMG_EVALUE, "scan: R'R is not finite (max |a| = %g)", amax);
     const int E = digit256_exponent(amax);                // |2 a| 2^-E <= 0.498 (a diagonal R'R has no off-diagonal digits at all)
     dim3 sgrid((unsigned)((n + 255) / 256), (unsigned)n);
-    quad_slice_kernel<<<sgrid, 256, 0, ctx->stream>>>(A, lda, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq, d_dg);
+    if (A.packed) quad_slice_kernel<true><<<sgrid, 256, 0, ctx->stream>>>(A.d, A.ld, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq, d_dg);
+    else quad_slice_kernel<false><<<sgrid, 256, 0, ctx->stream>>>(A.d, A.ld, (int)n, ldexp(1.0, -E), S, Bq, n_padN, ldq, d_dg);
     MMG_TRY(launch_check(ctx, "quad_slice_kernel"));
     *E_out = E;
     return MMG_OK;
 }
 
-// one launch of the quadratic-form scan over resident rows [snp_begin, +snp_count) with S of the S_alloc cut planes
 static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* Bq, int64_t n_padN, int64_t ldq, int64_t snp_begin,
                           int64_t snp_count, QuadEpi::Params ep, unsigned* d_wave_sync) {
     int cs = env_int("MMG_SCAN_CLUSTER", 2);
@@ -420,12 +453,13 @@ static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* B
 // T phenotypes (each with its own rotation R_t, residual y~_t and h0_rss_t) in one launch.  Device outputs are
 // [T][snp_count]; any may be NULL.
 //
-// A_given / v_given (T = 1 only): the quadratic form A = R'R (row-major lower triangle valid) and v = R'y~ were formed by
-// the caller -- the multi-GPU path builds A from per-rank row blocks of R and an all-reduce (parallel.py) instead of
-// repeating the n^3 product on every rank; Rs and V are then unused.
+// A_given / v_given (T = 1 only): the quadratic form A = R'R (dense or packed blocks, lower triangle valid) and v = R'y~ were
+// formed by the caller -- the multi-GPU path lets every rank form a range of the blocks of A on the int8 pipe and all-gathers
+// them (parallel.py) instead of repeating the n^3 product on every rank; Rs and V are then unused.  v_given is a device pointer
+// when v_on_device, a host pointer otherwise.
 static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const double* V, const double* h0_rss, double n_p, double lbeta,
                        int64_t snp_begin, int64_t snp_count, double* d_xx, double* d_xy, double* d_rss, double* d_f, double* d_p,
-                       double* d_vp, const MmgMat* A_given = nullptr, const double* v_given = nullptr) {
+                       double* d_vp, const QuadA* A_given = nullptr, const double* v_given = nullptr, bool v_on_device = false) {
     const int64_t n = ctx->n, n_out = A_given ? 1 : Rs[0]->rows;
     MMG_TRY(scan_tc_check_domain(ctx));
     const int S_fixed = scan_tc_fixed_slices();
@@ -435,8 +469,10 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     const int64_t plane = n_padN * ldq;
     MMG_CHECK(ctx, (int64_t)T * S_alloc * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
     DevBuf A, Bq, vec;
-    const int64_t lda_work = round_up(n, TC_BN);               // padded so that the int8 R'R epilogue needs no bounds checks
-    if (!A_given) MMG_CUDA(ctx, A.alloc(ctx->stream, (size_t)lda_work * lda_work * sizeof(double)));
+    const int64_t lda_work = round_up(n, TC_BN);               // dense (dsyrk) layout of A; the packed int8 product needs less
+    if (!A_given)
+        MMG_CUDA(ctx, A.alloc(ctx->stream, quad_use_int8() ? (size_t)qa_slots(n) * QA_TILE_ELEMS * sizeof(double)
+                                                           : (size_t)lda_work * lda_work * sizeof(double)));
     MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S_alloc * plane));
     // vec: v[T][n_padN] | dg[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | bscale[T] | amax | rho | wave counter
     const int64_t nd = 2 * (int64_t)T * n_padN + (int64_t)T * n_out + 3 * T + 3;
@@ -452,7 +488,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     unsigned* d_wave = (unsigned*)(d_rho + 1);
     MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)nd * sizeof(double), ctx->stream));
     MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)T * S_alloc * plane, ctx->stream));
-    if (A_given) MMG_CUDA(ctx, cudaMemcpyAsync(d_v, v_given, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (A_given) MMG_CUDA(ctx, cudaMemcpyAsync(d_v, v_given, (size_t)n * sizeof(double), v_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     else MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<double> escale((size_t)T), bscale((size_t)T), errA((size_t)T, 0.0);
@@ -498,7 +534,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     }
     for (int t = 0; t < T; ++t) {
         int E = 0;
-        MMG_TRY(quad_prepare(ctx, A_given ? nullptr : Rs[t], pre_launched ? nullptr : d_y + (int64_t)t * n_out, A_given ? A_given->d : nullptr, A.as<double>(), lda_work,
+        MMG_TRY(quad_prepare(ctx, A_given ? nullptr : Rs[t], pre_launched ? nullptr : d_y + (int64_t)t * n_out, A_given, A.as<double>(), lda_work,
                              d_amax, S_alloc, Bq.as<int8_t>() + (int64_t)t * S_alloc * plane, n_padN, ldq, d_v + (int64_t)t * n_padN,
                              d_dg + (int64_t)t * n_padN, &E, &errA[(size_t)t]));
         escale[t] = ldexp(1.0, E);
@@ -544,27 +580,34 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return MMG_OK;
     };
+    // bound(S) / bound(S0), worst phenotype: 256 per plane down to the floor set by the error of A itself
+    auto bound_ratio = [&](int planes, int planes0) {
+        double r = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const double c = 0.5 * DIGIT256_REM * escale[t];
+            r = std::max(r, (c * ldexp(1.0, -8 * planes) + errA[(size_t)t]) / (c * ldexp(1.0, -8 * planes0) + errA[(size_t)t]));
+        }
+        return r;
+    };
 
     int S = S_fixed ? S_fixed : S_alloc;                        // short scans: no pilot, every plane that was cut
     if (!S_fixed && snp_count >= 4 * QS_PILOT_ROWS) {
-        // pilot: bound of the first rows with few planes; the bound scales exactly by 256 per plane
-        QuadEpi::Params pp = ep;
-        pp.xx = pp.xy = pp.rss = pp.f = pp.p = pp.var_perc = nullptr;
-        MMG_TRY(set_bscale(QS_PILOT_PLANES));
-        MMG_TRY(scan_tc_launch(ctx, T, QS_PILOT_PLANES, S_alloc, Bq.p, n_padN, ldq, snp_begin, QS_PILOT_ROWS, pp, d_wave));
-        double rho = 0.0;
-        MMG_TRY(read_rho(&rho));
-        // bound(S) / bound(pilot planes), worst phenotype: 256 per plane down to the floor set by the error of A itself
-        auto bound_ratio = [&](int planes) {
-            double r = 0.0;
-            for (int t = 0; t < T; ++t) {
-                const double c = 0.5 * DIGIT256_REM * escale[t];
-                r = std::max(r, (c * ldexp(1.0, -8 * planes) + errA[(size_t)t]) / (c * ldexp(1.0, -8 * QS_PILOT_PLANES) + errA[(size_t)t]));
-            }
-            return r;
-        };
-        S = QS_PILOT_PLANES;
-        while (S < S_alloc && rho * bound_ratio(S) * QS_PILOT_HEADROOM > tol) ++S;
+        const bool use_hint = env_int("MMG_SCAN_HINT", 1) != 0 && ctx->scan_slices_hint > 0 && ctx->scan_hint_n == n;
+        if (use_hint) {
+            // the previous scan of this shape certified its bound with this many planes (with head-room): start there.  The full
+            // launch measures the bound over every SNP anyway and is repeated with one more plane if one violates it.
+            S = std::min(S_alloc, ctx->scan_slices_hint);
+        } else {
+            // pilot: bound of the first rows with few planes; the bound scales exactly by 256 per plane
+            QuadEpi::Params pp = ep;
+            pp.xx = pp.xy = pp.rss = pp.f = pp.p = pp.var_perc = nullptr;
+            MMG_TRY(set_bscale(QS_PILOT_PLANES));
+            MMG_TRY(scan_tc_launch(ctx, T, QS_PILOT_PLANES, S_alloc, Bq.p, n_padN, ldq, snp_begin, QS_PILOT_ROWS, pp, d_wave));
+            double rho = 0.0;
+            MMG_TRY(read_rho(&rho));
+            S = QS_PILOT_PLANES;
+            while (S < S_alloc && rho * bound_ratio(S, QS_PILOT_PLANES) * QS_PILOT_HEADROOM > tol) ++S;
+        }
     }
     double rho = 0.0;
     for (;;) {
@@ -579,16 +622,24 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     }
     ctx->last_scan_slices = S;
     ctx->last_scan_rho = rho;
+    if (!S_fixed && snp_count >= 4 * QS_PILOT_ROWS) {
+        // next call: one plane fewer when the measured bound says it would still certify with the pilot's head-room
+        ctx->scan_hint_n = n;
+        ctx->scan_slices_hint = (S > 1 && rho <= tol && rho * bound_ratio(S - 1, S) * QS_PILOT_HEADROOM <= tol) ? S - 1 : S;
+    }
     // a tolerance below what the int8 product of A can certify (its own error bound is a floor of ~1e-10 relative at n = 10k):
     // once more with A from the FP64 dsyrk
     bool int8_floor = false;
     for (double e : errA) int8_floor |= e > 0.0;
-    if (!S_fixed && rho > tol && int8_floor && !g_quad_force_dsyrk) {
+    if (!S_fixed && rho > tol && int8_floor && !g_quad_force_dsyrk && !A_given) {
         g_quad_force_dsyrk = true;
-        const int rc = scan_tc_run(ctx, T, Rs, V, h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp, A_given, v_given);
+        const int rc = scan_tc_run(ctx, T, Rs, V, h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp);
         g_quad_force_dsyrk = false;
         return rc;
     }
+    if (!S_fixed && rho > tol && !env_int("MMG_TC_ALLOW_UNCERTIFIED", 0))
+        return fail(ctx, MMG_EVALUE, "int8 scan: the certified truncation bound on x~.x~ is %.3g after %d digit planes, above the tolerance %.3g "
+                    "(MMG_TC_TOL); use scan_impl='dmma', a larger tolerance, or MMG_TC_ALLOW_UNCERTIFIED=1 to take the result as is", rho, S, tol);
     return MMG_OK;
 }
 
@@ -801,9 +852,24 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
     return MMG_OK;
 }
 
-// The int8 scan when the caller already holds the quadratic form A = R'R (n x n, row-major lower triangle valid) and
-// v = R'y~: the multi-GPU path forms A from per-rank row blocks of R (mmg_mat_syrk_rows) and one all-reduce instead of
-// repeating the 2 n^3 / 2 flops of the product on every rank (28 ms at n = 10k, more than an 8-way shard of the scan itself).
+// The int8 scan when the caller already holds the quadratic form A = R'R and v = R'y~: the multi-GPU path forms A once across
+// the ranks (mmg_quad_form_tiles + all-gather) instead of repeating the 2 n^3 / 2 flops of the product on every rank (12.5 ms at
+// n = 10k, as long as an 8-way shard of the scan itself).  Device outputs; the two ABI entries below differ in where v comes from
+// and where the results go.
+static int scan_quad_given(mmg_ctx* ctx, const QuadA& A, const double* v, bool v_on_device, double h0_rss, double n_p, int64_t snp_begin,
+                           int64_t snp_count, double* d_out /* [5 x ld]: p, f, rss, var_perc, xx */, int64_t ld) {
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+    DevBuf xy;
+    MMG_CUDA(ctx, xy.alloc(ctx->stream, (size_t)snp_count * sizeof(double)));
+    StageTimer tm(ctx, "scan");
+    MMG_TRY(scan_tc_run(ctx, 1, nullptr, nullptr, &h0_rss, n_p, lbeta, snp_begin, snp_count, d_out + 4 * ld, xy.as<double>(), d_out + 2 * ld,
+                        d_out + ld, d_out, d_out + 3 * ld, &A, v, v_on_device));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);           // scan_tc_run ends with a stream synchronisation
+    ctx->last_scan_ms = ms;
+    return MMG_OK;
+}
+
 int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat Ah, const double* v, double h0_rss, double n_p, int64_t snp_begin,
                             int64_t snp_count, double* ps, double* f_stats, double* rss, double* var_perc, double* xx) {
     MmgMat* A = ctx ? get_mat(ctx, Ah) : nullptr;
@@ -812,32 +878,60 @@ int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat Ah, const double* v, double h0
               (long long)A->rows, (long long)A->cols);
     MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
-    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
-    DevBuf out;      // xx, xy, rss, f, p, var_perc
-    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)6 * snp_count * sizeof(double)));
-    double* d_xx = out.as<double>();
-    double* d_xy = d_xx + snp_count;
-    double* d_rss = d_xy + snp_count;
-    double* d_f = d_rss + snp_count;
-    double* d_p = d_f + snp_count;
-    double* d_vp = d_p + snp_count;
-    {
-        StageTimer tm(ctx, "scan");
-        MMG_TRY(scan_tc_run(ctx, 1, nullptr, nullptr, &h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp, A, v));
-        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
-        ctx->last_scan_ms = ms;
-    }
+    DevBuf out;      // p, f, rss, var_perc, xx
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)5 * snp_count * sizeof(double)));
+    QuadA qa;
+    qa.d = A->d;
+    qa.ld = A->cols;
+    MMG_TRY(scan_quad_given(ctx, qa, v, false, h0_rss, n_p, snp_begin, snp_count, out.as<double>(), snp_count));
     StageTimer tm2(ctx, "d2h");
     const size_t bytes = snp_count * sizeof(double);
-    if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (f_stats) MMG_CUDA(ctx, cudaMemcpyAsync(f_stats, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (rss) MMG_CUDA(ctx, cudaMemcpyAsync(rss, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (var_perc) MMG_CUDA(ctx, cudaMemcpyAsync(var_perc, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (xx) MMG_CUDA(ctx, cudaMemcpyAsync(xx, d_xx, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    double* host[5] = {ps, f_stats, rss, var_perc, xx};
+    for (int k = 0; k < 5; ++k)
+        if (host[k]) MMG_CUDA(ctx, cudaMemcpyAsync(host[k], out.as<double>() + (int64_t)k * snp_count, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMG_OK;
+}
+
+int64_t mmg_quad_form_slots(int64_t n) { return n > 0 ? qa_slots(n) : 0; }
+
+int mmg_quad_form_tiles(mmg_ctx* ctx, mmg_mat Rh, int64_t slot_begin, int64_t slot_count, mmg_mat Ah, double* err_abs) {
+    MmgMat* R = ctx ? get_mat(ctx, Rh) : nullptr;
+    MmgMat* A = ctx ? get_mat(ctx, Ah) : nullptr;
+    MMG_CHECK(ctx, R && A && ctx->snps, "mmg_quad_form_tiles: need resident genotypes, R and the packed output");
+    MMG_CHECK(ctx, R->cols == ctx->n, "R must have n = %lld columns (has %lld)", (long long)ctx->n, (long long)R->cols);
+    MMG_CHECK(ctx, A->cols == QA_TILE_ELEMS && slot_begin >= 0 && slot_count >= 0 && slot_begin + slot_count <= A->rows,
+              "packed A must be [slots x 65536] and hold blocks [%lld, %lld)", (long long)slot_begin, (long long)(slot_begin + slot_count));
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm(ctx, "scan_prep");
+    DevBuf amax;
+    MMG_CUDA(ctx, amax.alloc(ctx->stream, sizeof(unsigned long long)));
+    double err = 0.0;
+    MMG_TRY(quad_form_int8(ctx, R, A->d + slot_begin * QA_TILE_ELEMS, slot_begin, slot_count, amax.as<unsigned long long>(), &err));
+    if (err_abs) *err_abs = err;
+    return MMG_OK;
+}
+
+int mmg_emmax_scan_quad_dev(mmg_ctx* ctx, mmg_mat Ah, int packed, double a_err, mmg_mat vh, double h0_rss, double n_p, int64_t snp_begin,
+                            int64_t snp_count, mmg_mat outh) {
+    MmgMat* A = ctx ? get_mat(ctx, Ah) : nullptr;
+    MmgMat* v = ctx ? get_mat(ctx, vh) : nullptr;
+    MmgMat* out = ctx ? get_mat(ctx, outh) : nullptr;
+    MMG_CHECK(ctx, A && v && out && ctx->snps, "mmg_emmax_scan_quad_dev: need resident genotypes, A, v and the output matrix");
+    const int64_t n = ctx->n;
+    if (packed) MMG_CHECK(ctx, A->cols == QA_TILE_ELEMS && A->rows >= qa_slots(n), "packed A must be [>= %lld x 65536]", (long long)qa_slots(n));
+    else MMG_CHECK(ctx, A->rows == n && A->cols == n, "dense A must be n x n with n = %lld", (long long)n);
+    MMG_CHECK(ctx, v->rows * v->cols == n, "v must hold n = %lld values", (long long)n);
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    MMG_CHECK(ctx, out->rows == 5 && out->cols >= snp_count, "out must be [5 x >= snp_count]");
+    MMG_CHECK(ctx, a_err >= 0.0, "a_err must be non-negative");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    QuadA qa;
+    qa.d = A->d;
+    qa.ld = A->cols;
+    qa.packed = packed != 0;
+    qa.err = a_err;
+    return scan_quad_given(ctx, qa, v->d, true, h0_rss, n_p, snp_begin, snp_count, out->d, out->cols);
 }
 
 // Phenotype-batched scan (BASELINE.json configs[2]; the reference runs one emmax() per phenotype): T rotations R_t

@@ -24,6 +24,13 @@ struct MmgTimer {
     int64_t calls = 0;
 };
 
+// a stage whose start / stop events are recorded but not read yet (read when the timers are queried: no host synchronisation
+// at the end of every stage)
+struct MmgPendingTimer {
+    const char* name;
+    cudaEvent_t e0, e1;
+};
+
 struct mmg_ctx {
     int device = 0;
     int sm_count = 0;
@@ -38,6 +45,10 @@ struct mmg_ctx {
     int64_t next_mat = 1;
     int64_t launches = 0;
     std::map<std::string, MmgTimer> timers;
+    std::vector<MmgPendingTimer> pending_timers;
+    std::vector<cudaEvent_t> event_pool;
+    int scan_slices_hint = 0;          // digit planes the previous int8 scan of this shape certified with (0 = none: run the pilot)
+    int64_t scan_hint_n = 0;
     double last_gram_ms = 0.0, last_scan_ms = 0.0, last_perm_ms = 0.0, last_ibd_ms = 0.0;
     int last_scan_slices = 0;          // digit planes used by the most recent int8 scan
     double last_scan_rho = 0.0;        // its certified relative truncation bound on x~.x~ (max over SNPs)
@@ -115,22 +126,53 @@ inline int fail(mmg_ctx* ctx, int code, const char* fmt, ...) {
 
 inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-// accumulates CUDA-event time of a stage; synchronises the stream at stop()
+// Reads every pending stage timer (waits for the stop events: the stream's work up to them must complete) and returns the
+// event pairs to the pool.
+inline void resolve_timers(mmg_ctx* ctx) {
+    for (const MmgPendingTimer& p : ctx->pending_timers) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            MmgTimer& t = ctx->timers[p.name];
+            t.seconds += ms * 1e-3;
+            t.calls += 1;
+        }
+        ctx->event_pool.push_back(p.e0);
+        ctx->event_pool.push_back(p.e1);
+    }
+    cudaGetLastError();
+    ctx->pending_timers.clear();
+}
+
+// accumulates CUDA-event time of a stage.  stop() only records the event: the elapsed time is read by resolve_timers
+// (mmg_timer_get / mmg_sync), so a stage ends without a host synchronisation.
 struct StageTimer {
     mmg_ctx* ctx;
     const char* name;
     bool running;
-    StageTimer(mmg_ctx* c, const char* nm) : ctx(c), name(nm), running(true) { cudaEventRecord(c->ev0, c->stream); }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    static cudaEvent_t take(mmg_ctx* c) {
+        cudaEvent_t e = nullptr;
+        if (!c->event_pool.empty()) {
+            e = c->event_pool.back();
+            c->event_pool.pop_back();
+        } else if (cudaEventCreate(&e) != cudaSuccess) {
+            cudaGetLastError();
+            e = nullptr;
+        }
+        return e;
+    }
+    StageTimer(mmg_ctx* c, const char* nm) : ctx(c), name(nm), running(true) {
+        if (c->pending_timers.size() >= 256) resolve_timers(c);
+        e0 = take(c);
+        e1 = take(c);
+        if (e0) cudaEventRecord(e0, c->stream);
+    }
     void stop() {
         if (!running) return;
         running = false;
-        cudaEventRecord(ctx->ev1, ctx->stream);
-        cudaEventSynchronize(ctx->ev1);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-        MmgTimer& t = ctx->timers[name];
-        t.seconds += ms * 1e-3;
-        t.calls += 1;
+        if (!e0 || !e1) return;
+        cudaEventRecord(e1, ctx->stream);
+        ctx->pending_timers.push_back(MmgPendingTimer{name, e0, e1});
     }
     ~StageTimer() { stop(); }
 };

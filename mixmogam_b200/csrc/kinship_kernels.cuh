@@ -173,6 +173,24 @@ static __global__ void kinship_finalize_kernel(const int32_t* __restrict__ G, in
     K[(int64_t)i * ldk + j] = k;
 }
 
+// The tensor-core Gram fills the 256 x 256 blocks (I, J) with I <= J of the padded square.  For the all-reduce between ranks
+// those blocks are packed back to back (slot J (J + 1) / 2 + I, 256 KB each) so that only the valid half of the matrix
+// crosses NVLink, and unpacked again afterwards.  One CTA per block, 16-byte accesses.
+template <bool UNPACK>
+static __global__ void __launch_bounds__(256) gram_tri_pack_kernel(int32_t* __restrict__ G, int64_t ldg, int32_t* __restrict__ packed) {
+    const int slot = blockIdx.x;
+    int J = (int)((sqrt(8.0 * (double)slot + 1.0) - 1.0) * 0.5);
+    while ((J + 1) * (J + 2) / 2 <= slot) ++J;
+    while (J * (J + 1) / 2 > slot) --J;
+    const int I = slot - J * (J + 1) / 2;
+    uint4* p = reinterpret_cast<uint4*>(packed + (int64_t)slot * 65536);
+    for (int idx = threadIdx.x; idx < 256 * 64; idx += 256) {
+        const int r = idx >> 6, c4 = idx & 63;
+        uint4* g = reinterpret_cast<uint4*>(G + (int64_t)(I * 256 + r) * ldg + J * 256) + c4;
+        if (UNPACK) *g = p[idx]; else p[idx] = *g;
+    }
+}
+
 // mirror the upper triangle of the integer Gram into the lower one (for downloads)
 static __global__ void gram_mirror_kernel(int32_t* __restrict__ G, int64_t ldg, int n) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;

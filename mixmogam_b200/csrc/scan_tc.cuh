@@ -33,6 +33,7 @@ constexpr int QS_FLAG_XY = 1;        // TcTile.aux1: accumulate x.v on this tile
 constexpr int QS_FLAG_FIRST = 2;     //              first tile of a phenotype: reset the running sums
 constexpr int QS_FLAG_LAST = 4;      //              last tile of a phenotype: evaluate and store
 constexpr int QS_PHEN_SHIFT = 8;     //              phenotype index = aux1 >> 8
+constexpr double QS_DEGENERATE_REL = 1e-8;   // x~.x~ <= this fraction of sum_j A_jj x_j^2: the SNP is collinear with the fixed effects
 
 struct QuadEpi {
     struct Params {
@@ -117,14 +118,19 @@ struct QuadEpi {
         const int64_t o = (int64_t)ph * p.out_stride + orow;
         const double h0 = p.h0_rss[ph];
         const double sxx = fma(q, p.escale[ph], qd), sxy = xy;
-        if (p.rho_max != nullptr && sxx > 0.0) {
+        // x~ numerically zero -- x is (nearly) in the span of the fixed effects, e.g. a monomorphic SNP or one collinear with a
+        // cofactor: x~.x~ is then the difference of two equal numbers (qd = sum_j A_jj x_j^2 bounds its scale) and the statistic
+        // carries no information.  Such a SNP keeps the null fit, like the reference's empty-residue case (`if rss:`,
+        // linear_models.py:1329), and stays out of the certification maximum (its relative bound is meaningless).
+        const bool degenerate = !(sxx > QS_DEGENERATE_REL * qd);
+        if (p.rho_max != nullptr && !degenerate) {
             const double rho = p.bscale[ph] * x1 * x1 / sxx;
             atomicMax(p.rho_max, (unsigned long long)__double_as_longlong(rho));
         }
         if (p.xx) p.xx[o] = sxx;
         if (p.xy) p.xy[o] = sxy;
         double rss = h0, f = 0.0, vp = 0.0, pv = 1.0;
-        if (sxx > 0.0) {
+        if (!degenerate) {
             const double r2 = (sxy * sxy) / (sxx * h0);
             const double rs = h0 - (sxy * sxy) / sxx;
             if (rs != 0.0) {
@@ -273,12 +279,27 @@ static __global__ void __launch_bounds__(256, PRE_MINB) snp_prepass_kernel(const
     }
 }
 
-// max |2 A[j][i]| over the strict lower triangle (i < j) of the row-major matrix -> bits of a non-negative double
+// Storage of the quadratic form A = R'R (only its lower triangle, i <= j, is ever read):
+//   dense  : row-major [n x ld]
+//   packed : the 256 x 256 blocks (J, I) with I <= J back to back, block (J, I) in slot J (J + 1) / 2 + I, row-major inside a
+//            block.  Half the memory of the padded square, and a contiguous range of slots is a contiguous range of bytes --
+//            which is what lets the ranks of a multi-GPU run each form a slot range and all-gather the result.
+constexpr int QA_TILE = 256;
+constexpr int64_t QA_TILE_ELEMS = (int64_t)QA_TILE * QA_TILE;
+__host__ __device__ __forceinline__ int64_t qa_slot(int J, int I) { return (int64_t)J * (J + 1) / 2 + I; }
+template <bool PACKED>
+__device__ __forceinline__ int64_t qa_index(int64_t ld, int j, int i) {          // element (j, i), i <= j
+    if (!PACKED) return (int64_t)j * ld + i;
+    return qa_slot(j >> 8, i >> 8) * QA_TILE_ELEMS + (int64_t)(j & 255) * QA_TILE + (i & 255);
+}
+
+// max |2 A[j][i]| over the strict lower triangle (i < j) -> bits of a non-negative double
+template <bool PACKED>
 static __global__ void quad_amax_kernel(const double* __restrict__ A, int64_t ld, int n, unsigned long long* __restrict__ amax_bits) {
     const int j = blockIdx.y;
     double m = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j; i += gridDim.x * blockDim.x) {
-        const double a = fabs(A[(int64_t)j * ld + i]) * 2.0;
+        const double a = fabs(A[qa_index<PACKED>(ld, j, i)]) * 2.0;
         m = fmax(m, a);
     }
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -287,16 +308,17 @@ static __global__ void quad_amax_kernel(const double* __restrict__ A, int64_t ld
 
 // digits of B[j][i] = 2 A[j][i] 2^-E (i < j) into S stacked int8 planes Bq[(k * n_padN + j) * ldq + i]; the diagonal
 // goes to dg[j] = A[j][j] and stays in FP64 (it is usually the largest entry: keeping it out of the digit planes lowers E)
+template <bool PACKED>
 static __global__ void quad_slice_kernel(const double* __restrict__ A, int64_t ld, int n, double scale /* 2^-E */, int S,
-                                  int8_t* __restrict__ Bq, int64_t n_padN, int64_t ldq, double* __restrict__ dg) {
+                                         int8_t* __restrict__ Bq, int64_t n_padN, int64_t ldq, double* __restrict__ dg) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i > j || i >= n) return;
     if (i == j) {
-        dg[j] = A[(int64_t)j * ld + j];
+        dg[j] = A[qa_index<PACKED>(ld, j, j)];
         return;
     }
-    const double r = A[(int64_t)j * ld + i] * 2.0 * scale;               // |r| <= 0.498, exact scaling
+    const double r = A[qa_index<PACKED>(ld, j, i)] * 2.0 * scale;        // |r| <= 0.498, exact scaling
     int d[DIGIT256_MAX_PLANES];
     digit256_split(r, S, d);                                             // base 256, exact (digits.cuh)
     for (int k = 0; k < S; ++k) Bq[((int64_t)k * n_padN + j) * ldq + i] = (int8_t)d[k];
@@ -351,9 +373,11 @@ static __global__ void __launch_bounds__(256) ozaki_planes_kernel(const double* 
 // group (same CTA, same epilogue thread per row), so the read-modify-write needs no atomics and stays in L2.
 struct OzakiEpi {
     struct Params {
-        double* A;             // [n_padM x ld] FP64, zeroed; lower-triangular tiles are written
-        int64_t ld;
+        double* A;             // FP64, zeroed; lower-triangular tiles are written: dense [n_padM x ld], or packed 256 x 256 blocks
+        int64_t ld;            //   (qa_index; `A` then points at slot `slot0`, the first one this launch owns)
         int64_t n_padM;
+        int packed;
+        int64_t slot0;
         double w[2 * OZ_PLANES];
     };
     __device__ __forceinline__ void begin_group(const Params&, int, int) {}
@@ -363,7 +387,9 @@ struct OzakiEpi {
     __device__ __forceinline__ void chunk(const Params& p, const TcTile& t, int row, int c, const uint32_t (&v)[32]) {
         const int64_t orow = (int64_t)t.m0 - (int64_t)t.aux0 * p.n_padM + row;       // aux0 = p, aux1 = q
         const int64_t ocol = (int64_t)t.n0 - (int64_t)t.aux1 * p.n_padM + c * 32;
-        double2* dst = reinterpret_cast<double2*>(p.A + orow * p.ld + ocol);
+        double2* dst = reinterpret_cast<double2*>(
+            p.packed ? p.A + (qa_slot((int)(orow >> 8), (int)(ocol >> 8)) - p.slot0) * QA_TILE_ELEMS + (orow & 255) * QA_TILE + (ocol & 255)
+                     : p.A + orow * p.ld + ocol);
         const double wk = p.w[t.aux0 + t.aux1];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

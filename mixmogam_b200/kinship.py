@@ -63,14 +63,13 @@ def calc_ibs_kinship(snps, snps_data_format='binary', snp_dtype='int8', dtype='s
 
 def partial_ibs_gram(snps, snps_data_format='binary', impl='auto', ctx=None, reset=True):
     """Multi-GPU building block: integer Gram of this rank's SNP slice, left resident for an int32
-    all-reduce (see mixmogam_b200.parallel).  Returns (device_ptr, n, ld)."""
+    all-reduce (mixmogam_b200.parallel.allreduce_gram).  Stream ordered: nothing waits for the Gram here."""
     ctx = ctx or _lib.get_context()
     if reset:
         ctx.kinship_gram_from(snps, _coding(snps_data_format), impl=impl)
     else:
         ctx.ensure_snps(snps)
         ctx.kinship_gram(_coding(snps_data_format), impl=impl, reset=False)
-    return ctx.kinship_gram_ptr()
 
 
 def calc_ibd_kinship(snps, dtype='single', scaled=True, ctx=None):

@@ -145,9 +145,12 @@ class LinearMixedModel(LinearModel):
     A class for linear mixed models (linear_models.py:554).
     """
 
-    def __init__(self, Y=None, dtype='single', ctx=None, scan_impl='auto'):
+    def __init__(self, Y=None, dtype='single', ctx=None, scan_impl='auto', shard=None):
         self.ctx = ctx or _lib.get_context()
         self.scan_impl = scan_impl
+        self.shard = None
+        if shard is not None:
+            self.set_sharding(**(shard if isinstance(shard, dict) else {'group': shard}))
         self.n = len(Y)
         self.y_var = np.var(Y, ddof=1)
         self.Y = np.array(Y, dtype=np.float64).reshape(self.n, 1)
@@ -162,6 +165,14 @@ class LinearMixedModel(LinearModel):
 
     def _invalidate(self):
         self._eig_R_cache = None
+
+    def set_sharding(self, group='world', m_total=None):
+        """Opt in to the SNP-sharded scan (one process per GPU, torch.distributed NCCL group): EVERY rank of `group` holds the
+        same model (phenotype, kinship, cofactors) and calls the scan with its own slice of the SNPs (parallel.shard_range
+        order); the n^3 set-up product is split over the ranks and the per-SNP results come back covering all SNPs
+        (parallel.scan_sharded).  m_total = total number of SNPs when the slices follow parallel.shard_range.  Not set: a
+        model never communicates, whatever process group exists (ranks may then fit different models independently)."""
+        self.shard = {'group': None if group == 'world' else group, 'm_total': m_total}
 
     # ------------------------------------------------------------------------------------------
     def add_random_effect(self, cov_matrix=None, effect_type='normal'):
@@ -463,16 +474,28 @@ class LinearMixedModel(LinearModel):
         impl = kwargs.get('impl', self.scan_impl)
 
         if not with_betas:
-            from . import parallel
             int8_scan = impl == 'tcgen05' or (impl in ('auto', None) and os.environ.get('MMG_SCAN_IMPL', 'tcgen05') == 'tcgen05')
-            if int8_scan and parallel.world_size() > 1 and parallel.nccl_backend():
-                # one process per GPU: R'R is formed once across the ranks instead of once per rank (parallel.py)
-                A = parallel.quad_form_sharded(ctx, Rm)
-                yd = DeviceMatrix.from_host(ctx, nf['Yres'].reshape(-1, 1))
-                vd = ctx.gemm(Rm, yd, ta=True)                 # v = R' y~   (x~.y~ = x.v)
-                out = ctx.emmax_scan_quad(A, vd.download().reshape(-1), h0_rss_f, n_p)
-                for d in (A, yd, vd):
-                    d.free()
+            if self.shard is not None:
+                # one process per GPU, explicitly requested (set_sharding): R'R is formed once across the ranks instead of once
+                # per rank, every rank scans its SNP slice, the outputs are all-gathered (parallel.py)
+                from . import parallel
+                if not int8_scan:
+                    raise ValueError("the sharded scan runs on the int8 tensor-core path (scan_impl='tcgen05')")
+                group, m_total = self.shard['group'], self.shard['m_total']
+                if parallel.world_size(group) > 1:
+                    if emma_num > 0 or return_transformed_snps or snp_priors is not None:
+                        raise ValueError('the sharded scan returns the per-SNP statistics only (emma_num=0, no t_snps / priors): '
+                                         'refine the top hits on one rank with expedited_REML_t_test')
+                    parallel.check_same_model(ctx, [h0_rss_f, float(n), float(np.sum(np.abs(nf['Yres']))), float(Rm.shape[0])], group)
+                    A, a_err = parallel.quad_form_sharded(ctx, Rm, group)
+                    yd = DeviceMatrix.from_host(ctx, nf['Yres'].reshape(-1, 1))
+                    vd = ctx.gemm(Rm, yd, ta=True)                 # v = R' y~   (x~.y~ = x.v)
+                    out = parallel.scan_sharded(ctx, A, a_err, vd, h0_rss_f, n_p, m_total=m_total, group=group)
+                    for d in (A, yd, vd):
+                        d.free()
+                    num_snps = len(out['ps'])
+                else:
+                    out = ctx.emmax_scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
             else:
                 out = ctx.emmax_scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
             p_vals, f_stats, rss_list, var_perc = out['ps'], out['f_stats'], out['rss'], out['var_perc']
@@ -620,11 +643,11 @@ def emma(snps, phenotypes, K, cofactors=None):
     return lmm.expedited_REML_t_test(snps)
 
 
-def emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_num=0, scan_impl='auto', ctx=None):
+def emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_num=0, scan_impl='auto', ctx=None, shard=None):
     """
-    Run EMMAX (linear_models.py:1790-1816).
+    Run EMMAX (linear_models.py:1790-1816).  `shard` (not in the reference): see LinearMixedModel.set_sharding.
     """
-    lmm = LinearMixedModel(phenotypes, ctx=ctx, scan_impl=scan_impl)
+    lmm = LinearMixedModel(phenotypes, ctx=ctx, scan_impl=scan_impl, shard=shard)
     if Z is not None:
         Zm = np.asarray(Z, dtype=np.float64)
         Kh = np.asarray(K, dtype=np.float64)

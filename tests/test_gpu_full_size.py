@@ -5,7 +5,16 @@ through size-independent properties -- the oracle cannot run there (the referenc
              bit for bit: additivity over SNPs, kinship.py:29-44)
            * trace(G) of the thermometer Gram == sum of all genotypes (every SNP counted exactly once)
            * unscaled K: symmetric, unit diagonal (kinship.py:51), entries in [0, 1]
-  scan     * the certified truncation bound of the int8 digit-plane scan holds over all 1M SNPs (<= 1e-7)
+           * a sample of 24 rows of the unscaled K == the oracle's integer identity for those rows, bit for bit
+  REML     * max_ll at delta-hat == the restricted log-likelihood evaluated WITHOUT any eigendecomposition (Cholesky of
+             K + delta I on the CPU: log|H|, log|X'H^-1 X|, y'Py) to 1e-9 relative, and delta-hat is a local maximum of that
+             function -- pins cuSOLVER's eigenbases and the REML kernels at n = 10 000
+  scan     * p-values of 400 sampled SNPs (top hits + random) == the GLS F-test computed from the same Cholesky factor
+             (x'Px, x'Py, y'Py; linear_models.py:1272-1349 in its textbook form) to 1e-6 relative in -log10 p: an
+             arithmetic path that shares nothing with the product (no eigenbasis, no rotation, no digit planes)
+           * MMG_TEST_ORACLE_FULL=1 adds the line-faithful oracle itself (oracle.emmax, dtype='double': two n x n eigh on
+             the CPU, ~5 min) on the same sample: p 1e-6, delta-hat 1e-9 (profiles/r02_parity_n10k.txt keeps one run)
+           * the certified truncation bound of the int8 digit-plane scan holds over all 1M SNPs (<= 1e-7)
            * the int8 scan of the whole block == the FP64 tensor-core (DMMA) scan of a re-uploaded sample of its rows
              (top hits + random rows, shuffled) within 1e-6 relative in -log10 p, identical ranking of the top 100:
              row-order / batch independence and agreement of two independent arithmetic paths
@@ -34,6 +43,7 @@ def test_full_size_properties(ctx):
     m = int(os.environ.get('MMG_TEST_FULL_M', 1000000))
     dev = torch.device('cuda:0')
     snps = bench.gen_genotypes_pinned(0, m, n, dev)
+    snps.flags.writeable = False                                         # residency contract: the device copy is reused across calls
     y = bench.gen_phenotype(n, dev)
 
     # ---- kinship ----
@@ -48,7 +58,18 @@ def test_full_size_properties(ctx):
     del G
     Ku = np.asarray(kinship.calc_ibs_kinship(snps, 'diploid_int', scaled=False))
     assert np.array_equal(Ku, Ku.T) and np.all(np.diag(Ku) == 1.0) and Ku.min() >= 0.0 and Ku.max() <= 1.0
-    del Ku
+    from oracle import reference_py3 as o
+    rows = np.random.default_rng(5).choice(n, size=24, replace=False)
+    x_rows = np.ascontiguousarray(snps[:, rows].T).astype(np.int16)       # [24 x m]
+    for blk in range(0, n, 2000):                                        # counts of equal / one-apart genotypes vs every individual
+        xb = np.ascontiguousarray(snps[:, blk:blk + 2000].T).astype(np.int16)
+        for a, r in enumerate(rows):
+            d = np.abs(xb - x_rows[a][None, :])
+            cnt = (d == 0).sum(axis=1, dtype=np.int64) + 0.5 * (d == 1).sum(axis=1, dtype=np.int64)    # kinship.py:36-38
+            ref = (cnt.astype(np.float32) / np.float32(m)).astype(np.float64)                          # :51
+            ref[np.arange(blk, blk + xb.shape[0]) == r] = 1.0                                          # :35 (diagonal never filled) + I
+            assert np.array_equal(Ku[r, blk:blk + xb.shape[0]], ref)
+    del Ku, x_rows
     K = kinship.calc_ibs_kinship(snps, 'diploid_int')
 
     # ---- scan, whole block on the int8 tensor cores ----
@@ -77,6 +98,52 @@ def test_full_size_properties(ctx):
     order_full = idx[np.argsort(-fs[idx], kind='stable')[:100]]
     order_dmma = idx[np.argsort(-r_dmma['f_stats'], kind='stable')[:100]]
     assert np.array_equal(order_full, order_dmma) and np.array_equal(np.sort(order_full), np.sort(top))
+
+    # ---- REML and scan against an eigendecomposition-free CPU evaluation (Cholesky of H = K + delta I) ----
+    from scipy import linalg as sla
+    Kh = np.array(np.asarray(mdl.random_effects[1][1]), dtype=np.float64)        # the scaled kinship the model holds (:580)
+    delta = 1.0 / full['pseudo_heritability'] - 1.0
+    X = np.ones((n, 1))
+    yv = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    pdim = n - 1
+
+    def reml_parts(d, extra=None):
+        H = Kh + d * np.eye(n)
+        c = sla.cho_factor(H, lower=True, overwrite_a=True, check_finite=False)
+        logdet = 2.0 * np.sum(np.log(np.diag(c[0])))
+        B = np.hstack([X, yv] + ([extra] if extra is not None else []))
+        Z = sla.cho_solve(c, B, check_finite=False)                              # H^-1 [X y xs]
+        xhx = (X.T @ Z[:, :1]).item()
+        py = Z[:, 1:2] - Z[:, :1] * ((X.T @ Z[:, 1:2]).item() / xhx)               # P y
+        ypy = (yv.T @ py).item()
+        ll = 0.5 * pdim * (np.log(pdim / (2.0 * np.pi)) - 1.0) - 0.5 * (pdim * np.log(ypy) + logdet + np.log(xhx) - np.log(float(n)))   # :618-623
+        return ll, xhx, py, ypy, Z
+
+    sidx = np.concatenate([top, rng.choice(m, size=300, replace=False)])
+    xs = np.ascontiguousarray(snps[sidx].T).astype(np.float64)                   # [n x 400]
+    ll0, xhx, py, ypy, Z = reml_parts(delta, xs)
+    assert abs(ll0 - full['max_ll']) <= 1e-9 * abs(ll0)
+    for eps in (-2e-3, 2e-3):
+        assert reml_parts(delta * (1.0 + eps))[0] <= ll0 + 1e-9 * abs(ll0)       # delta-hat is a local maximum of the REML likelihood
+    Zx = Z[:, 2:]
+    px = Zx - Z[:, :1] * ((X.T @ Zx) / xhx)                                      # P xs
+    xpx = np.einsum('ij,ij->j', xs, px)
+    xpy = (xs.T @ py).reshape(-1)
+    r2 = xpy * xpy / (xpx * ypy)
+    f_chol = (n - 2) * r2 / (1.0 - r2)                                           # :1346-1347 with rss = y'Py - (x'Py)^2 / x'Px
+    from scipy import stats
+    p_chol = stats.f.sf(f_chol, 1, n - 2)
+    assert neglog10_rel_err(ps[sidx], p_chol) < TOL
+    np.testing.assert_allclose(full['f_stats'][sidx], f_chol, rtol=1e-6)
+    del Z, Zx, px
+
+    if os.environ.get('MMG_TEST_ORACLE_FULL'):
+        ro = o.emmax([np.asarray(r) for r in snps[sidx]], np.asarray(y), np.asarray(K), dtype='double')
+        assert neglog10_rel_err(ps[sidx], ro['ps']) < TOL
+        assert abs(ro['_delta'] - delta) <= 1e-9 * delta
+        print('oracle(double) at n=%d on %d SNPs: max rel err in -log10 p %.3g, delta %.12g vs %.12g'
+              % (n, sidx.size, neglog10_rel_err(ps[sidx], ro['ps']), delta, ro['_delta']))
+    del Kh
 
     # ---- allele flip ----
     flipped = (2 - sub).astype(np.int8)

@@ -325,9 +325,11 @@ def test_scan_int8_domain_guard(ctx):
     ctx.invalidate_snps()
 
 
-def test_quad_form_row_blocks_and_scan_quad(ctx):
-    """The multi-GPU preparation path on one GPU: R'R summed from row blocks of R (mmg_mat_syrk_rows) equals the one-shot
-    product, and the scan fed with that A and v = R'y (mmg_emmax_scan_quad_f64) equals mmg_emmax_scan_f64."""
+def test_quad_form_tiles_and_scan_quad(ctx):
+    """The multi-GPU preparation path on one GPU: the packed 256 x 256 blocks of A = R'R formed in three slot ranges
+    (mmg_quad_form_tiles, what three ranks would each do before the all-gather) equal numpy's R'R inside the returned error
+    bound, and the scan fed with that packed A and v = R'y on the device (mmg_emmax_scan_quad_dev) equals
+    mmg_emmax_scan_f64; the dense host-vector entry (mmg_emmax_scan_quad_f64) agrees too."""
     from mixmogam_b200 import parallel
     from mixmogam_b200._lib import DeviceMatrix
     from oracle import reference_py3 as o
@@ -339,22 +341,62 @@ def test_quad_form_row_blocks_and_scan_quad(ctx):
     R = rng.standard_normal((n - 1, n)) / np.sqrt(n)
     y = rng.standard_normal(n - 1)
     Rd = DeviceMatrix.from_host(ctx, R)
-    parts = [parallel.split_rows(n - 1, r, 3) for r in range(3)]
-    assert parts[0][0] == 0 and parts[-1][1] == n - 1 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
-    A = np.zeros((n, n))
-    for b, e in parts:
-        Ab = ctx.syrk_rows(Rd, b, e - b)
-        A += np.tril(Ab.download())
-        Ab.free()
-    np.testing.assert_allclose(A, np.tril(R.T @ R), rtol=1e-12, atol=1e-14)
-    Ad = DeviceMatrix.from_host(ctx, A)
+    slots = ctx.quad_form_slots(n)
+    assert slots == 3 * 4 // 2                                         # n = 700 -> 3 block rows
+    world = 4                                                          # more ranks than some have blocks for: 6 = 2 + 2 + 2 + 0
+    per = parallel.slot_range(slots, 0, world)[2]
+    Ap = DeviceMatrix(ctx, per * world, 65536, zero=False)
+    errs = []
+    for r in range(world):
+        b, c, _ = parallel.slot_range(slots, r, world)
+        errs.append(ctx.quad_form_tiles(Rd, b, c, Ap))
+    assert len(set(errs)) == 1 and errs[0] > 0
+    blocks = Ap.download().reshape(-1, 256, 256)
+    A = np.zeros((768, 768))
+    for J in range(3):
+        for I in range(J + 1):
+            A[J * 256:(J + 1) * 256, I * 256:(I + 1) * 256] = blocks[J * (J + 1) // 2 + I]
+    ref = R.T @ R
+    assert np.max(np.abs(np.tril(A[:n, :n]) - np.tril(ref))) <= errs[0] + 1e-15
     h0 = float(y @ y)
     ra = ctx.emmax_scan(Rd, y.reshape(1, -1), h0, n - 2, impl='tcgen05')
+    vd = DeviceMatrix.from_host(ctx, (R.T @ y).reshape(-1, 1))
+    out = ctx.emmax_scan_quad_dev(Ap, vd, h0, n - 2, packed=True, a_err=errs[0]).download()
+    Ad = DeviceMatrix.from_host(ctx, np.tril(ref))
     rb = ctx.emmax_scan_quad(Ad, R.T @ y, h0, n - 2)
-    for k in ('ps', 'f_stats', 'rss', 'var_perc', 'xx'):
+    for i, k in enumerate(parallel.RESULT_KEYS):
+        np.testing.assert_allclose(out[i], ra[k], rtol=1e-9, atol=1e-300)
         np.testing.assert_allclose(rb[k], ra[k], rtol=1e-9, atol=1e-300)
     xt = snps.astype(np.float64) @ R.T
-    np.testing.assert_allclose(rb['xx'], np.sum(xt * xt, axis=1), rtol=1e-7)
+    np.testing.assert_allclose(out[4], np.sum(xt * xt, axis=1), rtol=1e-7)
+    ctx.invalidate_snps()
+
+
+def test_degenerate_snps_keep_the_null_fit(ctx):
+    """A monomorphic SNP and a SNP equal to a cofactor are collinear with the fixed effects: x~ = 0 up to rounding.  The int8
+    scan gives them the null fit (rss = h0_rss, f = 0, p = 1 -- the reference's empty-residue case, linear_models.py:1329),
+    keeps them out of the certification maximum, and the other SNPs are unaffected."""
+    from mixmogam_b200 import kinship, linear_models as lm
+    from oracle import reference_py3 as o
+    n, m = 400, 12000
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=5)
+    cof = snps[17].astype(np.float64)
+    snps[100] = 2                                                      # monomorphic
+    snps[200] = 0
+    snps[300] = snps[17]                                               # identical to the cofactor
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int')
+    y = o.synth_phenotype(snps, K, seed=2)
+    ctx.invalidate_snps()
+    r = lm.emmax(snps, y, K, cofactors=[cof], scan_impl='tcgen05')
+    S, rho = ctx.last_scan_info()
+    assert rho <= 1e-7                                                 # certified although three SNPs have x~.x~ ~ 0
+    for i in (100, 200, 300, 17):
+        assert r['ps'][i] == 1.0 and r['f_stats'][i] == 0.0 and r['var_perc'][i] == 0.0
+        assert r['rss'][i] == float(np.asarray(r['h0_rss']).reshape(-1)[0])
+    ro = o.emmax(list(snps), y, K, cofactors=[cof], dtype='double')
+    keep = np.ones(m, dtype=bool)
+    keep[[17, 100, 200, 300]] = False
+    assert neglog10_rel_err(r['ps'][keep], ro['ps'][keep]) < 1e-6
     ctx.invalidate_snps()
 
 

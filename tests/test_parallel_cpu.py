@@ -86,3 +86,19 @@ def test_split_rows_covers_and_balances():
             sizes = [e - b for b, e in parts]
             assert max(sizes) - min(sizes) <= 1
     assert parallel.world_size() == 1
+
+
+def test_slot_range_covers_the_packed_triangle():
+    for slots in (1, 6, 820, 19306):
+        for world in (1, 2, 3, 8):
+            parts = [parallel.slot_range(slots, r, world) for r in range(world)]
+            per = parts[0][2]
+            assert all(p[2] == per for p in parts) and per * world >= slots
+            assert sum(c for _, c, _ in parts) == slots
+            pos = 0
+            for b, c, _ in parts:
+                assert b == min(pos, b) or c == 0
+                if c:
+                    assert b == pos
+                pos += c
+            assert all(b == r * per for r, (b, _, _) in enumerate(parts))
