@@ -5,7 +5,8 @@ through size-independent properties -- the oracle cannot run there (the referenc
              bit for bit: additivity over SNPs, kinship.py:29-44)
            * trace(G) of the thermometer Gram == sum of all genotypes (every SNP counted exactly once)
            * unscaled K: symmetric, unit diagonal (kinship.py:51), entries in [0, 1]
-           * a sample of 24 rows of the unscaled K == the oracle's integer identity for those rows, bit for bit
+           * a 3 x 1000 sample of the entries of the unscaled K == the reference's counts for those pairs (kinship.py:36-38,51)
+             over all 1M SNPs, bit for bit
   REML     * max_ll at delta-hat == the restricted log-likelihood evaluated WITHOUT any eigendecomposition (Cholesky of
              K + delta I on the CPU: log|H|, log|X'H^-1 X|, y'Py) to 1e-9 relative, and delta-hat is a local maximum of that
              function -- pins cuSOLVER's eigenbases and the REML kernels at n = 10 000
@@ -59,16 +60,20 @@ def test_full_size_properties(ctx):
     Ku = np.asarray(kinship.calc_ibs_kinship(snps, 'diploid_int', scaled=False))
     assert np.array_equal(Ku, Ku.T) and np.all(np.diag(Ku) == 1.0) and Ku.min() >= 0.0 and Ku.max() <= 1.0
     from oracle import reference_py3 as o
-    rows = np.random.default_rng(5).choice(n, size=24, replace=False)
-    x_rows = np.ascontiguousarray(snps[:, rows].T).astype(np.int16)       # [24 x m]
-    for blk in range(0, n, 2000):                                        # counts of equal / one-apart genotypes vs every individual
-        xb = np.ascontiguousarray(snps[:, blk:blk + 2000].T).astype(np.int16)
-        for a, r in enumerate(rows):
-            d = np.abs(xb - x_rows[a][None, :])
-            cnt = (d == 0).sum(axis=1, dtype=np.int64) + 0.5 * (d == 1).sum(axis=1, dtype=np.int64)    # kinship.py:36-38
-            ref = (cnt.astype(np.float32) / np.float32(m)).astype(np.float64)                          # :51
-            ref[np.arange(blk, blk + xb.shape[0]) == r] = 1.0                                          # :35 (diagonal never filled) + I
-            assert np.array_equal(Ku[r, blk:blk + xb.shape[0]], ref)
+    krng = np.random.default_rng(5)
+    rows = krng.choice(n, size=3, replace=False)
+    cols = np.sort(krng.choice(n, size=1000, replace=False))
+    x_rows = np.ascontiguousarray(snps[:, rows].T).astype(np.int8)        # [3 x m]
+    cnt = np.zeros((3, cols.size))
+    for s0 in range(0, m, 100000):                                        # counts of equal / one-apart genotypes, SNP block by SNP block
+        xb = np.ascontiguousarray(snps[s0:s0 + 100000][:, cols].T)        # [1000 x block] int8
+        for a in range(3):
+            d = np.abs(xb - x_rows[a][None, s0:s0 + 100000])
+            cnt[a] += (d == 0).sum(axis=1, dtype=np.int64) + 0.5 * (d == 1).sum(axis=1, dtype=np.int64)      # kinship.py:36-38
+    for a, r in enumerate(rows):
+        ref = (cnt[a].astype(np.float32) / np.float32(m)).astype(np.float64)                                 # :51
+        ref[cols == r] = 1.0                                                                                  # :35 (diagonal never filled) + I
+        assert np.array_equal(Ku[r, cols], ref)
     del Ku, x_rows
     K = kinship.calc_ibs_kinship(snps, 'diploid_int')
 
