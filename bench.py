@@ -445,6 +445,12 @@ def main():
         if pk + rw > 0:
             e2e['h2d_pcie_bytes_per_step'] = int(m_loc * n * (rw + 0.25 * pk) / (pk + rw) + n * 8 * 2 * 2)
 
+    if os.environ.get('MMG_BENCH_DEBUG'):
+        # every rank's own view of the timed region (the JSON line below is rank 0's): stage timers, planes, wall times
+        dbg = {'rank': rank, 'stages_ms': {k: round(1e3 * v, 3) for k, v in timers.items()}, 'scan_info': ctx.last_scan_info(),
+               'detail_ms_last_region': {k: round(1e3 * v / args.steps, 3) for k, v in ctx.timers(detail=True).items() if k in ctx.DETAIL},
+               'e2e_stages_ms': {k: round(1e3 * v, 3) for k, v in e2e_timers.items()}, 'scan_ms': scan_ms, 'gram_ms': gram_ms}
+        open(os.path.join(os.environ['MMG_BENCH_DEBUG'], 'bench_rank%d.json' % rank), 'w').write(json.dumps(dbg))
     if rank == 0:
         value = m * args.steps / t_res
         # ---- roofline of the dominant kernel (the scan), measured live with CUDA events on its stream ----

@@ -304,8 +304,11 @@ class Context(object):
         self._ck(self.lib.mmg_timer_get(self.h, name.encode(), C.byref(s), C.byref(c)))
         return s.value, c.value
 
-    def timers(self):
-        return {k: self.timer(k)[0] for k in ('h2d', 'pack', 'gram', 'finalize', 'ibd', 'syevd', 'reml', 'scan_prep', 'scan', 'd2h')}
+    STAGES = ('h2d', 'pack', 'gram', 'finalize', 'ibd', 'syevd', 'reml', 'scan_prep', 'scan', 'd2h')
+    DETAIL = ('qf_gemm', 'host_qf_alloc', 'host_qf_total', 'host_qf_tiles')      # inside 'scan_prep' / host wall clock: not additive
+
+    def timers(self, detail=False):
+        return {k: self.timer(k)[0] for k in (self.STAGES + (self.DETAIL if detail else ()))}
 
     def timer_reset(self):
         self._ck(self.lib.mmg_timer_reset(self.h))

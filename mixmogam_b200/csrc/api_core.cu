@@ -77,6 +77,7 @@ int mmg_destroy(mmg_ctx* ctx) {
     cudaFree(ctx->tiles_d);
     cudaFree(ctx->flag_d);
     cudaFree(ctx->scratch);
+    for (int i = 0; i < 8; ++i) cudaFree(ctx->ws[i]);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage_host[i]) cudaFreeHost(ctx->stage_host[i]);
         cudaFree(ctx->stage_dev[i]);

@@ -217,6 +217,7 @@ static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_slots, int64_
                           double* err_out) {
     const int64_t n = ctx->n, n_out = R->rows;
     const int64_t n_padM = round_up(n, QA_TILE);
+    HostTimer ht_total(ctx, "host_qf_total");
     MMG_CHECK(ctx, n_out < 131072, "R'R on the int8 pipe: contraction too long for exact int32 accumulation");
     MMG_CUDA(ctx, cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), ctx->stream));
     {
@@ -233,8 +234,8 @@ static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_slots, int64_
     slot_count = std::max<int64_t>(0, std::min(slot_count, qa_slots(n) - slot_begin));
     if (slot_count == 0) return MMG_OK;
     const int64_t op_pitch = round_up(n_out, TC_BK);
-    DevBuf Op;
-    MMG_CUDA(ctx, Op.alloc(ctx->stream, (size_t)OZ_PLANES * n_padM * op_pitch));
+    struct { void* p = nullptr; template <class T> T* as() { return reinterpret_cast<T*>(p); } } Op;
+    MMG_TRY(ws_get(ctx, MMG_WS_OZAKI_PLANES, OZ_PLANES * n_padM * op_pitch, &Op.p));
     MMG_CUDA(ctx, cudaMemsetAsync(Op.p, 0, (size_t)OZ_PLANES * n_padM * op_pitch, ctx->stream));
     ozaki_planes_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n_out + 31) / 32)), 256, 0, ctx->stream>>>(
         R->d, n, (int)n_out, (int)n, ldexp(1.0, -F), Op.as<int8_t>(), n_padM, op_pitch);
@@ -273,7 +274,10 @@ static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_slots, int64_
         ++entries;
         if (++I > J) { I = 0; ++J; }
     }
-    MMG_TRY(ensure_tiles(ctx, tiles));
+    {
+        HostTimer ht(ctx, "host_qf_tiles");
+        MMG_TRY(ensure_tiles(ctx, tiles));
+    }
     CUtensorMap tmA, tmB;
     MMG_TRY(make_tmap_u8(ctx, &tmA, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BM));
     MMG_TRY(make_tmap_u8(ctx, &tmB, Op.p, op_pitch, (int64_t)OZ_PLANES * n_padM, op_pitch, TC_BN / 2));
@@ -284,9 +288,12 @@ static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_slots, int64_
     ep.packed = 1;
     ep.slot0 = slot_begin;
     for (int sl = 0; sl < 2 * OZ_PLANES; ++sl) ep.w[sl] = ldexp(1.0, 2 * F - 8 * (sl + 2));
-    MMG_TRY((launch_tc_gemm<OzakiEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, entries * 2, per_entry, per_entry, 0, TC_BM, ep,
-                                         "tc_gemm_i8_kernel<OzakiEpi,2>")));
-    return MMG_OK;                                             // (Op is released in stream order when this returns)
+    {
+        StageTimer tg(ctx, "qf_gemm");
+        MMG_TRY((launch_tc_gemm<OzakiEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, entries * 2, per_entry, per_entry, 0, TC_BM, ep,
+                                             "tc_gemm_i8_kernel<OzakiEpi,2>")));
+    }
+    return MMG_OK;
 }
 
 // MMG_QUAD_A = int8 (default: exact digit-plane products on the int8 tensor pipe) | dsyrk (cuBLAS, FP64 tensor pipe)
@@ -468,15 +475,15 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     const int64_t n_padN = round_up(n, TC_BN), ldq = round_up(n, TC_BK);
     const int64_t plane = n_padN * ldq;
     MMG_CHECK(ctx, (int64_t)T * S_alloc * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
-    DevBuf A, Bq, vec;
+    struct WsBuf { void* p = nullptr; template <class T> T* as() { return reinterpret_cast<T*>(p); } } A, Bq, vec, pre;
     const int64_t lda_work = round_up(n, TC_BN);               // dense (dsyrk) layout of A; the packed int8 product needs less
     if (!A_given)
-        MMG_CUDA(ctx, A.alloc(ctx->stream, quad_use_int8() ? (size_t)qa_slots(n) * QA_TILE_ELEMS * sizeof(double)
-                                                           : (size_t)lda_work * lda_work * sizeof(double)));
-    MMG_CUDA(ctx, Bq.alloc(ctx->stream, (size_t)T * S_alloc * plane));
+        MMG_TRY(ws_get(ctx, MMG_WS_QUAD_A, quad_use_int8() ? qa_slots(n) * QA_TILE_ELEMS * (int64_t)sizeof(double)
+                                                             : lda_work * lda_work * (int64_t)sizeof(double), &A.p));
+    MMG_TRY(ws_get(ctx, MMG_WS_QUAD_BQ, (int64_t)T * S_alloc * plane, &Bq.p));
     // vec: v[T][n_padN] | dg[T][n_padN] | y[T][n_out] | h0[T] | escale[T] | bscale[T] | amax | rho | wave counter
     const int64_t nd = 2 * (int64_t)T * n_padN + (int64_t)T * n_out + 3 * T + 3;
-    MMG_CUDA(ctx, vec.alloc(ctx->stream, (size_t)nd * sizeof(double)));
+    MMG_TRY(ws_get(ctx, MMG_WS_SCAN_VEC, nd * (int64_t)sizeof(double), &vec.p));
     double* d_v = vec.as<double>();
     double* d_dg = d_v + (int64_t)T * n_padN;
     double* d_y = d_dg + (int64_t)T * n_padN;
@@ -495,8 +502,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     // linear pre-pass: x.v_t, sum_j A_jj x_j^2 and ||x||_1 of every SNP in range, one stream over the genotypes.  When the rotation
     // is at hand, v_t = R_t'y~_t and diag(A_t) = column sums of squares of R_t are formed first and the pre-pass runs on a side
     // stream underneath the n^3 product A = R'R (FP64 / HBM work beside int8 tensor work); MMG_SCAN_OVERLAP=0 serialises them.
-    DevBuf pre;
-    MMG_CUDA(ctx, pre.alloc(ctx->stream, (size_t)((2 * T + 1) * snp_count + (int64_t)T * n_padN) * sizeof(double)));
+    MMG_TRY(ws_get(ctx, MMG_WS_SCAN_PRE, ((2 * T + 1) * snp_count + (int64_t)T * n_padN) * (int64_t)sizeof(double), &pre.p));
     double* d_dg_pre = pre.as<double>();                        // first: read as double2 by the pre-pass (16-byte aligned)
     double* p_xy = d_dg_pre + (int64_t)T * n_padN;
     double* p_qd = p_xy + (int64_t)T * snp_count;

@@ -83,6 +83,23 @@ static int ensure_scratch(mmg_ctx* ctx, int64_t bytes) {
     return MMG_OK;
 }
 
+// persistent workspace `id` of at least `bytes` bytes (contents undefined).  Work on it is ordered by the context's stream like
+// everything else; growing it waits for the stream (rare: sizes repeat from call to call).
+static int ws_get(mmg_ctx* ctx, int id, int64_t bytes, void** out) {
+    if (ctx->ws_bytes[id] < bytes) {
+        if (ctx->ws[id]) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->ws[id]);
+        }
+        ctx->ws[id] = nullptr;
+        ctx->ws_bytes[id] = 0;
+        MMG_CUDA(ctx, persistent_malloc(ctx->device, &ctx->ws[id], (size_t)bytes));
+        ctx->ws_bytes[id] = bytes;
+    }
+    *out = ctx->ws[id];
+    return MMG_OK;
+}
+
 static MmgMat* get_mat(mmg_ctx* ctx, mmg_mat h) {
     auto it = ctx->mats.find(h);
     return it == ctx->mats.end() ? nullptr : &it->second;

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
 
+#include <time.h>
+
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -79,7 +81,14 @@ struct mmg_ctx {
     // scratch
     void* scratch = nullptr;
     int64_t scratch_bytes = 0;
+
+    // persistent workspaces of the scan (grow-only, one per role): the few buffers of hundreds of MB a scan needs every call are
+    // kept instead of going through the stream-ordered pool each time -- the pool's occasional growth (cuMemCreate + map) showed
+    // up as milliseconds of host time on some ranks of a multi-GPU step, which every other rank then waits for in the next collective
+    void* ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t ws_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+enum { MMG_WS_OZAKI_PLANES = 0, MMG_WS_QUAD_A = 1, MMG_WS_QUAD_BQ = 2, MMG_WS_SCAN_PRE = 3, MMG_WS_SCAN_VEC = 4, MMG_WS_SCAN_OUT = 5 };
 
 namespace mmg {
 
@@ -175,6 +184,21 @@ struct StageTimer {
         ctx->pending_timers.push_back(MmgPendingTimer{name, e0, e1});
     }
     ~StageTimer() { stop(); }
+};
+
+// wall-clock time the HOST spends inside a scope (allocator calls, synchronisations), accumulated under `name`
+struct HostTimer {
+    mmg_ctx* ctx;
+    const char* name;
+    timespec t0;
+    HostTimer(mmg_ctx* c, const char* nm) : ctx(c), name(nm) { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    ~HostTimer() {
+        timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        MmgTimer& t = ctx->timers[name];
+        t.seconds += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        t.calls += 1;
+    }
 };
 
 }  // namespace mmg

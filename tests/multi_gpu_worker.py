@@ -50,7 +50,7 @@ def main():
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert torch.equal(lo, hi)
     # ranks fitting different models are refused
-    bad = lm.LinearMixedModel(y + 0.01 * rank, ctx=ctx, scan_impl='tcgen05', shard={'group': 'world', 'm_total': m})
+    bad = lm.LinearMixedModel(y * (1.0 + 0.01 * rank), ctx=ctx, scan_impl='tcgen05', shard={'group': 'world', 'm_total': m})
     bad.add_random_effect(Kd)
     try:
         bad.emmax_f_test(mine, eig_L=eig_L, eig_R=eig_R, emma_num=0)
