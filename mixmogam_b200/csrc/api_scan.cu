@@ -234,7 +234,7 @@ static int quad_form_int8(mmg_ctx* ctx, const MmgMat* R, double* A_slots, int64_
     slot_count = std::max<int64_t>(0, std::min(slot_count, qa_slots(n) - slot_begin));
     if (slot_count == 0) return MMG_OK;
     const int64_t op_pitch = round_up(n_out, TC_BK);
-    struct { void* p = nullptr; template <class T> T* as() { return reinterpret_cast<T*>(p); } } Op;
+    WsBuf Op;
     MMG_TRY(ws_get(ctx, MMG_WS_OZAKI_PLANES, OZ_PLANES * n_padM * op_pitch, &Op.p));
     MMG_CUDA(ctx, cudaMemsetAsync(Op.p, 0, (size_t)OZ_PLANES * n_padM * op_pitch, ctx->stream));
     ozaki_planes_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n_out + 31) / 32)), 256, 0, ctx->stream>>>(
@@ -475,7 +475,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     const int64_t n_padN = round_up(n, TC_BN), ldq = round_up(n, TC_BK);
     const int64_t plane = n_padN * ldq;
     MMG_CHECK(ctx, (int64_t)T * S_alloc * n_padN < (1ll << 31), "scan: too many phenotype slices for one launch");
-    struct WsBuf { void* p = nullptr; template <class T> T* as() { return reinterpret_cast<T*>(p); } } A, Bq, vec, pre;
+    WsBuf A, Bq, vec, pre;
     const int64_t lda_work = round_up(n, TC_BN);               // dense (dsyrk) layout of A; the packed int8 product needs less
     if (!A_given)
         MMG_TRY(ws_get(ctx, MMG_WS_QUAD_A, quad_use_int8() ? qa_slots(n) * QA_TILE_ELEMS * (int64_t)sizeof(double)

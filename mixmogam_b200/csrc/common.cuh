@@ -83,6 +83,12 @@ static int ensure_scratch(mmg_ctx* ctx, int64_t bytes) {
     return MMG_OK;
 }
 
+// view of a persistent workspace with DevBuf's accessors (nothing to release)
+struct WsBuf {
+    void* p = nullptr;
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
 // persistent workspace `id` of at least `bytes` bytes (contents undefined).  Work on it is ordered by the context's stream like
 // everything else; growing it waits for the stream (rare: sizes repeat from call to call).
 static int ws_get(mmg_ctx* ctx, int id, int64_t bytes, void** out) {
