@@ -164,6 +164,20 @@ int mmg_reml_f64(mmg_ctx* ctx, const double* eig_vals, const double* sq_etas, in
                  const double* deltas, int64_t g, double esp,
                  double* lls, double* dlls, double* opt_delta, double* opt_ll, int32_t* flags);
 
+/* Exact EMMA for a batch of k SNPs, and the ML / REML variance-component fits that need no eig_R (linear_models.py:931-968
+ * expedited_REML_t_test; :771-927 get_estimates with xs and its ML branch :811-824; get_ML :672-696).  The reference runs one
+ * n x n eigendecomposition of S(K+I)S per tested SNP; here every quantity of the likelihood (s1..s4 of :803-809) is evaluated
+ * from weighted moments in the eigenbasis of K alone (eig_L: UL = eigenvectors as rows, lam = eigenvalues), so a batch costs one
+ * rotation GEMM and O(k g n q^2) flops -- identical to the reference in exact arithmetic (csrc/emma.cuh has the algebra).
+ *   method: 0 = REML, 1 = ML.   X0 [n x q0] fixed effects (row-major), y [n].
+ *   SNPs: xs [k x n] host doubles, or snp_rows[k] = rows of the resident genotype block; both NULL (k = 0): fit the model
+ *   without a SNP (one output row).   deltas[g] = the grid (:796), esp = secant tolerance (:847).
+ *   out [k x (9 + q)], q = q0 + 1 (q0 without SNP): delta, max_ll, vg, ve, f_stat, p_val, var_perc, rss, mahalanobis_rss, beta[q]
+ *   (beta: fixed effects then the SNP, :903-906); lls / dlls [k x g] (nullable): the grid values (:807-810 / :821-824). */
+int mmg_emma_f64(mmg_ctx* ctx, int method, mmg_mat UL, const double* lam, const double* X0, int q0, const double* y,
+                 const double* xs, const int64_t* snp_rows, int64_t k, const double* deltas, int g, double esp,
+                 double* out, double* lls, double* dlls);
+
 /* ---- stage 3: SNP scan ------------------------------------------------------------------ */
 /* _emmax_f_test_ hot loops (linear_models.py:1315-1349) over the resident genotype rows
  * [snp_begin, +snp_count):

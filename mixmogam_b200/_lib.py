@@ -82,6 +82,7 @@ SIGNATURES = {
     'mmg_kinship_finalize_f64': (C.c_int, [_c_ctx, C.c_int, _i64, C.c_int, _i64, _dp]),
     'mmg_kinship_ibd_accumulate_f64': (C.c_int, [_c_ctx, _i64, _i64, _i64, _vp, C.POINTER(_i64)]),
     'mmg_reml_f64': (C.c_int, [_c_ctx, _vp, _vp, _i64, _i64, _vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_emma_f64': (C.c_int, [_c_ctx, C.c_int, _i64, _vp, _vp, C.c_int, _vp, _vp, _vp, _i64, _vp, C.c_int, C.c_double, _vp, _vp, _vp]),
     'mmg_emmax_scan_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _i64, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_quad_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_double, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -561,6 +562,40 @@ class Context(object):
         self._ck(self.lib.mmg_reml_f64(self.h, _ptr(eig_vals), _ptr(sq_etas), p, T, _ptr(deltas), g, float(esp),
                                        _ptr(lls), _ptr(dlls), _ptr(od), _ptr(ol), _ptr(fl)))
         return {'lls': lls, 'dlls': dlls, 'delta': od, 'll': ol, 'flags': fl}
+
+    EMMA_KEYS = ('delta', 'max_ll', 'vg', 've', 'f_stat', 'p_val', 'var_perc', 'rss', 'mahalanobis_rss')
+
+    def emma(self, UL, lam, X0, y, xs=None, snp_rows=None, deltas=None, esp=1e-6, method='REML', want_grid=False):
+        """Variance-component fit(s) in the eigenbasis of K alone (mmg_emma_f64): for every SNP of `xs` ([k x n]) or every
+        resident row of `snp_rows`, or -- with neither -- for the model without a SNP.  Returns a dict of length-k arrays
+        (EMMA_KEYS) plus 'betas' [k x q] (and 'lls', 'dlls' [k x g] with want_grid)."""
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        n = lam.shape[0]
+        X0 = np.ascontiguousarray(np.asarray(X0, dtype=np.float64).reshape(n, -1))
+        q0 = X0.shape[1]
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(n))
+        deltas = np.ascontiguousarray(deltas, dtype=np.float64)
+        k = 0
+        rows = None
+        if xs is not None:
+            xs = np.ascontiguousarray(np.asarray(xs, dtype=np.float64).reshape(-1, n))
+            k = xs.shape[0]
+        elif snp_rows is not None:
+            rows = np.ascontiguousarray(snp_rows, dtype=np.int64)
+            k = rows.shape[0]
+        kk = max(k, 1)
+        q = q0 + (1 if k else 0)
+        out = np.empty((kk, len(self.EMMA_KEYS) + q))
+        g = deltas.shape[0]
+        lls = np.empty((kk, g)) if want_grid else None
+        dlls = np.empty((kk, g)) if want_grid else None
+        self._ck(self.lib.mmg_emma_f64(self.h, 1 if method == 'ML' else 0, UL.handle, _ptr(lam), _ptr(X0), q0, _ptr(y), _ptr(xs), _ptr(rows),
+                                       k, _ptr(deltas), g, float(esp), _ptr(out), _ptr(lls), _ptr(dlls)))
+        res = {name: out[:, i].copy() for i, name in enumerate(self.EMMA_KEYS)}
+        res['betas'] = out[:, len(self.EMMA_KEYS):].copy()
+        if want_grid:
+            res['lls'], res['dlls'] = lls, dlls
+        return res
 
     # ---- stage 3 ----
     def emmax_scan(self, R, V, h0_rss, n_p, impl=IMPL_AUTO, snp_begin=0, snp_count=None, want_dots=False,

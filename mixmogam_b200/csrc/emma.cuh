@@ -36,6 +36,7 @@ struct EmmaParams {
     const double* deltas;                     // [g]
     int g;
     double esp;
+    double lbeta;                             // ln B(p/2, 1/2) of the F(1, p) survival function, p = n - q
     double *lls, *dlls;                       // [k x g]
     double* out;                              // [k x (EMMA_OUT + q)]
 };
@@ -283,7 +284,7 @@ static __global__ void __launch_bounds__(REML_THREADS) emma_refine_kernel(const 
         o[2] = vg;
         o[3] = vg * od;
         o[4] = f;
-        o[5] = prm.has_snp ? f_sf(f, 1.0, pd, lbeta_dev(0.5 * pd, 0.5)) : 1.0;   // :925
+        o[5] = prm.has_snp ? f_sf(f, 1.0, pd, prm.lbeta) : 1.0;                 // :925
         o[6] = 1.0 - full.s1 / h0;                                             // :921
         o[7] = rss;
         o[8] = full.s1;

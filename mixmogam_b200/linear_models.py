@@ -264,6 +264,34 @@ class LinearMixedModel(LinearModel):
         res['eig_L'] = eig_L
         return res
 
+    def get_ML(self, ngrids=100, llim=-10, ulim=10, esp=1e-6, eig_L=None, eig_R=None, H=None, H_inv=None, H_sqrt_inv=None,
+               dtype='single'):
+        """
+        Get ML estimates for the effect sizes, as well as the random effect contributions (linear_models.py:672-696).
+        H is the (full) covariance matrix, which speeds up calculations if it's available.
+        """
+        if _is_none(H):
+            if not eig_L:
+                eig_L = self._get_eigen_L_(None)
+            return self.get_estimates(eig_L, ngrids=ngrids, llim=llim, ulim=ulim, esp=esp, method='ML', eig_R=eig_R)
+        # the variance matrix is given: the likelihood from its eigenvalues and the transformed fit (:685-695)
+        ctx = self.ctx
+        Hd = ctx.to_device(H).copy()
+        evals = ctx.syevd(Hd)
+        Hd.free()
+        Hs = ctx.to_device(H_sqrt_inv)
+        XY = DeviceMatrix.from_host(ctx, np.hstack([self.X, self.Y]))
+        t = ctx.gemm(Hs, XY).download()
+        XY.free()
+        q = self.X.shape[1]
+        X_t, Y_t = t[:, :q], t[:, q:]
+        (betas, mahalanobis_rss, rank, hs) = np.linalg.lstsq(X_t, Y_t, rcond=None)
+        assert np.size(mahalanobis_rss) > 0, 'WTF?'
+        rss = float(np.sum((self.Y - self.X @ betas) ** 2))
+        n = Y_t.shape[0]
+        ll = -0.5 * (n * np.log(2 * np.pi) + np.sum(np.log(evals)) + mahalanobis_rss)
+        return {'ll': ll, 'rss': rss, 'mahalanobis_rss': mahalanobis_rss}
+
     def _etas(self, eig_R, Y):
         """etas = eig_R['vectors'] * Y (:794) with the eigenbasis resident in HBM."""
         ctx = self.ctx
@@ -287,39 +315,52 @@ class LinearMixedModel(LinearModel):
         Get REML estimates for the effect sizes, as well as the random effect contributions, using the
         EMMA algorithm (Kang et al., Genetics, 2008)  -- linear_models.py:771-927, REML branch.
         """
-        if method != 'REML':
-            raise NotImplementedError("mixmogam_b200 implements method='REML' (the EMMAX path); 'ML' is outside it")
+        if method not in ('REML', 'ML'):
+            raise Exception("method must be 'REML' or 'ML'")
         if xs is not None:
             xs = _col(xs, self.n)
             X = np.hstack([self.X, xs])
         else:
             X = self.X
-        if not eig_R or xs is not None:
-            if xs is None and self._eig_R_cache is not None and _is_none(K):
-                eig_R = self._eig_R_cache
-            else:
-                eig_R = self._get_eigen_R_(X=X, K=K)
-                if xs is None and _is_none(K):
-                    self._eig_R_cache = eig_R
         q = X.shape[1]
         n = self.n
         p = n - q
         m = ngrids + 1
-
-        etas = self._etas(eig_R, self.Y)                                       # :794
-        sq_etas = etas * etas
         log_deltas = (np.arange(m, dtype=np.float64) / ngrids) * (ulim - llim) + llim      # :796
         deltas = np.exp(log_deltas)
         assert len(deltas) == m, 'Number of deltas is incorrect.'
-        eig_vals = np.array(eig_R['values'], dtype=np.float64)
-        assert len(eig_vals) == p, 'Number of eigenvalues is incorrect.'
 
-        r = self.ctx.reml(eig_vals, sq_etas.T, deltas, esp)                    # :802-891 on the device
-        opt_delta = float(r['delta'][0])
-        opt_ll = float(r['ll'][0])
-
-        # :894-896 -- the reference divides a (p,1) by a (p,) array: a p x p outer quotient
-        opt_vg = float(np.sum(sq_etas) * np.sum(1.0 / (eig_vals + opt_delta)) / p)
+        if method == 'ML' or xs is not None:
+            # The reference eigendecomposes S(K+I)S for THIS X (:787-788: one n x n eigh per call, i.e. per tested SNP in
+            # expedited_REML_t_test) only to evaluate four sums that are functions of eig_L and the rotated columns alone
+            # (csrc/emma.cuh): no eig_R here.  REML without xs keeps the eig_R form below, which mirrors :789-810 literally.
+            if K is not None:
+                raise NotImplementedError('get_estimates(K=...) with xs / ML: pass the eig_L of that K instead')
+            UL = self.ctx.to_device(eig_L['vectors'])
+            r = self.ctx.emma(UL, eig_L['values'], X, self.Y, deltas=deltas, esp=esp, method=method, want_grid=True)
+            opt_delta = float(r['delta'][0])
+            opt_ll = float(r['max_ll'][0])
+            opt_vg = float(r['vg'][0])
+            self._last_reml = {'lls': r['lls'][0], 'dlls': r['dlls'][0], 'deltas': deltas, 'flags': None, 'eig_R': None}
+        else:
+            if not eig_R:
+                if self._eig_R_cache is not None and _is_none(K):
+                    eig_R = self._eig_R_cache
+                else:
+                    eig_R = self._get_eigen_R_(X=X, K=K)
+                    if _is_none(K):
+                        self._eig_R_cache = eig_R
+            etas = self._etas(eig_R, self.Y)                                       # :794
+            sq_etas = etas * etas
+            eig_vals = np.array(eig_R['values'], dtype=np.float64)
+            assert len(eig_vals) == p, 'Number of eigenvalues is incorrect.'
+            r = self.ctx.reml(eig_vals, sq_etas.T, deltas, esp)                    # :802-891 on the device
+            opt_delta = float(r['delta'][0])
+            opt_ll = float(r['ll'][0])
+            # :894-896 -- the reference divides a (p,1) by a (p,) array: a p x p outer quotient
+            opt_vg = float(np.sum(sq_etas) * np.sum(1.0 / (eig_vals + opt_delta)) / p)
+            self._last_reml = {'lls': r['lls'][0], 'dlls': r['dlls'][0], 'deltas': deltas, 'flags': int(r['flags'][0]),
+                               'eig_R': eig_R}
         opt_ve = opt_vg * opt_delta
 
         # H_sqrt_inv = diag(1/sqrt(eig_L.values + delta)) eig_L.vectors   (:898)
@@ -340,9 +381,6 @@ class LinearMixedModel(LinearModel):
         res_dict = {'max_ll': opt_ll, 'delta': opt_delta, 'beta': beta_est, 've': opt_ve, 'vg': opt_vg,
                     'rss': rss, 'mahalanobis_rss': mahalanobis_rss, 'H_sqrt_inv': LazyHostArray(H),
                     'pseudo_heritability': 1.0 / (1 + opt_delta)}
-        self._last_reml = {'lls': r['lls'][0], 'dlls': r['dlls'][0], 'deltas': deltas, 'flags': int(r['flags'][0]),
-                           'eig_R': eig_R}
-
         if xs is not None and return_f_stat:
             h0_X = X_t[:, :self.X.shape[1]]
             (h0_betas, h0_rss, h0_rank, h0_s) = np.linalg.lstsq(h0_X, Y_t, rcond=None)
@@ -354,37 +392,29 @@ class LinearMixedModel(LinearModel):
             res_dict['p_val'] = float(p_val[0])
         return res_dict
 
-    def expedited_REML_t_test(self, snps, ngrids=50, llim=-4, ulim=10, esp=1e-6, verbose=True, eig_L=None):
+    def expedited_REML_t_test(self, snps, ngrids=50, llim=-4, ulim=10, esp=1e-6, verbose=True, eig_L=None, _resident_rows=None):
         """
-        Single SNP analysis, i.e. EMMA (linear_models.py:931-968): one REML fit, hence one n x n
-        eigendecomposition of S(K+I)S, per SNP.
+        Single SNP analysis, i.e. EMMA (linear_models.py:931-968).  The reference calls get_estimates once per SNP, each call
+        eigendecomposing S(K+I)S for X = [X0, snp] (:787-788); here ALL the SNPs are fitted in one batch from eig_L alone
+        (mmg_emma_f64, csrc/emma.cuh): one rotation GEMM, then the delta grid, the secant refinement and the GLS fit per SNP in
+        two kernel launches.  Same outputs; identical in exact arithmetic (FP64 here, float32 grid in the reference).
+        `_resident_rows`: rows of the resident genotype block to refine instead of `snps` (the scan's own top hits).
         """
         assert len(self.random_effects) == 2, "Expedited REMLE only works when we have exactly two random effects."
         if _is_none(eig_L):
             eig_L = self._get_eigen_L_(None)
-        num_snps = len(snps)
-        f_stats = np.empty(num_snps)
-        vgs = np.empty(num_snps)
-        ves = np.empty(num_snps)
-        max_lls = np.empty(num_snps)
-        var_perc = np.empty(num_snps)
-        rss_list = np.empty(num_snps)
-        betas = []
-        p_vals = np.empty(num_snps)
-        for i, snp in enumerate(snps):
-            res = self.get_estimates(eig_L=eig_L, xs=np.asarray(snp, dtype=np.float64).reshape(-1, 1), ngrids=ngrids,
-                                     llim=llim, ulim=ulim, esp=esp, return_pvalue=True, return_f_stat=True)
-            f_stats[i] = res['f_stat']
-            vgs[i] = res['vg']
-            ves[i] = res['ve']
-            max_lls[i] = res['max_ll']
-            var_perc[i] = np.asarray(res['var_perc']).reshape(-1)[0]
-            betas.append(list(map(float, list(np.asarray(res['beta']).reshape(-1)))))
-            p_vals[i] = res['p_val']
-            rss_list[i] = np.asarray(res['rss']).reshape(-1)[0]
-            res['H_sqrt_inv'].dev.free()
-        return {'ps': p_vals, 'f_stats': f_stats, 'vgs': vgs, 'ves': ves, 'var_perc': var_perc,
-                'max_lls': max_lls, 'betas': betas, 'rss': rss_list}
+        deltas = np.exp((np.arange(ngrids + 1, dtype=np.float64) / ngrids) * (ulim - llim) + llim)
+        UL = self.ctx.to_device(eig_L['vectors'])
+        if _resident_rows is not None:
+            r = self.ctx.emma(UL, eig_L['values'], self.X, self.Y, snp_rows=_resident_rows, deltas=deltas, esp=esp)
+        else:
+            if len(snps) == 0:
+                return {'ps': np.empty(0), 'f_stats': np.empty(0), 'vgs': np.empty(0), 'ves': np.empty(0), 'var_perc': np.empty(0),
+                        'max_lls': np.empty(0), 'betas': [], 'rss': np.empty(0)}
+            xs = np.asarray([np.asarray(x, dtype=np.float64).reshape(-1) for x in snps])
+            r = self.ctx.emma(UL, eig_L['values'], self.X, self.Y, xs=xs, deltas=deltas, esp=esp)
+        return {'ps': r['p_val'], 'f_stats': r['f_stat'], 'vgs': r['vg'], 'ves': r['ve'], 'var_perc': r['var_perc'],
+                'max_lls': r['max_ll'], 'betas': [list(map(float, b)) for b in r['betas']], 'rss': r['rss']}
 
     # ------------------------------------------------------------------------------------------
     def emmax_f_test(self, snps, snp_priors=None, Z=None, with_betas=False, method='REML',
@@ -548,8 +578,8 @@ class LinearMixedModel(LinearModel):
             pval_indices = sorted(zip(res_d['ps'], range(num_snps)))[:emma_num]
             _say('Updating p-values using EMMA for the smallest %d p-values.' % len(pval_indices))
             l = list(map(list, zip(*pval_indices)))
-            top_snps = [np.asarray(snps[pi]) for pi in l[1]]
-            top_emma_res = self.expedited_REML_t_test(top_snps, eig_L=eig_L)
+            # the top hits are refined straight from the resident genotype block (the scan just used it): no re-upload
+            top_emma_res = self.expedited_REML_t_test(None, eig_L=eig_L, _resident_rows=np.asarray(l[1], dtype=np.int64))
             for pi, pv, f, r, v in zip(l[1], top_emma_res['ps'], top_emma_res['f_stats'],
                                        top_emma_res['rss'], top_emma_res['var_perc']):
                 res_d['ps'][pi] = pv

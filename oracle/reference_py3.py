@@ -368,6 +368,44 @@ class LinearMixedModel(object):
         res = (num_eig_vals * np.sum(v2 / v1) / np.sum(v2) - np.sum(1.0 / v1))
         return res
 
+    def _ll_(self, delta, eig_vals, eig_vals_L, sq_etas):
+        """linear_models.py:634-641."""
+        n = self.n
+        c_1 = 0.5 * n * (np.log(n / (2.0 * np.pi)) - 1)
+        v1 = eig_vals + delta
+        v2 = eig_vals_L + delta
+        res = c_1 - 0.5 * (n * np.log(np.sum(sq_etas.flatten() / v1)) + np.sum(np.log(v2)))
+        return res
+
+    def _dll_(self, delta, eig_vals, eig_vals_L, sq_etas):
+        """linear_models.py:644-650."""
+        v1 = eig_vals + delta
+        v2 = sq_etas.flatten() / v1
+        v3 = eig_vals_L + delta
+        res = (self.n * np.sum(v2 / v1) / np.sum(v2) - np.sum(1.0 / v3))
+        return res
+
+    def get_ML(self, ngrids=100, llim=-10, ulim=10, esp=1e-6, eig_L=None, eig_R=None, H=None, H_inv=None, H_sqrt_inv=None,
+               dtype=None):
+        """linear_models.py:672-696."""
+        dtype = self.dtype if dtype is None else _dt(dtype)
+        if H is None:
+            if not eig_L:
+                K = self.random_effects[1][1]
+                eig_L = self._get_eigen_L_(K)
+            res = self.get_estimates(eig_L, ngrids=ngrids, llim=llim, ulim=ulim, esp=esp, method='ML', eig_R=eig_R)
+        else:
+            evals, evecs = linalg.eigh(H)
+            X_t = np.array(H_sqrt_inv @ self.X, dtype=dtype)
+            Y_t = H_sqrt_inv @ self.Y
+            (betas, mahalanobis_rss, rank, hs) = linalg.lstsq(X_t, Y_t)
+            rss = np.sum(np.array(self.Y - np.dot(self.X, betas)) ** 2)
+            n = Y_t.shape[0]
+            ll = -0.5 * (n * np.log(2 * np.pi) + np.sum(np.log(evals)) + mahalanobis_rss)
+            assert len(mahalanobis_rss) > 0, 'WTF?'
+            res = {'ll': ll, 'rss': rss, 'mahalanobis_rss': mahalanobis_rss}
+        return res
+
     def get_REML(self, ngrids=100, llim=-10, ulim=10, esp=1e-6, eig_L=None, eig_R=None):
         """linear_models.py:653-668."""
         if not eig_L:
@@ -381,7 +419,7 @@ class LinearMixedModel(object):
     def get_estimates(self, eig_L, K=None, xs=None, ngrids=50, llim=-10, ulim=10, esp=1e-6,
                       return_pvalue=False, return_f_stat=False, method='REML', verbose=False,
                       dtype=None, eig_R=None, rss_0=None, literal_vg=None, reuse_eig_R=False):
-        """linear_models.py:771-927 (REML branch).
+        """linear_models.py:771-927 (REML and ML branches).
 
         reuse_eig_R=False is the reference: `if not (eig_R and xs != None)` at
         :787 is always true when xs is None, so a caller-supplied eig_R is
@@ -391,8 +429,8 @@ class LinearMixedModel(object):
         (default: literal when p <= 3000, else its closed form
         sum(sq_etas)*sum(1/(lambda+delta))/p)."""
         dtype = self.dtype if dtype is None else _dt(dtype)
-        if method != 'REML':
-            raise NotImplementedError('oracle covers the REML branch only')
+        if method not in ('REML', 'ML'):
+            raise Exception("method must be 'REML' or 'ML'")
         if xs is not None:
             X = np.hstack([self.X, xs])
         else:
@@ -416,14 +454,26 @@ class LinearMixedModel(object):
 
         lambdas = np.reshape(np.repeat(eig_vals, m), (p, m)) + np.reshape(np.repeat(deltas, p), (m, p)).T
         s1 = np.sum(sq_etas / lambdas, axis=0)
-        s2 = np.sum(np.log(lambdas), axis=0)
-        log_c = np.log((p) / (2.0 * np.pi))                    # np.float64 scalar
-        if self.promotion == 'numpy1':
-            log_c = float(log_c)                               # value-based casting: does not upcast s1, s2
-        lls = 0.5 * (p * (log_c - 1 - np.log(s1)) - s2)
-        s3 = np.sum(sq_etas / (lambdas * lambdas), axis=0)
-        s4 = np.sum(1 / lambdas, axis=0)
-        dlls = 0.5 * (p * s3 / s1 - s4)
+        if method == 'REML':
+            s2 = np.sum(np.log(lambdas), axis=0)
+            log_c = np.log((p) / (2.0 * np.pi))                    # np.float64 scalar
+            if self.promotion == 'numpy1':
+                log_c = float(log_c)                               # value-based casting: does not upcast s1, s2
+            lls = 0.5 * (p * (log_c - 1 - np.log(s1)) - s2)
+            s3 = np.sum(sq_etas / (lambdas * lambdas), axis=0)
+            s4 = np.sum(1 / lambdas, axis=0)
+            dlls = 0.5 * (p * s3 / s1 - s4)
+        else:                                                      # :811-824
+            eig_vals_L = np.array(eig_L['values'], dtype=dtype)
+            xis = np.reshape(np.repeat(eig_vals_L, m), (n, m)) + np.reshape(np.repeat(deltas, n), (m, n)).T
+            s2 = np.sum(np.log(xis), axis=0)
+            log_c = np.log((n) / (2.0 * np.pi))
+            if self.promotion == 'numpy1':
+                log_c = float(log_c)
+            lls = 0.5 * (n * (log_c - 1 - np.log(s1)) - s2)
+            s3 = np.sum(sq_etas / (lambdas * lambdas), axis=0)
+            s4 = np.sum(1 / xis, axis=0)
+            dlls = 0.5 * (n * s3 / s1 - s4)
 
         max_ll_i = np.argmax(lls)
         max_ll = lls[max_ll_i]
@@ -446,8 +496,12 @@ class LinearMixedModel(object):
             try:
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")
-                    new_opt_delta = optimize.newton(self._redll_, opt_delta, args=(eig_vals, sq_etas), tol=esp,
-                                                    maxiter=100)
+                    if method == 'REML':
+                        new_opt_delta = optimize.newton(self._redll_, opt_delta, args=(eig_vals, sq_etas), tol=esp,
+                                                        maxiter=100)
+                    else:
+                        new_opt_delta = optimize.newton(self._dll_, opt_delta, args=(eig_vals, eig_vals_L, sq_etas),
+                                                        tol=esp, maxiter=100)
                     if self.promotion == 'numpy1':
                         new_opt_delta = float(new_opt_delta)
             except Exception:
@@ -462,7 +516,10 @@ class LinearMixedModel(object):
                     and not np.isinf(new_opt_delta):
                 opt_delta = new_opt_delta
                 opt_ll = self._rell_(opt_delta, eig_vals, sq_etas)
-            opt_ll = self._rell_(opt_delta, eig_vals, sq_etas)                 # :881-882
+            if method == 'REML':
+                opt_ll = self._rell_(opt_delta, eig_vals, sq_etas)             # :881-882
+            else:
+                opt_ll = self._ll_(opt_delta, eig_vals, eig_vals_L, sq_etas)   # :883-884
 
             if opt_ll < max_ll:
                 opt_delta = deltas[max_ll_i]
@@ -636,6 +693,86 @@ class LinearMixedModel(object):
                 res_d['var_perc'][pi] = v
         return res_d
 
+    def emmax_GxT_f_test(self, snps, E, Z=None, with_betas=False, method='REML', eig_L=None, eig_R=None):
+        """linear_models.py:1383-1416."""
+        if not eig_L:
+            eig_L = self._get_eigen_L_()
+        if not eig_R:
+            eig_R = self._get_eigen_R_(X=self.X)
+        res = self.get_estimates(eig_L, method=method, eig_R=eig_R, reuse_eig_R=True)
+        r = self._emmax_GxT_f_test_(snps, res['H_sqrt_inv'], E, Z, with_betas=with_betas, eig_L=eig_L)
+        r['pseudo_heritability'] = res['pseudo_heritability']
+        r['ve'] = res['ve']
+        r['vg'] = res['vg']
+        r['max_ll'] = res['max_ll']
+        return r
+
+    def _emmax_GxT_f_test_(self, snps, H_sqrt_inv, T, Z, verbose=False, **kwargs):
+        """linear_models.py:1422-1514: per SNP the genetic model [h0_X, x~] and the full model [h0_X, x~, (x o T)~]."""
+        dtype = self.dtype                                                  # :1432 ('single' in the reference)
+        n = self.n
+        num_snps = len(snps)
+        if Z is None:
+            Z = np.eye(n)
+        h0_X = np.array(H_sqrt_inv @ self.X, dtype=dtype)
+        Y = H_sqrt_inv @ self.Y
+        (h0_betas, h0_rss, h0_rank, h0_s) = linalg.lstsq(h0_X, Y)
+        Y = np.array(Y - h0_X @ h0_betas, dtype=dtype)
+        h0_betas = list(map(float, list(np.asarray(h0_betas).reshape(-1))))
+        T_flat = np.array(T).flatten()
+
+        betas_g_list = [h0_betas] * num_snps
+        betas_gt_list = [h0_betas] * num_snps
+        M = H_sqrt_inv.T
+        rss_g_list = np.repeat(h0_rss, num_snps)
+        rss_gt_list = np.repeat(h0_rss, num_snps)
+        chunk_size = len(Y)
+        for i in range(0, num_snps, chunk_size):
+            snps_chunk = np.array(snps[i:i + chunk_size], dtype=dtype) @ Z.T
+            GT = np.array(np.array(snps_chunk) * T_flat) @ M
+            Xs = snps_chunk @ M
+            for j in range(len(Xs)):
+                X_j = Xs[j:j + 1]
+                GT_j = GT[j:j + 1]
+                (betas_g, rss_g, p, sigma) = linalg.lstsq(np.hstack([h0_X, X_j.T]), Y)
+                if _residue_value(rss_g) is not None:
+                    betas_g_list[i + j] = list(map(float, list(np.asarray(betas_g).reshape(-1))))
+                    rss_g_list[i + j] = np.asarray(rss_g).reshape(-1)[0]
+                    (betas_gt, rss_gt, p, sigma) = linalg.lstsq(np.hstack([h0_X, X_j.T, GT_j.T]), Y)
+                    if _residue_value(rss_gt) is not None:
+                        betas_gt_list[i + j] = list(map(float, list(np.asarray(betas_gt).reshape(-1))))
+                        rss_gt_list[i + j] = np.asarray(rss_gt).reshape(-1)[0]
+
+        q = 1
+        p = len(self.X.T) + q
+        n_p = n - p
+        rss_g_ratio = h0_rss / rss_g_list
+        var_perc_g = 1 - 1 / rss_g_ratio
+        f_stats_g = (rss_g_ratio - 1) * n_p / float(q)
+        p_vals_g = stats.f.sf(f_stats_g, q, n_p)
+        g_res_d = {'ps': p_vals_g, 'f_stats': f_stats_g, 'rss': rss_g_list, 'var_perc': var_perc_g,
+                   'h0_rss': h0_rss, 'h0_betas': h0_betas, 'betas': betas_g_list}
+
+        q = 2
+        p = len(self.X.T) + q
+        n_p = n - p
+        rss_gt_ratio = h0_rss / rss_gt_list
+        var_perc_gt = 1 - 1 / rss_gt_ratio
+        f_stats_gt = (rss_gt_ratio - 1) * n_p / float(q)
+        p_vals_gt = stats.f.sf(f_stats_gt, q, n_p)
+        gt_res_d = {'ps': p_vals_gt, 'f_stats': f_stats_gt, 'rss': rss_gt_list, 'var_perc': var_perc_gt,
+                    'betas': betas_gt_list}
+
+        q = 1
+        p = len(self.X.T) + q
+        n_p = n - p
+        rss_gt_g_ratio = rss_g_list / rss_gt_list
+        var_perc_gt_g = 1 - 1 / rss_gt_g_ratio
+        f_stats_gt_g = (rss_gt_g_ratio - 1) * n_p / float(q)
+        p_vals_gt_g = stats.f.sf(f_stats_gt_g, q, n_p)
+        gt_g_res_d = {'ps': p_vals_gt_g, 'f_stats': f_stats_gt_g, 'var_perc': var_perc_gt_g}
+        return {'g_res': g_res_d, 'gt_res': gt_res_d, 'gt_g_res': gt_g_res_d}
+
     def _emmax_permutations_(self, snps, K, H_sqrt_inv, num_perm=100, Ys=None):
         """linear_models.py:1125-1175, quirks kept: self.Y is mean-centred in
         place (:1140), the null fit is subtracted twice (:1144,:1147), SNPs are
@@ -698,6 +835,22 @@ def emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_nu
 # --------------------------------------------------------------------------
 # Synthetic inputs shared by tests and bench
 # --------------------------------------------------------------------------
+
+def emmax_w_two_env(snps, phenotypes, K, E, cofactors=None, Z=None, dtype='single', promotion='numpy1'):
+    """linear_models.py:1749-1787."""
+    lmm = LinearMixedModel(phenotypes, dtype=dtype, promotion=promotion)
+    if Z is not None:
+        lmm.add_random_effect(Z @ K @ Z.T)
+        if cofactors:
+            for cofactor in cofactors:
+                lmm.add_factor(Z @ cofactor)
+    else:
+        lmm.add_random_effect(K)
+        if cofactors:
+            for cofactor in cofactors:
+                lmm.add_factor(cofactor)
+    return lmm.emmax_GxT_f_test(snps, E=E, Z=Z)
+
 
 def synth_genotypes(m, n, coding='diploid_int', seed=20240601, maf_floor=0.1):
     """SNP-major int8[m, n]; per-SNP allele frequency U(0.05, 0.5) (U(maf_floor+,0.5)

@@ -93,11 +93,53 @@ def fast_f_test_golden(lm):
     save('ref_fast_f_test_n400.npz', **out)
 
 
+def ml_emma_gxt_golden(lm):
+    """get_ML and the ML branch of get_estimates (linear_models.py:672-696, 811-824), the exact-EMMA
+    refinement expedited_REML_t_test (:931-968, one eigendecomposition of S(K+I)S per SNP in the reference) and the G x E scan
+    emmax_w_two_env -> _emmax_GxT_f_test_ (:1749-1787, :1422-1514)."""
+    e = g('emmax_diploid_n400.npz')
+    snps, y, K, cof = e['snps'], e['y'], e['K'], e['cofactor']
+    out = {}
+    for tag, cofs in (('', []), ('cof_', [cof])):
+        lmm = lm.LinearMixedModel(list(y))
+        lmm.add_random_effect(K)
+        for c in cofs:
+            lmm.add_factor(c)
+        r = quiet(lmm.get_ML)
+        for k in ('delta', 'max_ll', 'vg', 've', 'pseudo_heritability'):
+            out['ml_' + tag + k] = np.float64(r[k])
+        out['ml_' + tag + 'beta'] = np.asarray(r['beta'], dtype=np.float64).reshape(-1)
+        out['ml_' + tag + 'mahalanobis_rss'] = np.asarray(r['mahalanobis_rss'], dtype=np.float64).reshape(-1)
+        out['ml_' + tag + 'rss'] = np.asarray(r['rss'], dtype=np.float64).reshape(-1)
+        rr = quiet(lmm.expedited_REML_t_test, list(snps[:12]))
+        for k in ('ps', 'f_stats', 'vgs', 'ves', 'var_perc', 'max_lls', 'rss'):
+            out['emma_' + tag + k] = np.asarray(rr[k], dtype=np.float64)
+        out['emma_' + tag + 'betas'] = np.asarray(rr['betas'], dtype=np.float64)
+    rng = np.random.Generator(np.random.PCG64(20240612))
+    E = (rng.random(400) < 0.5).astype(np.float64).reshape(-1, 1)
+    ye = np.asarray(y) + 0.8 * E[:, 0] * (snps[20] - snps[20].mean()) + 0.3 * E[:, 0]
+    out.update(E=E, ye=ye)
+    for tag, cofs in (('', None), ('cof_', [cof])):
+        r = quiet(lm.emmax_w_two_env, list(snps[:600]), list(ye), K, E, cofs)
+        for part in ('g_res', 'gt_res', 'gt_g_res'):
+            for k in ('ps', 'f_stats', 'var_perc'):
+                out['gxt_%s%s_%s' % (tag, part, k)] = np.asarray(r[part][k], dtype=np.float64)
+        for part in ('g_res', 'gt_res'):
+            out['gxt_%s%s_rss' % (tag, part)] = np.asarray(r[part]['rss'], dtype=np.float64)
+            out['gxt_%s%s_betas' % (tag, part)] = np.asarray(r[part]['betas'], dtype=np.float64)
+        out['gxt_%sh0_rss' % tag] = np.asarray(r['g_res']['h0_rss'], dtype=np.float64).reshape(-1)
+        for k in ('pseudo_heritability', 've', 'vg', 'max_ll'):
+            out['gxt_%s%s' % (tag, k)] = np.float64(r[k])
+    save('ref_ml_emma_gxt_n400.npz', **out)
+
+
 def main():
     kin = py2shim.load('kinship')
     lm = py2shim.load('linear_models')
     if sys.argv[1:] == ['fast_f_test']:
         return fast_f_test_golden(lm)
+    if sys.argv[1:] == ['ml_emma_gxt']:
+        return ml_emma_gxt_golden(lm)
 
     # ---- kinship.py:14-100, all three estimators, literal loops -------------------------------------
     xb = g('ibs_binary_n37.npz')['snps']
@@ -201,6 +243,7 @@ def main():
     out['ibd_kinship_nofilter'] = np.asarray(files2['in']['kinship'].data, dtype=np.float64)
     save('ref_hdf5_n198.npz', **out)
     fast_f_test_golden(lm)
+    ml_emma_gxt_golden(lm)
 
 
 if __name__ == '__main__':

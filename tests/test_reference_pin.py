@@ -170,3 +170,53 @@ def test_float64_oracle_within_reference_float32_noise(name, ref_name):
     assert d.max() < 1e-2
     assert np.array_equal(np.argsort(e['double_ps'])[:20], np.argsort(ref['ps'])[:20])
     assert abs(float(e['double_pseudo_heritability']) - float(ref['pseudo_heritability'])) < 1e-4
+
+
+def test_ml_emma_gxt_bit_exact_vs_reference_run():
+    """get_ML (linear_models.py:672-696 with the ML branch :811-824), expedited_REML_t_test (:931-968) and
+    emmax_w_two_env -> _emmax_GxT_f_test_ (:1749-1787, :1422-1514), oracle vs the reference's own code, bit for bit; the
+    float64 mode the GPU path is held to stays inside the reference's float32 noise."""
+    ref = golden('ref_ml_emma_gxt_n400.npz')
+    e = golden('emmax_diploid_n400.npz')
+    snps, y, K, cof = e['snps'], e['y'], e['K'], e['cofactor']
+
+    def same(a, key):
+        a = np.asarray(a, dtype=np.float64).reshape(-1)
+        b = np.asarray(ref[key], dtype=np.float64).reshape(-1)
+        assert np.array_equal(a, b, equal_nan=True), '%s differs: max abs %g' % (key, np.max(np.abs(a - b)))
+
+    for tag, cofs in (('', []), ('cof_', [cof])):
+        lmm = o.LinearMixedModel(list(y), 'single', promotion='numpy2')
+        lmm.add_random_effect(K)
+        for c in cofs:
+            lmm.add_factor(c)
+        r = lmm.get_ML()
+        for k in ('delta', 'max_ll', 'vg', 've', 'pseudo_heritability', 'beta', 'mahalanobis_rss', 'rss'):
+            same(r[k], 'ml_' + tag + k)
+        rr = lmm.expedited_REML_t_test(list(snps[:12]))
+        for k in ('ps', 'f_stats', 'vgs', 'ves', 'var_perc', 'max_lls', 'rss', 'betas'):
+            same(rr[k], 'emma_' + tag + k)
+        rd = o.LinearMixedModel(list(y), 'double')
+        rd.add_random_effect(K)
+        for c in cofs:
+            rd.add_factor(c)
+        md = rd.get_ML()
+        # (the float32 likelihood of the reference is flat to its own rounding around the optimum: delta moves by a few per cent)
+        assert abs(md['delta'] / float(ref['ml_' + tag + 'delta']) - 1) < 0.1 and abs(md['max_ll'] - float(ref['ml_' + tag + 'max_ll'])) < 5e-2
+    E, ye = ref['E'], ref['ye']
+    for tag, cofs in (('', None), ('cof_', [cof])):
+        r = o.emmax_w_two_env(list(snps[:600]), list(ye), K, E, cofs, dtype='single', promotion='numpy2')
+        for part in ('g_res', 'gt_res', 'gt_g_res'):
+            for k in ('ps', 'f_stats', 'var_perc'):
+                same(r[part][k], 'gxt_%s%s_%s' % (tag, part, k))
+        for part in ('g_res', 'gt_res'):
+            same(r[part]['rss'], 'gxt_%s%s_rss' % (tag, part))
+            same(r[part]['betas'], 'gxt_%s%s_betas' % (tag, part))
+        same(r['g_res']['h0_rss'], 'gxt_%sh0_rss' % tag)
+        for k in ('pseudo_heritability', 've', 'vg', 'max_ll'):
+            same(r[k], 'gxt_%s%s' % (tag, k))
+        rd = o.emmax_w_two_env(list(snps[:600]), list(ye), K, E, cofs, dtype='double')
+        ok = ~np.all(snps[:600] == cof[None, :], axis=1) if cofs else np.ones(600, dtype=bool)     # the cofactor itself: collinear, noise
+        for part in ('g_res', 'gt_res', 'gt_g_res'):
+            d = np.abs(np.log10(rd[part]['ps']) - np.log10(ref['gxt_%s%s_ps' % (tag, part)]))
+            assert np.max(d[ok]) < 5e-2                                   # float32 three-column lstsq
