@@ -61,7 +61,8 @@ int mmg_stream_handle(mmg_ctx* ctx, void** stream);
 /* number of kernels of THIS library launched on ctx since creation (bench.py gpu_launches) */
 int64_t mmg_launch_count(mmg_ctx* ctx);
 /* named stage timers in seconds, CUDA-event based, accumulated since the last reset.
- * names: "h2d","pack","gram","finalize","ibd","syevd","reml","scan_prep","scan","d2h" */
+ * names: "h2d","pack","gram","finalize","ibd","syevd","reml","scan_prep","scan","d2h","matrix" (FP64 matrix plumbing: copies,
+ * scalings, cuBLAS dgemm) */
 int mmg_timer_get(mmg_ctx* ctx, const char* name, double* seconds, int64_t* calls);
 int mmg_timer_reset(mmg_ctx* ctx);
 /* duration (ms) of the most recent launch of the dominant kernels, measured with CUDA
@@ -95,6 +96,8 @@ int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat A, const double* d_host);         /
 int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat A, double alpha);                   /* A += alpha*I   */
 /* kinship.scale_k (kinship.py:94-100): c = tr(K) - sum(K)/n ; K *= (n-1)/c ; returns the scalar */
 int mmg_mat_scale_k(mmg_ctx* ctx, mmg_mat K, double* scalar);
+/* dst = scale_k(src), src untouched (linear_models.py:580 add_random_effect scales a copy of the caller's K); scalar nullable */
+int mmg_mat_scale_k_copy(mmg_ctx* ctx, mmg_mat src, mmg_mat dst, double* scalar);
 /* linalg.eigh (linear_models.py:594,613) through cuSOLVER syevd, FP64.  A is overwritten by the
  * eigenvectors stored as ROWS (the reference's `evecs.T`, :596,:615), eigenvalues ascending in w_host. */
 int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat A, double* w_host, double* seconds);

@@ -62,6 +62,7 @@ SIGNATURES = {
     'mmg_mat_scale_rows': (C.c_int, [_c_ctx, _i64, _vp]),
     'mmg_mat_add_diag': (C.c_int, [_c_ctx, _i64, C.c_double]),
     'mmg_mat_scale_k': (C.c_int, [_c_ctx, _i64, _dp]),
+    'mmg_mat_scale_k_copy': (C.c_int, [_c_ctx, _i64, _i64, _dp]),
     'mmg_mat_syevd': (C.c_int, [_c_ctx, _i64, _vp, _dp]),
     'mmg_snps_upload': (C.c_int, [_c_ctx, _vp, _i64, _i64, _i64]),
     'mmg_snps_upload_rows': (C.c_int, [_c_ctx, _vp, _i64, _i64]),
@@ -305,7 +306,7 @@ class Context(object):
         self._ck(self.lib.mmg_timer_get(self.h, name.encode(), C.byref(s), C.byref(c)))
         return s.value, c.value
 
-    STAGES = ('h2d', 'pack', 'gram', 'finalize', 'ibd', 'syevd', 'reml', 'scan_prep', 'scan', 'd2h')
+    STAGES = ('h2d', 'pack', 'gram', 'finalize', 'ibd', 'syevd', 'reml', 'matrix', 'scan_prep', 'scan', 'd2h')
     DETAIL = ('qf_gemm', 'host_qf_alloc', 'host_qf_total', 'host_qf_tiles')      # inside 'scan_prep' / host wall clock: not additive
 
     def timers(self, detail=False):
@@ -479,6 +480,12 @@ class Context(object):
         s = C.c_double(0)
         self._ck(self.lib.mmg_mat_scale_k(self.h, K.handle, C.byref(s)))
         return s.value
+
+    def scale_k_copy(self, K):
+        """scale_k(K) as a new DeviceMatrix; K is left as it is.  Stream ordered (nothing waits for the factor)."""
+        out = DeviceMatrix(self, K.shape[0], K.shape[1], zero=False)
+        self._ck(self.lib.mmg_mat_scale_k_copy(self.h, K.handle, out.handle, None))
+        return out
 
     def syevd(self, A):
         """In place: A <- eigenvectors as rows; returns ascending eigenvalues."""

@@ -256,6 +256,7 @@ int mmg_mat_copy(mmg_ctx* ctx, mmg_mat dst, mmg_mat src) {
     MmgMat *d = ctx ? get_mat(ctx, dst) : nullptr, *s = ctx ? get_mat(ctx, src) : nullptr;
     MMG_CHECK(ctx, d && s && d->rows == s->rows && d->cols == s->cols, "mmg_mat_copy: shape mismatch");
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm_matrix(ctx, "matrix");
     MMG_CUDA(ctx, cudaMemcpyAsync(d->d, s->d, (size_t)d->rows * d->cols * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return MMG_OK;
 }
@@ -263,6 +264,7 @@ int mmg_mat_gemm(mmg_ctx* ctx, int ta, int tb, double alpha, mmg_mat Ah, mmg_mat
     MmgMat *A = ctx ? get_mat(ctx, Ah) : nullptr, *B = ctx ? get_mat(ctx, Bh) : nullptr, *C = ctx ? get_mat(ctx, Ch) : nullptr;
     MMG_CHECK(ctx, A && B && C, "mmg_mat_gemm: unknown handle");
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm_matrix(ctx, "matrix");
     const int64_t m = ta ? A->cols : A->rows, k = ta ? A->rows : A->cols;
     const int64_t kb = tb ? B->cols : B->rows, n = tb ? B->rows : B->cols;
     MMG_CHECK(ctx, k == kb && C->rows == m && C->cols == n, "mmg_mat_gemm: shape mismatch (%lldx%lld)*(%lldx%lld)->(%lldx%lld)",
@@ -277,6 +279,7 @@ int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat h, const double* d_host) {
     MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, A && d_host, "mmg_mat_scale_rows: bad argument");
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm_matrix(ctx, "matrix");
     MMG_TRY(ensure_scratch(ctx, A->rows * sizeof(double)));
     MMG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, d_host, A->rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((unsigned)((A->cols + 255) / 256), (unsigned)A->rows);
@@ -293,10 +296,38 @@ int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat h, double alpha) {
     return launch_check(ctx, "add_diag_kernel");
 }
 
+// dst = kinship.scale_k(src) without touching src (LinearMixedModel.add_random_effect keeps the caller's K intact,
+// linear_models.py:580): row sums of src, the factor on the device, one scaled copy -- instead of a copy, row sums and an
+// in-place scaling.  *scalar (nullable): the factor; asking for it waits for the stream.
+int mmg_mat_scale_k_copy(mmg_ctx* ctx, mmg_mat srch, mmg_mat dsth, double* scalar) {
+    MmgMat *S = ctx ? get_mat(ctx, srch) : nullptr, *D = ctx ? get_mat(ctx, dsth) : nullptr;
+    MMG_CHECK(ctx, S && D && S != D && S->rows == S->cols && D->rows == S->rows && D->cols == S->cols, "mmg_mat_scale_k_copy: needs two square matrices of one shape");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm(ctx, "matrix");
+    const int n = (int)S->rows;
+    MMG_TRY(ensure_scratch(ctx, (n + 3) * sizeof(double)));
+    double* rs = (double*)ctx->scratch;
+    rowsum_kernel<<<n, 256, 0, ctx->stream>>>(S->d, S->cols, n, rs);
+    MMG_TRY(launch_check(ctx, "rowsum_kernel"));
+    scale_k_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(rs, S->d, S->cols, n, rs + n);
+    MMG_TRY(launch_check(ctx, "scale_k_reduce_kernel"));
+    scale_factor_kernel<<<1, 1, 0, ctx->stream>>>(rs + n, n);
+    MMG_TRY(launch_check(ctx, "scale_factor_kernel"));
+    const int64_t cnt = (int64_t)n * n;
+    scaled_copy_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const double2*)S->d, (double2*)D->d, cnt / 2, rs + n + 2,
+                                                                  (cnt & 1) ? S->d + cnt - 1 : nullptr, (cnt & 1) ? D->d + cnt - 1 : nullptr);
+    MMG_TRY(launch_check(ctx, "scaled_copy_kernel"));
+    if (scalar) {
+        MMG_CUDA(ctx, cudaMemcpyAsync(scalar, rs + n + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MMG_OK;
+}
 int mmg_mat_scale_k(mmg_ctx* ctx, mmg_mat h, double* scalar) {
     MmgMat* K = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, K && K->rows == K->cols, "mmg_mat_scale_k: needs a square matrix");
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm_matrix(ctx, "matrix");
     MMG_TRY(scale_k_device(ctx, K, scalar));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMG_OK;

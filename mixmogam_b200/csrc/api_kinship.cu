@@ -430,16 +430,36 @@ int mmg_kinship_finalize_f64(mmg_ctx* ctx, int coding, int64_t m_total, int scal
     MMG_CHECK(ctx, K && ctx->G, "mmg_kinship_finalize_f64: need a Gram and an output matrix");
     MMG_CHECK(ctx, K->rows == ctx->n && K->cols == ctx->n, "K_out must be n x n");
     MMG_CHECK(ctx, m_total > 0, "m_total must be positive");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     StageTimer tm(ctx, "finalize");
     const int n = (int)ctx->n;
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    const int64_t T = (n + 31) / 32, tiles = T * (T + 1) / 2;
+    DevBuf part;                                                 // per-tile (sum, trace) partials + {sum, trace, factor}
+    MMG_CUDA(ctx, part.alloc(ctx->stream, (size_t)(2 * tiles + 3) * sizeof(double)));
+    double* d_part = part.as<double>();
+    double* d_sums = d_part + 2 * tiles;
+    if (scaled) {
+        if (coding == MMG_CODING_BINARY)
+            kin_tile_sums_kernel<0><<<(unsigned)tiles, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n, (double)m_total, d_part);
+        else
+            kin_tile_sums_kernel<1><<<(unsigned)tiles, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n, (double)m_total, d_part);
+        MMG_TRY(launch_check(ctx, "kin_tile_sums_kernel"));
+        kin_final_sums_kernel<<<1, 1024, 0, ctx->stream>>>(d_part, tiles, n, d_sums);
+        MMG_TRY(launch_check(ctx, "kin_final_sums_kernel"));
+    }
+    const double* d_scale = scaled ? d_sums + 2 : nullptr;
     if (coding == MMG_CODING_BINARY)
-        kinship_finalize_kernel<0><<<grid, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n, (double)m_total, K->d, K->cols);
+        kin_write_tile_kernel<0><<<(unsigned)tiles, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n, (double)m_total, d_scale, K->d, K->cols);
     else
-        kinship_finalize_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n, (double)m_total, K->d, K->cols);
-    MMG_TRY(launch_check(ctx, "kinship_finalize_kernel"));
-    if (scale_scalar) *scale_scalar = 1.0;
-    if (scaled) MMG_TRY(scale_k_device(ctx, K, scale_scalar));
+        kin_write_tile_kernel<1><<<(unsigned)tiles, 256, 0, ctx->stream>>>(ctx->G, ctx->g_pad, n, (double)m_total, d_scale, K->d, K->cols);
+    MMG_TRY(launch_check(ctx, "kin_write_tile_kernel"));
+    if (scale_scalar) {
+        *scale_scalar = 1.0;
+        if (scaled) {                                           // only a caller that asks for the factor waits for it
+            MMG_CUDA(ctx, cudaMemcpyAsync(scale_scalar, d_sums + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
     return MMG_OK;
 }
 

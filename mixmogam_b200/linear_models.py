@@ -179,15 +179,21 @@ class LinearMixedModel(LinearModel):
         """linear_models.py:577-580: stores kinship.scale_k(cov_matrix)."""
         if effect_type != 'normal':
             raise Exception('Currently, only Normal random effects are allowed.')
+        own = False
         if isinstance(cov_matrix, DeviceMatrix):
-            K = cov_matrix.copy()
+            src = cov_matrix
+        elif isinstance(cov_matrix, LazyHostArray) and cov_matrix._rows is None:
+            src = cov_matrix.dev
         else:
-            K = self.ctx.to_device(cov_matrix)
-            if isinstance(cov_matrix, LazyHostArray):
-                K = K.copy()
-        if K.shape != (self.n, self.n):
+            src = self.ctx.lookup_resident(cov_matrix)        # the kinship this context just handed out: still in HBM
+            if src is None:
+                src = DeviceMatrix.from_host(self.ctx, np.asarray(cov_matrix, dtype=np.float64))
+                own = True
+        if src.shape != (self.n, self.n):
             raise ValueError('kinship must be %d x %d' % (self.n, self.n))
-        self.ctx.scale_k(K)
+        K = self.ctx.scale_k_copy(src)                        # :580 -- the caller's matrix is never modified
+        if own:
+            src.free()
         self._K_dev.append(K)
         self.random_effects.append((effect_type, LazyHostArray(K)))
         self._invalidate()

@@ -240,27 +240,25 @@ def check_same_model(ctx, values, group=None):
 
 
 class GatheredRows(object):
-    """Per-SNP result vector of a sharded scan: lives in the all-gathered device buffer ([world x 5 x maxlen]) and turns into a
-    numpy array on first use (np.asarray(x), x[...], len(x))."""
+    """Per-SNP result vector of a sharded scan: a row of the gathered, compacted device matrix ([5 x m_total]) that turns
+    into a numpy array on first use (np.asarray(x), x[...], len(x))."""
 
-    def __init__(self, gathered, key_index, sizes):
-        self._g, self._k, self._sizes = gathered, key_index, sizes
+    def __init__(self, gathered, key_index, m_total):
+        self._g, self._k, self._m = gathered, key_index, m_total
         self._host = None
 
     def host(self):
         if self._host is None:
-            world = len(self._sizes)
-            a = self._g.download_rows(self._k, len(RESULT_KEYS), world)
-            self._host = np.concatenate([a[r, :e - b] for r, (b, e) in enumerate(self._sizes)])
+            self._host = self._g.download_rows(self._k, 1, 1)[0]      # one contiguous row: no host-side concatenation
             self._g = None
         return self._host
 
     @property
     def shape(self):
-        return (self._sizes[-1][1],)
+        return (self._m,)
 
     def __len__(self):
-        return self._sizes[-1][1]
+        return self._m
 
     def __array__(self, dtype=None, copy=None):
         a = self.host()
@@ -295,19 +293,31 @@ def scan_sharded(ctx, A, a_err, v, h0_rss, n_p, m_total=None, group=None, eager=
             cnt = cnt.cpu().numpy()
         ends = np.cumsum(cnt)
         sizes = [(int(e - c), int(e)) for c, e in zip(cnt, ends)]
+    m_all = sizes[-1][1]
     maxlen = max(e - b for b, e in sizes)
-    out = DeviceMatrix(ctx, len(RESULT_KEYS), maxlen)
+    nk = len(RESULT_KEYS)
+    out = DeviceMatrix(ctx, nk, maxlen)
     ctx.emmax_scan_quad_dev(A, v, h0_rss, n_p, packed=True, a_err=a_err, out=out)
-    gathered = DeviceMatrix(ctx, world * len(RESULT_KEYS), maxlen, zero=False)
+    gathered = DeviceMatrix(ctx, world * nk, maxlen, zero=False)
+    final = DeviceMatrix(ctx, nk, m_all, zero=False)
     with on_lib_stream(ctx, 'allgather'):
-        dist.all_gather_into_tensor(mat_as_tensor(ctx, gathered), mat_as_tensor(ctx, out), group=group)
+        tg = mat_as_tensor(ctx, gathered)
+        dist.all_gather_into_tensor(tg, mat_as_tensor(ctx, out), group=group)
+        # compact the padded per-rank blocks into [5 x m_total] on the device: the host then receives finished vectors
+        tg = tg.view(world, nk, maxlen)
+        torch.cat([tg[r, :, :e - b] for r, (b, e) in enumerate(sizes)], dim=1, out=mat_as_tensor(ctx, final))
     out.free()
+    gathered.free()
     if eager is None:
         eager = rank == 0
+    if eager:
+        host = final.download(pinned=True)                      # one copy; the five vectors are its rows
+        final.free()
+        return {name: host[k] for k, name in enumerate(RESULT_KEYS)}
     res = {}
     for k, name in enumerate(RESULT_KEYS):
-        g = GatheredRows(gathered, k, sizes)
-        res[name] = g.host() if (eager or name == 'ps') else g
+        g = GatheredRows(final, k, m_all)
+        res[name] = g.host() if name == 'ps' else g
     return res
 
 
