@@ -94,6 +94,10 @@ int mmg_mat_gemm(mmg_ctx* ctx, int trans_a, int trans_b, double alpha, mmg_mat A
                  double beta, mmg_mat C);
 int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat A, const double* d_host);         /* A[i,:] *= d[i] */
 int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat A, double alpha);                   /* A += alpha*I   */
+/* R = (I - QQ') diag(d) U in one pass over U: U [n x n] eigenvectors as rows (eig_L), d [n] = 1/sqrt(lambda + delta)
+ * (H_sqrt_inv = diag(d) U, linear_models.py:898), Q [n x q] orthonormal columns of the rotated fixed effects (:1300); q = 0
+ * gives H_sqrt_inv itself.  R is the transposed M of :1303. */
+int mmg_mat_rotation(mmg_ctx* ctx, mmg_mat U, const double* d_host, const double* Q_host, int q, mmg_mat R_out);
 /* kinship.scale_k (kinship.py:94-100): c = tr(K) - sum(K)/n ; K *= (n-1)/c ; returns the scalar */
 int mmg_mat_scale_k(mmg_ctx* ctx, mmg_mat K, double* scalar);
 /* dst = scale_k(src), src untouched (linear_models.py:580 add_random_effect scales a copy of the caller's K); scalar nullable */

@@ -61,6 +61,7 @@ SIGNATURES = {
     'mmg_mat_gemm': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_double, _i64, _i64, C.c_double, _i64]),
     'mmg_mat_scale_rows': (C.c_int, [_c_ctx, _i64, _vp]),
     'mmg_mat_add_diag': (C.c_int, [_c_ctx, _i64, C.c_double]),
+    'mmg_mat_rotation': (C.c_int, [_c_ctx, _i64, _vp, _vp, C.c_int, _i64]),
     'mmg_mat_scale_k': (C.c_int, [_c_ctx, _i64, _dp]),
     'mmg_mat_scale_k_copy': (C.c_int, [_c_ctx, _i64, _i64, _dp]),
     'mmg_mat_syevd': (C.c_int, [_c_ctx, _i64, _vp, _dp]),
@@ -256,6 +257,36 @@ class LazyHostArray(object):
 
     def __rmatmul__(self, o):
         return np.asarray(o) @ self.host()
+
+
+class LazyScaledRows(LazyHostArray):
+    """H_sqrt_inv = diag(d) U (linear_models.py:898) kept as its two factors: U stays the eigenbasis already in HBM, d is a
+    host vector.  The n x n product is formed only if somebody asks for it (np.asarray(x), x.dev); the scan builds its
+    rotation (I - QQ') diag(d) U straight from the factors in one pass (Context.rotation)."""
+
+    def __init__(self, U, d):
+        self.U = U
+        self.d = np.ascontiguousarray(d, dtype=np.float64)
+        self._rows = None
+        self._host = None
+        self._dev = None
+
+    @property
+    def dev(self):
+        if self._dev is None:
+            self._dev = self.U.ctx.rotation(self.U, self.d)
+        return self._dev
+
+    @property
+    def shape(self):
+        return self.U.shape
+
+    def times(self, B):
+        """diag(d) U B for a host matrix B [n x c] (c small): one skinny GEMM on the device, rows scaled on the host."""
+        Bd = DeviceMatrix.from_host(self.U.ctx, B)
+        t = self.U.ctx.gemm(self.U, Bd).download()
+        Bd.free()
+        return t * self.d[:, None]
 
 
 class Context(object):
@@ -472,6 +503,17 @@ class Context(object):
         d = np.ascontiguousarray(d, dtype=np.float64)
         assert d.shape[0] == A.shape[0]
         self._ck(self.lib.mmg_mat_scale_rows(self.h, A.handle, _ptr(d)))
+
+    def rotation(self, U, d, Q=None):
+        """R = (I - QQ') diag(d) U as a new DeviceMatrix (Q None: diag(d) U), one pass over U (mmg_mat_rotation)."""
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        q = 0
+        if Q is not None:
+            Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(d.shape[0], -1)
+            q = Q.shape[1]
+        R = DeviceMatrix(self, U.shape[0], U.shape[1], zero=False)
+        self._ck(self.lib.mmg_mat_rotation(self.h, U.handle, _ptr(d), _ptr(Q), q, R.handle))
+        return R
 
     def add_diag(self, A, alpha):
         self._ck(self.lib.mmg_mat_add_diag(self.h, A.handle, float(alpha)))

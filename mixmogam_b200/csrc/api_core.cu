@@ -288,6 +288,37 @@ int mmg_mat_scale_rows(mmg_ctx* ctx, mmg_mat h, const double* d_host) {
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMG_OK;
 }
+// R = (I - QQ') diag(d) U in one pass over U (rotation_kernel): U [n x n] eigenvectors as rows, d [n] host (1/sqrt(lambda + delta),
+// linear_models.py:898), Q [n x q] host with orthonormal columns (the QR of the rotated fixed effects, :1300; q = 0: R = diag(d) U,
+// the H_sqrt_inv of :898 itself).  R_out [n x n].
+int mmg_mat_rotation(mmg_ctx* ctx, mmg_mat Uh, const double* d_host, const double* Q_host, int q, mmg_mat Rh) {
+    MmgMat *U = ctx ? get_mat(ctx, Uh) : nullptr, *R = ctx ? get_mat(ctx, Rh) : nullptr;
+    MMG_CHECK(ctx, U && R && U != R && d_host && U->rows == U->cols && R->rows == U->rows && R->cols == U->cols, "mmg_mat_rotation: bad argument");
+    MMG_CHECK(ctx, q >= 0 && q <= 8 && (q == 0 || Q_host), "mmg_mat_rotation: 0..8 projected columns supported");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageTimer tm(ctx, "matrix");
+    const int64_t n = U->rows;
+    DevBuf buf;      // d[n] | Q[n x q] | Qd[n x q] (Q with rows scaled by d) | QtH[q x n]
+    MMG_CUDA(ctx, buf.alloc(ctx->stream, (size_t)(n + 3 * n * std::max(q, 1)) * sizeof(double)));
+    double* d_d = buf.as<double>();
+    double* d_q = d_d + n;
+    double* d_qd = d_q + n * std::max(q, 1);
+    double* d_qth = d_qd + n * std::max(q, 1);
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_d, d_host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (q > 0) {
+        std::vector<double> qd((size_t)(n * q));
+        for (int64_t k = 0; k < n; ++k)
+            for (int c = 0; c < q; ++c) qd[(size_t)(k * q + c)] = Q_host[k * q + c] * d_host[k];
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_q, Q_host, (size_t)(n * q) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_qd, qd.data(), (size_t)(n * q) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // qd goes out of scope
+        const double one = 1.0, zero = 0.0;
+        // QtH = Qd' U  (row-major [q x n] = [n x q]' [n x n]  <=>  column-major QtH' = U' Qd)
+        MMG_CUBLAS(ctx, cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)n, q, (int)n, &one, U->d, (int)n, d_qd, q, &zero, d_qth, (int)n));
+    }
+    rotation_kernel<<<dim3(4, (unsigned)n), 256, 0, ctx->stream>>>(U->d, d_d, q > 0 ? d_q : nullptr, d_qth, q, (int)n, R->d);
+    return launch_check(ctx, "rotation_kernel");
+}
 int mmg_mat_add_diag(mmg_ctx* ctx, mmg_mat h, double alpha) {
     MmgMat* A = ctx ? get_mat(ctx, h) : nullptr;
     MMG_CHECK(ctx, A && A->rows == A->cols, "mmg_mat_add_diag: needs a square matrix");

@@ -384,6 +384,26 @@ static __global__ void scale_rows_kernel(double* __restrict__ A, int64_t ld, int
     const int i = blockIdx.y;
     if (j < cols && i < rows) A[(int64_t)i * ld + j] *= d[i];
 }
+// The rotation of the EMMAX scan in one pass (linear_models.py:898 + :1299-1303): R = (I - QQ') diag(d) U, i.e.
+//     R[k][i] = d[k] U[k][i] - sum_c Q[k][c] QtH[c][i],      QtH = Q' diag(d) U  ([q x n], formed by one skinny GEMM)
+// read U once, write R once -- instead of copy + row scaling (H_sqrt_inv) + copy + rank-q GEMM update.
+static __global__ void __launch_bounds__(256) rotation_kernel(const double* __restrict__ U, const double* __restrict__ d,
+                                                              const double* __restrict__ Q /* [n x q] or null */,
+                                                              const double* __restrict__ QtH /* [q x n] */, int q, int n,
+                                                              double* __restrict__ R) {
+    const int k = blockIdx.y;
+    const double dk = d[k];
+    double qk[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) qk[c] = c < q ? Q[(int64_t)k * q + c] : 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double r = dk * U[(int64_t)k * n + i];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < q) r -= qk[c] * QtH[(int64_t)c * n + i];
+        R[(int64_t)k * n + i] = r;
+    }
+}
 static __global__ void add_diag_kernel(double* __restrict__ A, int64_t ld, int n, double alpha) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) A[(int64_t)i * ld + i] += alpha;

@@ -39,7 +39,7 @@ import numpy as np
 
 from . import _lib
 from . import kinship
-from ._lib import DeviceMatrix, LazyHostArray
+from ._lib import DeviceMatrix, LazyHostArray, LazyScaledRows
 
 __all__ = ['LinearModel', 'LinearMixedModel', 'emmax', 'emmax_multi', 'emma', 'get_emma_reml_estimates']
 
@@ -369,14 +369,11 @@ class LinearMixedModel(LinearModel):
                                'eig_R': eig_R}
         opt_ve = opt_vg * opt_delta
 
-        # H_sqrt_inv = diag(1/sqrt(eig_L.values + delta)) eig_L.vectors   (:898)
+        # H_sqrt_inv = diag(1/sqrt(eig_L.values + delta)) eig_L.vectors   (:898) -- kept as its two factors
         ctx = self.ctx
         UL = ctx.to_device(eig_L['vectors'])
-        H = UL.copy()
-        ctx.scale_rows(H, 1.0 / np.sqrt(np.asarray(eig_L['values'], dtype=np.float64) + opt_delta))
-        XY = DeviceMatrix.from_host(ctx, np.hstack([X, self.Y]))
-        t = ctx.gemm(H, XY).download()
-        XY.free()
+        H = LazyScaledRows(UL, 1.0 / np.sqrt(np.asarray(eig_L['values'], dtype=np.float64) + opt_delta))
+        t = H.times(np.hstack([X, self.Y]))
         X_t, Y_t = t[:, :q], t[:, q:]
         (beta_est, mahalanobis_rss, rank, sigma) = np.linalg.lstsq(X_t, Y_t, rcond=None)
         if np.size(mahalanobis_rss) == 0:
@@ -385,7 +382,7 @@ class LinearMixedModel(LinearModel):
         residuals = self.Y - x_beta
         rss = residuals.T @ residuals
         res_dict = {'max_ll': opt_ll, 'delta': opt_delta, 'beta': beta_est, 've': opt_ve, 'vg': opt_vg,
-                    'rss': rss, 'mahalanobis_rss': mahalanobis_rss, 'H_sqrt_inv': LazyHostArray(H),
+                    'rss': rss, 'mahalanobis_rss': mahalanobis_rss, 'H_sqrt_inv': H,
                     'pseudo_heritability': 1.0 / (1 + opt_delta)}
         if xs is not None and return_f_stat:
             h0_X = X_t[:, :self.X.shape[1]]
@@ -457,18 +454,29 @@ class LinearMixedModel(LinearModel):
 
     def _null_fit(self, H, Z=None, project=True):
         """Set-up of _emmax_f_test_ (linear_models.py:1290-1306): null GLS fit in the rotated space and
-        the rotation R = M' = (I - QQ')H (or H with no projection), resident in HBM."""
+        the rotation R = M' = (I - QQ')H (or H with no projection), resident in HBM.  H: a DeviceMatrix, or the factored
+        LazyScaledRows that get_estimates returns -- then R is formed from the eigenbasis in one pass."""
         ctx = self.ctx
         n = self.n
         q0 = self.X.shape[1]
-        XY = DeviceMatrix.from_host(ctx, np.hstack([self.X, self.Y]))
-        t = ctx.gemm(H, XY).download()
-        XY.free()
+        factored = isinstance(H, LazyScaledRows) and Z is None
+        if factored:
+            t = H.times(np.hstack([self.X, self.Y]))
+        else:
+            if isinstance(H, LazyScaledRows):
+                H = H.dev
+            XY = DeviceMatrix.from_host(ctx, np.hstack([self.X, self.Y]))
+            t = ctx.gemm(H, XY).download()
+            XY.free()
         h0_X, Y = t[:, :q0], t[:, q0:]
         (h0_betas, h0_rss, h0_rank, h0_s) = np.linalg.lstsq(h0_X, Y, rcond=None)
         Yres = Y - h0_X @ h0_betas
         if np.size(h0_rss) == 0:
             h0_rss = np.array([np.sum(Yres ** 2)])
+        if factored:
+            Q = np.linalg.qr(h0_X)[0] if project else None        # :1300
+            Rm = ctx.rotation(H.U, H.d, Q)                        # :1303 (transposed) / :1306
+            return {'h0_X': h0_X, 'h0_betas': h0_betas, 'h0_rss': h0_rss, 'Yres': Yres, 'R': Rm, 'owned': True}
         Hz = H
         if Z is not None:
             Zd = DeviceMatrix.from_host(ctx, np.asarray(Z, dtype=np.float64))
@@ -484,7 +492,7 @@ class LinearMixedModel(LinearModel):
             QtH.free()
         else:
             Rm = Hz                                           # :1306  M = H'
-        return {'h0_X': h0_X, 'h0_betas': h0_betas, 'h0_rss': h0_rss, 'Yres': Yres, 'R': Rm}
+        return {'h0_X': h0_X, 'h0_betas': h0_betas, 'h0_rss': h0_rss, 'Yres': Yres, 'R': Rm, 'owned': Rm is not H}
 
     def _emmax_f_test_(self, snps, H_sqrt_inv, snp_priors=None, verbose=True, return_transformed_snps=False,
                        Z=None, with_betas=False, emma_num=100, eig_L=None, **kwargs):
@@ -499,7 +507,7 @@ class LinearMixedModel(LinearModel):
         n = self.n
         n_p = n - p
         num_snps, n_lines = ctx.ensure_snps(snps)
-        H = ctx.to_device(H_sqrt_inv)
+        H = H_sqrt_inv if isinstance(H_sqrt_inv, LazyScaledRows) else ctx.to_device(H_sqrt_inv)
         nf = self._null_fit(H, Z=Z, project=not with_betas)
         h0_rss = nf['h0_rss']
         h0_rss_f = float(np.asarray(h0_rss).reshape(-1)[0])
@@ -577,7 +585,7 @@ class LinearMixedModel(LinearModel):
             pos = bfs * snp_priors / (1 - snp_priors)
             res_d['pos'] = pos
             res_d['ppas'] = pos / (1 + pos)
-        if Rm is not H:
+        if nf['owned']:
             Rm.free()
 
         if emma_num > 0:                                                                            # :1365-1377
@@ -760,12 +768,10 @@ def emmax_multi(snps, phenotypes, K, cofactors=None, ngrids=50, llim=-10, ulim=1
         Rs, V, h0, meta = [], [], [], []
         for t in ts:
             delta = float(r['delta'][t])
-            H = UL.copy()
-            ctx.scale_rows(H, 1.0 / np.sqrt(eigL_vals + delta))               # :898
+            H = LazyScaledRows(UL, 1.0 / np.sqrt(eigL_vals + delta))          # :898
             mt = LinearMixedModel(Y[t], ctx=ctx)
             mt.X = X
             nf = mt._null_fit(H, project=True)                                # :1290-1303
-            H.free()
             Rs.append(nf['R'])
             V.append(nf['Yres'].reshape(-1))
             h0.append(float(np.asarray(nf['h0_rss']).reshape(-1)[0]))
