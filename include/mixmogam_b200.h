@@ -220,6 +220,10 @@ int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat A, const double* v, double h0_
  * n x n lower triangle), a_err = the error bound of A's entries (enters the certified bound; 0 for an FP64 A), v = R'y~ as an
  * mmg_mat of n values, and out = [5 x >= snp_count] rows ps, f_stats, rss, var_perc, xx (left on the device for the all-gather
  * of the per-rank slices). */
+/* Launch the scan's linear pre-pass (v = R'y~, diag(R'R), then x.v, sum_j A_jj x_j^2, ||x||_1 per SNP) over resident rows
+ * [snp_begin, +snp_count) on the library's side stream, underneath the tensor-core work queued next; the following
+ * mmg_emmax_scan_quad_dev over the same rows joins it (and may pass v = 0). */
+int mmg_scan_prepass_begin(mmg_ctx* ctx, mmg_mat R, const double* yres, int64_t snp_begin, int64_t snp_count);
 int64_t mmg_quad_form_slots(int64_t n);
 int mmg_quad_form_tiles(mmg_ctx* ctx, mmg_mat R, int64_t slot_begin, int64_t slot_count, mmg_mat A, double* err_abs);
 int mmg_emmax_scan_quad_dev(mmg_ctx* ctx, mmg_mat A, int packed, double a_err, mmg_mat v, double h0_rss, double n_p,

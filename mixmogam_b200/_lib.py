@@ -88,6 +88,7 @@ SIGNATURES = {
     'mmg_emmax_scan_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _i64, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_quad_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_double, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_scan_prepass_begin': (C.c_int, [_c_ctx, _i64, _vp, _i64, _i64]),
     'mmg_quad_form_slots': (_i64, [_i64]),
     'mmg_quad_form_tiles': (C.c_int, [_c_ctx, _i64, _i64, _i64, _i64, _dp]),
     'mmg_emmax_scan_quad_dev': (C.c_int, [_c_ctx, _i64, C.c_int, C.c_double, _i64, C.c_double, C.c_double, _i64, _i64, _i64]),
@@ -282,11 +283,17 @@ class LazyScaledRows(LazyHostArray):
         return self.U.shape
 
     def times(self, B):
-        """diag(d) U B for a host matrix B [n x c] (c small): one skinny GEMM on the device, rows scaled on the host."""
+        """diag(d) U B for a host matrix B [n x c] (c small): one skinny GEMM on the device, rows scaled on the host.  The
+        last product is remembered: get_estimates and the scan set-up both ask for H [X, Y] (linear_models.py:899-900, :1290)."""
+        B = np.ascontiguousarray(B, dtype=np.float64)
+        last = getattr(self, '_last_times', None)
+        if last is not None and last[0].shape == B.shape and np.array_equal(last[0], B):
+            return last[1].copy()
         Bd = DeviceMatrix.from_host(self.U.ctx, B)
-        t = self.U.ctx.gemm(self.U, Bd).download()
+        t = self.U.ctx.gemm(self.U, Bd).download() * self.d[:, None]
         Bd.free()
-        return t * self.d[:, None]
+        self._last_times = (B.copy(), t)
+        return t.copy()
 
 
 class Context(object):
@@ -487,6 +494,15 @@ class Context(object):
             C_out = DeviceMatrix(self, m, n)
         self._ck(self.lib.mmg_mat_gemm(self.h, int(ta), int(tb), alpha, A.handle, B.handle, beta, C_out.handle))
         return C_out
+
+    def scan_prepass_begin(self, R, yres, snp_begin=0, snp_count=None):
+        """Starts the scan's linear pre-pass for these resident rows on the side stream (mmg_scan_prepass_begin)."""
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        yres = np.ascontiguousarray(np.asarray(yres, dtype=np.float64).reshape(-1))
+        assert yres.shape[0] == R.shape[0]
+        self._ck(self.lib.mmg_scan_prepass_begin(self.h, R.handle, _ptr(yres), int(snp_begin), int(snp_count)))
 
     def quad_form_slots(self, n):
         """Number of 256 x 256 blocks in the packed lower triangle of an n x n quadratic form (mmg_quad_form_slots)."""
@@ -692,7 +708,7 @@ class Context(object):
             snp_count = m - snp_begin
         if out is None:
             out = DeviceMatrix(self, 5, snp_count)
-        self._ck(self.lib.mmg_emmax_scan_quad_dev(self.h, A.handle, int(bool(packed)), float(a_err), v.handle, float(h0_rss), float(n_p),
+        self._ck(self.lib.mmg_emmax_scan_quad_dev(self.h, A.handle, int(bool(packed)), float(a_err), v.handle if v is not None else 0, float(h0_rss), float(n_p),
                                                   int(snp_begin), int(snp_count), out.handle))
         return out
 

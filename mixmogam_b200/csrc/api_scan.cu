@@ -495,8 +495,11 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     unsigned* d_wave = (unsigned*)(d_rho + 1);
     MMG_CUDA(ctx, cudaMemsetAsync(vec.p, 0, (size_t)nd * sizeof(double), ctx->stream));
     MMG_CUDA(ctx, cudaMemsetAsync(Bq.p, 0, (size_t)T * S_alloc * plane, ctx->stream));
-    if (A_given) MMG_CUDA(ctx, cudaMemcpyAsync(d_v, v_given, (size_t)n * sizeof(double), v_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-    else MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (A_given) {
+        if (v_given) MMG_CUDA(ctx, cudaMemcpyAsync(d_v, v_given, (size_t)n * sizeof(double), v_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        MMG_CUDA(ctx, cudaMemcpyAsync(d_y, V, (size_t)T * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
     MMG_CUDA(ctx, cudaMemcpyAsync(d_h0, h0_rss, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<double> escale((size_t)T), bscale((size_t)T), errA((size_t)T, 0.0);
     // linear pre-pass: x.v_t, sum_j A_jj x_j^2 and ||x||_1 of every SNP in range, one stream over the genotypes.  When the rotation
@@ -514,6 +517,13 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         cudaStream_t s = nullptr;
         ~SideJoin() { if (s) cudaStreamSynchronize(s); }
     } side_join;
+    const bool early = A_given && T == 1 && ctx->early_prepass && ctx->early_begin == snp_begin && ctx->early_count == snp_count;
+    ctx->early_prepass = false;
+    if (early) {
+        // mmg_scan_prepass_begin launched the pre-pass of exactly these rows on the side stream, underneath whatever ran since
+        // (the block-wise R'R product and its all-gather in the multi-GPU path): join it, the outputs are in `pre`
+        MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ov1, 0));
+    }
     if (!A_given && env_int("MMG_SCAN_OVERLAP", 1)) {
         if (!ctx->stream2) {
             MMG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
@@ -561,7 +571,10 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
     if (pre_launched) {
         MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ov1, 0));        // join the side stream
         side_join.s = nullptr;
+    } else if (early) {
+        // joined above
     } else {
+        MMG_CHECK(ctx, !A_given || v_given, "scan: v = R'y is needed (no pre-pass was launched ahead for these rows)");
         snp_prepass_kernel<PRE_ROWS, 4, 4><<<pre_grid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin, snp_count, T, d_v, d_dg, n_padN, p_xy, p_qd,
                                                                            p_a1, snp_count);
         MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
@@ -899,6 +912,57 @@ int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat Ah, const double* v, double h0
     return MMG_OK;
 }
 
+// Launches the linear pre-pass of the int8 scan over resident rows [snp_begin, +snp_count) on the SIDE stream: v = R'y~
+// (x~.y~ = x.v), diag(R'R) = column sums of squares of R, then x.v, sum_j A_jj x_j^2 and ||x||_1 per SNP (snp_prepass_kernel) --
+// HBM / FP64 work that runs underneath the tensor-core work the caller queues next on the main stream (mmg_quad_form_tiles and
+// the all-gather of the multi-GPU path).  The following mmg_emmax_scan_quad_dev over the same rows joins it and may then be
+// called with v = 0.
+int mmg_scan_prepass_begin(mmg_ctx* ctx, mmg_mat Rh, const double* yres, int64_t snp_begin, int64_t snp_count) {
+    MmgMat* R = ctx ? get_mat(ctx, Rh) : nullptr;
+    MMG_CHECK(ctx, R && yres && ctx->snps, "mmg_scan_prepass_begin: need resident genotypes, R and the residual phenotype");
+    MMG_CHECK(ctx, R->cols == ctx->n, "R must have n = %lld columns (has %lld)", (long long)ctx->n, (long long)R->cols);
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n, n_out = R->rows, n_padN = round_up(n, TC_BN);
+    ctx->early_prepass = false;
+    if (!ctx->stream2) {
+        MMG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov0, cudaEventDisableTiming));
+        MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov1, cudaEventDisableTiming));
+    }
+    WsBuf pre, in;
+    MMG_TRY(ws_get(ctx, MMG_WS_SCAN_PRE, (3 * snp_count + n_padN) * (int64_t)sizeof(double), &pre.p));       // the layout scan_tc_run expects (T = 1)
+    MMG_TRY(ws_get(ctx, MMG_WS_SCAN_EARLY, (2 * n_padN + n_out) * (int64_t)sizeof(double), &in.p));
+    double* d_dg = pre.as<double>();
+    double* p_xy = d_dg + n_padN;
+    double* p_qd = p_xy + snp_count;
+    double* p_a1 = p_qd + snp_count;
+    double* d_v = in.as<double>();
+    double* d_y = d_v + 2 * n_padN;
+    // the main stream's work so far (R) must be complete; everything below runs on the side stream
+    MMG_CUDA(ctx, cudaEventRecord(ctx->ov0, ctx->stream));
+    MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ov0, 0));
+    MMG_CUDA(ctx, cudaMemsetAsync(d_v, 0, (size_t)(2 * n_padN) * sizeof(double), ctx->stream2));
+    MMG_CUDA(ctx, cudaMemsetAsync(d_dg, 0, (size_t)n_padN * sizeof(double), ctx->stream2));
+    MMG_CUDA(ctx, cudaMemcpyAsync(d_y, yres, (size_t)n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream2));
+    const double one = 1.0, zero = 0.0;
+    cublasSetStream(ctx->cublas, ctx->stream2);
+    const cublasStatus_t st = cublasDgemv(ctx->cublas, CUBLAS_OP_N, (int)n, (int)n_out, &one, R->d, (int)n, d_y, 1, &zero, d_v, 1);
+    cublasSetStream(ctx->cublas, ctx->stream);
+    if (st != CUBLAS_STATUS_SUCCESS) return fail(ctx, MMG_ECUBLAS, "mmg_scan_prepass_begin: cublasDgemv status %d", (int)st);
+    col_sumsq_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream2>>>(R->d, n, (int)n_out, (int)n, d_dg);
+    MMG_TRY(launch_check(ctx, "col_sumsq_kernel"));
+    const unsigned grid = (unsigned)((snp_count + 8 * PRE_ROWS - 1) / (8 * PRE_ROWS));
+    snp_prepass_kernel<PRE_ROWS, 4, 4><<<grid, 256, 0, ctx->stream2>>>(ctx->snps, ctx->pitch, snp_begin, snp_count, 1, d_v, d_dg, n_padN, p_xy, p_qd, p_a1,
+                                                                    snp_count);
+    MMG_TRY(launch_check(ctx, "snp_prepass_kernel"));
+    MMG_CUDA(ctx, cudaEventRecord(ctx->ov1, ctx->stream2));
+    ctx->early_prepass = true;
+    ctx->early_begin = snp_begin;
+    ctx->early_count = snp_count;
+    return MMG_OK;
+}
+
 int64_t mmg_quad_form_slots(int64_t n) { return n > 0 ? qa_slots(n) : 0; }
 
 int mmg_quad_form_tiles(mmg_ctx* ctx, mmg_mat Rh, int64_t slot_begin, int64_t slot_count, mmg_mat Ah, double* err_abs) {
@@ -921,13 +985,15 @@ int mmg_quad_form_tiles(mmg_ctx* ctx, mmg_mat Rh, int64_t slot_begin, int64_t sl
 int mmg_emmax_scan_quad_dev(mmg_ctx* ctx, mmg_mat Ah, int packed, double a_err, mmg_mat vh, double h0_rss, double n_p, int64_t snp_begin,
                             int64_t snp_count, mmg_mat outh) {
     MmgMat* A = ctx ? get_mat(ctx, Ah) : nullptr;
-    MmgMat* v = ctx ? get_mat(ctx, vh) : nullptr;
+    MmgMat* v = (ctx && vh) ? get_mat(ctx, vh) : nullptr;
     MmgMat* out = ctx ? get_mat(ctx, outh) : nullptr;
-    MMG_CHECK(ctx, A && v && out && ctx->snps, "mmg_emmax_scan_quad_dev: need resident genotypes, A, v and the output matrix");
+    MMG_CHECK(ctx, A && out && ctx->snps, "mmg_emmax_scan_quad_dev: need resident genotypes, A and the output matrix");
+    MMG_CHECK(ctx, v || (ctx->early_prepass && ctx->early_begin == snp_begin && ctx->early_count == snp_count),
+              "mmg_emmax_scan_quad_dev: v = R'y is needed unless mmg_scan_prepass_begin ran for these rows");
     const int64_t n = ctx->n;
     if (packed) MMG_CHECK(ctx, A->cols == QA_TILE_ELEMS && A->rows >= qa_slots(n), "packed A must be [>= %lld x 65536]", (long long)qa_slots(n));
     else MMG_CHECK(ctx, A->rows == n && A->cols == n, "dense A must be n x n with n = %lld", (long long)n);
-    MMG_CHECK(ctx, v->rows * v->cols == n, "v must hold n = %lld values", (long long)n);
+    MMG_CHECK(ctx, !v || v->rows * v->cols == n, "v must hold n = %lld values", (long long)n);
     MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
     MMG_CHECK(ctx, out->rows == 5 && out->cols >= snp_count, "out must be [5 x >= snp_count]");
     MMG_CHECK(ctx, a_err >= 0.0, "a_err must be non-negative");
@@ -937,7 +1003,7 @@ int mmg_emmax_scan_quad_dev(mmg_ctx* ctx, mmg_mat Ah, int packed, double a_err, 
     qa.ld = A->cols;
     qa.packed = packed != 0;
     qa.err = a_err;
-    return scan_quad_given(ctx, qa, v->d, true, h0_rss, n_p, snp_begin, snp_count, out->d, out->cols);
+    return scan_quad_given(ctx, qa, v ? v->d : nullptr, true, h0_rss, n_p, snp_begin, snp_count, out->d, out->cols);
 }
 
 // Phenotype-batched scan (BASELINE.json configs[2]; the reference runs one emmax() per phenotype): T rotations R_t

@@ -85,10 +85,14 @@ struct mmg_ctx {
     // persistent workspaces of the scan (grow-only, one per role): the few buffers of hundreds of MB a scan needs every call are
     // kept instead of going through the stream-ordered pool each time -- the pool's occasional growth (cuMemCreate + map) showed
     // up as milliseconds of host time on some ranks of a multi-GPU step, which every other rank then waits for in the next collective
+    // linear pre-pass of the scan launched ahead on the side stream (mmg_scan_prepass_begin): its outputs wait in the
+    // MMG_WS_SCAN_PRE workspace for the scan over exactly this row range
+    bool early_prepass = false;
+    int64_t early_begin = 0, early_count = 0;
     void* ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t ws_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
-enum { MMG_WS_OZAKI_PLANES = 0, MMG_WS_QUAD_A = 1, MMG_WS_QUAD_BQ = 2, MMG_WS_SCAN_PRE = 3, MMG_WS_SCAN_VEC = 4, MMG_WS_SCAN_OUT = 5 };
+enum { MMG_WS_OZAKI_PLANES = 0, MMG_WS_QUAD_A = 1, MMG_WS_QUAD_BQ = 2, MMG_WS_SCAN_PRE = 3, MMG_WS_SCAN_VEC = 4, MMG_WS_SCAN_OUT = 5, MMG_WS_SCAN_EARLY = 6 };
 
 namespace mmg {
 

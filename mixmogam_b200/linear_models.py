@@ -531,12 +531,10 @@ class LinearMixedModel(LinearModel):
                         raise ValueError('the sharded scan returns the per-SNP statistics only (emma_num=0, no t_snps / priors): '
                                          'refine the top hits on one rank with expedited_REML_t_test')
                     parallel.check_same_model(ctx, [h0_rss_f, float(n), float(np.sum(np.abs(nf['Yres']))), float(Rm.shape[0])], group)
+                    ctx.scan_prepass_begin(Rm, nf['Yres'])         # v = R'y~ and the linear terms: side stream, under the next two
                     A, a_err = parallel.quad_form_sharded(ctx, Rm, group)
-                    yd = DeviceMatrix.from_host(ctx, nf['Yres'].reshape(-1, 1))
-                    vd = ctx.gemm(Rm, yd, ta=True)                 # v = R' y~   (x~.y~ = x.v)
-                    out = parallel.scan_sharded(ctx, A, a_err, vd, h0_rss_f, n_p, m_total=m_total, group=group)
-                    for d in (A, yd, vd):
-                        d.free()
+                    out = parallel.scan_sharded(ctx, A, a_err, None, h0_rss_f, n_p, m_total=m_total, group=group)
+                    A.free()
                     num_snps = len(out['ps'])
                 else:
                     out = ctx.emmax_scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)

@@ -362,6 +362,12 @@ def test_quad_form_tiles_and_scan_quad(ctx):
     ra = ctx.emmax_scan(Rd, y.reshape(1, -1), h0, n - 2, impl='tcgen05')
     vd = DeviceMatrix.from_host(ctx, (R.T @ y).reshape(-1, 1))
     out = ctx.emmax_scan_quad_dev(Ap, vd, h0, n - 2, packed=True, a_err=errs[0]).download()
+    # the pre-pass launched ahead on the side stream (what the multi-GPU path does underneath the block products): same numbers
+    ctx.scan_prepass_begin(Rd, y)
+    out2 = ctx.emmax_scan_quad_dev(Ap, None, h0, n - 2, packed=True, a_err=errs[0]).download()
+    np.testing.assert_allclose(out2, out, rtol=1e-11, atol=1e-300)
+    with pytest.raises(Exception):
+        ctx.emmax_scan_quad_dev(Ap, None, h0, n - 2, packed=True, a_err=errs[0])       # consumed: v is needed again
     Ad = DeviceMatrix.from_host(ctx, np.tril(ref))
     rb = ctx.emmax_scan_quad(Ad, R.T @ y, h0, n - 2)
     for i, k in enumerate(parallel.RESULT_KEYS):
