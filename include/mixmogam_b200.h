@@ -206,6 +206,14 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double 
                        int impl, int64_t snp_begin, int64_t snp_count,
                        double* ps, double* f_stats, double* rss, double* var_perc,
                        double* xx, double* dots);
+/* mmg_emmax_scan_f64 for REAL-VALUED genotype rows (imputed dosages; the reference's scan accepts any numeric row, it casts the
+ * chunk to float32 at linear_models.py:1317): xs = [m x ld] host FP64, SNP-major, ld >= n.  FP64 tensor-core path with the
+ * genotype operand staged as FP64; the rows pass through the device in chunks and do not become the resident block.
+ * Same outputs as mmg_emmax_scan_f64 (any may be NULL). */
+int mmg_emmax_scan_rows_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double h0_rss, double n_p,
+                            const double* xs, int64_t m, int64_t ld,
+                            double* ps, double* f_stats, double* rss, double* var_perc,
+                            double* xx, double* dots);
 /* The int8 tensor-core form of mmg_emmax_scan_f64 for a caller that already holds A = R'R (n x n, row-major lower
  * triangle valid) and v = R'y~ [n].  Same outputs. */
 int mmg_emmax_scan_quad_f64(mmg_ctx* ctx, mmg_mat A, const double* v, double h0_rss, double n_p,

@@ -871,6 +871,104 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
     return MMG_OK;
 }
 
+// Real-valued genotype rows (imputed dosages; the reference's scan takes any numeric row, linear_models.py:1317): the FP64
+// tensor-core scan with the A operand staged as FP64.  The rows are not made resident: host chunks of <= 16384 rows go through
+// one device buffer.
+int mmg_emmax_scan_rows_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double h0_rss, double n_p, const double* xs, int64_t m,
+                            int64_t ld, double* ps, double* f_stats, double* rss, double* var_perc, double* xx, double* dots) {
+    MmgMat* R = ctx ? get_mat(ctx, Rh) : nullptr;
+    MMG_CHECK(ctx, R && xs && m > 0, "mmg_emmax_scan_rows_f64: need R and the genotype rows");
+    MMG_CHECK(ctx, ld >= R->cols, "row stride %lld shorter than n = %lld", (long long)ld, (long long)R->cols);
+    MMG_CHECK(ctx, V && nv >= 1 && nv <= 16, "need 1..16 rotated-space vectors (V[0] = residual phenotype)");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = R->cols, n_out = R->rows;
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+    const int64_t chunk = std::min<int64_t>(m, 16384);
+    const int64_t pitch = round_up(n, SD_BK);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMG_CUDA(ctx, cudaFuncSetAttribute(scan_dmma_kernel<false, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sd_smem_bytes<double>()));
+        attr_set = true;
+    }
+    StageTimer tm(ctx, "scan");
+    DevBuf Rp, Vp, Xd, out, Vd, Wd;
+    int64_t rows_pad = 0, ldr = 0;
+    MMG_TRY(pad_matrix(ctx, R, Rp, &rows_pad, &ldr));
+    MMG_CUDA(ctx, Vp.alloc(ctx->stream, (size_t)rows_pad * sizeof(double)));
+    MMG_CUDA(ctx, cudaMemsetAsync(Vp.p, 0, (size_t)rows_pad * sizeof(double), ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(Vp.p, V, n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MMG_CUDA(ctx, Xd.alloc(ctx->stream, (size_t)chunk * pitch * sizeof(double)));
+    MMG_CUDA(ctx, cudaMemsetAsync(Xd.p, 0, (size_t)chunk * pitch * sizeof(double), ctx->stream));
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)(6 + nv) * chunk * sizeof(double)));
+    double* d_xx = out.as<double>();
+    double* d_xy = d_xx + chunk;
+    double* d_rss = d_xy + chunk;
+    double* d_f = d_rss + chunk;
+    double* d_p = d_f + chunk;
+    double* d_vp = d_p + chunk;
+    double* d_dots = d_vp + chunk;
+    if (dots) {
+        // x~.V[v] = x.(R' V[v]):  W = V R
+        MMG_CUDA(ctx, Vd.alloc(ctx->stream, (size_t)nv * n_out * sizeof(double)));
+        MMG_CUDA(ctx, Wd.alloc(ctx->stream, (size_t)nv * n * sizeof(double)));
+        MMG_CUDA(ctx, cudaMemcpyAsync(Vd.p, V, (size_t)nv * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        const double one = 1.0, zero = 0.0;
+        MMG_CUBLAS(ctx, cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, nv, (int)n_out, &one, R->d, (int)R->cols,
+                                    Vd.as<double>(), (int)n_out, &zero, Wd.as<double>(), (int)n));
+    }
+    std::vector<double> tmp;
+    double total_ms = 0.0;
+    for (int64_t r0 = 0; r0 < m; r0 += chunk) {
+        const int64_t rows = std::min<int64_t>(chunk, m - r0);
+        MMG_CUDA(ctx, cudaMemcpy2DAsync(Xd.p, pitch * sizeof(double), xs + r0 * ld, ld * sizeof(double), n * sizeof(double), rows,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+        ScanDmmaParams prm{};
+        prm.snps = Xd.p;
+        prm.pitch = pitch;
+        prm.row_begin = 0;
+        prm.row_count = rows;
+        prm.R = Rp.as<double>();
+        prm.ldr = ldr;
+        prm.n_out_pad = (int)rows_pad;
+        prm.k_pad = (int)pitch;
+        prm.y = Vp.as<double>();
+        prm.h0_rss = h0_rss;
+        prm.n_p = n_p;
+        prm.lbeta = lbeta;
+        prm.xx = d_xx; prm.xy = d_xy; prm.rss = d_rss; prm.f = d_f; prm.p = d_p; prm.var_perc = d_vp;
+        const int grid = (int)std::min<int64_t>((rows + SD_BM - 1) / SD_BM, ctx->sm_count);
+        cudaEventRecord(ctx->kev0, ctx->stream);
+        scan_dmma_kernel<false, double><<<grid, SD_THREADS, sd_smem_bytes<double>(), ctx->stream>>>(prm);
+        MMG_TRY(launch_check(ctx, "scan_dmma_kernel<double>"));
+        cudaEventRecord(ctx->kev1, ctx->stream);
+        if (dots)
+            for (int v = 0; v < nv; ++v) {
+                row_dots_f64_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(Xd.as<double>(), pitch, rows, (int)n,
+                                                                                         Wd.as<double>() + (int64_t)v * n, d_dots + (int64_t)v * chunk);
+                MMG_TRY(launch_check(ctx, "row_dots_f64_kernel"));
+            }
+        const size_t bytes = rows * sizeof(double);
+        if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps + r0, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (f_stats) MMG_CUDA(ctx, cudaMemcpyAsync(f_stats + r0, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (rss) MMG_CUDA(ctx, cudaMemcpyAsync(rss + r0, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (var_perc) MMG_CUDA(ctx, cudaMemcpyAsync(var_perc + r0, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (xx) MMG_CUDA(ctx, cudaMemcpyAsync(xx + r0, d_xx, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dots) {
+            tmp.resize((size_t)nv * chunk);
+            MMG_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_dots, (size_t)nv * chunk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (dots)
+            for (int v = 0; v < nv; ++v)
+                for (int64_t s = 0; s < rows; ++s) dots[(r0 + s) * nv + v] = tmp[(size_t)v * chunk + s];
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+        total_ms += ms;
+    }
+    ctx->last_scan_ms = total_ms;
+    return MMG_OK;
+}
+
 // The int8 scan when the caller already holds the quadratic form A = R'R and v = R'y~: the multi-GPU path forms A once across
 // the ranks (mmg_quad_form_tiles + all-gather) instead of repeating the 2 n^3 / 2 flops of the product on every rank (12.5 ms at
 // n = 10k, as long as an 8-way shard of the scan itself).  Device outputs; the two ABI entries below differ in where v comes from

@@ -26,9 +26,23 @@ constexpr int SD_A_STAGE = SD_BM * SD_A_PITCH;       // 6144 B
 constexpr int SD_B_STAGE = SD_BN * SD_B_PITCH * 8;   // 36864 B
 constexpr int SD_STAGE_BYTES = SD_A_STAGE + SD_B_STAGE;
 constexpr int SD_SMEM_BYTES = SD_STAGES * SD_STAGE_BYTES + 2 * 4 * SD_BM * 8;   // + reduction scratch
+// real-valued genotype rows (dosages, linear_models.py:1317 takes any numeric row): the A operand is staged as FP64 with the
+// pitch of B, three stages instead of four (3 x 72 KB + scratch = 224 KB)
+constexpr int SD_AD_PITCH = 36;                      // doubles per A row
+constexpr int SD_AD_STAGE = SD_BM * SD_AD_PITCH * 8; // 36864 B
+
+template <typename XT> struct SdShape;
+template <> struct SdShape<int8_t> {
+    static constexpr int STAGES = SD_STAGES, A_STAGE = SD_A_STAGE;
+};
+template <> struct SdShape<double> {
+    static constexpr int STAGES = 3, A_STAGE = SD_AD_STAGE;
+};
+template <typename XT> constexpr int sd_stage_bytes() { return SdShape<XT>::A_STAGE + SD_B_STAGE; }
+template <typename XT> constexpr int sd_smem_bytes() { return SdShape<XT>::STAGES * sd_stage_bytes<XT>() + 2 * 4 * SD_BM * 8; }
 
 struct ScanDmmaParams {
-    const int8_t* snps;      // resident genotypes, row pitch `pitch` bytes, zero padded to a multiple of 128
+    const void* snps;        // genotypes: int8 (resident block) or FP64 rows; row pitch `pitch` ELEMENTS, zero padded to k_pad
     int64_t pitch;
     int64_t row_begin;       // first SNP row of this call
     int64_t row_count;
@@ -52,10 +66,13 @@ __device__ __forceinline__ double i8_to_f64(int v) {
     return __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)v)) - 4503601774854144.0;
 }
 
-template <bool PERM>
+template <bool PERM, typename XT = int8_t>
 static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const ScanDmmaParams prm) {
+    constexpr bool REAL = sizeof(XT) == 8;
+    constexpr int SD_STAGES = SdShape<XT>::STAGES, SD_A_STAGE = SdShape<XT>::A_STAGE, SD_STAGE_BYTES = SdShape<XT>::A_STAGE + SD_B_STAGE;
     extern __shared__ __align__(16) uint8_t sd_smem[];
     double* red = reinterpret_cast<double*>(sd_smem + SD_STAGES * SD_STAGE_BYTES);   // [2][4][128]
+    const XT* snps = static_cast<const XT*>(prm.snps);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;           // 2 x 4 warps, warp tile 64 x 32
@@ -73,12 +90,22 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
             const int nt = it / KT, kt = it - nt * KT;
             uint8_t* sa = sd_smem + stage * SD_STAGE_BYTES;
             double* sb = reinterpret_cast<double*>(sa + SD_A_STAGE);
-            {   // A: 128 rows x 32 B -> one 16 B chunk per thread
+            if constexpr (!REAL) {   // A: 128 rows x 32 B -> one 16 B chunk per thread
                 const int r = tid >> 1, h = tid & 1;
                 const bool valid = (row0 + r) < prm.row_count;
                 const int64_t grow = prm.row_begin + (valid ? row0 + r : 0);
-                cp_async16_zfill(sa + r * SD_A_PITCH + 16 * h, prm.snps + grow * prm.pitch + (int64_t)kt * SD_BK + 16 * h,
+                cp_async16_zfill(sa + r * SD_A_PITCH + 16 * h, snps + grow * prm.pitch + (int64_t)kt * SD_BK + 16 * h,
                                  valid);
+            } else {
+                double* sad = reinterpret_cast<double*>(sa);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {   // A: 128 rows x 256 B -> eight 16 B chunks per thread
+                    const int c = tid + SD_THREADS * j;
+                    const int r = c >> 4, part = c & 15;
+                    const bool valid = (row0 + r) < prm.row_count;
+                    const int64_t grow = prm.row_begin + (valid ? row0 + r : 0);
+                    cp_async16_zfill(sad + r * SD_AD_PITCH + 2 * part, snps + grow * prm.pitch + (int64_t)kt * SD_BK + 2 * part, valid);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {   // B: 128 rows x 256 B -> eight 16 B chunks per thread
@@ -122,13 +149,15 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
             const double* sb = reinterpret_cast<const double*>(sa + SD_A_STAGE);
 
             // A fragments for the whole stage: row's 32 bytes -> byte (lane&3) of each word
-            uint32_t aw[8][8];
+            uint32_t aw[REAL ? 1 : 8][8];
+            if constexpr (!REAL) {
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi) {
-                const uint4* ap = reinterpret_cast<const uint4*>(sa + (wm * 64 + mi * 8 + lr) * SD_A_PITCH);
-                const uint4 lo = ap[0], hi = ap[1];
-                aw[mi][0] = lo.x; aw[mi][1] = lo.y; aw[mi][2] = lo.z; aw[mi][3] = lo.w;
-                aw[mi][4] = hi.x; aw[mi][5] = hi.y; aw[mi][6] = hi.z; aw[mi][7] = hi.w;
+                for (int mi = 0; mi < 8; ++mi) {
+                    const uint4* ap = reinterpret_cast<const uint4*>(sa + (wm * 64 + mi * 8 + lr) * SD_A_PITCH);
+                    const uint4 lo = ap[0], hi = ap[1];
+                    aw[mi][0] = lo.x; aw[mi][1] = lo.y; aw[mi][2] = lo.z; aw[mi][3] = lo.w;
+                    aw[mi][4] = hi.x; aw[mi][5] = hi.y; aw[mi][6] = hi.z; aw[mi][7] = hi.w;
+                }
             }
 #pragma unroll
             for (int kk = 0; kk < SD_BK / 4; ++kk) {
@@ -137,8 +166,13 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
                 for (int ni = 0; ni < 4; ++ni) b[ni] = sb[(wn * 32 + ni * 8 + lr) * SD_B_PITCH + kk * 4 + lc];
 #pragma unroll
                 for (int mi = 0; mi < 8; ++mi) {
-                    const int v = (int)(int8_t)((aw[mi][kk] >> (8 * lc)) & 0xffu);
-                    const double a = i8_to_f64(v);
+                    double a;
+                    if constexpr (REAL) {
+                        a = reinterpret_cast<const double*>(sa)[(wm * 64 + mi * 8 + lr) * SD_AD_PITCH + kk * 4 + lc];
+                    } else {
+                        const int v = (int)(int8_t)((aw[mi][kk] >> (8 * lc)) & 0xffu);
+                        a = i8_to_f64(v);
+                    }
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a, b[ni]);
                 }
@@ -244,6 +278,20 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
 
 // x . W[:, v] for a few FP64 vectors (with_betas columns, means): one warp per SNP row, HBM-bound on X.
 // W is [nv x ldw] (vector v contiguous).  dots is [row_count x nv].
+// FP64 rows: x . W[:, v], one warp per row (coalesced 8-byte loads)
+static __global__ void __launch_bounds__(256) row_dots_f64_kernel(const double* __restrict__ xs, int64_t pitch, int64_t row_count, int n,
+                                                                  const double* __restrict__ w, double* __restrict__ dots) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= row_count) return;
+    const double* x = xs + row * pitch;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s = fma(x[i], w[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dots[row] = s;
+}
+
 template <int NV>
 static __global__ void __launch_bounds__(256) snp_dots_kernel(const int8_t* __restrict__ snps, int64_t pitch, int64_t row_begin,
                                                        int64_t row_count, int n, const double* __restrict__ W,
