@@ -139,6 +139,13 @@ int mmg_kinship_gram_i8_host(mmg_ctx* ctx, int coding, int impl, const int8_t* s
  * mmg_kinship_gram_i8_host sends part of the chunks this way (a quarter of the PCIe bytes) while the DMA engine moves the
  * others unpacked; MMG_H2D_PACK=0 switches the packed lane off, MMG_HOST_THREADS sets the thread count. */
 int mmg_host_pack2(const int8_t* src, int64_t rows, int64_t n, int64_t ld, uint8_t* dst, int64_t dst_ld, int threads);
+/* The same two calls for genotype rows the CALLER holds packed already, 2 bits per genotype (code j of a row in bits
+ * 2 (j % 4) .. 2 (j % 4) + 1 of byte j / 4, codes 0..3; what mmg_host_pack2 writes; row stride ld_bytes >= ceil(n / 4)): a quarter
+ * of the bytes cross PCIe (n / 4 bytes per SNP) and no host core touches them; unpack2_kernel expands every chunk
+ * into the resident int8 block, bits beyond column n are ignored.  hdf5 readers / .bed-like stores hand this over directly. */
+int mmg_kinship_gram_i8_host_packed2(mmg_ctx* ctx, int coding, int impl, const uint8_t* packed, int64_t m, int64_t n,
+                                     int64_t ld_bytes, int reset);
+int mmg_snps_upload_packed2(mmg_ctx* ctx, const uint8_t* packed, int64_t m, int64_t n, int64_t ld_bytes);
 int mmg_host_threads_default(void);
 /* lanes of the most recent mmg_kinship_gram_i8_host: 65 536-SNP chunks sent packed / unpacked, measured host packing rate (GB/s) */
 int mmg_last_h2d_info(mmg_ctx* ctx, int64_t* packed_chunks, int64_t* raw_chunks, double* pack_gbs);

@@ -10,6 +10,7 @@ from . import _lib            # noqa: F401  (fails loudly if the shared library 
 from . import kinship         # noqa: F401
 from . import linear_models   # noqa: F401
 from . import hdf5_data       # noqa: F401
-from ._lib import Context, DeviceMatrix, MmgError, get_context, load_library, resident  # noqa: F401
+from ._lib import (Context, DeviceMatrix, MmgError, PackedGenotypes, get_context, load_library, pack_genotypes,  # noqa: F401
+                   resident)
 
 __version__ = '0.1.0'

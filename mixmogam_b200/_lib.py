@@ -76,6 +76,8 @@ SIGNATURES = {
     'mmg_kinship_gram_i8': (C.c_int, [_c_ctx, C.c_int, C.c_int, _i64, _i64, C.c_int]),
     'mmg_kinship_gram_i8_host': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, _i64, _i64, _i64, C.c_int]),
     'mmg_host_pack2': (C.c_int, [C.c_void_p, _i64, _i64, _i64, C.c_void_p, _i64, C.c_int]),
+    'mmg_kinship_gram_i8_host_packed2': (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p, _i64, _i64, _i64, C.c_int]),
+    'mmg_snps_upload_packed2': (C.c_int, [_c_ctx, C.c_void_p, _i64, _i64, _i64]),
     'mmg_host_threads_default': (C.c_int, []),
     'mmg_last_h2d_info': (C.c_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64), _dp]),
     'mmg_kinship_gram_ptr': (C.c_int, [_c_ctx, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
@@ -87,6 +89,8 @@ SIGNATURES = {
     'mmg_emma_f64': (C.c_int, [_c_ctx, C.c_int, _i64, _vp, _vp, C.c_int, _vp, _vp, _vp, _i64, _vp, C.c_int, C.c_double, _vp, _vp, _vp]),
     'mmg_emmax_scan_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _i64, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_emmax_scan_rows_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, _vp, _i64, _i64,
+                                          _vp, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_quad_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_double, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'mmg_scan_prepass_begin': (C.c_int, [_c_ctx, _i64, _vp, _i64, _i64]),
     'mmg_quad_form_slots': (_i64, [_i64]),
@@ -406,6 +410,18 @@ class Context(object):
         """Make `snps` (list of m int8 rows or an (m, n) array, SNP-major; kinship.py:21-23) the resident
         genotype block.  Uploads it unless this very read-only buffer is already resident (see the residency
         contract above).  Returns (m, n)."""
+        if isinstance(snps, ResidentSnps):
+            if snps.shape != self.snps_shape():
+                raise ValueError('the resident genotype block is %r, not the %r this handle was made for' % (self.snps_shape(), snps.shape))
+            return snps.shape
+        if isinstance(snps, PackedGenotypes):
+            key = snps._key()
+            if key is None or key != self._snps_key:
+                self._snps_key = None
+                self._ck(self.lib.mmg_snps_upload_packed2(self.h, _ptr(snps.packed), snps.shape[0], snps.shape[1], snps.packed.shape[1]))
+                self._snps_key = key
+                self._snps_owner = snps if key is not None else None
+            return snps.shape
         if isinstance(snps, np.ndarray) and snps.ndim == 2:
             a, key = self._array_key(snps)
             if key is None or key != self._snps_key:
@@ -431,6 +447,17 @@ class Context(object):
             self._snps_key = key
             self._snps_owner = list(snps) if key is not None else None
         return (m, n)
+
+    def snps_reserve(self, m, n):
+        """Allocate (or reuse) the resident genotype block for m SNPs x n individuals; its contents are undefined until written."""
+        self._snps_key = None
+        self._ck(self.lib.mmg_snps_reserve(self.h, int(m), int(n)))
+
+    def snps_write(self, row0, rows):
+        """Copy int8 rows [k x n] (C-contiguous; page-locked for the full PCIe rate) into resident rows [row0, row0 + k)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int8)
+        self._snps_key = None
+        self._ck(self.lib.mmg_snps_write(self.h, int(row0), _ptr(rows), rows.shape[0], rows.shape[1]))
 
     def snps_shape(self):
         m, n = _i64(0), _i64(0)
@@ -562,6 +589,15 @@ class Context(object):
         """Integer Gram of all of `snps`, which become the resident genotype block.  A 2-D array that is not resident yet
         is streamed: its 65 536-SNP chunks are copied on a second stream while the Gram of the chunks that have landed
         runs (mmg_kinship_gram_i8_host); anything else is uploaded first (ensure_snps).  Returns (m, n)."""
+        if isinstance(snps, PackedGenotypes):
+            key = snps._key()
+            if key is None or key != self._snps_key:
+                self._snps_key = None
+                self._ck(self.lib.mmg_kinship_gram_i8_host_packed2(self.h, coding, impl_id(impl), _ptr(snps.packed), snps.shape[0], snps.shape[1],
+                                                                   snps.packed.shape[1], 1))
+                self._snps_key = key
+                self._snps_owner = snps if key is not None else None
+                return snps.shape
         if isinstance(snps, np.ndarray) and snps.ndim == 2 and snps.shape[0] > 0:
             a, key = self._array_key(snps)
             if key is None or key != self._snps_key:
@@ -685,6 +721,26 @@ class Context(object):
                                              _ptr(out.get('dots'))))
         return out
 
+    def emmax_scan_rows(self, xs, R, V, h0_rss, n_p, want_dots=False, want_stats=True, **_ignored):
+        """emmax_scan for REAL-VALUED genotype rows xs [m x n] (imputed dosages): FP64 tensor-core path
+        (mmg_emmax_scan_rows_f64); the rows pass through the device in chunks, the resident block is untouched."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        m, n = xs.shape
+        V = np.ascontiguousarray(np.asarray(V, dtype=np.float64))
+        if V.ndim == 1:
+            V = V.reshape(1, -1)
+        nv = V.shape[0]
+        assert V.shape[1] == R.shape[0] and R.shape[1] == n, (V.shape, R.shape, xs.shape)
+        keys = (('ps', 'f_stats', 'rss', 'var_perc') if want_stats else ()) + ('xx',)
+        slab = result_empty((len(keys), m))
+        out = {k: slab[i] for i, k in enumerate(keys)}
+        if want_dots:
+            out['dots'] = result_empty((m, nv))
+        self._ck(self.lib.mmg_emmax_scan_rows_f64(self.h, R.handle, _ptr(V), nv, float(h0_rss), float(n_p), _ptr(xs), m, n,
+                                                  _ptr(out.get('ps')), _ptr(out.get('f_stats')), _ptr(out.get('rss')),
+                                                  _ptr(out.get('var_perc')), _ptr(out['xx']), _ptr(out.get('dots'))))
+        return out
+
     def emmax_scan_quad(self, A, v, h0_rss, n_p, snp_begin=0, snp_count=None):
         """The int8 scan given the quadratic form A = R'R (DeviceMatrix, lower triangle) and v = R'y~ (length n)."""
         m, n = self.snps_shape()
@@ -762,6 +818,99 @@ def _as_int8(a):
                             '(there is no CPU fallback for real-valued dosages)')
         return _as_int8(r.astype(np.int64))
     raise TypeError('unsupported genotype dtype %r' % a.dtype)
+
+
+class ResidentSnps(object):
+    """Stands for "the genotype block that is resident on the device right now" wherever the API takes `snps`: readers that
+    stream a file straight into HBM (hdf5_data.stream_snps) hand this to the scan instead of a host array."""
+
+    def __init__(self, m, n):
+        self.shape = (int(m), int(n))
+
+    def __len__(self):
+        return self.shape[0]
+
+
+class PackedGenotypes(object):
+    """Genotype codes 0..3 held at 2 bits each, SNP-major: `packed` is uint8 [m x >= ceil(n/4)], code j of a row in bits
+    2 (j % 4), 2 (j % 4) + 1 of byte j // 4 (the layout of mmg_host_pack2).  Accepted wherever the API takes `snps`
+    (calc_ibs_kinship, emmax, LinearMixedModel.emmax_f_test, ...): n / 4 bytes per SNP cross PCIe (SURVEY 8d's minimum) and the
+    device expands them into its resident int8 block.  `len()` is the number of SNPs, `[i]` / `unpack()` give int8 rows back.
+    A read-only `packed` array (the default of pack_genotypes) lets the device copy be reused across calls."""
+
+    def __init__(self, packed, n):
+        packed = np.asarray(packed)
+        if packed.dtype != np.uint8 or packed.ndim != 2 or not packed.flags.c_contiguous or packed.shape[1] < (n + 3) // 4:
+            raise ValueError('packed genotypes must be a C-contiguous uint8 [m x >= ceil(n/4)] array')
+        self.packed = packed
+        self.shape = (packed.shape[0], int(n))
+
+    def __len__(self):
+        return self.shape[0]
+
+    def _key(self):
+        return ('packed2', self.packed.ctypes.data, self.shape) if not self.packed.flags.writeable else None
+
+    def unpack(self, rows=None):
+        p = self.packed if rows is None else self.packed[rows]
+        p = p.reshape(-1, self.packed.shape[1])
+        out = np.empty((p.shape[0], 4 * p.shape[1]), dtype=np.int8)
+        for k in range(4):
+            out[:, k::4] = (p >> (2 * k)) & 3
+        return out[:, :self.shape[1]]
+
+    def __getitem__(self, i):
+        if isinstance(i, (int, np.integer)):
+            return self.unpack(slice(i, i + 1))[0]
+        if isinstance(i, slice):
+            return PackedGenotypes(self.packed[i], self.shape[1])
+        return self.unpack(i)
+
+
+def pack_genotypes(snps, threads=None, freeze=True):
+    """int8 genotype codes 0..3 ([m x n] array or list of rows) -> PackedGenotypes in page-locked memory (mmg_host_pack2, all host
+    threads).  freeze: mark the packed array read-only so that its device copy is kept between calls."""
+    a = np.asarray(snps)
+    if a.dtype != np.int8:
+        a = _as_int8(a)
+    a = np.ascontiguousarray(a)
+    m, n = a.shape
+    ld = ((n + 3) // 4 + 15) // 16 * 16
+    try:
+        packed = pinned_empty((m, ld), np.uint8)
+    except MmgError:                      # no CUDA device in this process (packing is host-only work): ordinary memory
+        packed = np.empty((m, ld), dtype=np.uint8)
+    lib = load_library()
+    rc = lib.mmg_host_pack2(_ptr(a), m, n, n, _ptr(packed), ld, int(threads or lib.mmg_host_threads_default()))
+    if rc != 0:
+        raise ValueError('genotype codes outside 0..3 cannot be packed to 2 bits')
+    if freeze:
+        packed.flags.writeable = False
+    return PackedGenotypes(packed, n)
+
+
+def real_valued(snps):
+    """The genotypes as one FP64 [m x n] array if they hold non-integral values (imputed dosages), else None (integer codes
+    go to the int8 tensor-core paths)."""
+    if isinstance(snps, (PackedGenotypes, ResidentSnps)):
+        return None
+    if isinstance(snps, np.ndarray):
+        if snps.dtype.kind != 'f':
+            return None
+        a = snps
+    else:
+        if len(snps) == 0 or all(getattr(r, 'dtype', None) is not None and r.dtype.kind in 'iub' for r in snps):
+            return None
+        a = np.asarray(snps)
+        if a.dtype.kind != 'f':
+            return None
+    if a.ndim != 2:
+        raise ValueError('genotypes must be an (m, n) array or a list of m rows')
+    if np.array_equal(np.rint(a), a) and (a.size == 0 or (a.min() >= -128 and a.max() <= 127)):
+        return None
+    if not np.all(np.isfinite(a)):
+        raise ValueError('genotypes contain NaN / inf')
+    return np.ascontiguousarray(a, dtype=np.float64)
 
 
 def resident(snps):

@@ -27,6 +27,8 @@ extern "C" {
 struct GramHostSource {
     const int8_t* snps = nullptr;      // SNP-major host rows, row stride ld
     int64_t ld = 0;
+    const uint8_t* packed2 = nullptr;  // or: rows the caller packed already (2 bits per genotype), row stride ld2 bytes -- a quarter
+    int64_t ld2 = 0;                   // of the bytes cross PCIe and no host core touches them
     cudaStream_t stream = nullptr;     // raw lane
     cudaStream_t stream2 = nullptr;    // packed lane (its small copies must not queue behind the raw ones)
     std::vector<cudaEvent_t> done;     // one per chunk
@@ -61,13 +63,19 @@ extern "C" int mmg_host_threads_default();
 
 // packed [rows x p_ld] (2 bits per genotype, code j of a row in bits 2 (j % 4) of byte j / 4) -> int8 [rows x pitch];
 // one thread per 32-bit word = 16 genotypes = one 16-byte store
-static __global__ void unpack2_kernel(const uint8_t* __restrict__ packed, int64_t p_ld, int8_t* __restrict__ out, int64_t pitch, int64_t rows) {
+// n_valid > 0: codes of columns >= n_valid are forced to 0 (rows packed by the caller: nothing is assumed about the unused bits)
+static __global__ void unpack2_kernel(const uint8_t* __restrict__ packed, int64_t p_ld, int8_t* __restrict__ out, int64_t pitch, int64_t rows,
+                                      int64_t n_valid = 0) {
     const int64_t wpr = p_ld >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * wpr) return;
     const int64_t r = idx / wpr, w = idx - r * wpr;
     if (16 * w >= pitch) return;
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(packed + r * p_ld + 4 * w);
+    uint32_t v = *reinterpret_cast<const uint32_t*>(packed + r * p_ld + 4 * w);
+    if (n_valid > 0 && 16 * (w + 1) > n_valid) {
+        const int64_t keep = n_valid - 16 * w;                       // genotypes of this word that exist
+        v = keep <= 0 ? 0u : (v & (0xffffffffu >> (32 - 2 * (int)keep)));
+    }
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -84,6 +92,7 @@ static double host_now() {
 }
 
 static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset, GramHostSource* src);
+static int host_source_open(mmg_ctx* ctx, GramHostSource& src);
 
 int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset) {
     return gram_run(ctx, coding, impl, snp_begin, snp_count, reset, nullptr);
@@ -96,10 +105,6 @@ int mmg_kinship_gram_i8_host(mmg_ctx* ctx, int coding, int impl, const int8_t* s
     GramHostSource src;
     src.snps = snps;
     src.ld = ld;
-    MMG_CUDA(ctx, cudaStreamCreateWithFlags(&src.stream, cudaStreamNonBlocking));
-    MMG_CUDA(ctx, cudaStreamCreateWithFlags(&src.stream2, cudaStreamNonBlocking));
-    MMG_CUDA(ctx, cudaEventCreate(&src.t0));
-    for (int i = 0; i < 2; ++i) MMG_CUDA(ctx, cudaEventCreateWithFlags(&src.slot_free[i], cudaEventDisableTiming));
     {
         cudaPointerAttributes pa{};
         src.pinned = cudaPointerGetAttributes(&pa, snps) == cudaSuccess && pa.type == cudaMemoryTypeHost;
@@ -107,14 +112,62 @@ int mmg_kinship_gram_i8_host(mmg_ctx* ctx, int coding, int impl, const int8_t* s
     }
     src.pack_ok = env_int("MMG_H2D_PACK", 1) != 0;
     src.threads = std::max(1, env_int("MMG_HOST_THREADS", mmg_host_threads_default()));
+    MMG_TRY(host_source_open(ctx, src));
+    const int rc = gram_run(ctx, coding, impl, 0, m, reset, &src);
+    if (rc == MMG_OK) ctx->snps_absmax = coding == MMG_CODING_DIPLOID ? 2 : 1;   // the pack kernels checked every byte against the coding
+    return rc;
+}
+
+static int host_source_open(mmg_ctx* ctx, GramHostSource& src) {
+    MMG_CUDA(ctx, cudaStreamCreateWithFlags(&src.stream, cudaStreamNonBlocking));
+    MMG_CUDA(ctx, cudaStreamCreateWithFlags(&src.stream2, cudaStreamNonBlocking));
+    MMG_CUDA(ctx, cudaEventCreate(&src.t0));
+    for (int i = 0; i < 2; ++i) MMG_CUDA(ctx, cudaEventCreateWithFlags(&src.slot_free[i], cudaEventDisableTiming));
     // the zero fill of the row padding (mmg_snps_reserve, compute stream) must not race with the copies
     MMG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     MMG_CUDA(ctx, cudaStreamWaitEvent(src.stream, ctx->ev0, 0));
     MMG_CUDA(ctx, cudaStreamWaitEvent(src.stream2, ctx->ev0, 0));
-    MMG_CUDA(ctx, cudaEventRecord(src.t0, src.stream));
+    MMG_CUDA(ctx, cudaEventRecord(src.t0, src.stream2));
+    return MMG_OK;
+}
+
+int mmg_kinship_gram_i8_host_packed2(mmg_ctx* ctx, int coding, int impl, const uint8_t* packed, int64_t m, int64_t n, int64_t ld_bytes, int reset) {
+    MMG_CHECK(ctx, ctx && packed && m > 0 && n > 0 && ld_bytes >= (n + 3) / 4, "mmg_kinship_gram_i8_host_packed2: bad argument");
+    MMG_TRY(mmg_snps_reserve(ctx, m, n));
+    ctx->snps_absmax = -1;
+    GramHostSource src;
+    src.packed2 = packed;
+    src.ld2 = ld_bytes;
+    MMG_TRY(host_source_open(ctx, src));
     const int rc = gram_run(ctx, coding, impl, 0, m, reset, &src);
-    if (rc == MMG_OK) ctx->snps_absmax = coding == MMG_CODING_DIPLOID ? 2 : 1;   // the pack kernels checked every byte against the coding
+    if (rc == MMG_OK) ctx->snps_absmax = coding == MMG_CODING_DIPLOID ? 2 : 1;
     return rc;
+}
+
+// Upload only (scan-only callers): caller-packed rows -> resident int8 block, chunk by chunk through the device slots.
+int mmg_snps_upload_packed2(mmg_ctx* ctx, const uint8_t* packed, int64_t m, int64_t n, int64_t ld_bytes) {
+    MMG_CHECK(ctx, ctx && packed && m > 0 && n > 0 && ld_bytes >= (n + 3) / 4, "mmg_snps_upload_packed2: bad argument");
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MMG_TRY(mmg_snps_reserve(ctx, m, n));
+    ctx->snps_absmax = -1;
+    StageTimer tm(ctx, "h2d");
+    const int64_t p2_ld = round_up((n + 3) / 4, 16), width = (n + 3) / 4;
+    const int64_t chunk = std::min<int64_t>(m, 65536);
+    DevBuf slot[2];
+    for (int i = 0; i < 2; ++i) {
+        MMG_CUDA(ctx, slot[i].alloc(ctx->stream, (size_t)chunk * p2_ld));
+        MMG_CUDA(ctx, cudaMemsetAsync(slot[i].p, 0, (size_t)chunk * p2_ld, ctx->stream));
+    }
+    int sl = 0;
+    for (int64_t r0 = 0; r0 < m; r0 += chunk, sl ^= 1) {
+        const int64_t cnt = std::min(chunk, m - r0);
+        MMG_CUDA(ctx, cudaMemcpy2DAsync(slot[sl].p, p2_ld, packed + r0 * ld_bytes, ld_bytes, width, cnt, cudaMemcpyHostToDevice, ctx->stream));
+        const int64_t words = cnt * (p2_ld >> 2);
+        unpack2_kernel<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(slot[sl].as<uint8_t>(), p2_ld, ctx->snps + r0 * ctx->pitch, ctx->pitch, cnt, n);
+        MMG_TRY(launch_check(ctx, "unpack2_kernel"));
+    }
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the caller's rows are borrowed for the duration of the call only
+    return MMG_OK;
 }
 
 static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset, GramHostSource* src) {
@@ -255,12 +308,54 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
         staged[(size_t)ci] = 1;
         return MMG_OK;
     };
+    // rows packed by the caller: straight from the caller's buffer into a device slot (no host core involved), then unpack2
+    auto queue_prepacked = [&](int64_t ci) -> int {
+        const int64_t s0 = ci * chunk, cnt = chunk_rows(ci);
+        const int sl = src->next_slot;
+        const int64_t width = (ctx->n + 3) / 4;
+        MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_dev[sl], p2_ld, src->packed2 + (snp_begin + s0) * src->ld2, src->ld2, width, cnt,
+                                        cudaMemcpyHostToDevice, src->stream2));
+        const int64_t words = cnt * (p2_ld >> 2);
+        unpack2_kernel<<<(unsigned)((words + 255) / 256), 256, 0, src->stream2>>>(ctx->stage_dev[sl], p2_ld, ctx->snps + (snp_begin + s0) * ctx->pitch,
+                                                                                ctx->pitch, cnt, ctx->n);
+        MMG_TRY(launch_check(ctx, "unpack2_kernel"));
+        MMG_CUDA(ctx, cudaEventRecord(src->done[(size_t)ci], src->stream2));
+        src->next_slot = sl ^ 1;
+        src->packed_chunks += 1;
+        staged[(size_t)ci] = 1;
+        return MMG_OK;
+    };
+    if (src && src->packed2) {
+        const int64_t stage_need = std::min(chunk, snp_count) * p2_ld;
+        if (ctx->stage_bytes < stage_need) {
+            for (int i = 0; i < 2; ++i) {
+                if (ctx->stage_host[i]) cudaFreeHost(ctx->stage_host[i]);
+                cudaFree(ctx->stage_dev[i]);
+                ctx->stage_host[i] = ctx->stage_dev[i] = nullptr;
+            }
+            ctx->stage_bytes = 0;
+            for (int i = 0; i < 2; ++i) {
+                MMG_CUDA(ctx, cudaHostAlloc((void**)&ctx->stage_host[i], (size_t)stage_need, cudaHostAllocDefault));
+                MMG_CUDA(ctx, cudaMalloc((void**)&ctx->stage_dev[i], (size_t)stage_need));
+            }
+            ctx->stage_bytes = stage_need;
+        }
+        // the copies fill the first ceil(n/4) bytes of a slot row; the rest of the row must read as zero
+        for (int i = 0; i < 2; ++i) MMG_CUDA(ctx, cudaMemsetAsync(ctx->stage_dev[i], 0, (size_t)ctx->stage_bytes, src->stream2));
+    }
     // Stage chunk ci (if a look-ahead has not done so already).  Packed lane when the raw lane would deliver it later:
     // pageable rows always (a raw copy blocks the host at the pageable rate), page-locked rows when the DMA backlog exceeds the
     // time the host needs to pack the chunk.  Before the host disappears into a pack, the raw lane is topped up with the
     // following chunks so that the link stays busy meanwhile.
     auto issue_copy = [&](int64_t ci) -> int {
         if (staged[(size_t)ci]) return MMG_OK;
+        if (src->packed2) {
+            // all the copies are queued at once, two chunks ahead of the Gram is enough to keep the link busy; the stream order
+            // of the packed lane (copy, unpack, copy, ...) makes the two device slots safe without events
+            for (int64_t cj = ci; cj < std::min<int64_t>(n_chunks, ci + 2); ++cj)
+                if (!staged[(size_t)cj]) MMG_TRY(queue_prepacked(cj));
+            return MMG_OK;
+        }
         double raw_s = raw_seconds(ci);
         const double pack_s = ctx->pack_s_per_byte > 0.0 ? ctx->pack_s_per_byte * (double)chunk_rows(ci) * (double)ctx->n : raw_s;
         // backlog of the raw lane: bytes queued and not yet seen complete, at the rate measured on the copies that are

@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib
 from . import linear_models as lm
 
-__all__ = ['calculate_ibd_kinship', 'run_emmax', 'run_emmax_perm']
+__all__ = ['calculate_ibd_kinship', 'run_emmax', 'run_emmax_perm', 'stream_snps', 'write_genotype_file']
 
 
 def _open(f, mode='r'):
@@ -52,6 +52,112 @@ def _arr(x):
     return np.asarray(x[...]) if hasattr(x, 'shape') and not isinstance(x, np.ndarray) else np.asarray(x)
 
 
+def stream_snps(ctx, parts, chunk_rows=None):
+    """
+    HDF5 dataset(s) -> resident genotype block without a host copy of the whole matrix (the reference reads
+    `gg[chrom]['raw_snps'][...]` in one piece and then filters it, hdf5_data.py:162-169, :298-305).  `parts` is a list of
+    (dataset, keep) pairs -- dataset: anything sliceable by rows that yields int8 [rows x n] (an h5py dataset decompresses its
+    lzf chunks slice by slice; a numpy array works too), keep: boolean row filter or None.  A reader thread fills two
+    page-locked chunks while the previous one is on its way over PCIe (mmg_snps_write).  Returns a ResidentSnps handle that
+    the scans accept in place of `snps`.
+    """
+    import threading
+    import queue
+    parts = [(ds, None if keep is None else np.asarray(keep, dtype=bool)) for ds, keep in parts]
+    n = int(parts[0][0].shape[1])
+    total = sum(int(ds.shape[0]) if keep is None else int(keep.sum()) for ds, keep in parts)
+    if total == 0:
+        raise ValueError('no SNPs')
+    if chunk_rows is None:
+        chunk_rows = max(256, (64 << 20) // max(n, 1))
+    ctx.snps_reserve(total, n)
+    bufs = [_lib.pinned_empty((chunk_rows, n), np.int8) for _ in range(2)]
+    free_q, full_q = queue.Queue(), queue.Queue()
+    for b in bufs:
+        free_q.put(b)
+
+    def reader():
+        try:
+            for ds, keep in parts:
+                for r0 in range(0, int(ds.shape[0]), chunk_rows):
+                    r1 = min(int(ds.shape[0]), r0 + chunk_rows)
+                    if keep is not None and not keep[r0:r1].any():
+                        continue
+                    block = np.asarray(ds[r0:r1])
+                    if keep is not None:
+                        block = block[keep[r0:r1]]
+                    if block.dtype != np.int8:
+                        block = _lib._as_int8(block)
+                    buf = free_q.get()
+                    buf[:block.shape[0]] = block
+                    full_q.put((buf, block.shape[0]))
+            full_q.put(None)
+        except BaseException as e:           # surfaces in the consumer
+            full_q.put(e)
+
+    th = threading.Thread(target=reader, daemon=True)
+    th.start()
+    row0 = 0
+    while True:
+        item = full_q.get()
+        if item is None:
+            break
+        if isinstance(item, BaseException):
+            raise item
+        buf, k = item
+        ctx.snps_write(row0, buf[:k])        # returns when the copy has left the buffer
+        row0 += k
+        free_q.put(buf)
+    th.join()
+    assert row0 == total
+    return _lib.ResidentSnps(total, n)
+
+
+def write_genotype_file(target, chromosomes, indiv_ids, phenotypes, sex=None, compression='lzf'):
+    """
+    Writer side of the layout hdf5_data reads (the reference's plink2hdf5.py:25-28, :57-59, :111-118, :216-226; the PLINK text
+    parsing in front of it is out of scope):
+        genot_data/chrom_<c>/{raw_snps int8 (m_c x n), positions, freqs, snp_ids, nts, nt_counts, missing_counts}
+        indiv_data/{indiv_ids, sex, phenotypes},  num_snps
+    `chromosomes`: mapping chrom -> dict with 'raw_snps' (int8 [m_c x n]) and optionally 'positions', 'snp_ids', 'nts',
+    'nt_counts', 'missing_counts'; 'freqs' defaults to the allele frequency mean(raw_snps) / 2 (plink2hdf5.py:96-99).
+    `target`: file name (h5py) or a mapping to fill.
+    """
+    f, opened = _open(target, 'w')
+
+    def put(g, name, data):
+        if hasattr(g, 'create_dataset'):
+            g.create_dataset(name, data=data, **({'compression': compression} if compression and np.ndim(data) > 0 else {}))
+        else:
+            g[name] = np.asarray(data)
+
+    gg = _group(f, 'genot_data')
+    ig = _group(f, 'indiv_data')
+    put(ig, 'indiv_ids', np.asarray(indiv_ids))
+    put(ig, 'sex', np.asarray(sex if sex is not None else np.zeros(len(indiv_ids), dtype=np.int64)))
+    put(ig, 'phenotypes', np.asarray(phenotypes, dtype=np.float64))
+    tot = 0
+    for chrom, d in chromosomes.items():
+        raw = np.asarray(d['raw_snps'])
+        if raw.dtype != np.int8:
+            raw = _lib._as_int8(raw)
+        m_c = raw.shape[0]
+        name = str(chrom) if str(chrom).startswith('chrom_') else 'chrom_%s' % chrom
+        cg = _group(gg, name)
+        put(cg, 'raw_snps', raw)
+        put(cg, 'positions', np.asarray(d.get('positions', np.arange(1, m_c + 1))))
+        put(cg, 'freqs', np.asarray(d['freqs']) if 'freqs' in d else raw.mean(axis=1, dtype=np.float64) / 2.0)
+        put(cg, 'snp_ids', np.asarray(d.get('snp_ids', np.array(['%s_%d' % (name, i) for i in range(m_c)], dtype='S'))))
+        for opt in ('nts', 'nt_counts', 'missing_counts'):
+            if opt in d:
+                put(cg, opt, np.asarray(d[opt]))
+        tot += m_c
+    put(f, 'num_snps', np.array(tot))
+    if opened:
+        f.close()
+    return f
+
+
 def _ibd_kinship_device(ctx, gg, n_indivs, min_maf=None, use_normalized=False):
     """hdf5_data.py:30-62 / :84-115 / :205-237: K = sum over chromosomes of Z'Z / n_snps, then the inline
     scale_k.  Returns (K DeviceMatrix, n_snps)."""
@@ -59,13 +165,12 @@ def _ibd_kinship_device(ctx, gg, n_indivs, min_maf=None, use_normalized=False):
     n_snps = 0
     for chrom in gg.keys():
         cg = gg[chrom]
-        snps = _arr(cg['raw_snps'])
         mask = None
         if min_maf is not None:
             freqs = _arr(cg['freqs'])
             mafs = np.minimum(freqs, 1 - freqs)
             mask = (mafs > min_maf)                          # :91-96
-        m_c, n = ctx.ensure_snps(snps)
+        m_c, n = stream_snps(ctx, [(cg['raw_snps'], None)]).shape
         try:
             n_snps += ctx.kinship_ibd_accumulate(K, 0, m_c, mask)
         except _lib.MmgError as e:
@@ -143,8 +248,8 @@ def run_emmax(hdf5_filename='/home/bv25/data/Ls154/Ls154_12.hdf5',
         freqs = _arr(gg[chrom]['freqs'])
         mafs = np.minimum(freqs, 1 - freqs)
         maf_filter = mafs > min_maf
-        snps = _arr(gg[chrom]['raw_snps'])[maf_filter]
         positions = _arr(gg[chrom]['positions'])[maf_filter]
+        snps = stream_snps(ctx, [(gg[chrom]['raw_snps'], maf_filter)])       # :162-169, chunk by chunk into HBM
         r = lmm._emmax_f_test_(snps, res['H_sqrt_inv'], with_betas=False, emma_num=0, eig_L=eig_L)
         _put(crg, 'ps', r['ps'])
         _put(crg, 'positions', positions)
@@ -200,17 +305,17 @@ def run_emmax_perm(hdf5_filename='/home/bv25/data/Ls154/Ls154_12.hdf5',
         freqs = _arr(gg[chrom]['freqs'])
         mafs = np.minimum(freqs, 1 - freqs)
         maf_filter = mafs > min_maf
-        snps = _arr(gg[chrom]['raw_snps'])[maf_filter]
         positions = _arr(gg[chrom]['positions'])[maf_filter]
         if chrom != chromosomes[-1]:
-            chr12.append(snps)
+            chr12.append((gg[chrom]['raw_snps'], maf_filter))
+        snps = stream_snps(ctx, [(gg[chrom]['raw_snps'], maf_filter)])
         r = lmm._emmax_f_test_(snps, res['H_sqrt_inv'], with_betas=False, emma_num=0, eig_L=eig_L)
         _put(crg, 'ps', r['ps'])
         _put(crg, 'positions', positions)
         if hasattr(oh5f, 'flush'):
             oh5f.flush()
 
-    chr12_snps = np.concatenate(chr12, axis=0) if chr12 else np.zeros((0, n_indivs), dtype=np.int8)
+    chr12_snps = stream_snps(ctx, chr12)                      # :294,:310-311 -- all chromosomes but the last, one resident block
     perm_res = lmm._emmax_permutations_(chr12_snps, k, res['H_sqrt_inv'], num_perm=num_perm)     # :330
 
     perm_res['min_ps'].sort()                                 # :339

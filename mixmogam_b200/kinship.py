@@ -5,6 +5,9 @@ Drop-in for mixmogam's `kinship` module, hot-path subset (reference kinship.py):
                      chunk_size=None, scaled=True)                          kinship.py:14-56
     calc_ibd_kinship(snps, dtype='single', scaled=True)                     kinship.py:59-75
     scale_k(k, verbose=False)                                               kinship.py:94-100
+    prepare_k(k, k_accessions, accessions)                                  kinship.py:79-90
+    update_k_monomorphic(...)                                               kinship.py:134-142
+    load_kinship_from_file / save_kinship_to_file / save_kinship_in_text_format     kinship.py:145-174
 
 Same names, argument meaning and return types; the arithmetic runs on the B200 through
 libmixmogam_b200 (no CPU fallback):
@@ -19,7 +22,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ['calc_ibs_kinship', 'calc_ibd_kinship', 'scale_k', 'calc_ibs_kinship_device', 'partial_ibs_gram']
+__all__ = ['calc_ibs_kinship', 'calc_ibd_kinship', 'scale_k', 'calc_ibs_kinship_device', 'partial_ibs_gram', 'prepare_k',
+           'update_k_monomorphic', 'load_kinship_from_file', 'save_kinship_to_file', 'save_kinship_in_text_format']
 
 
 def _coding(snps_data_format):
@@ -109,3 +113,77 @@ def scale_k(k, verbose=False, ctx=None):
             warnings.simplefilter('ignore', PendingDeprecationWarning)
             return np.asmatrix(out)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Kinship files (kinship.py:79-90, 134-174).  `kinship_file` is a file name (HDF5 through h5py, imported lazily: it is not part
+# of this image) or any mapping with the same three datasets -- 'kinship' (n x n), 'accessions' (n), 'n_snps' (scalar).
+
+def prepare_k(k, k_accessions, accessions):
+    """kinship.py:79-90: the sub-matrix of k for `accessions`, in that order; accessions k does not know are skipped."""
+    k_accessions = list(k_accessions)
+    accessions = list(accessions)
+    if k_accessions == accessions:
+        return np.asmatrix(np.asarray(k))
+    pos = {}
+    for i, acc in enumerate(k_accessions):
+        pos.setdefault(acc, i)                         # list.index semantics: the first occurrence
+    indices_to_keep = [pos[acc] for acc in accessions if acc in pos]
+    k = np.asarray(k)[indices_to_keep, :][:, indices_to_keep]
+    return np.asmatrix(k)
+
+
+def update_k_monomorphic(n_removed_snps, full_kinship, full_indivs, full_num_snps, retained_indivs, kinship_type='ibs', dtype='single'):
+    """kinship.py:134-142: the IBS kinship after dropping SNPs that are monomorphic among the retained individuals."""
+    assert kinship_type == 'ibs', 'Only IBS kinships can be updated at the moment'
+    cut_kinship = prepare_k(full_kinship, full_indivs, retained_indivs)
+    num_lines = cut_kinship.shape[0]
+    m = np.ones((num_lines, num_lines), dtype=np.float32 if dtype == 'single' else np.float64) * n_removed_snps
+    return (cut_kinship * full_num_snps - m) / (full_num_snps - n_removed_snps)
+
+
+def _open_kinship(kinship_file, mode):
+    if isinstance(kinship_file, str):
+        try:
+            import h5py
+        except ImportError:
+            raise ImportError('h5py is required to open %r; pass an in-memory mapping with the same datasets instead' % kinship_file)
+        return h5py.File(kinship_file, mode), True
+    return kinship_file, False
+
+
+def load_kinship_from_file(kinship_file, accessions=None, scaled=True, ctx=None):
+    """kinship.py:145-160.  Returns {'k', 'accessions', 'n_snps'}; scaling runs on the device (scale_k)."""
+    if isinstance(kinship_file, str):
+        import os
+        assert os.path.isfile(kinship_file), 'File not found.'
+    f, opened = _open_kinship(kinship_file, 'r')
+    k = np.asarray(f['kinship'][...])
+    k_accessions = list(np.asarray(f['accessions'][...]))
+    n_snps = int(np.asarray(f['n_snps'][...]))
+    if opened:
+        f.close()
+    if accessions:
+        k = prepare_k(k, k_accessions, accessions)
+    if scaled:
+        k = scale_k(np.asarray(k, dtype=np.float64), ctx=ctx)
+    return {'k': k, 'accessions': k_accessions, 'n_snps': n_snps}
+
+
+def save_kinship_to_file(kinship_file, kinship_mat, k_accessions, n_snps):
+    """kinship.py:164-169."""
+    f, opened = _open_kinship(kinship_file, 'w')
+    for name, data in (('kinship', np.asarray(kinship_mat)), ('accessions', np.asarray(k_accessions)), ('n_snps', np.asarray(n_snps))):
+        if hasattr(f, 'create_dataset'):
+            f.create_dataset(name, data=data)
+        else:
+            f[name] = data
+    if opened:
+        f.close()
+
+
+def save_kinship_in_text_format(filename, k, accessions):
+    """kinship.py:172-175: one line per accession, `acc,k_1,...,k_n`."""
+    with open(filename, 'w') as f:
+        for acc, row in zip(accessions, np.asarray(k)):
+            f.write('%s,%s\n' % (acc, ','.join(map(str, row.tolist()))))

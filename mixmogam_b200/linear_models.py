@@ -12,6 +12,8 @@ Drop-in for the EMMAX path of mixmogam's `linear_models` module (reference linea
         .emmax_f_test(snps, snp_priors, Z, with_betas, method, eig_L, eig_R, emma_num=100)   :1233
         ._emmax_f_test_(snps, H_sqrt_inv, ...)                               :1272
         ._emmax_permutations_(snps, K, H_sqrt_inv, num_perm=100)             :1125
+        .emmax_GxT_f_test(snps, E, Z, ...) / ._emmax_GxT_f_test_             :1383 / :1422
+    emmax_w_two_env(snps, phenotypes, K, E, cofactors=None, Z=None)          :1749
     emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_num=0)          :1790
     emma(snps, phenotypes, K, cofactors=None)                                :1725
     emmax_multi(snps, phenotypes[T], K, cofactors=None)                      T x emmax() on one eigenbasis, one scan launch
@@ -41,7 +43,7 @@ from . import _lib
 from . import kinship
 from ._lib import DeviceMatrix, LazyHostArray, LazyScaledRows
 
-__all__ = ['LinearModel', 'LinearMixedModel', 'emmax', 'emmax_multi', 'emma', 'get_emma_reml_estimates']
+__all__ = ['LinearModel', 'LinearMixedModel', 'emmax', 'emmax_multi', 'emmax_w_two_env', 'emma', 'get_emma_reml_estimates']
 
 _VERBOSE = False
 
@@ -506,7 +508,13 @@ class LinearMixedModel(LinearModel):
         p = len(self.X.T) + q
         n = self.n
         n_p = n - p
-        num_snps, n_lines = ctx.ensure_snps(snps)
+        xs_real = _lib.real_valued(snps)          # imputed dosages: FP64 tensor-core scan of the rows themselves (:1317 takes any numeric row)
+        if xs_real is not None:
+            num_snps, n_lines = xs_real.shape
+            scan = lambda R_, V_, h_, np_, **kw: ctx.emmax_scan_rows(xs_real, R_, V_, h_, np_, **kw)
+        else:
+            num_snps, n_lines = ctx.ensure_snps(snps)
+            scan = ctx.emmax_scan
         H = H_sqrt_inv if isinstance(H_sqrt_inv, LazyScaledRows) else ctx.to_device(H_sqrt_inv)
         nf = self._null_fit(H, Z=Z, project=not with_betas)
         h0_rss = nf['h0_rss']
@@ -519,7 +527,7 @@ class LinearMixedModel(LinearModel):
 
         if not with_betas:
             int8_scan = impl == 'tcgen05' or (impl in ('auto', None) and os.environ.get('MMG_SCAN_IMPL', 'tcgen05') == 'tcgen05')
-            if self.shard is not None:
+            if self.shard is not None and xs_real is None:
                 # one process per GPU, explicitly requested (set_sharding): R'R is formed once across the ranks instead of once
                 # per rank, every rank scans its SNP slice, the outputs are all-gathered (parallel.py)
                 from . import parallel
@@ -537,16 +545,16 @@ class LinearMixedModel(LinearModel):
                     A.free()
                     num_snps = len(out['ps'])
                 else:
-                    out = ctx.emmax_scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
+                    out = scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
             else:
-                out = ctx.emmax_scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
+                out = scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
             p_vals, f_stats, rss_list, var_perc = out['ps'], out['f_stats'], out['rss'], out['var_perc']
         else:
             # lstsq([h0_X, x~], Y) (:1323) through its normal equations: the kernel supplies
             # xx = x~.x~, xy = x~.Yres, b = x~.h0_X; the (q0+1)x(q0+1) solve is a Schur complement per SNP.
             h0_X, Yres = nf['h0_X'], nf['Yres']
             V = np.vstack([Yres.T, h0_X.T])
-            out = ctx.emmax_scan(Rm, V, h0_rss_f, n_p, impl=impl, want_dots=True, want_stats=False)
+            out = scan(Rm, V, h0_rss_f, n_p, impl=impl, want_dots=True, want_stats=False)
             xx, dots = out['xx'], out['dots']
             xy, b = dots[:, 0], dots[:, 1:]
             A = h0_X.T @ h0_X
@@ -591,7 +599,10 @@ class LinearMixedModel(LinearModel):
             _say('Updating p-values using EMMA for the smallest %d p-values.' % len(pval_indices))
             l = list(map(list, zip(*pval_indices)))
             # the top hits are refined straight from the resident genotype block (the scan just used it): no re-upload
-            top_emma_res = self.expedited_REML_t_test(None, eig_L=eig_L, _resident_rows=np.asarray(l[1], dtype=np.int64))
+            if xs_real is not None:
+                top_emma_res = self.expedited_REML_t_test(xs_real[np.asarray(l[1], dtype=np.int64)], eig_L=eig_L)
+            else:
+                top_emma_res = self.expedited_REML_t_test(None, eig_L=eig_L, _resident_rows=np.asarray(l[1], dtype=np.int64))
             for pi, pv, f, r, v in zip(l[1], top_emma_res['ps'], top_emma_res['f_stats'],
                                        top_emma_res['rss'], top_emma_res['var_perc']):
                 res_d['ps'][pi] = pv
@@ -611,6 +622,129 @@ class LinearMixedModel(LinearModel):
             xc.free()
             out.extend(list(t))
         return out
+
+    # ------------------------------------------------------------------------------------------
+    def emmax_GxT_f_test(self, snps, E, Z=None, with_betas=False, method='REML', eig_L=None, eig_R=None):
+        """
+        EMMAX with a genotype x environment term, single SNPs (linear_models.py:1383-1416).
+        """
+        if not eig_L:
+            eig_L = self._get_eigen_L_()
+        if not eig_R:
+            eig_R = self._get_eigen_R_(X=self.X)
+        res = self.get_estimates(eig_L, method=method, eig_R=eig_R)
+        r = self._emmax_GxT_f_test_(snps, res['H_sqrt_inv'], E, Z, with_betas=with_betas, eig_L=eig_L)
+        r['pseudo_heritability'] = res['pseudo_heritability']
+        r['ve'] = res['ve']
+        r['vg'] = res['vg']
+        r['max_ll'] = res['max_ll']
+        return r
+
+    def _moments(self, x, Rm, V, h0_rss_f, n_p, impl):
+        """x~.x~ and x~.V[k] of every row of the genotype block x through the fused scan kernels (int rows: resident block;
+        real-valued rows: FP64 tensor-core path)."""
+        ctx = self.ctx
+        xr = _lib.real_valued(x)
+        if xr is not None:
+            out = ctx.emmax_scan_rows(xr, Rm, V, h0_rss_f, n_p, want_dots=True, want_stats=False)
+        else:
+            ctx.ensure_snps(x)
+            out = ctx.emmax_scan(Rm, V, h0_rss_f, n_p, impl=impl, want_dots=True, want_stats=False)
+        return np.array(out['xx']), np.array(out['dots'])
+
+    def _emmax_GxT_f_test_(self, snps, H_sqrt_inv, T, Z, verbose=True, **kwargs):
+        """
+        EMMAX G and G x T tests, single SNPs (linear_models.py:1422-1514): per SNP the genetic model [h0_X, x~] and the full
+        model [h0_X, x~, t~] with x~ = H x, t~ = H (x o T) (:1447-1449, M = H', no Q projection).  The reference solves two
+        lstsq per SNP; here the moments of both models come from three passes of the fused scan kernel -- over the blocks x,
+        x o T and x o (1 + T): x~.x~, t~.t~ and, by polarisation, x~.t~ = (s~.s~ - x~.x~ - t~.t~) / 2 -- together with the dot
+        products against the residual phenotype and h0_X; the (q0+1) and (q0+2) normal equations are then Schur complements,
+        vectorised over the SNPs.  Returns {'g_res', 'gt_res', 'gt_g_res'} with the reference's keys.
+        """
+        ctx = self.ctx
+        n = self.n
+        impl = kwargs.get('impl', 'dmma' if self.scan_impl in ('auto', None) else self.scan_impl)   # differences of moments: FP64 pipe by default
+        H = H_sqrt_inv if isinstance(H_sqrt_inv, LazyScaledRows) else ctx.to_device(H_sqrt_inv)
+        nf = self._null_fit(H, Z=None, project=False)                       # :1437-1441, M = H' (:1446)
+        h0_X, Yres, Rm = nf['h0_X'], nf['Yres'], nf['R']
+        h0_rss = nf['h0_rss']
+        h0_rss_f = float(np.asarray(h0_rss).reshape(-1)[0])
+        h0_betas = list(map(float, list(np.asarray(nf['h0_betas']).reshape(-1))))
+        q0 = h0_X.shape[1]
+        T_flat = np.array(T, dtype=np.float64).flatten()
+        x = np.asarray(snps)
+        if x.ndim != 2:
+            x = np.asarray([np.asarray(r) for r in snps])
+        if Z is not None:
+            x = x @ np.asarray(Z).T                                          # :1452
+        if x.shape[1] != n or T_flat.shape[0] != n:
+            raise ValueError('SNPs / environment vector do not match the model (%d individuals)' % n)
+        num_snps = x.shape[0]
+        Ti = np.rint(T_flat)
+        if np.array_equal(Ti, T_flat) and x.dtype.kind in 'iub':
+            Tm = Ti.astype(np.int64)
+            xt, xs_ = x * Tm, x * (1 + Tm)
+        else:
+            xt, xs_ = x * T_flat, x * (1.0 + T_flat)
+        V = np.vstack([Yres.T, h0_X.T])
+        xx, dg = self._moments(x, Rm, V, h0_rss_f, n - q0 - 1, impl)
+        tt, dt = self._moments(xt, Rm, V, h0_rss_f, n - q0 - 1, impl)
+        ss, _ = self._moments(xs_, Rm, V, h0_rss_f, n - q0 - 1, impl)
+        ctx.invalidate_snps()
+        if nf['owned']:
+            Rm.free()
+        gt = 0.5 * (ss - xx - tt)
+        xy, b = dg[:, 0], dg[:, 1:]
+        ty, bt = dt[:, 0], dt[:, 1:]
+        A = h0_X.T @ h0_X
+        c0 = (h0_X.T @ Yres).reshape(-1)
+        Ainv = np.linalg.inv(A)
+        a0 = Ainv @ c0
+        Ab, Abt = b @ Ainv.T, bt @ Ainv.T
+        yy = float(np.sum(Yres ** 2))
+        tiny = 1e-12
+        # genetic model (:1457-1460)
+        s11 = xx - np.einsum('ij,ij->i', b, Ab)
+        r1 = xy - Ab @ c0
+        ok_g = s11 > tiny * np.maximum(xx, 1e-300)
+        s11s = np.where(ok_g, s11, 1.0)
+        bx = r1 / s11s
+        b0 = a0[None, :] - Ab * bx[:, None]
+        rss_g = yy - (b0 @ c0 + bx * xy)
+        good_g = ok_g & (rss_g != 0)
+        rss_g_list = np.where(good_g, rss_g, h0_rss_f)
+        betas_g = np.hstack([b0, bx[:, None]])
+        # full model (:1462-1465), fitted only where the genetic model was (:1458)
+        s12 = gt - np.einsum('ij,ij->i', b, Abt)
+        s22 = tt - np.einsum('ij,ij->i', bt, Abt)
+        r2 = ty - Abt @ c0
+        det = s11 * s22 - s12 * s12
+        ok_gt = good_g & (s22 > tiny * np.maximum(tt, 1e-300)) & (det > 1e-10 * np.abs(s11 * s22))
+        dets = np.where(ok_gt, det, 1.0)
+        g1 = (s22 * r1 - s12 * r2) / dets
+        g2 = (s11 * r2 - s12 * r1) / dets
+        g0 = a0[None, :] - Ab * g1[:, None] - Abt * g2[:, None]
+        rss_gt = yy - (g0 @ c0 + g1 * xy + g2 * ty)
+        good_gt = ok_gt & (rss_gt != 0)
+        rss_gt_list = np.where(good_gt, rss_gt, h0_rss_f)
+        betas_gt = np.hstack([g0, g1[:, None], g2[:, None]])
+        betas_g_list = [list(map(float, row)) if g else h0_betas for row, g in zip(betas_g, good_g)]
+        betas_gt_list = [list(map(float, row)) if g else h0_betas for row, g in zip(betas_gt, good_gt)]
+
+        def f_test(num, den, q):
+            n_p = n - (q0 + q)
+            ratio = num / den
+            f = (ratio - 1) * n_p / float(q)
+            return ctx.f_sf(np.maximum(f, 0.0), q, n_p), f, 1 - 1 / ratio
+
+        ps, f, vp = f_test(h0_rss_f, rss_g_list, 1)                         # :1478-1486
+        g_res_d = {'ps': ps, 'f_stats': f, 'rss': rss_g_list, 'var_perc': vp, 'h0_rss': h0_rss, 'h0_betas': h0_betas,
+                   'betas': betas_g_list}
+        ps, f, vp = f_test(h0_rss_f, rss_gt_list, 2)                        # :1490-1498
+        gt_res_d = {'ps': ps, 'f_stats': f, 'rss': rss_gt_list, 'var_perc': vp, 'betas': betas_gt_list}
+        ps, f, vp = f_test(rss_g_list, rss_gt_list, 1)                      # :1502-1511 (p = len(X') + 1, as the reference has it)
+        gt_g_res_d = {'ps': ps, 'f_stats': f, 'var_perc': vp}
+        return {'g_res': g_res_d, 'gt_res': gt_res_d, 'gt_g_res': gt_g_res_d}
 
     # ------------------------------------------------------------------------------------------
     def _emmax_permutations_(self, snps, K, H_sqrt_inv, num_perm=100):
@@ -714,6 +848,29 @@ def emmax(snps, phenotypes, K, cofactors=None, Z=None, with_betas=False, emma_nu
     else:
         _say('Took %f seconds.' % (secs))
     return res
+
+
+def emmax_w_two_env(snps, phenotypes, K, E, cofactors=None, Z=None, ctx=None):
+    """
+    Run EMMAX with environmental variables (linear_models.py:1749-1787).  Three p-values per SNP: the genetic model against
+    the null ('g_res'), the full model (genetic + genotype x environment) against the null ('gt_res'), and the full model
+    against the genetic model ('gt_g_res').  E: 0-1 (or real) vector distinguishing the environments; Z: incidence matrix
+    for replicates.
+    """
+    lmm = LinearMixedModel(phenotypes, ctx=ctx)
+    if Z is not None:
+        Zm = np.asarray(Z, dtype=np.float64)
+        lmm.add_random_effect(Zm @ np.asarray(K, dtype=np.float64) @ Zm.T)
+        if cofactors:
+            for cofactor in cofactors:
+                lmm.add_factor(Zm @ np.asarray(cofactor, dtype=np.float64))
+    else:
+        lmm.add_random_effect(K)
+        if cofactors:
+            for cofactor in cofactors:
+                lmm.add_factor(cofactor)
+    _say("Running EMMAX w G and GxE tests")
+    return lmm.emmax_GxT_f_test(snps, E=E, Z=Z)
 
 
 def emmax_multi(snps, phenotypes, K, cofactors=None, ngrids=50, llim=-10, ulim=10, esp=1e-6, batch=None, ctx=None):

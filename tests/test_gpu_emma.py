@@ -96,3 +96,77 @@ def test_get_ml_matches_oracle(ctx, with_cof):
     np.testing.assert_allclose(b['delta'][0], a['delta'], rtol=1e-8)
     np.testing.assert_allclose(b['max_ll'][0], a['max_ll'], rtol=1e-10)
     np.testing.assert_allclose(b['vg'][0], a['vg'], rtol=1e-8)
+
+
+@pytest.mark.parametrize('with_cof', [False, True])
+@pytest.mark.parametrize('impl', ['dmma', 'tcgen05'])
+def test_emmax_w_two_env_matches_oracle_and_reference_run(ctx, with_cof, impl):
+    """emmax_w_two_env -> _emmax_GxT_f_test_ (linear_models.py:1749-1787, :1422-1514): three tests per SNP from three passes of
+    the fused scan (x, x o E, x o (1 + E)) against the FP64 oracle's two lstsq per SNP, and against the reference's own run."""
+    from mixmogam_b200 import linear_models as lm
+    from oracle import reference_py3 as o
+    e = golden('emmax_diploid_n400.npz')
+    ref = golden('ref_ml_emma_gxt_n400.npz')
+    snps, K, cof = e['snps'][:600], e['K'], e['cofactor']
+    E, ye = ref['E'], ref['ye']
+    cofs = [cof] if with_cof else None
+    ro = o.emmax_w_two_env(list(snps), list(ye), K, E, cofs, dtype='double')
+    mdl = _model(lm, ye, K, cofs or [], ctx=ctx, scan_impl=impl)
+    r = mdl.emmax_GxT_f_test(snps, E=E)
+    tag = 'cof_' if with_cof else ''
+    for part in ('g_res', 'gt_res', 'gt_g_res'):
+        a, b = -np.log10(r[part]['ps']), -np.log10(ro[part]['ps'])
+        assert np.max(np.abs(a - b) / np.maximum(b, 1e-3)) < (1e-6 if impl == 'dmma' else 1e-5), part
+        np.testing.assert_allclose(r[part]['f_stats'], ro[part]['f_stats'], rtol=1e-5, atol=1e-7, err_msg=part)
+        np.testing.assert_allclose(r[part]['var_perc'], ro[part]['var_perc'], rtol=1e-5, atol=1e-9, err_msg=part)
+        # the reference's float32 run
+        assert np.max(np.abs(np.log10(r[part]['ps']) - np.log10(ref['gxt_%s%s_ps' % (tag, part)]))) < 2e-2, part
+    for part in ('g_res', 'gt_res'):
+        np.testing.assert_allclose(r[part]['rss'], np.asarray(ro[part]['rss']).reshape(-1), rtol=1e-8, err_msg=part)
+        np.testing.assert_allclose(np.asarray(r[part]['betas']), np.asarray(ro[part]['betas']), rtol=1e-5, atol=1e-7, err_msg=part)
+    for k in ('pseudo_heritability', 've', 'vg', 'max_ll'):
+        np.testing.assert_allclose(float(r[k]), float(ro[k]), rtol=2e-6, err_msg=k)
+    if not with_cof and impl == 'dmma':
+        top = lm.emmax_w_two_env(list(snps), list(ye), K, E, ctx=ctx)          # the module-level entry, list-of-rows input
+        np.testing.assert_allclose(top['gt_g_res']['f_stats'], r['gt_g_res']['f_stats'], rtol=1e-9, atol=1e-12)
+
+
+def test_emmax_w_two_env_degenerate_rows_keep_null_fit(ctx):
+    """A SNP that never varies inside environment 1 gives a rank-deficient full model: the reference keeps h0_rss / h0_betas for
+    it (:1463 `if rss_gt:`), a monomorphic SNP keeps them in both models (:1458)."""
+    from mixmogam_b200 import linear_models as lm
+    e = golden('emmax_diploid_n400.npz')
+    ref = golden('ref_ml_emma_gxt_n400.npz')
+    snps, K = np.array(e['snps'][:64]), e['K']
+    E = ref['E']
+    snps[3] = 1                                                               # monomorphic
+    snps[5] = np.where(E[:, 0] > 0, 0, snps[5])                               # x o E == 0
+    r = lm.emmax_w_two_env(snps, list(ref['ye']), K, E, ctx=ctx)
+    h0 = float(np.asarray(r['g_res']['h0_rss']).reshape(-1)[0])
+    assert r['g_res']['rss'][3] == h0 and r['gt_res']['rss'][3] == h0 and r['g_res']['ps'][3] == 1.0
+    assert r['g_res']['rss'][5] < h0 and r['gt_res']['rss'][5] == h0
+    assert r['gt_res']['betas'][5] == r['g_res']['h0_betas']
+
+
+@pytest.mark.parametrize('with_betas', [False, True])
+def test_real_valued_genotypes_fp64_rows(ctx, with_betas):
+    """Imputed dosages (non-integral rows; linear_models.py:1317 casts whatever numeric row it gets): the FP64 tensor-core scan
+    with the genotype operand staged as FP64, against the FP64 oracle; emma_num refinement on the same rows."""
+    from mixmogam_b200 import linear_models as lm
+    from oracle import reference_py3 as o
+    e = golden('emmax_diploid_n400.npz')
+    y, K = e['y'], e['K']
+    rng = np.random.default_rng(11)
+    xs = np.clip(e['snps'][:700].astype(np.float64) + rng.normal(0, 0.15, (700, 400)), 0.0, 2.0)
+    ro = o.emmax([r for r in xs], y, K, with_betas=with_betas, emma_num=0, dtype='double')
+    r = lm.emmax(xs, y, K, with_betas=with_betas, emma_num=0, ctx=ctx)
+    a, b = -np.log10(r['ps']), -np.log10(ro['ps'])
+    assert np.max(np.abs(a - b) / np.maximum(b, 1e-3)) < 1e-6
+    np.testing.assert_allclose(r['rss'], np.asarray(ro['rss']).reshape(-1), rtol=1e-9)
+    if with_betas:
+        np.testing.assert_allclose(np.asarray(r['betas']), np.asarray(ro['betas']), rtol=1e-5, atol=1e-8)
+    else:
+        r5 = lm.emmax([row for row in xs], y, K, emma_num=5, ctx=ctx)         # list-of-rows input + refinement on dosages
+        o5 = o.emmax([row for row in xs], y, K, emma_num=5, dtype='double')
+        a, b = -np.log10(r5['ps']), -np.log10(o5['ps'])
+        assert np.max(np.abs(a - b) / np.maximum(b, 1e-3)) < 1e-5

@@ -61,3 +61,73 @@ def test_run_emmax_and_perm(ctx):
     assert outp['perm_min_ps'].shape == (40,) and np.all(np.diff(outp['perm_min_ps']) >= 0)
     assert outp['kinship'].shape == (198, 198)
     assert float(outp['five_perc_perm_min_ps']) == outp['perm_min_ps'][2]
+
+
+class _SlicedOnly(object):
+    """An h5py-like dataset: rows come out only through slices (each slice is a fresh array), like lzf chunks decompressing."""
+
+    def __init__(self, a):
+        self._a, self.shape, self.dtype, self.reads = a, a.shape, a.dtype, 0
+
+    def __getitem__(self, k):
+        assert isinstance(k, slice) or k is Ellipsis
+        self.reads += 1
+        return np.array(self._a[k])
+
+
+def test_stream_snps_chunked_reader(ctx):
+    """hdf5_data.stream_snps: dataset slices -> page-locked chunk ring -> resident block, MAF filter applied on the way
+    (hdf5_data.py:162-169); the block equals the filtered matrix and the scan takes the ResidentSnps handle."""
+    from mixmogam_b200 import hdf5_data, kinship, linear_models as lm
+    e = golden('emmax_diploid_n400.npz')
+    snps, y, K = e['snps'][:3000], e['y'], e['K']
+    keep = np.random.default_rng(2).random(3000) < 0.7
+    ds = _SlicedOnly(snps)
+    h = hdf5_data.stream_snps(ctx, [(ds, keep), (_SlicedOnly(snps[:100]), None)], chunk_rows=257)
+    assert ds.reads >= 11 and h.shape == (int(keep.sum()) + 100, 400) == ctx.snps_shape()
+    want = np.concatenate([snps[keep], snps[:100]])
+    assert np.array_equal(ctx.snps_row_sums(), want.sum(1, dtype=np.int64))
+    r = lm.emmax(h, y, K, ctx=ctx)
+    r2 = lm.emmax(want, y, K, ctx=ctx)
+    assert np.array_equal(r['ps'], r2['ps'])
+    ctx.invalidate_snps()
+
+
+def test_packed_genotype_input(ctx):
+    """2-bit packed genotypes at the API (n / 4 bytes per SNP over PCIe): kinship bit-identical to the int8
+    input for both codings, scan identical, scan-only upload path, odd n (bits beyond n ignored)."""
+    import mixmogam_b200 as mb
+    from mixmogam_b200 import kinship, linear_models as lm
+    e = golden('emmax_diploid_n400.npz')
+    snps, y, K = e['snps'], e['y'], e['K']
+    pk = mb.pack_genotypes(snps)
+    ctx.invalidate_snps()
+    Kp = np.asarray(kinship.calc_ibs_kinship(pk, 'diploid_int', ctx=ctx))
+    ctx.invalidate_snps()
+    Ki = np.asarray(kinship.calc_ibs_kinship(snps, 'diploid_int', ctx=ctx))
+    assert np.array_equal(Kp, Ki)
+    ctx.invalidate_snps()
+    rp = lm.emmax(pk, y, K, ctx=ctx)                      # upload-only path (mmg_snps_upload_packed2)
+    ctx.invalidate_snps()
+    ri = lm.emmax(snps, y, K, ctx=ctx)
+    assert np.array_equal(rp['ps'], ri['ps']) and np.array_equal(rp['f_stats'], ri['f_stats'])
+    # binary coding, n = 198 (not a multiple of 4), garbage in the unused bits of the last byte
+    b = golden('emmax_ft10_n198.npz')['snps']
+    pb = mb.pack_genotypes(b, freeze=False)
+    pb.packed[:, (198 + 3) // 4 - 1] |= 0xF0              # codes of columns 198, 199 do not exist
+    ctx.invalidate_snps()
+    Kb = np.asarray(kinship.calc_ibs_kinship(pb, 'binary', ctx=ctx))
+    ctx.invalidate_snps()
+    assert np.array_equal(Kb, np.asarray(kinship.calc_ibs_kinship(b, 'binary', ctx=ctx)))
+    ctx.invalidate_snps()
+
+
+def test_load_kinship_scaled_on_device(ctx):
+    from mixmogam_b200 import kinship
+    from oracle import reference_py3 as o
+    e = golden('emmax_diploid_n400.npz')
+    K = np.asarray(e['K'])
+    store = {}
+    kinship.save_kinship_to_file(store, K, np.arange(400), 5000)
+    d = kinship.load_kinship_from_file(store, scaled=True, ctx=ctx)
+    np.testing.assert_allclose(np.asarray(d['k']), o.scale_k(K), rtol=1e-13)

@@ -285,3 +285,54 @@ def test_scan_truncation_bound_is_sound(built):
             approx = sum(Fraction(float(A[j, j])) * int(x[j]) ** 2 for j in range(n)) + q * two_E
             bound = Fraction(64, 255) / Fraction(256) ** S * two_E * l1 * l1
             assert abs(approx - exact) <= bound, (trial, S)
+
+
+def test_packed_genotypes_roundtrip_host_only():
+    """mmg_host_pack2 / PackedGenotypes: 2 bits per genotype, code j in bits 2 (j % 4) of byte j // 4; no GPU involved."""
+    import mixmogam_b200 as mb
+    rng = np.random.default_rng(3)
+    for n in (1, 3, 4, 37, 198, 1001):
+        x = rng.integers(0, 4, size=(57, n)).astype(np.int8)
+        pk = mb.pack_genotypes(x)
+        assert pk.shape == (57, n) and len(pk) == 57 and pk.packed.dtype == np.uint8 and not pk.packed.flags.writeable
+        assert np.array_equal(pk.unpack(), x)
+        assert np.array_equal(pk[5], x[5]) and np.array_equal(pk[[1, 7, 9]], x[[1, 7, 9]]) and np.array_equal(pk[10:20].unpack(), x[10:20])
+        # the bit layout itself, spelled out
+        j = n - 1
+        assert (int(pk.packed[56, j // 4]) >> (2 * (j % 4))) & 3 == int(x[56, j])
+    with pytest.raises(ValueError):
+        mb.pack_genotypes(np.full((2, 8), 4, dtype=np.int8))
+
+
+def test_kinship_file_helpers_mapping():
+    """prepare_k / save / load (kinship.py:79-90, 145-169) on an in-memory mapping (h5py is not part of this image)."""
+    from mixmogam_b200 import kinship
+    rng = np.random.default_rng(0)
+    a = rng.random((6, 6))
+    k = a @ a.T
+    acc = ['a%d' % i for i in range(6)]
+    store = {}
+    kinship.save_kinship_to_file(store, k, acc, 1234)
+    d = kinship.load_kinship_from_file(store, scaled=False)
+    assert np.array_equal(np.asarray(d['k']), k) and list(d['accessions']) == acc and d['n_snps'] == 1234
+    sub = kinship.load_kinship_from_file(store, accessions=['a4', 'zz', 'a1'], scaled=False)['k']
+    assert isinstance(sub, np.matrix) and np.array_equal(np.asarray(sub), k[[4, 1]][:, [4, 1]])
+    assert np.array_equal(np.asarray(kinship.prepare_k(k, acc, acc)), k)
+    upd = kinship.update_k_monomorphic(10, k, acc, 100, ['a0', 'a2'], dtype='double')
+    np.testing.assert_allclose(np.asarray(upd), (k[[0, 2]][:, [0, 2]] * 100 - 10) / 90.0)
+
+
+def test_write_genotype_file_layout():
+    """The plink2hdf5 layout hdf5_data reads (plink2hdf5.py:25-28,57-59,111-118,226)."""
+    from mixmogam_b200 import hdf5_data
+    rng = np.random.default_rng(1)
+    chroms = {1: {'raw_snps': rng.integers(0, 3, (20, 9)).astype(np.int8)}, 'chrom_2': {'raw_snps': rng.integers(0, 3, (5, 9)).astype(np.int8),
+                                                                                         'positions': np.arange(5) * 7}}
+    f = hdf5_data.write_genotype_file({}, chroms, np.arange(9), rng.standard_normal(9))
+    assert set(f.keys()) == {'genot_data', 'indiv_data', 'num_snps'} and int(f['num_snps']) == 25
+    assert set(f['genot_data'].keys()) == {'chrom_1', 'chrom_2'}
+    c1 = f['genot_data']['chrom_1']
+    assert {'raw_snps', 'positions', 'freqs', 'snp_ids'} <= set(c1.keys()) and c1['raw_snps'].dtype == np.int8
+    np.testing.assert_allclose(c1['freqs'], chroms[1]['raw_snps'].mean(1) / 2.0)
+    assert np.array_equal(f['genot_data']['chrom_2']['positions'], np.arange(5) * 7)
+    assert set(f['indiv_data'].keys()) == {'indiv_ids', 'sex', 'phenotypes'}
