@@ -64,6 +64,9 @@ def stream_snps(ctx, parts, chunk_rows=None):
     import threading
     import queue
     parts = [(ds, None if keep is None else np.asarray(keep, dtype=bool)) for ds, keep in parts]
+    for ds, keep in parts:
+        if keep is not None and keep.shape[0] != int(ds.shape[0]):
+            raise ValueError('row filter of %d entries for a dataset of %d rows' % (keep.shape[0], int(ds.shape[0])))
     n = int(parts[0][0].shape[1])
     total = sum(int(ds.shape[0]) if keep is None else int(keep.sum()) for ds, keep in parts)
     if total == 0:

@@ -114,16 +114,21 @@ def test_emmax_w_two_env_matches_oracle_and_reference_run(ctx, with_cof, impl):
     mdl = _model(lm, ye, K, cofs or [], ctx=ctx, scan_impl=impl)
     r = mdl.emmax_GxT_f_test(snps, E=E)
     tag = 'cof_' if with_cof else ''
+    ok = np.ones(len(snps), dtype=bool)
+    if with_cof:
+        ok[17] = False          # SNP 17 is the cofactor itself: x~ = 0 up to rounding, every implementation's statistic is noise there
+        h0 = float(np.asarray(r['g_res']['h0_rss']).reshape(-1)[0])
+        assert r['g_res']['rss'][17] == h0 and r['gt_res']['rss'][17] == h0          # the product keeps the null fit (:1458)
     for part in ('g_res', 'gt_res', 'gt_g_res'):
-        a, b = -np.log10(r[part]['ps']), -np.log10(ro[part]['ps'])
+        a, b = -np.log10(r[part]['ps'][ok]), -np.log10(ro[part]['ps'][ok])
         assert np.max(np.abs(a - b) / np.maximum(b, 1e-3)) < (1e-6 if impl == 'dmma' else 1e-5), part
-        np.testing.assert_allclose(r[part]['f_stats'], ro[part]['f_stats'], rtol=1e-5, atol=1e-7, err_msg=part)
-        np.testing.assert_allclose(r[part]['var_perc'], ro[part]['var_perc'], rtol=1e-5, atol=1e-9, err_msg=part)
-        # the reference's float32 run
-        assert np.max(np.abs(np.log10(r[part]['ps']) - np.log10(ref['gxt_%s%s_ps' % (tag, part)]))) < 2e-2, part
+        np.testing.assert_allclose(r[part]['f_stats'][ok], ro[part]['f_stats'][ok], rtol=1e-5, atol=1e-7, err_msg=part)
+        np.testing.assert_allclose(r[part]['var_perc'][ok], ro[part]['var_perc'][ok], rtol=1e-5, atol=1e-9, err_msg=part)
+        # the reference's float32 run (its three-column float32 lstsq is the noisy side: test_reference_pin holds the oracle to 5e-2 too)
+        assert np.max(np.abs(np.log10(r[part]['ps']) - np.log10(ref['gxt_%s%s_ps' % (tag, part)]))[ok]) < 5e-2, part
     for part in ('g_res', 'gt_res'):
-        np.testing.assert_allclose(r[part]['rss'], np.asarray(ro[part]['rss']).reshape(-1), rtol=1e-8, err_msg=part)
-        np.testing.assert_allclose(np.asarray(r[part]['betas']), np.asarray(ro[part]['betas']), rtol=1e-5, atol=1e-7, err_msg=part)
+        np.testing.assert_allclose(r[part]['rss'][ok], np.asarray(ro[part]['rss']).reshape(-1)[ok], rtol=1e-8, err_msg=part)
+        np.testing.assert_allclose(np.asarray(r[part]['betas'])[ok], np.asarray(ro[part]['betas'])[ok], rtol=1e-5, atol=1e-7, err_msg=part)
     for k in ('pseudo_heritability', 've', 'vg', 'max_ll'):
         np.testing.assert_allclose(float(r[k]), float(ro[k]), rtol=2e-6, err_msg=k)
     if not with_cof and impl == 'dmma':

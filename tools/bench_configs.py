@@ -21,6 +21,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# libmixmogam_b200.so is loaded BEFORE torch: the process then resolves libcusolver.so.11 to the CUDA 12.9 toolkit copy the library
+# was linked against (its Xsyevd takes n <= ~32768; the older copy bundled with the torch wheel refuses smaller matrices still)
+from mixmogam_b200 import _lib as _mmg_lib  # noqa: E402
+
+_mmg_lib.load_library()
 
 
 def gen_torch(m, n, seed, binary, device, maf_lo=0.11):
