@@ -250,6 +250,19 @@ int mmg_emmax_scan_quad_dev(mmg_ctx* ctx, mmg_mat A, int packed, double a_err, m
 int mmg_emmax_scan_multi_f64(mmg_ctx* ctx, const mmg_mat* R, int T, const double* V, const double* h0_rss, double n_p,
                              int64_t snp_begin, int64_t snp_count,
                              double* ps, double* f_stats, double* rss, double* var_perc, double* xx);
+/* Phenotype-batched scan with SHARED work: the T phenotypes are measured on the same individuals, so they share
+ * the eigenbasis U of the kinship (mmg_mat n x n, eigenvectors as ROWS, linear_models.py:596) and differ in delta_t only.
+ * One rotation g = U x per SNP (int8 tensor cores, exact digit planes of U) serves all of them; per phenotype
+ *     x~.x~ = sum_k W[t][k] g_k^2 - sum_j (x.c_tj)^2        x~.y~ = x.v_t
+ * with W[t][k] = 1 / (lambda_k + delta_t) (host, [T x n]) and Ext (mmg_mat [T (1 + q0) x n]) holding, for each phenotype,
+ * v_t = U' diag(d_t) y~res_t followed by the q0 rows c_tj = U' diag(d_t) Q_t[:, j] (d_t = sqrt(W[t]), Q_t an orthonormal basis
+ * of the rotated fixed effects, :1300).  Cost: one rotation + O(n T) per SNP instead of T rotations.  The number of digit
+ * planes is raised until the certified bounds hold (MMG_TC_TOL, default 1e-7 relative on x~.x~); SNPs collinear with the
+ * fixed effects keep the null fit.  Outputs are [T x snp_count] (any may be NULL); info (optional, 5 doubles): planes used,
+ * certified bound on x~.x~, bound on x~.y~ (t-statistic scale), rotation ms, contraction ms. */
+int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat U, mmg_mat Ext, const double* W, int T, int q0, const double* h0_rss,
+                              double n_p, int64_t snp_begin, int64_t snp_count,
+                              double* ps, double* f_stats, double* rss, double* var_perc, double* xx, double* info);
 /* _emmax_permutations_ inner loop (linear_models.py:1157-1164): with centred SNPs x_c = x - mean(x),
  * x~ = R x_c, for each permuted phenotype column W[:,p] (already rotated back: W = R' Ys, [n x P]):
  *     ratio[p] = max over SNPs of (x_c.W[:,p])^2 / (x~.x~)

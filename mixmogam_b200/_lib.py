@@ -97,6 +97,7 @@ SIGNATURES = {
     'mmg_quad_form_tiles': (C.c_int, [_c_ctx, _i64, _i64, _i64, _i64, _dp]),
     'mmg_emmax_scan_quad_dev': (C.c_int, [_c_ctx, _i64, C.c_int, C.c_double, _i64, C.c_double, C.c_double, _i64, _i64, _i64]),
     'mmg_emmax_scan_multi_f64': (C.c_int, [_c_ctx, _vp, C.c_int, _vp, _vp, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_emmax_scan_shared_f64': (C.c_int, [_c_ctx, _i64, _i64, _vp, C.c_int, C.c_int, _vp, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_perm_scan_f64': (C.c_int, [_c_ctx, _i64, _i64, C.c_int, C.c_int, _i64, _i64, _vp]),
     'mmg_f_sf_f64': (C.c_int, [_c_ctx, _vp, _i64, C.c_double, C.c_double, _vp]),
 }
@@ -783,6 +784,25 @@ class Context(object):
         self._ck(self.lib.mmg_emmax_scan_multi_f64(self.h, _ptr(handles), T, _ptr(V), _ptr(h0), float(n_p), snp_begin, snp_count,
                                                    _ptr(out.get('ps')), _ptr(out.get('f_stats')), _ptr(out.get('rss')),
                                                    _ptr(out.get('var_perc')), _ptr(out.get('xx'))))
+        return out
+
+    def emmax_scan_shared(self, U, Ext, W, q0, h0_rss, n_p, snp_begin=0, snp_count=None, want=('ps', 'f_stats', 'rss', 'var_perc')):
+        """T phenotypes on one eigenbasis with ONE rotation per SNP (mmg_emmax_scan_shared_f64): U = eig_L vectors (rows),
+        Ext [T (1 + q0) x n] = per phenotype v_t and the q0 rows c_tj, W [T x n] = 1 / (lambda + delta_t).
+        Returns a dict of [T x snp_count] arrays plus 'info' (planes, certified bounds, kernel ms)."""
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        T = W.shape[0]
+        assert W.shape == (T, n) and Ext.shape == (T * (1 + q0), n) and U.shape == (n, n), (W.shape, Ext.shape, U.shape)
+        h0 = np.ascontiguousarray(np.asarray(h0_rss, dtype=np.float64).reshape(T))
+        out = {k: result_empty((T, snp_count)) for k in want}
+        info = np.zeros(5)
+        self._ck(self.lib.mmg_emmax_scan_shared_f64(self.h, U.handle, Ext.handle, _ptr(W), T, int(q0), _ptr(h0), float(n_p), snp_begin, snp_count,
+                                                    _ptr(out.get('ps')), _ptr(out.get('f_stats')), _ptr(out.get('rss')),
+                                                    _ptr(out.get('var_perc')), _ptr(out.get('xx')), _ptr(info)))
+        out['info'] = {'planes': int(info[0]), 'rho_xx': info[1], 'rho_xy': info[2], 'rotation_ms': info[3], 'contraction_ms': info[4]}
         return out
 
     def emmax_perm_scan(self, R, Wt, ratio, centre=True, impl=IMPL_AUTO, snp_begin=0, snp_count=None):

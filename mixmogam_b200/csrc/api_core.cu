@@ -10,6 +10,7 @@ namespace mmg {
 thread_local std::string g_create_error;
 void kinship_init_attrs();
 void scan_init_attrs();
+void multi_init_attrs();
 }  // namespace mmg
 
 using namespace mmg;
@@ -61,6 +62,7 @@ int mmg_create(int device, mmg_ctx** out) {
     // opt in to large dynamic shared memory once (per translation unit: each knows its own kernel instances)
     kinship_init_attrs();
     scan_init_attrs();
+    multi_init_attrs();
     *out = ctx;
     return MMG_OK;
 }

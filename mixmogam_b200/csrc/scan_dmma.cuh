@@ -59,14 +59,19 @@ struct ScanDmmaParams {
     // PERM mode
     const double* xx_in;     // [row_count] x~.x~ of the centred SNPs
     unsigned long long* ratio_max;   // [n_out_pad] bit patterns of non-negative doubles
+    // SD_MODE_SQUARE_STORE: C[s][k'] = sum_i X[s][i]^2 R[k'][i] is stored, not reduced (scan_shared.cuh: the contraction of the
+    // squared rotated genotypes with the per-phenotype weights)
+    double* cstore;          // [row_count x ldc]
+    int64_t ldc;
 };
+constexpr int SD_MODE_SCAN = 0, SD_MODE_SQUARE_STORE = 1;
 
 __device__ __forceinline__ double i8_to_f64(int v) {
     // exact int -> double without the conversion pipe: 2^52 + 2^31 + v has v ^ 0x80000000 in its low word
     return __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)v)) - 4503601774854144.0;
 }
 
-template <bool PERM, typename XT = int8_t>
+template <bool PERM, typename XT = int8_t, int MODE = SD_MODE_SCAN>
 static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const ScanDmmaParams prm) {
     constexpr bool REAL = sizeof(XT) == 8;
     constexpr int SD_STAGES = SdShape<XT>::STAGES, SD_A_STAGE = SdShape<XT>::A_STAGE, SD_STAGE_BYTES = SdShape<XT>::A_STAGE + SD_B_STAGE;
@@ -169,6 +174,7 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
                     double a;
                     if constexpr (REAL) {
                         a = reinterpret_cast<const double*>(sa)[(wm * 64 + mi * 8 + lr) * SD_AD_PITCH + kk * 4 + lc];
+                        if constexpr (MODE == SD_MODE_SQUARE_STORE) a *= a;
                     } else {
                         const int v = (int)(int8_t)((aw[mi][kk] >> (8 * lc)) & 0xffu);
                         a = i8_to_f64(v);
@@ -184,7 +190,16 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
                     const int col = nt * SD_BN + wn * 32 + ni * 8 + 2 * lc;
-                    if (!PERM) {
+                    if constexpr (MODE == SD_MODE_SQUARE_STORE) {
+#pragma unroll
+                        for (int mi = 0; mi < 8; ++mi) {
+                            const int64_t r = row0 + wm * 64 + mi * 8 + lr;
+                            if (r < prm.row_count)
+                                *reinterpret_cast<double2*>(prm.cstore + r * prm.ldc + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                            acc[mi][ni][0] = 0.0;
+                            acc[mi][ni][1] = 0.0;
+                        }
+                    } else if (!PERM) {
                         const double y0 = prm.y[col], y1 = prm.y[col + 1];
                         double r10 = 0.0, r11 = 0.0;
                         if (prm.mu != nullptr) { r10 = prm.r1[col]; r11 = prm.r1[col + 1]; }
@@ -227,7 +242,7 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
         }
         cp_async_wait<0>();
 
-        if (!PERM) {
+        if (!PERM && MODE == SD_MODE_SCAN) {
             // ---- row reduction: 4 lanes per row inside the warp, then the 4 warps along N ----
 #pragma unroll
             for (int mi = 0; mi < 8; ++mi) {

@@ -873,17 +873,20 @@ def emmax_w_two_env(snps, phenotypes, K, E, cofactors=None, Z=None, ctx=None):
     return lmm.emmax_GxT_f_test(snps, E=E, Z=Z)
 
 
-def emmax_multi(snps, phenotypes, K, cofactors=None, ngrids=50, llim=-10, ulim=10, esp=1e-6, batch=None, ctx=None):
+def emmax_multi(snps, phenotypes, K, cofactors=None, ngrids=50, llim=-10, ulim=10, esp=1e-6, batch=None, ctx=None, shared=None):
     """
     EMMAX for T phenotypes measured on the same individuals (BASELINE.json configs[2]: "all phenotypes scanned
     against one kinship eigenbasis").  Equivalent to [emmax(snps, y, K, cofactors) for y in phenotypes]
     (linear_models.py:1790-1816, emma_num=0) with the work shared:
       * K is scaled and eigendecomposed once (eig_L and eig_R do not depend on the phenotype);
       * the REML grid + secant refinement of all T phenotypes is one launch pair (mmg_reml_f64, T rows);
-      * the T scans -- each phenotype has its own delta, hence its own rotation -- are ONE int8 tensor-core launch
-        in which every 128-SNP genotype block is reused by the digit planes of all T rotations.
-    `phenotypes` is a sequence of T length-n vectors.  Returns a list of T result dicts with emmax()'s keys.
-    `batch` bounds the number of phenotypes per launch (default: sized from free HBM).
+      * the scan rotates every SNP ONCE, g = U_L x on the int8 tensor cores, for all phenotypes (mmg_emmax_scan_shared_f64):
+        per phenotype only sum_k g_k^2 / (lambda_k + delta_t) (an FP64 tensor-core contraction, O(n) per SNP and phenotype) and
+        the dot products with v_t = R_t' y~_t and the projected-out fixed effects remain -- one rotation + O(n T) per SNP
+        instead of T rotations; the null fits need U_L [X, Y] (one skinny GEMM) and no per-phenotype n x n matrix.
+    `shared=False` (default for T < 4) scans each phenotype with its own rotation R_t in one launch of the quadratic-form
+    kernel instead.  `phenotypes` is a sequence of T length-n vectors.  Returns a list of T result dicts with emmax()'s keys.
+    `batch` bounds the number of phenotypes per launch.
     """
     Y = np.asarray(phenotypes, dtype=np.float64)
     if Y.ndim != 2:
@@ -908,16 +911,65 @@ def emmax_multi(snps, phenotypes, K, cofactors=None, ngrids=50, llim=-10, ulim=1
     m_g = ngrids + 1
     deltas = np.exp((np.arange(m_g, dtype=np.float64) / ngrids) * (ulim - llim) + llim)
     r = ctx.reml(eig_vals, sq_etas.T, deltas, esp)                            # :802-891, T phenotypes at once
+    if _lib.real_valued(snps) is not None:
+        raise TypeError('emmax_multi scans integer genotype codes (dosages: call emmax per phenotype)')
     num_snps, n_lines = ctx.ensure_snps(snps)
     if n_lines != n:
         raise ValueError('SNP length %d does not match the phenotypes (%d)' % (n_lines, n))
     UL = ctx.to_device(eig_L['vectors'])
+    if shared is None:
+        shared = T >= 4 and os.environ.get('MMG_MULTI_SHARED', '1') != '0'
+
+    def meta_of(t, delta, h0_rss, h0_betas):
+        vg = float(np.sum(sq_etas[:, t]) * np.sum(1.0 / (eig_vals + delta)) / p)          # :894-896
+        return {'h0_rss': h0_rss, 'h0_betas': list(map(float, np.asarray(h0_betas).reshape(-1))),
+                'pseudo_heritability': 1.0 / (1 + delta), 'vg': vg, 've': vg * delta, 'max_ll': float(r['ll'][t]), 'delta': delta}
+
+    results = []
+    if shared:
+        XYd = DeviceMatrix.from_host(ctx, np.hstack([X, Y.T]))
+        UXY = ctx.gemm(UL, XYd).download()                                   # U_L [X, Y]: H_t [X, y_t] = diag(d_t) of its columns (:1290)
+        XYd.free()
+        UX, UY = UXY[:, :q0], UXY[:, q0:]
+        if batch is None:
+            batch = max(1, min(T, int(2.0e9 / (8.0 * max(num_snps, 1)))))    # <= ~2 GB per output array
+        for t0 in range(0, T, batch):
+            ts = list(range(t0, min(T, t0 + batch)))
+            Z = np.empty((n, len(ts) * (1 + q0)))
+            W = np.empty((len(ts), n))
+            h0, meta = [], []
+            for i, t in enumerate(ts):
+                delta = float(r['delta'][t])
+                w = 1.0 / (eigL_vals + delta)
+                d = np.sqrt(w)                                               # :898
+                h0_X = d[:, None] * UX
+                y_t = (d * UY[:, t]).reshape(-1, 1)
+                (h0_betas, h0_rss, h0_rank, h0_s) = np.linalg.lstsq(h0_X, y_t, rcond=None)      # :1292
+                Yres = y_t - h0_X @ h0_betas
+                if np.size(h0_rss) == 0:
+                    h0_rss = np.array([np.sum(Yres ** 2)])
+                Q = np.linalg.qr(h0_X)[0]                                    # :1300
+                Z[:, i * (1 + q0)] = d * Yres[:, 0]                          # v_t = U' diag(d_t) y~res_t
+                Z[:, i * (1 + q0) + 1:(i + 1) * (1 + q0)] = d[:, None] * Q   # c_tj = U' diag(d_t) Q_t[:, j]   (:1303)
+                W[i] = w
+                h0.append(float(np.asarray(h0_rss).reshape(-1)[0]))
+                meta.append(meta_of(t, delta, h0_rss, h0_betas))
+            Zd = DeviceMatrix.from_host(ctx, Z)
+            Ext = ctx.gemm(Zd, UL, ta=True)                                  # [len(ts) (1 + q0) x n] = Z' U_L
+            Zd.free()
+            out = ctx.emmax_scan_shared(UL, Ext, W, q0, h0, n_p)
+            Ext.free()
+            for i, md in enumerate(meta):
+                dct = {'ps': out['ps'][i], 'f_stats': out['f_stats'][i], 'rss': out['rss'][i], 'var_perc': out['var_perc'][i]}
+                dct.update(md)
+                results.append(dct)
+        return results
+
     if batch is None:
         free = ctx.device_info()['free_bytes']
         n_pad = (n + 255) // 256 * 256
         per = n * n * 8 + 7 * n_pad * n_pad + 5 * 8 * num_snps
         batch = max(1, min(T, int(0.5 * free / per)))
-    results = []
     for t0 in range(0, T, batch):
         ts = range(t0, min(T, t0 + batch))
         Rs, V, h0, meta = [], [], [], []
@@ -930,10 +982,7 @@ def emmax_multi(snps, phenotypes, K, cofactors=None, ngrids=50, llim=-10, ulim=1
             Rs.append(nf['R'])
             V.append(nf['Yres'].reshape(-1))
             h0.append(float(np.asarray(nf['h0_rss']).reshape(-1)[0]))
-            vg = float(np.sum(sq_etas[:, t]) * np.sum(1.0 / (eig_vals + delta)) / p)      # :894-896
-            meta.append({'h0_rss': nf['h0_rss'], 'h0_betas': list(map(float, np.asarray(nf['h0_betas']).reshape(-1))),
-                         'pseudo_heritability': 1.0 / (1 + delta), 'vg': vg, 've': vg * delta, 'max_ll': float(r['ll'][t]),
-                         'delta': delta})
+            meta.append(meta_of(t, delta, nf['h0_rss'], nf['h0_betas']))
         out = ctx.emmax_scan_multi(Rs, np.asarray(V), h0, n_p)
         for Rm in Rs:
             Rm.free()

@@ -204,8 +204,10 @@ def test_permutation_scan_tcgen05_matches_dmma(ctx, n, m, P):
     np.testing.assert_allclose(rc, np.max((xt @ Ys) ** 2 / np.sum(xt * xt, axis=1)[:, None], axis=0), rtol=1e-8)
 
 
-def test_emmax_multi_matches_single_and_oracle(ctx):
-    """Phenotype-batched scan (configs[2]): T phenotypes, one eigenbasis, one launch == T independent emmax() calls."""
+@pytest.mark.parametrize('shared', [True, False])
+def test_emmax_multi_matches_single_and_oracle(ctx, shared):
+    """Phenotype-batched scan (configs[2]): T phenotypes, one eigenbasis == T independent emmax() calls.  shared=True: ONE
+    rotation g = U x per SNP for all phenotypes (mmg_emmax_scan_shared_f64); shared=False: T rotations in one launch."""
     from mixmogam_b200 import linear_models as lm
     from oracle import reference_py3 as o
     g = golden('emmax_diploid_n400.npz')
@@ -214,27 +216,70 @@ def test_emmax_multi_matches_single_and_oracle(ctx):
     Y = [g['y']] + [o.synth_phenotype(snps, K, seed=100 + t, h2_poly=h) for t, h in enumerate((0.0, 0.3, 0.8, 0.5))]
     Y.append(rng.standard_normal(400))
     ctx.invalidate_snps()
-    res = lm.emmax_multi(snps, Y, K)
+    res = lm.emmax_multi(snps, Y, K, shared=shared)
     assert len(res) == len(Y)
+    if shared:
+        S, rho = ctx.last_scan_info()
+        assert 4 <= S <= 7 and 0.0 < rho <= 1e-7                 # the certified bound of the rotation's digit planes
     for t, y in enumerate(Y):
         single = lm.emmax(snps, y, K, scan_impl='tcgen05')
-        # same kernels; the only difference is cuBLAS gemm vs gemv rounding in etas = U_R Y (delta moves by ~1e-13)
-        np.testing.assert_allclose(res[t]['ps'], single['ps'], rtol=1e-9, atol=0)
-        np.testing.assert_allclose(res[t]['rss'], single['rss'], rtol=1e-10)
+        # shared=False: same kernels, the only difference is cuBLAS gemm vs gemv rounding in etas = U_R Y (delta moves by ~1e-13);
+        # shared=True: a different arithmetic path (rotation in the eigenbasis), held to the north-star tolerance
+        if shared:
+            assert neglog10_rel_err(res[t]['ps'], single['ps']) < 1e-6
+            np.testing.assert_allclose(res[t]['rss'], single['rss'], rtol=1e-7)
+            np.testing.assert_allclose(res[t]['f_stats'], single['f_stats'], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(res[t]['var_perc'], single['var_perc'], rtol=1e-6, atol=1e-12)
+        else:
+            np.testing.assert_allclose(res[t]['ps'], single['ps'], rtol=1e-9, atol=0)
+            np.testing.assert_allclose(res[t]['rss'], single['rss'], rtol=1e-10)
         for k in ('pseudo_heritability', 'vg', 've', 'max_ll'):
             np.testing.assert_allclose(res[t][k], single[k], rtol=1e-9)
         np.testing.assert_allclose(res[t]['h0_betas'], single['h0_betas'], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(np.asarray(res[t]['h0_rss']).reshape(-1), np.asarray(single['h0_rss']).reshape(-1), rtol=1e-9)
         if t in (0, 2, 5):
             ro = o.emmax(list(snps), y, K, dtype='double')
             assert neglog10_rel_err(res[t]['ps'], ro['ps']) < 1e-6
             assert abs(res[t]['pseudo_heritability'] - ro['pseudo_heritability']) < 1e-8
     # with a cofactor and a batch size that does not divide T
     cof = g['cofactor']
-    res2 = lm.emmax_multi(snps, Y[:3], K, cofactors=[cof], batch=2)
+    res2 = lm.emmax_multi(snps, Y[:3], K, cofactors=[cof], batch=2, shared=shared)
     ok = np.arange(len(snps)) != 17
     for t in range(3):
         single = lm.emmax(snps, Y[t], K, cofactors=[cof], scan_impl='tcgen05')
-        np.testing.assert_allclose(res2[t]['ps'][ok], single['ps'][ok], rtol=1e-9)
+        if shared:
+            assert neglog10_rel_err(res2[t]['ps'][ok], single['ps'][ok]) < 1e-6
+            assert res2[t]['ps'][17] == 1.0 and res2[t]['rss'][17] == float(np.asarray(res2[t]['h0_rss']).reshape(-1)[0])   # collinear SNP: null fit
+        else:
+            np.testing.assert_allclose(res2[t]['ps'][ok], single['ps'][ok], rtol=1e-9)
+
+
+def test_emmax_multi_shared_many_phenotypes_ragged(ctx, monkeypatch):
+    """Shared-rotation batch at a size with several column tiles, K parts and SNP chunks: T = 37 phenotypes (two 32-row blocks
+    of extra basis rows), n = 1100 (K = 9 blocks of 128, split in 2 parts), ragged last SNP group, 3 chunks; against the
+    per-phenotype int8 scan and the FP64 oracle."""
+    from mixmogam_b200 import kinship, linear_models as lm
+    from oracle import reference_py3 as o
+    n, m, T = 1100, 9000 + 77, 37
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=78)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int')
+    Y = [o.synth_phenotype(snps, np.asarray(K), seed=200 + t, h2_poly=(t % 5) / 5.0) for t in range(T)]
+    monkeypatch.setenv('MMG_SHARED_KSPLIT', '2')
+    monkeypatch.setenv('MMG_SHARED_CHUNK', '4096')
+    res = lm.emmax_multi(snps, Y, K)
+    assert ctx.last_scan_info()[1] <= 1e-7
+    for t in (0, 7, 36):
+        single = lm.emmax(snps, Y[t], K, scan_impl='tcgen05')
+        assert neglog10_rel_err(res[t]['ps'], single['ps']) < 1e-6
+    ro = o.emmax(list(snps[:1500]), Y[36], np.asarray(K), dtype='double')
+    assert neglog10_rel_err(res[36]['ps'][:1500], ro['ps']) < 1e-6
+    for cs in ('1', '4'):
+        monkeypatch.setenv('MMG_SHARED_CLUSTER', cs)
+        r2 = lm.emmax_multi(snps, Y[:5], K)
+        for t in range(5):
+            np.testing.assert_array_equal(r2[t]['ps'], res[t]['ps'])          # exact integer plane sums: the schedule cannot change a bit
+    ctx.invalidate_snps()
 
 
 @pytest.mark.parametrize('sched,panel', [('panel', '8'), ('panel', '6'), ('pair', '8'), ('pair128', '10'), ('n128', '8'), ('table', '8')])
