@@ -803,6 +803,7 @@ class Context(object):
                                                     _ptr(out.get('ps')), _ptr(out.get('f_stats')), _ptr(out.get('rss')),
                                                     _ptr(out.get('var_perc')), _ptr(out.get('xx')), _ptr(info)))
         out['info'] = {'planes': int(info[0]), 'rho_xx': info[1], 'rho_xy': info[2], 'rotation_ms': info[3], 'contraction_ms': info[4]}
+        self.last_shared_info = out['info']
         return out
 
     def emmax_perm_scan(self, R, Wt, ratio, centre=True, impl=IMPL_AUTO, snp_begin=0, snp_count=None):

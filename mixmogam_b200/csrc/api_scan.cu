@@ -22,7 +22,7 @@ static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensor
     cfg.blockDim = dim3(QP_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS;
     attr[0].val.clusterDim.y = 1;
@@ -40,7 +40,23 @@ static int launch_scan_quad(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensor
     const int clusters = std::max(1, std::min(cgroups, max_clusters));
     cfg.gridDim = dim3((unsigned)(clusters * CS));
     const uint64_t pa = env_policy("MMG_TC_HINT_A", L2_EVICT_FIRST), pb = env_policy("MMG_TC_HINT_B", L2_EVICT_LAST);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, sh, pa, pb, ep);
+    // The per-wave barrier (sh.wave_sync) spins until every CTA of the grid has arrived: the grid is launched COOPERATIVELY, so the
+    // runtime starts it only when all its CTAs can be co-resident (another kernel holding SMs -- the side-stream pre-pass, a second
+    // process under MPS -- delays the launch instead of dead-locking the spin).  A driver that refuses the cooperative cluster launch
+    // gets the scan without the barrier (correct, only more HBM traffic).
+    cudaError_t e = cudaErrorUnknown;
+    if (sh.wave_sync != nullptr && env_int("MMG_SCAN_COOP", 1) != 0) {
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, sh, pa, pb, ep);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cfg.numAttrs = 1;
+            sh.wave_sync = nullptr;
+        }
+    }
+    if (e != cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, sh, pa, pb, ep);
     ctx->launches += 1;
     if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of scan_quad_kernel<%d,%d,%d,%d> (grid %d) failed: %s", CS, PKB, STAGES,
                                       (int)PAIR, clusters * CS, cudaGetErrorString(e));

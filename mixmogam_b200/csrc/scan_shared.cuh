@@ -30,10 +30,11 @@ struct RotEpi {
         double* g;               // [rows_pad x ldg] rotated genotypes of this SNP chunk
         int64_t ldg;             // multiple of 32, >= 32 * nblocks
         int64_t row_count;       // SNPs of the chunk
-        int P;                   // digit planes
-        int nblocks;             // blocks of 32 basis rows
+        int P_u, P_e;            // digit planes of the eigenvector rows / of the extra rows (v_t, c_tj: few rows, more planes)
+        int nb_u;                // blocks of 32 eigenvector rows (the extra rows start a new block)
+        int nblocks;             // blocks of 32 basis rows in all
         double w[RS_MAX_PLANES]; // 256^-(p+1)
-        const double* rscale;    // [32 * nblocks] 2^E_r of basis row r
+        const double* rscale;    // [32 * nblocks] 2^E_r of the basis row at that position
     };
     double d[32];
     int64_t orow;
@@ -44,7 +45,18 @@ struct RotEpi {
     __device__ __forceinline__ void tile_end(const Params&, const TcTile&, int, int) {}
     __device__ __forceinline__ void chunk(const Params& p, const TcTile& t, int, int c, const uint32_t (&v)[32]) {
         const int gidx = t.aux0 + c;                 // position in the (block, plane) sequence: uniform across the CTA
-        const int blk = gidx / p.P, pl = gidx - blk * p.P;
+        const int gu = p.nb_u * p.P_u;
+        int blk, pl, P;
+        if (gidx < gu) {
+            P = p.P_u;
+            blk = gidx / P;
+            pl = gidx - blk * P;
+        } else {
+            P = p.P_e;
+            const int b = (gidx - gu) / P;
+            blk = p.nb_u + b;
+            pl = gidx - gu - b * P;
+        }
         if (blk >= p.nblocks) return;
         const double wk = p.w[pl];
         if (pl == 0) {
@@ -54,7 +66,7 @@ struct RotEpi {
 #pragma unroll
             for (int j = 0; j < 32; ++j) d[j] = fma(wk, (double)(int)v[j], d[j]);
         }
-        if (pl != p.P - 1 || orow >= p.row_count) return;
+        if (pl != P - 1 || orow >= p.row_count) return;
         const double2* sc = reinterpret_cast<const double2*>(p.rscale + 32 * blk);
         double2* dst = reinterpret_cast<double2*>(p.g + orow * p.ldg + 32 * blk);
         if (t.aux1 == 0) {
@@ -79,7 +91,7 @@ struct RotEpi {
 // max |row| of the extended basis [U (n rows); Ext (n_e rows)] -> rscale[r] = 2^E_r (digit256_exponent); one block per row
 static __global__ void __launch_bounds__(256) rot_row_scale_kernel(const double* __restrict__ U, int64_t ldu, int n_u,
                                                                    const double* __restrict__ Ext, int64_t lde, int n_e, int n,
-                                                                   double* __restrict__ rscale, int* __restrict__ bad) {
+                                                                   int n_u_pad, double* __restrict__ rscale, int* __restrict__ bad) {
     __shared__ double red[8];
     const int r = blockIdx.x;
     const double* src = r < n_u ? U + (int64_t)r * ldu : Ext + (int64_t)(r - n_u) * lde;
@@ -96,23 +108,29 @@ static __global__ void __launch_bounds__(256) rot_row_scale_kernel(const double*
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
-        rscale[r] = ldexp(1.0, digit256_exponent(m));
+        rscale[r < n_u ? r : n_u_pad + (r - n_u)] = ldexp(1.0, digit256_exponent(m));
     }
     (void)n_e;
 }
 
-// digit planes of the extended basis into the B operand of kernel A: plane p of basis row r = 32 b + j is operand row
-// (b P + p) 32 + j, contraction index (individual) contiguous
+// digit planes of the extended basis into the B operand of kernel A: the blocks of 32 basis rows follow each other, every block
+// as its P planes of 32 operand rows (P_u planes for the eigenvector blocks, P_e for the blocks of extra rows, which start at
+// block nb_u); contraction index (individual) contiguous
 static __global__ void __launch_bounds__(256) rot_slice_kernel(const double* __restrict__ U, int64_t ldu, int n_u, const double* __restrict__ Ext,
-                                                               int64_t lde, int n_e, int n, int P, const double* __restrict__ rscale,
-                                                               int8_t* __restrict__ Bq, int64_t ldq) {
+                                                               int64_t lde, int n_e, int n, int P_u, int P_e, int nb_u,
+                                                               const double* __restrict__ rscale, int8_t* __restrict__ Bq, int64_t ldq) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (i >= n || r >= n_u + n_e) return;
-    const double x = (r < n_u ? U[(int64_t)r * ldu + i] : Ext[(int64_t)(r - n_u) * lde + i]) / rscale[r];     // exact: power of two
+    const bool is_u = r < n_u;
+    const int re = is_u ? r : r - n_u;
+    const int P = is_u ? P_u : P_e;
+    const double sc = rscale[is_u ? r : 32 * nb_u + re];
+    const double x = (is_u ? U[(int64_t)r * ldu + i] : Ext[(int64_t)re * lde + i]) / sc;     // exact: power of two
     int dg[DIGIT256_MAX_PLANES];
     digit256_split(x, P, dg);
-    const int64_t base = ((int64_t)(r >> 5) * P * 32 + (r & 31)) * ldq + i;
+    const int64_t row0 = is_u ? (int64_t)(re >> 5) * P_u * 32 : ((int64_t)nb_u * P_u + (int64_t)(re >> 5) * P_e) * 32;
+    const int64_t base = (row0 + (re & 31)) * ldq + i;
     for (int p = 0; p < P; ++p) Bq[base + (int64_t)p * 32 * ldq] = (int8_t)dg[p];
 }
 
@@ -145,8 +163,8 @@ struct SharedFinishParams {
     const double* h0_rss;    // [T]
     const double* w1;        // [T] sum_k w_tk
     const double* escale;    // [T (1 + q0)] 2^E of the extra basis rows (error of the dot products per unit ||x||_1 and digit remainder)
-    double eps_u;            // max_k 2^E_k * rem: absolute error of g_k per unit ||x||_1
-    double rem;              // DIGIT256_REM 256^-P
+    double eps_u;            // max_k 2^E_k * DIGIT256_REM 256^-P_u: absolute error of g_k per unit ||x||_1
+    double rem;              // DIGIT256_REM 256^-P_e (extra rows)
     double n_p, lbeta;
     int64_t out_stride, out_row0;      // outputs are [T][out_stride], this chunk starts at out_row0
     double *xx, *xy, *rss, *f, *p, *var_perc;

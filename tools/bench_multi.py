@@ -56,7 +56,7 @@ def main():
     planes, rho = ctx.last_scan_info()
     line = {'config': 'configs[2] multi-phenotype batch at n = %d' % a.n, 'n': a.n, 'm': a.m, 'T': a.T,
             'emmax_multi_s': t_multi, 'stage_seconds': timers, 'planes': planes, 'certified_rel_bound_xx': rho,
-            'scan_kernels_ms': ctx.last_kernel_ms('scan'),
+            'scan_kernels_ms': ctx.last_kernel_ms('scan'), 'shared_scan_info': getattr(ctx, 'last_shared_info', None),
             'snp_tests_per_s_scan_stage': a.m * a.T / max(timers['scan'], 1e-9),
             'snp_tests_per_s_whole_call_excl_eigh': a.m * a.T / max(t_multi - timers['syevd'], 1e-9)}
     # single-phenotype scans (what the reference does T times, linear_models.py:1790)
@@ -85,6 +85,7 @@ def main():
         ctx.timer_reset()
         lm.emmax_multi(snps, Y, K)
         line['variant_cluster%s_ksplit%s_scan_stage_s' % (cs, ks)] = ctx.timers()['scan']
+        line['variant_cluster%s_ksplit%s_info' % (cs, ks)] = getattr(ctx, 'last_shared_info', None)
     print(json.dumps(line))
 
 
