@@ -213,6 +213,14 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int nv, double 
                        int impl, int64_t snp_begin, int64_t snp_count,
                        double* ps, double* f_stats, double* rss, double* var_perc,
                        double* xx, double* dots);
+/* with_betas=True of _emmax_f_test_ (linear_models.py:1323: lstsq([h0_X, x~], y~res) per SNP) finished on the device: the scan
+ * with R = H (no projection) and V = [y~res; h0_X'] ([1 + q0] x n_out), then per SNP the (q0 + 1) x (q0 + 1) normal equations
+ * through the Schur complement of A = h0_X'h0_X (Ainv = A^-1 [q0 x q0], c0 = h0_X'y~res [q0], yy = y~res.y~res), F and p.
+ * betas: [snp_count x (q0 + 1)]; a SNP whose column is rank deficient (or whose residue is exactly 0) keeps the null fit like
+ * the reference's `if rss:` (:1325) -- rss = h0_rss, the row holds h0_betas followed by NaN. */
+int mmg_emmax_scan_betas_f64(mmg_ctx* ctx, mmg_mat R, const double* V, int q0, const double* Ainv, const double* c0, double yy,
+                             const double* h0_betas, double h0_rss, double n_p, int impl, int64_t snp_begin, int64_t snp_count,
+                             double* ps, double* f_stats, double* rss, double* var_perc, double* betas);
 /* mmg_emmax_scan_f64 for REAL-VALUED genotype rows (imputed dosages; the reference's scan accepts any numeric row, it casts the
  * chunk to float32 at linear_models.py:1317): xs = [m x ld] host FP64, SNP-major, ld >= n.  FP64 tensor-core path with the
  * genotype operand staged as FP64; the rows pass through the device in chunks and do not become the resident block.

@@ -89,6 +89,8 @@ SIGNATURES = {
     'mmg_emma_f64': (C.c_int, [_c_ctx, C.c_int, _i64, _vp, _vp, C.c_int, _vp, _vp, _vp, _i64, _vp, C.c_int, C.c_double, _vp, _vp, _vp]),
     'mmg_emmax_scan_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _i64, _i64,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
+    'mmg_emmax_scan_betas_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, _vp, _vp, C.c_double, _vp, C.c_double, C.c_double, C.c_int, _i64, _i64,
+                                           _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_rows_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_int, C.c_double, C.c_double, _vp, _i64, _i64,
                                           _vp, _vp, _vp, _vp, _vp, _vp]),
     'mmg_emmax_scan_quad_f64': (C.c_int, [_c_ctx, _i64, _vp, C.c_double, C.c_double, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -720,6 +722,28 @@ class Context(object):
                                              snp_begin, snp_count, _ptr(out.get('ps')), _ptr(out.get('f_stats')),
                                              _ptr(out.get('rss')), _ptr(out.get('var_perc')), _ptr(out['xx']),
                                              _ptr(out.get('dots'))))
+        return out
+
+    def emmax_scan_betas(self, R, Yres, h0_X, h0_betas, h0_rss, n_p, impl=IMPL_AUTO, snp_begin=0, snp_count=None):
+        """with_betas=True (linear_models.py:1323): lstsq([h0_X, x~], y~res) for every resident SNP, finished on the device
+        (mmg_emmax_scan_betas_f64).  Returns ps, f_stats, rss, var_perc and betas [snp_count x (q0 + 1)] (last entry NaN where
+        the SNP kept the null fit)."""
+        m, n = self.snps_shape()
+        if snp_count is None:
+            snp_count = m - snp_begin
+        h0_X = np.ascontiguousarray(h0_X, dtype=np.float64)
+        Yres = np.ascontiguousarray(Yres, dtype=np.float64).reshape(-1)
+        q0 = h0_X.shape[1]
+        V = np.ascontiguousarray(np.vstack([Yres[None, :], h0_X.T]))
+        Ainv = np.ascontiguousarray(np.linalg.inv(h0_X.T @ h0_X))
+        c0 = np.ascontiguousarray(h0_X.T @ Yres)
+        hb = np.ascontiguousarray(np.asarray(h0_betas, dtype=np.float64).reshape(q0))
+        slab = result_empty((4, snp_count))
+        out = {k: slab[i] for i, k in enumerate(('ps', 'f_stats', 'rss', 'var_perc'))}
+        out['betas'] = result_empty((snp_count, q0 + 1))
+        self._ck(self.lib.mmg_emmax_scan_betas_f64(self.h, R.handle, _ptr(V), q0, _ptr(Ainv), _ptr(c0), float(Yres @ Yres), _ptr(hb),
+                                                   float(h0_rss), float(n_p), impl_id(impl), snp_begin, snp_count, _ptr(out['ps']),
+                                                   _ptr(out['f_stats']), _ptr(out['rss']), _ptr(out['var_perc']), _ptr(out['betas'])))
         return out
 
     def emmax_scan_rows(self, xs, R, V, h0_rss, n_p, want_dots=False, want_stats=True, **_ignored):

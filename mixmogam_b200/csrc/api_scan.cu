@@ -785,6 +785,135 @@ static int perm_scan_tc(mmg_ctx* ctx, const MmgMat* R, const MmgMat* Wt, int cen
     return MMG_OK;
 }
 
+// x~.x~, x~.V[0] and the statistics of SNP rows [snp_begin, +snp_count) of the resident block, left on the device in `out`:
+// xx | xy | rss | f | p | var_perc (snp_count doubles each), then -- with want_dots -- x~.V[v] for v < nv ([nv][snp_count]).
+static int scan_device(mmg_ctx* ctx, MmgMat* R, const double* V, int nv, double h0_rss, double n_p, int impl, int64_t snp_begin,
+                       int64_t snp_count, double lbeta, DevBuf& out, bool want_dots) {
+    const int64_t n = ctx->n, n_out = R->rows;
+    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)(6 + nv) * snp_count * sizeof(double)));
+    double* d_xx = out.as<double>();
+    double* d_xy = d_xx + snp_count;
+    double* d_rss = d_xy + snp_count;
+    double* d_f = d_rss + snp_count;
+    double* d_p = d_f + snp_count;
+    double* d_vp = d_p + snp_count;
+    double* d_dots = d_vp + snp_count;
+    StageTimer tm(ctx, "scan");
+    if (impl == MMG_IMPL_DMMA) {
+        DevBuf Rp, Vp;
+        int64_t rows_pad = 0, ld = 0;
+        MMG_TRY(pad_matrix(ctx, R, Rp, &rows_pad, &ld));
+        MMG_CUDA(ctx, Vp.alloc(ctx->stream, (size_t)rows_pad * sizeof(double)));
+        MMG_CUDA(ctx, cudaMemsetAsync(Vp.p, 0, (size_t)rows_pad * sizeof(double), ctx->stream));
+        MMG_CUDA(ctx, cudaMemcpyAsync(Vp.p, V, n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ScanDmmaParams prm{};
+        prm.snps = ctx->snps;
+        prm.pitch = ctx->pitch;
+        prm.row_begin = snp_begin;
+        prm.row_count = snp_count;
+        prm.R = Rp.as<double>();
+        prm.ldr = ld;
+        prm.n_out_pad = (int)rows_pad;
+        prm.k_pad = (int)round_up(n, SD_BK);
+        prm.y = Vp.as<double>();
+        prm.h0_rss = h0_rss;
+        prm.n_p = n_p;
+        prm.lbeta = lbeta;
+        prm.xx = d_xx;
+        prm.xy = d_xy;
+        prm.rss = d_rss;
+        prm.f = d_f;
+        prm.p = d_p;
+        prm.var_perc = d_vp;
+        MMG_TRY(launch_scan_dmma(ctx, false, prm));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        const MmgMat* Rs[1] = {R};
+        MMG_TRY(scan_tc_run(ctx, 1, Rs, V, &h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
+    ctx->last_scan_ms = ms;
+
+    if (want_dots) {
+        // x~.V[v] = x.(R' V[v]):  W = V R  ([nv x n_out] x [n_out x n]) then an HBM-bound dot kernel
+        DevBuf Vd, Wd;
+        MMG_CUDA(ctx, Vd.alloc(ctx->stream, (size_t)nv * n_out * sizeof(double)));
+        MMG_CUDA(ctx, Wd.alloc(ctx->stream, (size_t)nv * n * sizeof(double)));
+        MMG_CUDA(ctx, cudaMemcpyAsync(Vd.p, V, (size_t)nv * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        const double one = 1.0, zero = 0.0;
+        // row-major W[nv x n] = V[nv x n_out] R[n_out x n]  ->  column-major W' = R' V'
+        MMG_CUBLAS(ctx, cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, nv, (int)n_out, &one, R->d, (int)R->cols,
+                                    Vd.as<double>(), (int)n_out, &zero, Wd.as<double>(), (int)n));
+        for (int v = 0; v < nv; ++v) {
+            // one vector per launch keeps the kernel simple; dots is strided by nv on the host side
+            snp_dots_kernel<1><<<(unsigned)((snp_count + 7) / 8), 256, 0, ctx->stream>>>(
+                ctx->snps, ctx->pitch, snp_begin, snp_count, (int)n, Wd.as<double>() + (int64_t)v * n, n, d_dots + (int64_t)v * snp_count);
+            MMG_TRY(launch_check(ctx, "snp_dots_kernel"));
+        }
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MMG_OK;
+}
+
+// lstsq([h0_X, x~], y~res) per SNP (linear_models.py:1323, with_betas=True) from its normal equations: with A = h0_X'h0_X,
+// c0 = h0_X'y~res, b = x~'h0_X, the Schur complement s = x~.x~ - b'A^-1 b gives beta_x = (x~.y~ - b'A^-1 c0) / s,
+// beta_0 = A^-1 c0 - A^-1 b beta_x, rss = y~.y~ - beta_0'c0 - beta_x x~.y~; then F and p (:1345-1349).  A rank-deficient
+// column (s ~ 0) or an exact zero residue keeps the null fit (`if rss:`, :1325).  One thread per SNP.
+struct BetasParams {
+    const double *xx, *dots;     // [snp_count], [1 + q0][snp_count]
+    int64_t snp_count;
+    int q0;
+    double Ainv[16 * 16], c0[16], a0[16], h0_betas[16];
+    double yy, h0_rss, n_p, lbeta;
+    double *rss, *f, *p, *var_perc, *betas;      // betas: [snp_count][q0 + 1]
+};
+static __global__ void __launch_bounds__(256) betas_finish_kernel(const BetasParams prm) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= prm.snp_count) return;
+    const int q0 = prm.q0;
+    const double xx = prm.xx[s], xy = prm.dots[s];
+    double Ab[16];
+    double bAb = 0.0, Abc = 0.0;
+    for (int i = 0; i < q0; ++i) {
+        double a = 0.0;
+        for (int j = 0; j < q0; ++j) a = fma(prm.Ainv[i * 16 + j], prm.dots[(int64_t)(1 + j) * prm.snp_count + s], a);
+        Ab[i] = a;
+        bAb = fma(a, prm.dots[(int64_t)(1 + i) * prm.snp_count + s], bAb);
+        Abc = fma(a, prm.c0[i], Abc);
+    }
+    const double sc = xx - bAb;
+    const bool ok = sc > 1e-12 * fmax(xx, 1e-300);
+    double rss = prm.h0_rss;
+    bool good = false;
+    double bx = 0.0;
+    if (ok) {
+        bx = (xy - Abc) / sc;
+        double fit = bx * xy;
+        for (int i = 0; i < q0; ++i) fit = fma(prm.a0[i] - Ab[i] * bx, prm.c0[i], fit);
+        const double r = prm.yy - fit;
+        if (r != 0.0) {
+            rss = r;
+            good = true;
+        }
+    }
+    double* bo = prm.betas + s * (q0 + 1);
+    if (good) {
+        for (int i = 0; i < q0; ++i) bo[i] = prm.a0[i] - Ab[i] * bx;
+        bo[q0] = bx;
+    } else {
+        for (int i = 0; i < q0; ++i) bo[i] = prm.h0_betas[i];
+        bo[q0] = nan("");                           // marks "null fit kept": the host hands out h0_betas for this SNP
+    }
+    const double ratio = prm.h0_rss / rss;
+    const double f = (ratio - 1.0) * prm.n_p;
+    prm.rss[s] = rss;
+    prm.f[s] = f;
+    prm.var_perc[s] = 1.0 - 1.0 / ratio;
+    prm.p[s] = f_sf(fmax(f, 0.0), 1.0, prm.n_p, prm.lbeta);
+}
+
 extern "C" {
 
 int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double h0_rss, double n_p, int impl, int64_t snp_begin,
@@ -797,77 +926,15 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
     if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_SCAN_IMPL", MMG_IMPL_TCGEN05);
     MMG_CHECK(ctx, impl == MMG_IMPL_DMMA || impl == MMG_IMPL_TCGEN05, "unsupported impl %d for the scan", impl);
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int64_t n = ctx->n, n_out = R->rows;
     const double lbeta = lbeta_host(0.5 * n_p, 0.5);
-
-    DevBuf out;      // xx, xy, rss, f, p, var_perc  (6 x snp_count doubles) + dots
-    MMG_CUDA(ctx, out.alloc(ctx->stream, (size_t)(6 + nv) * snp_count * sizeof(double)));
+    DevBuf out;
+    MMG_TRY(scan_device(ctx, R, V, nv, h0_rss, n_p, impl, snp_begin, snp_count, lbeta, out, dots != nullptr));
     double* d_xx = out.as<double>();
-    double* d_xy = d_xx + snp_count;
-    double* d_rss = d_xy + snp_count;
+    double* d_rss = d_xx + 2 * snp_count;
     double* d_f = d_rss + snp_count;
     double* d_p = d_f + snp_count;
     double* d_vp = d_p + snp_count;
     double* d_dots = d_vp + snp_count;
-
-    {
-        StageTimer tm(ctx, "scan");
-        if (impl == MMG_IMPL_DMMA) {
-            DevBuf Rp, Vp;
-            int64_t rows_pad = 0, ld = 0;
-            MMG_TRY(pad_matrix(ctx, R, Rp, &rows_pad, &ld));
-            MMG_CUDA(ctx, Vp.alloc(ctx->stream, (size_t)rows_pad * sizeof(double)));
-            MMG_CUDA(ctx, cudaMemsetAsync(Vp.p, 0, (size_t)rows_pad * sizeof(double), ctx->stream));
-            MMG_CUDA(ctx, cudaMemcpyAsync(Vp.p, V, n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-            ScanDmmaParams prm{};
-            prm.snps = ctx->snps;
-            prm.pitch = ctx->pitch;
-            prm.row_begin = snp_begin;
-            prm.row_count = snp_count;
-            prm.R = Rp.as<double>();
-            prm.ldr = ld;
-            prm.n_out_pad = (int)rows_pad;
-            prm.k_pad = (int)round_up(n, SD_BK);
-            prm.y = Vp.as<double>();
-            prm.h0_rss = h0_rss;
-            prm.n_p = n_p;
-            prm.lbeta = lbeta;
-            prm.xx = d_xx;
-            prm.xy = d_xy;
-            prm.rss = d_rss;
-            prm.f = d_f;
-            prm.p = d_p;
-            prm.var_perc = d_vp;
-            MMG_TRY(launch_scan_dmma(ctx, false, prm));
-            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        } else {
-            const MmgMat* Rs[1] = {R};
-            MMG_TRY(scan_tc_run(ctx, 1, Rs, V, &h0_rss, n_p, lbeta, snp_begin, snp_count, d_xx, d_xy, d_rss, d_f, d_p, d_vp));
-            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        }
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
-        ctx->last_scan_ms = ms;
-
-        if (dots) {
-            // x~.V[v] = x.(R' V[v]):  W = V R  ([nv x n_out] x [n_out x n]) then an HBM-bound dot kernel
-            DevBuf Vd, Wd;
-            MMG_CUDA(ctx, Vd.alloc(ctx->stream, (size_t)nv * n_out * sizeof(double)));
-            MMG_CUDA(ctx, Wd.alloc(ctx->stream, (size_t)nv * n * sizeof(double)));
-            MMG_CUDA(ctx, cudaMemcpyAsync(Vd.p, V, (size_t)nv * n_out * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-            const double one = 1.0, zero = 0.0;
-            // row-major W[nv x n] = V[nv x n_out] R[n_out x n]  ->  column-major W' = R' V'
-            MMG_CUBLAS(ctx, cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, nv, (int)n_out, &one, R->d, (int)R->cols,
-                                        Vd.as<double>(), (int)n_out, &zero, Wd.as<double>(), (int)n));
-            for (int v = 0; v < nv; ++v) {
-                // one vector per launch keeps the kernel simple; dots is strided by nv on the host side
-                snp_dots_kernel<1><<<(unsigned)((snp_count + 7) / 8), 256, 0, ctx->stream>>>(
-                    ctx->snps, ctx->pitch, snp_begin, snp_count, (int)n, Wd.as<double>() + (int64_t)v * n, n, d_dots + (int64_t)v * snp_count);
-                MMG_TRY(launch_check(ctx, "snp_dots_kernel"));
-            }
-            MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        }
-    }
     StageTimer tm2(ctx, "d2h");
     const size_t bytes = snp_count * sizeof(double);
     if (ps) MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -883,6 +950,70 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
         for (int v = 0; v < nv; ++v)
             for (int64_t s = 0; s < snp_count; ++s) dots[s * nv + v] = tmp[(size_t)v * snp_count + s];
     }
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMG_OK;
+}
+
+// with_betas=True (linear_models.py:1323): the scan with R = H (no projection), V = [y~res; h0_X'] and the per-SNP
+// (q0 + 1) x (q0 + 1) least squares finished on the device (betas_finish_kernel).  Ainv = (h0_X'h0_X)^-1 [q0 x q0], c0 = h0_X'y~res,
+// yy = y~res.y~res, h0_betas [q0].  Outputs (host): ps, f_stats, rss, var_perc [snp_count], betas [snp_count x (q0 + 1)] -- the last
+// entry of a row is NaN where the SNP kept the null fit (rank-deficient column or zero residue).
+int mmg_emmax_scan_betas_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int q0, const double* Ainv, const double* c0, double yy,
+                             const double* h0_betas, double h0_rss, double n_p, int impl, int64_t snp_begin, int64_t snp_count,
+                             double* ps, double* f_stats, double* rss, double* var_perc, double* betas) {
+    MmgMat* R = ctx ? get_mat(ctx, Rh) : nullptr;
+    MMG_CHECK(ctx, R && ctx->snps, "mmg_emmax_scan_betas_f64: need resident genotypes and R");
+    MMG_CHECK(ctx, R->cols == ctx->n, "R must have n = %lld columns (has %lld)", (long long)ctx->n, (long long)R->cols);
+    MMG_CHECK(ctx, V && q0 >= 1 && q0 <= 15 && Ainv && c0 && h0_betas, "need V = [y~res; h0_X'] with 1..15 fixed-effect columns");
+    MMG_CHECK(ctx, ps && f_stats && rss && var_perc && betas, "all outputs are required");
+    MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
+    if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_SCAN_IMPL", MMG_IMPL_TCGEN05);
+    MMG_CHECK(ctx, impl == MMG_IMPL_DMMA || impl == MMG_IMPL_TCGEN05, "unsupported impl %d for the scan", impl);
+    MMG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double lbeta = lbeta_host(0.5 * n_p, 0.5);
+    DevBuf out, bbuf;
+    MMG_TRY(scan_device(ctx, R, V, 1 + q0, h0_rss, n_p, impl, snp_begin, snp_count, lbeta, out, true));
+    MMG_CUDA(ctx, bbuf.alloc(ctx->stream, (size_t)snp_count * (q0 + 1) * sizeof(double)));
+    BetasParams bp{};
+    bp.xx = out.as<double>();
+    double* d_rss = out.as<double>() + 2 * snp_count;
+    double* d_f = d_rss + snp_count;
+    double* d_p = d_f + snp_count;
+    double* d_vp = d_p + snp_count;
+    bp.dots = d_vp + snp_count;
+    bp.snp_count = snp_count;
+    bp.q0 = q0;
+    for (int i = 0; i < q0; ++i) {
+        bp.c0[i] = c0[i];
+        bp.h0_betas[i] = h0_betas[i];
+        double a = 0.0;
+        for (int j = 0; j < q0; ++j) {
+            bp.Ainv[i * 16 + j] = Ainv[i * q0 + j];
+            a += Ainv[i * q0 + j] * c0[j];
+        }
+        bp.a0[i] = a;
+    }
+    bp.yy = yy;
+    bp.h0_rss = h0_rss;
+    bp.n_p = n_p;
+    bp.lbeta = lbeta;
+    bp.rss = d_rss;
+    bp.f = d_f;
+    bp.p = d_p;
+    bp.var_perc = d_vp;
+    bp.betas = bbuf.as<double>();
+    {
+        StageTimer tm(ctx, "scan");
+        betas_finish_kernel<<<(unsigned)((snp_count + 255) / 256), 256, 0, ctx->stream>>>(bp);
+        MMG_TRY(launch_check(ctx, "betas_finish_kernel"));
+    }
+    StageTimer tm2(ctx, "d2h");
+    const size_t bytes = snp_count * sizeof(double);
+    MMG_CUDA(ctx, cudaMemcpyAsync(ps, d_p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(f_stats, d_f, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(rss, d_rss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(var_perc, d_vp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MMG_CUDA(ctx, cudaMemcpyAsync(betas, bbuf.p, (size_t)(q0 + 1) * bytes, cudaMemcpyDeviceToHost, ctx->stream));
     MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMG_OK;
 }

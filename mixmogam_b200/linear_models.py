@@ -550,32 +550,42 @@ class LinearMixedModel(LinearModel):
                 out = scan(Rm, nf['Yres'].reshape(1, -1), h0_rss_f, n_p, impl=impl)
             p_vals, f_stats, rss_list, var_perc = out['ps'], out['f_stats'], out['rss'], out['var_perc']
         else:
-            # lstsq([h0_X, x~], Y) (:1323) through its normal equations: the kernel supplies
-            # xx = x~.x~, xy = x~.Yres, b = x~.h0_X; the (q0+1)x(q0+1) solve is a Schur complement per SNP.
+            # lstsq([h0_X, x~], Y) (:1323) through its normal equations: the scan supplies xx = x~.x~, xy = x~.Yres, b = x~.h0_X;
+            # the (q0+1)x(q0+1) solve is a Schur complement per SNP
             h0_X, Yres = nf['h0_X'], nf['Yres']
-            V = np.vstack([Yres.T, h0_X.T])
-            out = scan(Rm, V, h0_rss_f, n_p, impl=impl, want_dots=True, want_stats=False)
-            xx, dots = out['xx'], out['dots']
-            xy, b = dots[:, 0], dots[:, 1:]
-            A = h0_X.T @ h0_X
-            c0 = (h0_X.T @ Yres).reshape(-1)
-            Ainv = np.linalg.inv(A)
-            Ab = b @ Ainv.T                                   # rows: A^-1 b_s
-            s = xx - np.einsum('ij,ij->i', b, Ab)
-            ok = s > 1e-12 * np.maximum(xx, 1e-300)
-            s_safe = np.where(ok, s, 1.0)
-            beta_x = (xy - Ab @ c0) / s_safe
-            beta_0 = (Ainv @ c0)[None, :] - Ab * beta_x[:, None]
-            yy = float(np.sum(Yres ** 2))
-            rss_full = yy - (beta_0 @ c0 + beta_x * xy)
-            good = ok & (rss_full != 0)
-            rss_list = np.where(good, rss_full, h0_rss_f)
-            betas_arr = np.hstack([beta_0, beta_x[:, None]])
-            betas_list = [list(map(float, row)) if g else h0_betas for row, g in zip(betas_arr, good)]
-            rss_ratio = h0_rss_f / rss_list
-            var_perc = 1 - 1 / rss_ratio
-            f_stats = (rss_ratio - 1) * n_p / float(q)
-            p_vals = ctx.f_sf(f_stats, q, n_p)
+            if xs_real is None:
+                # ... evaluated on the device, with F and p (betas_finish_kernel): no statistic is computed on the host
+                out = ctx.emmax_scan_betas(Rm, Yres, h0_X, h0_betas, h0_rss_f, n_p, impl=impl)
+                p_vals, f_stats, rss_list, var_perc = out['ps'], out['f_stats'], out['rss'], out['var_perc']
+                kept = np.isnan(out['betas'][:, -1])
+                betas_list = out['betas'].tolist()
+                for i in np.flatnonzero(kept):
+                    betas_list[i] = h0_betas
+            else:
+                # real-valued rows (dosages): the moments come back and the small solve runs vectorised on the host
+                V = np.vstack([Yres.T, h0_X.T])
+                out = scan(Rm, V, h0_rss_f, n_p, impl=impl, want_dots=True, want_stats=False)
+                xx, dots = out['xx'], out['dots']
+                xy, b = dots[:, 0], dots[:, 1:]
+                A = h0_X.T @ h0_X
+                c0 = (h0_X.T @ Yres).reshape(-1)
+                Ainv = np.linalg.inv(A)
+                Ab = b @ Ainv.T                                   # rows: A^-1 b_s
+                s = xx - np.einsum('ij,ij->i', b, Ab)
+                ok = s > 1e-12 * np.maximum(xx, 1e-300)
+                s_safe = np.where(ok, s, 1.0)
+                beta_x = (xy - Ab @ c0) / s_safe
+                beta_0 = (Ainv @ c0)[None, :] - Ab * beta_x[:, None]
+                yy = float(np.sum(Yres ** 2))
+                rss_full = yy - (beta_0 @ c0 + beta_x * xy)
+                good = ok & (rss_full != 0)
+                rss_list = np.where(good, rss_full, h0_rss_f)
+                betas_arr = np.hstack([beta_0, beta_x[:, None]])
+                betas_list = [list(map(float, row)) if g else h0_betas for row, g in zip(betas_arr, good)]
+                rss_ratio = h0_rss_f / rss_list
+                var_perc = 1 - 1 / rss_ratio
+                f_stats = (rss_ratio - 1) * n_p / float(q)
+                p_vals = ctx.f_sf(f_stats, q, n_p)
 
         res_d = {'ps': p_vals, 'f_stats': f_stats, 'rss': rss_list, 'var_perc': var_perc,
                  'h0_rss': h0_rss, 'h0_betas': h0_betas}
