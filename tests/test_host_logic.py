@@ -336,3 +336,16 @@ def test_write_genotype_file_layout():
     np.testing.assert_allclose(c1['freqs'], chroms[1]['raw_snps'].mean(1) / 2.0)
     assert np.array_equal(f['genot_data']['chrom_2']['positions'], np.arange(5) * 7)
     assert set(f['indiv_data'].keys()) == {'indiv_ids', 'sex', 'phenotypes'}
+
+
+def test_f_sf_series_branch_dense(built):
+    """The power-series branch of f_sf (fdist.cuh: small F at large dfd -- where nearly every SNP of a scan lands) on a dense grid
+    against scipy, including the switch-over to the continued fraction at (a + b) z = 4."""
+    from scipy import stats
+    for dfn in (1.0, 2.0):
+        for dfd in (196.0, 397.0, 4998.0, 9998.0, 49998.0):
+            F = np.concatenate([np.logspace(-14, 0, 150), np.linspace(1.0, 12.0, 221)])
+            payload = np.concatenate([[F.size], np.stack([F, np.full_like(F, dfn), np.full_like(F, dfd)], axis=1).ravel()])
+            out = _run(built, 'fsf', payload)
+            ref = stats.f.sf(F, dfn, dfd)
+            assert np.max(np.abs(out - ref) / ref) < 1e-11, (dfn, dfd)

@@ -72,7 +72,8 @@ def main():
     line['single_emmax_s'] = [x[0] for x in ts]
     line['single_scan_stage_s'] = [x[1] for x in ts]
     line['max_rel_err_neglog10p_vs_single'] = errs
-    line['scan_cost_vs_one_single_scan'] = timers['scan'] / max(min(x[1] for x in ts), 1e-9)
+    if ts:
+        line['scan_cost_vs_one_single_scan'] = timers['scan'] / max(min(x[1] for x in ts), 1e-9)
     if a.unshared:
         ctx.timer_reset()
         t0 = time.perf_counter()
