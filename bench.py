@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument('--scan-impl', default=os.environ.get('MMG_BENCH_SCAN_IMPL', 'tcgen05'), choices=['tcgen05', 'dmma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-e2e-variants', action='store_true', help='skip the packed / pageable host-buffer variants of the e2e step')
     ap.add_argument('--profile-host', default=None, help='write a cProfile of one resident step and one e2e step to this file')
     return ap.parse_args()
 
@@ -344,15 +345,21 @@ def main():
         return r, r['ps']
 
     # ---- one step through the public API with host buffers (e2e) ----
-    def step_e2e():
+    def step_e2e(buf=None):
+        buf = snps if buf is None else buf
         ctx.invalidate_snps()                                                        # force the H2D copy every step
         if world == 1:
-            K = kinship.calc_ibs_kinship(snps, 'diploid_int')                        # H2D snps, Gram, D2H K
+            K = kinship.calc_ibs_kinship(buf, 'diploid_int')                         # H2D snps, Gram, D2H K
             r = lm.LinearMixedModel(y, ctx=ctx, scan_impl=args.scan_impl)
             r.add_random_effect(K)                                                   # K found on the device again: no upload
-            res = r.emmax_f_test(snps, eig_L=eig_L, eig_R=eig_R, emma_num=0)         # D2H ps, f, rss, var_perc, xx
+            res = r.emmax_f_test(buf, eig_L=eig_L, eig_R=eig_R, emma_num=0)          # D2H ps, f, rss, var_perc, xx
             return res, res['ps']
-        return step_resident()
+        K = parallel.calc_ibs_kinship_sharded(buf, m, 'diploid_int', ctx=ctx)
+        mdl = lm.LinearMixedModel(y, ctx=ctx, scan_impl=args.scan_impl, shard=shard)
+        mdl.add_random_effect(K)
+        K.free()
+        r = mdl.emmax_f_test(buf, eig_L=eig_L, eig_R=eig_R, emma_num=0)
+        return r, r['ps']
 
     def stage_seconds(steps, wall_s):
         t = {k: v / steps for k, v in ctx.timers().items()}
@@ -422,6 +429,36 @@ def main():
         barrier()
         t_e2e = time.perf_counter() - t0
         e2e_timers = stage_seconds(args.steps, t_e2e)
+    # ---- the same e2e step fed from other host buffers (2 timed steps each; reported beside the headline e2e, which stays the
+    #      reference's input format in page-locked memory): genotypes the caller holds packed at 2 bits (n / 4 bytes per SNP over
+    #      PCIe, SURVEY 8d's minimum), and an ordinary pageable numpy array (what snpsdata.get_snps() hands over) ----
+    e2e_variants = {}
+    if not args.no_e2e and not args.no_e2e_variants:
+        for name in ('packed2_pinned', 'int8_pageable'):
+            if name == 'packed2_pinned':
+                buf = _lib.pack_genotypes(snps)                      # outside the timed region: the caller's storage format
+                nbytes = buf.packed.shape[0] * ((n + 3) // 4)
+            else:
+                buf = np.array(snps)                                 # a private copy in pageable memory
+                buf.flags.writeable = False
+                nbytes = buf.nbytes
+            step_e2e(buf)
+            barrier()
+            ctx.timer_reset()
+            parallel.collective_timers(ctx, reset=True)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                step_e2e(buf)
+            barrier()
+            tv = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([tv], dtype=torch.float64, device=device)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                tv = float(tt[0])
+            e2e_variants[name] = {'value': m * 2 / tv, 'ms_per_step': 1e3 * tv / 2, 'steps': 2, 'h2d_bytes_per_step': int(nbytes),
+                                  'stage_seconds_per_step': stage_seconds(2, tv)}
+            del buf
+        ctx.invalidate_snps()
     if world > 1:
         tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -444,6 +481,7 @@ def main():
         pk, rw, _ = ctx.last_h2d_info()
         if pk + rw > 0:
             e2e['h2d_pcie_bytes_per_step'] = int(m_loc * n * (rw + 0.25 * pk) / (pk + rw) + n * 8 * 2 * 2)
+        e2e['other_host_buffers'] = e2e_variants
 
     if os.environ.get('MMG_BENCH_DEBUG'):
         # every rank's own view of the timed region (the JSON line below is rank 0's): stage timers, planes, wall times

@@ -16,6 +16,15 @@ void multi_init_attrs() {
 }
 }  // namespace mmg
 
+// L2 policy "evict_last for `frac` of the lines, evict_first for the rest" (createpolicy.fractional): with the genotype blocks of
+// all co-resident CTAs (148 x 1.3 MB at n = 10k) larger than L2, a uniform priority makes every re-read of a block miss
+// (ncu: 34.6 GB of DRAM reads per 16 k SNPs = every K-block of every tile); pinning a fraction that fits keeps that fraction.
+static __global__ void make_l2_policy_kernel(float frac, unsigned long long* out) {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(p) : "f"(frac));
+    *out = p;
+}
+
 extern "C" {
 
 int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const double* W, int T, int q0, const double* h0_rss, double n_p,
@@ -53,10 +62,36 @@ int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const doub
     int ksplit = std::max(1, env_int("MMG_SHARED_KSPLIT", 1));
     int cs = env_int("MMG_SHARED_CLUSTER", 2);
     if (cs != 1 && cs != 2 && cs != 4) cs = 2;
-    // SNP chunk: the FP64 rotated block g [chunk x ldg] is the one large temporary (<= ~2 GB)
-    int64_t chunk = std::max<int64_t>(128 * cs, ((int64_t)2 << 30) / (ldg * 8) / (128 * cs) * (128 * cs));
+    // SNP chunk: the FP64 rotated block g [chunk x ldg] is the one large temporary (<= ~4 GB).  A whole number of waves of the
+    // persistent rotation grid (one 128-SNP group per CTA and wave): a chunk of 1.35 waves costs two
+    const int64_t wave = (int64_t)128 * cs * (cs == 4 ? tc_gemm_max_clusters<RotEpi, 4>(ctx) : cs == 2 ? tc_gemm_max_clusters<RotEpi, 2>(ctx)
+                                                                                                      : tc_gemm_max_clusters<RotEpi, 1>(ctx));
+    int64_t chunk = wave * std::max<int64_t>(1, std::min<int64_t>(4, ((int64_t)4 << 30) / (wave * ldg * 8)));
     chunk = std::min<int64_t>(chunk, round_up(snp_count, 128));
     if (const int c = env_int("MMG_SHARED_CHUNK", 0)) chunk = round_up(c, 128);
+    // genotype operand: evict_last for 30 % of its lines (what fits L2 beside the basis stream), evict_first for the rest --
+    // measured 52.4 -> 47.4 ms per 131 k SNPs against a uniform priority; MMG_SHARED_A_FRAC = 0 switches it off
+    uint64_t policy_a = L2_EVICT_LAST;
+    {
+        const char* fr = getenv("MMG_SHARED_A_FRAC");
+        const float f = fr ? (float)atof(fr) : 0.3f;
+        static float cached_f = -1.f;
+        static unsigned long long cached_p = 0;
+        if (f > 0.f && f <= 1.f) {
+            if (cached_f != f) {
+                DevBuf pb;
+                MMG_CUDA(ctx, pb.alloc(ctx->stream, 8));
+                make_l2_policy_kernel<<<1, 1, 0, ctx->stream>>>(f, pb.as<unsigned long long>());
+                MMG_TRY(launch_check(ctx, "make_l2_policy_kernel"));
+                unsigned long long pv = 0;
+                MMG_CUDA(ctx, cudaMemcpyAsync(&pv, pb.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                cached_p = pv;
+                cached_f = f;
+            }
+            policy_a = cached_p;
+        }
+    }
 
     StageTimer tm(ctx, "scan");
     DevBuf rs, Bq, Wd, gbuf, abuf, l1buf, outbuf, small;
@@ -164,11 +199,11 @@ int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const doub
             for (auto& x : e) { MMG_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
             cudaEventRecord(e[0], ctx->stream);
             if (cs == 4)
-                MMG_TRY((launch_tc_gemm<RotEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<RotEpi,4>", L2_EVICT_LAST, L2_EVICT_NORMAL)));
+                MMG_TRY((launch_tc_gemm<RotEpi, 4>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<RotEpi,4>", policy_a, L2_EVICT_NORMAL)));
             else if (cs == 2)
-                MMG_TRY((launch_tc_gemm<RotEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<RotEpi,2>", L2_EVICT_LAST, L2_EVICT_NORMAL)));
+                MMG_TRY((launch_tc_gemm<RotEpi, 2>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<RotEpi,2>", policy_a, L2_EVICT_NORMAL)));
             else
-                MMG_TRY((launch_tc_gemm<RotEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<RotEpi,1>", L2_EVICT_LAST, L2_EVICT_NORMAL)));
+                MMG_TRY((launch_tc_gemm<RotEpi, 1>(ctx, tmA, tmB, td, groups, (int)tiles.size(), 0, TC_BM, 0, ep, "tc_gemm_i8_kernel<RotEpi,1>", policy_a, L2_EVICT_NORMAL)));
             cudaEventRecord(e[1], ctx->stream);
             // ---- kernel B: a[s][t] = sum_k g[s][k]^2 w[t][k] ----
             ScanDmmaParams prm{};

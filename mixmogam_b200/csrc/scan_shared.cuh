@@ -172,9 +172,10 @@ struct SharedFinishParams {
 };
 
 static __global__ void __launch_bounds__(256) shared_finish_kernel(const SharedFinishParams prm) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
-    if (s >= prm.rows) return;
+    const bool valid = s_raw < prm.rows;               // every lane stays for the warp reductions below
+    const int64_t s = valid ? s_raw : prm.rows - 1;
     const double a = prm.a[s * prm.lda + t];
     const double* ge = prm.g + s * prm.ldg + prm.n_u + (int64_t)t * (1 + prm.q0);
     const double* es = prm.escale + (int64_t)t * (1 + prm.q0);
@@ -194,11 +195,26 @@ static __global__ void __launch_bounds__(256) shared_finish_kernel(const SharedF
     }
     const double h0 = prm.h0_rss[t];
     const bool degenerate = !(sxx > QS_DEGENERATE_REL * a);      // x in the span of the fixed effects: keeps the null fit (:1329)
-    if (!degenerate) {
-        atomicMax(prm.rho_max, (unsigned long long)__double_as_longlong(err / sxx));
-        const double exy = es[0] * prm.rem * x1;
-        atomicMax(prm.rho_max + 1, (unsigned long long)__double_as_longlong(exy * sqrt(prm.n_p / (sxx * h0))));
+    {   // certification maxima: reduced over the warp first (bit patterns of non-negative doubles order like the values), one
+        // atomic per warp and quantity -- a per-thread atomic on two addresses serialised the whole kernel (4.5 ms per 16 k SNPs)
+        unsigned long long r0 = 0ull, r1 = 0ull;
+        if (!degenerate && valid) {
+            r0 = (unsigned long long)__double_as_longlong(err / sxx);
+            const double exy = es[0] * prm.rem * x1;
+            r1 = (unsigned long long)__double_as_longlong(exy * sqrt(prm.n_p / (sxx * h0)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a0 = __shfl_xor_sync(0xffffffffu, r0, o), a1 = __shfl_xor_sync(0xffffffffu, r1, o);
+            r0 = a0 > r0 ? a0 : r0;
+            r1 = a1 > r1 ? a1 : r1;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (r0 > prm.rho_max[0]) atomicMax(prm.rho_max, r0);
+            if (r1 > prm.rho_max[1]) atomicMax(prm.rho_max + 1, r1);
+        }
     }
+    if (!valid) return;
     const int64_t o = (int64_t)t * prm.out_stride + prm.out_row0 + s;
     if (prm.xx) prm.xx[o] = sxx;
     if (prm.xy) prm.xy[o] = sxy;

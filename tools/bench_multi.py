@@ -28,6 +28,7 @@ def main():
     ap.add_argument('--phenotypes', dest='T', type=int, default=199)
     ap.add_argument('--single', type=int, default=2)
     ap.add_argument('--unshared', type=int, default=4, help='phenotypes to run through the per-phenotype-rotation launch for comparison')
+    ap.add_argument('--envs', default='', help='semicolon list of comma separated ENV=value settings to time the shared scan under')
     ap.add_argument('--variants', default='', help='comma list of cluster:ksplit pairs to time besides the default, e.g. 1:1,4:1,2:2')
     a = ap.parse_args()
     import torch
@@ -87,6 +88,18 @@ def main():
         lm.emmax_multi(snps, Y, K)
         line['variant_cluster%s_ksplit%s_scan_stage_s' % (cs, ks)] = ctx.timers()['scan']
         line['variant_cluster%s_ksplit%s_info' % (cs, ks)] = getattr(ctx, 'last_shared_info', None)
+    for ev in [x for x in a.envs.split(';') if x]:
+        sets = dict(kv.split('=') for kv in ev.split(','))
+        old = {k: os.environ.get(k) for k in sets}
+        os.environ.update(sets)
+        ctx.timer_reset()
+        lm.emmax_multi(snps, Y, K)
+        line['env[%s]' % ev] = {'scan_stage_s': ctx.timers()['scan'], 'info': getattr(ctx, 'last_shared_info', None)}
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     print(json.dumps(line))
 
 
