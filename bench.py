@@ -468,9 +468,9 @@ def main():
     if not args.no_e2e:
         # K is downloaded to the caller (read-only, pinned) but its device copy is kept and found again by
         # add_random_effect: no K upload.  Uploads: genotypes + X|Y columns for the two null fits.  Downloads: one rank, K and
-        # the five per-SNP vectors; several ranks, the gathered p-values on every rank (+ the other four vectors on rank 0).
+        # the five per-SNP vectors; several ranks, the gathered p-values on every rank (+ the other three vectors on rank 0).
         h2d = m_loc * n + n * 8 * 2 * 2
-        d2h = (n * n * 8 + 5 * m * 8) if world == 1 else 5 * m * 8
+        d2h = (n * n * 8 + 5 * m * 8) if world == 1 else 4 * m * 8
         e2e = {'value': m * args.steps / t_e2e_max, 'unit': 'SNP-tests/s', 'h2d_bytes_per_step': int(h2d),
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * t_e2e_max / args.steps,
                'metric': METRIC, 'stage_seconds_per_step': e2e_timers,

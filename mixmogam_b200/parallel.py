@@ -23,6 +23,7 @@ import contextlib
 import numpy as np
 
 RESULT_KEYS = ('ps', 'f_stats', 'rss', 'var_perc', 'xx')       # row order of mmg_emmax_scan_quad_dev's output
+GATHERED_KEYS = RESULT_KEYS[:4]                                 # what the sharded scan hands back (linear_models.py:1351-1352)
 
 
 def shard_range(m, rank, world):
@@ -273,7 +274,7 @@ class GatheredRows(object):
 
 def scan_sharded(ctx, A, a_err, v, h0_rss, n_p, m_total=None, group=None, eager=None):
     """The int8 scan of this rank's resident SNP slice given the packed quadratic form, followed by the all-gather of the
-    per-rank outputs on the device.  Returns {'ps', 'f_stats', 'rss', 'var_perc', 'xx'} covering ALL m_total SNPs (rank
+    per-rank outputs on the device.  Returns {'ps', 'f_stats', 'rss', 'var_perc'} covering ALL m_total SNPs (rank
     order = shard_range order): `ps` as a numpy array on every rank; the other four as numpy arrays on rank 0 and as
     GatheredRows (downloaded on first use) elsewhere, unless `eager` says otherwise."""
     import torch
@@ -295,14 +296,14 @@ def scan_sharded(ctx, A, a_err, v, h0_rss, n_p, m_total=None, group=None, eager=
         sizes = [(int(e - c), int(e)) for c, e in zip(cnt, ends)]
     m_all = sizes[-1][1]
     maxlen = max(e - b for b, e in sizes)
-    nk = len(RESULT_KEYS)
-    out = DeviceMatrix(ctx, nk, maxlen)
+    out = DeviceMatrix(ctx, len(RESULT_KEYS), maxlen)
     ctx.emmax_scan_quad_dev(A, v, h0_rss, n_p, packed=True, a_err=a_err, out=out)
+    nk = len(GATHERED_KEYS)                                     # x~.x~ (the kernel's fifth row) is not part of the result dict: it stays behind
     gathered = DeviceMatrix(ctx, world * nk, maxlen, zero=False)
     final = DeviceMatrix(ctx, nk, m_all, zero=False)
     with on_lib_stream(ctx, 'allgather'):
         tg = mat_as_tensor(ctx, gathered)
-        dist.all_gather_into_tensor(tg, mat_as_tensor(ctx, out), group=group)
+        dist.all_gather_into_tensor(tg, mat_as_tensor(ctx, out)[:nk], group=group)
         # compact the padded per-rank blocks into [5 x m_total] on the device: the host then receives finished vectors
         tg = tg.view(world, nk, maxlen)
         torch.cat([tg[r, :, :e - b] for r, (b, e) in enumerate(sizes)], dim=1, out=mat_as_tensor(ctx, final))
@@ -313,9 +314,9 @@ def scan_sharded(ctx, A, a_err, v, h0_rss, n_p, m_total=None, group=None, eager=
     if eager:
         host = final.download(pinned=True)                      # one copy; the five vectors are its rows
         final.free()
-        return {name: host[k] for k, name in enumerate(RESULT_KEYS)}
+        return {name: host[k] for k, name in enumerate(GATHERED_KEYS)}
     res = {}
-    for k, name in enumerate(RESULT_KEYS):
+    for k, name in enumerate(GATHERED_KEYS):
         g = GatheredRows(final, k, m_all)
         res[name] = g.host() if name == 'ps' else g
     return res
