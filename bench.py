@@ -271,6 +271,21 @@ def load_json(path):
         return {}
 
 
+def kinship_roofline(ctx, n, m_loc, gram_s, rates):
+    """Second kernel of the step: the Gram of the thermometer planes (c = 2 per SNP).  Executed ops = the upper-triangular
+    128 x 256 tiles the kernel multiplies; the peak is the issue rate of the MMA kind it uses, measured in this run."""
+    fp4 = ctx.last_kernel_ms('gram_is_fp4') != 0.0
+    tiles = sum(2 * jn + 2 for jn in range((n + 255) // 256))
+    exec_ops = 2.0 * tiles * 128 * 256 * 2.0 * m_loc
+    peak = rates.get('mxf4_sustained_tops' if fp4 else 'int8_sustained_tops')
+    return {'gram_ms': gram_s * 1e3, 'kernel': 'tc_gemm_i8_kernel<GramEpiF4, 2, mxf4>' if fp4 else 'tc_gemm_i8_kernel<GramEpi, 2>',
+            'operands': 'e2m1 (kind::mxf4.block_scale, unit scales, FP32 accumulators holding exact integers)' if fp4 else 'int8 (kind::i8)',
+            'tops_algorithmic': 2.0 * n * n * 2 * m_loc / gram_s / 1e12, 'tops_executed': exec_ops / gram_s / 1e12,
+            'peak_tops': peak, 'frac': exec_ops / gram_s / 1e12 / peak if peak else None,
+            'peak_is': 'tcgen05 %s issue rate, smem-resident operands, held 0.5 s; measured in this run' % ('mxf4' if fp4 else 'int8'),
+            'note': 'thermometer coding c=2; the symmetric kernel executes ~half of the algorithmic ops'}
+
+
 def main():
     args = parse_args()
     if args.impl == 'reference':
@@ -317,7 +332,8 @@ def main():
     rates = {}
     if rank == 0:
         rates = {'dmma_tflops': ctx.microbench('dmma'), 'int8_burst_tops': ctx.microbench('imma_pair'),
-                 'int8_sustained_tops': ctx.microbench('imma_pair_sustained500')}
+                 'int8_sustained_tops': ctx.microbench('imma_pair_sustained500'),
+                 'mxf4_sustained_tops': ctx.microbench('mxf4_tcgen05_sustained500')}
 
     # ---- set-up outside the hot path: K once, its two eigendecompositions (timed separately; with several ranks eigh(K)
     #      runs on rank 0, eigh(S(K+I)S) on rank 1, both are broadcast) ----
@@ -538,8 +554,7 @@ def main():
                'eigh_seconds': {'wall': eigh_wall, 'syevd_device_this_rank': eigh_dev, 'count': 2, 'broadcast_device': eigh_bcast,
                                 'placement': 'eigh(K) on rank 0, eigh(S(K+I)S) on rank 1, broadcast' if world > 1 else 'both on the one GPU'},
                'stage_seconds_per_step': timers,
-               'kinship': {'gram_ms': gram_s * 1e3, 'int8_tops_algorithmic': 2.0 * n * n * 2 * m_loc / gram_s / 1e12,
-                           'note': 'thermometer coding c=2; symmetric kernel executes ~half of the algorithmic ops'},
+               'kinship': kinship_roofline(ctx, n, m_loc, gram_s, rates),
                'setup_seconds': {'generate': gen_s}}
         if not args.no_cpu_baseline and world == 1:
             out['cpu_baseline'] = cpu_baseline(n, m)

@@ -9,6 +9,8 @@ namespace mmg {
 void kinship_init_attrs() {
     cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpiF4, 1, TC_KIND_MXF4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpiF4, 2, TC_KIND_MXF4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<IbdEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<IbdEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }
@@ -194,8 +196,14 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     // int32 accumulator headroom: |entries| <= K-dim (values are +-1 or 0/1)
     MMG_CHECK(ctx, (double)snp_count * c < 2.0e9, "Gram K-dimension too large for int32 accumulation");
 
-    const int64_t chunk = 65536;                         // SNPs per packed chunk (multiple of 128)
-    const int64_t p_pitch = chunk * c;
+    // MMG_GRAM_KIND = fp4 (default) | i8: the 0 / +-1 planes of both codings are exact e2m1 values, which the tensor cores
+    // multiply at twice the int8 rate (kind::mxf4, unit block scales); sums of at most 2^17 such products per chunk are exact
+    // in the FP32 accumulator.  The SIMT cross-check kernel reads int8 operands.
+    bool fp4 = impl == MMG_IMPL_TCGEN05;
+    if (const char* e = getenv("MMG_GRAM_KIND")) fp4 = fp4 && strcmp(e, "i8") != 0;
+    ctx->last_gram_fp4 = fp4 ? 1 : 0;
+    const int64_t chunk = 65536;                         // SNPs per packed chunk (multiple of 256)
+    const int64_t p_pitch = fp4 ? chunk * c / 2 : chunk * c;   // bytes per individual
     const int64_t need = (int64_t)n * p_pitch;
     if (ctx->pack_bytes < need) {
         cudaFree(ctx->pack);
@@ -396,7 +404,7 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     } tev_guard{tev};
     for (int64_t s0 = 0; s0 < snp_count; s0 += chunk) {
         const int64_t cnt = std::min(chunk, snp_count - s0);
-        const int64_t kbytes = round_up(cnt, 128) * c;
+        const int64_t kbytes = fp4 ? round_up(cnt, 256) * c / 2 : round_up(cnt, 128) * c;   // whole 128-byte K blocks
         cudaEvent_t e_p0 = ctx->ev0, e_p1 = ctx->ev1, e_g0 = ctx->kev0, e_g1 = ctx->kev1;
         if (src) {
             MMG_TRY(issue_copy(s0 / chunk));
@@ -408,11 +416,14 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
         }
         // ---- pack ----
         cudaEventRecord(e_p0, ctx->stream);
-        dim3 pgrid((unsigned)((cnt + 127) / 128), (unsigned)((n + 63) / 64));
-        if (coding == MMG_CODING_BINARY)
-            pack_kmajor_kernel<0><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
-        else
-            pack_kmajor_kernel<1><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+        dim3 pgrid((unsigned)((fp4 ? round_up(cnt, 256) : round_up(cnt, 128)) / 128), (unsigned)((n + 63) / 64));   // SNPs >= cnt pack to zeros
+        if (coding == MMG_CODING_BINARY) {
+            if (fp4) pack_kmajor_kernel<0, true><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+            else pack_kmajor_kernel<0><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+        } else {
+            if (fp4) pack_kmajor_kernel<1, true><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+            else pack_kmajor_kernel<1><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+        }
         MMG_TRY(launch_check(ctx, "pack_kmajor_kernel"));
         cudaEventRecord(e_p1, ctx->stream);
         // ---- Gram ----
@@ -426,7 +437,13 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
             MMG_TRY(ensure_tiles(ctx, table));
             GramEpi::Params ep{ctx->G, g_pad, accumulate};
             const int ngroups = (int)table.size() * gram_cs;
-            if (gram_cs == 2)
+            if (fp4) {
+                GramEpiF4::Params ep4{ctx->G, g_pad, accumulate};
+                if (gram_cs == 2)
+                    MMG_TRY((launch_tc_gemm<GramEpiF4, 2, TC_KIND_MXF4>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep4, "tc_gemm_i8_kernel<GramEpiF4,2,mxf4>")));
+                else
+                    MMG_TRY((launch_tc_gemm<GramEpiF4, 1, TC_KIND_MXF4>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, 0, ep4, "tc_gemm_i8_kernel<GramEpiF4,1,mxf4>")));
+            } else if (gram_cs == 2)
                 MMG_TRY((launch_tc_gemm<GramEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep, "tc_gemm_i8_kernel<GramEpi,2>")));
             else
                 MMG_TRY((launch_tc_gemm<GramEpi, 1>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, 0, ep, "tc_gemm_i8_kernel<GramEpi,1>")));

@@ -25,6 +25,12 @@ static __global__ void make_l2_policy_kernel(float frac, unsigned long long* out
     *out = p;
 }
 
+static double wall_now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 extern "C" {
 
 int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const double* W, int T, int q0, const double* h0_rss, double n_p,
@@ -94,6 +100,7 @@ int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const doub
     }
 
     StageTimer tm(ctx, "scan");
+    const double t_setup0 = wall_now();
     DevBuf rs, Bq, Wd, gbuf, abuf, l1buf, outbuf, small;
     MMG_CUDA(ctx, rs.alloc(ctx->stream, (size_t)ldg * sizeof(double)));
     MMG_CUDA(ctx, small.alloc(ctx->stream, 64 + (size_t)(2 * T + n_e) * sizeof(double)));
@@ -143,7 +150,9 @@ int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const doub
     double* o_vp = o_rss + (size_t)T * snp_count;
     double* o_xx = o_vp + (size_t)T * snp_count;
 
-    double rho_xx = 0.0, rho_xy = 0.0, rot_ms = 0.0, con_ms = 0.0;
+    double rho_xx = 0.0, rho_xy = 0.0, rot_ms = 0.0, con_ms = 0.0, fin_ms = 0.0;
+    int passes = 0;
+    const double t_loop0 = wall_now();
     for (;;) {
         // ---- digit planes of the extended basis ----
         const int64_t b_rows = round_up(((int64_t)nb_u * P + (int64_t)nb_e * P_e) * 32, TC_BN);
@@ -195,7 +204,7 @@ int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const doub
             MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->snps + (snp_begin + c0) * ctx->pitch, ctx->pitch, rows, ctx->pitch, TC_BM));
             MMG_TRY(make_tmap_u8(ctx, &tmB, Bq.p, ldq, b_rows, ldq, TC_BN / cs));
             const int groups = (int)((rows + TC_BM - 1) / TC_BM);
-            cudaEvent_t e[4];
+            cudaEvent_t e[6];
             for (auto& x : e) { MMG_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
             cudaEventRecord(e[0], ctx->stream);
             if (cs == 4)
@@ -248,17 +257,22 @@ int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const doub
             fp.p = o_p;
             fp.var_perc = o_vp;
             fp.rho_max = d_rho;
+            cudaEventRecord(e[4], ctx->stream);
             shared_finish_kernel<<<dim3((unsigned)((rows + 255) / 256), (unsigned)T), 256, 0, ctx->stream>>>(fp);
             MMG_TRY(launch_check(ctx, "shared_finish_kernel"));
+            cudaEventRecord(e[5], ctx->stream);
         }
         double rho[2] = {0.0, 0.0};
         MMG_CUDA(ctx, cudaMemcpyAsync(rho, d_rho, 16, cudaMemcpyDeviceToHost, ctx->stream));
         MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (size_t i = 0; i + 3 < evs.size(); i += 4) {
+        fin_ms = 0.0;
+        for (size_t i = 0; i + 5 < evs.size(); i += 6) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, evs[i], evs[i + 1]) == cudaSuccess) rot_ms += ms;
             if (cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]) == cudaSuccess) con_ms += ms;
+            if (cudaEventElapsedTime(&ms, evs[i + 4], evs[i + 5]) == cudaSuccess) fin_ms += ms;
         }
+        passes += 1;
         for (cudaEvent_t x : evs) cudaEventDestroy(x);
         rho_xx = rho[0];
         rho_xy = rho[1];
@@ -272,6 +286,9 @@ int mmg_emmax_scan_shared_f64(mmg_ctx* ctx, mmg_mat Uh, mmg_mat Exth, const doub
         if (!ok_xx) ++P;
         P_e = std::min(RS_MAX_PLANES, std::max(P_e + (ok_xy ? 0 : 1), P));
     }
+    if (env_int("MMG_SHARED_DEBUG", 0))
+        fprintf(stderr, "[shared scan] set-up %.1f ms, %d pass(es) %.1f ms wall; last pass: rotation %.1f contraction %.1f statistics %.1f ms; chunk %lld SNPs\n",
+                1e3 * (t_loop0 - t_setup0), passes, 1e3 * (wall_now() - t_loop0), rot_ms, con_ms, fin_ms, (long long)chunk);
     ctx->last_scan_ms = rot_ms + con_ms;
     ctx->last_scan_slices = P;
     ctx->last_scan_rho = rho_xx;

@@ -133,7 +133,7 @@ static uint64_t env_policy(const char* var, uint64_t dflt) {
 }
 
 // clusters of CS CTAs of tc_gemm_i8_kernel<Epi, CS> that can be co-resident: the persistent grid of launch_tc_gemm
-template <class Epi, int CS>
+template <class Epi, int CS, int KIND = TC_KIND_I8>
 static int tc_gemm_max_clusters(mmg_ctx* ctx) {
     int max_clusters = ctx->sm_count / CS;
     if (CS > 1) {
@@ -150,7 +150,7 @@ static int tc_gemm_max_clusters(mmg_ctx* ctx) {
         cfg.numAttrs = 1;
         cfg.gridDim = dim3((unsigned)(ctx->sm_count / CS * CS));
         int q = 0;
-        if (cudaOccupancyMaxActiveClusters(&q, tc_gemm_i8_kernel<Epi, CS>, &cfg) == cudaSuccess && q > 0) max_clusters = std::min(max_clusters, q);
+        if (cudaOccupancyMaxActiveClusters(&q, tc_gemm_i8_kernel<Epi, CS, KIND>, &cfg) == cudaSuccess && q > 0) max_clusters = std::min(max_clusters, q);
         else cudaGetLastError();
     }
     return std::max(1, max_clusters);
@@ -158,12 +158,12 @@ static int tc_gemm_max_clusters(mmg_ctx* ctx) {
 
 // Launch the tcgen05 GEMM with a cluster of CS CTAs.  The persistent grid is the number of clusters that can be
 // co-resident (cudaOccupancyMaxActiveClusters; clusters of 4 do not tile every GPC) times CS.
-template <class Epi, int CS>
+template <class Epi, int CS, int KIND = TC_KIND_I8>
 static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcTile* tiles_d, int num_groups,
                           int tiles_per_group, int table_stride, int group_m_step, int rank_m_step,
                           const typename Epi::Params& ep, const char* name, uint64_t hint_a = L2_EVICT_NORMAL,
                           uint64_t hint_b = L2_EVICT_NORMAL) {
-    auto kern = tc_gemm_i8_kernel<Epi, CS>;
+    auto kern = tc_gemm_i8_kernel<Epi, CS, KIND>;
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = TC_SMEM_BYTES;
@@ -175,7 +175,7 @@ static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const int max_clusters = tc_gemm_max_clusters<Epi, CS>(ctx);
+    const int max_clusters = tc_gemm_max_clusters<Epi, CS, KIND>(ctx);
     const int cgroups = (num_groups + CS - 1) / CS;
     const int clusters = std::max(1, std::min(cgroups, max_clusters));
     cfg.gridDim = dim3((unsigned)(clusters * CS));

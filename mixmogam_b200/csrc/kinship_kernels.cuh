@@ -25,7 +25,16 @@ __device__ __forceinline__ uint32_t bytes_lt_mask(int first_idx, int nvalid) {
     return m;
 }
 
-template <int CODING>
+// 4 bytes (0 / 1 each, or e2m1 codes in the low nibble) -> 4 nibbles in the low 16 bits, byte b in bits 4b..4b+3
+__device__ __forceinline__ uint32_t squeeze_nibbles(uint32_t w) {
+    const uint32_t y = (w | (w >> 4)) & 0x00ff00ffu;
+    return (y | (y >> 8)) & 0xffffu;
+}
+
+// FP4 = true: the operand of the kind::mxf4 Gram, e2m1 codes packed two per byte (p_pitch in bytes as before):
+//   binary : code(2 x - 1) = 0x2 (+1.0) / 0xa (-1.0), SNP s0 + j of a 16-SNP group in nibble j
+//   diploid: [x >= 1] of the 16 SNPs in the first 8 bytes of the group's 16, [x >= 2] in the second 8; code 0x2 = 1.0
+template <int CODING, bool FP4 = false>
 static __global__ void __launch_bounds__(256) pack_kmajor_kernel(const int8_t* __restrict__ snps, int64_t pitch,
                                                           int64_t s_begin, int64_t s_count, int n,
                                                           int8_t* __restrict__ P, int64_t p_pitch,
@@ -71,7 +80,26 @@ static __global__ void __launch_bounds__(256) pack_kmajor_kernel(const int8_t* _
         int64_t rem = s_count - (s0 + 16 * c);
         const int nvalid = rem < 0 ? 0 : (rem > 16 ? 16 : (int)rem);
         const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-        if (CODING == 0) {
+        if (FP4) {
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t m = bytes_lt_mask(4 * k, nvalid);
+                if (CODING == 0) {
+                    // x = 1 -> 0x2, x = 0 -> 0xa
+                    a[k] = squeeze_nibbles((0x0a0a0a0au ^ ((xs[k] & 0x01010101u) << 3)) & m);
+                } else {
+                    a[k] = squeeze_nibbles((__vcmpgeu4(xs[k], 0x01010101u) & 0x02020202u & m));
+                    b[k] = squeeze_nibbles((__vcmpgeu4(xs[k], 0x02020202u) & 0x02020202u & m));
+                }
+            }
+            if (CODING == 0) {
+                *reinterpret_cast<uint2*>(P + (int64_t)i * p_pitch + (s0 + 16 * c) / 2) = make_uint2(a[0] | (a[1] << 16), a[2] | (a[3] << 16));
+            } else {
+                *reinterpret_cast<uint4*>(P + (int64_t)i * p_pitch + (s0 + 16 * c)) =
+                    make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), b[0] | (b[1] << 16), b[2] | (b[3] << 16));
+            }
+        } else if (CODING == 0) {
             uint32_t o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)

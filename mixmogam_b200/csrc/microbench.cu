@@ -38,7 +38,8 @@ __global__ void bench_copy_kernel(const uint4* __restrict__ src, uint4* __restri
 // (4 x UMMA K=32, M=128 per CTA, N=256) into two alternating accumulators.  ldtm != 0: the four epilogue warps read
 // the accumulators back with tcgen05.ld at the rate of one full 128x256 tile per `ldtm` K blocks, free running
 // (measures whether TMEM reads take cycles from the tensor pipe).  PAIR: cta_group::2 (M = 256 over two CTAs).
-template <bool PAIR>
+// F4: e2m1 operands, kind::mxf4.block_scale with unit scale factors (K = 64 per instruction), one accumulator (the Gram's form).
+template <bool PAIR, bool F4 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) bench_imma_kernel(int iters, int ldtm, unsigned* sink) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bench_imma_kernel(int iters, in
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < (TC_A_BYTES + TC_B_BYTES) / 4; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(smem)[i] = (0x9E3779B9u * (i + 1)) & 0x03030303u;      // genotype-like bytes 0..3
+        reinterpret_cast<uint32_t*>(smem)[i] = (0x9E3779B9u * (i + 1)) & (F4 ? 0x22222222u : 0x03030303u);   // genotype-like bytes 0..3 | e2m1 0 / 1.0
     if (threadIdx.x == 0) {
         mbar_init(&done_bar, 1);
         mbar_fence_init();
@@ -61,7 +62,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bench_imma_kernel(int iters, in
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     const bool leader = !PAIR || cluster_ctarank() == 0;
-    if (warp == 1 && lane == 0 && leader) {
+    if (F4) {
+        if (warp >= 2) {
+            const uint32_t ta = tmem_base + TC_SF_COL + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+            for (int c = 0; c < (TC_TMEM_COLS - TC_SF_COL) / 8; ++c) tmem_st_32x8_const(ta + c * 8, 0x7f7f7f7fu);
+            tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (F4 && warp == 1 && lane == 0) {
+        constexpr uint32_t idesc4 = umma_idesc_mxf4(TC_BM, TC_BN);
+        const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem)), db = umma_desc_kmajor_sw128(smem_u32(smem) + TC_A_BYTES);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                umma_mxf4(tmem_base, da + 2 * kk, db + 2 * kk, idesc4, ((it & 7) | kk) ? 1u : 0u, tmem_base + TC_SF_COL + 64, tmem_base + TC_SF_COL + 128);
+        }
+        umma_commit(&done_bar);
+    }
+    if (!F4 && warp == 1 && lane == 0 && leader) {
         constexpr uint32_t idesc = umma_idesc_i8(PAIR ? 2 * TC_BM : TC_BM, TC_BN);
         const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem)), db = umma_desc_kmajor_sw128(smem_u32(smem) + TC_A_BYTES);
         for (int it = 0; it < iters; ++it) {
@@ -300,9 +321,10 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
         if (w == 16 && x == 16) return run_bench_ldtm<16, 16>(ctx, mma, value);
         return run_bench_ldtm<16, 32>(ctx, mma, value);
     }
-    if (!strncmp(which, "imma", 4)) {
-        // "imma_tcgen05" | "imma_pair" | "imma_tcgen05_ldtm<k>" | "imma_pair_ldtm<k>": TOP/s
-        const bool pair = strstr(which, "pair") != nullptr;
+    if (!strncmp(which, "imma", 4) || !strncmp(which, "mxf4", 4)) {
+        // "imma_tcgen05" | "imma_pair" | "imma_tcgen05_ldtm<k>" | "imma_pair_ldtm<k>" | "mxf4_tcgen05": TOP/s
+        const bool f4 = !strncmp(which, "mxf4", 4);
+        const bool pair = !f4 && strstr(which, "pair") != nullptr;
         const char* l = strstr(which, "ldtm");
         const int ldtm = l ? std::max(1, atoi(l + 4)) : 0;
         const int iters = 40000, smem = TC_A_BYTES + TC_B_BYTES + 1024;
@@ -321,8 +343,10 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
         cfg.numAttrs = 1;
         cudaFuncSetAttribute(bench_imma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(bench_imma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(bench_imma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         auto launch = [&]() -> int {
-            cudaError_t e = pair ? cudaLaunchKernelEx(&cfg, bench_imma_kernel<true>, iters, ldtm, (unsigned*)ctx->scratch)
+            cudaError_t e = f4 ? cudaLaunchKernelEx(&cfg, bench_imma_kernel<false, true>, iters, 0, (unsigned*)ctx->scratch)
+                          : pair ? cudaLaunchKernelEx(&cfg, bench_imma_kernel<true>, iters, ldtm, (unsigned*)ctx->scratch)
                                  : cudaLaunchKernelEx(&cfg, bench_imma_kernel<false>, iters, ldtm, (unsigned*)ctx->scratch);
             ctx->launches += 1;
             if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "bench_imma_kernel launch failed: %s", cudaGetErrorString(e));
@@ -350,7 +374,7 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
             cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
             ms /= (float)timed;
         }
-        *value = 2.0 * (double)grid * iters * TC_BM * TC_BN * TC_BK / (ms * 1e-3) / 1e12;
+        *value = 2.0 * (double)grid * iters * TC_BM * TC_BN * TC_BK * (f4 ? 2 : 1) / (ms * 1e-3) / 1e12;   // 256 e2m1 values per 128-byte K block
         return MMG_OK;
     }
     return fail(ctx, MMG_EBADARG, "unknown microbench '%s'", which);

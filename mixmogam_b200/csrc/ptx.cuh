@@ -270,6 +270,30 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(uint32_t M, uint32_t N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Instruction descriptor, kind::mxf4 (cute::UMMA::InstrDescriptorBlockScaled): a/b format E2M1 (1) at [7,10)/[10,13), K-major
+// both, N>>3 at [17,23), scale format UE8M0 (1) at bit 23, M>>4 at [24,29), scale-factor ids 0 (bits [4,6) and [29,31)),
+// K = 64 (bit 31 = 0).  The accumulator is always FP32.
+__host__ __device__ constexpr uint32_t umma_idesc_mxf4(uint32_t M, uint32_t N) {
+    return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
+}
+// D[tmem, FP32] (+)= (A o 2^sfa)[smem, e2m1] * (B o 2^sfb)[smem, e2m1], one UE8M0 scale per 32 elements of K read from tensor
+// memory at sf_a / sf_b; K = 64 per instruction, twice the int8 rate
+__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t sf_a, uint32_t sf_b) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(sf_a), "r"(sf_b)
+        : "memory");
+}
+// 32 lanes x 8 columns of tensor memory <- one 32-bit constant (thread t of the warp writes lane base_lane + t)
+__device__ __forceinline__ void tmem_st_32x8_const(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- cp.async (LDGSTS) --------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");

@@ -48,7 +48,18 @@ constexpr int TC_TILE_CHAIN = 1;
 // tile ti of that group is tiles[(g / CS) * table_stride + ti] with m0 += g * group_m_step + r * rank_m_step.
 //   scan: one shared table (table_stride 0), group_m_step = 128 (consecutive SNP row blocks), rank_m_step = 0
 //   Gram: one entry per cluster group (table_stride 1), group_m_step = 0, rank_m_step = 128 (adjacent row tiles)
-template <class Epi, int CS>
+//
+// KIND = TC_KIND_MXF4: the operands are packed e2m1 (4-bit) values, 256 per 128-byte K block, multiplied with
+// tcgen05.mma.kind::mxf4.block_scale (K = 64 per instruction: the same 32 bytes of K per MMA as int8, twice the elements, at
+// twice the int8 issue rate).  The block scale factors (UE8M0, one per 32 elements) are all 2^0: TMEM columns 256..511 are
+// filled with 0x7f bytes once and both scale-factor operands point there, which leaves ONE 256-column FP32 accumulator
+// (the tiles of the Gram are hundreds of K blocks long, the missing epilogue overlap is ~1 % of a tile).  Sums of products of
+// 0 / +-1 are integers < 2^24, so the FP32 accumulator is exact; the epilogue converts it to int32.
+constexpr int TC_KIND_I8 = 0;
+constexpr int TC_KIND_MXF4 = 1;
+constexpr int TC_SF_COL = 256;        // first TMEM column of the constant scale factors (KIND = MXF4)
+
+template <class Epi, int CS, int KIND = TC_KIND_I8>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcTile* __restrict__ tiles, int num_groups, int tiles_per_group, int table_stride,
@@ -60,8 +71,9 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* full_bar = bars;                               // [TC_STAGES]
     uint64_t* empty_bar = bars + TC_STAGES;                  // [TC_STAGES]
-    uint64_t* tfull_bar = bars + 2 * TC_STAGES;              // [TC_ACC_STAGES]
-    uint64_t* tempty_bar = bars + 2 * TC_STAGES + TC_ACC_STAGES;
+    constexpr int kAcc = KIND == TC_KIND_MXF4 ? 1 : TC_ACC_STAGES;
+    uint64_t* tfull_bar = bars + 2 * TC_STAGES;              // [kAcc]
+    uint64_t* tempty_bar = bars + 2 * TC_STAGES + kAcc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_ACC_STAGES);
 
     // warp index through a shuffle: the role branches are then provably warp-uniform, so loop counters, addresses and
@@ -82,7 +94,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], CS);   // one tcgen05.commit arrival from every CTA of the cluster
         }
-        for (int a = 0; a < TC_ACC_STAGES; ++a) {
+        for (int a = 0; a < kAcc; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], 4);   // one elected lane of each epilogue warp
         }
@@ -96,6 +108,18 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (CS > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (KIND == TC_KIND_MXF4) {
+        // constant scale factors 2^0 (UE8M0 0x7f) in every byte of columns 256..511, all 128 lanes: whatever layout the MMA
+        // reads its A / B scale vectors in, it reads ones
+        if (warp >= 2) {
+            const uint32_t taddr = tmem_base + TC_SF_COL + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+            for (int c = 0; c < (TC_TMEM_COLS - TC_SF_COL) / 8; ++c) tmem_st_32x8_const(taddr + c * 8, 0x7f7f7f7fu);
+            tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (warp == 0) {
         // ===================== TMA producer (all lanes run the loops, one elected lane issues) =====================
@@ -129,7 +153,8 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer (all lanes run the loops, one elected lane issues) =====================
         {
-            constexpr uint32_t idesc = umma_idesc_i8(TC_BM, TC_BN);
+            constexpr uint32_t idesc = KIND == TC_KIND_MXF4 ? umma_idesc_mxf4(TC_BM, TC_BN) : umma_idesc_i8(TC_BM, TC_BN);
+            const uint32_t sf_a = tmem_base + TC_SF_COL + 64, sf_b = tmem_base + TC_SF_COL + 128;
             const uint64_t da0 = umma_desc_kmajor_sw128(smem_u32(smem)), db0 = umma_desc_kmajor_sw128(smem_u32(smem) + TC_A_BYTES);
             int stage = 0;
             uint32_t phase = 0;
@@ -154,8 +179,10 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                             for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                                 // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
-                                umma_i8(d_tmem, da + (uint64_t)(k * (TC_UMMA_K >> 4)), db + (uint64_t)(k * (TC_UMMA_K >> 4)),
-                                        idesc, (chained || kb > t.kb0 || k > 0) ? 1u : 0u);
+                                const uint64_t ka = da + (uint64_t)(k * (TC_UMMA_K >> 4)), kb_ = db + (uint64_t)(k * (TC_UMMA_K >> 4));
+                                const uint32_t accum = (chained || kb > t.kb0 || k > 0) ? 1u : 0u;
+                                if (KIND == TC_KIND_MXF4) umma_mxf4(d_tmem, ka, kb_, idesc, accum, sf_a, sf_b);
+                                else umma_i8(d_tmem, ka, kb_, idesc, accum);
                             }
                             // frees the smem slot (in every CTA of the cluster) when these MMAs retire
                             if (CS == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], kMask);
@@ -165,7 +192,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     chained = (t.flags & TC_TILE_CHAIN) != 0;
                     if (chained) continue;                           // the next tile adds to the same accumulator
                     if (elect_one()) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
-                    if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                    if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
                 }
             }
         }
@@ -202,7 +229,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
             }
             if (live) epi.end_group(ep, g, row);
         }
@@ -217,7 +244,8 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ---- epilogue of the kinship Gram: G[m0+row][n0 + 32c .. +31] (+)= acc ------------------------------
-struct GramEpi {
+template <bool F32ACC>
+struct GramEpiT {
     struct Params {
         int32_t* G;        // [n_pad x ld] int32, n_pad multiple of 256 so no bounds checks are needed
         int64_t ld;
@@ -227,7 +255,10 @@ struct GramEpi {
     __device__ __forceinline__ void end_group(const Params&, int, int) {}
     __device__ __forceinline__ int tile_begin(const Params&, const TcTile&, int) { return TC_BN / 32; }
     __device__ __forceinline__ void tile_end(const Params&, const TcTile&, int, int) {}
-    __device__ __forceinline__ void chunk(const Params& p, const TcTile& t, int row, int c, const uint32_t (&v)[32]) {
+    __device__ __forceinline__ void chunk(const Params& p, const TcTile& t, int row, int c, const uint32_t (&raw)[32]) {
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = F32ACC ? (uint32_t)__float2int_rn(__uint_as_float(raw[j])) : raw[j];   // exact: integers < 2^24
         int4* dst = reinterpret_cast<int4*>(p.G + (int64_t)(t.m0 + row) * p.ld + t.n0 + c * 32);
         if (t.aux0) {
             // split-K slice of a tail tile (several clusters share one output tile): integer atomics are exact and order
@@ -252,5 +283,8 @@ struct GramEpi {
         }
     }
 };
+
+using GramEpi = GramEpiT<false>;      // int8 operands, int32 accumulators
+using GramEpiF4 = GramEpiT<true>;     // e2m1 operands, FP32 accumulators holding exact integers
 
 }  // namespace mmg

@@ -24,21 +24,33 @@ def _rand_snps(m, n, coding, seed):
     return rng.binomial(2, rng.uniform(0.05, 0.95, size=(m, 1)), size=(m, n)).astype(np.int8)
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tcgen05'])
+def _gram_kind(monkeypatch, impl):
+    """'tcgen05' is the e2m1 / kind::mxf4 Gram (default), 'tcgen05_i8' the int8 one (MMG_GRAM_KIND=i8)."""
+    if impl == 'tcgen05_i8':
+        monkeypatch.setenv('MMG_GRAM_KIND', 'i8')
+        return 'tcgen05'
+    return impl
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_i8'])
 @pytest.mark.parametrize('coding', [0, 1])
 @pytest.mark.parametrize('m,n', [(700, 37), (3000, 198), (5001, 300), (1, 5), (129, 257), (2048, 1000)])
-def test_gram_bit_exact(ctx, impl, coding, m, n):
+def test_gram_bit_exact(ctx, monkeypatch, impl, coding, m, n):
+    kind = impl
+    impl = _gram_kind(monkeypatch, impl)
     snps = _rand_snps(m, n, coding, seed=m * 1000 + n + coding)
     ctx.invalidate_snps()
     ctx.ensure_snps(snps)
     ctx.kinship_gram(coding, impl=impl)
+    assert ctx.last_kernel_ms('gram_is_fp4') == (1.0 if kind == 'tcgen05' else 0.0)
     G = ctx.kinship_gram_download()
     assert np.array_equal(G.astype(np.int64), _gram_ref(snps, coding))
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tcgen05'])
-def test_gram_chunk_boundary_and_accumulate(ctx, impl):
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_i8'])
+def test_gram_chunk_boundary_and_accumulate(ctx, monkeypatch, impl):
     """m crosses the 65536-SNP pack chunk; a second call with reset=False accumulates (multi-call == one call)."""
+    impl = _gram_kind(monkeypatch, impl)
     n, m = 130, 70000
     snps = _rand_snps(m, n, 1, seed=5)
     ctx.invalidate_snps()
@@ -138,6 +150,11 @@ def test_gram_split_k_tail_bit_exact(ctx, monkeypatch, coding):
     ctx.kinship_gram(coding, impl='tcgen05')
     assert np.array_equal(ctx.kinship_gram_download(), G)
     monkeypatch.delenv('MMG_GRAM_SPLITK')
+    monkeypatch.setenv('MMG_GRAM_KIND', 'i8')                              # int8 operands: same integers as the e2m1 ones
+    ctx.kinship_gram(coding, impl='tcgen05')
+    assert ctx.last_kernel_ms('gram_is_fp4') == 0.0
+    assert np.array_equal(ctx.kinship_gram_download(), G)
+    monkeypatch.delenv('MMG_GRAM_KIND')
     x = snps.astype(np.float64)
     if coding == 0:
         s = 2.0 * x - 1.0
