@@ -204,7 +204,13 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     ctx->last_gram_fp4 = fp4 ? 1 : 0;
     const int64_t chunk = 65536;                         // SNPs per packed chunk (multiple of 256)
     const int64_t p_pitch = fp4 ? chunk * c / 2 : chunk * c;   // bytes per individual
-    const int64_t need = (int64_t)n * p_pitch;
+    // MMG_GRAM_OVERLAP=1: the pack kernel of chunk c + 1 (HBM bound, a few KB of shared memory per block) runs on the side stream
+    // underneath the Gram of chunk c (one persistent CTA per SM), in two operand slots.  Measured neutral at n = 10k x 1M (209.6 vs
+    // 209.8 ms per step: the packs take 23 instead of 8 ms next to the Gram and the Gram 37.7 instead of 34.0 ms -- they compete for
+    // the same L2 / HBM path), so the default stays the serial order.
+    const bool overlap = env_int("MMG_GRAM_OVERLAP", 0) != 0 && snp_count > chunk;
+    const int64_t slot_bytes = (int64_t)n * p_pitch;
+    const int64_t need = slot_bytes * (overlap ? 2 : 1);
     if (ctx->pack_bytes < need) {
         cudaFree(ctx->pack);
         ctx->pack = nullptr;
@@ -396,81 +402,92 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
         if (!staged[(size_t)ci]) MMG_TRY(queue_raw(ci));
         return MMG_OK;
     };
-    // host source: no host synchronisation inside the chunk loop (the host packs while the GPU works): per-chunk events
+    // No host synchronisation inside the chunk loop (a host source packs its chunks meanwhile): per-chunk events, read at the end.
     std::vector<cudaEvent_t> tev;
     struct TevGuard {
         std::vector<cudaEvent_t>& v;
         ~TevGuard() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
     } tev_guard{tev};
+    cudaStream_t ps = ctx->stream;                                  // stream of the pack kernels
+    if (overlap) {
+        MMG_TRY(ensure_side_stream(ctx));
+        ps = ctx->stream2;
+        // the resident block, the zeroed Gram and the cleared flag are ordered on the main stream
+        MMG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->ev0, 0));
+    }
+    int table_kb = -1;
     for (int64_t s0 = 0; s0 < snp_count; s0 += chunk) {
+        const int64_t ci = s0 / chunk;
         const int64_t cnt = std::min(chunk, snp_count - s0);
         const int64_t kbytes = fp4 ? round_up(cnt, 256) * c / 2 : round_up(cnt, 128) * c;   // whole 128-byte K blocks
-        cudaEvent_t e_p0 = ctx->ev0, e_p1 = ctx->ev1, e_g0 = ctx->kev0, e_g1 = ctx->kev1;
-        if (src) {
-            MMG_TRY(issue_copy(s0 / chunk));
-            MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, src->done[(size_t)(s0 / chunk)], 0));
-            for (cudaEvent_t* e : {&e_p0, &e_p1, &e_g0, &e_g1}) {
-                MMG_CUDA(ctx, cudaEventCreate(e));
-                tev.push_back(*e);
-            }
+        int8_t* slot = ctx->pack + (overlap ? (ci & 1) * slot_bytes : 0);
+        cudaEvent_t ev4[4];                                          // pack begin / end, Gram begin / end
+        for (cudaEvent_t& e : ev4) {
+            MMG_CUDA(ctx, cudaEventCreate(&e));
+            tev.push_back(e);
         }
+        if (src) {
+            MMG_TRY(issue_copy(ci));
+            MMG_CUDA(ctx, cudaStreamWaitEvent(ps, src->done[(size_t)ci], 0));
+        }
+        if (overlap && ci >= 2) MMG_CUDA(ctx, cudaStreamWaitEvent(ps, tev[(size_t)(4 * (ci - 2) + 3)], 0));   // the slot's previous Gram
         // ---- pack ----
-        cudaEventRecord(e_p0, ctx->stream);
+        cudaEventRecord(ev4[0], ps);
         dim3 pgrid((unsigned)((fp4 ? round_up(cnt, 256) : round_up(cnt, 128)) / 128), (unsigned)((n + 63) / 64));   // SNPs >= cnt pack to zeros
         if (coding == MMG_CODING_BINARY) {
-            if (fp4) pack_kmajor_kernel<0, true><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
-            else pack_kmajor_kernel<0><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+            if (fp4) pack_kmajor_kernel<0, true><<<pgrid, 256, 0, ps>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, slot, p_pitch, ctx->flag_d);
+            else pack_kmajor_kernel<0><<<pgrid, 256, 0, ps>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, slot, p_pitch, ctx->flag_d);
         } else {
-            if (fp4) pack_kmajor_kernel<1, true><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
-            else pack_kmajor_kernel<1><<<pgrid, 256, 0, ctx->stream>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, ctx->pack, p_pitch, ctx->flag_d);
+            if (fp4) pack_kmajor_kernel<1, true><<<pgrid, 256, 0, ps>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, slot, p_pitch, ctx->flag_d);
+            else pack_kmajor_kernel<1><<<pgrid, 256, 0, ps>>>(ctx->snps, ctx->pitch, snp_begin + s0, cnt, n, slot, p_pitch, ctx->flag_d);
         }
         MMG_TRY(launch_check(ctx, "pack_kmajor_kernel"));
-        cudaEventRecord(e_p1, ctx->stream);
+        cudaEventRecord(ev4[1], ps);
+        if (overlap) MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev4[1], 0));
         // ---- Gram ----
         const int accumulate = ctx->g_zero ? 0 : 1;
-        cudaEventRecord(e_g0, ctx->stream);
         if (impl == MMG_IMPL_TCGEN05) {
             CUtensorMap tmA, tmB;
-            MMG_TRY(make_tmap_u8(ctx, &tmA, ctx->pack, kbytes, n, p_pitch, TC_BM));
-            MMG_TRY(make_tmap_u8(ctx, &tmB, ctx->pack, kbytes, n, p_pitch, TC_BN / gram_cs));
-            build_table((int)(kbytes / TC_BK));
-            MMG_TRY(ensure_tiles(ctx, table));
-            GramEpi::Params ep{ctx->G, g_pad, accumulate};
+            MMG_TRY(make_tmap_u8(ctx, &tmA, slot, kbytes, n, p_pitch, TC_BM));
+            MMG_TRY(make_tmap_u8(ctx, &tmB, slot, kbytes, n, p_pitch, TC_BN / gram_cs));
+            if (table_kb != (int)(kbytes / TC_BK)) {                // same table for every full chunk
+                table_kb = (int)(kbytes / TC_BK);
+                build_table(table_kb);
+                MMG_TRY(ensure_tiles(ctx, table));
+            }
+            cudaEventRecord(ev4[2], ctx->stream);
             const int ngroups = (int)table.size() * gram_cs;
+            const int pf = env_int("MMG_GRAM_PREFETCH", 0);         // L2 prefetch distance of the operand streams in K blocks; off: measured 34 -> 52 ms at 8
             if (fp4) {
                 GramEpiF4::Params ep4{ctx->G, g_pad, accumulate};
                 if (gram_cs == 2)
-                    MMG_TRY((launch_tc_gemm<GramEpiF4, 2, TC_KIND_MXF4>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep4, "tc_gemm_i8_kernel<GramEpiF4,2,mxf4>")));
+                    MMG_TRY((launch_tc_gemm<GramEpiF4, 2, TC_KIND_MXF4>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep4, "tc_gemm_i8_kernel<GramEpiF4,2,mxf4>", L2_EVICT_NORMAL, L2_EVICT_NORMAL, pf)));
                 else
-                    MMG_TRY((launch_tc_gemm<GramEpiF4, 1, TC_KIND_MXF4>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, 0, ep4, "tc_gemm_i8_kernel<GramEpiF4,1,mxf4>")));
-            } else if (gram_cs == 2)
-                MMG_TRY((launch_tc_gemm<GramEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep, "tc_gemm_i8_kernel<GramEpi,2>")));
-            else
-                MMG_TRY((launch_tc_gemm<GramEpi, 1>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, 0, ep, "tc_gemm_i8_kernel<GramEpi,1>")));
+                    MMG_TRY((launch_tc_gemm<GramEpiF4, 1, TC_KIND_MXF4>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, 0, ep4, "tc_gemm_i8_kernel<GramEpiF4,1,mxf4>", L2_EVICT_NORMAL, L2_EVICT_NORMAL, pf)));
+            } else {
+                GramEpi::Params ep{ctx->G, g_pad, accumulate};
+                if (gram_cs == 2)
+                    MMG_TRY((launch_tc_gemm<GramEpi, 2>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep, "tc_gemm_i8_kernel<GramEpi,2>", L2_EVICT_NORMAL, L2_EVICT_NORMAL, pf)));
+                else
+                    MMG_TRY((launch_tc_gemm<GramEpi, 1>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, 0, ep, "tc_gemm_i8_kernel<GramEpi,1>", L2_EVICT_NORMAL, L2_EVICT_NORMAL, pf)));
+            }
         } else {
+            cudaEventRecord(ev4[2], ctx->stream);
             dim3 ggrid((unsigned)((n + 63) / 64), (unsigned)((n + 63) / 64));
-            gram_simt_kernel<<<ggrid, 256, 0, ctx->stream>>>(ctx->pack, p_pitch, n, kbytes, ctx->G, g_pad, accumulate);
+            gram_simt_kernel<<<ggrid, 256, 0, ctx->stream>>>(slot, p_pitch, n, kbytes, ctx->G, g_pad, accumulate);
             MMG_TRY(launch_check(ctx, "gram_simt_kernel"));
         }
-        cudaEventRecord(e_g1, ctx->stream);
+        cudaEventRecord(ev4[3], ctx->stream);
         ctx->g_zero = false;
-        if (src) continue;                                      // timed after the loop
-        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-        pack_s += ms * 1e-3;
-        cudaEventElapsedTime(&ms, ctx->kev0, ctx->kev1);
-        gram_ms += ms;
     }
-    if (src) {
-        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (size_t i = 0; i + 3 < tev.size(); i += 4) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
-            pack_s += ms * 1e-3;
-            cudaEventElapsedTime(&ms, tev[i + 2], tev[i + 3]);
-            gram_ms += ms;
-        }
+    MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));             // every pack was waited for by its Gram
+    for (size_t i = 0; i + 3 < tev.size(); i += 4) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+        pack_s += ms * 1e-3;
+        cudaEventElapsedTime(&ms, tev[i + 2], tev[i + 3]);
+        gram_ms += ms;
     }
     ctx->timers["pack"].seconds += pack_s;
     ctx->timers["pack"].calls += 1;

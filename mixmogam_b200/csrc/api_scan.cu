@@ -541,11 +541,7 @@ static int scan_tc_run(mmg_ctx* ctx, int T, const MmgMat* const* Rs, const doubl
         MMG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ov1, 0));
     }
     if (!A_given && env_int("MMG_SCAN_OVERLAP", 1)) {
-        if (!ctx->stream2) {
-            MMG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-            MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov0, cudaEventDisableTiming));
-            MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov1, cudaEventDisableTiming));
-        }
+        MMG_TRY(ensure_side_stream(ctx));
         MMG_CUDA(ctx, cudaMemsetAsync(d_dg_pre, 0, (size_t)T * n_padN * sizeof(double), ctx->stream));
         const double one = 1.0, zero = 0.0;
         for (int t = 0; t < T; ++t) {
@@ -787,6 +783,16 @@ static int perm_scan_tc(mmg_ctx* ctx, const MmgMat* R, const MmgMat* Wt, int cen
 
 // x~.x~, x~.V[0] and the statistics of SNP rows [snp_begin, +snp_count) of the resident block, left on the device in `out`:
 // xx | xy | rss | f | p | var_perc (snp_count doubles each), then -- with want_dots -- x~.V[v] for v < nv ([nv][snp_count]).
+// What MMG_IMPL_AUTO means for a scan of snp_count SNPs: the int8 quadratic-form scan pays a one-off n^3 product (A = R'R,
+// digit planes, pilot: ~15 ms at n = 10k) before its 0.14 us per SNP; the FP64 tensor-core scan rotates each SNP directly
+// (2 n^2 flops, ~8 us at n = 10k) with no set-up.  Short scans -- the single-SNP calls of the stepwise / MLMM callers
+// (linear_models.py:2720,2825), the top-hit lists -- therefore take the FP64 kernel: crossover near snp_count = n / 8.
+static int resolve_scan_impl(mmg_ctx* ctx, int impl, int64_t snp_count) {
+    if (impl != MMG_IMPL_AUTO) return impl;
+    if (getenv("MMG_SCAN_IMPL")) return env_impl("MMG_SCAN_IMPL", MMG_IMPL_TCGEN05);
+    return snp_count * 8 <= ctx->n ? MMG_IMPL_DMMA : MMG_IMPL_TCGEN05;
+}
+
 static int scan_device(mmg_ctx* ctx, MmgMat* R, const double* V, int nv, double h0_rss, double n_p, int impl, int64_t snp_begin,
                        int64_t snp_count, double lbeta, DevBuf& out, bool want_dots) {
     const int64_t n = ctx->n, n_out = R->rows;
@@ -923,8 +929,9 @@ int mmg_emmax_scan_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, double
     MMG_CHECK(ctx, R->cols == ctx->n, "R must have n = %lld columns (has %lld)", (long long)ctx->n, (long long)R->cols);
     MMG_CHECK(ctx, V && nv >= 1 && nv <= 16, "need 1..16 rotated-space vectors (V[0] = residual phenotype)");
     MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
-    if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_SCAN_IMPL", MMG_IMPL_TCGEN05);
+    impl = resolve_scan_impl(ctx, impl, snp_count);
     MMG_CHECK(ctx, impl == MMG_IMPL_DMMA || impl == MMG_IMPL_TCGEN05, "unsupported impl %d for the scan", impl);
+    ctx->last_scan_impl = impl;
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const double lbeta = lbeta_host(0.5 * n_p, 0.5);
     DevBuf out;
@@ -967,8 +974,9 @@ int mmg_emmax_scan_betas_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int q0, 
     MMG_CHECK(ctx, V && q0 >= 1 && q0 <= 15 && Ainv && c0 && h0_betas, "need V = [y~res; h0_X'] with 1..15 fixed-effect columns");
     MMG_CHECK(ctx, ps && f_stats && rss && var_perc && betas, "all outputs are required");
     MMG_CHECK(ctx, snp_begin >= 0 && snp_count > 0 && snp_begin + snp_count <= ctx->m, "SNP range out of bounds");
-    if (impl == MMG_IMPL_AUTO) impl = env_impl("MMG_SCAN_IMPL", MMG_IMPL_TCGEN05);
+    impl = resolve_scan_impl(ctx, impl, snp_count);
     MMG_CHECK(ctx, impl == MMG_IMPL_DMMA || impl == MMG_IMPL_TCGEN05, "unsupported impl %d for the scan", impl);
+    ctx->last_scan_impl = impl;
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const double lbeta = lbeta_host(0.5 * n_p, 0.5);
     DevBuf out, bbuf;
@@ -1170,11 +1178,7 @@ int mmg_scan_prepass_begin(mmg_ctx* ctx, mmg_mat Rh, const double* yres, int64_t
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t n = ctx->n, n_out = R->rows, n_padN = round_up(n, TC_BN);
     ctx->early_prepass = false;
-    if (!ctx->stream2) {
-        MMG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-        MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov0, cudaEventDisableTiming));
-        MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov1, cudaEventDisableTiming));
-    }
+    MMG_TRY(ensure_side_stream(ctx));
     WsBuf pre, in;
     MMG_TRY(ws_get(ctx, MMG_WS_SCAN_PRE, (3 * snp_count + n_padN) * (int64_t)sizeof(double), &pre.p));       // the layout scan_tc_run expects (T = 1)
     MMG_TRY(ws_get(ctx, MMG_WS_SCAN_EARLY, (2 * n_padN + n_out) * (int64_t)sizeof(double), &in.p));

@@ -162,7 +162,7 @@ template <class Epi, int CS, int KIND = TC_KIND_I8>
 static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcTile* tiles_d, int num_groups,
                           int tiles_per_group, int table_stride, int group_m_step, int rank_m_step,
                           const typename Epi::Params& ep, const char* name, uint64_t hint_a = L2_EVICT_NORMAL,
-                          uint64_t hint_b = L2_EVICT_NORMAL) {
+                          uint64_t hint_b = L2_EVICT_NORMAL, int prefetch = 0) {
     auto kern = tc_gemm_i8_kernel<Epi, CS, KIND>;
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(TC_THREADS);
@@ -182,7 +182,7 @@ static int launch_tc_gemm(mmg_ctx* ctx, const CUtensorMap& tmA, const CUtensorMa
     // L2 eviction priority of the two operand streams: MMG_TC_HINT_A / MMG_TC_HINT_B = normal | first | last
     const uint64_t pa = env_policy("MMG_TC_HINT_A", hint_a), pb = env_policy("MMG_TC_HINT_B", hint_b);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tiles_d, num_groups, tiles_per_group, table_stride, group_m_step,
-                                       rank_m_step, pa, pb, ep);
+                                       rank_m_step, pa, pb, ep, prefetch);
     ctx->launches += 1;
     if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of %s (cluster %d, grid %d) failed: %s", name, CS, clusters * CS,
                                       cudaGetErrorString(e));
@@ -201,6 +201,15 @@ static int env_impl(const char* var, int dflt) {
 
 static double lbeta_host(double a, double b) {
     return (double)(lgammal((long double)a) + lgammal((long double)b) - lgammal((long double)a + (long double)b));
+}
+
+// the side stream (pack kernels under the Gram, the scan's linear pre-pass under the R'R product) and its two join events
+static int ensure_side_stream(mmg_ctx* ctx) {
+    if (ctx->stream2) return MMG_OK;
+    MMG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov0, cudaEventDisableTiming));
+    MMG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ov1, cudaEventDisableTiming));
+    return MMG_OK;
 }
 
 static int ensure_tiles(mmg_ctx* ctx, const std::vector<TcTile>& tiles) {

@@ -40,7 +40,7 @@ __global__ void bench_copy_kernel(const uint4* __restrict__ src, uint4* __restri
 // (measures whether TMEM reads take cycles from the tensor pipe).  PAIR: cta_group::2 (M = 256 over two CTAs).
 // F4: e2m1 operands, kind::mxf4.block_scale with unit scale factors (K = 64 per instruction), one accumulator (the Gram's form).
 template <bool PAIR, bool F4 = false>
-__global__ void __launch_bounds__(TC_THREADS, 1) bench_imma_kernel(int iters, int ldtm, unsigned* sink) {
+__global__ void __launch_bounds__(192, 1) bench_imma_kernel(int iters, int ldtm, unsigned* sink) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t done_bar;
@@ -330,7 +330,7 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
         const int iters = 40000, smem = TC_A_BYTES + TC_B_BYTES + 1024;
         const int grid = pair ? ctx->sm_count / 2 * 2 : ctx->sm_count;
         cudaLaunchConfig_t cfg{};
-        cfg.blockDim = dim3(TC_THREADS);
+        cfg.blockDim = dim3(192);            // MMA warp + four read-back warps
         cfg.gridDim = dim3((unsigned)grid);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = ctx->stream;

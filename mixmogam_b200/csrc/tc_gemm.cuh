@@ -21,7 +21,7 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK;                 // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK;                 // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;   // 48 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;          // producer, MMA issuer, 4 epilogue warps, L2 prefetcher
 constexpr int TC_ACC_STAGES = 2;
 constexpr int TC_TMEM_COLS = TC_ACC_STAGES * TC_BN;       // 512
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -63,7 +63,7 @@ template <class Epi, int CS, int KIND = TC_KIND_I8>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcTile* __restrict__ tiles, int num_groups, int tiles_per_group, int table_stride,
-                  int group_m_step, int rank_m_step, uint64_t policy_a, uint64_t policy_b, const typename Epi::Params ep) {
+                  int group_m_step, int rank_m_step, uint64_t policy_a, uint64_t policy_b, const typename Epi::Params ep, int prefetch = 0) {
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle wants 1024-byte aligned stage bases (the dynamic smem base is the same in every CTA of a
     // cluster, so CTA-relative offsets agree across the cluster)
@@ -75,6 +75,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tfull_bar = bars + 2 * TC_STAGES;              // [kAcc]
     uint64_t* tempty_bar = bars + 2 * TC_STAGES + kAcc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_ACC_STAGES);
+    volatile uint32_t* progress = tmem_slot + 1;             // K blocks the producer has requested so far (read by the prefetch warp)
 
     // warp index through a shuffle: the role branches are then provably warp-uniform, so loop counters, addresses and
     // descriptors live in uniform registers and UTCIMMA / UTMALDG issue without per-lane ELECT loops
@@ -88,6 +89,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int kBRows = TC_BN / CS;                       // B rows fetched by one CTA
 
     if (warp == 0 && lane == 0) {
+        *progress = 0u;
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -111,7 +113,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (KIND == TC_KIND_MXF4) {
         // constant scale factors 2^0 (UE8M0 0x7f) in every byte of columns 256..511, all 128 lanes: whatever layout the MMA
         // reads its A / B scale vectors in, it reads ones
-        if (warp >= 2) {
+        if (warp >= 2 && warp < 6) {
             const uint32_t taddr = tmem_base + TC_SF_COL + (static_cast<uint32_t>((warp & 3) * 32) << 16);
             for (int c = 0; c < (TC_TMEM_COLS - TC_SF_COL) / 8; ++c) tmem_st_32x8_const(taddr + c * 8, 0x7f7f7f7fu);
             tmem_st_wait();
@@ -126,6 +128,7 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         {
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t requested = 0;
             for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
                 const int g = cg * CS + crank;
                 for (int ti = 0; ti < tiles_per_group; ++ti) {
@@ -145,6 +148,31 @@ tc_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             }
                         }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        ++requested;
+                        if (prefetch > 0 && lane == 0) *progress = requested;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 6) {
+        // ===================== L2 prefetch warp =====================
+        // walks the producer's K-block sequence `prefetch` blocks ahead of what it has requested (cp.async.bulk.prefetch.tensor):
+        // the 4-stage ring covers ~2000 cycles, less than an HBM miss under load, so the lines are brought into L2 beforehand
+        if (prefetch > 0) {
+            uint32_t done = 0;
+            for (int cg = cluster_id; cg < num_cgroups; cg += num_clusters) {
+                const int g = cg * CS + crank;
+                for (int ti = 0; ti < tiles_per_group; ++ti) {
+                    TcTile t = tiles[(int64_t)cg * table_stride + ti];
+                    t.m0 += g * group_m_step + crank * rank_m_step;
+                    for (int kb = t.kb0; kb < t.kb1; ++kb) {
+                        while ((int)(done - *progress) >= prefetch) __nanosleep(64);
+                        if (elect_one()) {
+                            tma_prefetch_2d(&tmA, kb * TC_BK, t.m0);
+                            tma_prefetch_2d(&tmB, kb * TC_BK, t.n0 + crank * kBRows);
+                        }
+                        ++done;
                     }
                 }
             }

@@ -47,11 +47,15 @@ def test_gram_bit_exact(ctx, monkeypatch, impl, coding, m, n):
     assert np.array_equal(G.astype(np.int64), _gram_ref(snps, coding))
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_i8'])
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_i8', 'tcgen05_overlap'])
 def test_gram_chunk_boundary_and_accumulate(ctx, monkeypatch, impl):
-    """m crosses the 65536-SNP pack chunk; a second call with reset=False accumulates (multi-call == one call)."""
-    impl = _gram_kind(monkeypatch, impl)
+    """m crosses the 65536-SNP pack chunk (three chunks with the packs of the later ones on the side stream under the previous
+    Gram for 'tcgen05_overlap'); a second call with reset=False accumulates (multi-call == one call)."""
     n, m = 130, 70000
+    if impl == 'tcgen05_overlap':
+        monkeypatch.setenv('MMG_GRAM_OVERLAP', '1')
+        impl, m = 'tcgen05', 140000
+    impl = _gram_kind(monkeypatch, impl)
     snps = _rand_snps(m, n, 1, seed=5)
     ctx.invalidate_snps()
     ctx.ensure_snps(snps)

@@ -177,6 +177,46 @@ def test_scan_implementations_agree_and_match_oracle_sample(ctx, n, m):
     assert abs(ra['pseudo_heritability'] - ro['pseudo_heritability']) < 1e-8
 
 
+def test_single_snp_calls_take_the_low_latency_path(ctx):
+    """The stepwise / MLMM callers test one SNP at a time (`_emmax_f_test_([snp])`, linear_models.py:2720,2825): with
+    scan_impl='auto' a short scan goes to the FP64 tensor-core kernel (no n^3 set-up product), a long one to the int8 scan; both
+    match the oracle, with and without betas and with a cofactor."""
+    import time
+    from mixmogam_b200 import kinship, linear_models as lm
+    from oracle import reference_py3 as o
+    n, m = 1500, 4000
+    snps = o.synth_genotypes(m, n, 'diploid_int', seed=99)
+    ctx.invalidate_snps()
+    K = kinship.calc_ibs_kinship(snps, 'diploid_int')
+    y = o.synth_phenotype(snps, K, seed=3)
+    lmm = lm.LinearMixedModel(y)
+    lmm.add_random_effect(K)
+    lmm.add_factor(snps[7].astype(np.float64))                                   # a cofactor SNP, as in the stepwise loop
+    eig_L = lmm._get_eigen_L_()
+    res = lmm.get_estimates(eig_L=eig_L)
+    olmm = o.LinearMixedModel(y, dtype='double')
+    olmm.add_random_effect(K)
+    olmm.add_factor(snps[7].astype(np.float64))
+    ores = olmm.get_estimates(eig_L=olmm._get_eigen_L_())
+    for with_betas in (False, True):
+        one = [snps[123]]
+        lmm._emmax_f_test_(one, res['H_sqrt_inv'], emma_num=0, with_betas=with_betas)          # warm-up (handles, workspaces)
+        t0 = time.perf_counter()
+        r = lmm._emmax_f_test_(one, res['H_sqrt_inv'], emma_num=0, with_betas=with_betas)
+        dt = time.perf_counter() - t0
+        assert ctx.last_kernel_ms('scan_impl') == 3.0                             # MMG_IMPL_DMMA
+        ro = olmm._emmax_f_test_(one, ores['H_sqrt_inv'], emma_num=0, with_betas=with_betas)
+        assert neglog10_rel_err(r['ps'], ro['ps']) < 1e-6
+        np.testing.assert_allclose(r['rss'], np.asarray(ro['rss'], dtype=np.float64), rtol=1e-8)
+        if with_betas:
+            np.testing.assert_allclose(np.asarray(r['betas'], dtype=np.float64), np.asarray(ro['betas'], dtype=np.float64).reshape(1, -1),
+                                       rtol=1e-6, atol=1e-9)
+        assert dt < 0.25, 'single-SNP call took %.1f ms' % (1e3 * dt)
+    r_all = lmm._emmax_f_test_(snps, res['H_sqrt_inv'], emma_num=0)               # 4000 SNPs > n / 8: the int8 scan
+    assert ctx.last_kernel_ms('scan_impl') == 1.0
+    assert abs(-np.log10(r_all['ps'][123]) + np.log10(r['ps'][0])) <= 1e-6 * max(-np.log10(r['ps'][0]), 1e-3)
+
+
 @pytest.mark.parametrize('n,m,P', [(500, 3000, 70), (1300, 2000, 33)])
 def test_permutation_scan_tcgen05_matches_dmma(ctx, n, m, P):
     """The int8 tensor-core permutation scan (centred quadratic form + digit-plane GEMM) against the FP64 tensor-core

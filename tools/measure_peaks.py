@@ -24,7 +24,7 @@ def main():
     ctx = get_context(0)
     res = {'gpu': ctx.device_info()['name'], 'when': time.strftime('%Y-%m-%dT%H:%M:%SZ', time.gmtime()), 'idle': smi()}
     for key, which in (('dmma_tflops', 'dmma'), ('dfma_tflops', 'dfma'), ('copy_gbs', 'copy'), ('int8_single_cta_burst_tops', 'imma_tcgen05'),
-                       ('int8_burst_tops', 'imma_pair')):
+                       ('int8_burst_tops', 'imma_pair'), ('mxf4_burst_tops', 'mxf4_tcgen05')):
         res[key] = ctx.microbench(which)
     samples = []
     stop = []
@@ -37,6 +37,7 @@ def main():
     th.start()
     res['int8_sustained_tops'] = ctx.microbench('imma_pair_sustained2000')
     res['int8_single_cta_sustained_tops'] = ctx.microbench('imma_tcgen05_sustained2000')
+    res['mxf4_sustained_tops'] = ctx.microbench('mxf4_tcgen05_sustained2000')
     stop.append(1)
     th.join()
     sm = sorted(float(s[0]) for s in samples if s and s[0].replace('.', '').isdigit())
@@ -44,7 +45,7 @@ def main():
                          'power_w_max': max([float(s[2]) for s in samples if len(s) > 2 and s[2].replace('.', '').isdigit()] or [0]),
                          'sw_power_cap_seen': any(len(s) > 3 and s[3].lower().startswith('active') for s in samples)}
     res['how'] = ('libmixmogam_b200_bench.so (mixmogam_b200/csrc/microbench.cu): tcgen05.mma kind::i8 128(256)x256x32 issued back to back '
-                  'from shared-memory-resident operands, 148 CTAs; burst = second of two 40k-K-block launches, sustained = last '
+                  'from shared-memory-resident operands, 148 CTAs (mxf4: kind::mxf4.block_scale 128x256x64 on e2m1 operands, unit scales); burst = second of two 40k-K-block launches, sustained = last '
                   'quarter of ~2 s of back-to-back launches; dmma = mma.sync m8n8k4 f64 chains, 4 blocks/SM')
     json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'PEAKS_int8_fp64.json'), 'w'), indent=1)
     print(json.dumps(res, indent=1))
