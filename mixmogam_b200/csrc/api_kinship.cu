@@ -2,6 +2,7 @@
 // finalisation, and the IBD kinship (int8 digit planes or cuBLAS dsyrk).
 #include "common.cuh"
 #include "ibd_tc.cuh"
+#include "gram_pair.cuh"
 
 using namespace mmg;
 
@@ -11,10 +12,37 @@ void kinship_init_attrs() {
     cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpiF4, 1, TC_KIND_MXF4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<GramEpiF4, 2, TC_KIND_MXF4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<IbdEpi, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_i8_kernel<IbdEpi, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }
 }  // namespace mmg
+
+// CTA-pair Gram (gram_pair.cuh): launch configuration and the number of co-resident clusters (= persistent grid / 2)
+static void gram_pair_config(mmg_ctx* ctx, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int clusters) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.blockDim = dim3(GP_THREADS);
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.dynamicSmemBytes = GP_SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+}
+static int gram_pair_max_clusters(mmg_ctx* ctx) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    gram_pair_config(ctx, cfg, attr, ctx->sm_count / 2);
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, gram_pair_kernel, &cfg) != cudaSuccess || q <= 0) {
+        cudaGetLastError();
+        q = ctx->sm_count / 2;
+    }
+    return std::max(1, std::min(q, ctx->sm_count / 2));
+}
 
 extern "C" {
 
@@ -224,13 +252,18 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     // With a cluster of 2, one entry covers the row-tile pair (im, im+1) of a column tile (2 jn + 2 is even).
     int gram_cs = env_int("MMG_GRAM_CLUSTER", 2);
     if (gram_cs != 1) gram_cs = 2;
+    // MMG_GRAM_PAIR (default 1): the e2m1 Gram as a CTA-pair MMA (tcgen05.mma.cta_group::2, gram_pair.cuh) instead of two
+    // single-CTA MMAs that multicast the shared operand
+    const bool pair = fp4 && gram_cs == 2 && env_int("MMG_GRAM_PAIR", 1) != 0;
     std::vector<TcTile> tiles, table;
     int gram_clusters = 1;
     if (impl == MMG_IMPL_TCGEN05) {
         const int tiles_n = (n + TC_BN - 1) / TC_BN;
         for (int jn = 0; jn < tiles_n; ++jn)
             for (int im = 0; im <= 2 * jn + 1; im += gram_cs) tiles.push_back(TcTile{im * TC_BM, jn * TC_BN, 0, 0, 0, 0, 0, 0});
-        gram_clusters = gram_cs == 2 ? tc_gemm_max_clusters<GramEpi, 2>(ctx) : tc_gemm_max_clusters<GramEpi, 1>(ctx);
+        if (pair) gram_clusters = gram_pair_max_clusters(ctx);
+        else if (fp4) gram_clusters = gram_cs == 2 ? tc_gemm_max_clusters<GramEpiF4, 2, TC_KIND_MXF4>(ctx) : tc_gemm_max_clusters<GramEpiF4, 1, TC_KIND_MXF4>(ctx);
+        else gram_clusters = gram_cs == 2 ? tc_gemm_max_clusters<GramEpi, 2>(ctx) : tc_gemm_max_clusters<GramEpi, 1>(ctx);
     }
     // Tile table of one chunk.  Entry e runs on cluster e % W (W co-resident clusters), every tile costs the same, so
     // nt = q W + r tiles take q + 1 waves with only r clusters busy in the last one (n = 10k: 820 = 11 x 74 + 6, an 8 %
@@ -459,7 +492,18 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
             cudaEventRecord(ev4[2], ctx->stream);
             const int ngroups = (int)table.size() * gram_cs;
             const int pf = env_int("MMG_GRAM_PREFETCH", 0);         // L2 prefetch distance of the operand streams in K blocks; off: measured 34 -> 52 ms at 8
-            if (fp4) {
+            if (pair) {
+                GramEpiF4::Params ep4{ctx->G, g_pad, accumulate};
+                CUtensorMap tmBh;                                   // this CTA's half of the B tile: a box of 128 rows
+                MMG_TRY(make_tmap_u8(ctx, &tmBh, slot, kbytes, n, p_pitch, TC_BN / 2));
+                cudaLaunchConfig_t cfg;
+                cudaLaunchAttribute attr[1];
+                const int nt = (int)table.size();
+                gram_pair_config(ctx, cfg, attr, std::max(1, std::min(nt, gram_clusters)));
+                cudaError_t e = cudaLaunchKernelEx(&cfg, gram_pair_kernel, tmA, tmBh, (const TcTile*)ctx->tiles_d, nt, (uint64_t)L2_EVICT_NORMAL, ep4);
+                ctx->launches += 1;
+                if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of gram_pair_kernel (grid %u) failed: %s", cfg.gridDim.x, cudaGetErrorString(e));
+            } else if (fp4) {
                 GramEpiF4::Params ep4{ctx->G, g_pad, accumulate};
                 if (gram_cs == 2)
                     MMG_TRY((launch_tc_gemm<GramEpiF4, 2, TC_KIND_MXF4>(ctx, tmA, tmB, (const TcTile*)ctx->tiles_d, ngroups, 1, 1, 0, TC_BM, ep4, "tc_gemm_i8_kernel<GramEpiF4,2,mxf4>", L2_EVICT_NORMAL, L2_EVICT_NORMAL, pf)));
