@@ -191,7 +191,10 @@ int mmg_snps_upload_packed2(mmg_ctx* ctx, const uint8_t* packed, int64_t m, int6
     int sl = 0;
     for (int64_t r0 = 0; r0 < m; r0 += chunk, sl ^= 1) {
         const int64_t cnt = std::min(chunk, m - r0);
-        MMG_CUDA(ctx, cudaMemcpy2DAsync(slot[sl].p, p2_ld, packed + r0 * ld_bytes, ld_bytes, width, cnt, cudaMemcpyHostToDevice, ctx->stream));
+        if (ld_bytes == p2_ld)                               // rows at the slot's pitch: one contiguous copy (see queue_prepacked)
+            MMG_CUDA(ctx, cudaMemcpyAsync(slot[sl].p, packed + r0 * ld_bytes, (size_t)(cnt * p2_ld), cudaMemcpyHostToDevice, ctx->stream));
+        else
+            MMG_CUDA(ctx, cudaMemcpy2DAsync(slot[sl].p, p2_ld, packed + r0 * ld_bytes, ld_bytes, width, cnt, cudaMemcpyHostToDevice, ctx->stream));
         const int64_t words = cnt * (p2_ld >> 2);
         unpack2_kernel<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(slot[sl].as<uint8_t>(), p2_ld, ctx->snps + r0 * ctx->pitch, ctx->pitch, cnt, n);
         MMG_TRY(launch_check(ctx, "unpack2_kernel"));
@@ -360,8 +363,14 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
         const int64_t s0 = ci * chunk, cnt = chunk_rows(ci);
         const int sl = src->next_slot;
         const int64_t width = (ctx->n + 3) / 4;
-        MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_dev[sl], p2_ld, src->packed2 + (snp_begin + s0) * src->ld2, src->ld2, width, cnt,
-                                        cudaMemcpyHostToDevice, src->stream2));
+        // rows at the slot's own pitch (what _lib.pack_genotypes writes): ONE contiguous copy at the link rate -- a strided copy of
+        // 2500-byte rows reaches a third of it (138 instead of ~50 ms for 1M SNPs); unpack2_kernel masks the codes beyond n
+        if (src->ld2 == p2_ld)
+            MMG_CUDA(ctx, cudaMemcpyAsync(ctx->stage_dev[sl], src->packed2 + (snp_begin + s0) * src->ld2, (size_t)(cnt * p2_ld), cudaMemcpyHostToDevice,
+                                          src->stream2));
+        else
+            MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_dev[sl], p2_ld, src->packed2 + (snp_begin + s0) * src->ld2, src->ld2, width, cnt,
+                                            cudaMemcpyHostToDevice, src->stream2));
         const int64_t words = cnt * (p2_ld >> 2);
         unpack2_kernel<<<(unsigned)((words + 255) / 256), 256, 0, src->stream2>>>(ctx->stage_dev[sl], p2_ld, ctx->snps + (snp_begin + s0) * ctx->pitch,
                                                                                 ctx->pitch, cnt, ctx->n);
