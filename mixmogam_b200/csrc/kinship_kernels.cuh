@@ -53,8 +53,8 @@ static __global__ void __launch_bounds__(256) pack_kmajor_kernel(const int8_t* _
         for (int j = 0; j < 4; ++j) {
             const int64_t s = s0 + 4 * quad + j;
             r[j] = (s < s_count) ? *reinterpret_cast<const uint32_t*>(snps + (s_begin + s) * pitch + i0 + 4 * i4) : 0u;
-            const uint32_t maxv = (CODING == 0) ? 0x01010101u : 0x02020202u;
-            bad |= (__vcmpgtu4(r[j], maxv) != 0u);
+            // a byte outside the coding's domain: any bit above bit 0 (binary); any bit above bit 1, or the value 3 (diploid)
+            bad |= (CODING == 0 ? (r[j] & 0xfefefefeu) : ((r[j] & 0xfcfcfcfcu) | (r[j] & (r[j] >> 1) & 0x01010101u))) != 0u;
         }
         const uint32_t t0 = __byte_perm(r[0], r[1], 0x5140), t1 = __byte_perm(r[2], r[3], 0x5140);
         const uint32_t t2 = __byte_perm(r[0], r[1], 0x7362), t3 = __byte_perm(r[2], r[3], 0x7362);
@@ -89,8 +89,9 @@ static __global__ void __launch_bounds__(256) pack_kmajor_kernel(const int8_t* _
                     // x = 1 -> 0x2, x = 0 -> 0xa
                     a[k] = squeeze_nibbles((0x0a0a0a0au ^ ((xs[k] & 0x01010101u) << 3)) & m);
                 } else {
-                    a[k] = squeeze_nibbles((__vcmpgeu4(xs[k], 0x01010101u) & 0x02020202u & m));
-                    b[k] = squeeze_nibbles((__vcmpgeu4(xs[k], 0x02020202u) & 0x02020202u & m));
+                    // bytes in {0, 1, 2} (anything else raised the flag above): [x >= 1] = bit0 | bit1, [x >= 2] = bit1; code 0x2 = 1.0
+                    a[k] = squeeze_nibbles(((xs[k] | (xs[k] << 1)) & 0x02020202u & m));
+                    b[k] = squeeze_nibbles((xs[k] & 0x02020202u & m));
                 }
             }
             if (CODING == 0) {
