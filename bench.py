@@ -333,7 +333,8 @@ def main():
     if rank == 0:
         rates = {'dmma_tflops': ctx.microbench('dmma'), 'int8_burst_tops': ctx.microbench('imma_pair'),
                  'int8_sustained_tops': ctx.microbench('imma_pair_sustained500'),
-                 'mxf4_sustained_tops': ctx.microbench('mxf4_tcgen05_sustained500')}
+                 'mxf4_sustained_tops': ctx.microbench('mxf4_tcgen05_sustained500'),
+                 'int8_digits_sustained_tops': ctx.microbench('imma_pair_digits_sustained500')}
 
     # ---- set-up outside the hot path: K once, its two eigendecompositions (timed separately; with several ranks eigh(K)
     #      runs on rank 0, eigh(S(K+I)S) on rank 1, both are broadcast) ----
@@ -533,6 +534,10 @@ def main():
                     'algorithmic_bytes': float(m_loc) * n + 8.0 * m_loc,
                     'peak_is': 'tcgen05 int8 issue rate (TOP/s), CTA-pair MMA, smem-resident operands, held 0.5 s; measured in this run',
                     'int8_burst_tops': burst, 'frac_of_burst_issue_rate': achieved / burst if burst else None,
+                    # the same MMA stream with the scan's operand DATA (full-range digit bytes in B instead of genotype-like bytes):
+                    # what the pipe sustains under the board's power cap on this kind of product
+                    'int8_sustained_tops_digit_operands': rates.get('int8_digits_sustained_tops'),
+                    'frac_of_rate_with_digit_operands': achieved / rates['int8_digits_sustained_tops'] if rates.get('int8_digits_sustained_tops') else None,
                     'twice_bf16_sustained': 2.0 * peaks['bf16_tflops_sustained'] if peaks.get('bf16_tflops_sustained') else None,
                     'twice_bf16_burst': 2.0 * peaks['bf16_tflops'] if peaks.get('bf16_tflops') else None,
                     'algorithmic_fp64_tflops': alg_flops / scan_s / 1e12, 'fp64_tensor_peak_measured': rates.get('dmma_tflops'),

@@ -66,7 +66,9 @@ int64_t mmg_launch_count(mmg_ctx* ctx);
 int mmg_timer_get(mmg_ctx* ctx, const char* name, double* seconds, int64_t* calls);
 int mmg_timer_reset(mmg_ctx* ctx);
 /* duration (ms) of the most recent launch of the dominant kernels, measured with CUDA
- * events on the launching stream: which = "gram" | "scan" | "perm" | "ibd" */
+ * events on the launching stream: which = "gram" | "scan" | "perm" | "ibd".  Two more keys report what the last call ran
+ * rather than a time: "gram_is_fp4" (1: the Gram multiplied e2m1 operands with tcgen05 kind::mxf4, 0: int8 / SIMT) and
+ * "scan_impl" (the MMG_IMPL_* value MMG_IMPL_AUTO resolved to in the last mmg_emmax_scan_f64 / _betas_f64 call). */
 int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms);
 
 /* the most recent int8 tensor-core scan: number of base-128 digit planes it used (chosen per call unless MMG_TC_SLICES
@@ -125,7 +127,11 @@ int mmg_snps_row_sums(mmg_ctx* ctx, int64_t* sums_host, int64_t* sumsq_host);
 /* Integer Gram of the resident genotype rows [snp_begin, snp_begin+snp_count):
  *   binary  (kinship.py:43-44): G += S S', S = 2x-1 (int8), K-dim = snp_count
  *   diploid (kinship.py:33-41): G += T T', T = [x>=1 | x>=2] thermometer planes, K-dim = 2*snp_count
- * accumulated into the ctx's int32 n x n Gram (bit-exact, order independent).  reset!=0 zeroes it first. */
+ * accumulated into the ctx's int32 n x n Gram (bit-exact, order independent).  reset!=0 zeroes it first.
+ * impl MMG_IMPL_TCGEN05 (default): the planes hold only 0 / +-1, exact e2m1 values, and are multiplied by
+ * tcgen05.mma.cta_group::2.kind::mxf4.block_scale (unit scales, FP32 accumulators holding exact integers) at twice the int8
+ * rate (MMG_GRAM_KIND=i8 keeps int8 operands, kind::i8); MMG_IMPL_SIMT: dp4a cross-check kernel.  All three give the same
+ * integers ("i8" in the entry-point names is the type of the resident genotypes). */
 int mmg_kinship_gram_i8(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64_t snp_count, int reset);
 /* The same Gram straight from HOST genotypes (kinship.py:29-32 walks the caller's `snps` chunk by chunk): the rows
  * stream into the resident block on a copy stream, one 65 536-SNP chunk at a time, and the pack + Gram of chunk c start

@@ -40,14 +40,23 @@ __global__ void bench_copy_kernel(const uint4* __restrict__ src, uint4* __restri
 // (measures whether TMEM reads take cycles from the tensor pipe).  PAIR: cta_group::2 (M = 256 over two CTAs).
 // F4: e2m1 operands, kind::mxf4.block_scale with unit scale factors (K = 64 per instruction), one accumulator (the Gram's form).
 template <bool PAIR, bool F4 = false>
-__global__ void __launch_bounds__(192, 1) bench_imma_kernel(int iters, int ldtm, unsigned* sink) {
+__global__ void __launch_bounds__(192, 1) bench_imma_kernel(int iters, int ldtm, unsigned* sink, int bfull = 0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t done_bar;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < (TC_A_BYTES + TC_B_BYTES) / 4; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(smem)[i] = (0x9E3779B9u * (i + 1)) & (F4 ? 0x22222222u : 0x03030303u);   // genotype-like bytes 0..3 | e2m1 0 / 1.0
+    for (int i = threadIdx.x; i < (TC_A_BYTES + TC_B_BYTES) / 4; i += blockDim.x) {
+        uint32_t h = 0x9E3779B9u * (i + 1);
+        if (bfull && i >= TC_A_BYTES / 4) {
+            // the scan's B operand: base-256 digits, every byte value -- the multiplier arrays toggle far more than on genotype-like
+            // bytes, which is what the power-capped rate of a real int8 product depends on
+            h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+            reinterpret_cast<uint32_t*>(smem)[i] = h;
+        } else {
+            reinterpret_cast<uint32_t*>(smem)[i] = h & (F4 ? 0x22222222u : 0x03030303u);   // genotype-like bytes 0..3 | e2m1 0 / 1.0
+        }
+    }
     if (threadIdx.x == 0) {
         mbar_init(&done_bar, 1);
         mbar_fence_init();
@@ -322,9 +331,11 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
         return run_bench_ldtm<16, 32>(ctx, mma, value);
     }
     if (!strncmp(which, "imma", 4) || !strncmp(which, "mxf4", 4)) {
-        // "imma_tcgen05" | "imma_pair" | "imma_tcgen05_ldtm<k>" | "imma_pair_ldtm<k>" | "mxf4_tcgen05": TOP/s
+        // "imma_tcgen05" | "imma_pair" | "imma_tcgen05_ldtm<k>" | "imma_pair_ldtm<k>" | "mxf4_tcgen05": TOP/s; "..._digits": the B operand
+        // holds full-range bytes (the scan's digit planes) instead of genotype-like ones
         const bool f4 = !strncmp(which, "mxf4", 4);
         const bool pair = !f4 && strstr(which, "pair") != nullptr;
+        const int bfull = (!f4 && strstr(which, "digits") != nullptr) ? 1 : 0;
         const char* l = strstr(which, "ldtm");
         const int ldtm = l ? std::max(1, atoi(l + 4)) : 0;
         const int iters = 40000, smem = TC_A_BYTES + TC_B_BYTES + 1024;
@@ -345,9 +356,9 @@ int mmg_microbench(mmg_ctx* ctx, const char* which, double* value) {
         cudaFuncSetAttribute(bench_imma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(bench_imma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         auto launch = [&]() -> int {
-            cudaError_t e = f4 ? cudaLaunchKernelEx(&cfg, bench_imma_kernel<false, true>, iters, 0, (unsigned*)ctx->scratch)
-                          : pair ? cudaLaunchKernelEx(&cfg, bench_imma_kernel<true>, iters, ldtm, (unsigned*)ctx->scratch)
-                                 : cudaLaunchKernelEx(&cfg, bench_imma_kernel<false>, iters, ldtm, (unsigned*)ctx->scratch);
+            cudaError_t e = f4 ? cudaLaunchKernelEx(&cfg, bench_imma_kernel<false, true>, iters, 0, (unsigned*)ctx->scratch, 0)
+                          : pair ? cudaLaunchKernelEx(&cfg, bench_imma_kernel<true>, iters, ldtm, (unsigned*)ctx->scratch, bfull)
+                                 : cudaLaunchKernelEx(&cfg, bench_imma_kernel<false>, iters, ldtm, (unsigned*)ctx->scratch, bfull);
             ctx->launches += 1;
             if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "bench_imma_kernel launch failed: %s", cudaGetErrorString(e));
             return MMG_OK;

@@ -38,6 +38,7 @@ def main():
     res['int8_sustained_tops'] = ctx.microbench('imma_pair_sustained2000')
     res['int8_single_cta_sustained_tops'] = ctx.microbench('imma_tcgen05_sustained2000')
     res['mxf4_sustained_tops'] = ctx.microbench('mxf4_tcgen05_sustained2000')
+    res['int8_digits_sustained_tops'] = ctx.microbench('imma_pair_digits_sustained2000')     # B operand: full-range bytes (digit planes)
     stop.append(1)
     th.join()
     sm = sorted(float(s[0]) for s in samples if s and s[0].replace('.', '').isdigit())
