@@ -118,6 +118,36 @@ def config4(args):
                       'perm_tests_per_s': (m - per) * P / max(timers.get('scan', 0.0), 1e-9), 'stage_seconds': timers}))
 
 
+def standin_eigen(ctx, n):
+    """Orthonormal stand-in for the two eigenbases where cuSOLVER's syevd refuses the size (n > 32768): ONE Householder reflection
+    H = I - 2 v v' with H e_1 = 1/sqrt(n) 1, built on the device.  eig_L = (ascending positive values, rows of H); eig_R = rows 1..n-1
+    of the same matrix (orthogonal to the intercept, as linear_models.py:600-615 requires) with the values shifted by one place.
+    The numbers that come out of the scan mean nothing; the kernels, their operands and their memory are the real ones."""
+    import torch
+    from mixmogam_b200 import parallel
+    from mixmogam_b200._lib import DeviceMatrix, LazyHostArray
+    from mixmogam_b200.linear_models import EigenDict
+    dev = 'cuda:%d' % ctx.device
+    v = torch.full((n,), -1.0 / np.sqrt(n), dtype=torch.float64, device=dev)
+    v[0] += 1.0
+    v = v / v.norm()
+    U = DeviceMatrix(ctx, n, n, zero=False)
+    ctx.sync()
+    t = parallel.mat_as_tensor(ctx, U)
+    step = 2048
+    for r0 in range(0, n, step):
+        r1 = min(n, r0 + step)
+        blk = -2.0 * torch.outer(v[r0:r1], v)
+        blk[torch.arange(r1 - r0, device=dev), torch.arange(r0, r1, device=dev)] += 1.0
+        t[r0:r1, :n].copy_(blk)
+    torch.cuda.synchronize()
+    del blk, t
+    torch.cuda.empty_cache()
+    w = np.linspace(0.2, 3.0, n)
+    return (EigenDict(values=w, vectors=LazyHostArray(U)),
+            EigenDict(values=w[1:].copy(), vectors=LazyHostArray(U, rows=(1, n)), _q=1))
+
+
 def config3(args):
     import torch
     from mixmogam_b200 import _lib, kinship, linear_models as lm
@@ -125,6 +155,7 @@ def config3(args):
     n, m = args.n or 50000, args.m or 500000
     dev = torch.device('cuda:0')
     snps = gen_torch(m, n, 20240601 + 3, False, dev)
+    torch.cuda.empty_cache()                                   # the generator's temporaries go back to the driver: the library needs the room
     rng = np.random.Generator(np.random.PCG64(20240601 + 3))
     y = rng.normal(0, 0.5, 10) @ snps[:10] + rng.standard_normal(n)
     ctx.timer_reset()
@@ -136,16 +167,24 @@ def config3(args):
     mdl.add_random_effect(K)
     K.free()
     t0 = time.perf_counter()
-    eig_L = mdl._get_eigen_L_()
-    eig_R = mdl._get_eigen_R_(X=mdl.X)
+    if args.standin_eigen:
+        eig_L, eig_R = standin_eigen(ctx, n)
+    else:
+        eig_L = mdl._get_eigen_L_()
+        eig_R = mdl._get_eigen_R_(X=mdl.X)
     t_eig = time.perf_counter() - t0
     t0 = time.perf_counter()
     r = mdl.emmax_f_test(snps, eig_L=eig_L, eig_R=eig_R, emma_num=0)
     t_scan = time.perf_counter() - t0
+    planes, rho = ctx.last_scan_info()
+    info = ctx.device_info()
     print(json.dumps({'config': 'configs[3] large cohort', 'n': n, 'm': m, 'kinship_s': t_kin, 'gram_kernel_ms': ctx.last_kernel_ms('gram'),
-                      'eigh_s': t_eig, 'reml_scan_s': t_scan, 'scan_kernel_ms': ctx.last_kernel_ms('scan'),
-                      'snp_tests_per_s_excl_eigh': m / (t_kin + t_scan), 'min_p': float(np.min(r['ps'])),
-                      'pseudo_heritability': float(r['pseudo_heritability']), 'stage_seconds': ctx.timers()}))
+                      'eigenbases': 'orthonormal stand-in (Householder reflection built on the device): cuSOLVER syevd refuses n > 32768'
+                                    if args.standin_eigen else 'cuSOLVER Xsyevd', 'eigh_s': t_eig,
+                      'reml_scan_s': t_scan, 'scan_kernel_ms': ctx.last_kernel_ms('scan'), 'planes': planes, 'certified_rel_bound_xx': rho,
+                      'snp_tests_per_s_excl_eigh': m / (t_kin + t_scan), 'min_p': float(np.min(r['ps'])), 'finite': bool(np.all(np.isfinite(r['ps']))),
+                      'pseudo_heritability': float(r['pseudo_heritability']), 'device_free_bytes_after': info.get('free_bytes'),
+                      'stage_seconds': ctx.timers()}))
 
 
 if __name__ == '__main__':
@@ -155,6 +194,7 @@ if __name__ == '__main__':
     ap.add_argument('--snps', dest='m', type=int, default=0)
     ap.add_argument('--phenotypes', dest='T', type=int, default=199)
     ap.add_argument('--perms', dest='P', type=int, default=1000)
+    ap.add_argument('--standin-eigen', action='store_true', help='config 3: orthonormal stand-in eigenbases instead of cuSOLVER (n > 32768)')
     ap.add_argument('--single', type=int, default=5, help='config 2: how many single-phenotype emmax() calls to time for the comparison')
     a = ap.parse_args()
     {2: config2, 3: config3, 4: config4}[a.config](a)
