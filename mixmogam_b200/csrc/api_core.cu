@@ -465,8 +465,16 @@ int mmg_snps_upload_rows(mmg_ctx* ctx, const int8_t* const* rows, int64_t m, int
     MMG_TRY(mmg_snps_reserve(ctx, m, n));
     ctx->snps_absmax = -1;
     StageTimer tm(ctx, "h2d");
+    if (m * n <= (4ll << 20)) {
+        // a few rows (the single-SNP calls of the stepwise callers, linear_models.py:2720,2825): straight from the caller's rows --
+        // the driver stages small pageable copies itself; two page-locked buffers cost ~20 ms to allocate, far more than the copy
+        for (int64_t r = 0; r < m; ++r)
+            MMG_CUDA(ctx, cudaMemcpyAsync(ctx->snps + r * ctx->pitch, rows[r], (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return MMG_OK;
+    }
     // gather rows into two pinned staging buffers and copy them asynchronously
-    const int64_t rows_per = std::max<int64_t>(1, (32ll << 20) / n);
+    const int64_t rows_per = std::max<int64_t>(1, std::min<int64_t>(m, (32ll << 20) / n));
     int8_t* stage[2] = {nullptr, nullptr};
     cudaEvent_t done[2];
     for (int b = 0; b < 2; ++b) {

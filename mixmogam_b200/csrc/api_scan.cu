@@ -137,15 +137,34 @@ static int pad_matrix(mmg_ctx* ctx, const MmgMat* R, DevBuf& out, int64_t* rows_
     return MMG_OK;
 }
 
-static int launch_scan_dmma(mmg_ctx* ctx, bool perm, const ScanDmmaParams& prm) {
+static int launch_scan_dmma(mmg_ctx* ctx, bool perm, const ScanDmmaParams& prm_in) {
+    ScanDmmaParams prm = prm_in;
     const int64_t blocks = (prm.row_count + SD_BM - 1) / SD_BM;
-    const int grid = (int)std::min<int64_t>(blocks, ctx->sm_count);
+    // Short scans (the single-SNP calls of the stepwise callers, top-hit lists): with one CTA per 128-row block a 1-SNP scan at
+    // n = 10k runs 2.6e10 flops on ONE SM (127 ms).  The column tiles of R are split over the idle SMs instead and the partial
+    // moments are added in a fixed order by a finishing kernel (1-2 ms).
+    DevBuf part;
+    prm.nsplit = 0;
+    prm.part = nullptr;
+    const int NT = prm.n_out_pad / SD_BN;
+    if (!perm && prm.mu == nullptr && blocks * 2 <= ctx->sm_count && NT > 1) {
+        prm.nsplit = (int)std::min<int64_t>(NT, ctx->sm_count / blocks);
+        MMG_CUDA(ctx, part.alloc(ctx->stream, (size_t)(2 * prm.nsplit) * prm.row_count * sizeof(double)));
+        prm.part = part.as<double>();
+    }
+    const int64_t items = blocks * std::max(1, prm.nsplit);
+    const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
     cudaEventRecord(ctx->kev0, ctx->stream);
     if (perm)
         scan_dmma_kernel<true><<<grid, SD_THREADS, SD_SMEM_BYTES, ctx->stream>>>(prm);
     else
         scan_dmma_kernel<false><<<grid, SD_THREADS, SD_SMEM_BYTES, ctx->stream>>>(prm);
     MMG_TRY(launch_check(ctx, "scan_dmma_kernel"));
+    if (prm.nsplit > 1) {
+        scan_split_finish_kernel<<<(unsigned)((prm.row_count + 127) / 128), 128, 0, ctx->stream>>>(prm.part, prm.nsplit, prm.row_count, prm.h0_rss, prm.n_p,
+                                                                                                 prm.lbeta, prm.xx, prm.xy, prm.rss, prm.f, prm.p, prm.var_perc);
+        MMG_TRY(launch_check(ctx, "scan_split_finish_kernel"));
+    }
     cudaEventRecord(ctx->kev1, ctx->stream);
     return MMG_OK;
 }

@@ -63,6 +63,10 @@ struct ScanDmmaParams {
     // squared rotated genotypes with the per-phenotype weights)
     double* cstore;          // [row_count x ldc]
     int64_t ldc;
+    // short scans (fewer 128-row blocks than SMs): the column tiles of R are split over nsplit CTAs per row block, each writes its
+    // partial (x~.x~, x~.y~) to part[(which * nsplit + split) * row_count + row]; scan_split_finish_kernel adds them in a fixed order
+    int nsplit;              // 0 / 1: off
+    double* part;
 };
 constexpr int SD_MODE_SCAN = 0, SD_MODE_SQUARE_STORE = 1;
 
@@ -85,14 +89,20 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
     const int KT = prm.k_pad / SD_BK;
     const int NT = prm.n_out_pad / SD_BN;
     const int64_t num_blocks = (prm.row_count + SD_BM - 1) / SD_BM;
+    const int nsplit = (!PERM && MODE == SD_MODE_SCAN && prm.nsplit > 1) ? prm.nsplit : 1;
+    const int nt_per = (NT + nsplit - 1) / nsplit;
 
-    for (int64_t mb = blockIdx.x; mb < num_blocks; mb += gridDim.x) {
+    for (int64_t item = blockIdx.x; item < num_blocks * nsplit; item += gridDim.x) {
+        const int64_t mb = item / nsplit;
+        const int sp = (int)(item - mb * nsplit);
+        const int nt_begin = sp * nt_per, nt_count = max(0, min(NT, nt_begin + nt_per) - nt_begin);
         const int64_t row0 = mb * SD_BM;               // relative to row_begin
-        const int total_it = NT * KT;
+        const int total_it = nt_count * KT;
 
         auto load_stage = [&](int it) {
             const int stage = it % SD_STAGES;
-            const int nt = it / KT, kt = it - nt * KT;
+            const int ntl = it / KT, kt = it - ntl * KT;
+            const int nt = nt_begin + ntl;
             uint8_t* sa = sd_smem + stage * SD_STAGE_BYTES;
             double* sb = reinterpret_cast<double*>(sa + SD_A_STAGE);
             if constexpr (!REAL) {   // A: 128 rows x 32 B -> one 16 B chunk per thread
@@ -184,8 +194,9 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
                 }
             }
 
-            const int nt = it / KT;
-            if (it - nt * KT == KT - 1) {
+            const int ntl = it / KT;
+            const int nt = nt_begin + ntl;
+            if (it - ntl * KT == KT - 1) {
                 // ---- epilogue of this N tile: fold the 128 x 128 block of C into the running row sums ----
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
@@ -265,6 +276,10 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
                 const double sxx = red[0 * SD_BM + tid] + red[1 * SD_BM + tid] + red[2 * SD_BM + tid] + red[3 * SD_BM + tid];
                 const double sxy = red[4 * SD_BM + tid] + red[5 * SD_BM + tid] + red[6 * SD_BM + tid] + red[7 * SD_BM + tid];
                 const int64_t o = row0 + tid;
+                if (nsplit > 1) {
+                    prm.part[(int64_t)sp * prm.row_count + o] = sxx;
+                    prm.part[(int64_t)(nsplit + sp) * prm.row_count + o] = sxy;
+                } else {
                 if (prm.xx) prm.xx[o] = sxx;
                 if (prm.xy) prm.xy[o] = sxy;
                 if (prm.p || prm.f || prm.rss || prm.var_perc) {
@@ -284,6 +299,7 @@ static __global__ void __launch_bounds__(SD_THREADS, 1) scan_dmma_kernel(const S
                     if (prm.f) prm.f[o] = f;
                     if (prm.var_perc) prm.var_perc[o] = vp;
                     if (prm.p) prm.p[o] = pv;
+                }
                 }
             }
         }
@@ -346,6 +362,35 @@ static __global__ void scan_stats_kernel(const double* __restrict__ xx, const do
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= count) return;
     const double sxx = xx[o], sxy = xy[o];
+    double rss = h0_rss, f = 0.0, vp = 0.0, pv = 1.0;
+    if (sxx > 0.0) {
+        const double r2 = (sxy * sxy) / (sxx * h0_rss);
+        const double rs = h0_rss - (sxy * sxy) / sxx;
+        if (rs != 0.0) {
+            rss = rs;
+            vp = r2;
+            f = n_p * r2 / (1.0 - r2);
+            pv = f_sf(f, 1.0, n_p, lbeta);
+        }
+    }
+    if (rss_o) rss_o[o] = rss;
+    if (f_o) f_o[o] = f;
+    if (vp_o) vp_o[o] = vp;
+    if (p_o) p_o[o] = pv;
+}
+
+// short scans: the partial moments of the column splits (ScanDmmaParams::part) added in split order, then the same epilogue
+static __global__ void scan_split_finish_kernel(const double* __restrict__ part, int nsplit, int64_t count, double h0_rss, double n_p,
+                                                double lbeta, double* xx_o, double* xy_o, double* rss_o, double* f_o, double* p_o, double* vp_o) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= count) return;
+    double sxx = 0.0, sxy = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) {
+        sxx += part[(int64_t)sp * count + o];
+        sxy += part[(int64_t)(nsplit + sp) * count + o];
+    }
+    if (xx_o) xx_o[o] = sxx;
+    if (xy_o) xy_o[o] = sxy;
     double rss = h0_rss, f = 0.0, vp = 0.0, pv = 1.0;
     if (sxx > 0.0) {
         const double r2 = (sxy * sxy) / (sxx * h0_rss);

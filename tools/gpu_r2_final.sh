@@ -3,7 +3,7 @@
 # (e2e + variants + CPU arm), the reference arm, launch list of one step, ncu --set full of the Gram and the scan.
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { echo build failed; tail -20 gpurun_out/build.log; exit 1; }
-MMG_TEST_FULL_M=1 timeout 2400 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "t_all rc=$?"; tail -6 gpurun_out/t_all.log
+timeout 2400 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "t_all rc=$?"; tail -6 gpurun_out/t_all.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_n1.err
 python - <<'PY'
@@ -19,6 +19,6 @@ PY
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; tail -c 600 gpurun_out/bench_ref.json
 export MMG_PROFILE_RANGE=1 MMG_SCAN_COOP=0
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_1m.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/launches_bench.log 2>&1; echo "launch list rc=$?"
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"tc_gemm_i8_kernel" -s 4 -c 1 -f -o gpurun_out/prof_gram_1m python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/prof_gram_1m.log 2>&1; echo "ncu gram rc=$?"
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"gram_pair_kernel" -s 4 -c 1 -f -o gpurun_out/prof_gram_1m python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/prof_gram_1m.log 2>&1; echo "ncu gram rc=$?"
 ncu -i gpurun_out/prof_gram_1m.ncu-rep --page raw --csv > gpurun_out/prof_gram_1m_raw.csv 2>/dev/null
 rm -f gpurun_out/prof_gram_1m.ncu-rep
