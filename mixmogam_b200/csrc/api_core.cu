@@ -374,6 +374,37 @@ int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat h, double* w_host, double* seconds) {
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t n = A->rows;
     StageTimer tm(ctx, "syevd");
+    // MMG_SYEVD_JACOBI_MAX = k: matrices up to k x k take cuSOLVER's Jacobi solver (entirely on the device, tolerance 1e-15, eigenvalues
+    // sorted ascending like syevd) instead of Xsyevd, whose tridiagonal stage runs on the host for small n.  Off by default: at
+    // n = 198 (configs[0]) it is the slower of the two at steady state (6.3 against 2.7 ms per decomposition); it exists for hosts whose
+    // cores are busy (one run next to numpy's BLAS threads showed 0.1 - 0.8 s in Xsyevd for the same matrix).
+    if (n <= env_int("MMG_SYEVD_JACOBI_MAX", 0)) {
+        syevjInfo_t jp = nullptr;
+        MMG_CUSOLVER(ctx, cusolverDnCreateSyevjInfo(&jp));
+        cusolverDnXsyevjSetTolerance(jp, 1e-15);
+        cusolverDnXsyevjSetMaxSweeps(jp, 200);
+        cusolverDnXsyevjSetSortEig(jp, 1);
+        DevBuf wd, work, infod;
+        int lwork = 0, rc = MMG_OK, info = 0;
+        do {
+            if (wd.alloc(ctx->stream, n * sizeof(double)) != cudaSuccess || infod.alloc(ctx->stream, sizeof(int)) != cudaSuccess) { rc = fail(ctx, MMG_EOOM, "syevj: allocation failed"); break; }
+            cusolverStatus_t st = cusolverDnDsyevj_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, A->d, (int)n, wd.as<double>(), &lwork, jp);
+            if (st != CUSOLVER_STATUS_SUCCESS) { rc = fail(ctx, MMG_ECUSOLVER, "Dsyevj_bufferSize status %d", (int)st); break; }
+            if (work.alloc(ctx->stream, (size_t)std::max(lwork, 1) * sizeof(double)) != cudaSuccess) { rc = fail(ctx, MMG_EOOM, "syevj: workspace"); break; }
+            st = cusolverDnDsyevj(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, A->d, (int)n, wd.as<double>(), work.as<double>(), lwork,
+                                  infod.as<int>(), jp);
+            if (st != CUSOLVER_STATUS_SUCCESS) { rc = fail(ctx, MMG_ECUSOLVER, "Dsyevj status %d", (int)st); break; }
+            if (cudaMemcpyAsync(&info, infod.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaMemcpyAsync(w_host, wd.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fail(ctx, MMG_ECUDA, "syevj: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            if (info != 0) rc = fail(ctx, MMG_ECUSOLVER, "syevj did not converge (info=%d)", info);
+        } while (0);
+        cusolverDnDestroySyevjInfo(jp);
+        tm.stop();
+        resolve_timers(ctx);
+        if (seconds) *seconds = ctx->timers["syevd"].seconds;
+        return rc;
+    }
     cusolverDnParams_t params = nullptr;
     MMG_CUSOLVER(ctx, cusolverDnCreateParams(&params));
     size_t ws_dev = 0, ws_host = 0;
@@ -418,6 +449,15 @@ int mmg_mat_syevd(mmg_ctx* ctx, mmg_mat h, double* w_host, double* seconds) {
 // ======================================================================================================
 // genotypes
 // ======================================================================================================
+}  // extern "C" (interrupted for a kernel)
+// contiguous rows of n bytes -> rows at the resident block's pitch (grid-stride over the bytes; the padding stays zero)
+static __global__ void repitch_rows_kernel(const int8_t* __restrict__ src, int64_t n, int8_t* __restrict__ dst, int64_t pitch, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n;
+        dst[r * pitch + (i - r * n)] = src[i];
+    }
+}
+extern "C" {
 int mmg_snps_free(mmg_ctx* ctx) {
     MMG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -448,7 +488,25 @@ int mmg_snps_write(mmg_ctx* ctx, int64_t row0, const int8_t* snps, int64_t rows,
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->snps_absmax = -1;
     StageTimer tm(ctx, "h2d");
-    // one strided DMA; measured at the PCIe rate (52 GB/s from page-locked memory), a staged 1-D copy + re-pitch kernel was no faster
+    if (rows && ld == ctx->n && ctx->n != ctx->pitch && ctx->n < 2048) {
+        // short rows (configs[0]: n = 198 accessions): a strided DMA moves them one 198-byte row at a time -- 0.8 GB/s, 52 ms for
+        // 214 k SNPs.  The block is contiguous on the host: 1-D copies into a device staging buffer + a re-pitch kernel instead.
+        const int64_t piece = std::max<int64_t>(1, (256ll << 20) / ctx->n);
+        DevBuf tmp;
+        MMG_CUDA(ctx, tmp.alloc(ctx->stream, (size_t)std::min(piece, rows) * ctx->n));
+        for (int64_t r0 = 0; r0 < rows; r0 += piece) {
+            const int64_t cnt = std::min(piece, rows - r0);
+            MMG_CUDA(ctx, cudaMemcpyAsync(tmp.p, snps + r0 * ld, (size_t)(cnt * ctx->n), cudaMemcpyHostToDevice, ctx->stream));
+            const int64_t total = cnt * ctx->n;
+            repitch_rows_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1 << 20), 256, 0, ctx->stream>>>(
+                tmp.as<int8_t>(), ctx->n, ctx->snps + (row0 + r0) * ctx->pitch, ctx->pitch, total);
+            MMG_TRY(launch_check(ctx, "repitch_rows_kernel"));
+        }
+        MMG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return MMG_OK;
+    }
+    // one strided DMA; measured at the PCIe rate for 10 KB rows (52 GB/s from page-locked memory), where a staged 1-D copy +
+    // re-pitch kernel was no faster
     if (rows)
         MMG_CUDA(ctx, cudaMemcpy2DAsync(ctx->snps + row0 * ctx->pitch, ctx->pitch, snps, ld, ctx->n, rows, cudaMemcpyHostToDevice,
                                         ctx->stream));

@@ -40,6 +40,23 @@ def test_syevd_and_eigen(ctx):
     np.testing.assert_allclose(eig_R['values'], g['reml_eigR_values'], rtol=1e-8, atol=1e-10)
 
 
+def test_small_eigenproblems_on_the_jacobi_solver(ctx, monkeypatch):
+    """MMG_SYEVD_JACOBI_MAX: the device-only Jacobi eigensolver for small matrices gives the same eigenvalues and an orthonormal
+    eigenbasis that reconstructs K (rows = eigenvectors, linear_models.py:596)."""
+    from mixmogam_b200 import linear_models as lm
+    g = golden('emmax_ft10_n198.npz')
+    monkeypatch.setenv('MMG_SYEVD_JACOBI_MAX', '512')
+    lmm = lm.LinearMixedModel(g['y'])
+    lmm.add_random_effect(g['K'])
+    eig_L = lmm._get_eigen_L_()
+    np.testing.assert_allclose(eig_L['values'], g['reml_eigL_values'], rtol=1e-9, atol=1e-11)
+    U = np.asarray(eig_L['vectors'])
+    np.testing.assert_allclose(U @ U.T, np.eye(len(U)), atol=1e-12)
+    np.testing.assert_allclose(U.T @ np.diag(eig_L['values']) @ U, np.asarray(lmm.random_effects[1][1]), atol=1e-10)
+    r = lm.emmax(g['snps'], g['y'], g['K'])
+    assert neglog10_rel_err(r['ps'], g['double_ps']) < 1e-6
+
+
 @pytest.mark.parametrize('name', ['emmax_ft10_n198.npz', 'emmax_diploid_n400.npz'])
 def test_get_reml(ctx, name):
     from mixmogam_b200 import linear_models as lm
