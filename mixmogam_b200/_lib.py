@@ -1035,7 +1035,10 @@ def result_empty(shape, dtype=np.float64):
     """Output buffer of a device call: page-locked (pooled) once it is large enough for the copy rate to matter --
     a pageable 8 MB per-SNP vector comes back at ~5 GB/s, a page-locked one at the PCIe rate."""
     dtype = np.dtype(dtype)
-    if int(np.prod(shape)) * dtype.itemsize >= (1 << 20):
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    # ... and not so large that page-locking it costs more than it saves: cudaHostAlloc runs at ~0.45 s / GB (3 s for the 6.4 GB of
+    # a 199-phenotype x 1M-SNP batch), a pageable copy of that size at ~0.1 s / GB
+    if (1 << 20) <= nbytes <= (1 << 30):
         return pinned_empty(shape, dtype)
     return np.empty(shape, dtype=dtype)
 

@@ -464,6 +464,7 @@ int mmg_snps_free(mmg_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->snps);
     ctx->snps = nullptr;
+    ctx->snps_capacity = 0;
     ctx->m = ctx->n = ctx->pitch = 0;
     ctx->snps_absmax = -1;
     return MMG_OK;
@@ -473,8 +474,15 @@ int mmg_snps_reserve(mmg_ctx* ctx, int64_t m, int64_t n) {
     MMG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t pitch = round_up(n, 256);   // zero padded: kernels read whole 16/32-byte groups up to the next 256
     if (!(ctx->snps && ctx->m == m && ctx->n == n)) {
-        MMG_TRY(mmg_snps_free(ctx));
-        MMG_CUDA(ctx, persistent_malloc(ctx->device, (void**)&ctx->snps, (size_t)m * pitch));
+        // a block that fits the allocation (but not one that would strand more than 3/4 of a large one) re-uses it: the chromosome
+        // loop of hdf5_data.run_emmax reserves a different m every time, and cudaFree + cudaMalloc of a GB-sized block cost ~40 ms
+        const int64_t need = m * pitch;
+        if (!(ctx->snps && need <= ctx->snps_capacity && (need * 4 >= ctx->snps_capacity || ctx->snps_capacity <= (256ll << 20)))) {
+            MMG_TRY(mmg_snps_free(ctx));
+            MMG_CUDA(ctx, persistent_malloc(ctx->device, (void**)&ctx->snps, (size_t)need));
+            ctx->snps_capacity = need;
+        }
+        ctx->snps_absmax = -1;
         ctx->m = m;
         ctx->n = n;
         ctx->pitch = pitch;

@@ -59,6 +59,7 @@ struct mmg_ctx {
 
     // resident genotypes
     int8_t* snps = nullptr;
+    int64_t snps_capacity = 0;         // bytes behind snps (a smaller block re-uses the allocation: mmg_snps_reserve)
     int64_t m = 0, n = 0, pitch = 0;
     int snps_absmax = -1;          // max |genotype| of the resident block, -1 = not measured since the last write
 

@@ -74,7 +74,13 @@ def stream_snps(ctx, parts, chunk_rows=None):
     if chunk_rows is None:
         chunk_rows = max(256, (64 << 20) // max(n, 1))
     ctx.snps_reserve(total, n)
-    bufs = [_lib.pinned_empty((chunk_rows, n), np.int8) for _ in range(2)]
+    # the two page-locked chunk buffers are kept on the context between calls (allocating them costs ~50 ms each; run_emmax_perm
+    # streams every chromosome twice)
+    ring = getattr(ctx, '_stream_ring', None)
+    if ring is None or ring[0].size < chunk_rows * n:
+        ring = [_lib.pinned_empty((chunk_rows * n,), np.int8) for _ in range(2)]
+        ctx._stream_ring = ring
+    bufs = [b[:chunk_rows * n].reshape(chunk_rows, n) for b in ring]
     free_q, full_q = queue.Queue(), queue.Queue()
     for b in bufs:
         free_q.put(b)

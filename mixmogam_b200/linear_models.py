@@ -782,9 +782,13 @@ class LinearMixedModel(LinearModel):
         Y = Y - h0_X @ h0_betas                                                # :1144
         Y = Y - h0_X * float(h0_betas[0, 0])                                   # :1147
         Ys = np.zeros((n, num_perm))
+        y_col = Y[:, 0]                                                        # 1-D view of the (n, 1) column
         for perm_i in range(num_perm):
-            np.random.shuffle(Y)                                               # :1153
-            Ys[:, perm_i] = Y[:, 0]
+            # :1153 `sp.random.shuffle(Y)`: shuffling the 1-D view draws the same random_interval sequence from the legacy global
+            # RNG and produces the same permutation as shuffling the (n, 1) array, without its row-by-row buffer swaps (5.7 ms -> 0.09 ms
+            # per permutation at n = 5000; tests/test_host_logic.py pins the equivalence)
+            np.random.shuffle(y_col)
+            Ys[:, perm_i] = y_col
         h0_rss_f = float(np.asarray(h0_rss).reshape(-1)[0])
 
         num_snps, n_lines = ctx.ensure_snps(snps)

@@ -349,3 +349,23 @@ def test_f_sf_series_branch_dense(built):
             out = _run(built, 'fsf', payload)
             ref = stats.f.sf(F, dfn, dfd)
             assert np.max(np.abs(out - ref) / ref) < 1e-11, (dfn, dfd)
+
+
+def test_permutation_shuffle_of_the_column_view_matches_the_reference_call():
+    """_emmax_permutations_ shuffles the 1-D view of the (n, 1) phenotype column: same draws from the legacy global RNG and the same
+    cumulative permutations as the reference's `sp.random.shuffle(Y)` on the 2-D array (linear_models.py:1151-1154)."""
+    n = 777
+    a = np.random.RandomState(7).standard_normal((n, 1))
+    b = a.copy()
+    np.random.seed(20240601)
+    ref = []
+    for _ in range(4):
+        np.random.shuffle(a)
+        ref.append(a[:, 0].copy())
+    tail_ref = np.random.random()
+    np.random.seed(20240601)
+    col = b[:, 0]
+    for k in range(4):
+        np.random.shuffle(col)
+        assert np.array_equal(col, ref[k])
+    assert np.random.random() == tail_ref                   # the RNG stream is in the same state afterwards
