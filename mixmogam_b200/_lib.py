@@ -1036,11 +1036,25 @@ def result_empty(shape, dtype=np.float64):
     a pageable 8 MB per-SNP vector comes back at ~5 GB/s, a page-locked one at the PCIe rate."""
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
-    # ... and not so large that page-locking it costs more than it saves: cudaHostAlloc runs at ~0.45 s / GB (3 s for the 6.4 GB of
-    # a 199-phenotype x 1M-SNP batch), a pageable copy of that size at ~0.1 s / GB
-    if (1 << 20) <= nbytes <= (1 << 30):
+    if nbytes < (1 << 20):
+        return np.empty(shape, dtype=dtype)
+    if nbytes <= (64 << 20):
         return pinned_empty(shape, dtype)
+    # Large buffers: cudaHostAlloc runs at ~0.4 s / GB -- 0.55 of the 0.62 s of a one-off 199-phenotype x 214k-SNP batch, 3 s for
+    # the 6.4 GB of a 1M-SNP one -- which only pays off when the block comes back from the pool.  The FIRST request of a size is
+    # served from pageable memory (~0.1 s / GB to copy into); a second request of the same size (a loop) gets the page-locked block,
+    # and every later one re-uses it.  Nothing above 1 GB is page-locked.
+    if nbytes <= (1 << 30):
+        with _PinnedBlock._pool_lock:
+            pooled = bool(_PinnedBlock._pool.get(max(1, nbytes)))
+            seen = _large_seen.get(nbytes, 0)
+            _large_seen[nbytes] = seen + 1
+        if pooled or seen >= 1:
+            return pinned_empty(shape, dtype)
     return np.empty(shape, dtype=dtype)
+
+
+_large_seen = {}
 
 
 def pinned_free(arr):
