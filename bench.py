@@ -278,7 +278,9 @@ def kinship_roofline(ctx, n, m_loc, gram_s, rates):
     tiles = sum(2 * jn + 2 for jn in range((n + 255) // 256))
     exec_ops = 2.0 * tiles * 128 * 256 * 2.0 * m_loc
     peak = rates.get('mxf4_sustained_tops' if fp4 else 'int8_sustained_tops')
-    return {'gram_ms': gram_s * 1e3, 'kernel': 'tc_gemm_i8_kernel<GramEpiF4, 2, mxf4>' if fp4 else 'tc_gemm_i8_kernel<GramEpi, 2>',
+    pair = ctx.last_kernel_ms('gram_is_pair') != 0.0
+    return {'gram_ms': gram_s * 1e3,
+            'kernel': ('gram_pair_kernel (tcgen05.mma.cta_group::2)' if pair else 'tc_gemm_i8_kernel<GramEpiF4, 2, mxf4>') if fp4 else 'tc_gemm_i8_kernel<GramEpi, 2>',
             'operands': 'e2m1 (kind::mxf4.block_scale, unit scales, FP32 accumulators holding exact integers)' if fp4 else 'int8 (kind::i8)',
             'tops_algorithmic': 2.0 * n * n * 2 * m_loc / gram_s / 1e12, 'tops_executed': exec_ops / gram_s / 1e12,
             'peak_tops': peak, 'frac': exec_ops / gram_s / 1e12 / peak if peak else None,

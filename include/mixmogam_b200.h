@@ -67,7 +67,8 @@ int mmg_timer_get(mmg_ctx* ctx, const char* name, double* seconds, int64_t* call
 int mmg_timer_reset(mmg_ctx* ctx);
 /* duration (ms) of the most recent launch of the dominant kernels, measured with CUDA
  * events on the launching stream: which = "gram" | "scan" | "perm" | "ibd".  Two more keys report what the last call ran
- * rather than a time: "gram_is_fp4" (1: the Gram multiplied e2m1 operands with tcgen05 kind::mxf4, 0: int8 / SIMT) and
+ * rather than a time: "gram_is_fp4" (1: the Gram multiplied e2m1 operands with tcgen05 kind::mxf4, 0: int8 / SIMT), "gram_is_pair"
+ * (1: as a CTA-pair MMA, cta_group::2) and
  * "scan_impl" (the MMG_IMPL_* value MMG_IMPL_AUTO resolved to in the last mmg_emmax_scan_f64 / _betas_f64 call). */
 int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms);
 

@@ -153,6 +153,7 @@ int mmg_last_kernel_ms(mmg_ctx* ctx, const char* which, double* ms) {
     MMG_CHECK(ctx, ctx && which && ms, "bad argument");
     if (!strcmp(which, "gram")) *ms = ctx->last_gram_ms;
     else if (!strcmp(which, "gram_is_fp4")) *ms = (double)ctx->last_gram_fp4;
+    else if (!strcmp(which, "gram_is_pair")) *ms = (double)ctx->last_gram_pair;
     else if (!strcmp(which, "scan_impl")) *ms = (double)ctx->last_scan_impl;
     else if (!strcmp(which, "scan")) *ms = ctx->last_scan_ms;
     else if (!strcmp(which, "perm")) *ms = ctx->last_perm_ms;

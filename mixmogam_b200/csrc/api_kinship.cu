@@ -258,6 +258,7 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
     // MMG_GRAM_PAIR (default 1): the e2m1 Gram as a CTA-pair MMA (tcgen05.mma.cta_group::2, gram_pair.cuh) instead of two
     // single-CTA MMAs that multicast the shared operand
     const bool pair = fp4 && gram_cs == 2 && env_int("MMG_GRAM_PAIR", 1) != 0;
+    ctx->last_gram_pair = pair ? 1 : 0;
     std::vector<TcTile> tiles, table;
     int gram_clusters = 1;
     if (impl == MMG_IMPL_TCGEN05) {
@@ -501,15 +502,13 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
             cudaEventRecord(ev4[2], ctx->stream);
             const int ngroups = (int)table.size() * gram_cs;
             const int pf = env_int("MMG_GRAM_PREFETCH", 0);         // L2 prefetch distance of the operand streams in K blocks; off: measured 34 -> 52 ms at 8
-            if (pair) {
+            if (pair) {                                             // tmB's box is this CTA's half of the B tile (128 rows: gram_cs == 2)
                 GramEpiF4::Params ep4{ctx->G, g_pad, accumulate};
-                CUtensorMap tmBh;                                   // this CTA's half of the B tile: a box of 128 rows
-                MMG_TRY(make_tmap_u8(ctx, &tmBh, slot, kbytes, n, p_pitch, TC_BN / 2));
                 cudaLaunchConfig_t cfg;
                 cudaLaunchAttribute attr[1];
                 const int nt = (int)table.size();
                 gram_pair_config(ctx, cfg, attr, std::max(1, std::min(nt, gram_clusters)));
-                cudaError_t e = cudaLaunchKernelEx(&cfg, gram_pair_kernel, tmA, tmBh, (const TcTile*)ctx->tiles_d, nt, (uint64_t)L2_EVICT_NORMAL, ep4);
+                cudaError_t e = cudaLaunchKernelEx(&cfg, gram_pair_kernel, tmA, tmB, (const TcTile*)ctx->tiles_d, nt, (uint64_t)L2_EVICT_NORMAL, ep4);
                 ctx->launches += 1;
                 if (e != cudaSuccess) return fail(ctx, MMG_ECUDA, "launch of gram_pair_kernel (grid %u) failed: %s", cfg.gridDim.x, cudaGetErrorString(e));
             } else if (fp4) {

@@ -53,6 +53,7 @@ struct mmg_ctx {
     int64_t scan_hint_n = 0;
     double last_gram_ms = 0.0, last_scan_ms = 0.0, last_perm_ms = 0.0, last_ibd_ms = 0.0;
     int last_scan_impl = 0;            // MMG_IMPL_* the last mmg_emmax_scan_f64 / _betas_f64 call ran (what AUTO resolved to)
+    int last_gram_pair = 0;            // ... as a CTA-pair MMA (gram_pair_kernel) rather than the multicast form of the GEMM core
     int last_gram_fp4 = 0;             // the last tcgen05 Gram multiplied e2m1 operands (kind::mxf4) rather than int8
     int last_scan_slices = 0;          // digit planes used by the most recent int8 scan
     double last_scan_rho = 0.0;        // its certified relative truncation bound on x~.x~ (max over SNPs)

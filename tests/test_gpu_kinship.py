@@ -25,14 +25,18 @@ def _rand_snps(m, n, coding, seed):
 
 
 def _gram_kind(monkeypatch, impl):
-    """'tcgen05' is the e2m1 / kind::mxf4 Gram (default), 'tcgen05_i8' the int8 one (MMG_GRAM_KIND=i8)."""
+    """'tcgen05' is the e2m1 / kind::mxf4 Gram as a CTA-pair MMA (default), 'tcgen05_mcast' its multicast form (MMG_GRAM_PAIR=0),
+    'tcgen05_i8' the int8 one (MMG_GRAM_KIND=i8)."""
     if impl == 'tcgen05_i8':
         monkeypatch.setenv('MMG_GRAM_KIND', 'i8')
+        return 'tcgen05'
+    if impl == 'tcgen05_mcast':
+        monkeypatch.setenv('MMG_GRAM_PAIR', '0')
         return 'tcgen05'
     return impl
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_i8'])
+@pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_mcast', 'tcgen05_i8'])
 @pytest.mark.parametrize('coding', [0, 1])
 @pytest.mark.parametrize('m,n', [(700, 37), (3000, 198), (5001, 300), (1, 5), (129, 257), (2048, 1000)])
 def test_gram_bit_exact(ctx, monkeypatch, impl, coding, m, n):
@@ -42,7 +46,8 @@ def test_gram_bit_exact(ctx, monkeypatch, impl, coding, m, n):
     ctx.invalidate_snps()
     ctx.ensure_snps(snps)
     ctx.kinship_gram(coding, impl=impl)
-    assert ctx.last_kernel_ms('gram_is_fp4') == (1.0 if kind == 'tcgen05' else 0.0)
+    assert ctx.last_kernel_ms('gram_is_fp4') == (1.0 if kind in ('tcgen05', 'tcgen05_mcast') else 0.0)
+    assert ctx.last_kernel_ms('gram_is_pair') == (1.0 if kind == 'tcgen05' else 0.0)
     G = ctx.kinship_gram_download()
     assert np.array_equal(G.astype(np.int64), _gram_ref(snps, coding))
 
