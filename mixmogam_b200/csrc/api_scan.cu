@@ -1110,10 +1110,24 @@ int mmg_emmax_scan_rows_f64(mmg_ctx* ctx, mmg_mat Rh, const double* V, int nv, d
         prm.n_p = n_p;
         prm.lbeta = lbeta;
         prm.xx = d_xx; prm.xy = d_xy; prm.rss = d_rss; prm.f = d_f; prm.p = d_p; prm.var_perc = d_vp;
-        const int grid = (int)std::min<int64_t>((rows + SD_BM - 1) / SD_BM, ctx->sm_count);
+        // short scans: column tiles of R split over the idle SMs, as in launch_scan_dmma
+        const int64_t blocks = (rows + SD_BM - 1) / SD_BM;
+        const int NT = (int)(rows_pad / SD_BN);
+        DevBuf part;
+        if (blocks * 2 <= ctx->sm_count && NT > 1) {
+            prm.nsplit = (int)std::min<int64_t>(NT, ctx->sm_count / blocks);
+            MMG_CUDA(ctx, part.alloc(ctx->stream, (size_t)(2 * prm.nsplit) * rows * sizeof(double)));
+            prm.part = part.as<double>();
+        }
+        const int grid = (int)std::min<int64_t>(blocks * std::max(1, prm.nsplit), ctx->sm_count);
         cudaEventRecord(ctx->kev0, ctx->stream);
         scan_dmma_kernel<false, double><<<grid, SD_THREADS, sd_smem_bytes<double>(), ctx->stream>>>(prm);
         MMG_TRY(launch_check(ctx, "scan_dmma_kernel<double>"));
+        if (prm.nsplit > 1) {
+            scan_split_finish_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(prm.part, prm.nsplit, rows, h0_rss, n_p, lbeta, d_xx, d_xy, d_rss,
+                                                                                            d_f, d_p, d_vp);
+            MMG_TRY(launch_check(ctx, "scan_split_finish_kernel"));
+        }
         cudaEventRecord(ctx->kev1, ctx->stream);
         if (dots)
             for (int v = 0; v < nv; ++v) {
