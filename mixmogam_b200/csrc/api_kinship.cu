@@ -1,5 +1,6 @@
 // libmixmogam_b200: stage 1 of the C ABI -- the kinship Gram (tcgen05 int8 / SIMT), its streamed host source, the FP64
 // finalisation, and the IBD kinship (int8 digit planes or cuBLAS dsyrk).
+#include <algorithm>
 #include "common.cuh"
 #include "ibd_tc.cuh"
 #include "gram_pair.cuh"
@@ -265,6 +266,17 @@ static int gram_run(mmg_ctx* ctx, int coding, int impl, int64_t snp_begin, int64
         const int tiles_n = (n + TC_BN - 1) / TC_BN;
         for (int jn = 0; jn < tiles_n; ++jn)
             for (int im = 0; im <= 2 * jn + 1; im += gram_cs) tiles.push_back(TcTile{im * TC_BM, jn * TC_BN, 0, 0, 0, 0, 0, 0});
+        // MMG_GRAM_BLOCKED=1: walk the triangle in blocks of 9 column tiles x 8 row-tile pairs (about one wave of the persistent grid)
+        // instead of column by column: a wave then touches 4352 operand rows instead of nearly all of them, and the operand is
+        // read from HBM ~5 instead of ~9 times per chunk.  The integer result does not depend on the order.
+        if (gram_cs == 2 && env_int("MMG_GRAM_BLOCKED", 0) != 0)
+            std::stable_sort(tiles.begin(), tiles.end(), [](const TcTile& a, const TcTile& b) {
+                const int aj = a.n0 / TC_BN, bj = b.n0 / TC_BN, ai = a.m0 / (2 * TC_BM), bi = b.m0 / (2 * TC_BM);
+                if (aj / 9 != bj / 9) return aj / 9 < bj / 9;
+                if (ai / 8 != bi / 8) return ai / 8 < bi / 8;
+                if (aj != bj) return aj < bj;
+                return ai < bi;
+            });
         if (pair) gram_clusters = gram_pair_max_clusters(ctx);
         else if (fp4) gram_clusters = gram_cs == 2 ? tc_gemm_max_clusters<GramEpiF4, 2, TC_KIND_MXF4>(ctx) : tc_gemm_max_clusters<GramEpiF4, 1, TC_KIND_MXF4>(ctx);
         else gram_clusters = gram_cs == 2 ? tc_gemm_max_clusters<GramEpi, 2>(ctx) : tc_gemm_max_clusters<GramEpi, 1>(ctx);
