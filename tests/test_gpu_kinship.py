@@ -9,12 +9,13 @@ pytestmark = pytest.mark.gpu
 
 
 def _gram_ref(snps, coding):
-    x = snps.astype(np.int64)
+    """Integer Gram of the coded planes through the FP64 BLAS: every sum is an integer far below 2^53, so the result is exact."""
+    x = snps.astype(np.float64)
     if coding == 0:
-        s = 2 * x - 1
-        return s.T @ s
-    t = np.concatenate([(x >= 1), (x >= 2)], axis=0).astype(np.int64)
-    return t.T @ t
+        s = 2.0 * x - 1.0
+        return np.rint(s.T @ s).astype(np.int64)
+    t = np.concatenate([(x >= 1), (x >= 2)], axis=0).astype(np.float64)
+    return np.rint(t.T @ t).astype(np.int64)
 
 
 def _rand_snps(m, n, coding, seed):
@@ -38,7 +39,7 @@ def _gram_kind(monkeypatch, impl):
 
 @pytest.mark.parametrize('impl', ['simt', 'tcgen05', 'tcgen05_mcast', 'tcgen05_i8'])
 @pytest.mark.parametrize('coding', [0, 1])
-@pytest.mark.parametrize('m,n', [(700, 37), (3000, 198), (5001, 300), (1, 5), (129, 257), (2048, 1000)])
+@pytest.mark.parametrize('m,n', [(700, 37), (3000, 198), (5001, 300), (1, 5), (129, 257), (2048, 1000), (65537, 260), (300, 512), (4097, 769)])
 def test_gram_bit_exact(ctx, monkeypatch, impl, coding, m, n):
     kind = impl
     impl = _gram_kind(monkeypatch, impl)
