@@ -53,7 +53,7 @@ MMG_HD double betacf(double a, double b, double x) {
 
 // 2F1(a + b, 1; b + 1; z) = sum_k t_k,  t_0 = 1,  t_{k+1} = t_k (a + b + k) z / (b + 1 + k)  -- the same quantity betacf(b, a, z)
 // evaluates (I_z(b, a) = z^b (1 - z)^a / (b B(a, b)) times it), as its power series.  All terms are positive (no cancellation).
-// For q = (a + b) z <= 4 and z <= 0.01 the terms fall below 1e-17 of the sum within K = 20 + 3.5 q of them (t_{k+1} / t_k <=
+// For q = (a + b) z <= 5 and z <= 0.01 the terms fall below 1e-17 of the sum within K = 20 + 3.5 q of them (t_{k+1} / t_k <=
 // q / (k + 3/2) + z); the sum is
 // evaluated as ONE fraction A / B by the nested recurrence  R_k = 1 + (u_k / v_k) R_{k+1} = (v_k B_{k+1} + u_k A_{k+1}) / (v_k B_{k+1}),
 // u_k = (a + b + k) z, v_k = b + 1 + k: two FMAs and a multiplication per term and a single division at the end, where the
@@ -82,14 +82,16 @@ MMG_HD double f_sf(double f, double dfn, double dfd, double lbeta) {
     const double l1x = -log1p(1.0 / t);   // ln (1-x)
     const double x = 1.0 / (1.0 + t);
     const double lbt = a * lx + b * l1x - lbeta;
-    if (x < (a + 1.0) / (a + b + 2.0)) {
-        return exp(lbt) * betacf(a, b, x) / a;
-    } else {
-        const double omx = t / (1.0 + t);
-        const double q = (a + b) * omx;
-        const double h = (q <= 4.0 && omx <= 0.01) ? beta_series_small(a, b, omx, q) : betacf(b, a, omx);
-        return 1.0 - exp(lbt) * h / b;
-    }
+    const double omx = t / (1.0 + t);
+    const double q = (a + b) * omx;
+    // The series of the complement first, wherever it applies -- also beyond the usual switch point x = (a+1)/(a+b+2), which at
+    // dfd ~ 10^4 sends every F > 3 (8 % of the tests, i.e. a lane of nearly every warp) into ~100 iterations of the continued
+    // fraction at four divisions each: ~20 k instructions for the whole warp against ~600.  q <= 5 is F <= 10 at dfn = 1 (0.16 % of
+    // the tests beyond it): the complement is then still >= 1.6e-3, so 1 - (.) costs under three of the subtrahend's ~14 good
+    // digits (measured <= 7e-12 relative against scipy up to dfd = 5e4; the tests hold 1e-11 there and 1e-10 in the tails).
+    if (q <= 5.0 && omx <= 0.01) return 1.0 - exp(lbt) * beta_series_small(a, b, omx, q) / b;
+    if (x < (a + 1.0) / (a + b + 2.0)) return exp(lbt) * betacf(a, b, x) / a;
+    return 1.0 - exp(lbt) * betacf(b, a, omx) / b;
 }
 
 }  // namespace mmg
