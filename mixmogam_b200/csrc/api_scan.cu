@@ -441,13 +441,25 @@ static int scan_tc_launch(mmg_ctx* ctx, int T, int S, int S_alloc, const void* B
             sh.dbg = dbg.as<long long>();
         }
         const int panel = env_int("MMG_SCAN_PANEL", 8);
-        if (pair128) MMG_TRY(launch_scan_quad_pair128(ctx, panel, tmA, tmB, sh, ep));
-        else if (n128) MMG_TRY(launch_scan_quad_n128(ctx, panel, tmA, tmB, sh, ep));
-        else if (pair) MMG_TRY(launch_scan_quad_pair(ctx, panel, tmA, tmB, sh, ep));
-        else if (cs == 8) MMG_TRY(launch_scan_quad_cs<8>(ctx, panel, tmA, tmB, sh, ep));
-        else if (cs == 4) MMG_TRY(launch_scan_quad_cs<4>(ctx, panel, tmA, tmB, sh, ep));
-        else if (cs == 2) MMG_TRY(launch_scan_quad_cs<2>(ctx, panel, tmA, tmB, sh, ep));
-        else MMG_TRY(launch_scan_quad_cs<1>(ctx, panel, tmA, tmB, sh, ep));
+        // MMG_SCAN_DEFER_STATS (default 1): the epilogue stores x~.x~ only and quad_finish_kernel derives RSS / F / p and the certification
+        // maximum afterwards -- nothing but accumulator draining is left between two SNP groups of a CTA
+        const bool defer = env_int("MMG_SCAN_DEFER_STATS", 1) != 0 && ep.xx != nullptr && ep.pre_xy != nullptr;
+        QuadEpi::Params epk = ep;
+        epk.defer = defer ? 1 : 0;
+        if (pair128) MMG_TRY(launch_scan_quad_pair128(ctx, panel, tmA, tmB, sh, epk));
+        else if (n128) MMG_TRY(launch_scan_quad_n128(ctx, panel, tmA, tmB, sh, epk));
+        else if (pair) MMG_TRY(launch_scan_quad_pair(ctx, panel, tmA, tmB, sh, epk));
+        else if (cs == 8) MMG_TRY(launch_scan_quad_cs<8>(ctx, panel, tmA, tmB, sh, epk));
+        else if (cs == 4) MMG_TRY(launch_scan_quad_cs<4>(ctx, panel, tmA, tmB, sh, epk));
+        else if (cs == 2) MMG_TRY(launch_scan_quad_cs<2>(ctx, panel, tmA, tmB, sh, epk));
+        else MMG_TRY(launch_scan_quad_cs<1>(ctx, panel, tmA, tmB, sh, epk));
+        if (defer) {
+            QuadEpi::Params epf = ep;
+            epf.defer = 0;
+            const int64_t total = (int64_t)T * snp_count;
+            quad_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(epf, T);
+            MMG_TRY(launch_check(ctx, "quad_finish_kernel"));
+        }
         if (dbg_path) {
             std::vector<long long> h((size_t)dbg_ctas * 16);
             MMG_CUDA(ctx, cudaMemcpyAsync(h.data(), dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));

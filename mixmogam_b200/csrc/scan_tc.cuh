@@ -55,6 +55,7 @@ struct QuadEpi {
         double n_p, lbeta;
         int64_t out_stride;          // outputs are [T][out_stride]
         double *xx, *xy, *rss, *f, *p, *var_perc;
+        int defer;                   // 1: store() writes x~.x~ only; quad_finish_kernel derives everything else afterwards
     };
     double q, xy, qd, xl1;
     const int8_t* xrow;
@@ -115,9 +116,16 @@ struct QuadEpi {
     //   q  = off-diagonal part of x'Ax in units of 2^E (digit planes), qd = sum_j A_jj x_j^2 (FP64), xy = x.(R'y~),
     //   x1 = ||x||_1 (for the certified truncation bound |dq| <= (64/255) 256^-S 2^E ||x||_1^2)
     static __device__ __forceinline__ void store(const Params& p, int ph, int64_t orow, double q, double xy, double qd, double x1) {
+        const double sxx = fma(q, p.escale[ph], qd);
+        if (p.defer) {               // the statistics (divisions, log / exp, an atomic) leave the scan's epilogue: one store per SNP here
+            p.xx[(int64_t)ph * p.out_stride + orow] = sxx;
+            return;
+        }
+        finish(p, ph, orow, sxx, xy, qd, x1);
+    }
+    static __device__ __forceinline__ void finish(const Params& p, int ph, int64_t orow, double sxx, double sxy, double qd, double x1) {
         const int64_t o = (int64_t)ph * p.out_stride + orow;
         const double h0 = p.h0_rss[ph];
-        const double sxx = fma(q, p.escale[ph], qd), sxy = xy;
         // x~ numerically zero -- x is (nearly) in the span of the fixed effects, e.g. a monomorphic SNP or one collinear with a
         // cofactor: x~.x~ is then the difference of two equal numbers (qd = sum_j A_jj x_j^2 bounds its scale) and the statistic
         // carries no information.  Such a SNP keeps the null fit, like the reference's empty-residue case (`if rss:`,
@@ -146,6 +154,17 @@ struct QuadEpi {
         if (p.p) p.p[o] = pv;
     }
 };
+
+// the statistics of a deferred scan (QuadEpi::Params::defer): one thread per (phenotype, SNP), x~.x~ from the scan, the linear
+// terms from the pre-pass
+static __global__ void __launch_bounds__(256) quad_finish_kernel(const QuadEpi::Params p, int T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)T * p.row_count) return;
+    const int ph = (int)(i / p.row_count);
+    const int64_t orow = i - (int64_t)ph * p.row_count;
+    const int64_t po = (int64_t)ph * p.pre_stride + orow;
+    QuadEpi::finish(p, ph, orow, p.xx[(int64_t)ph * p.out_stride + orow], p.pre_xy[po], p.pre_qd[po], p.pre_a1[orow]);
+}
 
 // ---- permutation scan epilogue --------------------------------------------------------------------------
 // B operand rows of perm block b: row (b*8 + k)*32 + j = digit plane k of permutation 32 b + j.
