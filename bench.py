@@ -555,7 +555,7 @@ def main():
         out = {'metric': METRIC, 'value': value, 'unit': 'SNP-tests/s', 'impl': 'ours', 'n_gpus': world, 'steps': args.steps,
                'warmup': args.warmup, 'ms_per_step': 1e3 * t_res / args.steps, 'higher_is_better': True, 'scaling': 'strong',
                'vs_baseline': None,
-               'dtype': 'f64 (scan: exact int8 slices of the FP64 rotation; kinship: int8/int32)' if args.scan_impl == 'tcgen05' else 'f64',
+               'dtype': 'f64 (scan: exact int8 slices of the FP64 rotation; kinship: exact integer Gram of e2m1 / int8 planes)' if args.scan_impl == 'tcgen05' else 'f64',
                'data': 'synthetic', 'config': workload_config(n, m), 'scan_impl': args.scan_impl,
                'roofline': roof, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk.summary(),
                'eigh_seconds': {'wall': eigh_wall, 'syevd_device_this_rank': eigh_dev, 'count': 2, 'broadcast_device': eigh_bcast,
